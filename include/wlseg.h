@@ -1,0 +1,224 @@
+/*
+ * wlseg.h -- C ABI of libwlseg.so, the B200 (sm_100a) implementation of the
+ * segmentation hot path of pmeletis/IV2019-boosting-semantic-segmentation-with-weak-labels.
+ *
+ * The reference has no FFI layer: every device op it runs is a TensorFlow-1.12 op reached
+ * from its Python model / loss / estimator code.  Each entry point below therefore cites the
+ * reference call site (relative to /root/reference/code/) whose TF op(s) it replaces; the
+ * Python host (wlseg/ops.py) binds them with ctypes exactly as INTEGRATION.md shows.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless named `h_*`;
+ *     the library never allocates or frees user memory and keeps no reference to it
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing blocks
+ *   - activations are NHWC, convolution kernels are KRSC ([Cout][kh][kw][Cin])
+ *   - dtype: WLSEG_F32 or WLSEG_BF16 storage; all arithmetic accumulates in fp32
+ *   - return 0 on success, <0 invalid argument / unsupported configuration,
+ *     >0 a cudaError_t; wlseg_last_error() returns a thread-local description
+ *   - there is NO CPU fallback: unsupported configurations return an error
+ */
+#ifndef WLSEG_H_
+#define WLSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WLSEG_VERSION 100 /* 0.1.0 */
+
+typedef void* wlseg_stream_t;
+
+enum { WLSEG_F32 = 0, WLSEG_BF16 = 1 };
+enum { WLSEG_ALGO_AUTO = 0, WLSEG_ALGO_DIRECT = 1, WLSEG_ALGO_TCGEN05 = 2 };
+
+int wlseg_version(void);
+const char* wlseg_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution (replaces slim.conv2d / resnet_utils.conv2d_same:
+ *   models/resnet50_extended_feature_extractor.py:25-30,39-43,
+ *   models/resnet50_extended_model_hierarchical.py:60-64,80)
+ * y[n,p,q,k] = epi( sum_{r,s,c} x[n, p*stride - pad_top + r*dilation,
+ *                                   q*stride - pad_left + s*dilation, c] * w[k,r,s,c] )
+ * epi(v) = relu?( v*scale[k] + shift[k] + residual[n, p*res_stride, q*res_stride, k] )
+ * (scale/shift/residual optional; they carry the folded inference batch-norm,
+ *  resnet50_extended_model_hierarchical.py:298-312, and the bottleneck shortcut add).
+ * bn_sum/bn_sqsum (optional, double[K]) receive sum / sum of squares of the RAW fp32
+ * accumulators per output channel (training-mode batch-norm statistics); they are
+ * accumulated into, the caller zeroes them.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct wlseg_conv_params {
+  int32_t N, H, W, C;       /* input NHWC, C = input channels */
+  int32_t K, R, S;          /* output channels, kernel height / width */
+  int32_t P, Q;             /* output height / width */
+  int32_t stride, dilation;
+  int32_t pad_top, pad_left; /* zero padding before; padding after is implied by P, Q */
+  int32_t x_pitch;          /* elements between consecutive input pixels  (>= C) */
+  int32_t y_pitch;          /* elements between consecutive output pixels (>= K) */
+  int32_t res_pitch;        /* elements between consecutive residual pixels */
+  int32_t res_stride;       /* residual is read at (p*res_stride, q*res_stride) */
+  int32_t res_H, res_W;     /* spatial size of the residual tensor */
+  int32_t relu;
+  int32_t dtype;            /* WLSEG_F32 | WLSEG_BF16: x, w, residual (and y) storage */
+  int32_t y_dtype;          /* storage of y; WLSEG_F32 lets a bf16 layer emit fp32 (logits) */
+  int32_t algo;             /* WLSEG_ALGO_* */
+} wlseg_conv_params;
+
+/* 1 if the tcgen05 implicit-GEMM kernel covers this configuration, else 0. */
+int wlseg_conv2d_tcgen05_supported(const wlseg_conv_params* p);
+
+int wlseg_conv2d_fprop(const wlseg_conv_params* p, const void* x, const void* w, void* y,
+                       const float* scale, const float* shift, const void* residual,
+                       double* bn_sum, double* bn_sqsum, wlseg_stream_t stream);
+
+/* dx = conv_transpose(dy, w): gradient wrt the input (TF Conv2DBackpropInput, reached through
+ * create_train_op, estimator/define_estimator_hierarchical.py:120-129).  dx is fully written. */
+int wlseg_conv2d_dgrad(const wlseg_conv_params* p, const void* dy, const void* w, void* dx,
+                       wlseg_stream_t stream);
+
+/* dw[k,r,s,c] = sum_{n,p,q} dy[n,p,q,k] * x[...]  (TF Conv2DBackpropFilter); dw is fp32 KRSC,
+ * fully written (beta = 0). */
+int wlseg_conv2d_wgrad(const wlseg_conv_params* p, const void* x, const void* dy, float* dw,
+                       wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batch norm, training mode (replaces tf.contrib.layers.batch_norm / FusedBatchNorm(+Grad),
+ * models/resnet50_extended_model_hierarchical.py:298-312,325).
+ * ------------------------------------------------------------------------------------------ */
+/* per-channel sum / sum of squares of z (count x C, pitch elements per row) into double[C]
+ * (accumulated into; the caller zeroes). */
+int wlseg_bn_stats(const void* z, int64_t count, int32_t C, int32_t pitch, int32_t dtype,
+                   double* sum, double* sqsum, wlseg_stream_t stream);
+
+/* mean = sum/count, var = sqsum/count - mean^2 (biased); scale = gamma*rsqrt(var+eps),
+ * shift = beta - mean*scale; moving stats updated in place with `decay` and the unbiased
+ * variance (skipped if moving_mean is NULL); saved_mean / saved_invstd for the backward. */
+int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t count, int32_t C,
+                      const float* gamma, const float* beta, float eps, float decay,
+                      float* moving_mean, float* moving_var, float* scale, float* shift,
+                      float* saved_mean, float* saved_invstd, wlseg_stream_t stream);
+
+/* y = relu?( z*scale[c] + shift[c] + residual ), elementwise over count x C. */
+int wlseg_bn_apply(const void* z, const float* scale, const float* shift, const void* residual,
+                   void* y, int64_t count, int32_t C, int32_t relu, int32_t dtype,
+                   wlseg_stream_t stream);
+
+/* Backward of y = relu?(bn(z) + residual).  Pass 1 (reduce): with g = dy * (y > 0 if relu),
+ * dbeta[c] += sum g, dgamma[c] += sum g * (z - mean)*invstd  (double[C], caller zeroes).
+ * Pass 2 (apply): dz = gamma*invstd*(g - dbeta/count - zhat*dgamma/count); if dres != NULL the
+ * masked gradient g is also written there (gradient of the residual input). */
+int wlseg_bn_bwd_reduce(const void* dy, const void* y, const void* z, const float* mean,
+                        const float* invstd, int64_t count, int32_t C, int32_t relu,
+                        int32_t dtype, double* dgamma, double* dbeta, wlseg_stream_t stream);
+int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* mean,
+                       const float* invstd, const float* gamma, const double* dgamma,
+                       const double* dbeta, int64_t count, int32_t C, int32_t relu, int32_t dtype,
+                       void* dz, void* dres, wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Max pool, TF 'SAME' padding (replaces slim.max_pool2d: resnet pool1 3x3 s2 and the 1x1 s2
+ * shortcut subsample; arg scope models/resnet50_extended_model_hierarchical.py:351-353).
+ * Backward routes the gradient to the first maximum of each window in row-major scan order.
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_maxpool_same_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                           int32_t ksize, int32_t stride, int32_t dtype, wlseg_stream_t stream);
+int wlseg_maxpool_same_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H,
+                           int32_t W, int32_t C, int32_t ksize, int32_t stride, int32_t dtype,
+                           wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hierarchical head, forward (replaces _create_upsampler + softmax x3 + argmax x3 + gather /
+ * where composition, models/resnet50_extended_model_hierarchical.py:84-117,143-184).
+ * logits: fp32 [N, h, w, logits_pitch] low-resolution logits of the three heads, concatenated
+ * along channels (the first C1+Cv+Ch of every logits_pitch-wide pixel are used).  Bilinear upsampling to (H, W) with align_corners=True is done on the fly.
+ * Outputs (each optional, NULL to skip): decisions int32 [N,H,W] in common class ids;
+ * l1/l2v/l2h decisions int32 [N,H,W]; l1/l2v/l2h probabilities fp32 [N,H,W,C*];
+ * full-resolution logits fp32 [N,H,W,C1+Cv+Ch].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct wlseg_hierarchy {
+  int32_t C1, Cv, Ch;           /* head widths (14/7/3 cityscapes, 53/12/5 vistas) */
+  int32_t cid_l1_vehicle, cid_l1_human;
+  int32_t l1_to_common[64];     /* l1 cid -> common cid */
+  int32_t veh_to_common[16];
+  int32_t hum_to_common[8];
+  /* loss side (estimator/define_losses_hierarchical.py:38-93) */
+  int32_t num_classes;          /* strong label ids in [0, num_classes) */
+  int32_t pp_to_l1[80], pp_to_veh[80], pp_to_hum[80];
+  int32_t bb_to_veh[15], bb_to_hum[15];
+} wlseg_hierarchy;
+
+int wlseg_head_fwd(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch,
+                   int32_t N, int32_t h, int32_t w, int32_t H, int32_t W, int32_t* decisions, int32_t* l1_decisions,
+                   int32_t* l2v_decisions, int32_t* l2h_decisions, float* l1_probs,
+                   float* l2v_probs, float* l2h_probs, float* fullres_logits,
+                   wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hierarchical strong + weak masked cross-entropy, forward and backward fused with the
+ * bilinear upsample and its transpose (replaces estimator/define_losses_hierarchical.py:97-203
+ * and ResizeBilinearGrad).  Batch order: n_strong images with per-pixel labels int32 [.,H,W],
+ * then n_bbox images with fp32 [.,H,W,15] labels, then n_image images with fp32 [.,H,W,15].
+ * sums: double[3] += sum(ce*w) for (l1, l2_vehicle, l2_human); counts: double[3] += count(w!=0)
+ * (caller zeroes).  dlogits: fp32 [N,h,w,logits_pitch], accumulated into (caller zeroes), holds the
+ * UNNORMALISED gradient sum_pixels w*(softmax - target) transposed through the upsample;
+ * wlseg_loss_finalize scales it by coef/count per head and produces the six scalar losses.
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_loss_fwd_bwd(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch,
+                       int32_t n_strong, int32_t n_bbox, int32_t n_image, int32_t h, int32_t w, int32_t H, int32_t W,
+                       const int32_t* strong_labels, const float* bbox_labels,
+                       const float* image_labels, double* sums, double* counts, float* dlogits,
+                       wlseg_stream_t stream);
+/* losses: float[4] = {l1, l2_vehicle, l2_human, segmentation = l1 + l2_coef*(l2v + l2h)};
+ * dlogits scaled in place by grad_scale * coef_head / count_head (0 where count is 0). */
+int wlseg_loss_finalize(const wlseg_hierarchy* hier, const double* sums, const double* counts,
+                        float l2_coef, float grad_scale, float* dlogits, int32_t logits_pitch,
+                        int64_t n_lowres_pixels, float* losses, wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Confusion matrix (replaces metrics_impl._streaming_confusion_matrix,
+ * estimator/define_estimator_hierarchical.py:185-194, and tf.confusion_matrix in
+ * estimator/define_metrics.py:10-12): cm[label*C + decision] += 1 for n pixels, int64,
+ * accumulated into.  `lut` (optional, int32[lut_size]) remaps decisions first
+ * (_map_predictions_to_new_cids, define_estimator_hierarchical.py:511-514).  Pairs outside
+ * [0, C) are skipped and counted in *invalid (optional, int64).
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_confmat_accumulate(const int32_t* labels, const int32_t* decisions, int64_t n,
+                             int32_t num_classes, const int32_t* lut, int32_t lut_size,
+                             int64_t* cm, int64_t* invalid, wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer (replaces tf.train.MomentumOptimizer + slim.l2_regularizer gradient,
+ * estimator/define_optimizer.py:17-22, models/resnet50_extended_model_hierarchical.py:336):
+ *   g' = g*grad_scale + wd*w (wd only for the first n_decay elements: conv kernels)
+ *   acc = momentum*acc + g' ; w -= lr*acc   (nesterov: w -= lr*(g' + momentum*acc))
+ * over flat fp32 buffers of n elements; w_bf16 (optional) receives the rounded copy;
+ * reg_loss (optional, double) += wd/2 * sum_{i<n_decay} w_i^2 (pre-update weights).
+ * lr is read from device memory (`lr_dev`, float[1]) so the step is CUDA-graph replayable.
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_sgdm_step(float* w, const float* g, float* acc, void* w_bf16, int64_t n, int64_t n_decay,
+                    const float* lr_dev, float momentum, int32_t nesterov, float wd,
+                    float grad_scale, double* reg_loss, wlseg_stream_t stream);
+
+/* Layout / dtype helpers used by the host mirror (no reference counterpart: TF keeps HWIO
+ * fp32 kernels; we keep KRSC bf16 operand copies). */
+int wlseg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, wlseg_stream_t stream);
+int wlseg_cast_bf16_to_f32(const void* src, float* dst, int64_t n, wlseg_stream_t stream);
+/* dst[k,r,s,c] (optionally rotated 180 degrees in r,s and with k<->c swapped: the kernel a
+ * stride-1 dgrad runs as an fprop) from src KRSC. */
+int wlseg_weights_transpose_flip(const void* src, void* dst, int32_t K, int32_t R, int32_t S,
+                                 int32_t C, int32_t dtype, wlseg_stream_t stream);
+/* Packs a 3-channel NHWC image (fp32 or bf16) for the ResNet root convolution
+ * (7x7 stride 2, models/resnet50_extended_feature_extractor.py:25-30) into the bf16 tensor
+ * out[N, ceil(H/2), ceil(W/2), 64] = space-to-depth(2) with the 4 horizontal taps unrolled into
+ * channels, so that conv1 runs on the tensor cores as an R=4, S=1, C=64 convolution
+ * (csrc/transform.cu gives the exact index map). */
+int wlseg_conv1_pack(const void* img, int32_t dtype, int32_t N, int32_t H, int32_t W, void* out,
+                     wlseg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WLSEG_H_ */

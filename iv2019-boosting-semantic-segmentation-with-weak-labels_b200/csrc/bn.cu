@@ -1,0 +1,289 @@
+// Training-mode batch normalisation around the tensor-core convolutions.
+//
+// Replaces tf.contrib.layers.batch_norm (FusedBatchNorm / FusedBatchNormGrad) configured by
+// code/models/resnet50_extended_model_hierarchical.py:298-312,325: batch mean / biased variance
+// over N*H*W, eps 1e-5, moving statistics updated with `decay` using the UNBIASED variance.
+// In inference mode BN is folded into the convolution epilogue (scale/shift) and none of these
+// kernels run.
+//
+// All kernels are HBM-bound passes over [count x C] NHWC activations, 8 channels per thread.
+// Statistics are reduced per thread in fp32 over a few rows, per CTA in shared memory, and
+// across CTAs with fp64 global atomics (sums of up to 10^5..10^6 values per channel).
+#include "common.cuh"
+
+namespace wlseg {
+
+constexpr int kBnThreads = 256;
+
+// thread (tx, ty): tx = channel-vector index within C/8 (<= 256), ty = row lane
+template <typename T, bool kBackward>
+__global__ void __launch_bounds__(kBnThreads)
+bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* __restrict__ z,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, int64_t count, int C, int pitch,
+                 int relu, double* __restrict__ out0, double* __restrict__ out1) {
+  // forward (kBackward=false): a = z;  out0 += sum z, out1 += sum z^2
+  // backward: a = dy; g = dy*(yact>0 if relu); out0 += sum g*(z-mean)*invstd (dgamma), out1 += sum g (dbeta)
+  extern __shared__ float part[];  // [lanes][2][C]
+  const int cv = C / 8;
+  const int lanes = kBnThreads / cv;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+  float mu[8], is[8];
+  if (kBackward) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[tx * 8 + j]; is[j] = invstd[tx * 8 + j]; }
+  }
+  if (ty < lanes) {
+    for (int64_t row = (int64_t)blockIdx.x * lanes + ty; row < count; row += (int64_t)gridDim.x * lanes) {
+      float f[8];
+      Vec8<T> v;
+      v.load(a + row * pitch + tx * 8);
+      v.unpack(f);
+      if (!kBackward) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] += f[j] * f[j]; }
+      } else {
+        float zz[8];
+        Vec8<T> vz;
+        vz.load(z + row * pitch + tx * 8);
+        vz.unpack(zz);
+        if (relu) {
+          float yy[8];
+          Vec8<T> vy;
+          vy.load(yact + row * pitch + tx * 8);
+          vy.unpack(yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = yy[j] > 0.f ? f[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0[j] += f[j] * (zz[j] - mu[j]) * is[j]; s1[j] += f[j]; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      part[(ty * 2 + 0) * C + tx * 8 + j] = s0[j];
+      part[(ty * 2 + 1) * C + tx * 8 + j] = s1[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kBnThreads) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int l = 0; l < lanes; ++l) { t0 += (double)part[(l * 2 + 0) * C + c]; t1 += (double)part[(l * 2 + 1) * C + c]; }
+    atomicAdd(out0 + c, t0);
+    atomicAdd(out1 + c, t1);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, int64_t count,
+                                   int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ saved_mean,
+                                   float* __restrict__ saved_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double n = (double)count;
+  double m = sum[c] / n;
+  double var = sqsum[c] / n - m * m;
+  if (var < 0.0) var = 0.0;
+  float mf = (float)m, vf = (float)var;
+  float inv = rsqrtf(vf + eps);
+  float sc = gamma[c] * inv;
+  if (scale) scale[c] = sc;
+  if (shift) shift[c] = beta[c] - mf * sc;
+  if (saved_mean) saved_mean[c] = mf;
+  if (saved_invstd) saved_invstd[c] = inv;
+  if (moving_mean) {
+    // TF: moving <- moving - (1 - decay) * (moving - stat); variance with Bessel's correction
+    float unbiased = count > 1 ? (float)(var * (n / (n - 1.0))) : vf;
+    moving_mean[c] -= (1.0f - decay) * (moving_mean[c] - mf);
+    moving_var[c] -= (1.0f - decay) * (moving_var[c] - unbiased);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                const T* __restrict__ res, T* __restrict__ y, int64_t count, int C, int relu) {
+  const int cv = C / 8;
+  const int64_t total = count * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c0 = (int)(i % cv) * 8;
+    float f[8];
+    Vec8<T> v;
+    v.load(z + i * 8);
+    v.unpack(f);
+    float4 sa = *reinterpret_cast<const float4*>(scale + c0), sb = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    float4 ha = *reinterpret_cast<const float4*>(shift + c0), hb = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+    if (res != nullptr) {
+      float r[8];
+      Vec8<T> vr;
+      vr.load(res + i * 8);
+      vr.unpack(r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    Vec8<T> o;
+    o.pack(f);
+    o.store(y + i * 8);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ z,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const double* __restrict__ dgamma, const double* __restrict__ dbeta, int64_t count, int C,
+                    int relu, T* __restrict__ dz, T* __restrict__ dres) {
+  const int cv = C / 8;
+  const int64_t total = count * cv;
+  const float invn = 1.0f / (float)count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c0 = (int)(i % cv) * 8;
+    float g[8], zz[8];
+    Vec8<T> v;
+    v.load(dy + i * 8);
+    v.unpack(g);
+    if (relu) {
+      float yy[8];
+      Vec8<T> vy;
+      vy.load(yact + i * 8);
+      vy.unpack(yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yy[j] > 0.f ? g[j] : 0.f;
+    }
+    if (dres != nullptr) {
+      Vec8<T> o;
+      o.pack(g);
+      o.store(dres + i * 8);
+    }
+    Vec8<T> vz;
+    vz.load(z + i * 8);
+    vz.unpack(zz);
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = c0 + j;
+      float is = invstd[c];
+      float zh = (zz[j] - mean[c]) * is;
+      out[j] = gamma[c] * is * (g[j] - (float)dbeta[c] * invn - zh * (float)dgamma[c] * invn);
+    }
+    Vec8<T> o;
+    o.pack(out);
+    o.store(dz + i * 8);
+  }
+}
+
+static int check_bn_shape(int64_t count, int C, const char* who) {
+  WLSEG_CHECK_ARG(count >= 0 && C > 0 && C % 8 == 0 && C <= 2048, "%s: C (%d) must be a multiple of 8 and <= 2048", who, C);
+  return 0;
+}
+
+template <typename T, bool kBackward>
+static int launch_reduce(const void* a, const void* y, const void* z, const float* mean, const float* invstd,
+                         int64_t count, int C, int pitch, int relu, double* o0, double* o1, cudaStream_t s) {
+  const int cv = C / 8;
+  const int lanes = kBnThreads / cv;
+  size_t smem = (size_t)lanes * 2 * C * sizeof(float);
+  int grid = bw_grid(count * cv, kBnThreads, 4);
+  bn_reduce_kernel<T, kBackward><<<grid, kBnThreads, smem, s>>>((const T*)a, (const T*)y, (const T*)z, mean, invstd,
+                                                                count, C, pitch, relu, o0, o1);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace wlseg
+
+using namespace wlseg;
+
+extern "C" int wlseg_bn_stats(const void* z, int64_t count, int32_t C, int32_t pitch, int32_t dtype, double* sum,
+                              double* sqsum, wlseg_stream_t stream) {
+  if (int e = check_bn_shape(count, C, "bn_stats")) return e;
+  WLSEG_CHECK_ARG(pitch >= C && pitch % 8 == 0, "bn_stats: bad pitch %d", pitch);
+  if (count == 0) return 0;
+  WLSEG_CHECK_ARG(z && sum && sqsum, "bn_stats: null pointer");
+  if (dtype == WLSEG_BF16)
+    return launch_reduce<__nv_bfloat16, false>(z, nullptr, nullptr, nullptr, nullptr, count, C, pitch, 0, sum, sqsum,
+                                               (cudaStream_t)stream);
+  if (dtype == WLSEG_F32)
+    return launch_reduce<float, false>(z, nullptr, nullptr, nullptr, nullptr, count, C, pitch, 0, sum, sqsum,
+                                       (cudaStream_t)stream);
+  WLSEG_CHECK_ARG(false, "bn_stats: bad dtype %d", dtype);
+}
+
+extern "C" int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t count, int32_t C, const float* gamma,
+                                 const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
+                                 float* scale, float* shift, float* saved_mean, float* saved_invstd,
+                                 wlseg_stream_t stream) {
+  WLSEG_CHECK_ARG(sum && sqsum && gamma && beta && count > 0 && C > 0, "bn_finalize: bad args");
+  WLSEG_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving stats must come in pairs");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, count, C, gamma, beta, eps, decay,
+                                                                        moving_mean, moving_var, scale, shift,
+                                                                        saved_mean, saved_invstd);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wlseg_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y,
+                              int64_t count, int32_t C, int32_t relu, int32_t dtype, wlseg_stream_t stream) {
+  if (int e = check_bn_shape(count, C, "bn_apply")) return e;
+  if (count == 0) return 0;
+  WLSEG_CHECK_ARG(z && scale && shift && y, "bn_apply: null pointer");
+  int grid = bw_grid(count * (C / 8), 256, 8);
+  if (dtype == WLSEG_BF16)
+    bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, scale, shift,
+                                                            (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, count, C, relu);
+  else if (dtype == WLSEG_F32)
+    bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)z, scale, shift, (const float*)residual,
+                                                            (float*)y, count, C, relu);
+  else
+    WLSEG_CHECK_ARG(false, "bn_apply: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wlseg_bn_bwd_reduce(const void* dy, const void* y, const void* z, const float* mean,
+                                   const float* invstd, int64_t count, int32_t C, int32_t relu, int32_t dtype,
+                                   double* dgamma, double* dbeta, wlseg_stream_t stream) {
+  if (int e = check_bn_shape(count, C, "bn_bwd_reduce")) return e;
+  if (count == 0) return 0;
+  WLSEG_CHECK_ARG(dy && z && mean && invstd && dgamma && dbeta && (!relu || y), "bn_bwd_reduce: null pointer");
+  if (dtype == WLSEG_BF16)
+    return launch_reduce<__nv_bfloat16, true>(dy, y, z, mean, invstd, count, C, C, relu, dgamma, dbeta,
+                                              (cudaStream_t)stream);
+  if (dtype == WLSEG_F32)
+    return launch_reduce<float, true>(dy, y, z, mean, invstd, count, C, C, relu, dgamma, dbeta, (cudaStream_t)stream);
+  WLSEG_CHECK_ARG(false, "bn_bwd_reduce: bad dtype %d", dtype);
+}
+
+extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* mean, const float* invstd,
+                                  const float* gamma, const double* dgamma, const double* dbeta, int64_t count,
+                                  int32_t C, int32_t relu, int32_t dtype, void* dz, void* dres,
+                                  wlseg_stream_t stream) {
+  if (int e = check_bn_shape(count, C, "bn_bwd_apply")) return e;
+  if (count == 0) return 0;
+  WLSEG_CHECK_ARG(dy && z && mean && invstd && gamma && dgamma && dbeta && dz && (!relu || y),
+                  "bn_bwd_apply: null pointer");
+  int grid = bw_grid(count * (C / 8), 256, 8);
+  if (dtype == WLSEG_BF16)
+    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, invstd, gamma, dgamma, dbeta,
+        count, C, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
+  else if (dtype == WLSEG_F32)
+    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z, mean,
+                                                                invstd, gamma, dgamma, dbeta, count, C, relu,
+                                                                (float*)dz, (float*)dres);
+  else
+    WLSEG_CHECK_ARG(false, "bn_bwd_apply: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}

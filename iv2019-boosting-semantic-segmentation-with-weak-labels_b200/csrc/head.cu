@@ -1,0 +1,186 @@
+// Hierarchical head, forward: bilinear x8 upsample (align_corners) of the three low-resolution
+// logit maps fused with softmax, argmax and the hierarchical decision composition.
+//
+// Replaces, from code/models/resnet50_extended_model_hierarchical.py:
+//   :84-86,:143-184  _create_upsampler  -> tf.image.resize_images(bilinear, align_corners=True)
+//   :88-93           tf.nn.softmax x3, tf.argmax x3 (lowest index on ties)
+//   :95-117          tf.gather / tf.where composition into common class ids
+// so that the 24- (70-) channel full-resolution logits are never materialised unless asked for.
+//
+// Bandwidth kernel.  A CTA owns a 64 x 16 output tile, stages the low-resolution patch that
+// supports it in shared memory (read once from L2/HBM), and every thread interpolates its
+// pixels from the patch.  Algorithmic HBM bytes per output pixel: 4 (decisions) + 4*channels
+// of each requested probability map + 4*(C1+Cv+Ch)/64 (low-res logits).
+#include "common.cuh"
+
+namespace wlseg {
+
+constexpr int kHeadTX = 64;
+constexpr int kHeadTY = 16;
+constexpr int kHeadThreads = 256;
+
+struct HeadArgs {
+  const float* logits;
+  int N, h, w, H, W;
+  int cp;        // channel pitch of the low-res logits (>= Ct)
+  float sy, sx;  // (h-1)/(H-1), (w-1)/(W-1) in fp32, as TF's CalculateResizeScale
+  int ph, pw;    // patch capacity (rows, cols)
+  int32_t* decisions;
+  int32_t* l1_dec;
+  int32_t* l2v_dec;
+  int32_t* l2h_dec;
+  float* l1_probs;
+  float* l2v_probs;
+  float* l2h_probs;
+  float* full_logits;
+};
+
+struct Interp {
+  const float* p00;
+  const float* p01;
+  const float* p10;
+  const float* p11;
+  float tx, ty;
+  // TF ResizeBilinear: top = tl + (tr - tl)*x_lerp ; out = top + (bottom - top)*y_lerp
+  __device__ __forceinline__ float at(int c) const {
+    float tl = p00[c], tr = p01[c], bl = p10[c], br = p11[c];
+    float top = tl + (tr - tl) * tx;
+    float bot = bl + (br - bl) * tx;
+    return top + (bot - top) * ty;
+  }
+};
+
+__device__ __forceinline__ int head_argmax(const Interp& it, int c0, int C, float& best) {
+  int arg = 0;
+  best = it.at(c0);
+  for (int c = 1; c < C; ++c) {
+    float v = it.at(c0 + c);
+    if (v > best) { best = v; arg = c; }  // strict: first maximum wins, as tf.argmax
+  }
+  return arg;
+}
+
+__device__ __forceinline__ void head_probs(const Interp& it, int c0, int C, float mx, float* out) {
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(it.at(c0 + c) - mx);
+  float inv = 1.0f / s;
+  for (int c = 0; c < C; ++c) out[c] = expf(it.at(c0 + c) - mx) * inv;
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
+head_fwd_kernel(const __grid_constant__ wlseg_hierarchy hier, const HeadArgs a) {
+  extern __shared__ float patch[];  // [ph][pw][Ct]
+  const int Ct = hier.C1 + hier.Cv + hier.Ch;
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * kHeadTY, x0 = blockIdx.x * kHeadTX;
+  const int yl0 = (int)floorf(y0 * a.sy), xl0 = (int)floorf(x0 * a.sx);
+
+  // stage the low-res patch (clamped at the borders; clamped cells are only read with weight 0
+  // or as the duplicated hi neighbour, exactly as TF's min(lo+1, in-1))
+  const int cells = a.ph * a.pw;
+  const float* src = a.logits + (int64_t)n * a.h * a.w * a.cp;
+  for (int i = threadIdx.x; i < cells * Ct; i += kHeadThreads) {
+    int c = i % Ct;
+    int cell = i / Ct;
+    int px = cell % a.pw, py = cell / a.pw;
+    int yy = min(yl0 + py, a.h - 1), xx = min(xl0 + px, a.w - 1);
+    patch[i] = __ldg(src + ((int64_t)yy * a.w + xx) * a.cp + c);
+  }
+  __syncthreads();
+
+  const int tx = threadIdx.x % kHeadTX;
+  const int x = x0 + tx;
+  if (x >= a.W) return;
+  const float fx = x * a.sx;
+  const int xl = (int)floorf(fx);
+  const int xh = min(xl + 1, a.w - 1);
+  const float lx = fx - (float)xl;
+
+  for (int ry = threadIdx.x / kHeadTX; ry < kHeadTY; ry += kHeadThreads / kHeadTX) {
+    const int y = y0 + ry;
+    if (y >= a.H) break;
+    const float fy = y * a.sy;
+    const int yl = (int)floorf(fy);
+    const int yh = min(yl + 1, a.h - 1);
+    Interp it;
+    it.tx = lx;
+    it.ty = fy - (float)yl;
+    it.p00 = patch + ((yl - yl0) * a.pw + (xl - xl0)) * Ct;
+    it.p01 = patch + ((yl - yl0) * a.pw + (xh - xl0)) * Ct;
+    it.p10 = patch + ((yh - yl0) * a.pw + (xl - xl0)) * Ct;
+    it.p11 = patch + ((yh - yl0) * a.pw + (xh - xl0)) * Ct;
+
+    float m1, mv, mh;
+    const int d1 = head_argmax(it, 0, hier.C1, m1);
+    const int dv = head_argmax(it, hier.C1, hier.Cv, mv);
+    const int dh = head_argmax(it, hier.C1 + hier.Cv, hier.Ch, mh);
+    int dec;
+    if (d1 == hier.cid_l1_vehicle) dec = hier.veh_to_common[dv];
+    else if (d1 == hier.cid_l1_human) dec = hier.hum_to_common[dh];
+    else dec = hier.l1_to_common[d1];
+
+    const int64_t pix = ((int64_t)n * a.H + y) * a.W + x;
+    if (a.decisions) a.decisions[pix] = dec;
+    if (a.l1_dec) a.l1_dec[pix] = d1;
+    if (a.l2v_dec) a.l2v_dec[pix] = dv;
+    if (a.l2h_dec) a.l2h_dec[pix] = dh;
+    if (a.l1_probs) head_probs(it, 0, hier.C1, m1, a.l1_probs + pix * hier.C1);
+    if (a.l2v_probs) head_probs(it, hier.C1, hier.Cv, mv, a.l2v_probs + pix * hier.Cv);
+    if (a.l2h_probs) head_probs(it, hier.C1 + hier.Cv, hier.Ch, mh, a.l2h_probs + pix * hier.Ch);
+    if (a.full_logits) {
+      float* o = a.full_logits + pix * Ct;
+      for (int c = 0; c < Ct; ++c) o[c] = it.at(c);
+    }
+  }
+}
+
+int check_hierarchy(const wlseg_hierarchy* hier) {
+  WLSEG_CHECK_ARG(hier != nullptr, "hierarchy is NULL");
+  WLSEG_CHECK_ARG(hier->C1 > 0 && hier->C1 <= 64 && hier->Cv > 0 && hier->Cv <= 16 && hier->Ch > 0 && hier->Ch <= 8,
+                  "hierarchy head widths (%d, %d, %d) out of range", hier->C1, hier->Cv, hier->Ch);
+  WLSEG_CHECK_ARG(hier->cid_l1_vehicle >= 0 && hier->cid_l1_vehicle < hier->C1 && hier->cid_l1_human >= 0 &&
+                      hier->cid_l1_human < hier->C1,
+                  "hierarchy: l1 super-class ids out of range");
+  return 0;
+}
+
+// scale exactly as TF: (in - 1) / float(out - 1) when out > 1 (align_corners), else in/out
+float resize_scale(int in, int out) {
+  return (out > 1) ? (float)(in - 1) / (float)(out - 1) : (float)in / (float)out;
+}
+
+}  // namespace wlseg
+
+using namespace wlseg;
+
+extern "C" int wlseg_head_fwd(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch, int32_t N,
+                              int32_t h, int32_t w, int32_t H, int32_t W, int32_t* decisions, int32_t* l1_decisions,
+                              int32_t* l2v_decisions, int32_t* l2h_decisions, float* l1_probs, float* l2v_probs,
+                              float* l2h_probs, float* fullres_logits, wlseg_stream_t stream) {
+  if (int e = check_hierarchy(hier)) return e;
+  WLSEG_CHECK_ARG(N >= 0 && h > 0 && w > 0 && H > 0 && W > 0, "head_fwd: bad shape");
+  if (N == 0) return 0;
+  WLSEG_CHECK_ARG(logits != nullptr, "head_fwd: logits is NULL");
+  WLSEG_CHECK_ARG(N <= 65535, "head_fwd: N too large");
+  WLSEG_CHECK_ARG(logits_pitch >= hier->C1 + hier->Cv + hier->Ch, "head_fwd: logits_pitch %d < channels", logits_pitch);
+  HeadArgs a;
+  a.logits = logits;
+  a.N = N; a.h = h; a.w = w; a.H = H; a.W = W;
+  a.cp = logits_pitch;
+  a.sy = resize_scale(h, H);
+  a.sx = resize_scale(w, W);
+  a.ph = (int)fminf((float)h, floorf(kHeadTY * a.sy) + 3.f);
+  a.pw = (int)fminf((float)w, floorf(kHeadTX * a.sx) + 3.f);
+  a.decisions = decisions; a.l1_dec = l1_decisions; a.l2v_dec = l2v_decisions; a.l2h_dec = l2h_decisions;
+  a.l1_probs = l1_probs; a.l2v_probs = l2v_probs; a.l2h_probs = l2h_probs; a.full_logits = fullres_logits;
+  const int Ct = hier->C1 + hier->Cv + hier->Ch;
+  size_t smem = (size_t)a.ph * a.pw * Ct * sizeof(float);
+  WLSEG_CHECK_ARG(smem <= 200 * 1024, "head_fwd: low-res patch (%zu B) does not fit shared memory; "
+                  "downsampling by more than ~8x is not supported", smem);
+  if (smem > 48 * 1024)
+    WLSEG_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(W, kHeadTX), (unsigned)ceil_div(H, kHeadTY), (unsigned)N);
+  head_fwd_kernel<<<grid, kHeadThreads, smem, (cudaStream_t)stream>>>(*hier, a);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}

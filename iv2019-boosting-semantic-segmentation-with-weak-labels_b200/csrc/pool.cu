@@ -1,0 +1,171 @@
+// Max pooling with TensorFlow 'SAME' padding, NHWC, forward and backward.
+//
+// Replaces slim.max_pool2d under the arg scope of
+// code/models/resnet50_extended_model_hierarchical.py:351-353: resnet pool1 (3x3, stride 2) and
+// the 1x1 stride-2 `resnet_utils.subsample` on the identity shortcut of block1/unit_3.
+// SAME: out = ceil(in/stride); pad_total = max((out-1)*stride + k - in, 0); pad_before =
+// pad_total/2 (the odd cell goes bottom/right); padded cells never win.
+// Backward: every window's gradient goes to its FIRST maximum in row-major scan order (TF
+// MaxPoolGrad); implemented as a gather per input element so no atomics are needed.
+//
+// HBM-bound: 8 channels (16 B for bf16) per thread, channels innermost => coalesced.
+#include "common.cuh"
+
+namespace wlseg {
+
+struct PoolGeom {
+  int N, H, W, C, P, Q, k, stride, pad_t, pad_l;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g) {
+  const int cv = g.C / 8;
+  const int64_t total = (int64_t)g.N * g.P * g.Q * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % cv);
+    int64_t t = i / cv;
+    int q = (int)(t % g.Q); t /= g.Q;
+    int p = (int)(t % g.P);
+    int n = (int)(t / g.P);
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+    for (int r = 0; r < g.k; ++r) {
+      int hh = p * g.stride - g.pad_t + r;
+      if (hh < 0 || hh >= g.H) continue;
+      for (int s = 0; s < g.k; ++s) {
+        int ww = q * g.stride - g.pad_l + s;
+        if (ww < 0 || ww >= g.W) continue;
+        Vec8<T> v;
+        v.load(x + (((int64_t)n * g.H + hh) * g.W + ww) * g.C + c8 * 8);
+        float f[8];
+        v.unpack(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
+      }
+    }
+    Vec8<T> o;
+    o.pack(best);
+    o.store(y + (((int64_t)n * g.P + p) * g.Q + q) * g.C + c8 * 8);
+  }
+}
+
+// dx[n,h,w,c] = sum over windows (p,q) containing (h,w) whose first maximum is (h,w) of dy[n,p,q,c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, PoolGeom g) {
+  const int cv = g.C / 8;
+  const int64_t total = (int64_t)g.N * g.H * g.W * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % cv);
+    int64_t t = i / cv;
+    int w = (int)(t % g.W); t /= g.W;
+    int h = (int)(t % g.H);
+    int n = (int)(t / g.H);
+    float me[8], acc[8];
+    {
+      Vec8<T> v;
+      v.load(x + (((int64_t)n * g.H + h) * g.W + w) * g.C + c8 * 8);
+      v.unpack(me);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows p with p*stride - pad_t <= h <= p*stride - pad_t + k - 1
+    int p_lo = (h + g.pad_t - g.k + 1 + g.stride - 1);
+    p_lo = p_lo <= 0 ? 0 : p_lo / g.stride;
+    int p_hi = min((h + g.pad_t) / g.stride, g.P - 1);
+    int q_lo = (w + g.pad_l - g.k + 1 + g.stride - 1);
+    q_lo = q_lo <= 0 ? 0 : q_lo / g.stride;
+    int q_hi = min((w + g.pad_l) / g.stride, g.Q - 1);
+    for (int p = p_lo; p <= p_hi; ++p) {
+      for (int q = q_lo; q <= q_hi; ++q) {
+        // am I the first maximum of window (p,q)?  earlier cells must be strictly smaller,
+        // later cells must not be larger
+        bool win[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = true;
+        for (int r = 0; r < g.k; ++r) {
+          int hh = p * g.stride - g.pad_t + r;
+          if (hh < 0 || hh >= g.H) continue;
+          for (int s = 0; s < g.k; ++s) {
+            int ww = q * g.stride - g.pad_l + s;
+            if (ww < 0 || ww >= g.W) continue;
+            if (hh == h && ww == w) continue;
+            const bool earlier = (hh < h) || (hh == h && ww < w);
+            Vec8<T> v;
+            v.load(x + (((int64_t)n * g.H + hh) * g.W + ww) * g.C + c8 * 8);
+            float f[8];
+            v.unpack(f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) win[j] = win[j] && (earlier ? (f[j] < me[j]) : (f[j] <= me[j]));
+          }
+        }
+        Vec8<T> gv;
+        gv.load(dy + (((int64_t)n * g.P + p) * g.Q + q) * g.C + c8 * 8);
+        float gf[8];
+        gv.unpack(gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += win[j] ? gf[j] : 0.f;
+      }
+    }
+    Vec8<T> o;
+    o.pack(acc);
+    o.store(dx + (((int64_t)n * g.H + h) * g.W + w) * g.C + c8 * 8);
+  }
+}
+
+static int make_geom(PoolGeom& g, int N, int H, int W, int C, int k, int stride) {
+  WLSEG_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "maxpool: bad shape");
+  WLSEG_CHECK_ARG(C % 8 == 0, "maxpool: C (%d) must be a multiple of 8", C);
+  g.N = N; g.H = H; g.W = W; g.C = C; g.k = k; g.stride = stride;
+  g.P = (H + stride - 1) / stride;
+  g.Q = (W + stride - 1) / stride;
+  int tot_h = (g.P - 1) * stride + k - H; if (tot_h < 0) tot_h = 0;
+  int tot_w = (g.Q - 1) * stride + k - W; if (tot_w < 0) tot_w = 0;
+  g.pad_t = tot_h / 2;
+  g.pad_l = tot_w / 2;
+  return 0;
+}
+
+}  // namespace wlseg
+
+using namespace wlseg;
+
+extern "C" int wlseg_maxpool_same_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                                      int32_t ksize, int32_t stride, int32_t dtype, wlseg_stream_t stream) {
+  PoolGeom g;
+  if (int e = make_geom(g, N, H, W, C, ksize, stride)) return e;
+  if (N == 0) return 0;
+  WLSEG_CHECK_ARG(x && y, "maxpool_fwd: null pointer");
+  int64_t items = (int64_t)N * g.P * g.Q * (C / 8);
+  int grid = bw_grid(items, 256, 8);
+  if (dtype == WLSEG_BF16)
+    maxpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, g);
+  else if (dtype == WLSEG_F32)
+    maxpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, g);
+  else
+    WLSEG_CHECK_ARG(false, "maxpool_fwd: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wlseg_maxpool_same_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W,
+                                      int32_t C, int32_t ksize, int32_t stride, int32_t dtype,
+                                      wlseg_stream_t stream) {
+  PoolGeom g;
+  if (int e = make_geom(g, N, H, W, C, ksize, stride)) return e;
+  if (N == 0) return 0;
+  WLSEG_CHECK_ARG(x && dy && dx, "maxpool_bwd: null pointer");
+  int64_t items = (int64_t)N * H * W * (C / 8);
+  int grid = bw_grid(items, 256, 8);
+  if (dtype == WLSEG_BF16)
+    maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                               (__nv_bfloat16*)dx, g);
+  else if (dtype == WLSEG_F32)
+    maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)dy, (float*)dx, g);
+  else
+    WLSEG_CHECK_ARG(false, "maxpool_bwd: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}

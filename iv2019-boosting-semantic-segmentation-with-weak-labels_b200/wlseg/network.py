@@ -1,0 +1,333 @@
+"""Parameters and the forward / backward drivers of the network on libwlseg kernels.
+
+Host-side mirror of the reference's `model()` (code/models/resnet50_extended_model_hierarchical.py:17-141)
+and `feature_extractor()` (code/models/resnet50_extended_feature_extractor.py:8-51).  This file
+only sequences kernel launches and owns buffers; all arithmetic is in csrc/.
+
+Data layout in HBM
+  activations  NHWC, bf16 (fp32 in the check mode)
+  conv kernels KRSC; ONE fp32 arena holds [all conv kernels | all gammas | all betas] (the
+               optimizer updates it with one launch), a parallel bf16 arena holds the MMA operands
+  BN moving statistics: a separate fp32 arena [all means | all variances]
+  low-res logits: fp32 [N, h, w, logits_pitch] with the three heads concatenated along channels
+"""
+
+import math
+
+import torch
+
+from wlseg import arch, ops
+
+
+def _trunc_normal_(t, std, gen):
+  torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=gen)
+
+
+class Params:
+  """All trainable variables + BN moving statistics, addressable by TF variable name."""
+
+  def __init__(self, hier, device, output_stride=8):
+    self.hier = hier
+    self.device = torch.device(device)
+    self.specs = arch.conv_specs(hier.head_widths, output_stride)
+    self.by_scope = {s.scope: s for s in self.specs}
+    self.w_off, self.c_off = {}, {}
+    off = 0
+    for s in self.specs:
+      self.w_off[s.scope] = off
+      off += s.K * s.R * s.S * s.C
+    self.n_conv = off
+    coff = 0
+    for s in self.specs:
+      self.c_off[s.scope] = coff
+      coff += s.K
+    self.n_chan = coff
+    # arenas are padded to a multiple of 8 elements so that every region stays 16-byte aligned
+    self.n_conv_pad = (self.n_conv + 7) // 8 * 8
+    self.n_chan_pad = (self.n_chan + 7) // 8 * 8
+    self.n_total = self.n_conv_pad + 2 * self.n_chan_pad
+    dev = self.device
+    self.master = torch.zeros(self.n_total, dtype=torch.float32, device=dev)
+    self.operand = torch.zeros(self.n_total, dtype=torch.bfloat16, device=dev)
+    self.moving = torch.zeros(2 * self.n_chan_pad, dtype=torch.float32, device=dev)
+    self.moving[self.n_chan_pad:] = 1.0
+    self.master[self.n_conv_pad:self.n_conv_pad + self.n_chan_pad] = 1.0  # gamma
+    self._derived = {}
+    self.version = 0
+
+  # ---- views -------------------------------------------------------------------------------
+  def _wview(self, arena, scope):
+    s = self.by_scope[scope]
+    o = self.w_off[scope]
+    return arena[o:o + s.K * s.R * s.S * s.C].view(s.K, s.R, s.S, s.C)
+
+  def w32(self, scope):
+    return self._wview(self.master, scope)
+
+  def wbf(self, scope):
+    return self._wview(self.operand, scope)
+
+  def _cview(self, arena, base, scope, n=None):
+    o = base + self.c_off[scope]
+    return arena[o:o + (self.by_scope[scope].K if n is None else n)]
+
+  def gamma(self, scope, n=None):
+    return self._cview(self.master, self.n_conv_pad, scope, n)
+
+  def beta(self, scope, n=None):
+    return self._cview(self.master, self.n_conv_pad + self.n_chan_pad, scope, n)
+
+  def moving_mean(self, scope, n=None):
+    return self._cview(self.moving, 0, scope, n)
+
+  def moving_var(self, scope, n=None):
+    return self._cview(self.moving, self.n_chan_pad, scope, n)
+
+  # ---- initialisation / import --------------------------------------------------------------
+  def init_random(self, seed=0):
+    """variance_scaling_initializer() defaults: truncated normal, stddev sqrt(1.3*2/fan_in)
+    (code/models/resnet50_extended_model_hierarchical.py:337); gamma 1, beta 0, moving 0 / 1."""
+    gen = torch.Generator().manual_seed(seed)
+    host = torch.zeros(self.n_total, dtype=torch.float32)
+    for s in self.specs:
+      w = torch.empty(s.K, s.R, s.S, s.C)
+      _trunc_normal_(w, math.sqrt(1.3 * 2.0 / (s.R * s.S * s.C)), gen)
+      o = self.w_off[s.scope]
+      host[o:o + w.numel()] = w.reshape(-1)
+    host[self.n_conv_pad:self.n_conv_pad + self.n_chan_pad] = 1.0
+    self.master.copy_(host)
+    self.moving[:self.n_chan_pad] = 0.0
+    self.moving[self.n_chan_pad:] = 1.0
+    self.sync_operands()
+
+  def load_tf_dict(self, tensors):
+    """Import a {TF variable name: tensor} dict (conv kernels HWIO as TF stores them)."""
+    host = self.master.cpu()
+    mov = self.moving.cpu()
+    for s in self.specs:
+      w = tensors[f'{s.scope}/weights'].to(torch.float32)
+      assert tuple(w.shape) == (s.R, s.S, s.C, s.K), (s.scope, tuple(w.shape))
+      o = self.w_off[s.scope]
+      host[o:o + w.numel()] = w.permute(3, 0, 1, 2).reshape(-1)
+      c = self.c_off[s.scope]
+      host[self.n_conv_pad + c:self.n_conv_pad + c + s.K] = tensors[f'{s.scope}/BatchNorm/gamma']
+      host[self.n_conv_pad + self.n_chan_pad + c:self.n_conv_pad + self.n_chan_pad + c + s.K] = \
+          tensors[f'{s.scope}/BatchNorm/beta']
+      mov[c:c + s.K] = tensors[f'{s.scope}/BatchNorm/moving_mean']
+      mov[self.n_chan_pad + c:self.n_chan_pad + c + s.K] = tensors[f'{s.scope}/BatchNorm/moving_variance']
+    self.master.copy_(host)
+    self.moving.copy_(mov)
+    self.sync_operands()
+
+  def to_tf_dict(self):
+    out = {}
+    for s in self.specs:
+      out[f'{s.scope}/weights'] = self.w32(s.scope).permute(1, 2, 3, 0).contiguous().cpu()
+      out[f'{s.scope}/BatchNorm/gamma'] = self.gamma(s.scope).cpu().clone()
+      out[f'{s.scope}/BatchNorm/beta'] = self.beta(s.scope).cpu().clone()
+      out[f'{s.scope}/BatchNorm/moving_mean'] = self.moving_mean(s.scope).cpu().clone()
+      out[f'{s.scope}/BatchNorm/moving_variance'] = self.moving_var(s.scope).cpu().clone()
+    return out
+
+  def sync_operands(self):
+    """bf16 operand copy of the master arena (the optimizer kernel keeps it in sync afterwards)."""
+    ops.cast_f32_to_bf16(self.master, self.operand)
+    self.touch()
+
+  def touch(self):
+    self.version += 1
+    self._derived.clear()
+
+  # ---- derived operands ----------------------------------------------------------------------
+  def conv1_packed_weights(self, dtype):
+    """Root 7x7/2 kernel rewritten for the packed input of csrc/transform.cu:
+    W2[k, a, 0, b*16 + (i*2+j)*3 + c] = w[k, 2a+i-1, 2b+j-1, c] (zero where the index is -1)."""
+    key = ('conv1_packed', dtype)
+    if key not in self._derived:
+      w = self.w32(f'{arch.RES}/conv1')  # [64, 7, 7, 3]
+      w2 = torch.zeros(64, 4, 1, 64, dtype=torch.float32, device=self.device)
+      for a in range(4):
+        for i in range(2):
+          r = 2 * a + i - 1
+          if r < 0:
+            continue
+          for b in range(4):
+            for j in range(2):
+              s = 2 * b + j - 1
+              if s < 0:
+                continue
+              c0 = b * 16 + (i * 2 + j) * 3
+              w2[:, a, 0, c0:c0 + 3] = w[:, r, s, :]
+      self._derived[key] = w2.to(dtype).contiguous()
+    return self._derived[key]
+
+  def folded_bn(self, scope, n=None, eps=1e-5):
+    """Inference batch norm as per-channel scale / shift (fp32)."""
+    key = ('fold', scope, n)
+    if key not in self._derived:
+      scale = self.gamma(scope, n) * torch.rsqrt(self.moving_var(scope, n) + eps)
+      shift = self.beta(scope, n) - self.moving_mean(scope, n) * scale
+      self._derived[key] = (scale.contiguous(), shift.contiguous())
+    return self._derived[key]
+
+  def flipped(self, scope, dtype):
+    """Filter bank of the stride-1 dgrad-as-fprop: [C, R, S, K], rotated 180 degrees."""
+    key = ('flip', scope, dtype)
+    if key not in self._derived:
+      src = self.wbf(scope) if dtype == torch.bfloat16 else self.w32(scope)
+      s = self.by_scope[scope]
+      dst = torch.empty(s.C, s.R, s.S, s.K, dtype=dtype, device=self.device)
+      ops.weights_transpose_flip(src, dst)
+      self._derived[key] = dst
+    return self._derived[key]
+
+
+class Network:
+  """Sequences the kernels of one forward (and backward) pass.
+
+  dtype=torch.bfloat16 is the product path (tcgen05 convolutions); dtype=torch.float32 is the
+  check mode: same kernels for everything but the convolutions, which run the direct fp32 kernel.
+  """
+
+  def __init__(self, params, dtype=torch.bfloat16, bn_decay=0.9, eps=1e-5, conv_algo=ops.ALGO_AUTO):
+    self.p = params
+    self.hier = params.hier
+    self.hstruct = params.hier.as_struct()
+    self.dtype = dtype
+    self.code = ops.dtype_code(dtype)
+    self.bn_decay = bn_decay
+    self.eps = eps
+    self.conv_algo = conv_algo
+    self.dev = params.device
+    self.tape = None
+
+  # ---- helpers ---------------------------------------------------------------------------------
+  def _weights(self, scope):
+    return self.p.wbf(scope) if self.dtype == torch.bfloat16 else self.p.w32(scope)
+
+  def _geom(self, spec, H, W):
+    pt, P = arch.same_pad_before(spec.R, spec.stride, spec.dilation, H)
+    pl, Q = arch.same_pad_before(spec.S, spec.stride, spec.dilation, W)
+    return pt, pl, P, Q
+
+  def _conv(self, x, w, *, stride=1, dilation=1, pad=(0, 0), out_hw, scale=None, shift=None, relu=False,
+            residual=None, res_stride=1, y=None, y_dtype=None, bn_sum=None, bn_sqsum=None):
+    N, H, W, C = x.shape
+    K = w.shape[0]
+    if y is None:
+      ydt = self.dtype if y_dtype is None else y_dtype
+      y = torch.empty((N, out_hw[0], out_hw[1], K), dtype=ydt, device=self.dev)
+    prm = ops.conv_params((N, H, W, C), tuple(w.shape), stride=stride, dilation=dilation, pad=pad, out_hw=out_hw,
+                          x_pitch=x.stride(2), y_pitch=y.stride(2), relu=relu, dtype=self.code,
+                          y_dtype=ops.dtype_code(y.dtype), algo=self.conv_algo, res=residual, res_stride=res_stride)
+    if bn_sum is not None and not (self.conv_algo != ops.ALGO_DIRECT and ops.conv2d_tcgen05_supported(prm)):
+      # direct kernel: statistics from the stored output instead of the accumulators
+      ops.conv2d_fprop(prm, x, w, y, scale, shift, residual)
+      ops.bn_stats(y, N * out_hw[0] * out_hw[1], K, y.stride(2), bn_sum, bn_sqsum)
+      return y
+    ops.conv2d_fprop(prm, x, w, y, scale, shift, residual, bn_sum, bn_sqsum)
+    return y
+
+  # ---- inference ---------------------------------------------------------------------------------
+  def _conv_bn_infer(self, x, scope, relu=None, residual=None, res_stride=1):
+    spec = self.p.by_scope[scope]
+    pt, pl, P, Q = self._geom(spec, x.shape[1], x.shape[2])
+    scale, shift = self.p.folded_bn(scope, eps=self.eps)
+    return self._conv(x, self._weights(scope), stride=spec.stride, dilation=spec.dilation, pad=(pt, pl),
+                      out_hw=(P, Q), scale=scale, shift=shift, relu=spec.relu if relu is None else relu,
+                      residual=residual, res_stride=res_stride)
+
+  def _root_infer(self, images):
+    scope = f'{arch.RES}/conv1'
+    N, H, W, _ = images.shape
+    scale, shift = self.p.folded_bn(scope, eps=self.eps)
+    if self.dtype == torch.bfloat16:
+      Hs, Ws = (H + 1) // 2, (W + 1) // 2
+      packed = torch.empty((N, Hs, Ws, 64), dtype=torch.bfloat16, device=self.dev)
+      ops.conv1_pack(images, packed)
+      w2 = self.p.conv1_packed_weights(torch.bfloat16)
+      y = self._conv(packed, w2, pad=(2, 0), out_hw=(Hs, Ws), scale=scale, shift=shift, relu=True)
+    else:
+      y = self._conv_bn_infer(images.to(self.dtype), scope)
+    P, Q = (y.shape[1] + 1) // 2, (y.shape[2] + 1) // 2
+    pooled = torch.empty((N, P, Q, 64), dtype=self.dtype, device=self.dev)
+    ops.maxpool_same_fwd(y, pooled, 3, 2)
+    return pooled
+
+  def _unit_infer(self, x, u):
+    if u.has_shortcut_conv:
+      shortcut, rs = self._conv_bn_infer(x, f'{u.scope}/shortcut'), 1
+    else:
+      # identity shortcut; a strided unit subsamples it (1x1 max-pool, stride s) -> strided read
+      shortcut, rs = x, u.stride
+    r = self._conv_bn_infer(x, f'{u.scope}/conv1')
+    r = self._conv_bn_infer(r, f'{u.scope}/conv2')
+    return self._conv_bn_infer(r, f'{u.scope}/conv3', relu=True, residual=shortcut, res_stride=rs)
+
+  def features_infer(self, images):
+    x = self._root_infer(images)
+    for u in arch.units():
+      x = self._unit_infer(x, u)
+    return self._conv_bn_infer(x, 'feature_extractor/extension/decrease_fdims')
+
+  def lowres_logits_infer(self, images):
+    """fp32 [N, h, w, logits_pitch]: the three heads' logits, concatenated along channels."""
+    f = self.features_infer(images)
+    N, h, w, d = f.shape
+    au = arch.adaptation_units(d)
+    # the three adaptation conv1 kernels are adjacent in the arena: one 256 -> 768 GEMM
+    s0 = f'{au[0].scope}/conv1'
+    o = self.p.w_off[s0]
+    arena = self.p.operand if self.dtype == torch.bfloat16 else self.p.master
+    w1 = arena[o:o + 3 * d * d].view(3 * d, 1, 1, d)
+    scale, shift = self.p.folded_bn(s0, n=3 * d, eps=self.eps)
+    a1 = self._conv(f, w1, out_hw=(h, w), scale=scale, shift=shift, relu=True)
+    pitch = self.hier.logits_pitch
+    logits = torch.zeros((N, h, w, pitch), dtype=torch.float32, device=self.dev)
+    c0 = 0
+    for b, (u, (_, lg)) in enumerate(zip(au, arch.BRANCHES)):
+      r = self._conv_bn_infer(a1[..., b * d:(b + 1) * d], f'{u.scope}/conv2')
+      r = self._conv_bn_infer(r, f'{u.scope}/conv3', relu=True, residual=f)
+      scope = f'softmax_classifier/{lg}'
+      ck = self.p.by_scope[scope].K
+      sc, sh = self.p.folded_bn(scope, eps=self.eps)
+      self._conv(r, self._weights(scope), out_hw=(h, w), scale=sc, shift=sh, relu=False,
+                 y=logits[..., c0:c0 + ck])
+      c0 += ck
+    return logits
+
+  def predict(self, images, want=('decisions',)):
+    """Forward pass -> dict with the requested keys of the reference's predictions dict
+    (code/models/resnet50_extended_model_hierarchical.py:121-130)."""
+    N, H, W, _ = images.shape
+    logits = self.lowres_logits_infer(images)
+    out = {'lowres_logits': logits}
+    out.update(self.head(logits, H, W, want))
+    return out
+
+  def head(self, logits, H, W, want=('decisions',)):
+    N = logits.shape[0]
+    C1, Cv, Ch = self.hier.head_widths
+    dev = self.dev
+
+    def i32(key):
+      return torch.empty((N, H, W), dtype=torch.int32, device=dev) if key in want else None
+
+    def f32(key, c):
+      return torch.empty((N, H, W, c), dtype=torch.float32, device=dev) if key in want else None
+    res = {'decisions': i32('decisions'), 'l1_decisions': i32('l1_decisions'),
+           'l2_vehicle_decisions': i32('l2_vehicle_decisions'), 'l2_human_decisions': i32('l2_human_decisions'),
+           'l1_probabilities': f32('l1_probabilities', C1), 'l2_vehicle_probabilities': f32('l2_vehicle_probabilities', Cv),
+           'l2_human_probabilities': f32('l2_human_probabilities', Ch)}
+    full = None
+    if any(k in want for k in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits', 'logits')):
+      full = torch.empty((N, H, W, C1 + Cv + Ch), dtype=torch.float32, device=dev)
+    ops.head_fwd(self.hstruct, logits, H, W, res['decisions'], res['l1_decisions'], res['l2_vehicle_decisions'],
+                 res['l2_human_decisions'], res['l1_probabilities'], res['l2_vehicle_probabilities'],
+                 res['l2_human_probabilities'], full)
+    out = {k: v for k, v in res.items() if v is not None}
+    if full is not None:
+      out['l1_logits'] = full[..., :C1]
+      out['l2_vehicle_logits'] = full[..., C1:C1 + Cv]
+      out['l2_human_logits'] = full[..., C1 + Cv:]
+    return out

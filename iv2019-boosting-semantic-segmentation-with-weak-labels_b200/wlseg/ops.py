@@ -1,0 +1,307 @@
+"""ctypes binding of libwlseg.so (include/wlseg.h) for torch CUDA tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every device op of the hot path is
+a call into the hand-written sm_100a library.  There is NO CPU / eager fallback: if the library
+is missing or a call fails, `WlsegError` is raised.
+"""
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libwlseg.so')
+
+F32, BF16 = 0, 1
+ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05 = 0, 1, 2
+
+_c_int = ctypes.c_int32
+_c_i64 = ctypes.c_int64
+_c_f = ctypes.c_float
+_vp = ctypes.c_void_p
+
+
+class WlsegError(RuntimeError):
+  pass
+
+
+class ConvParams(ctypes.Structure):
+  _fields_ = [(n, _c_int) for n in (
+      'N', 'H', 'W', 'C', 'K', 'R', 'S', 'P', 'Q', 'stride', 'dilation', 'pad_top', 'pad_left',
+      'x_pitch', 'y_pitch', 'res_pitch', 'res_stride', 'res_H', 'res_W', 'relu', 'dtype', 'y_dtype', 'algo')]
+
+
+class Hierarchy(ctypes.Structure):
+  _fields_ = [('C1', _c_int), ('Cv', _c_int), ('Ch', _c_int),
+              ('cid_l1_vehicle', _c_int), ('cid_l1_human', _c_int),
+              ('l1_to_common', _c_int * 64), ('veh_to_common', _c_int * 16), ('hum_to_common', _c_int * 8),
+              ('num_classes', _c_int),
+              ('pp_to_l1', _c_int * 80), ('pp_to_veh', _c_int * 80), ('pp_to_hum', _c_int * 80),
+              ('bb_to_veh', _c_int * 15), ('bb_to_hum', _c_int * 15)]
+
+
+_SIGNATURES = {
+    'wlseg_version': (ctypes.c_int, []),
+    'wlseg_last_error': (ctypes.c_char_p, []),
+    'wlseg_conv2d_tcgen05_supported': (ctypes.c_int, [ctypes.POINTER(ConvParams)]),
+    'wlseg_conv2d_fprop': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'wlseg_conv2d_dgrad': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp]),
+    'wlseg_conv2d_wgrad': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp]),
+    'wlseg_bn_stats': (ctypes.c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    'wlseg_bn_finalize': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp]),
+    'wlseg_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp]),
+    'wlseg_bn_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int,
+                                          _vp, _vp, _vp]),
+    'wlseg_maxpool_same_fwd': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    'wlseg_maxpool_same_bwd': (ctypes.c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                              _vp]),
+    'wlseg_head_fwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'wlseg_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                          _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'wlseg_loss_finalize': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _vp, _c_f, _c_f, _vp, _c_int, _c_i64, _vp,
+                                           _vp]),
+    'wlseg_confmat_accumulate': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _c_int, _vp, _vp, _vp]),
+    'wlseg_sgdm_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _c_f, _c_int, _c_f, _c_f, _vp, _vp]),
+    'wlseg_cast_f32_to_bf16': (ctypes.c_int, [_vp, _vp, _c_i64, _vp]),
+    'wlseg_cast_bf16_to_f32': (ctypes.c_int, [_vp, _vp, _c_i64, _vp]),
+    'wlseg_weights_transpose_flip': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    'wlseg_conv1_pack': (ctypes.c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+launches = 0  # number of library kernels enqueued (bench.py's gpu_launches claim)
+
+
+def lib():
+  """Load libwlseg.so; fails loudly when it has not been built (no fallback path exists)."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise WlsegError(
+          f'{LIB_PATH} is missing: build it with `python __graft_entry__.py` (or wlseg build.py). '
+          'wlseg has no CPU or eager fallback.')
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+      fn = getattr(L, name)
+      fn.restype = res
+      fn.argtypes = args
+    _lib = L
+  return _lib
+
+
+def _check(rc, what):
+  if rc != 0:
+    msg = lib().wlseg_last_error().decode('utf-8', 'replace')
+    raise WlsegError(f'{what} failed (rc={rc}): {msg}')
+
+
+def _ptr(t):
+  if t is None:
+    return None
+  assert t.is_cuda, 'wlseg ops take CUDA tensors only'
+  return t.data_ptr()
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt):
+  if dt == torch.bfloat16:
+    return BF16
+  if dt == torch.float32:
+    return F32
+  raise WlsegError(f'unsupported dtype {dt}')
+
+
+def _count(n=1):
+  global launches
+  launches += n
+
+
+# ------------------------------------------------------------------------------------ convolution
+def conv_params(x_shape, w_shape, stride=1, dilation=1, pad=(0, 0), out_hw=None, x_pitch=None, y_pitch=None,
+                relu=False, dtype=BF16, y_dtype=None, algo=ALGO_AUTO, res=None, res_stride=1):
+  N, H, W, C = x_shape
+  K, R, S, Cw = w_shape
+  assert Cw == C, f'filter channels {Cw} != input channels {C}'
+  p = ConvParams()
+  p.N, p.H, p.W, p.C = N, H, W, C
+  p.K, p.R, p.S = K, R, S
+  p.stride, p.dilation = stride, dilation
+  p.pad_top, p.pad_left = pad
+  if out_hw is None:
+    raise WlsegError('conv_params: out_hw required')
+  p.P, p.Q = out_hw
+  p.x_pitch = x_pitch if x_pitch is not None else C
+  p.y_pitch = y_pitch if y_pitch is not None else K
+  if res is not None:
+    p.res_H, p.res_W, p.res_pitch = res.shape[1], res.shape[2], res.stride(2)
+    p.res_stride = res_stride
+  else:
+    p.res_H = p.res_W = p.res_pitch = 0
+    p.res_stride = 1
+  p.relu = int(relu)
+  p.dtype = dtype
+  p.y_dtype = dtype if y_dtype is None else y_dtype
+  p.algo = algo
+  return p
+
+
+def conv2d_fprop(p, x, w, y, scale=None, shift=None, residual=None, bn_sum=None, bn_sqsum=None):
+  _check(lib().wlseg_conv2d_fprop(ctypes.byref(p), _ptr(x), _ptr(w), _ptr(y), _ptr(scale), _ptr(shift),
+                                  _ptr(residual), _ptr(bn_sum), _ptr(bn_sqsum), _stream()), 'wlseg_conv2d_fprop')
+  _count()
+  return y
+
+
+def conv2d_dgrad(p, dy, w, dx):
+  _check(lib().wlseg_conv2d_dgrad(ctypes.byref(p), _ptr(dy), _ptr(w), _ptr(dx), _stream()), 'wlseg_conv2d_dgrad')
+  _count()
+  return dx
+
+
+def conv2d_wgrad(p, x, dy, dw):
+  _check(lib().wlseg_conv2d_wgrad(ctypes.byref(p), _ptr(x), _ptr(dy), _ptr(dw), _stream()), 'wlseg_conv2d_wgrad')
+  _count()
+  return dw
+
+
+def conv2d_tcgen05_supported(p):
+  return bool(lib().wlseg_conv2d_tcgen05_supported(ctypes.byref(p)))
+
+
+def conv1_pack(img, out):
+  N, H, W, C = img.shape
+  assert C == 3
+  _check(lib().wlseg_conv1_pack(_ptr(img), dtype_code(img.dtype), N, H, W, _ptr(out), _stream()), 'wlseg_conv1_pack')
+  _count()
+  return out
+
+
+def weights_transpose_flip(src, dst):
+  K, R, S, C = src.shape
+  _check(lib().wlseg_weights_transpose_flip(_ptr(src), _ptr(dst), K, R, S, C, dtype_code(src.dtype), _stream()),
+         'wlseg_weights_transpose_flip')
+  _count()
+  return dst
+
+
+def cast_f32_to_bf16(src, dst):
+  _check(lib().wlseg_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), 'wlseg_cast_f32_to_bf16')
+  _count()
+  return dst
+
+
+def cast_bf16_to_f32(src, dst):
+  _check(lib().wlseg_cast_bf16_to_f32(_ptr(src), _ptr(dst), src.numel(), _stream()), 'wlseg_cast_bf16_to_f32')
+  _count()
+  return dst
+
+
+# ------------------------------------------------------------------------------------ batch norm
+def bn_stats(z, count, C, pitch, sum_, sqsum):
+  _check(lib().wlseg_bn_stats(_ptr(z), count, C, pitch, dtype_code(z.dtype), _ptr(sum_), _ptr(sqsum), _stream()),
+         'wlseg_bn_stats')
+  _count()
+
+
+def bn_finalize(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, saved_mean,
+                saved_invstd):
+  _check(lib().wlseg_bn_finalize(_ptr(sum_), _ptr(sqsum), count, C, _ptr(gamma), _ptr(beta), eps, decay,
+                                 _ptr(moving_mean), _ptr(moving_var), _ptr(scale), _ptr(shift), _ptr(saved_mean),
+                                 _ptr(saved_invstd), _stream()), 'wlseg_bn_finalize')
+  _count()
+
+
+def bn_apply(z, scale, shift, residual, y, count, C, relu):
+  _check(lib().wlseg_bn_apply(_ptr(z), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(y), count, C, int(relu),
+                              dtype_code(z.dtype), _stream()), 'wlseg_bn_apply')
+  _count()
+  return y
+
+
+def bn_bwd_reduce(dy, y, z, mean, invstd, count, C, relu, dgamma, dbeta):
+  _check(lib().wlseg_bn_bwd_reduce(_ptr(dy), _ptr(y), _ptr(z), _ptr(mean), _ptr(invstd), count, C, int(relu),
+                                   dtype_code(z.dtype), _ptr(dgamma), _ptr(dbeta), _stream()), 'wlseg_bn_bwd_reduce')
+  _count()
+
+
+def bn_bwd_apply(dy, y, z, mean, invstd, gamma, dgamma, dbeta, count, C, relu, dz, dres=None):
+  _check(lib().wlseg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dgamma),
+                                  _ptr(dbeta), count, C, int(relu), dtype_code(z.dtype), _ptr(dz), _ptr(dres),
+                                  _stream()), 'wlseg_bn_bwd_apply')
+  _count()
+  return dz
+
+
+# ------------------------------------------------------------------------------------ pooling
+def maxpool_same_fwd(x, y, ksize, stride):
+  N, H, W, C = x.shape
+  _check(lib().wlseg_maxpool_same_fwd(_ptr(x), _ptr(y), N, H, W, C, ksize, stride, dtype_code(x.dtype), _stream()),
+         'wlseg_maxpool_same_fwd')
+  _count()
+  return y
+
+
+def maxpool_same_bwd(x, dy, dx, ksize, stride):
+  N, H, W, C = x.shape
+  _check(lib().wlseg_maxpool_same_bwd(_ptr(x), _ptr(dy), _ptr(dx), N, H, W, C, ksize, stride, dtype_code(x.dtype),
+                                      _stream()), 'wlseg_maxpool_same_bwd')
+  _count()
+  return dx
+
+
+# ------------------------------------------------------------------------------------ head / loss / metrics
+def head_fwd(hier, logits, H, W, decisions=None, l1_decisions=None, l2v_decisions=None, l2h_decisions=None,
+             l1_probs=None, l2v_probs=None, l2h_probs=None, fullres_logits=None):
+  N, h, w, pitch = logits.shape
+  assert logits.dtype == torch.float32 and logits.is_contiguous()
+  _check(lib().wlseg_head_fwd(ctypes.byref(hier), _ptr(logits), pitch, N, h, w, H, W, _ptr(decisions),
+                              _ptr(l1_decisions), _ptr(l2v_decisions), _ptr(l2h_decisions), _ptr(l1_probs),
+                              _ptr(l2v_probs), _ptr(l2h_probs), _ptr(fullres_logits), _stream()), 'wlseg_head_fwd')
+  _count()
+
+
+def loss_fwd_bwd(hier, logits, H, W, strong_labels, bbox_labels, image_labels, sums, counts, dlogits):
+  B, h, w, pitch = logits.shape
+  ns = 0 if strong_labels is None else strong_labels.shape[0]
+  nb = 0 if bbox_labels is None else bbox_labels.shape[0]
+  ni = 0 if image_labels is None else image_labels.shape[0]
+  assert ns + nb + ni == B, 'labels do not cover the batch'
+  assert logits.dtype == torch.float32 and logits.is_contiguous() and dlogits.shape == logits.shape
+  _check(lib().wlseg_loss_fwd_bwd(ctypes.byref(hier), _ptr(logits), pitch, ns, nb, ni, h, w, H, W,
+                                  _ptr(strong_labels), _ptr(bbox_labels), _ptr(image_labels), _ptr(sums),
+                                  _ptr(counts), _ptr(dlogits), _stream()), 'wlseg_loss_fwd_bwd')
+  _count()
+
+
+def loss_finalize(hier, sums, counts, l2_coef, grad_scale, dlogits, losses):
+  pitch = dlogits.shape[-1] if dlogits is not None else hier.C1 + hier.Cv + hier.Ch
+  npix = 0 if dlogits is None else dlogits.numel() // pitch
+  _check(lib().wlseg_loss_finalize(ctypes.byref(hier), _ptr(sums), _ptr(counts), l2_coef, grad_scale, _ptr(dlogits),
+                                   pitch, npix, _ptr(losses), _stream()), 'wlseg_loss_finalize')
+  _count()
+
+
+def confmat_accumulate(labels, decisions, num_classes, cm, lut=None, invalid=None):
+  assert labels.dtype == torch.int32 and decisions.dtype == torch.int32 and cm.dtype == torch.int64
+  assert labels.numel() == decisions.numel() and labels.is_contiguous() and decisions.is_contiguous()
+  assert cm.numel() == num_classes * num_classes
+  _check(lib().wlseg_confmat_accumulate(_ptr(labels), _ptr(decisions), labels.numel(), num_classes, _ptr(lut),
+                                        0 if lut is None else lut.numel(), _ptr(cm), _ptr(invalid), _stream()),
+         'wlseg_confmat_accumulate')
+  _count()
+  return cm
+
+
+def sgdm_step(w, g, acc, w_bf16, n_decay, lr_dev, momentum, nesterov, wd, grad_scale=1.0, reg_loss=None):
+  _check(lib().wlseg_sgdm_step(_ptr(w), _ptr(g), _ptr(acc), _ptr(w_bf16), w.numel(), n_decay, _ptr(lr_dev), momentum,
+                               int(nesterov), wd, grad_scale, _ptr(reg_loss), _stream()), 'wlseg_sgdm_step')
+  _count()

@@ -1,0 +1,200 @@
+"""Oracle forward pass: ResNet-50 (OS8) + extension + adaptation + hierarchical heads.
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED (the
+ResNet-50 graph itself is tf.contrib.slim's `resnet_v1_50`, un-vendored).
+
+Follows, in order:
+  code/models/resnet50_extended_feature_extractor.py:8-51   (base + decrease_fdims)
+  code/models/resnet50_extended_model_hierarchical.py:17-141 (adaptation, logits,
+      upsample, softmax, argmax, hierarchical composition)
+  [TF-1.12] slim resnet_v1 / resnet_utils semantics, SURVEY.md section 3.4 + Appendix A.
+
+Parameters live in a flat dict keyed by the TF variable names
+(`.../weights` HWIO, `.../BatchNorm/{gamma,beta,moving_mean,moving_variance}`).
+"""
+
+import collections
+
+import torch
+
+from oracle import tfops
+from oracle.tables import TABLES
+
+# (block name, base depth, number of units, nominal stride of the block)
+_BLOCKS = [('block1', 64, 3, 2), ('block2', 128, 4, 2), ('block3', 256, 6, 2), ('block4', 512, 3, 1)]
+_RES = 'feature_extractor/base/resnet_v1_50'
+
+
+def conv_specs(dataset='cityscapes', feature_dims_decreased=256):
+  """Ordered {scope: (kh, kw, cin, cout)} for the 66 convs of the default model."""
+  c1, cv, ch = TABLES[dataset]['head_widths']
+  specs = collections.OrderedDict()
+  specs[f'{_RES}/conv1'] = (7, 7, 3, 64)
+  cin = 64
+  for name, base, units, _ in _BLOCKS:
+    for u in range(1, units + 1):
+      sc = f'{_RES}/{name}/unit_{u}/bottleneck_v1'
+      if cin != base * 4:
+        specs[f'{sc}/shortcut'] = (1, 1, cin, base * 4)
+      specs[f'{sc}/conv1'] = (1, 1, cin, base)
+      specs[f'{sc}/conv2'] = (3, 3, base, base)
+      specs[f'{sc}/conv3'] = (1, 1, base, base * 4)
+      cin = base * 4
+  d = feature_dims_decreased
+  specs['feature_extractor/extension/decrease_fdims'] = (1, 1, cin, d)
+  for br in ('l1_features', 'l2_vehicle_features', 'l2_human_features'):
+    sc = f'adaptation_module/{br}/bottleneck_v1'
+    specs[f'{sc}/conv1'] = (1, 1, d, d)
+    specs[f'{sc}/conv2'] = (3, 3, d, d)
+    specs[f'{sc}/conv3'] = (1, 1, d, d)
+  specs['softmax_classifier/l1_logits'] = (1, 1, d, c1)
+  specs['softmax_classifier/l2_vehicle_logits'] = (1, 1, d, cv)
+  specs['softmax_classifier/l2_human_logits'] = (1, 1, d, ch)
+  return specs
+
+
+def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False):
+  """Random init as the reference's arg scope does (variance scaling conv
+  kernels, gamma=1, beta=0, moving_mean=0, moving_var=1;
+  resnet50_extended_model_hierarchical.py:335-340).  `randomize_bn=True`
+  perturbs the BN variables so that tests exercise the BN arithmetic; `tame=True`
+  halves gamma on every residual-branch output / shortcut BN so that activations
+  of the random network stay O(1) through the 16 units (inference-mode BN with
+  moving stats 0/1 is otherwise an identity and the residual sums grow)."""
+  g = torch.Generator().manual_seed(seed)
+  params = collections.OrderedDict()
+  for scope, shape in conv_specs(dataset).items():
+    params[f'{scope}/weights'] = tfops.variance_scaling_trunc_normal(shape, g)
+    c = shape[3]
+    if randomize_bn:
+      params[f'{scope}/BatchNorm/gamma'] = 0.75 + 0.5 * torch.rand(c, generator=g)
+      params[f'{scope}/BatchNorm/beta'] = 0.1 * torch.randn(c, generator=g)
+      params[f'{scope}/BatchNorm/moving_mean'] = 0.1 * torch.randn(c, generator=g)
+      params[f'{scope}/BatchNorm/moving_variance'] = 0.75 + 0.5 * torch.rand(c, generator=g)
+    else:
+      params[f'{scope}/BatchNorm/gamma'] = torch.ones(c)
+      params[f'{scope}/BatchNorm/beta'] = torch.zeros(c)
+      params[f'{scope}/BatchNorm/moving_mean'] = torch.zeros(c)
+      params[f'{scope}/BatchNorm/moving_variance'] = torch.ones(c)
+    if tame and (scope.endswith('/conv3') or scope.endswith('/shortcut')):
+      params[f'{scope}/BatchNorm/gamma'] = params[f'{scope}/BatchNorm/gamma'] * 0.5
+  return params
+
+
+class Net:
+  """Functional forward over a parameter dict.
+
+  training=True uses batch statistics in every BN layer (the reference's
+  `batch_norm_accumulate_statistics`, train.py:45-46) and records the updated
+  moving statistics in `self.new_moving`.
+  """
+
+  def __init__(self, params, dataset='cityscapes', training=False, bn_decay=0.9, eps=1e-5):
+    self.p = params
+    self.dataset = dataset
+    self.training = training
+    self.bn_decay = bn_decay
+    self.eps = eps
+    self.new_moving = {}
+    self.taps = {}
+
+  def _bn(self, x, scope):
+    bn = f'{scope}/BatchNorm'
+    y, mm, mv, _, _ = tfops.batch_norm(
+        x, self.p[f'{bn}/gamma'], self.p[f'{bn}/beta'],
+        self.p[f'{bn}/moving_mean'], self.p[f'{bn}/moving_variance'],
+        self.training, self.bn_decay, self.eps)
+    if self.training:
+      self.new_moving[f'{bn}/moving_mean'] = mm
+      self.new_moving[f'{bn}/moving_variance'] = mv
+    return y
+
+  def _conv_bn(self, x, scope, stride=1, rate=1, relu=True, same_explicit=False):
+    w = self.p[f'{scope}/weights']
+    if same_explicit:
+      y = tfops.conv2d_same(x, w, stride, rate)
+    else:
+      y = tfops.conv2d(x, w, stride, rate, 'SAME')
+    y = self._bn(y, scope)
+    return torch.relu(y) if relu else y
+
+  def _bottleneck(self, x, scope, depth, depth_bottleneck, stride, rate):
+    """slim resnet_v1.bottleneck [TF-1.12]."""
+    if x.shape[-1] == depth:
+      shortcut = x if stride == 1 else tfops.max_pool_same(x, 1, stride)
+    else:
+      shortcut = self._conv_bn(x, f'{scope}/shortcut', stride=stride, relu=False)
+    r = self._conv_bn(x, f'{scope}/conv1')
+    r = self._conv_bn(r, f'{scope}/conv2', stride=stride, rate=rate, same_explicit=True)
+    r = self._conv_bn(r, f'{scope}/conv3', relu=False)
+    return torch.relu(shortcut + r)
+
+  def features(self, images, output_stride=8):
+    """feature_extractor(): base resnet_v1_50(global_pool=False, output_stride)
+    then extension/decrease_fdims.  images: NHWC fp32 in [-1, 1)."""
+    x = self._conv_bn(images, f'{_RES}/conv1', stride=2, same_explicit=True)
+    x = tfops.max_pool_same(x, 3, 2)
+    self.taps['pool1'] = x
+    # stack_blocks_dense: the root counts as stride 4
+    current_stride, rate = 4, 1
+    for name, base, units, block_stride in _BLOCKS:
+      for u in range(1, units + 1):
+        unit_stride = block_stride if u == units else 1
+        sc = f'{_RES}/{name}/unit_{u}/bottleneck_v1'
+        if current_stride == output_stride:
+          x = self._bottleneck(x, sc, base * 4, base, 1, rate)
+          rate *= unit_stride
+        else:
+          x = self._bottleneck(x, sc, base * 4, base, unit_stride, 1)
+          current_stride *= unit_stride
+      self.taps[name] = x
+    x = self._conv_bn(x, 'feature_extractor/extension/decrease_fdims')
+    self.taps['decrease_fdims'] = x
+    return x
+
+  def lowres_logits(self, images):
+    f = self.features(images)
+    d = f.shape[-1]
+    out = []
+    for br, lg in (('l1_features', 'l1_logits'), ('l2_vehicle_features', 'l2_vehicle_logits'),
+                   ('l2_human_features', 'l2_human_logits')):
+      a = self._bottleneck(f, f'adaptation_module/{br}/bottleneck_v1', d, d, 1, 1)
+      # slim.conv2d(activation_fn=None) inside the arg scope: BN still applied
+      out.append(self._conv_bn(a, f'softmax_classifier/{lg}', relu=False))
+    return out
+
+  def forward(self, images):
+    """model(): returns the 10-key predictions dict of
+    resnet50_extended_model_hierarchical.py:121-130 (+ 'lowres_logits')."""
+    hf, wf = images.shape[1], images.shape[2]
+    low = self.lowres_logits(images)
+    t = TABLES[self.dataset]
+    l1, l2v, l2h = [tfops.resize_bilinear(z, hf, wf, align_corners=True) for z in low]
+    pred = compose_predictions(l1, l2v, l2h, self.dataset)
+    pred['lowres_logits'] = low
+    del t
+    return pred
+
+
+def compose_predictions(l1_logits, l2v_logits, l2h_logits, dataset):
+  """softmax x3, argmax-of-probabilities x3, hierarchical composition
+  (resnet50_extended_model_hierarchical.py:88-117)."""
+  t = TABLES[dataset]
+  l1_probs = tfops.softmax(l1_logits)
+  l2v_probs = tfops.softmax(l2v_logits)
+  l2h_probs = tfops.softmax(l2h_logits)
+  l1_decs = tfops.argmax_first(l1_probs)
+  l2v_decs = tfops.argmax_first(l2v_probs)
+  l2h_decs = tfops.argmax_first(l2h_probs)
+  l1_map = torch.tensor(t['l1_cids2common_cids'], dtype=torch.int32)
+  v_map = torch.tensor(t['l2_vehicle_cids2common_cids'], dtype=torch.int32)
+  h_map = torch.tensor(t['l2_human_cids2common_cids'], dtype=torch.int32)
+  decs = torch.where(
+      l1_decs == t['cid_l1_vehicle'], v_map[l2v_decs.long()],
+      torch.where(l1_decs == t['cid_l1_human'], h_map[l2h_decs.long()], l1_map[l1_decs.long()]))
+  return {'l1_logits': l1_logits, 'l1_probabilities': l1_probs, 'l1_decisions': l1_decs,
+          'l2_vehicle_logits': l2v_logits, 'l2_vehicle_probabilities': l2v_probs,
+          'l2_vehicle_decisions': l2v_decs,
+          'l2_human_logits': l2h_logits, 'l2_human_probabilities': l2h_probs,
+          'l2_human_decisions': l2h_decs,
+          'decisions': decs}

@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'iv2019-boosting-semantic-segmentation-with-weak-labels_b200')
+for p in (ROOT, PKG):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+  config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200); run with -m gpu')
+
+
+@pytest.fixture(scope='session')
+def cuda():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+  return torch.device('cuda:0')

@@ -1,0 +1,180 @@
+"""Parity of the convolution kernels with the oracle's conv (TF SAME / conv2d_same semantics).
+
+fp32 direct kernel: 1e-4 relative to max|ref| (north star check mode).
+bf16 kernels (direct and tcgen05 implicit GEMM): inputs are rounded to bf16 first, the oracle
+convolves the rounded values in fp32, outputs must agree within 1e-2 relative to max|ref| (one bf16
+rounding of the output + fp32 accumulation-order noise).
+"""
+
+import pytest
+import torch
+
+from oracle import tfops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x, w_krsc, stride, dilation, scale, shift, res, res_stride, relu):
+  w = w_krsc.permute(1, 2, 3, 0)  # KRSC -> HWIO
+  y = tfops.conv2d_same(x, w, stride, dilation)
+  if scale is not None:
+    y = y * scale + shift
+  if res is not None:
+    y = y + res[:, ::res_stride, ::res_stride][:, :y.shape[1], :y.shape[2]]
+  return torch.relu(y) if relu else y
+
+
+def _run_conv(cuda, N, H, W, C, K, R, stride, dilation, dtype, algo, with_epi=True, res_stride=1, relu=True, seed=0,
+              y_dtype=None):
+  from wlseg import arch, ops
+  g = torch.Generator().manual_seed(seed)
+  x = torch.randn(N, H, W, C, generator=g).to(dtype).float()
+  w = (torch.randn(K, R, R, C, generator=g) / (R * R * C) ** 0.5).to(dtype).float()
+  pt, P = arch.same_pad_before(R, stride, dilation, H)
+  pl, Q = arch.same_pad_before(R, stride, dilation, W)
+  scale = shift = res = None
+  if with_epi:
+    scale = 0.5 + torch.rand(K, generator=g)
+    shift = torch.randn(K, generator=g) * 0.2
+    res = torch.randn(N, P * res_stride, Q * res_stride, K, generator=g).to(dtype).float()
+  ref = _ref_conv(x, w, stride, dilation, scale, shift, res, res_stride, relu)
+  assert ref.shape == (N, P, Q, K)
+  code = ops.dtype_code(dtype)
+  ydt = dtype if y_dtype is None else y_dtype
+  y = torch.full((N, P, Q, K), float('nan'), dtype=ydt, device=cuda)
+  resd = None if res is None else res.to(dtype).to(cuda)
+  prm = ops.conv_params((N, H, W, C), (K, R, R, C), stride=stride, dilation=dilation, pad=(pt, pl), out_hw=(P, Q),
+                        relu=relu, dtype=code, y_dtype=ops.dtype_code(ydt), algo=algo, res=resd, res_stride=res_stride)
+  ops.conv2d_fprop(prm, x.to(dtype).to(cuda), w.to(dtype).to(cuda), y,
+                   None if scale is None else scale.to(cuda), None if shift is None else shift.to(cuda), resd)
+  torch.cuda.synchronize()
+  return y.float().cpu(), ref
+
+
+DIRECT_CASES = [
+    # N, H, W, C, K, R, stride, dilation
+    (1, 9, 11, 3, 8, 7, 2, 1),     # root conv shape class (C=3, 7x7/2)
+    (2, 8, 10, 16, 24, 3, 1, 1),
+    (1, 12, 12, 8, 8, 3, 1, 2),    # dilated
+    (1, 13, 9, 8, 16, 3, 2, 1),    # strided 3x3 on odd sizes
+    (1, 6, 6, 32, 14, 1, 1, 1),    # logits-like 1x1
+]
+
+
+@pytest.mark.parametrize('case', DIRECT_CASES)
+def test_conv_direct_fp32(cuda, case):
+  from wlseg import ops
+  got, ref = _run_conv(cuda, *case, dtype=torch.float32, algo=ops.ALGO_DIRECT)
+  assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('case', DIRECT_CASES[1:])
+def test_conv_direct_bf16(cuda, case):
+  from wlseg import ops
+  got, ref = _run_conv(cuda, *case, dtype=torch.bfloat16, algo=ops.ALGO_DIRECT)
+  assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+
+
+TC_CASES = [
+    # N, H, W, C, K, R, stride, dilation
+    (1, 8, 16, 64, 64, 1, 1, 1),       # one tile, one K block
+    (2, 16, 32, 64, 64, 3, 1, 1),      # 3x3: TMA zero-fill is the padding
+    (1, 16, 16, 128, 256, 1, 1, 1),    # BN = 256
+    (1, 24, 40, 256, 128, 3, 1, 2),    # dilation 2 (block3)
+    (1, 16, 24, 128, 128, 3, 1, 4),    # dilation 4 (block4)
+    (1, 13, 19, 64, 96, 3, 1, 1),      # ragged spatial size, K not a multiple of the tile
+    (1, 12, 20, 32, 24, 1, 1, 1),      # C < 64 (zero-filled K block), K = 24 (BN = 32, scalar stores)
+    (1, 32, 32, 64, 64, 3, 2, 1),      # stride 2 via TMA element strides (block1/unit_3/conv2)
+    (1, 17, 23, 64, 64, 3, 2, 1),      # stride 2, odd sizes
+    (3, 8, 16, 512, 2048, 1, 1, 1),    # many N tiles, deep K
+    (1, 4, 4, 64, 64, 3, 1, 1),        # tiny image (TW = 4)
+    (1, 1, 200, 64, 64, 1, 1, 1),      # P == 1 (TW = 128)
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_conv_tcgen05_bf16(cuda, case):
+  from wlseg import ops
+  got, ref = _run_conv(cuda, *case, dtype=torch.bfloat16, algo=ops.ALGO_TCGEN05, seed=sum(case))
+  assert not torch.isnan(got).any(), 'some outputs were never written'
+  assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+
+
+def test_conv_tcgen05_plain_and_strided_residual(cuda):
+  from wlseg import ops
+  got, ref = _run_conv(cuda, 1, 16, 32, 64, 128, 1, 1, 1, dtype=torch.bfloat16, algo=ops.ALGO_TCGEN05,
+                       with_epi=False, relu=False)
+  assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+  got, ref = _run_conv(cuda, 1, 16, 32, 64, 128, 1, 1, 1, dtype=torch.bfloat16, algo=ops.ALGO_TCGEN05,
+                       res_stride=2)
+  assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+
+
+def test_conv_tcgen05_fp32_output(cuda):
+  from wlseg import ops
+  got, ref = _run_conv(cuda, 1, 8, 16, 256, 14, 1, 1, 1, dtype=torch.bfloat16, algo=ops.ALGO_TCGEN05,
+                       with_epi=False, relu=False, y_dtype=torch.float32)
+  assert float((got - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+def test_conv_tcgen05_fused_bn_statistics(cuda):
+  from wlseg import arch, ops
+  g = torch.Generator().manual_seed(5)
+  N, H, W, C, K = 2, 13, 17, 64, 96
+  x = torch.randn(N, H, W, C, generator=g).to(torch.bfloat16)
+  w = (torch.randn(K, 3, 3, C, generator=g) / 24).to(torch.bfloat16)
+  pt, P = arch.same_pad_before(3, 1, 1, H)
+  y = torch.empty((N, H, W, K), dtype=torch.bfloat16, device=cuda)
+  s1 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  s2 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  prm = ops.conv_params((N, H, W, C), (K, 3, 3, C), pad=(pt, pt), out_hw=(H, W), dtype=ops.BF16, algo=ops.ALGO_TCGEN05)
+  ops.conv2d_fprop(prm, x.to(cuda), w.to(cuda), y, bn_sum=s1, bn_sqsum=s2)
+  torch.cuda.synchronize()
+  ref = tfops.conv2d_same(x.float(), w.float().permute(1, 2, 3, 0), 1, 1)
+  assert torch.allclose(s1.float().cpu(), ref.sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+  assert torch.allclose(s2.float().cpu(), (ref ** 2).sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize('case', [(2, 8, 10, 16, 24, 3, 1, 1), (1, 13, 9, 8, 16, 3, 2, 1), (1, 12, 12, 8, 8, 3, 1, 2),
+                                  (1, 9, 11, 3, 8, 7, 2, 1)])
+def test_conv_direct_backward_fp32(cuda, case):
+  from wlseg import arch, ops
+  N, H, W, C, K, R, stride, dilation = case
+  g = torch.Generator().manual_seed(4)
+  x = torch.randn(N, H, W, C, generator=g, requires_grad=True)
+  w = (torch.randn(K, R, R, C, generator=g) / (R * R * C) ** 0.5).requires_grad_(True)
+  y = tfops.conv2d_same(x, w.permute(1, 2, 3, 0), stride, dilation)
+  dy = torch.randn(y.shape, generator=g)
+  y.backward(dy)
+  pt, P = arch.same_pad_before(R, stride, dilation, H)
+  pl, Q = arch.same_pad_before(R, stride, dilation, W)
+  prm = ops.conv_params((N, H, W, C), (K, R, R, C), stride=stride, dilation=dilation, pad=(pt, pl), out_hw=(P, Q),
+                        dtype=ops.F32, algo=ops.ALGO_DIRECT)
+  dx = torch.full((N, H, W, C), float('nan'), device=cuda)
+  dw = torch.full((K, R, R, C), float('nan'), device=cuda)
+  ops.conv2d_dgrad(prm, dy.to(cuda), w.detach().to(cuda), dx)
+  ops.conv2d_wgrad(prm, x.detach().to(cuda), dy.to(cuda), dw)
+  torch.cuda.synchronize()
+  assert float((dx.cpu() - x.grad).abs().max()) <= 1e-4 * float(x.grad.abs().max())
+  assert float((dw.cpu() - w.grad).abs().max()) <= 1e-4 * float(w.grad.abs().max())
+
+
+def test_dgrad_as_flipped_fprop_tcgen05(cuda):
+  """Stride-1 dgrad runs on the tensor cores as an fprop over dy with the rotated, transposed bank."""
+  from wlseg import arch, ops
+  g = torch.Generator().manual_seed(8)
+  N, H, W, C, K, R, dil = 1, 16, 24, 64, 128, 3, 2
+  x = torch.randn(N, H, W, C, generator=g, requires_grad=True)
+  w = (torch.randn(K, R, R, C, generator=g) / 24).to(torch.bfloat16).float().requires_grad_(True)
+  y = tfops.conv2d_same(x, w.permute(1, 2, 3, 0), 1, dil)
+  dy = torch.randn(y.shape, generator=g).to(torch.bfloat16).float()
+  y.backward(dy)
+  wf = torch.empty((C, R, R, K), dtype=torch.bfloat16, device=cuda)
+  ops.weights_transpose_flip(w.detach().to(torch.bfloat16).to(cuda), wf)
+  pad = dil * (R - 1) - arch.same_pad_before(R, 1, dil, H)[0]
+  prm = ops.conv_params((N, H, W, K), (C, R, R, K), dilation=dil, pad=(pad, pad), out_hw=(H, W), dtype=ops.BF16,
+                        algo=ops.ALGO_TCGEN05)
+  dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=cuda)
+  ops.conv2d_fprop(prm, dy.to(torch.bfloat16).to(cuda), wf, dx)
+  torch.cuda.synchronize()
+  assert float((dx.float().cpu() - x.grad).abs().max()) <= 1e-2 * float(x.grad.abs().max())

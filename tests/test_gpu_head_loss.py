@@ -1,0 +1,169 @@
+"""Parity of the fused head-forward and loss forward/backward kernels with the oracle.
+
+Tolerances (floating point, fp32 kernels): 1e-4 relative on logits / probabilities / losses
+(north star fp32 check mode); decisions must agree except at numerical near-ties, which the
+seeded inputs do not contain (asserted exactly); gradients: cosine >= 0.99999 and 1e-4 relative.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import network as onet
+from oracle import tfops
+from oracle import weak_labels as oweak
+from oracle.tables import TABLES
+
+pytestmark = pytest.mark.gpu
+
+
+def _hier(dataset):
+  from wlseg import hierarchy, problem_defs
+  return hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+
+
+def _lowres(hier, N, h, w, seed, scale=3.0):
+  g = torch.Generator().manual_seed(seed)
+  ct = hier.total_channels
+  logits = torch.zeros(N, h, w, hier.logits_pitch)
+  logits[..., :ct] = torch.randn(N, h, w, ct, generator=g) * scale
+  return logits
+
+
+def _split(hier, t):
+  c1, cv, ch = hier.head_widths
+  return t[..., :c1], t[..., c1:c1 + cv], t[..., c1 + cv:c1 + cv + ch]
+
+
+@pytest.mark.parametrize('dataset,N,h,w,H,W', [
+    ('cityscapes', 2, 8, 16, 64, 128),
+    ('cityscapes', 1, 7, 9, 50, 70),       # ragged: not a multiple of the tile, odd scale
+    ('vistas', 1, 9, 12, 68, 95),
+    ('cityscapes', 1, 4, 4, 4, 4),         # identity resize
+])
+def test_head_fwd_matches_oracle(cuda, dataset, N, h, w, H, W):
+  from wlseg import network
+  hier = _hier(dataset)
+  logits = _lowres(hier, N, h, w, seed=h * 100 + W)
+  want_keys = ('decisions', 'l1_decisions', 'l2_vehicle_decisions', 'l2_human_decisions', 'l1_probabilities',
+               'l2_vehicle_probabilities', 'l2_human_probabilities', 'logits')
+  net = network.Network.__new__(network.Network)
+  net.hier, net.hstruct, net.dev = hier, hier.as_struct(), cuda
+  got = net.head(logits.to(cuda), H, W, want_keys)
+  torch.cuda.synchronize()
+  l1, l2v, l2h = [tfops.resize_bilinear(z.contiguous(), H, W) for z in _split(hier, logits)]
+  ref = onet.compose_predictions(l1, l2v, l2h, dataset)
+  for key in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits', 'l1_probabilities', 'l2_vehicle_probabilities',
+              'l2_human_probabilities'):
+    a, b = got[key].cpu(), ref[key]
+    assert a.shape == b.shape
+    assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max())), key
+  for key in ('decisions', 'l1_decisions', 'l2_vehicle_decisions', 'l2_human_decisions'):
+    assert torch.equal(got[key].cpu(), ref[key]), key
+
+
+def test_head_argmax_first_index_on_ties(cuda):
+  from wlseg import network
+  hier = _hier('cityscapes')
+  logits = torch.zeros(1, 2, 2, hier.logits_pitch)  # all-equal logits: every head must answer 0
+  net = network.Network.__new__(network.Network)
+  net.hier, net.hstruct, net.dev = hier, hier.as_struct(), cuda
+  got = net.head(logits.to(cuda), 16, 16, ('decisions', 'l1_decisions', 'l2_vehicle_decisions'))
+  assert int(got['l1_decisions'].abs().sum()) == 0 and int(got['l2_vehicle_decisions'].abs().sum()) == 0
+  assert int((got['decisions'] != hier.l1_2common[0]).sum()) == 0
+
+
+def _weak_labels(rng, n, H, W, kind):
+  out = np.zeros((n, H, W, 15), dtype=np.float32)
+  for i in range(n):
+    if kind == 'bbox':
+      boxes = []
+      for _ in range(int(rng.integers(1, 8))):
+        x0, x1 = sorted(rng.random(2))
+        y0, y1 = sorted(rng.random(2))
+        boxes.append((int(rng.integers(0, 14)), x0, min(x1, 0.999), y0, min(y1, 0.999)))
+      out[i] = oweak.bbox_labels(boxes, H, W)
+    else:
+      cids = list(rng.choice(14, size=int(rng.integers(0, 4)), replace=False))
+      out[i] = oweak.image_labels(cids, H, W)
+  return torch.from_numpy(out)
+
+
+@pytest.mark.parametrize('dataset,ns,nb,ni,h,w,H,W', [
+    ('cityscapes', 2, 0, 0, 8, 12, 64, 96),
+    ('cityscapes', 1, 2, 1, 6, 20, 45, 150),     # mixed strong + bbox + image, ragged tile edges
+    ('vistas', 1, 1, 1, 5, 7, 40, 56),
+    ('cityscapes', 0, 1, 1, 4, 6, 32, 48),       # weak only: L1 loss must be exactly 0
+])
+def test_loss_fwd_bwd_matches_oracle(cuda, dataset, ns, nb, ni, h, w, H, W):
+  from wlseg import ops
+  hier = _hier(dataset)
+  hs = hier.as_struct()
+  B = ns + nb + ni
+  rng = np.random.default_rng(h * 31 + W)
+  logits = _lowres(hier, B, h, w, seed=H + w, scale=2.0)
+  ncls = TABLES[dataset]['num_classes']
+  strong = torch.from_numpy(rng.integers(0, ncls, size=(ns, H, W), dtype=np.int32))
+  # make the vehicle / human classes frequent enough to matter
+  strong[:, : H // 3] = int(np.flatnonzero(np.array(hier.pp2veh) != hier.Cv - 1)[0])
+  bbox = _weak_labels(rng, nb, H, W, 'bbox')
+  image = _weak_labels(rng, ni, H, W, 'image')
+
+  # ---- oracle: upsample -> predictions -> losses, autograd back to the low-res logits
+  low = logits[..., :hier.total_channels].clone().requires_grad_(True)
+  l1, l2v, l2h = [tfops.resize_bilinear(z, H, W) for z in _split(hier, low)]
+  pred = {'l1_logits': l1, 'l2_vehicle_logits': l2v, 'l2_human_logits': l2h,
+          'l1_decisions': tfops.argmax_first(tfops.softmax(l1.detach()))}
+  labels = {'prolabels_per_pixel': strong, 'prolabels_per_bbox': bbox, 'prolabels_per_image': image}
+  if ns == 0:
+    # the reference always has strong images; restate the weak-only limit with an empty strong part
+    labels['prolabels_per_pixel'] = torch.zeros(0, H, W, dtype=torch.int32)
+  ref = olosses.define_losses(pred, labels, dataset)
+  ref['segmentation'].backward()
+
+  # ---- kernels
+  dl = torch.zeros(B, h, w, hier.logits_pitch, device=cuda)
+  sums = torch.zeros(3, dtype=torch.float64, device=cuda)
+  counts = torch.zeros(3, dtype=torch.float64, device=cuda)
+  out = torch.zeros(4, device=cuda)
+  ops.loss_fwd_bwd(hs, logits.to(cuda), H, W, strong.to(cuda) if ns else None, bbox.to(cuda) if nb else None,
+                   image.to(cuda) if ni else None, sums, counts, dl)
+  ops.loss_finalize(hs, sums, counts, 0.1, 1.0, dl, out)
+  torch.cuda.synchronize()
+  got = out.cpu()
+  want = torch.stack([ref['l1_segmentation'], ref['l2_vehicle_segmentation'], ref['l2_human_segmentation'],
+                      ref['segmentation']]).detach()
+  cnt = counts.cpu()
+  assert cnt[0] == ref['counts']['l1'] and cnt[1] == ref['counts']['l2_vehicle'] and cnt[2] == ref['counts']['l2_human']
+  assert torch.allclose(got, want, rtol=1e-4, atol=1e-6), (got, want)
+  if ns == 0:
+    assert got[0] == 0
+  g = dl.cpu()[..., :hier.total_channels]
+  assert float(dl.cpu()[..., hier.total_channels:].abs().max() if hier.logits_pitch > hier.total_channels else 0) == 0
+  gr = low.grad
+  assert float((g - gr).abs().max()) <= 1e-4 * float(gr.abs().max()) + 1e-9
+  cos = float((g * gr).sum() / (g.norm() * gr.norm() + 1e-30))
+  assert cos >= 0.99999
+
+
+def test_loss_known_answer_segment_sum(cuda):
+  """Worked example of define_losses_hierarchical.py:112-113: a pixel inside one human box and
+  one vehicle box gives the vehicle head the target 1/2 vehicle-class + 1/2 void; with the L1
+  argmax on 'vehicle' the pixel is supervised by the vehicle head only."""
+  from wlseg import ops
+  hier = _hier('cityscapes')
+  hs = hier.as_struct()
+  H = W = 8
+  lab = oweak.bbox_labels([(2, 0.0, 0.999, 0.0, 0.999), (6, 0.0, 0.999, 0.0, 0.999)], H, W)  # car + human
+  assert np.allclose(lab[0, 0, [2, 6]], 0.5)
+  logits = torch.zeros(1, 1, 1, hier.logits_pitch)
+  logits[..., hier.cid_l1_vehicle] = 5.0
+  dl = torch.zeros_like(logits, device=cuda)
+  sums = torch.zeros(3, dtype=torch.float64, device=cuda)
+  counts = torch.zeros(3, dtype=torch.float64, device=cuda)
+  ops.loss_fwd_bwd(hs, logits.to(cuda), H, W, None, torch.from_numpy(lab)[None].to(cuda), None, sums, counts, dl)
+  torch.cuda.synchronize()
+  assert counts.cpu().tolist() == [0.0, float(H * W), 0.0]
+  # uniform vehicle logits: CE = -(1/2 log(1/7) + 1/2 log(1/7)) = log 7 per pixel
+  assert abs(float(sums[1]) / (H * W) - np.log(7.0)) < 1e-5

@@ -1,0 +1,138 @@
+"""Parity of the bandwidth kernels (max-pool, batch-norm train fwd/bwd, SGD-momentum, packing)
+with the oracle's TF-1.12 restatements.  fp32 storage: 1e-5 relative; bf16 storage: one bf16 ulp
+of the fp32 result (values are compared after rounding the oracle result to bf16)."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import optimizer as oopt
+from oracle import tfops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('shape,k,s', [((2, 12, 16, 64), 3, 2), ((1, 9, 7, 8), 3, 2), ((1, 8, 8, 16), 1, 2)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_maxpool_same_fwd_bwd(cuda, shape, k, s, dtype):
+  from wlseg import ops
+  g = torch.Generator().manual_seed(1)
+  x = torch.randn(shape, generator=g).to(dtype).float()
+  x[0, :4, :4] = 0.0  # ties (post-ReLU zeros): gradient must go to the first maximum
+  xr = x.clone().requires_grad_(True)
+  yr = tfops.max_pool_same(xr, k, s)
+  N, P, Q, C = yr.shape
+  y = torch.empty((N, P, Q, C), dtype=dtype, device=cuda)
+  xd = x.to(dtype).to(cuda)
+  ops.maxpool_same_fwd(xd, y, k, s)
+  assert torch.equal(y.float().cpu(), yr.detach())
+  dy = torch.randn(yr.shape, generator=g).to(dtype).float()
+  yr.backward(dy)
+  dx = torch.empty_like(xd)
+  ops.maxpool_same_bwd(xd, dy.to(dtype).to(cuda), dx, k, s)
+  torch.cuda.synchronize()
+  want = xr.grad
+  tol = 0 if dtype == torch.float32 else 2e-2
+  assert float((dx.float().cpu() - want).abs().max()) <= tol * float(want.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize('C', [64, 24, 256])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_batch_norm_train_fwd_bwd(cuda, C, dtype):
+  from wlseg import ops
+  g = torch.Generator().manual_seed(C)
+  N, H, W = 2, 9, 11
+  count = N * H * W
+  z = (torch.randn(N, H, W, C, generator=g) * 2 + 0.5).to(dtype).float()
+  res = torch.randn(N, H, W, C, generator=g).to(dtype).float()
+  gamma = 0.5 + torch.rand(C, generator=g)
+  beta = torch.randn(C, generator=g) * 0.1
+  mm = torch.randn(C, generator=g) * 0.1
+  mv = 0.5 + torch.rand(C, generator=g)
+  zr = z.clone().requires_grad_(True)
+  rr = res.clone().requires_grad_(True)
+  gr = gamma.clone().requires_grad_(True)
+  br = beta.clone().requires_grad_(True)
+  y_bn, new_mm, new_mv, mean, var = tfops.batch_norm(zr, gr, br, mm, mv, True, decay=0.9, eps=1e-5)
+  yr = torch.relu(y_bn + rr)
+  dy = torch.randn(N, H, W, C, generator=g).to(dtype).float()
+  yr.backward(dy)
+
+  dev = cuda
+  zd, resd = z.to(dtype).to(dev), res.to(dtype).to(dev)
+  s1 = torch.zeros(C, dtype=torch.float64, device=dev)
+  s2 = torch.zeros(C, dtype=torch.float64, device=dev)
+  ops.bn_stats(zd, count, C, C, s1, s2)
+  gd, bd, mmd, mvd = gamma.to(dev), beta.to(dev), mm.to(dev), mv.to(dev)
+  scale, shift = torch.empty(C, device=dev), torch.empty(C, device=dev)
+  smean, sinv = torch.empty(C, device=dev), torch.empty(C, device=dev)
+  ops.bn_finalize(s1, s2, count, C, gd, bd, 1e-5, 0.9, mmd, mvd, scale, shift, smean, sinv)
+  y = torch.empty_like(zd)
+  ops.bn_apply(zd, scale, shift, resd, y, count, C, True)
+  torch.cuda.synchronize()
+  assert torch.allclose(smean.cpu(), mean.detach(), rtol=1e-5, atol=1e-6)
+  assert torch.allclose(sinv.cpu(), torch.rsqrt(var.detach() + 1e-5), rtol=1e-5)
+  assert torch.allclose(mmd.cpu(), new_mm, rtol=1e-5, atol=1e-6)
+  assert torch.allclose(mvd.cpu(), new_mv, rtol=1e-5, atol=1e-6)
+  tol = 1e-5 if dtype == torch.float32 else 1e-2
+  assert float((y.float().cpu() - yr.detach()).abs().max()) <= tol * float(yr.abs().max())
+
+  dgm = torch.zeros(C, dtype=torch.float64, device=dev)
+  dbt = torch.zeros(C, dtype=torch.float64, device=dev)
+  dyd = dy.to(dtype).to(dev)
+  # the mask uses the oracle's activation so that bf16 rounding of y cannot flip it
+  yact = yr.detach().to(dtype).to(dev)
+  ops.bn_bwd_reduce(dyd, yact, zd, smean, sinv, count, C, True, dgm, dbt)
+  dz, dres = torch.empty_like(zd), torch.empty_like(zd)
+  ops.bn_bwd_apply(dyd, yact, zd, smean, sinv, gd, dgm, dbt, count, C, True, dz, dres)
+  torch.cuda.synchronize()
+  assert torch.allclose(dgm.float().cpu(), gr.grad, rtol=1e-4, atol=1e-4)
+  assert torch.allclose(dbt.float().cpu(), br.grad, rtol=1e-4, atol=1e-4)
+  assert float((dz.float().cpu() - zr.grad).abs().max()) <= tol * float(zr.grad.abs().max()) + 1e-6
+  assert float((dres.float().cpu() - rr.grad).abs().max()) <= tol * float(rr.grad.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize('nesterov', [False, True])
+def test_sgdm_matches_momentum_optimizer(cuda, nesterov):
+  from wlseg import ops
+  g = torch.Generator().manual_seed(9)
+  n, n_decay = 1003, 640
+  w = torch.randn(n, generator=g)
+  acc = torch.randn(n, generator=g) * 0.1
+  grad = torch.randn(n, generator=g)
+  wd, lr, mom = 1.7e-4, 0.01, 0.9
+  gfull = grad.clone()
+  gfull[:n_decay] += wd * w[:n_decay]
+  w_ref, acc_ref = oopt.momentum_step(w, gfull, acc, lr, mom, nesterov)
+  reg_ref = 0.5 * wd * float((w[:n_decay].double() ** 2).sum())
+  wdv, accd, gd = w.clone().to(cuda), acc.clone().to(cuda), grad.to(cuda)
+  wb = torch.zeros(n, dtype=torch.bfloat16, device=cuda)
+  lr_dev = torch.tensor([lr], device=cuda)
+  reg = torch.zeros(1, dtype=torch.float64, device=cuda)
+  ops.sgdm_step(wdv, gd, accd, wb, n_decay, lr_dev, mom, nesterov, wd, 1.0, reg)
+  torch.cuda.synchronize()
+  assert torch.allclose(wdv.cpu(), w_ref, rtol=1e-6, atol=1e-7)
+  assert torch.allclose(accd.cpu(), acc_ref, rtol=1e-6, atol=1e-7)
+  assert torch.equal(wb.cpu(), wdv.cpu().to(torch.bfloat16))
+  assert abs(float(reg) - reg_ref) <= 1e-6 * reg_ref
+
+
+def test_conv1_pack_is_exact_rewrite(cuda):
+  """The packed R=4,S=1,C=64 convolution equals the 7x7 stride-2 `conv2d_same` (fp64 check on CPU
+  of the index map: pack on the GPU, convolve the packed tensor with the rewritten kernel)."""
+  from wlseg import hierarchy, network, ops, problem_defs
+  g = torch.Generator().manual_seed(2)
+  N, H, W = 1, 20, 26
+  img = torch.rand(N, H, W, 3, generator=g) * 2 - 1
+  img = img.to(torch.bfloat16).float()
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  params = network.Params(hier, cuda)
+  params.init_random(3)
+  packed = torch.empty((N, H // 2, W // 2, 64), dtype=torch.bfloat16, device=cuda)
+  ops.conv1_pack(img.to(cuda), packed)
+  w2 = params.conv1_packed_weights(torch.float32).cpu()          # [64, 4, 1, 64]
+  w = params.w32('feature_extractor/base/resnet_v1_50/conv1').cpu()  # [64, 7, 7, 3] KRSC
+  ref = tfops.conv2d_same(img.double(), w.permute(1, 2, 3, 0).double(), 2)
+  got = tfops.conv2d(packed.float().cpu().double(), w2.permute(1, 2, 3, 0).double(), 1, 1, (2, 1, 0, 0))
+  assert got.shape == ref.shape
+  assert float((got - ref).abs().max()) < 1e-9

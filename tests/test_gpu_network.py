@@ -1,0 +1,82 @@
+"""End-to-end parity of the forward path (extractor -> heads -> decisions -> confusion matrix)
+with the oracle on identical inputs and weights.
+
+Tolerances (north star): low-res logits within 2e-2 relative (bf16 product path) and 1e-4 (fp32
+check mode), measured as max|a-b|/max|b| and as relative L2; decisions: disagreement rate reported
+and bounded (near-ties flip under bf16); confusion matrix bit-exact given identical decisions.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as ometrics
+from oracle import network as onet
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cuda, dataset, dtype, seed=0):
+  from wlseg import hierarchy, network, problem_defs
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  tf_params = onet.init_params(dataset, seed=seed, randomize_bn=True, tame=True)
+  params = network.Params(hier, cuda)
+  params.load_tf_dict(tf_params)
+  return hier, tf_params, network.Network(params, dtype=dtype)
+
+
+def _errors(got, ref):
+  return float((got - ref).abs().max() / ref.abs().max()), float((got - ref).norm() / ref.norm())
+
+
+@pytest.mark.parametrize('dataset,shape', [('cityscapes', (1, 64, 128)), ('cityscapes', (2, 72, 88)),
+                                           ('vistas', (1, 56, 104))])
+def test_forward_bf16_matches_oracle(cuda, dataset, shape):
+  hier, tf_params, net = _setup(cuda, dataset, torch.bfloat16)
+  N, H, W = shape
+  g = torch.Generator().manual_seed(H)
+  images = torch.rand(N, H, W, 3, generator=g) * 2 - 1
+  out = net.predict(images.to(cuda), want=('decisions', 'l1_probabilities'))
+  torch.cuda.synchronize()
+  oracle = onet.Net(tf_params, dataset)
+  ref = oracle.forward(images)
+  ref_low = torch.cat(ref['lowres_logits'], -1)
+  got_low = out['lowres_logits'][..., :hier.total_channels].cpu()
+  emax, el2 = _errors(got_low, ref_low)
+  print(f'{dataset} {shape}: low-res logits max-rel {emax:.3e} rel-L2 {el2:.3e}')
+  assert emax <= 2e-2 and el2 <= 2e-2
+  dis = float((out['decisions'].cpu() != ref['decisions']).float().mean())
+  print(f'decision disagreement rate {dis:.4f}')
+  assert dis <= 0.05
+  assert float((out['l1_probabilities'].cpu() - ref['l1_probabilities']).abs().max()) <= 5e-2
+
+
+def test_forward_fp32_check_mode(cuda):
+  hier, tf_params, net = _setup(cuda, 'cityscapes', torch.float32, seed=1)
+  g = torch.Generator().manual_seed(3)
+  images = torch.rand(1, 48, 64, 3, generator=g) * 2 - 1
+  out = net.predict(images.to(cuda), want=('decisions', 'l1_probabilities', 'logits'))
+  torch.cuda.synchronize()
+  ref = onet.Net(tf_params, 'cityscapes').forward(images)
+  ref_low = torch.cat(ref['lowres_logits'], -1)
+  emax, el2 = _errors(out['lowres_logits'][..., :hier.total_channels].cpu(), ref_low)
+  print(f'fp32 check mode: low-res logits max-rel {emax:.3e} rel-L2 {el2:.3e}')
+  assert emax <= 1e-4 and el2 <= 1e-4
+  emax, _ = _errors(out['l1_logits'].cpu(), ref['l1_logits'])
+  assert emax <= 1e-4
+  assert float((out['decisions'].cpu() != ref['decisions']).float().mean()) <= 1e-3
+
+
+def test_eval_confusion_matrix_bit_exact_given_decisions(cuda):
+  """decisions -> cm through the kernel equals the oracle histogram on the SAME decisions."""
+  from wlseg import ops
+  hier, tf_params, net = _setup(cuda, 'cityscapes', torch.bfloat16, seed=2)
+  g = torch.Generator().manual_seed(11)
+  images = torch.rand(2, 64, 96, 3, generator=g) * 2 - 1
+  labels = torch.randint(0, 20, (2, 64, 96), generator=g, dtype=torch.int32)
+  out = net.predict(images.to(cuda))
+  cm = torch.zeros(20, 20, dtype=torch.int64, device=cuda)
+  ops.confmat_accumulate(labels.to(cuda), out['decisions'], 20, cm)
+  torch.cuda.synchronize()
+  want = ometrics.confusion_matrix(labels.numpy(), out['decisions'].cpu().numpy(), 20)
+  assert np.array_equal(cm.cpu().numpy(), want)
