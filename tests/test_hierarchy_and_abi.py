@@ -1,0 +1,85 @@
+"""Host-side checks that need no GPU: derived hierarchy tables vs the reference's literals,
+problem-definition JSON, and that the C-ABI library loads and exports every declared symbol."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+from oracle.tables import TABLES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('dataset', ['cityscapes', 'vistas'])
+def test_derived_hierarchy_equals_reference_literals(dataset):
+  from wlseg import hierarchy, problem_defs
+  pd = problem_defs.GENERATORS[dataset]()
+  h = hierarchy.Hierarchy(dataset, pd['cids2labels'])
+  t = TABLES[dataset]
+  assert h.pp2l1 == t['per_pixel_cids2l1_cids']
+  assert h.pp2veh == t['per_pixel_cids2vehicle_cids']
+  assert h.pp2hum == t['per_pixel_cids2human_cids']
+  assert h.bb2veh == t['per_bbox_cids2vehicle_cids']
+  assert h.bb2hum == t['per_bbox_cids2human_cids']
+  assert h.bb2l1 == t['per_bbox_cids2l1_cids']
+  assert h.l1_2common == t['l1_cids2common_cids']
+  assert h.veh2common == t['l2_vehicle_cids2common_cids']
+  assert h.hum2common == t['l2_human_cids2common_cids']
+  assert h.head_widths == t['head_widths']
+  assert (h.cid_l1_vehicle, h.cid_l1_human) == (t['cid_l1_vehicle'], t['cid_l1_human'])
+  s = h.as_struct()
+  assert (s.C1, s.Cv, s.Ch) == t['head_widths'] and s.num_classes == t['num_classes']
+  assert list(s.pp_to_l1)[:t['num_classes']] == t['per_pixel_cids2l1_cids']
+  assert h.logits_pitch % 8 == 0 and h.logits_pitch >= h.total_channels
+
+
+def test_problem_definitions_schema_and_counts():
+  from wlseg import problem_defs
+  c = problem_defs.cityscapes()
+  assert len(c['lids2cids']) == 34 and max(c['lids2cids']) == 18 and c['lids2cids'].count(-1) == 15
+  assert c['cids2labels'][-1] == 'void' and len(c['cids2labels']) == 20 == len(c['cids2colors']) == len(c['cids2lids'])
+  assert c['cids2lids'][:3] == [7, 8, 11]
+  v = problem_defs.vistas()
+  assert len(v['lids2cids']) == 66 and v['lids2cids'][-1] == -1 and len(v['cids2labels']) == 66
+  for path in problem_defs.write_all():
+    assert problem_defs.load(path)['version'] == 2.0
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+  """No compute calls (no GPU here): dlopen + symbol table vs include/wlseg.h."""
+  from wlseg import ops
+  header = open(os.path.join(ROOT, 'include', 'wlseg.h')).read()
+  declared = set(re.findall(r'\b(wlseg_[a-z0-9_]+)\s*\(', header))
+  declared -= {'wlseg_conv_params', 'wlseg_hierarchy', 'wlseg_stream_t'}
+  assert declared == set(ops.EXPORTED_SYMBOLS), declared ^ set(ops.EXPORTED_SYMBOLS)
+  lib = ops.lib()
+  for name in declared:
+    assert getattr(lib, name) is not None
+  assert lib.wlseg_version() == 100
+  assert ctypes.sizeof(ops.Hierarchy) == 4 * (5 + 64 + 16 + 8 + 1 + 240 + 30)
+  assert ctypes.sizeof(ops.ConvParams) == 4 * 23
+
+
+def test_invalid_arguments_are_reported_not_crashed():
+  """Argument validation happens before any CUDA call, so it is testable without a GPU."""
+  from wlseg import ops
+  lib = ops.lib()
+  rc = lib.wlseg_confmat_accumulate(None, None, 10, 0, None, 0, None, None, None)
+  assert rc < 0 and b'cm is NULL' in lib.wlseg_last_error()
+  rc = lib.wlseg_confmat_accumulate(None, None, 10, 500, None, 0, 1, None, None)
+  assert rc < 0 and b'num_classes' in lib.wlseg_last_error()
+  p = ops.ConvParams()
+  rc = lib.wlseg_conv2d_fprop(ctypes.byref(p), None, None, None, None, None, None, None, None, None)
+  assert rc < 0 and b'bad shape' in lib.wlseg_last_error()
+  assert lib.wlseg_conv2d_tcgen05_supported(ctypes.byref(p)) in (0, 1)
+
+
+def test_product_does_not_import_the_oracle():
+  pkg = os.path.join(ROOT, 'iv2019-boosting-semantic-segmentation-with-weak-labels_b200', 'wlseg')
+  for dirpath, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith('.py'):
+        src = open(os.path.join(dirpath, f)).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f'{f} imports the oracle'

@@ -7,7 +7,7 @@ python __graft_entry__.py > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; ta
 rc_all=0
 for f in ${@:-tests/test_gpu_confmat.py tests/test_gpu_head_loss.py tests/test_gpu_misc.py tests/test_gpu_conv.py tests/test_gpu_network.py}; do
   name=$(basename $f .py)
-  timeout 600 python -m pytest $f -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  timeout 600 python -m pytest $f -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/$name.log 2>&1
   rc=$?
   echo "== $f rc=$rc"; tail -25 gpurun_out/$name.log
   [ $rc -ne 0 ] && rc_all=1
