@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the wlseg hot path (contract: see the task statement).
+
+Workload (BASELINE.json configs[1]): Cityscapes-shaped evaluation -- ResNet-50 OS8 forward +
+hierarchical heads + argmax + confusion matrix at 1024x2048, batch 4 per step, synthetic images
+and labels, random-init weights, bf16 tensor-core convolutions.  Metric: eval Mpix/s.
+
+  python bench.py --gpus N --steps K --warmup W          # this implementation
+  python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host CPU
+                                                         # (oracle port; TF 1.12 is uninstallable)
+  python bench.py --workload train ...                   # training images/s @768x768 (secondary)
+
+One JSON line is printed by rank 0.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'iv2019-boosting-semantic-segmentation-with-weak-labels_b200')
+for _p in (ROOT, PKG):
+  if _p not in sys.path:
+    sys.path.insert(0, _p)
+
+EVAL_H, EVAL_W, EVAL_NB = 1024, 2048, 4
+TRAIN_H, TRAIN_W, TRAIN_NB = 768, 768, 4
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', type=str, default='wlseg', choices=['wlseg', 'reference'])
+  ap.add_argument('--workload', type=str, default='eval', choices=['eval', 'train'])
+  ap.add_argument('--dataset', type=str, default='cityscapes', choices=['cityscapes', 'vistas'])
+  ap.add_argument('--height', type=int, default=None)
+  ap.add_argument('--width', type=int, default=None)
+  ap.add_argument('--batch', type=int, default=None)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--detail', type=str, default=None, help='write the per-kernel-class roofline table here')
+  return ap.parse_args()
+
+
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as fp:
+      p = json.load(fp)
+    return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'],
+            'bf16_tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'source': 'measured'}
+  return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index=0):
+    self.file = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+    self.proc = None
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                    '-i', str(index), '-lms', '100'], stdout=self.file, stderr=subprocess.DEVNULL)
+    except OSError:
+      self.proc = None
+
+  def stop(self):
+    out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+    if self.proc is None:
+      return out
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    self.file.flush()
+    self.file.seek(0)
+    sm, mx, reasons = [], [], set()
+    names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+    for line in self.file.read().splitlines():
+      f = [x.strip() for x in line.split(',')]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1]))
+        mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, f[5:9]):
+        if val.lower().startswith('active'):
+          reasons.add(name)
+    self.file.close()
+    os.unlink(self.file.name)
+    if sm:
+      out['sm_mhz'] = statistics.median(sm)
+      out['sm_max_mhz'] = max(mx)
+      out['samples'] = len(sm)
+    out['reasons'] = sorted(reasons)
+    return out
+
+
+def cpu_reference_eval(dataset, h, w, steps, warmup, images_per_step=1):
+  """The reference algorithm (oracle port: PyTorch-CPU fp32 restatement of the TF-1.12 graph)
+  timed on the host cores: forward + argmax + confusion matrix, `images_per_step` images per step."""
+  import numpy as np
+  import torch
+  from oracle import metrics as ometrics
+  from oracle import network as onet
+  from oracle.tables import TABLES
+  torch.set_num_threads(os.cpu_count() or 1)
+  ncls = TABLES[dataset]['num_classes']
+  params = onet.init_params(dataset, seed=0)
+  net = onet.Net(params, dataset)
+  g = torch.Generator().manual_seed(1234)
+  images = torch.rand(images_per_step, h, w, 3, generator=g) * 2 - 1
+  labels = torch.randint(0, ncls, (images_per_step, h, w), generator=g, dtype=torch.int32).numpy()
+  cm = np.zeros((ncls, ncls), dtype=np.int64)
+  times = []
+  with torch.no_grad():
+    for i in range(warmup + steps):
+      t0 = time.perf_counter()
+      pred = net.forward(images)
+      cm += ometrics.confusion_matrix(labels, pred['decisions'].numpy(), ncls)
+      dt = time.perf_counter() - t0
+      if i >= warmup:
+        times.append(dt)
+  total = sum(times)
+  mpix = images_per_step * h * w * len(times) / 1e6
+  return {'value': mpix / total, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+          'sample': f'{len(times)} step(s) of {images_per_step} image(s) {h}x{w}, oracle fp32 on CPU, '
+                    f'{warmup} warm-up', 'ms_per_step': 1e3 * total / len(times)}
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  h = args.height or EVAL_H
+  w = args.width or EVAL_W
+  steps = max(1, min(args.steps, 3))
+  warm = min(args.warmup, 1)
+  r = cpu_reference_eval(args.dataset, h, w, steps, warm, images_per_step=1)
+  line = {'impl': 'reference', 'metric': 'eval_mpix_per_s', 'value': r['value'], 'unit': 'Mpix/s',
+          'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': r['ms_per_step'],
+          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+          'config': {'workload': f'{args.dataset} eval: ResNet-50 OS8 forward + hierarchical heads + argmax + '
+                                 f'confusion matrix, {h}x{w}; reference arm = oracle port on host CPU, 1 image/step'},
+          'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+          'e2e': {'value': r['value'], 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+          'gpu_launches': 0}
+  print(json.dumps(line), flush=True)
+
+
+def run_wlseg_eval(args):
+  import torch
+  import torch.distributed as dist
+  from wlseg import arch, hierarchy, network, ops, problem_defs, synthetic
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py: no CUDA device; wlseg has no CPU fallback')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+
+  H, W, NB = args.height or EVAL_H, args.width or EVAL_W, args.batch or EVAL_NB
+  pd = problem_defs.GENERATORS[args.dataset]()
+  hier = hierarchy.Hierarchy(args.dataset, pd['cids2labels'])
+  ncls = hier.num_classes
+  params = network.Params(hier, dev)
+  params.init_random(0)
+  net = network.Network(params, dtype=torch.bfloat16)
+  src = synthetic.SyntheticInputs(ncls, dev, rank=rank)
+  batches = [src.eval_batch(NB, H, W) for _ in range(2)]  # 2 x 133 MB + GBs of activations >> 126 MB L2
+  cm = torch.zeros((ncls, ncls), dtype=torch.int64, device=dev)
+
+  def step(i):
+    f, l = batches[i % 2]
+    out = net.predict(f['proimages'], want=('decisions',))
+    ops.confmat_accumulate(l['prolabels'], out['decisions'], ncls, cm)
+
+  for i in range(args.warmup):
+    step(i)
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+
+  net.profile = []
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  launches0 = ops.launches
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(args.steps):
+    step(i)
+  if world > 1:
+    dist.all_reduce(cm, op=dist.ReduceOp.SUM)  # evaluation sharded by image: one exact integer reduction
+  e1.record()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  clocks = sampler.stop() if sampler else None
+  ms = e0.elapsed_time(e1)
+  launches = ops.launches - launches0
+  prof = net.profile
+  net.profile = None
+  t = torch.tensor([ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_max = float(t.item())
+  total_pix = world * args.steps * NB * H * W
+  value = total_pix / 1e6 / (ms_max / 1e3)
+
+  # ---- roofline of the dominant kernel: conv_igemm_kernel<BN=256> (bulk of the FLOPs) ----------
+  peaks = load_peaks()
+  classes = {}
+  for rec in prof:
+    rec['ms'] = rec['e0'].elapsed_time(rec['e1'])
+    c = classes.setdefault(rec['cls'], {'flops': 0.0, 'ms': 0.0, 'launches': 0, 'bytes': 0.0})
+    c['flops'] += rec['flops']
+    c['ms'] += rec['ms']
+    c['bytes'] += rec['bytes']
+    c['launches'] += 1
+  dom = classes.get('igemm_bn256')
+  roofline = None
+  if dom and dom['ms'] > 0:
+    ach = dom['flops'] / (dom['ms'] / 1e3) / 1e12
+    # timed inside a long step under the power cap -> sustained peak
+    roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel<256, bf16>', 'achieved': ach,
+                'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'],
+                'traffic': None, 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)',
+                'launches': dom['launches'], 'share_of_step': dom['ms'] / ms}
+  if args.detail and rank == 0:
+    table = {k: {'launches': v['launches'], 'ms_per_step': v['ms'] / args.steps,
+                 'tflops': v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] else None,
+                 'gbs_algorithmic': v['bytes'] / (v['ms'] / 1e3) / 1e9 if v['ms'] else None}
+             for k, v in sorted(classes.items())}
+    with open(args.detail, 'w') as fp:
+      json.dump({'ms_per_step': ms / args.steps, 'classes': table}, fp, indent=1)
+
+  # ---- end to end through the public API with host buffers -------------------------------------
+  e2e = None
+  if not args.no_e2e:
+    e2e = measure_e2e(args, dev, rank, world, H, W, NB)
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cpu = cpu_reference_eval(args.dataset, H, W, steps=2, warmup=1, images_per_step=1)
+    cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+
+  if rank == 0:
+    line = {'metric': 'eval_mpix_per_s', 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': f'{args.dataset} eval (BASELINE configs[1]): ResNet-50 OS8 forward + hierarchical '
+                                   f'heads + argmax + confusion matrix, {H}x{W}, batch {NB}/GPU/step, random init',
+                       'l2': 'inputs (2 rotating 133 MB batches) and multi-GB activations exceed the 126 MB L2',
+                       'parallelism': f'image-sharded x{world}, int64 confusion-matrix all-reduce' if world > 1 else 'single GPU',
+                       'fwd_gflop_per_image': arch.conv_flops(params.specs, H, W) / 1e9},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * world, 'roofline': roofline,
+            'cpu_baseline': cpu}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def measure_e2e(args, dev, rank, world, H, W, NB):
+  """Same metric through the reference-facing API (`SemanticSegmentation.evaluate` machinery) with
+  HOST buffers: every step copies its fp32 images + int32 labels from pinned host memory and reads
+  the running confusion matrix back."""
+  import types
+
+  import torch
+  import torch.distributed as dist
+  from wlseg import problem_defs, settings as wsettings
+  from wlseg.system_factory import SemanticSegmentation
+
+  tmp = tempfile.mkdtemp(prefix='wlseg_bench_')
+  ss = wsettings.build_parser(wsettings.EVAL)
+  argv = [tmp, str(NB * (args.warmup + args.steps) * world), problem_defs.default_path(args.dataset), 'synthetic',
+          args.dataset, '--Nb', str(NB), '--height_feature_extractor', str(H), '--width_feature_extractor', str(W),
+          '--synthetic']
+  st = wsettings.eval_extra_args(ss.parse_args(argv))
+  st.device, st.rank, st.world_size = str(dev), rank, world
+  nsteps = {'n': args.warmup}
+  # two pinned host batches reused round-robin (what a host input pipeline would hand over)
+  g = torch.Generator().manual_seed(1234 + rank)
+  host = []
+  for _ in range(2):
+    img = (torch.rand((NB, H, W, 3), generator=g) * 2 - 1).pin_memory()
+    lab = torch.randint(0, 20 if args.dataset == 'cityscapes' else 66, (NB, H, W), generator=g,
+                        dtype=torch.int32).pin_memory()
+    host.append(({'proimages': img}, {'prolabels': lab}))
+
+  def input_fn(config, params):
+    for i in range(nsteps['n']):
+      yield host[i % 2]
+
+  system = SemanticSegmentation({'eval': input_fn}, None, st)
+  import contextlib
+  import io
+  with contextlib.redirect_stdout(io.StringIO()):
+    system.evaluate()  # builds the estimator, warm-up steps
+  est = system.estimator
+  nsteps['n'] = args.steps
+  ncls = system.settings.output_Nclasses
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  t0 = time.perf_counter()
+  m = est.evaluate(input_fn(None, st), ncls)
+  if world > 1:
+    system._reduce_across_ranks(m)
+  torch.cuda.synchronize()
+  dt = time.perf_counter() - t0
+  t = torch.tensor([dt], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  dt = float(t.item())
+  assert int(m['confusion_matrix_int64'].sum()) == world * args.steps * NB * H * W
+  import shutil
+  shutil.rmtree(tmp, ignore_errors=True)
+  del types
+  return {'value': world * args.steps * NB * H * W / 1e6 / dt, 'unit': 'Mpix/s',
+          'h2d_bytes_per_step': est.last_h2d_bytes // args.steps, 'd2h_bytes_per_step': est.last_d2h_bytes // args.steps,
+          'ms_per_step': 1e3 * dt / args.steps}
+
+
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    return run_reference(args)
+  if args.workload == 'train':
+    from wlseg import train_bench
+    return train_bench.run(args)
+  return run_wlseg_eval(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -1,0 +1,78 @@
+"""Entry points of train.py / evaluate.py / predict.py (code/train.py:24-40, code/evaluate.py:25-67,
+code/predict.py:22-169)."""
+
+import os
+import pickle
+from datetime import datetime
+
+import numpy as np
+
+from wlseg import metrics, settings as wsettings, synthetic
+from wlseg.system_factory import SemanticSegmentation
+
+
+def _dist_env(st):
+  """One process per GPU (torchrun): rank / world size from the environment."""
+  import torch
+  st.rank = int(os.environ.get('RANK', '0'))
+  st.world_size = int(os.environ.get('WORLD_SIZE', '1'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  st.device = f'cuda:{local}'
+  if torch.cuda.is_available():
+    torch.cuda.set_device(local)
+  if st.world_size > 1:
+    import torch.distributed as dist
+    if not dist.is_initialized():
+      dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+  return st
+
+
+def train_main(argv):
+  ss = wsettings.build_parser(wsettings.TRAIN)
+  st = ss.parse_args(argv)
+  # upstream insists on an ImageNet checkpoint path (train.py:31-33); none exists here, so training
+  # starts from the random initialisation unless log_dir holds a checkpoint
+  wsettings.train_extra_args(st)
+  _dist_env(st)
+  system = SemanticSegmentation({'train': synthetic.train_input_fn}, None, st)
+  return system.train()
+
+
+def evaluate_main(argv):
+  np.set_printoptions(formatter={'float': '{:>5.2f}'.format}, nanstr=u'nan', linewidth=10000)
+  ss = wsettings.build_parser(wsettings.EVAL)
+  st = wsettings.eval_extra_args(ss.parse_args(argv))
+  _dist_env(st)
+  system = SemanticSegmentation({'eval': synthetic.eval_input_fn}, None, st)
+  labels = system.settings.evaluation_problem_def['cids2labels']
+  void_exists = -1 in system.settings.evaluation_problem_def['lids2cids']
+  if void_exists and not system.settings.train_void_class:
+    labels = labels[:-1]
+  all_metrics = system.evaluate()
+  if st.rank == 0:
+    mr_filename = os.path.join(system.settings.eval_res_dir, 'all_metrics.txt')
+    with open(mr_filename, 'w') as f:
+      for m in all_metrics:
+        print(f"{m['global_step']:>05} ", end='', file=f)
+        metrics.print_metrics_from_confusion_matrix(m['confusion_matrix'], labels, printfile=f)
+    with open(os.path.join(system.settings.eval_res_dir, 'all_metrics.p'), 'wb') as f:
+      pickle.dump([{k: m[k] for k in ('global_step', 'loss', 'confusion_matrix')} for m in all_metrics], f)
+  return all_metrics
+
+
+def predict_main(argv):
+  ss = wsettings.build_parser(wsettings.PREDICT)
+  st = wsettings.predict_extra_args(ss.parse_args(argv))
+  _dist_env(st)
+  for flag in ('plotting', 'plotting_overlapped', 'export_color_decisions', 'export_overlapped_color_decisions',
+               'export_lids_images'):
+    if getattr(st, flag, False):
+      raise NotImplementedError(f'--{flag}: plotting / export is outside the B200 hot path')
+  system = SemanticSegmentation({'predict': synthetic.predict_input_fn}, None, st)
+  start = total = datetime.now()
+  n = 0
+  for outputs in system.predict():
+    n += 1
+    print(f"\nTime per image (input pipeline + network): {datetime.now() - start}", outputs['decisions'].shape)
+    start = datetime.now()
+  print('\nTotal time (input pipeline + network):', datetime.now() - total, 'for', n, 'image(s)')

@@ -1,0 +1,212 @@
+"""Train / eval / predict step drivers: the host-side mirror of the reference's Estimator glue.
+
+Mirrors code/estimator/define_estimator_hierarchical.py:39-239 (`define_estimator` TRAIN / EVAL /
+PREDICT branches), :490-528 (`_map_predictions_to_new_cids`), :530-571 (`_resize_predictions`),
+code/estimator/define_metrics.py:5-20, code/estimator/define_optimizer.py:3-26 and
+code/input_pipelines/utils.py:118-124 (`get_temp_Nb`).  Everything here is launch sequencing and
+buffer ownership; the arithmetic lives in libwlseg.
+"""
+
+import glob
+import os
+
+import numpy as np
+import torch
+
+from wlseg import network, ops
+
+
+def _replacevoids(mappings):
+  """code/utils/utils.py:286-289."""
+  max_m = max(mappings)
+  return [m if m != -1 else max_m + 1 for m in mappings]
+
+
+def get_temp_Nb(params, Nb):
+  """code/input_pipelines/utils.py:118-124: per-replica batch = Nb / num_towers (must divide)."""
+  if getattr(params, 'distribute', False):
+    world = max(1, getattr(params, 'world_size', 1))
+    div, mod = divmod(Nb, world)
+    assert not mod, 'for now Nb must be divisible by the number of available GPUs.'
+    return div
+  return Nb
+
+
+def learning_rate(params, global_step):
+  """code/estimator/define_optimizer.py:3-13 with the [TF-1.12] schedule semantics."""
+  if params.learning_rate_schedule == 'piecewise_constant':
+    for b, v in zip(params.learning_rate_boundaries, params.learning_rate_values):
+      if global_step <= b:
+        return v
+    return params.learning_rate_values[-1]
+  if params.learning_rate_schedule == 'polynomial_decay':
+    t = params.num_training_steps
+    s = min(global_step, t)
+    return ((params.learning_rate_initial - params.learning_rate_final) * (1.0 - s / t) ** params.learning_rate_power
+            + params.learning_rate_final)
+  raise ValueError('Unknown option for learning rate schedule.')
+
+
+def mean_iou_from_cm(cm, num_classes):
+  """code/estimator/define_metrics.py:13-20 on an int confusion matrix (training summary)."""
+  cm = np.asarray(cm).astype(np.int32)
+  inter = np.diagonal(cm).astype(np.float32)
+  union = (cm.sum(0) + cm.sum(1) - np.diagonal(cm)).astype(np.float32) + np.float32(1e-9)
+  del num_classes
+  return float(np.mean(inter / union, dtype=np.float32))
+
+
+def resize_decisions_nearest(decs, new_h, new_w):
+  """`_resize_predictions` for decisions: NEAREST_NEIGHBOR, align_corners=True, roundf
+  (define_estimator_hierarchical.py:559-563).  Identity at every BASELINE configuration; index
+  plumbing otherwise."""
+  n, h, w = decs.shape
+  if (h, w) == (new_h, new_w):
+    return decs
+  sy = (h - 1) / (new_h - 1) if new_h > 1 else h / new_h
+  sx = (w - 1) / (new_w - 1) if new_w > 1 else w / new_w
+  dev = decs.device
+  yi = torch.clamp(torch.floor(torch.arange(new_h, device=dev, dtype=torch.float32) * np.float32(sy) + 0.5).long(), max=h - 1)
+  xi = torch.clamp(torch.floor(torch.arange(new_w, device=dev, dtype=torch.float32) * np.float32(sx) + 0.5).long(), max=w - 1)
+  return decs[:, yi][:, :, xi].contiguous()
+
+
+class _Prefetcher:
+  """Double-buffered host->device staging: batch i+1 is copied (pinned memory, side stream) while
+  batch i computes.  Device-resident batches pass through untouched."""
+
+  def __init__(self, it, device):
+    self.it = iter(it)
+    self.device = device
+    self.stream = torch.cuda.Stream(device=device)
+    self.h2d_bytes = 0
+    self.next = None
+    self._advance()
+
+  def _to_dev(self, t):
+    if not torch.is_tensor(t) or t.is_cuda:
+      return t
+    if not t.is_pinned():
+      t = t.pin_memory()
+    self.h2d_bytes += t.numel() * t.element_size()
+    return t.to(self.device, non_blocking=True)
+
+  def _advance(self):
+    try:
+      features, labels = next(self.it)
+    except StopIteration:
+      self.next = None
+      return
+    with torch.cuda.stream(self.stream):
+      f = {k: self._to_dev(v) for k, v in features.items()}
+      l = None if labels is None else {k: self._to_dev(v) for k, v in labels.items()}
+      ev = torch.cuda.Event()
+      ev.record(self.stream)
+    self.next = (f, l, ev)
+
+  def __iter__(self):
+    return self
+
+  def __next__(self):
+    if self.next is None:
+      raise StopIteration
+    f, l, ev = self.next
+    torch.cuda.current_stream().wait_event(ev)
+    for d in (f, l or {}):
+      for v in d.values():
+        if torch.is_tensor(v) and v.is_cuda:
+          v.record_stream(torch.cuda.current_stream())
+    self._advance()
+    return f, l
+
+
+class Estimator:
+  """Owns the parameters and runs the three modes for `SemanticSegmentation`."""
+
+  def __init__(self, params, hier, device='cuda'):
+    self.settings = params
+    self.hier = hier
+    self.device = torch.device(device)
+    self.dtype = torch.bfloat16 if getattr(params, 'dtype', 'bf16') == 'bf16' else torch.float32
+    self.params = network.Params(hier, self.device, getattr(params, 'stride_feature_extractor', 8))
+    self.global_step = 0
+    self.net = None
+    self.last_h2d_bytes = 0
+    self.last_d2h_bytes = 0
+
+  # ---- checkpoints (torch files keyed by TF variable names) -------------------------------------
+  def latest_checkpoint(self, log_dir):
+    cands = glob.glob(os.path.join(log_dir, 'model.ckpt-*.pt'))
+    if not cands:
+      return None
+    return max(cands, key=lambda p: int(p.rsplit('-', 1)[1].split('.')[0]))
+
+  def save(self, log_dir):
+    os.makedirs(log_dir, exist_ok=True)
+    path = os.path.join(log_dir, f'model.ckpt-{self.global_step}.pt')
+    torch.save({'global_step': self.global_step, 'variables': self.params.to_tf_dict()}, path)
+    return path
+
+  def restore(self, path):
+    blob = torch.load(path, map_location='cpu')
+    self.params.load_tf_dict(blob['variables'])
+    self.global_step = int(blob.get('global_step', 0))
+
+  def initialize(self, ckpt_path=None, log_dir=None, seed=0):
+    path = ckpt_path or (self.latest_checkpoint(log_dir) if log_dir else None)
+    if path:
+      self.restore(path)
+    else:
+      self.params.init_random(seed)  # no checkpoint: random init (BASELINE configs use random weights)
+    self.net = network.Network(self.params, dtype=self.dtype,
+                               bn_decay=getattr(self.settings, 'batch_norm_decay', 0.9))
+    return path
+
+  # ---- EVAL ---------------------------------------------------------------------------------------
+  def evaluate(self, batches, num_classes, lut=None):
+    """define_estimator EVAL branch: forward, remap cids, resize to label size, streaming confusion
+    matrix.  `batches` yields (features, labels) with host or device tensors.  Returns the
+    reference's metrics dict {'confusion_matrix': np.int32[C, C], 'loss': 0.0, 'global_step'}."""
+    dev = self.device
+    cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=dev)
+    invalid = torch.zeros(1, dtype=torch.int64, device=dev)
+    lut_t = None if lut is None else torch.tensor(lut, dtype=torch.int32, device=dev)
+    pre = _Prefetcher(batches, dev)
+    steps = 0
+    host_cm = torch.zeros((num_classes, num_classes), dtype=torch.int64).pin_memory()
+    for features, labels in pre:
+      out = self.net.predict(features['proimages'], want=('decisions',))
+      lab = labels['prolabels']
+      decs = resize_decisions_nearest(out['decisions'], lab.shape[1], lab.shape[2])
+      ops.confmat_accumulate(lab.contiguous(), decs, num_classes, cm, lut_t, invalid)
+      # the step's result (running metric) goes back to the host every step, asynchronously
+      host_cm.copy_(cm, non_blocking=True)
+      steps += 1
+    torch.cuda.synchronize(dev)
+    self.last_h2d_bytes = pre.h2d_bytes
+    self.last_d2h_bytes = steps * host_cm.numel() * 8
+    if int(invalid.item()):
+      raise ops.WlsegError(f'{int(invalid.item())} (label, decision) pairs outside [0, {num_classes})')
+    total = cm.cpu().numpy()
+    # the reference exposes tf.to_int32(total_cm)
+    return {'confusion_matrix': total.astype(np.int32), 'confusion_matrix_int64': total, 'loss': 0.0,
+            'global_step': self.global_step, 'steps': steps}
+
+  # ---- PREDICT ------------------------------------------------------------------------------------
+  def predict(self, batches, predict_keys):
+    """define_estimator PREDICT branch: yields one dict per example with the requested keys."""
+    want = tuple(k for k in predict_keys if k not in ('rawimages', 'rawimagespaths'))
+    for features, _ in batches:
+      pro = features['proimages']
+      if not pro.is_cuda:
+        pro = pro.to(self.device, non_blocking=True)
+      out = self.net.predict(pro, want=want)
+      host = {k: out[k].cpu().numpy() for k in want}
+      n = pro.shape[0]
+      for i in range(n):
+        ex = {k: v[i] for k, v in host.items()}
+        if 'rawimages' in predict_keys and 'rawimages' in features:
+          ex['rawimages'] = features['rawimages'][i].cpu().numpy()
+        if 'rawimagespaths' in predict_keys and 'rawimagespaths' in features:
+          ex['rawimagespaths'] = features['rawimagespaths'][i]
+        yield ex

@@ -200,6 +200,7 @@ class Network:
     self.conv_algo = conv_algo
     self.dev = params.device
     self.tape = None
+    self.profile = None  # bench.py: list receiving one CUDA-event record per convolution launch
 
   # ---- helpers ---------------------------------------------------------------------------------
   def _weights(self, scope):
@@ -220,12 +221,25 @@ class Network:
     prm = ops.conv_params((N, H, W, C), tuple(w.shape), stride=stride, dilation=dilation, pad=pad, out_hw=out_hw,
                           x_pitch=x.stride(2), y_pitch=y.stride(2), relu=relu, dtype=self.code,
                           y_dtype=ops.dtype_code(y.dtype), algo=self.conv_algo, res=residual, res_stride=res_stride)
-    if bn_sum is not None and not (self.conv_algo != ops.ALGO_DIRECT and ops.conv2d_tcgen05_supported(prm)):
+    tc = self.conv_algo != ops.ALGO_DIRECT and ops.conv2d_tcgen05_supported(prm)
+    rec = None
+    if self.profile is not None:
+      esz = 2 if self.dtype == torch.bfloat16 else 4
+      rec = {'cls': ('igemm_bn%d' % (256 if K > 128 else 128 if K > 64 else 64 if K > 32 else 32)) if tc else 'direct',
+             'flops': 2.0 * N * out_hw[0] * out_hw[1] * w.shape[1] * w.shape[2] * C * K,
+             'bytes': float(esz * (N * H * W * C + w.numel()) + y.element_size() * N * out_hw[0] * out_hw[1] * K +
+                            (esz * N * out_hw[0] * out_hw[1] * K if residual is not None else 0)),
+             'e0': torch.cuda.Event(enable_timing=True), 'e1': torch.cuda.Event(enable_timing=True)}
+      rec['e0'].record()
+    if bn_sum is not None and not tc:
       # direct kernel: statistics from the stored output instead of the accumulators
       ops.conv2d_fprop(prm, x, w, y, scale, shift, residual)
       ops.bn_stats(y, N * out_hw[0] * out_hw[1], K, y.stride(2), bn_sum, bn_sqsum)
-      return y
-    ops.conv2d_fprop(prm, x, w, y, scale, shift, residual, bn_sum, bn_sqsum)
+    else:
+      ops.conv2d_fprop(prm, x, w, y, scale, shift, residual, bn_sum, bn_sqsum)
+    if rec is not None:
+      rec['e1'].record()
+      self.profile.append(rec)
     return y
 
   # ---- inference ---------------------------------------------------------------------------------

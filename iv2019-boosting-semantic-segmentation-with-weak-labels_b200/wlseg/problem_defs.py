@@ -83,8 +83,16 @@ GENERATORS = {'cityscapes': cityscapes, 'vistas': vistas}
 
 
 def default_path(dataset):
+  """Path of the generated problem definition of `dataset` (written on first use; the files are
+  build artefacts, not sources)."""
   here = os.path.dirname(os.path.abspath(__file__))
-  return os.path.join(here, 'problem_definitions', dataset, 'problem01.json')
+  path = os.path.join(here, 'problem_definitions', dataset, 'problem01.json')
+  if not os.path.exists(path):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, 'w') as fp:
+      json.dump(GENERATORS[dataset](), fp)
+      fp.write('\n')
+  return path
 
 
 def write_all(root=None):
