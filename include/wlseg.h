@@ -202,6 +202,16 @@ int wlseg_sgdm_step(float* w, const float* g, float* acc, void* w_bf16, int64_t 
                     const float* lr_dev, float momentum, int32_t nesterov, float wd,
                     float grad_scale, double* reg_loss, wlseg_stream_t stream);
 
+/* Shadow variables of tf.train.ExponentialMovingAverage(decay, num_updates=global_step,
+ * zero_debias=True) (estimator/define_estimator_hierarchical.py:96-111): biased <- biased -
+ * (1-decay)*(biased - w); shadow = biased * inv_correction with inv_correction = 1/(1-decay^t). */
+int wlseg_ema_update(float* biased, float* shadow, const float* w, int64_t n, float decay,
+                     float inv_correction, wlseg_stream_t stream);
+
+/* dst += src (n elements, n % 8 == 0): gradient fan-in of the residual connections
+ * (tf.add_n of the gradients reaching one tensor in the reference's backward graph). */
+int wlseg_add_inplace(void* dst, const void* src, int64_t n, int32_t dtype, wlseg_stream_t stream);
+
 /* Layout / dtype helpers used by the host mirror (no reference counterpart: TF keeps HWIO
  * fp32 kernels; we keep KRSC bf16 operand copies). */
 int wlseg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, wlseg_stream_t stream);

@@ -22,8 +22,13 @@
 //   warp 1  MMA issuer     (one elected lane; 4 x tcgen05.mma K=16 per stage; tcgen05.commit
 //                           releases the stage and finally publishes the accumulator)
 //   warp 2  TMEM allocator
-//   warps 4-7 epilogue     (tcgen05.ld 32 lanes x 32 columns -> scale/shift/residual/ReLU ->
-//                           bf16 (or fp32) NHWC stores; overlaps the next tile's MMAs)
+//   warps 4-7 epilogue     (tcgen05.ld 32 lanes x 32 columns -> scale/shift/residual/ReLU -> bf16;
+//                           overlaps the next tile's MMAs).  bf16 outputs stream through shared
+//                           memory: the residual tile arrives by TMA into a swizzled staging
+//                           buffer, results are written to a second swizzled buffer and leave by
+//                           TMA store (cp.async.bulk.tensor ... bulk_group), 64 channels at a time,
+//                           double buffered - the epilogue threads never touch global memory.
+//                           fp32 outputs (the logits layers) use plain per-thread stores.
 //
 // Roofline: tensor-bound for the block3/block4 3x3 and wide 1x1 layers
 // (flops = 2*N*P*Q*R*S*C*K); HBM-bound for block1 and the 64-channel 1x1 layers.
@@ -34,6 +39,7 @@
 #include <tuple>
 
 #include "common.cuh"
+#include "tc_sm100.cuh"
 
 namespace wlseg {
 
@@ -47,11 +53,13 @@ constexpr int kUmmaK = 16;        // bf16 MMA K
 constexpr int kIgemmThreads = 256;
 constexpr int kEpiWarp0 = 4;      // first epilogue warp
 constexpr int kABytes = kBM * kBK * 2;  // 16 KB
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 224 * 1024;
 
 struct IgemmParams {
   CUtensorMap map_a;  // activations {C, W, H, N}
   CUtensorMap map_b;  // filters {C, R*S, K}
+  CUtensorMap map_y;  // output {K, Q, P, N}                         (TMA epilogue only)
+  CUtensorMap map_r;  // residual {K, res_W, res_H, N}, strided box  (TMA epilogue only)
   void* y;
   const float* scale;
   const float* shift;
@@ -66,136 +74,86 @@ struct IgemmParams {
   int tiles_w, tiles_h, n_tiles, total_tiles;
   int cchunks;        // ceil(C / 64)
   int num_kb;         // R * S * cchunks
+  int stages;         // depth of the {A,B} operand ring
+  int epi_bufs;       // 16 KB epilogue staging buffers (0: direct epilogue, else 2 or 4)
 };
 
-// ----------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M = 128, N from the instruction descriptor
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (= 1024 B:
-//   8 rows x 128 B per swizzle atom) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A bf16 [7,10)=1,
-// B bf16 [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
+constexpr int kSubW = 64;                       // epilogue sub-tile: 64 channels = one 128-byte row
+constexpr int kSubBytes = kBM * kSubW * 2;      // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kMaxEpiBufs = 4;
+constexpr int kBarBytes = 256;                  // full[8] empty[8] tfull[2] tempty[2] rfull[4] + TMEM slot
+constexpr int kSmemMax = 227 * 1024;            // opt-in dynamic shared memory per CTA on sm_100
 
 template <int BN>
 struct IgemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (kSmemBudget - 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kVecBytes = 2 * BN * 4;  // the tile's scale / shift vectors
 };
 
+// 32 x 32 transpose-reduce: on entry every lane holds 32 column values of ITS row; on exit
+// v[0] of lane L is the sum over the warp's 32 rows of column L.  31 shuffles instead of 160.
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+// Sequence of 64-channel output sub-tiles a CTA walks through (persistent tile loop x sub-tiles).
+struct SubTileCursor {
+  int tile, st;     // current tile id and sub-tile index inside it
+  int n, p0, q0, k0;  // decoded tile origin
+};
+
+template <int BN>
+__device__ __forceinline__ void decode_tile(const IgemmParams& prm, int tile, int& n, int& p0, int& q0, int& k0) {
+  const int nt = tile % prm.n_tiles;
+  int mt = tile / prm.n_tiles;
+  const int twi = mt % prm.tiles_w; mt /= prm.tiles_w;
+  const int thi = mt % prm.tiles_h;
+  n = mt / prm.tiles_h;
+  q0 = twi << prm.tw_log2;
+  p0 = thi * (kBM >> prm.tw_log2);
+  k0 = nt * BN;
+}
+
+template <int BN>
+__device__ __forceinline__ int num_subtiles(const IgemmParams& prm, int k0) {
+  const int left = prm.K - k0;
+  const int full = BN / kSubW;
+  const int need = (left + kSubW - 1) / kSubW;
+  return need < full ? need : full;
+}
+
 // ----------------------------------------------------------------------------- kernel
-template <int BN, typename TY>
+template <int BN, typename TY, bool kTmaEpi>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   using Cfg = IgemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte aligned stages
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                         // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;     // [2]
-  uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // SWIZZLE_128B operands need 1024-byte aligned stages (the kernel has no static shared memory,
+  // so the dynamic window starts at offset 0 of the CTA's shared space)
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int stages = prm.stages;
+  uint8_t* epi_smem = smem + stages * Cfg::kStageBytes;            // [buf0 .. buf(epi_bufs-1)]
+  float* s_scale = reinterpret_cast<float*>(epi_smem + prm.epi_bufs * kSubBytes);
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
+  uint64_t* full_bar = bars;                             // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;               // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;           // [2]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;      // [2]
+  uint64_t* rfull_bar = bars + 2 * kMaxStages + 4;       // [kMaxEpiBufs] residual sub-tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kMaxEpiBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -203,9 +161,13 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&prm.map_a);
     tma_prefetch_desc(&prm.map_b);
+    if (kTmaEpi) {
+      tma_prefetch_desc(&prm.map_y);
+      if (prm.res != nullptr) tma_prefetch_desc(&prm.map_r);
+    }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(full_bar + s), 1);
       mbar_init(smem_u32(empty_bar + s), 1);
     }
@@ -213,6 +175,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       mbar_init(smem_u32(tfull_bar + a), 1);
       mbar_init(smem_u32(tempty_bar + a), 4);  // one arrival per epilogue warp
     }
+    for (int a = 0; a < kMaxEpiBufs; ++a) mbar_init(smem_u32(rfull_bar + a), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
@@ -229,14 +192,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        const int nt = tile % prm.n_tiles;
-        int mt = tile / prm.n_tiles;
-        const int twi = mt % prm.tiles_w; mt /= prm.tiles_w;
-        const int thi = mt % prm.tiles_h;
-        const int n = mt / prm.tiles_h;
-        const int q0 = twi << prm.tw_log2;
-        const int p0 = thi * (kBM >> prm.tw_log2);
-        const int k0 = nt * BN;
+        int n, p0, q0, k0;
+        decode_tile<BN>(prm, tile, n, p0, q0, k0);
         for (int kb = 0; kb < prm.num_kb; ++kb) {
           const int tap = kb / prm.cchunks;
           const int cc = kb - tap * prm.cchunks;
@@ -250,7 +207,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
           tma_load_4d(a_dst, &prm.map_a, bar, cc * kBK, q0 * prm.stride - prm.pad_left + s * prm.dilation,
                       p0 * prm.stride - prm.pad_top + r * prm.dilation, n);
           tma_load_3d(b_dst, &prm.map_b, bar, cc * kBK, tap, k0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -279,7 +236,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
           umma_commit(smem_u32(empty_bar + stage));              // stage free once these MMAs retire
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(tfull_bar + acc));                  // accumulator complete
       }
@@ -290,117 +247,224 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     const int row = ew * 32 + lane;           // tile row = pixel within the patch
     const int dy_ = row >> prm.tw_log2, dx_ = row & (TW - 1);
     int iter = 0;
-    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
-      const int nt = tile % prm.n_tiles;
-      int mt = tile / prm.n_tiles;
-      const int twi = mt % prm.tiles_w; mt /= prm.tiles_w;
-      const int thi = mt % prm.tiles_h;
-      const int n = mt / prm.tiles_h;
-      const int q = (twi << prm.tw_log2) + dx_;
-      const int p = thi * (kBM >> prm.tw_log2) + dy_;
-      const bool valid = (p < prm.P) && (q < prm.Q);
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
-      mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
-      tc_fence_after();
-      const int64_t opix = ((int64_t)n * prm.P + p) * prm.Q + q;
-      TY* yrow = reinterpret_cast<TY*>(prm.y) + opix * prm.y_pitch;
-      const __nv_bfloat16* rrow = nullptr;
-      if (prm.res != nullptr && valid)
-        rrow = reinterpret_cast<const __nv_bfloat16*>(prm.res) +
-               (((int64_t)n * prm.res_H + (int64_t)p * prm.res_stride) * prm.res_W + (int64_t)q * prm.res_stride) *
-                   prm.res_pitch;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int kbase = nt * BN + ch * 32;
-        if (kbase >= prm.K) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-
-        if (prm.bn_sum != nullptr) {
-          // training-mode BN statistics of the raw accumulators (rows outside the image masked)
-          float mys = 0.f, mysq = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = valid ? f[j] : 0.f;
-            float s1 = warp_sum(a);
-            float s2 = warp_sum(a * a);
-            if (lane == j) { mys = s1; mysq = s2; }
-          }
-          if (kbase + lane < prm.K) {
-            atomicAdd(prm.bn_sum + kbase + lane, (double)mys);
-            atomicAdd(prm.bn_sqsum + kbase + lane, (double)mysq);
+    if constexpr (kTmaEpi) {
+      // ---- staged epilogue: TMEM -> registers -> swizzled shared memory -> TMA store; the residual
+      // sub-tile is TMA-loaded INTO the staging buffer it will leave from (read-modify-write in place)
+      const bool has_res = prm.res != nullptr;
+      const bool leader = (row == 0);
+      const int nb = prm.epi_bufs;            // 2 or 4
+      const int nb_mask = nb - 1, nb_shift = (nb == 4) ? 2 : 1;
+      const uint32_t sw = (uint32_t)(row & 7);
+      // residual prefetch cursor (leader only): sub-tile sequence index `rs` is loaded into buffer rs % nb
+      int r_tile = blockIdx.x, r_st = 0, r_seq = 0;
+      auto issue_residual = [&]() {
+        // loads the residual of sequence index r_seq (if any is left) and advances the cursor
+        if (r_tile >= prm.total_tiles) return;
+        int n, p0, q0, k0;
+        decode_tile<BN>(prm, r_tile, n, p0, q0, k0);
+        const int b = r_seq & nb_mask;
+        const uint32_t bar = smem_u32(rfull_bar + b);
+        mbar_arrive_expect_tx(bar, kSubBytes);
+        tma_load_4d(smem_u32(epi_smem + b * kSubBytes), &prm.map_r, bar, k0 + r_st * kSubW, q0 * prm.res_stride,
+                    p0 * prm.res_stride, n);
+        ++r_seq;
+        if (++r_st == num_subtiles<BN>(prm, k0)) { r_st = 0; r_tile += gridDim.x; }
+      };
+      if (has_res && leader)
+        for (int i = 0; i < nb - 1; ++i) issue_residual();
+      int seq = 0;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
+        int n, p0, q0, k0;
+        decode_tile<BN>(prm, tile, n, p0, q0, k0);
+        const bool valid = (p0 + dy_ < prm.P) && (q0 + dx_ < prm.Q);
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        const int nsub = num_subtiles<BN>(prm, k0);
+        // this tile's scale / shift vectors (readers of the previous tile's are past its last barrier)
+        if (prm.scale != nullptr) {
+          for (int j = row; j < BN; j += 128) {
+            const bool in = (k0 + j < prm.K);
+            s_scale[j] = in ? __ldg(prm.scale + k0 + j) : 0.f;
+            s_shift[j] = in ? __ldg(prm.shift + k0 + j) : 0.f;
           }
         }
-        if (valid) {
-          const bool full = (kbase + 32 <= prm.K);
-          if (prm.scale != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || kbase + j < prm.K) f[j] = f[j] * __ldg(prm.scale + kbase + j) + __ldg(prm.shift + kbase + j);
+        mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+        tc_fence_after();
+        for (int st = 0; st < nsub; ++st, ++seq) {
+          const int b = seq & nb_mask;
+          uint8_t* buf = epi_smem + b * kSubBytes;
+          if (has_res) {
+            mbar_wait(smem_u32(rfull_bar + b), (uint32_t)((seq >> nb_shift) & 1));
+          } else if (leader) {
+            // the store that last left from this buffer (nb sub-tiles ago) must have read it
+            if (nb == 2) bulk_wait_read<1>(); else bulk_wait_read<3>();
           }
-          if (rrow != nullptr) {
-            if (full && (prm.res_pitch % 8 == 0)) {
-              const uint4* rp = reinterpret_cast<const uint4*>(rrow + kbase);
+          epi_barrier();  // buffer writable by everyone; scale / shift visible
+          uint8_t* myrow = buf + row * 128;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 raw = __ldg(rp + g);
+          for (int half = 0; half < 2; ++half) {
+            const int col = st * kSubW + half * 32;   // column inside the BN-wide tile
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + col), v);
+            tmem_ld_wait();
+            if (half == 1 && st == nsub - 1) {
+              // last TMEM read of this tile: hand the accumulator back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+            }
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (prm.bn_sum != nullptr) {
+              // training-mode BN statistics of the raw fp32 accumulators (rows outside the image masked)
+              float s1[32], s2[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                s1[j] = valid ? f[j] : 0.f;
+                s2[j] = s1[j] * s1[j];
+              }
+              warp_column_sums(s1, lane);
+              warp_column_sums(s2, lane);
+              if (k0 + col + lane < prm.K) {
+                atomicAdd(prm.bn_sum + k0 + col + lane, (double)s1[0]);
+                atomicAdd(prm.bn_sqsum + k0 + col + lane, (double)s2[0]);
+              }
+            }
+            if (prm.scale != nullptr) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + col + g * 4);
+                const float4 sh = *reinterpret_cast<const float4*>(s_shift + col + g * 4);
+                f[g * 4 + 0] = f[g * 4 + 0] * sc.x + sh.x;
+                f[g * 4 + 1] = f[g * 4 + 1] * sc.y + sh.y;
+                f[g * 4 + 2] = f[g * 4 + 2] * sc.z + sh.z;
+                f[g * 4 + 3] = f[g * 4 + 3] * sc.w + sh.w;
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              // 16-byte chunk (half*4 + g) of this row sits at the XOR-swizzled position
+              uint4* slot = reinterpret_cast<uint4*>(myrow + ((((uint32_t)(half * 4 + g)) ^ sw) << 4));
+              if (has_res) {
+                const uint4 raw = *slot;
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  float2 t = __bfloat1622float2(h[e]);
+                  const float2 t = __bfloat1622float2(h[e]);
                   f[g * 8 + 2 * e] += t.x;
                   f[g * 8 + 2 * e + 1] += t.y;
                 }
               }
-            } else {
+              if (prm.relu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (kbase + j < prm.K) f[j] += __bfloat162float(rrow[kbase + j]);
-            }
-          }
-          if (prm.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (sizeof(TY) == 2) {
-            __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(yrow) + kbase;
-            if (full && (prm.y_pitch % 8 == 0)) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 raw;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
-                reinterpret_cast<uint4*>(yo)[g] = raw;
+                for (int e = 0; e < 8; ++e) f[g * 8 + e] = fmaxf(f[g * 8 + e], 0.f);
               }
-            } else {
+              uint4 outv;
+              __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (kbase + j < prm.K) yo[j] = __float2bfloat16_rn(f[j]);
+              for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+              *slot = outv;
             }
-          } else {
-            float* yo = reinterpret_cast<float*>(yrow) + kbase;
-            if (full && (prm.y_pitch % 4 == 0)) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                reinterpret_cast<float4*>(yo)[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (kbase + j < prm.K) yo[j] = f[j];
+          }
+          fence_async_smem();   // my generic-proxy writes -> visible to the TMA store
+          epi_barrier();        // whole sub-tile written
+          if (leader) {
+            tma_store_4d(&prm.map_y, smem_u32(buf), k0 + st * kSubW, q0, p0, n);
+            bulk_commit();
+            if (has_res) {
+              // refill the buffer used one sub-tile ago: its store must have finished reading it
+              bulk_wait_read<1>();
+              issue_residual();
             }
           }
         }
       }
-      // this warp no longer reads the accumulator: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+      if (leader) bulk_wait_all();  // outstanding stores complete before the CTA retires
+    } else {
+      // ---- direct epilogue: per-thread global stores (fp32 logits, odd channel counts)
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
+        int n, p0, q0, k0;
+        decode_tile<BN>(prm, tile, n, p0, q0, k0);
+        const int q = q0 + dx_;
+        const int p = p0 + dy_;
+        const bool valid = (p < prm.P) && (q < prm.Q);
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+        tc_fence_after();
+        const int64_t opix = ((int64_t)n * prm.P + p) * prm.Q + q;
+        TY* yrow = reinterpret_cast<TY*>(prm.y) + opix * prm.y_pitch;
+        const __nv_bfloat16* rrow = nullptr;
+        if (prm.res != nullptr && valid)
+          rrow = reinterpret_cast<const __nv_bfloat16*>(prm.res) +
+                 (((int64_t)n * prm.res_H + (int64_t)p * prm.res_stride) * prm.res_W + (int64_t)q * prm.res_stride) *
+                     prm.res_pitch;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          const int kbase = k0 + ch * 32;
+          if (kbase >= prm.K) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+
+          if (prm.bn_sum != nullptr) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s1[j] = valid ? f[j] : 0.f;
+              s2[j] = s1[j] * s1[j];
+            }
+            warp_column_sums(s1, lane);
+            warp_column_sums(s2, lane);
+            if (kbase + lane < prm.K) {
+              atomicAdd(prm.bn_sum + kbase + lane, (double)s1[0]);
+              atomicAdd(prm.bn_sqsum + kbase + lane, (double)s2[0]);
+            }
+          }
+          if (valid) {
+            const bool full = (kbase + 32 <= prm.K);
+            if (prm.scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || kbase + j < prm.K) f[j] = f[j] * __ldg(prm.scale + kbase + j) + __ldg(prm.shift + kbase + j);
+            }
+            if (rrow != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || kbase + j < prm.K) f[j] += __bfloat162float(rrow[kbase + j]);
+            }
+            if (prm.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (sizeof(TY) == 2) {
+              __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(yrow) + kbase;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || kbase + j < prm.K) yo[j] = __float2bfloat16_rn(f[j]);
+            } else {
+              float* yo = reinterpret_cast<float*>(yrow) + kbase;
+              if (full && (prm.y_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(yo) & 15) == 0)) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  reinterpret_cast<float4*>(yo)[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (kbase + j < prm.K) yo[j] = f[j];
+              }
+            }
+          }
+        }
+        // this warp no longer reads the accumulator: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+      }
     }
   }
 
@@ -467,17 +531,25 @@ static bool igemm_supported(const wlseg_conv_params* p) {
   return true;
 }
 
-template <int BN, typename TY>
-static int launch_igemm(const IgemmParams& prm, cudaStream_t s) {
+template <int BN, typename TY, bool kTmaEpi>
+static int launch_igemm(IgemmParams& prm, cudaStream_t s) {
   using Cfg = IgemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::kSmemBytes));
+    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemMax));
     configured = true;
   }
+  // shared memory plan: [stages x {A,B}] [epi_bufs x 16 KB] [scale | shift] [barriers]
+  prm.epi_bufs = kTmaEpi ? (prm.res != nullptr ? 4 : 2) : 0;
+  const int fixed = prm.epi_bufs * kSubBytes + Cfg::kVecBytes + kBarBytes;
+  int stages = (kSmemMax - fixed) / Cfg::kStageBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  WLSEG_CHECK_ARG(stages >= 2, "conv(tcgen05): shared memory plan leaves fewer than 2 pipeline stages");
+  prm.stages = stages;
+  const int smem_bytes = stages * Cfg::kStageBytes + fixed;
   int grid = prm.total_tiles < kNumSMs ? prm.total_tiles : kNumSMs;
-  conv_igemm_kernel<BN, TY><<<grid, kIgemmThreads, Cfg::kSmemBytes, s>>>(prm);
+  conv_igemm_kernel<BN, TY, kTmaEpi><<<grid, kIgemmThreads, smem_bytes, s>>>(prm);
   WLSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -512,6 +584,33 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
     MapKey key(w, 3, p->C, p->R * p->S, p->K, BN, 0, 0, 0, 1);
     if (int e = encode_cached(key, &prm.map_b, 3, w, dims, strides, box, estr)) return e;
   }
+  const bool f32out = (p->y_dtype == WLSEG_F32);
+  // staged (TMA) epilogue: bf16 output whose pixel pitch and base keep every 64-channel row 16-byte aligned
+  bool tma_epi = !f32out && BN >= kSubW && (p->y_pitch % 8 == 0) && ((((uintptr_t)y) & 15) == 0);
+  if (residual != nullptr && ((p->res_pitch % 8 != 0) || ((((uintptr_t)residual) & 15) != 0) ||
+                              TW * p->res_stride > 256 || TH * p->res_stride > 256))
+    tma_epi = false;
+  if (tma_epi) {
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)p->K, (cuuint64_t)p->Q, (cuuint64_t)p->P, (cuuint64_t)p->N};
+      cuuint64_t strides[3] = {(cuuint64_t)p->y_pitch * 2, (cuuint64_t)p->y_pitch * 2 * p->Q,
+                               (cuuint64_t)p->y_pitch * 2 * p->Q * p->P};
+      cuuint32_t box[4] = {(cuuint32_t)kSubW, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      MapKey key(y, 4, p->K, p->Q, p->P, p->N, p->y_pitch, TW, 1, 2);
+      if (int e = encode_cached(key, &prm.map_y, 4, y, dims, strides, box, estr)) return e;
+    }
+    if (residual != nullptr) {
+      const int rs = p->res_stride;
+      cuuint64_t dims[4] = {(cuuint64_t)p->K, (cuuint64_t)p->res_W, (cuuint64_t)p->res_H, (cuuint64_t)p->N};
+      cuuint64_t strides[3] = {(cuuint64_t)p->res_pitch * 2, (cuuint64_t)p->res_pitch * 2 * p->res_W,
+                               (cuuint64_t)p->res_pitch * 2 * p->res_W * p->res_H};
+      cuuint32_t box[4] = {(cuuint32_t)kSubW, (cuuint32_t)(TW * rs), (cuuint32_t)(TH * rs), 1};
+      cuuint32_t estr[4] = {1, (cuuint32_t)rs, (cuuint32_t)rs, 1};
+      MapKey key(residual, 4, p->K, p->res_W, p->res_H, p->N, p->res_pitch, TW, rs, 3);
+      if (int e = encode_cached(key, &prm.map_r, 4, residual, dims, strides, box, estr)) return e;
+    }
+  }
   prm.y = y; prm.scale = scale; prm.shift = shift; prm.res = residual;
   prm.bn_sum = bn_sum; prm.bn_sqsum = bn_sqsum;
   prm.N = p->N; prm.P = p->P; prm.Q = p->Q; prm.K = p->K; prm.C = p->C;
@@ -529,10 +628,11 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   prm.total_tiles = (int)total;
   prm.cchunks = (int)ceil_div(p->C, kBK);
   prm.num_kb = p->R * p->S * prm.cchunks;
-  const bool f32out = (p->y_dtype == WLSEG_F32);
-#define WLSEG_IGEMM_CASE(bn)                                                   \
-  case bn:                                                                     \
-    return f32out ? launch_igemm<bn, float>(prm, s) : launch_igemm<bn, __nv_bfloat16>(prm, s);
+#define WLSEG_IGEMM_CASE(bn)                                                          \
+  case bn:                                                                            \
+    if (f32out) return launch_igemm<bn, float, false>(prm, s);                        \
+    if (bn >= kSubW && tma_epi) return launch_igemm<bn, __nv_bfloat16, (bn >= kSubW)>(prm, s); \
+    return launch_igemm<bn, __nv_bfloat16, false>(prm, s);
   switch (BN) {
     WLSEG_IGEMM_CASE(32)
     WLSEG_IGEMM_CASE(64)

@@ -79,9 +79,63 @@ sgdm_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restric
   }
 }
 
+// shadow update of tf.train.ExponentialMovingAverage(decay, num_updates, zero_debias=True)
+// [TF-1.12 assign_moving_average/_zero_debias]: biased <- biased - (1-d)(biased - w);
+// unbiased = biased / (1 - d^local_step), where d = min(decay, (1+t)/(10+t)).
+__global__ void __launch_bounds__(256)
+ema_kernel(float* __restrict__ biased, float* __restrict__ shadow, const float* __restrict__ w, int64_t n,
+           float d, float inv_correction) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float b = biased[i];
+    b -= (1.0f - d) * (b - w[i]);
+    biased[i] = b;
+    shadow[i] = b * inv_correction;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_inplace_kernel(T* __restrict__ dst, const T* __restrict__ src, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    Vec8<T> va, vb;
+    va.load(dst + i * 8);
+    vb.load(src + i * 8);
+    va.unpack(a);
+    vb.unpack(b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    va.pack(a);
+    va.store(dst + i * 8);
+  }
+}
+
 }  // namespace wlseg
 
 using namespace wlseg;
+
+extern "C" int wlseg_ema_update(float* biased, float* shadow, const float* w, int64_t n, float decay,
+                                float inv_correction, wlseg_stream_t stream) {
+  WLSEG_CHECK_ARG(n >= 0 && (n == 0 || (biased && shadow && w)), "ema_update: bad args");
+  if (n == 0) return 0;
+  ema_kernel<<<bw_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(biased, shadow, w, n, decay, inv_correction);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wlseg_add_inplace(void* dst, const void* src, int64_t n, int32_t dtype, wlseg_stream_t stream) {
+  WLSEG_CHECK_ARG(n >= 0 && n % 8 == 0, "add_inplace: n (%lld) must be a multiple of 8", (long long)n);
+  if (n == 0) return 0;
+  WLSEG_CHECK_ARG(dst && src, "add_inplace: null pointer");
+  int grid = bw_grid(n / 8, 256, 8);
+  if (dtype == WLSEG_BF16)
+    add_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, n / 8);
+  else if (dtype == WLSEG_F32)
+    add_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float*)dst, (const float*)src, n / 8);
+  else
+    WLSEG_CHECK_ARG(false, "add_inplace: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int wlseg_sgdm_step(float* w, const float* g, float* acc, void* w_bf16, int64_t n, int64_t n_decay,
                                const float* lr_dev, float momentum, int32_t nesterov, float wd, float grad_scale,

@@ -345,3 +345,276 @@ class Network:
       out['l2_vehicle_logits'] = full[..., C1:C1 + Cv]
       out['l2_human_logits'] = full[..., C1 + Cv:]
     return out
+
+
+# ================================================================================================
+# Training: forward with batch statistics, fused loss forward/backward, backward pass
+# ================================================================================================
+class _Rec:
+  """Tape entry of one conv + BN (+ residual) (+ ReLU) layer."""
+  __slots__ = ('scope', 'spec', 'x', 'w', 'z', 'a', 'relu', 'has_res', 'geom', 'nch', 'kind')
+
+
+class TrainWorkspace:
+  """Per-step scratch that lives across steps: BN statistic accumulators (fp64), per-layer BN
+  scale / shift / saved mean / inverse std (fp32), the gradient arena (same layout as the master
+  parameter arena) and the momentum / EMA arenas."""
+
+  def __init__(self, params):
+    p = params
+    dev = p.device
+    n = p.n_chan_pad
+    self.stat = torch.zeros(4 * n, dtype=torch.float64, device=dev)  # [sum | sqsum | dgamma | dbeta]
+    self.bn = torch.zeros(4 * n, dtype=torch.float32, device=dev)    # [scale | shift | mean | invstd]
+    self.grads = torch.zeros(p.n_total, dtype=torch.float32, device=dev)
+    self.momentum = torch.zeros(p.n_total, dtype=torch.float32, device=dev)
+    self.ema_biased = None
+    self.ema_shadow = None
+    self.loss_sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    self.loss_counts = torch.zeros(3, dtype=torch.float64, device=dev)
+    self.losses = torch.zeros(4, dtype=torch.float32, device=dev)
+    self.reg_loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    self.lr = torch.zeros(1, dtype=torch.float32, device=dev)
+    self.n = n
+
+  def view(self, arena, slot, off, k):
+    return arena[slot * self.n + off:slot * self.n + off + k]
+
+
+class TrainNetwork(Network):
+  """Forward with batch statistics + backward.  BN follows every convolution (also the logits
+  convolutions, code/models/resnet50_extended_model_hierarchical.py:76-83); statistics are per
+  replica (the reference's default without --cross_replica_norm)."""
+
+  def __init__(self, params, dtype=torch.bfloat16, bn_decay=0.9, eps=1e-5, conv_algo=ops.ALGO_AUTO):
+    super().__init__(params, dtype, bn_decay, eps, conv_algo)
+    self.ws = TrainWorkspace(params)
+
+  # ---- one layer ---------------------------------------------------------------------------------
+  def _layer_fwd(self, x, scope, *, w=None, nch=None, relu=None, residual=None, pad=None, stride=None,
+                 dilation=None, out_hw=None, y_f32=False, kind='conv'):
+    spec = self.p.by_scope[scope]
+    if w is None:
+      w = self._weights(scope)
+    K = w.shape[0] if nch is None else nch
+    if pad is None:
+      pt, pl, P, Q = self._geom(spec, x.shape[1], x.shape[2])
+      pad, out_hw, stride, dilation = (pt, pl), (P, Q), spec.stride, spec.dilation
+    N = x.shape[0]
+    count = N * out_hw[0] * out_hw[1]
+    ws, off = self.ws, self.p.c_off[scope]
+    s1, s2 = ws.view(ws.stat, 0, off, K), ws.view(ws.stat, 1, off, K)
+    zdt = torch.float32 if y_f32 else self.dtype
+    z = self._conv(x, w, stride=stride, dilation=dilation, pad=pad, out_hw=out_hw, y_dtype=zdt,
+                   bn_sum=s1, bn_sqsum=s2)
+    scale, shift = ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K)
+    mean, invstd = ws.view(ws.bn, 2, off, K), ws.view(ws.bn, 3, off, K)
+    ops.bn_finalize(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
+                    self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd)
+    a = torch.empty_like(z)
+    do_relu = spec.relu if relu is None else relu
+    ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu)
+    rec = _Rec()
+    rec.scope, rec.spec, rec.x, rec.w, rec.z, rec.a = scope, spec, x, w, z, a
+    rec.relu, rec.has_res, rec.geom, rec.nch, rec.kind = do_relu, residual is not None, (pad, out_hw, stride, dilation), K, kind
+    self.tape[scope] = rec
+    return a
+
+  def _wgrad_view(self, scope, shape):
+    o = self.p.w_off[scope]
+    n = 1
+    for d in shape:
+      n *= d
+    return self.ws.grads[o:o + n].view(*shape)
+
+  def _layer_bwd(self, scope, da, need_dx=True, dx_out=None, dx_add=None):
+    """Backward of one tape entry.  Returns (dx, dres): dres is the gradient of the residual input
+    (None if the layer had none).  `dx_add` is accumulated into dx (fused into the tensor-core
+    dgrad epilogue when possible); `dx_out` lets the caller place dx (channel-sliced views)."""
+    rec = self.tape[scope]
+    ws, off, K = self.ws, self.p.c_off[scope], rec.nch
+    pad, out_hw, stride, dilation = rec.geom
+    N, H, W, C = rec.x.shape
+    count = N * out_hw[0] * out_hw[1]
+    mean, invstd = ws.view(ws.bn, 2, off, K), ws.view(ws.bn, 3, off, K)
+    dgamma, dbeta = ws.view(ws.stat, 2, off, K), ws.view(ws.stat, 3, off, K)
+    ops.bn_bwd_reduce(da, rec.a, rec.z, mean, invstd, count, K, rec.relu, dgamma, dbeta)
+    dz = torch.empty_like(rec.z)
+    dres = torch.empty_like(rec.z) if rec.has_res else None
+    ops.bn_bwd_apply(da, rec.a, rec.z, mean, invstd, self.p.gamma(scope, K), dgamma, dbeta, count, K, rec.relu, dz, dres)
+    if dz.dtype != self.dtype:  # fp32 logits layer feeding bf16 convolutions
+      dzc = torch.empty(dz.shape, dtype=self.dtype, device=self.dev)
+      ops.cast_f32_to_bf16(dz, dzc)
+      dz = dzc
+    # ---- filter gradient
+    if rec.kind == 'root_packed':
+      self._root_wgrad(rec, dz)
+    else:
+      prm = ops.conv_params((N, H, W, C), tuple(rec.w.shape), stride=stride, dilation=dilation, pad=pad,
+                            out_hw=out_hw, x_pitch=rec.x.stride(2), y_pitch=dz.stride(2), dtype=self.code)
+      ops.conv2d_wgrad(prm, rec.x, dz, self._wgrad_view(scope, rec.w.shape))
+    if not need_dx:
+      return None, dres
+    # ---- data gradient
+    dx = dx_out if dx_out is not None else torch.empty((N, H, W, C), dtype=self.dtype, device=self.dev)
+    R, S = rec.w.shape[1], rec.w.shape[2]
+    done = False
+    if stride == 1 and self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT and K % 8 == 0:
+      # stride-1 dgrad == fprop over dz with the 180-degree rotated, transposed filter bank
+      wf = torch.empty((C, R, S, K), dtype=self.dtype, device=self.dev)
+      ops.weights_transpose_flip(rec.w, wf)
+      fpad = (dilation * (R - 1) - pad[0], dilation * (S - 1) - pad[1])
+      self._conv(dz, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx)
+      done = True
+    if not done:
+      prm = ops.conv_params((N, H, W, C), tuple(rec.w.shape), stride=stride, dilation=dilation, pad=pad,
+                            out_hw=out_hw, x_pitch=dx.stride(2), y_pitch=dz.stride(2), dtype=self.code)
+      ops.conv2d_dgrad(prm, dz, rec.w, dx)
+      if dx_add is not None:
+        assert dx.is_contiguous()
+        ops.add_inplace(dx, dx_add)
+    return dx, dres
+
+  # ---- root ----------------------------------------------------------------------------------------
+  def _root_fwd(self, images):
+    scope = f'{arch.RES}/conv1'
+    N, H, W, _ = images.shape
+    if self.dtype == torch.bfloat16:
+      Hs, Ws = (H + 1) // 2, (W + 1) // 2
+      packed = torch.empty((N, Hs, Ws, 64), dtype=torch.bfloat16, device=self.dev)
+      ops.conv1_pack(images, packed)
+      self._root_images = images
+      y = self._layer_fwd(packed, scope, w=self.p.conv1_packed_weights(torch.bfloat16), pad=(2, 0), stride=1,
+                          dilation=1, out_hw=(Hs, Ws), relu=True, kind='root_packed')
+    else:
+      y = self._layer_fwd(images.to(self.dtype), scope)
+    P, Q = (y.shape[1] + 1) // 2, (y.shape[2] + 1) // 2
+    pooled = torch.empty((N, P, Q, 64), dtype=self.dtype, device=self.dev)
+    ops.maxpool_same_fwd(y, pooled, 3, 2)
+    self.tape['pool1'] = (y, pooled)
+    return pooled
+
+  def _root_wgrad(self, rec, dz):
+    """Filter gradient of the 7x7/2 root convolution on the ORIGINAL image and geometry (the packed
+    tensor only serves the forward GEMM)."""
+    scope = rec.scope
+    img = self._root_images
+    if img.dtype != self.dtype:
+      imgc = torch.empty(img.shape, dtype=self.dtype, device=self.dev)
+      ops.cast_f32_to_bf16(img.contiguous(), imgc)
+      img = imgc
+    N, H, W, _ = img.shape
+    spec = rec.spec
+    pt, pl, P, Q = self._geom(spec, H, W)
+    prm = ops.conv_params((N, H, W, 3), (64, 7, 7, 3), stride=2, pad=(pt, pl), out_hw=(P, Q), dtype=self.code)
+    ops.conv2d_wgrad(prm, img, dz, self._wgrad_view(scope, (64, 7, 7, 3)))
+
+  def _root_bwd(self, dpool):
+    y, pooled = self.tape['pool1']
+    dy = torch.empty_like(y)
+    ops.maxpool_same_bwd(y, dpool, dy, 3, 2)
+    self._layer_bwd(f'{arch.RES}/conv1', dy, need_dx=False)
+
+  # ---- bottleneck units ------------------------------------------------------------------------------
+  def _unit_fwd(self, x, u):
+    if u.has_shortcut_conv:
+      sc = self._layer_fwd(x, f'{u.scope}/shortcut')
+    elif u.stride > 1:
+      N, H, W, C = x.shape
+      sc = torch.empty((N, (H + u.stride - 1) // u.stride, (W + u.stride - 1) // u.stride, C), dtype=self.dtype,
+                       device=self.dev)
+      ops.maxpool_same_fwd(x, sc, 1, u.stride)
+    else:
+      sc = x
+    r = self._layer_fwd(x, f'{u.scope}/conv1')
+    r = self._layer_fwd(r, f'{u.scope}/conv2')
+    self.tape[u.scope] = x
+    return self._layer_fwd(r, f'{u.scope}/conv3', relu=True, residual=sc)
+
+  def _unit_bwd(self, dout, u):
+    x = self.tape[u.scope]
+    dr, dsc = self._layer_bwd(f'{u.scope}/conv3', dout)
+    dr, _ = self._layer_bwd(f'{u.scope}/conv2', dr)
+    if u.has_shortcut_conv:
+      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr)
+      dx, _ = self._layer_bwd(f'{u.scope}/shortcut', dsc, dx_add=dx)
+    elif u.stride > 1:
+      dsub = torch.empty_like(x)
+      ops.maxpool_same_bwd(x, dsc, dsub, 1, u.stride)
+      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsub)
+    else:
+      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsc)
+    return dx
+
+  # ---- whole network -----------------------------------------------------------------------------------
+  def forward_train(self, images):
+    """-> post-BN low-res logits fp32 [N, h, w, logits_pitch] (tape recorded for backward)."""
+    self.tape = {}
+    self.ws.stat.zero_()
+    x = self._root_fwd(images)
+    for u in arch.units():
+      x = self._unit_fwd(x, u)
+    f = self._layer_fwd(x, 'feature_extractor/extension/decrease_fdims')
+    N, h, w, d = f.shape
+    au = arch.adaptation_units(d)
+    s0 = f'{au[0].scope}/conv1'
+    o = self.p.w_off[s0]
+    arena = self.p.operand if self.dtype == torch.bfloat16 else self.p.master
+    w1 = arena[o:o + 3 * d * d].view(3 * d, 1, 1, d)
+    a1 = self._layer_fwd(f, s0, w=w1, nch=3 * d, pad=(0, 0), stride=1, dilation=1, out_hw=(h, w), relu=True)
+    pitch = self.hier.logits_pitch
+    logits = torch.zeros((N, h, w, pitch), dtype=torch.float32, device=self.dev)
+    self.tape['features'] = f
+    c0 = 0
+    for b, (u, (_, lg)) in enumerate(zip(au, arch.BRANCHES)):
+      r = self._layer_fwd(a1[..., b * d:(b + 1) * d], f'{u.scope}/conv2')
+      r = self._layer_fwd(r, f'{u.scope}/conv3', relu=True, residual=f)
+      scope = f'softmax_classifier/{lg}'
+      ck = self.p.by_scope[scope].K
+      lz = self._layer_fwd(r, scope, y_f32=True, relu=False)
+      logits[..., c0:c0 + ck] = lz  # tiny [N,h,w,ck] placement into the pitched logits buffer
+      c0 += ck
+    return logits
+
+  def backward(self, dlogits):
+    """dlogits: fp32 [N, h, w, logits_pitch] gradient wrt the post-BN low-res logits.  Fills the
+    gradient arena (conv kernels, gammas, betas)."""
+    ws = self.ws
+    f = self.tape['features']
+    N, h, w, d = f.shape
+    au = arch.adaptation_units(d)
+    da1 = torch.empty((N, h, w, 3 * d), dtype=self.dtype, device=self.dev)
+    df = None
+    c0 = 0
+    for b, (u, (_, lg)) in enumerate(zip(au, arch.BRANCHES)):
+      scope = f'softmax_classifier/{lg}'
+      ck = self.p.by_scope[scope].K
+      dl = dlogits[..., c0:c0 + ck].contiguous()
+      c0 += ck
+      dr, _ = self._layer_bwd(scope, dl)
+      dr, dres = self._layer_bwd(f'{u.scope}/conv3', dr)
+      self._layer_bwd(f'{u.scope}/conv2', dr, dx_out=da1[..., b * d:(b + 1) * d])
+      df = dres if df is None else ops.add_inplace(df, dres)
+    s0 = f'{au[0].scope}/conv1'
+    dx, _ = self._layer_bwd(s0, da1, dx_add=df)
+    dx, _ = self._layer_bwd('feature_extractor/extension/decrease_fdims', dx)
+    for u in reversed(arch.units()):
+      dx = self._unit_bwd(dx, u)
+    self._root_bwd(dx)
+    # BN parameter gradients: fp64 accumulators -> fp32 gradient arena
+    n = self.p.n_chan_pad
+    ws.grads[self.p.n_conv_pad:self.p.n_conv_pad + n] = ws.stat[2 * n:3 * n].to(torch.float32)
+    ws.grads[self.p.n_conv_pad + n:self.p.n_conv_pad + 2 * n] = ws.stat[3 * n:4 * n].to(torch.float32)
+    return ws.grads
+
+  def loss_and_grad(self, logits, labels, H, W, l2_coef=0.1, grad_scale=1.0):
+    """define_losses (TRAIN) + its gradient wrt the low-res logits, one fused kernel + finalize."""
+    ws = self.ws
+    ws.loss_sums.zero_()
+    ws.loss_counts.zero_()
+    dlogits = torch.zeros_like(logits)
+    ops.loss_fwd_bwd(self.hstruct, logits, H, W, labels.get('prolabels_per_pixel'),
+                     labels.get('prolabels_per_bbox'), labels.get('prolabels_per_image'), ws.loss_sums,
+                     ws.loss_counts, dlogits)
+    ops.loss_finalize(self.hstruct, ws.loss_sums, ws.loss_counts, l2_coef, grad_scale, dlogits, ws.losses)
+    return ws.losses, dlogits

@@ -66,6 +66,8 @@ _SIGNATURES = {
                                            _vp]),
     'wlseg_confmat_accumulate': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _c_int, _vp, _vp, _vp]),
     'wlseg_sgdm_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _c_f, _c_int, _c_f, _c_f, _vp, _vp]),
+    'wlseg_ema_update': (ctypes.c_int, [_vp, _vp, _vp, _c_i64, _c_f, _c_f, _vp]),
+    'wlseg_add_inplace': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
     'wlseg_cast_f32_to_bf16': (ctypes.c_int, [_vp, _vp, _c_i64, _vp]),
     'wlseg_cast_bf16_to_f32': (ctypes.c_int, [_vp, _vp, _c_i64, _vp]),
     'wlseg_weights_transpose_flip': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
@@ -305,3 +307,17 @@ def sgdm_step(w, g, acc, w_bf16, n_decay, lr_dev, momentum, nesterov, wd, grad_s
   _check(lib().wlseg_sgdm_step(_ptr(w), _ptr(g), _ptr(acc), _ptr(w_bf16), w.numel(), n_decay, _ptr(lr_dev), momentum,
                                int(nesterov), wd, grad_scale, _ptr(reg_loss), _stream()), 'wlseg_sgdm_step')
   _count()
+
+
+def ema_update(biased, shadow, w, decay, inv_correction):
+  _check(lib().wlseg_ema_update(_ptr(biased), _ptr(shadow), _ptr(w), w.numel(), decay, inv_correction, _stream()),
+         'wlseg_ema_update')
+  _count()
+
+
+def add_inplace(dst, src):
+  assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel() and dst.dtype == src.dtype
+  _check(lib().wlseg_add_inplace(_ptr(dst), _ptr(src), dst.numel(), dtype_code(dst.dtype), _stream()),
+         'wlseg_add_inplace')
+  _count()
+  return dst
