@@ -43,6 +43,7 @@ def parse_args():
   ap.add_argument('--height', type=int, default=None)
   ap.add_argument('--width', type=int, default=None)
   ap.add_argument('--batch', type=int, default=None)
+  ap.add_argument('--mixed', action='store_true', help='train workload: add 8 bbox + 4 image-level images per GPU')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--detail', type=str, default=None, help='write the per-kernel-class roofline table here')
@@ -139,6 +140,38 @@ def cpu_reference_eval(dataset, h, w, steps, warmup, images_per_step=1):
   return {'value': mpix / total, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': 'port',
           'sample': f'{len(times)} step(s) of {images_per_step} image(s) {h}x{w}, oracle fp32 on CPU, '
                     f'{warmup} warm-up', 'ms_per_step': 1e3 * total / len(times)}
+
+
+def cpu_reference_train(dataset, h, w):
+  """The reference algorithm's training step (oracle: fp32 PyTorch-CPU restatement, autograd
+  backward, momentum update) on ONE image, all host cores."""
+  import torch
+  from oracle import losses as olosses
+  from oracle import network as onet
+  from oracle import optimizer as oopt
+  from oracle.tables import TABLES
+  torch.set_num_threads(os.cpu_count() or 1)
+  ncls = TABLES[dataset]['num_classes']
+  params = {k: v.clone().requires_grad_(not k.endswith(('moving_mean', 'moving_variance')))
+            for k, v in onet.init_params(dataset, seed=0).items()}
+  g = torch.Generator().manual_seed(1234)
+  images = torch.rand(1, h, w, 3, generator=g) * 2 - 1
+  labels = {'prolabels_per_pixel': torch.randint(0, ncls, (1, h, w), generator=g, dtype=torch.int32)}
+  acc = {k: torch.zeros_like(v) for k, v in params.items() if v.requires_grad}
+  t0 = time.perf_counter()
+  net = onet.Net(params, dataset, training=True)
+  pred = net.forward(images)
+  loss = olosses.define_losses(pred, labels, dataset)['total']
+  loss.backward()
+  with torch.no_grad():
+    for k, v in params.items():
+      if v.requires_grad:
+        wn, an = oopt.momentum_step(v, v.grad + (0.00017 * v if k.endswith('weights') else 0.0), acc[k], 0.01)
+        v.copy_(wn)
+        acc[k] = an
+  dt = time.perf_counter() - t0
+  return {'value': 1.0 / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+          'sample': f'1 training step on 1 image {h}x{w}, oracle fp32 autograd on CPU, no warm-up'}
 
 
 def run_reference(args):
@@ -346,7 +379,7 @@ def main():
     return run_reference(args)
   if args.workload == 'train':
     from wlseg import train_bench
-    return train_bench.run(args)
+    return train_bench.run(args, cpu_train_sample=cpu_reference_train)
   return run_wlseg_eval(args)
 
 

@@ -202,9 +202,11 @@ int wlseg_sgdm_step(float* w, const float* g, float* acc, void* w_bf16, int64_t 
                     const float* lr_dev, float momentum, int32_t nesterov, float wd,
                     float grad_scale, double* reg_loss, wlseg_stream_t stream);
 
-/* Shadow variables of tf.train.ExponentialMovingAverage(decay, num_updates=global_step,
- * zero_debias=True) (estimator/define_estimator_hierarchical.py:96-111): biased <- biased -
- * (1-decay)*(biased - w); shadow = biased * inv_correction with inv_correction = 1/(1-decay^t). */
+/* Shadow variables of tf.train.ExponentialMovingAverage(decay, num_updates=global_step)
+ * (estimator/define_estimator_hierarchical.py:96-111): biased <- biased - (1-decay)*(biased - w);
+ * shadow = biased * inv_correction.  For tf.Variables TF initialises the shadow with the variable
+ * and applies no zero-debiasing: pass biased == shadow and inv_correction = 1; a zero-debiased
+ * average (plain tensors) passes a zero-initialised `biased` and 1/(1-decay^t). */
 int wlseg_ema_update(float* biased, float* shadow, const float* w, int64_t n, float decay,
                      float inv_correction, wlseg_stream_t stream);
 

@@ -183,14 +183,92 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
   }
 }
 
+// ---- generic path for channel counts that are not a multiple of 8 (the logits layers: 14/7/3 and
+// 53/12/5 channels).  Tiny tensors; one thread per (row lane, channel), fp64 partial sums.
+constexpr int kSmallMaxC = 64;
+
+template <typename T, bool kBackward>
+__global__ void __launch_bounds__(kBnThreads)
+bn_reduce_small_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* __restrict__ z,
+                       const float* __restrict__ mean, const float* __restrict__ invstd, int64_t count, int C,
+                       int pitch, int relu, double* __restrict__ out0, double* __restrict__ out1) {
+  __shared__ double part[2][kBnThreads];
+  const int lanes = kBnThreads / C;
+  const int c = threadIdx.x % C, ty = threadIdx.x / C;
+  double s0 = 0.0, s1 = 0.0;
+  if (ty < lanes) {
+    const float mu = kBackward ? mean[c] : 0.f, is = kBackward ? invstd[c] : 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * lanes + ty; row < count; row += (int64_t)gridDim.x * lanes) {
+      float f = to_f32<T>(a[row * pitch + c]);
+      if (!kBackward) {
+        s0 += f;
+        s1 += (double)f * f;
+      } else {
+        if (relu && !(to_f32<T>(yact[row * pitch + c]) > 0.f)) f = 0.f;
+        s0 += f * (to_f32<T>(z[row * pitch + c]) - mu) * is;
+        s1 += f;
+      }
+    }
+  }
+  part[0][threadIdx.x] = s0;
+  part[1][threadIdx.x] = s1;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int l = 0; l < lanes; ++l) { t0 += part[0][l * C + threadIdx.x]; t1 += part[1][l * C + threadIdx.x]; }
+    atomicAdd(out0 + threadIdx.x, t0);
+    atomicAdd(out1 + threadIdx.x, t1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_small_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                      const T* __restrict__ res, T* __restrict__ y, int64_t total, int C, int relu) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float f = to_f32<T>(z[i]) * scale[c] + shift[c];
+    if (res != nullptr) f += to_f32<T>(res[i]);
+    if (relu) f = fmaxf(f, 0.f);
+    y[i] = from_f32<T>(f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_small_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ z,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const float* __restrict__ gamma, const double* __restrict__ dgamma,
+                          const double* __restrict__ dbeta, int64_t total, int64_t count, int C, int relu,
+                          T* __restrict__ dz, T* __restrict__ dres) {
+  const float invn = 1.0f / (float)count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float g = to_f32<T>(dy[i]);
+    if (relu && !(to_f32<T>(yact[i]) > 0.f)) g = 0.f;
+    if (dres != nullptr) dres[i] = from_f32<T>(g);
+    const float is = invstd[c];
+    const float zh = (to_f32<T>(z[i]) - mean[c]) * is;
+    dz[i] = from_f32<T>(gamma[c] * is * (g - (float)dbeta[c] * invn - zh * (float)dgamma[c] * invn));
+  }
+}
+
 static int check_bn_shape(int64_t count, int C, const char* who) {
-  WLSEG_CHECK_ARG(count >= 0 && C > 0 && C % 8 == 0 && C <= 2048, "%s: C (%d) must be a multiple of 8 and <= 2048", who, C);
+  WLSEG_CHECK_ARG(count >= 0 && C > 0 && ((C % 8 == 0 && C <= 2048) || C <= kSmallMaxC),
+                  "%s: C (%d) must be a multiple of 8 and <= 2048, or <= %d", who, C, kSmallMaxC);
   return 0;
 }
 
 template <typename T, bool kBackward>
 static int launch_reduce(const void* a, const void* y, const void* z, const float* mean, const float* invstd,
                          int64_t count, int C, int pitch, int relu, double* o0, double* o1, cudaStream_t s) {
+  if (C % 8 != 0) {
+    int grid = bw_grid(count * C, kBnThreads, 4);
+    bn_reduce_small_kernel<T, kBackward><<<grid, kBnThreads, 0, s>>>((const T*)a, (const T*)y, (const T*)z, mean,
+                                                                      invstd, count, C, pitch, relu, o0, o1);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
   const int cv = C / 8;
   const int lanes = kBnThreads / cv;
   size_t smem = (size_t)lanes * 2 * C * sizeof(float);
@@ -208,7 +286,7 @@ using namespace wlseg;
 extern "C" int wlseg_bn_stats(const void* z, int64_t count, int32_t C, int32_t pitch, int32_t dtype, double* sum,
                               double* sqsum, wlseg_stream_t stream) {
   if (int e = check_bn_shape(count, C, "bn_stats")) return e;
-  WLSEG_CHECK_ARG(pitch >= C && pitch % 8 == 0, "bn_stats: bad pitch %d", pitch);
+  WLSEG_CHECK_ARG(pitch >= C && (pitch % 8 == 0 || C % 8 != 0), "bn_stats: bad pitch %d", pitch);
   if (count == 0) return 0;
   WLSEG_CHECK_ARG(z && sum && sqsum, "bn_stats: null pointer");
   if (dtype == WLSEG_BF16)
@@ -238,6 +316,20 @@ extern "C" int wlseg_bn_apply(const void* z, const float* scale, const float* sh
   if (int e = check_bn_shape(count, C, "bn_apply")) return e;
   if (count == 0) return 0;
   WLSEG_CHECK_ARG(z && scale && shift && y, "bn_apply: null pointer");
+  if (C % 8 != 0) {
+    const int64_t total = count * C;
+    int g = bw_grid(total, 256, 8);
+    if (dtype == WLSEG_BF16)
+      bn_apply_small_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, scale, shift,
+                                                                 (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, total, C, relu);
+    else if (dtype == WLSEG_F32)
+      bn_apply_small_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const float*)z, scale, shift, (const float*)residual,
+                                                                 (float*)y, total, C, relu);
+    else
+      WLSEG_CHECK_ARG(false, "bn_apply: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
   int grid = bw_grid(count * (C / 8), 256, 8);
   if (dtype == WLSEG_BF16)
     bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, scale, shift,
@@ -273,6 +365,22 @@ extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, 
   if (count == 0) return 0;
   WLSEG_CHECK_ARG(dy && z && mean && invstd && gamma && dgamma && dbeta && dz && (!relu || y),
                   "bn_bwd_apply: null pointer");
+  if (C % 8 != 0) {
+    const int64_t total = count * C;
+    int g = bw_grid(total, 256, 8);
+    if (dtype == WLSEG_BF16)
+      bn_bwd_apply_small_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, invstd, gamma, dgamma, dbeta,
+          total, count, C, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
+    else if (dtype == WLSEG_F32)
+      bn_bwd_apply_small_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z,
+                                                                     mean, invstd, gamma, dgamma, dbeta, total, count, C,
+                                                                     relu, (float*)dz, (float*)dres);
+    else
+      WLSEG_CHECK_ARG(false, "bn_bwd_apply: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
   int grid = bw_grid(count * (C / 8), 256, 8);
   if (dtype == WLSEG_BF16)
     bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(

@@ -172,6 +172,9 @@ conv_wgrad_direct_kernel(const wlseg_conv_params p, const T* __restrict__ x, con
   }
 }
 
+int conv_wgrad_tcgen05(const wlseg_conv_params* p, const void* x, const void* dy, float* dw, cudaStream_t s);
+bool conv_wgrad_tcgen05_supported(const wlseg_conv_params* p);
+
 int check_conv_params(const wlseg_conv_params* p) {
   WLSEG_CHECK_ARG(p != nullptr, "conv: params is NULL");
   WLSEG_CHECK_ARG(p->N >= 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->K > 0 && p->R > 0 && p->S > 0 && p->P > 0 &&
@@ -237,6 +240,14 @@ extern "C" int wlseg_conv2d_wgrad(const wlseg_conv_params* p, const void* x, con
   if (p->N == 0) return 0;
   WLSEG_CHECK_ARG(x && dy, "conv_wgrad: null pointer");
   WLSEG_CHECK_ARG(p->y_dtype == p->dtype, "conv_wgrad: dy must be stored in dtype");
+  {
+    int algo = p->algo;
+    if (algo == WLSEG_ALGO_AUTO) algo = conv_wgrad_tcgen05_supported(p) ? WLSEG_ALGO_TCGEN05 : WLSEG_ALGO_DIRECT;
+    if (algo == WLSEG_ALGO_TCGEN05) {
+      WLSEG_CHECK_ARG(conv_wgrad_tcgen05_supported(p), "conv_wgrad: configuration not covered by the tcgen05 kernel");
+      return conv_wgrad_tcgen05(p, x, dy, dw, (cudaStream_t)stream);
+    }
+  }
   const int64_t npix = (int64_t)p->N * p->P * p->Q;
   int gx = bw_grid(total, 128, 4);
   // enough pixel chunks to fill the machine a few times over

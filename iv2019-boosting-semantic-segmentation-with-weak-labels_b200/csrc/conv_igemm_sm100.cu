@@ -37,6 +37,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "common.cuh"
 #include "tc_sm100.cuh"
@@ -497,12 +498,23 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // the only shared mutable state of the library: a mutex-guarded tensor-map cache
-typedef std::tuple<const void*, int, int, int, int, int, int, int, int, int> MapKey;
+typedef std::vector<uint64_t> MapKeyV;
 static std::mutex g_map_mutex;
-static std::map<MapKey, CUtensorMap> g_map_cache;
+static std::map<MapKeyV, CUtensorMap> g_map_cache;
 
-static int encode_cached(const MapKey& key, CUtensorMap* out, int rank, const void* base, const cuuint64_t* dims,
-                         const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr) {
+// Encodes (or fetches from the cache) a SWIZZLE_128B tiled tensor map.  elem_bytes 2 = bf16, 4 = fp32.
+int encode_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, int kind) {
+  MapKeyV key;
+  key.reserve(4 + 4 * rank);
+  key.push_back((uint64_t)(uintptr_t)base);
+  key.push_back((uint64_t)elem_bytes);
+  key.push_back((uint64_t)rank);
+  key.push_back((uint64_t)kind);
+  for (int i = 0; i < rank; ++i) key.push_back(dims[i]);
+  for (int i = 0; i + 1 < rank; ++i) key.push_back(strides_bytes[i]);
+  for (int i = 0; i < rank; ++i) key.push_back(box[i]);
+  for (int i = 0; i < rank; ++i) key.push_back(estr[i]);
   std::lock_guard<std::mutex> lock(g_map_mutex);
   auto it = g_map_cache.find(key);
   if (it != g_map_cache.end()) {
@@ -510,11 +522,15 @@ static int encode_cached(const MapKey& key, CUtensorMap* out, int rank, const vo
     return 0;
   }
   EncodeTiledFn fn = get_encode_fn();
-  WLSEG_CHECK_ARG(fn != nullptr, "conv(tcgen05): cuTensorMapEncodeTiled not available from the driver");
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  WLSEG_CHECK_ARG(r == CUDA_SUCCESS, "conv(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  WLSEG_CHECK_ARG(fn != nullptr, "tensor map: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t d[5], st[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WLSEG_CHECK_ARG(r == CUDA_SUCCESS, "tensor map: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   if (g_map_cache.size() > 8192) g_map_cache.clear();
   g_map_cache[key] = *out;
   return 0;
@@ -568,21 +584,19 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   const int TW = 1 << tw_log2, TH = kBM / TW;
   WLSEG_CHECK_ARG(TW * p->stride <= 256 && TH * p->stride <= 256, "conv(tcgen05): TMA box too large");
   {
-    cuuint64_t dims[4] = {(cuuint64_t)p->C, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
-    cuuint64_t strides[3] = {(cuuint64_t)p->x_pitch * 2, (cuuint64_t)p->x_pitch * 2 * p->W,
-                             (cuuint64_t)p->x_pitch * 2 * p->W * p->H};
-    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(TW * p->stride), (cuuint32_t)(TH * p->stride), 1};
-    cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
-    MapKey key(x, 4, p->C, p->W, p->H, p->N, p->x_pitch, TW, p->stride, 0);
-    if (int e = encode_cached(key, &prm.map_a, 4, x, dims, strides, box, estr)) return e;
+    uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+    uint64_t strides[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->x_pitch * 2 * p->W,
+                           (uint64_t)p->x_pitch * 2 * p->W * p->H};
+    uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(TW * p->stride), (uint32_t)(TH * p->stride), 1};
+    uint32_t estr[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
+    if (int e = encode_tensor_map(&prm.map_a, x, 2, 4, dims, strides, box, estr, 0)) return e;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)p->C, (cuuint64_t)(p->R * p->S), (cuuint64_t)p->K};
-    cuuint64_t strides[2] = {(cuuint64_t)p->C * 2, (cuuint64_t)p->C * 2 * p->R * p->S};
-    cuuint32_t box[3] = {(cuuint32_t)kBK, 1, (cuuint32_t)BN};
-    cuuint32_t estr[3] = {1, 1, 1};
-    MapKey key(w, 3, p->C, p->R * p->S, p->K, BN, 0, 0, 0, 1);
-    if (int e = encode_cached(key, &prm.map_b, 3, w, dims, strides, box, estr)) return e;
+    uint64_t dims[3] = {(uint64_t)p->C, (uint64_t)(p->R * p->S), (uint64_t)p->K};
+    uint64_t strides[2] = {(uint64_t)p->C * 2, (uint64_t)p->C * 2 * p->R * p->S};
+    uint32_t box[3] = {(uint32_t)kBK, 1, (uint32_t)BN};
+    uint32_t estr[3] = {1, 1, 1};
+    if (int e = encode_tensor_map(&prm.map_b, w, 2, 3, dims, strides, box, estr, 1)) return e;
   }
   const bool f32out = (p->y_dtype == WLSEG_F32);
   // staged (TMA) epilogue: bf16 output whose pixel pitch and base keep every 64-channel row 16-byte aligned
@@ -592,23 +606,21 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
     tma_epi = false;
   if (tma_epi) {
     {
-      cuuint64_t dims[4] = {(cuuint64_t)p->K, (cuuint64_t)p->Q, (cuuint64_t)p->P, (cuuint64_t)p->N};
-      cuuint64_t strides[3] = {(cuuint64_t)p->y_pitch * 2, (cuuint64_t)p->y_pitch * 2 * p->Q,
-                               (cuuint64_t)p->y_pitch * 2 * p->Q * p->P};
-      cuuint32_t box[4] = {(cuuint32_t)kSubW, (cuuint32_t)TW, (cuuint32_t)TH, 1};
-      cuuint32_t estr[4] = {1, 1, 1, 1};
-      MapKey key(y, 4, p->K, p->Q, p->P, p->N, p->y_pitch, TW, 1, 2);
-      if (int e = encode_cached(key, &prm.map_y, 4, y, dims, strides, box, estr)) return e;
+      uint64_t dims[4] = {(uint64_t)p->K, (uint64_t)p->Q, (uint64_t)p->P, (uint64_t)p->N};
+      uint64_t strides[3] = {(uint64_t)p->y_pitch * 2, (uint64_t)p->y_pitch * 2 * p->Q,
+                             (uint64_t)p->y_pitch * 2 * p->Q * p->P};
+      uint32_t box[4] = {(uint32_t)kSubW, (uint32_t)TW, (uint32_t)TH, 1};
+      uint32_t estr[4] = {1, 1, 1, 1};
+      if (int e = encode_tensor_map(&prm.map_y, y, 2, 4, dims, strides, box, estr, 2)) return e;
     }
     if (residual != nullptr) {
       const int rs = p->res_stride;
-      cuuint64_t dims[4] = {(cuuint64_t)p->K, (cuuint64_t)p->res_W, (cuuint64_t)p->res_H, (cuuint64_t)p->N};
-      cuuint64_t strides[3] = {(cuuint64_t)p->res_pitch * 2, (cuuint64_t)p->res_pitch * 2 * p->res_W,
-                               (cuuint64_t)p->res_pitch * 2 * p->res_W * p->res_H};
-      cuuint32_t box[4] = {(cuuint32_t)kSubW, (cuuint32_t)(TW * rs), (cuuint32_t)(TH * rs), 1};
-      cuuint32_t estr[4] = {1, (cuuint32_t)rs, (cuuint32_t)rs, 1};
-      MapKey key(residual, 4, p->K, p->res_W, p->res_H, p->N, p->res_pitch, TW, rs, 3);
-      if (int e = encode_cached(key, &prm.map_r, 4, residual, dims, strides, box, estr)) return e;
+      uint64_t dims[4] = {(uint64_t)p->K, (uint64_t)p->res_W, (uint64_t)p->res_H, (uint64_t)p->N};
+      uint64_t strides[3] = {(uint64_t)p->res_pitch * 2, (uint64_t)p->res_pitch * 2 * p->res_W,
+                             (uint64_t)p->res_pitch * 2 * p->res_W * p->res_H};
+      uint32_t box[4] = {(uint32_t)kSubW, (uint32_t)(TW * rs), (uint32_t)(TH * rs), 1};
+      uint32_t estr[4] = {1, (uint32_t)rs, (uint32_t)rs, 1};
+      if (int e = encode_tensor_map(&prm.map_r, residual, 2, 4, dims, strides, box, estr, 3)) return e;
     }
   }
   prm.y = y; prm.scale = scale; prm.shift = shift; prm.res = residual;

@@ -83,7 +83,7 @@ sgdm_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restric
 // [TF-1.12 assign_moving_average/_zero_debias]: biased <- biased - (1-d)(biased - w);
 // unbiased = biased / (1 - d^local_step), where d = min(decay, (1+t)/(10+t)).
 __global__ void __launch_bounds__(256)
-ema_kernel(float* __restrict__ biased, float* __restrict__ shadow, const float* __restrict__ w, int64_t n,
+ema_kernel(float* biased, float* shadow, const float* __restrict__ w, int64_t n,
            float d, float inv_correction) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float b = biased[i];

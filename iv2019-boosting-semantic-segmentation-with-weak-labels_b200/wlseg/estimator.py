@@ -162,6 +162,43 @@ class Estimator:
                                bn_decay=getattr(self.settings, 'batch_norm_decay', 0.9))
     return path
 
+  # ---- TRAIN --------------------------------------------------------------------------------------
+  def train(self, batches, max_steps, log_every=0):
+    """define_estimator TRAIN branch driven for `max_steps` steps (create_train_op + the
+    MonitoredTrainingSession loop, define_estimator_hierarchical.py:77-159).  `batches` yields
+    (features, labels) with host or device tensors in the reference's contract.
+    Returns the per-step loss vectors [total, segmentation, l1, l2_vehicle, l2_human, regularization]
+    as one host array (read back once per step, asynchronously)."""
+    from wlseg import trainer as wtrainer
+    s = self.settings
+    dev = self.device
+    if getattr(self, 'trainer', None) is None:
+      self.trainer = wtrainer.Trainer(self.params, s, dtype=self.dtype, rank=getattr(s, 'rank', 0),
+                                      world_size=getattr(s, 'world_size', 1) if getattr(s, 'distribute', False) else 1)
+      self.trainer.global_step = self.global_step
+    tr = self.trainer
+    pre = _Prefetcher(batches, dev)
+    host = torch.zeros((max(1, max_steps), 6), dtype=torch.float32).pin_memory()
+    steps = 0
+    save_every = getattr(s, 'save_checkpoints_steps', None)
+    for features, labels in pre:
+      if steps >= max_steps:
+        break
+      lr = learning_rate(s, tr.global_step)
+      out = tr.step(features, {k: v for k, v in labels.items() if v is not None}, lr)
+      host[steps].copy_(out, non_blocking=True)
+      steps += 1
+      self.global_step = tr.global_step
+      if log_every and steps % log_every == 0 and getattr(s, 'rank', 0) == 0:
+        torch.cuda.synchronize(dev)
+        print(f'step {tr.global_step}: total loss {float(host[steps - 1, 0]):.4f} lr {lr:g}', flush=True)
+      if save_every and getattr(s, 'rank', 0) == 0 and tr.global_step % save_every == 0 and getattr(s, 'save_checkpoints', True):
+        self.save(s.log_dir)
+    torch.cuda.synchronize(dev)
+    self.last_h2d_bytes = pre.h2d_bytes
+    self.last_d2h_bytes = steps * 6 * 4
+    return host[:steps].numpy().copy()
+
   # ---- EVAL ---------------------------------------------------------------------------------------
   def evaluate(self, batches, num_classes, lut=None):
     """define_estimator EVAL branch: forward, remap cids, resize to label size, streaming confusion

@@ -352,7 +352,8 @@ class Network:
 # ================================================================================================
 class _Rec:
   """Tape entry of one conv + BN (+ residual) (+ ReLU) layer."""
-  __slots__ = ('scope', 'spec', 'x', 'w', 'z', 'a', 'relu', 'has_res', 'geom', 'nch', 'kind')
+  __slots__ = ('scope', 'spec', 'x', 'w', 'z', 'a', 'relu', 'has_res', 'geom', 'nch', 'kind',
+               'res', 'da', 'dz', 'dx', 'dx_add')  # the last five only when TrainNetwork.keep (tests)
 
 
 class TrainWorkspace:
@@ -389,6 +390,26 @@ class TrainNetwork(Network):
   def __init__(self, params, dtype=torch.bfloat16, bn_decay=0.9, eps=1e-5, conv_algo=ops.ALGO_AUTO):
     super().__init__(params, dtype, bn_decay, eps, conv_algo)
     self.ws = TrainWorkspace(params)
+    self.grad_ready = None  # callback(lo): every conv-kernel gradient at arena offset >= lo is final
+    self.keep = False       # tests: keep per-layer gradient tensors on the tape
+    self._order = {s.scope: i for i, s in enumerate(params.specs)}
+
+  def _mark_done(self, scope, n_elems):
+    """Bookkeeping for the gradient exchange: backward completes the arena roughly tail first."""
+    if self.grad_ready is None:
+      return
+    lo = self.p.w_off[scope]
+    i = self._order[scope]
+    specs = self.p.specs
+    while i < len(specs) and self.p.w_off[specs[i].scope] < lo + n_elems:
+      self._done[i] = True
+      i += 1
+    t = self._tail
+    while t > 0 and self._done[t - 1]:
+      t -= 1
+    if t != self._tail:
+      self._tail = t
+      self.grad_ready(self.p.w_off[specs[t].scope])
 
   # ---- one layer ---------------------------------------------------------------------------------
   def _layer_fwd(self, x, scope, *, w=None, nch=None, relu=None, residual=None, pad=None, stride=None,
@@ -417,6 +438,7 @@ class TrainNetwork(Network):
     rec = _Rec()
     rec.scope, rec.spec, rec.x, rec.w, rec.z, rec.a = scope, spec, x, w, z, a
     rec.relu, rec.has_res, rec.geom, rec.nch, rec.kind = do_relu, residual is not None, (pad, out_hw, stride, dilation), K, kind
+    rec.res = residual if self.keep else None
     self.tape[scope] = rec
     return a
 
@@ -442,27 +464,50 @@ class TrainNetwork(Network):
     dz = torch.empty_like(rec.z)
     dres = torch.empty_like(rec.z) if rec.has_res else None
     ops.bn_bwd_apply(da, rec.a, rec.z, mean, invstd, self.p.gamma(scope, K), dgamma, dbeta, count, K, rec.relu, dz, dres)
-    if dz.dtype != self.dtype:  # fp32 logits layer feeding bf16 convolutions
-      dzc = torch.empty(dz.shape, dtype=self.dtype, device=self.dev)
-      ops.cast_f32_to_bf16(dz, dzc)
+    wsrc = rec.w
+    if dz.dtype != self.dtype or (self.dtype == torch.bfloat16 and K % 8 != 0):
+      # logits layers (fp32 z, 14/7/3 channels) feeding bf16 tensor-core kernels: bf16 copy of dz with
+      # the channel count padded to a multiple of 8 (zero columns), TMA needs 16-byte pixel pitches
+      kp = (K + 7) // 8 * 8 if self.dtype == torch.bfloat16 else K
+      dzc = torch.zeros(dz.shape[:-1] + (kp,), dtype=self.dtype, device=self.dev)
+      dzc[..., :K] = dz
       dz = dzc
     # ---- filter gradient
     if rec.kind == 'root_packed':
       self._root_wgrad(rec, dz)
     else:
-      prm = ops.conv_params((N, H, W, C), tuple(rec.w.shape), stride=stride, dilation=dilation, pad=pad,
+      prm = ops.conv_params((N, H, W, C), (K,) + tuple(rec.w.shape[1:]), stride=stride, dilation=dilation, pad=pad,
                             out_hw=out_hw, x_pitch=rec.x.stride(2), y_pitch=dz.stride(2), dtype=self.code)
-      ops.conv2d_wgrad(prm, rec.x, dz, self._wgrad_view(scope, rec.w.shape))
+      prof = None
+      if self.profile is not None:
+        Rr, Ss = rec.w.shape[1], rec.w.shape[2]
+        prof = {'cls': 'wgrad_tc' if (self.dtype == torch.bfloat16 and C % 8 == 0) else 'wgrad_direct',
+                'flops': 2.0 * N * out_hw[0] * out_hw[1] * Rr * Ss * C * K,
+                'bytes': float(2 * (N * H * W * C + N * out_hw[0] * out_hw[1] * K) + 4 * K * Rr * Ss * C),
+                'e0': torch.cuda.Event(enable_timing=True), 'e1': torch.cuda.Event(enable_timing=True)}
+        prof['e0'].record()
+      ops.conv2d_wgrad(prm, rec.x, dz, self._wgrad_view(scope, (K,) + tuple(rec.w.shape[1:])))
+      if prof is not None:
+        prof['e1'].record()
+        self.profile.append(prof)
+    self._mark_done(scope, K * rec.spec.R * rec.spec.S * rec.spec.C)
+    if self.keep:
+      rec.da, rec.dz, rec.dx, rec.dx_add = da, dz, None, dx_add
     if not need_dx:
       return None, dres
     # ---- data gradient
     dx = dx_out if dx_out is not None else torch.empty((N, H, W, C), dtype=self.dtype, device=self.dev)
     R, S = rec.w.shape[1], rec.w.shape[2]
     done = False
-    if stride == 1 and self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT and K % 8 == 0:
+    if stride == 1 and self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT:
       # stride-1 dgrad == fprop over dz with the 180-degree rotated, transposed filter bank
+      Kp = dz.shape[-1]
       wf = torch.empty((C, R, S, K), dtype=self.dtype, device=self.dev)
-      ops.weights_transpose_flip(rec.w, wf)
+      ops.weights_transpose_flip(wsrc, wf)
+      if Kp != K:
+        wfp = torch.zeros((C, R, S, Kp), dtype=self.dtype, device=self.dev)
+        wfp[..., :K] = wf
+        wf = wfp
       fpad = (dilation * (R - 1) - pad[0], dilation * (S - 1) - pad[1])
       self._conv(dz, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx)
       done = True
@@ -473,6 +518,8 @@ class TrainNetwork(Network):
       if dx_add is not None:
         assert dx.is_contiguous()
         ops.add_inplace(dx, dx_add)
+    if self.keep:
+      rec.dx = dx
     return dx, dres
 
   # ---- root ----------------------------------------------------------------------------------------
@@ -495,19 +542,28 @@ class TrainNetwork(Network):
     return pooled
 
   def _root_wgrad(self, rec, dz):
-    """Filter gradient of the 7x7/2 root convolution on the ORIGINAL image and geometry (the packed
-    tensor only serves the forward GEMM)."""
+    """Filter gradient of the 7x7/2 root convolution, taken in the PACKED domain the forward GEMM
+    runs in (R=4, S=1, C=64 over the space-to-depth tensor, on the tensor cores) and gathered back:
+    every w[k, r, s, c] appears exactly once in the packed bank (conv1_packed_weights)."""
     scope = rec.scope
-    img = self._root_images
-    if img.dtype != self.dtype:
-      imgc = torch.empty(img.shape, dtype=self.dtype, device=self.dev)
-      ops.cast_f32_to_bf16(img.contiguous(), imgc)
-      img = imgc
-    N, H, W, _ = img.shape
-    spec = rec.spec
-    pt, pl, P, Q = self._geom(spec, H, W)
-    prm = ops.conv_params((N, H, W, 3), (64, 7, 7, 3), stride=2, pad=(pt, pl), out_hw=(P, Q), dtype=self.code)
-    ops.conv2d_wgrad(prm, img, dz, self._wgrad_view(scope, (64, 7, 7, 3)))
+    N, Hs, Ws, _ = rec.x.shape
+    pad, out_hw, stride, dilation = rec.geom
+    dw2 = torch.empty((64, 4, 1, 64), dtype=torch.float32, device=self.dev)
+    prm = ops.conv_params((N, Hs, Ws, 64), (64, 4, 1, 64), stride=stride, dilation=dilation, pad=pad, out_hw=out_hw,
+                          x_pitch=rec.x.stride(2), y_pitch=dz.stride(2), dtype=self.code)
+    ops.conv2d_wgrad(prm, rec.x, dz, dw2)
+    idx = self.p._derived.get('conv1_unpack_index')
+    if idx is None:
+      ii = []
+      for r in range(7):
+        a, i = (r + 1) // 2, (r + 1) % 2
+        for s_ in range(7):
+          b, j = (s_ + 1) // 2, (s_ + 1) % 2
+          for c in range(3):
+            ii.append(a * 64 + b * 16 + (i * 2 + j) * 3 + c)
+      idx = torch.tensor(ii, dtype=torch.long, device=self.dev)
+      self.p._derived['conv1_unpack_index'] = idx
+    self._wgrad_view(scope, (64, 7, 7, 3)).copy_(dw2.view(64, 256)[:, idx].view(64, 7, 7, 3))
 
   def _root_bwd(self, dpool):
     y, pooled = self.tape['pool1']
@@ -580,6 +636,8 @@ class TrainNetwork(Network):
     """dlogits: fp32 [N, h, w, logits_pitch] gradient wrt the post-BN low-res logits.  Fills the
     gradient arena (conv kernels, gammas, betas)."""
     ws = self.ws
+    self._done = [False] * len(self.p.specs)
+    self._tail = len(self.p.specs)
     f = self.tape['features']
     N, h, w, d = f.shape
     au = arch.adaptation_units(d)

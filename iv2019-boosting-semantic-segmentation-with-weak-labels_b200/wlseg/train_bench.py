@@ -1,0 +1,161 @@
+"""`bench.py --workload train`: training images/s at 768x768 crops (BASELINE.json configs[2] / [3]).
+
+One step = forward with batch statistics + fused hierarchical loss fwd/bwd + backward through the
+whole network + gradient all-reduce (N > 1) + fused SGD-momentum update, on synthetic
+Cityscapes-shaped batches of 4 images per GPU (strong labels; `--mixed` adds 8 bbox + 4 image-level
+images per GPU, the reference's 4:8:4 ratio, train.py:52-55).
+"""
+
+import json
+import os
+import time
+
+import torch
+
+
+def run(args, cpu_train_sample=None):
+  import torch.distributed as dist
+  from bench import ClockSampler, load_peaks  # noqa: E402 (bench.py is the caller)
+  from wlseg import arch, hierarchy, network, ops, problem_defs, synthetic, trainer as wtrainer
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py: no CUDA device; wlseg has no CPU fallback')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  H, W, NB = args.height or 768, args.width or 768, args.batch or 4
+  mixed = getattr(args, 'mixed', False)
+  npb, npi = (2 * NB, NB) if mixed else (0, 0)
+  hier = hierarchy.Hierarchy(args.dataset, problem_defs.GENERATORS[args.dataset]()['cids2labels'])
+  params = network.Params(hier, dev)
+  params.init_random(0)
+
+  class S:
+    pass
+  st = S()
+  st.momentum, st.use_nesterov, st.optimizer, st.regularization_weight = 0.9, False, 'SGDM', 0.00017
+  st.batch_norm_decay, st.distribute, st.ema_decay = 0.9, world > 1, 0.0
+  tr = wtrainer.Trainer(params, st, dtype=torch.bfloat16, rank=rank, world_size=world)
+  src = synthetic.SyntheticInputs(hier.num_classes, dev, rank=rank)
+  batches = [src.train_batch(NB, npb, npi, H, W) for _ in range(2)]
+
+  def step(i):
+    f, l = batches[i % 2]
+    return tr.step(f, {k: v for k, v in l.items() if v is not None}, 0.01)
+
+  for i in range(args.warmup):
+    step(i)
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  tr.net.profile = []
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  l0 = ops.launches
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(args.steps):
+    out = step(i)
+  e1.record()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  clocks = sampler.stop() if sampler else None
+  ms = e0.elapsed_time(e1)
+  launches = ops.launches - l0
+  prof, tr.net.profile = tr.net.profile, None
+  t = torch.tensor([ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_max = float(t.item())
+  nimg = NB + npb + npi
+  value = world * args.steps * nimg / (ms_max / 1e3)
+
+  peaks = load_peaks()
+  classes = {}
+  for rec in prof:
+    rec['ms'] = rec['e0'].elapsed_time(rec['e1'])
+    c = classes.setdefault(rec['cls'], {'flops': 0.0, 'ms': 0.0, 'launches': 0, 'bytes': 0.0})
+    c['flops'] += rec['flops']
+    c['ms'] += rec['ms']
+    c['bytes'] += rec['bytes']
+    c['launches'] += 1
+  roofline = None
+  tc = {k: v for k, v in classes.items() if k.startswith(('igemm', 'wgrad_tc'))}
+  if tc:
+    name, dom = max(tc.items(), key=lambda kv: kv[1]['ms'])
+    ach = dom['flops'] / (dom['ms'] / 1e3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': name, 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
+                'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)', 'launches': dom['launches'],
+                'share_of_step': dom['ms'] / ms}
+  if args.detail and rank == 0:
+    table = {k: {'launches': v['launches'], 'ms_per_step': v['ms'] / args.steps,
+                 'tflops': v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] else None,
+                 'gbs_algorithmic': v['bytes'] / (v['ms'] / 1e3) / 1e9 if v['ms'] else None}
+             for k, v in sorted(classes.items())}
+    with open(args.detail, 'w') as fp:
+      json.dump({'ms_per_step': ms / args.steps, 'classes': table}, fp, indent=1)
+
+  # ---- end to end: host batches (pinned fp32 images + int32 labels) -> step -> loss back to the host
+  e2e = None
+  if not args.no_e2e:
+    from wlseg import estimator as west
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = []
+    for _ in range(2):
+      img = (torch.rand((nimg, H, W, 3), generator=g) * 2 - 1).pin_memory()
+      lab = {'prolabels_per_pixel': torch.randint(0, hier.num_classes, (NB, H, W), generator=g, dtype=torch.int32).pin_memory()}
+      if mixed:
+        f, l = batches[0]
+        lab['prolabels_per_bbox'] = l['prolabels_per_bbox'].cpu().pin_memory()
+        lab['prolabels_per_image'] = l['prolabels_per_image'].cpu().pin_memory()
+      host.append(({'proimages': img}, lab))
+    est = west.Estimator.__new__(west.Estimator)
+    st.rank, st.world_size = rank, world
+    st.learning_rate_schedule, st.learning_rate_boundaries, st.learning_rate_values = 'piecewise_constant', [10 ** 9], [0.01, 0.01]
+    est.settings, est.hier, est.device, est.dtype, est.params = st, hier, dev, torch.bfloat16, params
+    est.global_step, est.trainer = tr.global_step, tr
+
+    def gen(n):
+      for i in range(n):
+        yield host[i % 2]
+    est.train(gen(2), 2)
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    t0 = time.perf_counter()
+    est.train(gen(args.steps), args.steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    e2e = {'value': world * args.steps * nimg / dt, 'unit': 'images/s', 'h2d_bytes_per_step': est.last_h2d_bytes // args.steps,
+           'd2h_bytes_per_step': est.last_d2h_bytes // args.steps, 'ms_per_step': 1e3 * dt / args.steps}
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline and cpu_train_sample is not None:
+    cpu = cpu_train_sample(args.dataset, H, W)
+
+  if rank == 0:
+    fwd = arch.conv_flops(params.specs, H, W) / 1e9
+    line = {'metric': 'train_images_per_s', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': f'{args.dataset} training step (BASELINE configs[{3 if mixed else 2}]): ResNet-50 OS8 + '
+                                   f'hierarchical heads, fwd (batch-stat BN) + masked strong{"+weak" if mixed else ""} loss + bwd + '
+                                   f'SGD-momentum, {H}x{W} crops, {NB} strong + {npb} bbox + {npi} image-level images/GPU, random init',
+                       'l2': 'two rotating input batches; activations + gradients (GBs) exceed the 126 MB L2',
+                       'parallelism': f'data parallel x{world}, NCCL gradient all-reduce bucketed behind backward' if world > 1 else 'single GPU',
+                       'fwd_gflop_per_image': fwd, 'last_loss': [float(x) for x in out.tolist()]},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * world, 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()

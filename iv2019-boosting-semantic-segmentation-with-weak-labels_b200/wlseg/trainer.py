@@ -1,0 +1,141 @@
+"""One data-parallel training step: the host-side mirror of the TRAIN branch of `define_estimator`
+(code/estimator/define_estimator_hierarchical.py:77-159), `define_optimizer`
+(code/estimator/define_optimizer.py:3-26) and the MirroredStrategy gradient exchange the reference
+gets from `RunConfig(train_distribute=...)` (code/system_factory.py:279-295).
+
+  forward (batch statistics) -> fused hierarchical loss fwd+bwd -> backward through the network
+  -> gradient all-reduce (mean over replicas of each replica's own normalised-loss gradient, the
+     [TF-1.12] MirroredStrategy semantics) overlapped with backward
+  -> fused SGD-momentum + L2 + bf16 operand refresh (one launch over the parameter arena)
+  -> optional EMA shadows (forced off under --distribute, system_factory.py:236-238)
+
+Launch sequencing and buffer ownership only; the arithmetic is in libwlseg.
+"""
+
+import torch
+
+from wlseg import network, ops
+
+
+class GradientBuckets:
+  """Reverse-order bucketing of a flat gradient arena for overlap with backward.
+
+  The arena is laid out in FORWARD layer order, backward finishes its tail first.  `ready(lo)` tells
+  the bucketer that every element at offset >= lo is final; whole buckets that became final are
+  all-reduced asynchronously on `comm_stream` (NCCL) or inline (gloo / CPU tests); `finish()`
+  flushes the rest and averages.  Device agnostic so that the logic is testable with gloo."""
+
+  def __init__(self, flat, bucket_elems, world_size, process_group=None, comm_stream=None, extra=()):
+    self.flat = flat
+    self.extra = list(extra)  # tensors that only become final at the very end (BN gamma / beta gradients)
+    self.n = flat.numel()
+    self.world = world_size
+    self.group = process_group
+    self.stream = comm_stream
+    # bucket boundaries from the tail: [n - k*b, n - (k-1)*b)
+    self.bounds = []
+    hi = self.n
+    while hi > 0:
+      lo = max(0, hi - bucket_elems)
+      self.bounds.append((lo, hi))
+      hi = lo
+    self.next = 0
+    self.handles = []
+    self.launched_bytes = 0
+
+  def reset(self):
+    self.next = 0
+    self.handles = []
+
+  def _launch(self, lo, hi):
+    self._launch_view(self.flat[lo:hi])
+
+  def _launch_view(self, view):
+    import torch.distributed as dist
+    self.launched_bytes += view.numel() * view.element_size()
+    if self.world == 1:
+      return
+    if self.stream is not None:
+      self.stream.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(self.stream):
+        dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+    else:
+      self.handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+  def ready(self, lo):
+    while self.next < len(self.bounds) and self.bounds[self.next][0] >= lo:
+      self._launch(*self.bounds[self.next])
+      self.next += 1
+
+  def finish(self):
+    """All remaining buckets; returns the factor the caller must scale the summed gradient by
+    (1/world: mean over replicas) - folded into the optimizer kernel's grad_scale."""
+    self.ready(0)
+    for t in self.extra:
+      self._launch_view(t)
+    for h in self.handles:
+      h.wait()
+    self.handles = []
+    if self.stream is not None and self.world > 1:
+      torch.cuda.current_stream().wait_stream(self.stream)
+    return 1.0 / self.world
+
+
+class Trainer:
+  def __init__(self, params, settings, dtype=torch.bfloat16, rank=0, world_size=1, bucket_mb=25):
+    self.p = params
+    self.s = settings
+    self.rank, self.world = rank, world_size
+    self.net = network.TrainNetwork(params, dtype=dtype, bn_decay=getattr(settings, 'batch_norm_decay', 0.9))
+    self.ws = self.net.ws
+    self.momentum = float(getattr(settings, 'momentum', 0.9))
+    self.nesterov = bool(getattr(settings, 'use_nesterov', False))
+    self.optimizer = getattr(settings, 'optimizer', 'SGDM')
+    if self.optimizer not in ('SGD', 'SGDM'):
+      raise ValueError('Optimizer is not supported.')  # define_optimizer.py:24
+    self.wd = float(getattr(settings, 'regularization_weight', 0.00017))
+    self.ema_decay = 0.0 if getattr(settings, 'distribute', False) else float(getattr(settings, 'ema_decay', 0.0))
+    if self.ema_decay > 0:
+      # [TF-1.12] ExponentialMovingAverage.apply on tf.Variables: the shadow slot starts at the
+      # variable's initial value and zero-debiasing is NOT applied (it only applies to plain tensors)
+      self.ws.ema_shadow = params.master.clone()
+    self.comm_stream = torch.cuda.Stream(device=params.device) if (world_size > 1 and params.device.type == 'cuda') else None
+    self.buckets = GradientBuckets(self.ws.grads[:params.n_conv_pad], bucket_mb * (1 << 20) // 4, world_size,
+                                   comm_stream=self.comm_stream, extra=[self.ws.grads[params.n_conv_pad:]])
+    self.net.grad_ready = self.buckets.ready if world_size > 1 else None
+    self.global_step = 0
+    self._lr_host = None
+
+  def set_lr(self, lr):
+    if lr != self._lr_host:
+      self.ws.lr.fill_(float(lr))
+      self._lr_host = lr
+
+  def step(self, features, labels, lr):
+    """-> device tensor float[6]: total, segmentation, l1, l2_vehicle, l2_human, regularization."""
+    net, ws, p = self.net, self.ws, self.p
+    images = features['proimages']
+    H, W = images.shape[1], images.shape[2]
+    self.set_lr(lr)
+    self.buckets.reset()
+    logits = net.forward_train(images)
+    losses, dlogits = net.loss_and_grad(logits, labels, H, W)
+    net.backward(dlogits)
+    gscale = self.buckets.finish()
+    ws.reg_loss.zero_()
+    mom = self.momentum if self.optimizer == 'SGDM' else 0.0
+    ops.sgdm_step(p.master, ws.grads, ws.momentum, p.operand, p.n_conv_pad, ws.lr, mom, self.nesterov, self.wd, gscale,
+                  ws.reg_loss)
+    p.touch()
+    self.global_step += 1
+    if self.ema_decay > 0:
+      t = self.global_step
+      d = min(self.ema_decay, (1.0 + t) / (10.0 + t))  # num_updates=global_step
+      ops.ema_update(ws.ema_shadow, ws.ema_shadow, p.master, d, 1.0)
+    out = torch.empty(6, dtype=torch.float32, device=p.device)
+    reg = ws.reg_loss.to(torch.float32)
+    out[0] = losses[3] + reg[0]
+    out[1] = losses[3]
+    out[2:5] = losses[0:3]
+    out[5] = reg[0]
+    return out

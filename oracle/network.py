@@ -81,15 +81,49 @@ def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False):
   return params
 
 
+class _RoundSte(torch.autograd.Function):
+  """bf16 storage rounding with a straight-through gradient."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.to(torch.bfloat16).to(x.dtype)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g
+
+
+class _RoundGrad(torch.autograd.Function):
+  """Identity whose incoming gradient is rounded to bf16 (a gradient tensor stored in bf16)."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.view_as(x)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g.to(torch.bfloat16).to(g.dtype)
+
+
 class Net:
   """Functional forward over a parameter dict.
+
+  storage='bf16' restates the SAME graph with the storage roundings of the product path made
+  explicit (images, conv kernels, pre-BN conv outputs and activations rounded to bf16 with
+  straight-through gradients; batch statistics taken from the fp32 conv output; activation and
+  pre-BN gradients rounded to bf16; the logits layers stay fp32).  A train-mode batch-norm network
+  at random init amplifies a 1e-3 perturbation by ~10^2 (measured: tests/test_gpu_train.py), so
+  comparing a bf16 pipeline with the fp32 graph end to end says nothing; comparing it with the
+  same graph rounded at the same points does.
 
   training=True uses batch statistics in every BN layer (the reference's
   `batch_norm_accumulate_statistics`, train.py:45-46) and records the updated
   moving statistics in `self.new_moving`.
   """
 
-  def __init__(self, params, dataset='cityscapes', training=False, bn_decay=0.9, eps=1e-5):
+  def __init__(self, params, dataset='cityscapes', training=False, bn_decay=0.9, eps=1e-5, storage='fp32'):
+    assert storage in ('fp32', 'bf16')
+    self.storage = storage
     self.p = params
     self.dataset = dataset
     self.training = training
@@ -97,6 +131,8 @@ class Net:
     self.eps = eps
     self.new_moving = {}
     self.taps = {}
+    self.record_layers = False
+    self.layer_taps = {}  # scope -> (pre-BN conv output, layer output), filled when record_layers
 
   def _bn(self, x, scope):
     bn = f'{scope}/BatchNorm'
@@ -109,14 +145,44 @@ class Net:
       self.new_moving[f'{bn}/moving_variance'] = mv
     return y
 
-  def _conv_bn(self, x, scope, stride=1, rate=1, relu=True, same_explicit=False):
-    w = self.p[f'{scope}/weights']
+  def _q(self, x):
+    return _RoundSte.apply(x) if self.storage == 'bf16' else x
+
+  def _qg(self, x):
+    return _RoundGrad.apply(x) if self.storage == 'bf16' else x
+
+  def _conv_bn(self, x, scope, stride=1, rate=1, relu=True, same_explicit=False, residual=None, fp32_out=False):
+    """conv -> batch norm (-> + residual) (-> ReLU); the residual add sits here so that the bf16
+    storage mode rounds the activation once, after the add, as the fused kernels do."""
+    w = self._q(self.p[f'{scope}/weights'])
     if same_explicit:
-      y = tfops.conv2d_same(x, w, stride, rate)
+      z = tfops.conv2d_same(x, w, stride, rate)
     else:
-      y = tfops.conv2d(x, w, stride, rate, 'SAME')
-    y = self._bn(y, scope)
-    return torch.relu(y) if relu else y
+      z = tfops.conv2d(x, w, stride, rate, 'SAME')
+    if self.storage == 'bf16' and self.training:
+      z = self._qg(z)
+      bn = f'{scope}/BatchNorm'
+      n = z.shape[0] * z.shape[1] * z.shape[2]
+      mean = z.mean(dim=(0, 1, 2))
+      var = ((z - mean) ** 2).mean(dim=(0, 1, 2))
+      zs = z if fp32_out else self._q(z)
+      y = (zs - mean) * torch.rsqrt(var + self.eps) * self.p[f'{bn}/gamma'] + self.p[f'{bn}/beta']
+      with torch.no_grad():
+        self.new_moving[f'{bn}/moving_mean'] = self.p[f'{bn}/moving_mean'] - (1.0 - self.bn_decay) * (
+            self.p[f'{bn}/moving_mean'] - mean)
+        self.new_moving[f'{bn}/moving_variance'] = self.p[f'{bn}/moving_variance'] - (1.0 - self.bn_decay) * (
+            self.p[f'{bn}/moving_variance'] - var * (n / max(n - 1, 1)))
+    else:
+      y = self._bn(z, scope)
+    if residual is not None:
+      y = y + residual
+    if relu:
+      y = torch.relu(y)
+    if not fp32_out:
+      y = self._qg(self._q(y))
+    if self.record_layers:
+      self.layer_taps[scope] = (z.detach(), y.detach())
+    return y
 
   def _bottleneck(self, x, scope, depth, depth_bottleneck, stride, rate):
     """slim resnet_v1.bottleneck [TF-1.12]."""
@@ -126,13 +192,12 @@ class Net:
       shortcut = self._conv_bn(x, f'{scope}/shortcut', stride=stride, relu=False)
     r = self._conv_bn(x, f'{scope}/conv1')
     r = self._conv_bn(r, f'{scope}/conv2', stride=stride, rate=rate, same_explicit=True)
-    r = self._conv_bn(r, f'{scope}/conv3', relu=False)
-    return torch.relu(shortcut + r)
+    return self._conv_bn(r, f'{scope}/conv3', relu=True, residual=shortcut)
 
   def features(self, images, output_stride=8):
     """feature_extractor(): base resnet_v1_50(global_pool=False, output_stride)
     then extension/decrease_fdims.  images: NHWC fp32 in [-1, 1)."""
-    x = self._conv_bn(images, f'{_RES}/conv1', stride=2, same_explicit=True)
+    x = self._conv_bn(self._q(images), f'{_RES}/conv1', stride=2, same_explicit=True)
     x = tfops.max_pool_same(x, 3, 2)
     self.taps['pool1'] = x
     # stack_blocks_dense: the root counts as stride 4
@@ -160,7 +225,7 @@ class Net:
                    ('l2_human_features', 'l2_human_logits')):
       a = self._bottleneck(f, f'adaptation_module/{br}/bottleneck_v1', d, d, 1, 1)
       # slim.conv2d(activation_fn=None) inside the arg scope: BN still applied
-      out.append(self._conv_bn(a, f'softmax_classifier/{lg}', relu=False))
+      out.append(self._conv_bn(a, f'softmax_classifier/{lg}', relu=False, fp32_out=True))
     return out
 
   def forward(self, images):

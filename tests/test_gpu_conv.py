@@ -178,3 +178,48 @@ def test_dgrad_as_flipped_fprop_tcgen05(cuda):
   ops.conv2d_fprop(prm, dy.to(torch.bfloat16).to(cuda), wf, dx)
   torch.cuda.synchronize()
   assert float((dx.float().cpu() - x.grad).abs().max()) <= 1e-2 * float(x.grad.abs().max())
+
+
+WGRAD_TC_CASES = [
+    # N, H, W, C, K, R, stride, dilation
+    (1, 8, 8, 64, 64, 1, 1, 1),        # one patch, one chunk (BN = 64), K < 128 (zero-filled rows)
+    (2, 16, 24, 128, 128, 1, 1, 1),    # BN = 128
+    (1, 16, 16, 64, 128, 3, 1, 1),     # 9 taps x 1 chunk: N tiles of 4 chunks, the last one partial
+    (2, 24, 40, 256, 256, 3, 1, 2),    # dilation 2 (block3), two M tiles, pixel splits
+    (1, 16, 24, 128, 64, 3, 1, 4),     # dilation 4 (block4)
+    (1, 13, 19, 64, 96, 3, 1, 1),      # ragged spatial size, K not a multiple of 64
+    (1, 32, 32, 64, 64, 3, 2, 1),      # stride 2 (block1/unit_3/conv2)
+    (1, 17, 23, 64, 64, 3, 2, 1),      # stride 2, odd sizes
+    (3, 8, 16, 512, 256, 1, 1, 1),     # deep C: 8 chunks -> 2 N tiles
+    (1, 12, 20, 256, 14, 1, 1, 1),     # logits layer: K = 14 (dy pitch padded to 16)
+    (1, 1, 200, 64, 64, 1, 1, 1),      # P == 1
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_TC_CASES)
+def test_conv_wgrad_tcgen05(cuda, case):
+  """dw on the tensor cores (MN-major operands, TMA reduce-add of the pixel splits) against autograd of
+  the oracle convolution on the same bf16-rounded operands: 2e-3 of max|dw| (fp32 accumulation, bf16 inputs
+  are exact in both)."""
+  from wlseg import arch, ops
+  N, H, W, C, K, R, stride, dilation = case
+  g = torch.Generator().manual_seed(sum(case))
+  x = torch.randn(N, H, W, C, generator=g).to(torch.bfloat16).float().requires_grad_(True)
+  w = (torch.randn(K, R, R, C, generator=g) / (R * R * C) ** 0.5).requires_grad_(True)
+  y = tfops.conv2d_same(x, w.permute(1, 2, 3, 0), stride, dilation)
+  dy = torch.randn(y.shape, generator=g).to(torch.bfloat16).float()
+  y.backward(dy)
+  pt, P = arch.same_pad_before(R, stride, dilation, H)
+  pl, Q = arch.same_pad_before(R, stride, dilation, W)
+  kp = (K + 7) // 8 * 8
+  dyd = torch.zeros((N, P, Q, kp), dtype=torch.bfloat16, device=cuda)
+  dyd[..., :K] = dy.to(torch.bfloat16).to(cuda)
+  prm = ops.conv_params((N, H, W, C), (K, R, R, C), stride=stride, dilation=dilation, pad=(pt, pl), out_hw=(P, Q),
+                        y_pitch=kp, dtype=ops.BF16, algo=ops.ALGO_TCGEN05)
+  dw = torch.full((K, R, R, C), float('nan'), device=cuda)
+  ops.conv2d_wgrad(prm, x.detach().to(torch.bfloat16).to(cuda), dyd, dw)
+  torch.cuda.synchronize()
+  assert not torch.isnan(dw).any()
+  err = float((dw.cpu() - w.grad).abs().max()) / float(w.grad.abs().max())
+  print(f'wgrad {case}: max-rel {err:.3e}')
+  assert err <= 2e-3
