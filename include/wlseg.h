@@ -122,12 +122,16 @@ int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, const float
  * Max pool, TF 'SAME' padding (replaces slim.max_pool2d: resnet pool1 3x3 s2 and the 1x1 s2
  * shortcut subsample; arg scope models/resnet50_extended_model_hierarchical.py:351-353).
  * Backward routes the gradient to the first maximum of each window in row-major scan order.
+ * `argmax` (optional, uint8 [N,P,Q,C]) receives / supplies the winning window position r*k+s of
+ * every output element; with it the backward is a pure gather over dy (no re-read of x).  Without
+ * it (NULL) the backward recomputes the winners from x.
  * ------------------------------------------------------------------------------------------ */
-int wlseg_maxpool_same_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
-                           int32_t ksize, int32_t stride, int32_t dtype, wlseg_stream_t stream);
-int wlseg_maxpool_same_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H,
-                           int32_t W, int32_t C, int32_t ksize, int32_t stride, int32_t dtype,
+int wlseg_maxpool_same_fwd(const void* x, void* y, uint8_t* argmax, int32_t N, int32_t H, int32_t W,
+                           int32_t C, int32_t ksize, int32_t stride, int32_t dtype,
                            wlseg_stream_t stream);
+int wlseg_maxpool_same_bwd(const void* x, const uint8_t* argmax, const void* dy, void* dx, int32_t N,
+                           int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t stride,
+                           int32_t dtype, wlseg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Hierarchical head, forward (replaces _create_upsampler + softmax x3 + argmax x3 + gather /

@@ -138,20 +138,37 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const 
   }
 }
 
+// dz = gamma*invstd*(g - dbeta/n - zhat*dgamma/n) = A*g + c1*z + c0 with per-channel constants
+//   A = gamma*invstd, c1 = -A*invstd*dgamma/n, c0 = -A*dbeta/n - c1*mean
+// computed once per CTA into shared memory (the fp64 sums are touched C times, not count*C times).
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const double* __restrict__ dgamma, const double* __restrict__ dbeta, int64_t count, int C,
                     int relu, T* __restrict__ dz, T* __restrict__ dres) {
+  extern __shared__ float bconst[];  // [3][C]: A | c1 | c0
+  float* sA = bconst;
+  float* s1 = bconst + C;
+  float* s0 = bconst + 2 * C;
+  const double invn = 1.0 / (double)count;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float is = invstd[c];
+    const float A = gamma[c] * is;
+    const float c1 = -A * is * (float)(dgamma[c] * invn);
+    sA[c] = A;
+    s1[c] = c1;
+    s0[c] = -A * (float)(dbeta[c] * invn) - c1 * mean[c];
+  }
+  __syncthreads();
   const int cv = C / 8;
   const int64_t total = count * cv;
-  const float invn = 1.0f / (float)count;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c0 = (int)(i % cv) * 8;
+    const int c0 = (int)(i % cv) * 8;
     float g[8], zz[8];
-    Vec8<T> v;
+    Vec8<T> v, vz;
     v.load(dy + i * 8);
+    vz.load(z + i * 8);
     v.unpack(g);
     if (relu) {
       float yy[8];
@@ -166,17 +183,16 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
       o.pack(g);
       o.store(dres + i * 8);
     }
-    Vec8<T> vz;
-    vz.load(z + i * 8);
     vz.unpack(zz);
+    const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(s1 + c0), b1 = *reinterpret_cast<const float4*>(s1 + c0 + 4);
+    const float4 d0 = *reinterpret_cast<const float4*>(s0 + c0), d1 = *reinterpret_cast<const float4*>(s0 + c0 + 4);
+    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
     float out[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = c0 + j;
-      float is = invstd[c];
-      float zh = (zz[j] - mean[c]) * is;
-      out[j] = gamma[c] * is * (g[j] - (float)dbeta[c] * invn - zh * (float)dgamma[c] * invn);
-    }
+    for (int j = 0; j < 8; ++j) out[j] = fmaf(A[j], g[j], fmaf(B[j], zz[j], D[j]));
     Vec8<T> o;
     o.pack(out);
     o.store(dz + i * 8);
@@ -383,11 +399,11 @@ extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, 
   }
   int grid = bw_grid(count * (C / 8), 256, 8);
   if (dtype == WLSEG_BF16)
-    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    bn_bwd_apply_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, invstd, gamma, dgamma, dbeta,
         count, C, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
   else if (dtype == WLSEG_F32)
-    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z, mean,
+    bn_bwd_apply_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z, mean,
                                                                 invstd, gamma, dgamma, dbeta, count, C, relu,
                                                                 (float*)dz, (float*)dres);
   else

@@ -19,7 +19,7 @@ struct PoolGeom {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g) {
+maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ argmax, PoolGeom g) {
   const int cv = g.C / 8;
   const int64_t total = (int64_t)g.N * g.P * g.Q * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -29,8 +29,9 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g) {
     int p = (int)(t % g.P);
     int n = (int)(t / g.P);
     float best[8];
+    uint32_t arg[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 255u; }
     for (int r = 0; r < g.k; ++r) {
       int hh = p * g.stride - g.pad_t + r;
       if (hh < 0 || hh >= g.H) continue;
@@ -41,13 +42,24 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g) {
         v.load(x + (((int64_t)n * g.H + hh) * g.W + ww) * g.C + c8 * 8);
         float f[8];
         v.unpack(f);
+        const uint32_t pos = (uint32_t)(r * g.k + s);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
+        for (int j = 0; j < 8; ++j) {
+          // strict '>' keeps the FIRST maximum in row-major scan order (TF MaxPoolGrad routing)
+          if (f[j] > best[j] || arg[j] == 255u) { best[j] = f[j]; arg[j] = pos; }
+        }
       }
     }
     Vec8<T> o;
     o.pack(best);
-    o.store(y + (((int64_t)n * g.P + p) * g.Q + q) * g.C + c8 * 8);
+    const int64_t oi = (((int64_t)n * g.P + p) * g.Q + q) * g.C + c8 * 8;
+    o.store(y + oi);
+    if (argmax != nullptr) {
+      uint2 packed;
+      packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + oi) = packed;
+    }
   }
 }
 
@@ -115,6 +127,53 @@ maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restr
   }
 }
 
+// backward with the forward's argmax map (uint8 window position per output element): every input
+// cell looks at the <= ceil(k/stride)^2 windows containing it and takes dy where it was the winner.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_argmax_kernel(const uint8_t* __restrict__ argmax, const T* __restrict__ dy, T* __restrict__ dx,
+                          PoolGeom g) {
+  const int cv = g.C / 8;
+  const int64_t total = (int64_t)g.N * g.H * g.W * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % cv);
+    int64_t t = i / cv;
+    int w = (int)(t % g.W); t /= g.W;
+    int h = (int)(t % g.H);
+    int n = (int)(t / g.H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int p_lo = (h + g.pad_t - g.k + 1 + g.stride - 1);
+    p_lo = p_lo <= 0 ? 0 : p_lo / g.stride;
+    int p_hi = min((h + g.pad_t) / g.stride, g.P - 1);
+    int q_lo = (w + g.pad_l - g.k + 1 + g.stride - 1);
+    q_lo = q_lo <= 0 ? 0 : q_lo / g.stride;
+    int q_hi = min((w + g.pad_l) / g.stride, g.Q - 1);
+    for (int p = p_lo; p <= p_hi; ++p) {
+      const int r = h - (p * g.stride - g.pad_t);
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const int s = w - (q * g.stride - g.pad_l);
+        const uint32_t pos = (uint32_t)(r * g.k + s);
+        const int64_t oi = (((int64_t)n * g.P + p) * g.Q + q) * g.C + c8 * 8;
+        const uint2 am = *reinterpret_cast<const uint2*>(argmax + oi);
+        Vec8<T> gv;
+        gv.load(dy + oi);
+        float gf[8];
+        gv.unpack(gf);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j] += (((am.x >> (8 * j)) & 255u) == pos) ? gf[j] : 0.f;
+          acc[4 + j] += (((am.y >> (8 * j)) & 255u) == pos) ? gf[4 + j] : 0.f;
+        }
+      }
+    }
+    Vec8<T> o;
+    o.pack(acc);
+    o.store(dx + i * 8);
+  }
+}
+
 static int make_geom(PoolGeom& g, int N, int H, int W, int C, int k, int stride) {
   WLSEG_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "maxpool: bad shape");
   WLSEG_CHECK_ARG(C % 8 == 0, "maxpool: C (%d) must be a multiple of 8", C);
@@ -132,33 +191,46 @@ static int make_geom(PoolGeom& g, int N, int H, int W, int C, int k, int stride)
 
 using namespace wlseg;
 
-extern "C" int wlseg_maxpool_same_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
-                                      int32_t ksize, int32_t stride, int32_t dtype, wlseg_stream_t stream) {
+extern "C" int wlseg_maxpool_same_fwd(const void* x, void* y, uint8_t* argmax, int32_t N, int32_t H, int32_t W,
+                                      int32_t C, int32_t ksize, int32_t stride, int32_t dtype,
+                                      wlseg_stream_t stream) {
   PoolGeom g;
   if (int e = make_geom(g, N, H, W, C, ksize, stride)) return e;
   if (N == 0) return 0;
   WLSEG_CHECK_ARG(x && y, "maxpool_fwd: null pointer");
+  WLSEG_CHECK_ARG(argmax == nullptr || ksize * ksize < 255, "maxpool_fwd: window too large for the uint8 argmax map");
   int64_t items = (int64_t)N * g.P * g.Q * (C / 8);
   int grid = bw_grid(items, 256, 8);
   if (dtype == WLSEG_BF16)
-    maxpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, g);
+    maxpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, g);
   else if (dtype == WLSEG_F32)
-    maxpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, g);
+    maxpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, argmax, g);
   else
     WLSEG_CHECK_ARG(false, "maxpool_fwd: bad dtype %d", dtype);
   WLSEG_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int wlseg_maxpool_same_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W,
-                                      int32_t C, int32_t ksize, int32_t stride, int32_t dtype,
-                                      wlseg_stream_t stream) {
+extern "C" int wlseg_maxpool_same_bwd(const void* x, const uint8_t* argmax, const void* dy, void* dx, int32_t N,
+                                      int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t stride,
+                                      int32_t dtype, wlseg_stream_t stream) {
   PoolGeom g;
   if (int e = make_geom(g, N, H, W, C, ksize, stride)) return e;
   if (N == 0) return 0;
-  WLSEG_CHECK_ARG(x && dy && dx, "maxpool_bwd: null pointer");
+  WLSEG_CHECK_ARG((x || argmax) && dy && dx, "maxpool_bwd: null pointer");
   int64_t items = (int64_t)N * H * W * (C / 8);
   int grid = bw_grid(items, 256, 8);
+  if (argmax != nullptr) {
+    if (dtype == WLSEG_BF16)
+      maxpool_bwd_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(argmax, (const __nv_bfloat16*)dy,
+                                                                        (__nv_bfloat16*)dx, g);
+    else if (dtype == WLSEG_F32)
+      maxpool_bwd_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(argmax, (const float*)dy, (float*)dx, g);
+    else
+      WLSEG_CHECK_ARG(false, "maxpool_bwd: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == WLSEG_BF16)
     maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
                                                                (__nv_bfloat16*)dx, g);

@@ -53,6 +53,7 @@ class Params:
     self.moving[self.n_chan_pad:] = 1.0
     self.master[self.n_conv_pad:self.n_conv_pad + self.n_chan_pad] = 1.0  # gamma
     self._derived = {}
+    self._pack_idx = None
     self.version = 0
 
   # ---- views -------------------------------------------------------------------------------
@@ -139,26 +140,29 @@ class Params:
     self._derived.clear()
 
   # ---- derived operands ----------------------------------------------------------------------
+  def conv1_pack_index(self):
+    """Column of the packed [64, 4*64] root filter bank that holds w[k, r, s, c] (flattened r, s, c):
+    W2[k, a, 0, b*16 + (i*2+j)*3 + c] = w[k, 2a+i-1, 2b+j-1, c] (csrc/transform.cu)."""
+    if self._pack_idx is None:
+      ii = []
+      for r in range(7):
+        a, i = (r + 1) // 2, (r + 1) % 2
+        for s_ in range(7):
+          b, j = (s_ + 1) // 2, (s_ + 1) % 2
+          for c in range(3):
+            ii.append(a * 64 + b * 16 + (i * 2 + j) * 3 + c)
+      self._pack_idx = torch.tensor(ii, dtype=torch.long, device=self.device)
+    return self._pack_idx
+
   def conv1_packed_weights(self, dtype):
-    """Root 7x7/2 kernel rewritten for the packed input of csrc/transform.cu:
-    W2[k, a, 0, b*16 + (i*2+j)*3 + c] = w[k, 2a+i-1, 2b+j-1, c] (zero where the index is -1)."""
+    """Root 7x7/2 kernel rewritten for the packed input of csrc/transform.cu (zero where the packed
+    tap has no counterpart)."""
     key = ('conv1_packed', dtype)
     if key not in self._derived:
-      w = self.w32(f'{arch.RES}/conv1')  # [64, 7, 7, 3]
-      w2 = torch.zeros(64, 4, 1, 64, dtype=torch.float32, device=self.device)
-      for a in range(4):
-        for i in range(2):
-          r = 2 * a + i - 1
-          if r < 0:
-            continue
-          for b in range(4):
-            for j in range(2):
-              s = 2 * b + j - 1
-              if s < 0:
-                continue
-              c0 = b * 16 + (i * 2 + j) * 3
-              w2[:, a, 0, c0:c0 + 3] = w[:, r, s, :]
-      self._derived[key] = w2.to(dtype).contiguous()
+      w = self.w32(f'{arch.RES}/conv1').reshape(64, 147)
+      w2 = torch.zeros(64, 256, dtype=torch.float32, device=self.device)
+      w2[:, self.conv1_pack_index()] = w
+      self._derived[key] = w2.to(dtype).view(64, 4, 1, 64)
     return self._derived[key]
 
   def folded_bn(self, scope, n=None, eps=1e-5):
@@ -537,8 +541,9 @@ class TrainNetwork(Network):
       y = self._layer_fwd(images.to(self.dtype), scope)
     P, Q = (y.shape[1] + 1) // 2, (y.shape[2] + 1) // 2
     pooled = torch.empty((N, P, Q, 64), dtype=self.dtype, device=self.dev)
-    ops.maxpool_same_fwd(y, pooled, 3, 2)
-    self.tape['pool1'] = (y, pooled)
+    amax = torch.empty((N, P, Q, 64), dtype=torch.uint8, device=self.dev)
+    ops.maxpool_same_fwd(y, pooled, 3, 2, argmax=amax)
+    self.tape['pool1'] = (y, amax)
     return pooled
 
   def _root_wgrad(self, rec, dz):
@@ -552,23 +557,13 @@ class TrainNetwork(Network):
     prm = ops.conv_params((N, Hs, Ws, 64), (64, 4, 1, 64), stride=stride, dilation=dilation, pad=pad, out_hw=out_hw,
                           x_pitch=rec.x.stride(2), y_pitch=dz.stride(2), dtype=self.code)
     ops.conv2d_wgrad(prm, rec.x, dz, dw2)
-    idx = self.p._derived.get('conv1_unpack_index')
-    if idx is None:
-      ii = []
-      for r in range(7):
-        a, i = (r + 1) // 2, (r + 1) % 2
-        for s_ in range(7):
-          b, j = (s_ + 1) // 2, (s_ + 1) % 2
-          for c in range(3):
-            ii.append(a * 64 + b * 16 + (i * 2 + j) * 3 + c)
-      idx = torch.tensor(ii, dtype=torch.long, device=self.dev)
-      self.p._derived['conv1_unpack_index'] = idx
+    idx = self.p.conv1_pack_index()
     self._wgrad_view(scope, (64, 7, 7, 3)).copy_(dw2.view(64, 256)[:, idx].view(64, 7, 7, 3))
 
   def _root_bwd(self, dpool):
-    y, pooled = self.tape['pool1']
+    y, amax = self.tape['pool1']
     dy = torch.empty_like(y)
-    ops.maxpool_same_bwd(y, dpool, dy, 3, 2)
+    ops.maxpool_same_bwd(None, dpool, dy, 3, 2, argmax=amax)
     self._layer_bwd(f'{arch.RES}/conv1', dy, need_dx=False)
 
   # ---- bottleneck units ------------------------------------------------------------------------------

@@ -55,9 +55,10 @@ _SIGNATURES = {
     'wlseg_bn_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int,
                                           _vp, _vp, _vp]),
-    'wlseg_maxpool_same_fwd': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
-    'wlseg_maxpool_same_bwd': (ctypes.c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+    'wlseg_maxpool_same_fwd': (ctypes.c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                               _vp]),
+    'wlseg_maxpool_same_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                              _c_int, _vp]),
     'wlseg_head_fwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'wlseg_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -244,18 +245,19 @@ def bn_bwd_apply(dy, y, z, mean, invstd, gamma, dgamma, dbeta, count, C, relu, d
 
 
 # ------------------------------------------------------------------------------------ pooling
-def maxpool_same_fwd(x, y, ksize, stride):
+def maxpool_same_fwd(x, y, ksize, stride, argmax=None):
+  """argmax: optional uint8 tensor shaped like y receiving each output's winning window position."""
   N, H, W, C = x.shape
-  _check(lib().wlseg_maxpool_same_fwd(_ptr(x), _ptr(y), N, H, W, C, ksize, stride, dtype_code(x.dtype), _stream()),
-         'wlseg_maxpool_same_fwd')
+  _check(lib().wlseg_maxpool_same_fwd(_ptr(x), _ptr(y), _ptr(argmax), N, H, W, C, ksize, stride,
+                                      dtype_code(x.dtype), _stream()), 'wlseg_maxpool_same_fwd')
   _count()
   return y
 
 
-def maxpool_same_bwd(x, dy, dx, ksize, stride):
-  N, H, W, C = x.shape
-  _check(lib().wlseg_maxpool_same_bwd(_ptr(x), _ptr(dy), _ptr(dx), N, H, W, C, ksize, stride, dtype_code(x.dtype),
-                                      _stream()), 'wlseg_maxpool_same_bwd')
+def maxpool_same_bwd(x, dy, dx, ksize, stride, argmax=None):
+  N, H, W, C = dx.shape
+  _check(lib().wlseg_maxpool_same_bwd(_ptr(x), _ptr(argmax), _ptr(dy), _ptr(dx), N, H, W, C, ksize, stride,
+                                      dtype_code(dx.dtype), _stream()), 'wlseg_maxpool_same_bwd')
   _count()
   return dx
 

@@ -82,7 +82,14 @@ class GradientBuckets:
 
 
 class Trainer:
-  def __init__(self, params, settings, dtype=torch.bfloat16, rank=0, world_size=1, bucket_mb=25):
+  def __init__(self, params, settings, dtype=torch.bfloat16, rank=0, world_size=1, bucket_mb=25, use_graph=True):
+    """use_graph: after two eager steps (lazy initialisation, kernel attributes, allocator warm-up)
+    the whole step - ~520 kernel launches - is captured into ONE CUDA graph per input signature and
+    replayed; the learning rate is read from device memory so the graph stays valid across the
+    schedule.  Inputs are copied into static buffers before each replay."""
+    self.use_graph = bool(use_graph) and params.device.type == 'cuda'
+    self._graphs = {}
+    self._eager_steps = 0
     self.p = params
     self.s = settings
     self.rank, self.world = rank, world_size
@@ -111,12 +118,10 @@ class Trainer:
       self.ws.lr.fill_(float(lr))
       self._lr_host = lr
 
-  def step(self, features, labels, lr):
-    """-> device tensor float[6]: total, segmentation, l1, l2_vehicle, l2_human, regularization."""
+  def _core(self, images, labels):
+    """forward + loss + backward + gradient exchange + optimizer; returns the device loss vector."""
     net, ws, p = self.net, self.ws, self.p
-    images = features['proimages']
     H, W = images.shape[1], images.shape[2]
-    self.set_lr(lr)
     self.buckets.reset()
     logits = net.forward_train(images)
     losses, dlogits = net.loss_and_grad(logits, labels, H, W)
@@ -127,15 +132,48 @@ class Trainer:
     ops.sgdm_step(p.master, ws.grads, ws.momentum, p.operand, p.n_conv_pad, ws.lr, mom, self.nesterov, self.wd, gscale,
                   ws.reg_loss)
     p.touch()
-    self.global_step += 1
-    if self.ema_decay > 0:
-      t = self.global_step
-      d = min(self.ema_decay, (1.0 + t) / (10.0 + t))  # num_updates=global_step
-      ops.ema_update(ws.ema_shadow, ws.ema_shadow, p.master, d, 1.0)
     out = torch.empty(6, dtype=torch.float32, device=p.device)
     reg = ws.reg_loss.to(torch.float32)
     out[0] = losses[3] + reg[0]
     out[1] = losses[3]
     out[2:5] = losses[0:3]
     out[5] = reg[0]
+    return out
+
+  def step(self, features, labels, lr):
+    """-> device tensor float[6]: total, segmentation, l1, l2_vehicle, l2_human, regularization."""
+    images = features['proimages']
+    labels = {k: v for k, v in labels.items() if v is not None}
+    self.set_lr(lr)
+    if not self.use_graph or self.net.profile is not None or self.net.keep:
+      out = self._core(images, labels)
+    else:
+      key = (tuple(images.shape), images.dtype) + tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in labels.items()))
+      entry = self._graphs.get(key)
+      if entry is None and self._eager_steps < 2:
+        self._eager_steps += 1
+        out = self._core(images, labels)
+      else:
+        if entry is None:
+          static_img = images.clone()
+          static_lab = {k: v.clone() for k, v in labels.items()}
+          torch.cuda.synchronize()
+          graph = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(graph):
+            static_out = self._core(static_img, static_lab)
+          entry = (graph, static_img, static_lab, static_out)
+          self._graphs[key] = entry
+          # the capture itself did not execute anything: fall through to the first replay
+        graph, static_img, static_lab, static_out = entry
+        static_img.copy_(images, non_blocking=True)
+        for k, v in labels.items():
+          static_lab[k].copy_(v, non_blocking=True)
+        graph.replay()
+        self.p.touch()
+        out = static_out
+    self.global_step += 1
+    if self.ema_decay > 0:
+      t = self.global_step
+      d = min(self.ema_decay, (1.0 + t) / (10.0 + t))  # num_updates=global_step
+      ops.ema_update(self.ws.ema_shadow, self.ws.ema_shadow, self.p.master, d, 1.0)
     return out

@@ -34,6 +34,15 @@ def test_maxpool_same_fwd_bwd(cuda, shape, k, s, dtype):
   want = xr.grad
   tol = 0 if dtype == torch.float32 else 2e-2
   assert float((dx.float().cpu() - want).abs().max()) <= tol * float(want.abs().max()) + 1e-6
+  # same result through the forward's argmax map (the training path: no re-read of x in the backward)
+  amax = torch.full((N, P, Q, C), 77, dtype=torch.uint8, device=cuda)
+  y2 = torch.empty_like(y)
+  ops.maxpool_same_fwd(xd, y2, k, s, argmax=amax)
+  dx2 = torch.full_like(dx, float('nan'))
+  ops.maxpool_same_bwd(None, dy.to(dtype).to(cuda), dx2, k, s, argmax=amax)
+  torch.cuda.synchronize()
+  assert torch.equal(y2, y) and int(amax.max()) < k * k
+  assert torch.equal(dx2, dx)
 
 
 @pytest.mark.parametrize('C', [64, 24, 256])
