@@ -34,6 +34,7 @@
 // (flops = 2*N*P*Q*R*S*C*K); HBM-bound for block1 and the 64-channel 1x1 layers.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -51,7 +52,6 @@ int conv_fprop_direct(const wlseg_conv_params* p, const void* x, const void* w, 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
 constexpr int kBK = 64;           // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int kUmmaK = 16;        // bf16 MMA K
-constexpr int kIgemmThreads = 256;
 constexpr int kEpiWarp0 = 4;      // first epilogue warp
 constexpr int kABytes = kBM * kBK * 2;  // 16 KB
 constexpr int kSmemBudget = 224 * 1024;
@@ -76,14 +76,14 @@ struct IgemmParams {
   int cchunks;        // ceil(C / 64)
   int num_kb;         // R * S * cchunks
   int stages;         // depth of the {A,B} operand ring
-  int epi_bufs;       // 16 KB epilogue staging buffers (0: direct epilogue, else 2 or 4)
+  int epi_bufs;       // 4 KB per-warp epilogue staging buffers (0: direct epilogue, else EW or 2 * EW)
 };
 
 constexpr int kSubW = 64;                       // epilogue sub-tile: 64 channels = one 128-byte row
-constexpr int kSubBytes = kBM * kSubW * 2;      // 16 KB
+constexpr int kWarpBufBytes = 32 * kSubW * 2;   // 4 KB: one epilogue warp's 32 rows x 64 channels
 constexpr int kMaxStages = 8;
-constexpr int kMaxEpiBufs = 4;
-constexpr int kBarBytes = 256;                  // full[8] empty[8] tfull[2] tempty[2] rfull[4] + TMEM slot
+constexpr int kMaxEpiWarps = 16;
+constexpr int kBarBytes = 512;                  // full[8] empty[8] tfull[2] tempty[2] rfull[32] + TMEM slot
 constexpr int kSmemMax = 227 * 1024;            // opt-in dynamic shared memory per CTA on sm_100
 
 template <int BN>
@@ -91,7 +91,6 @@ struct IgemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kVecBytes = 2 * BN * 4;  // the tile's scale / shift vectors
 };
 
 // 32 x 32 transpose-reduce: on entry every lane holds 32 column values of ITS row; on exit
@@ -136,25 +135,29 @@ __device__ __forceinline__ int num_subtiles(const IgemmParams& prm, int k0) {
 }
 
 // ----------------------------------------------------------------------------- kernel
-template <int BN, typename TY, bool kTmaEpi>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+// EW epilogue warps (8 or 16): warp e serves TMEM lane quarter e % 4 (the hardware restriction:
+// a warp reads the lanes 32*(warpid % 4) ..) and column group e / 4 of every 64-channel sub-tile.
+// Two to four epilogue warps per scheduler hide each other's ALU / shared-memory latencies - with
+// one warp per scheduler the epilogue, not HBM, bounded every bandwidth-bound layer (profiles/).
+template <int BN, typename TY, bool kTmaEpi, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   using Cfg = IgemmCfg<BN>;
+  constexpr int CG = EW / 4;             // warps per TMEM lane quarter: each takes every CG-th sub-tile
   extern __shared__ __align__(1024) uint8_t smem[];
   // SWIZZLE_128B operands need 1024-byte aligned stages (the kernel has no static shared memory,
   // so the dynamic window starts at offset 0 of the CTA's shared space)
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int stages = prm.stages;
   uint8_t* epi_smem = smem + stages * Cfg::kStageBytes;            // [buf0 .. buf(epi_bufs-1)]
-  float* s_scale = reinterpret_cast<float*>(epi_smem + prm.epi_bufs * kSubBytes);
-  float* s_shift = s_scale + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + prm.epi_bufs * kWarpBufBytes);
   uint64_t* full_bar = bars;                             // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;               // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;           // [2]
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;      // [2]
-  uint64_t* rfull_bar = bars + 2 * kMaxStages + 4;       // [kMaxEpiBufs] residual sub-tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kMaxEpiBufs);
+  uint64_t* rfull_bar = bars + 2 * kMaxStages + 4;       // [2 * EW] residual box landed (per warp, per buffer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + 2 * kMaxEpiWarps);
+  float* s_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][BN] (kTmaEpi)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -174,12 +177,14 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(tfull_bar + a), 1);
-      mbar_init(smem_u32(tempty_bar + a), 4);  // one arrival per epilogue warp
+      mbar_init(smem_u32(tempty_bar + a), EW);  // one arrival per epilogue warp
     }
-    for (int a = 0; a < kMaxEpiBufs; ++a) mbar_init(smem_u32(rfull_bar + a), 1);
+    for (int a = 0; a < 2 * EW; ++a) mbar_init(smem_u32(rfull_bar + a), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  if (kTmaEpi && warp == 3 && prm.bn_sum != nullptr)
+    for (int j = lane; j < 2 * BN; j += 32) s_stat[j] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -244,36 +249,69 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
-    const int ew = warp - kEpiWarp0;          // TMEM lanes [32*ew, 32*ew + 32)
-    const int row = ew * 32 + lane;           // tile row = pixel within the patch
+    const int ew = warp - kEpiWarp0;
+    const int quarter = ew & 3;               // TMEM lanes [32*quarter, 32*quarter + 32)
+    const int cgrp = ew >> 2;                 // column group inside a 64-channel sub-tile
+    const int et = threadIdx.x - kEpiWarp0 * 32;
+    const int row = quarter * 32 + lane;      // tile row = pixel within the patch
     const int dy_ = row >> prm.tw_log2, dx_ = row & (TW - 1);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int iter = 0;
     if constexpr (kTmaEpi) {
-      // ---- staged epilogue: TMEM -> registers -> swizzled shared memory -> TMA store; the residual
-      // sub-tile is TMA-loaded INTO the staging buffer it will leave from (read-modify-write in place)
+      // ---- staged epilogue, one INDEPENDENT pipeline per warp: a warp owns the 32 rows of its TMEM
+      // lane quarter and every CG-th 64-channel sub-tile; TMEM -> registers -> its own swizzled 4 KB
+      // staging buffer -> its own TMA store (box {64 ch, 32 pixels}).  The residual box is TMA-loaded
+      // INTO the staging buffer it will leave from (read-modify-write in place, double buffered per
+      // warp).  No CTA-wide barrier: the warps drift apart and hide each other's latencies.
       const bool has_res = prm.res != nullptr;
-      const bool leader = (row == 0);
-      const int nb = prm.epi_bufs;            // 2 or 4
-      const int nb_mask = nb - 1, nb_shift = (nb == 4) ? 2 : 1;
-      const uint32_t sw = (uint32_t)(row & 7);
-      // residual prefetch cursor (leader only): sub-tile sequence index `rs` is loaded into buffer rs % nb
-      int r_tile = blockIdx.x, r_st = 0, r_seq = 0;
-      auto issue_residual = [&]() {
-        // loads the residual of sequence index r_seq (if any is left) and advances the cursor
-        if (r_tile >= prm.total_tiles) return;
-        int n, p0, q0, k0;
-        decode_tile<BN>(prm, r_tile, n, p0, q0, k0);
-        const int b = r_seq & nb_mask;
-        const uint32_t bar = smem_u32(rfull_bar + b);
-        mbar_arrive_expect_tx(bar, kSubBytes);
-        tma_load_4d(smem_u32(epi_smem + b * kSubBytes), &prm.map_r, bar, k0 + r_st * kSubW, q0 * prm.res_stride,
-                    p0 * prm.res_stride, n);
-        ++r_seq;
-        if (++r_st == num_subtiles<BN>(prm, k0)) { r_st = 0; r_tile += gridDim.x; }
+      const bool has_stat = prm.bn_sum != nullptr;
+      const float lo = prm.relu ? 0.f : -INFINITY;
+      const uint32_t sw = (uint32_t)(lane & 7);           // row & 7 of this thread's staging row
+      uint8_t* wbuf = epi_smem + ew * (has_res ? 2 : 1) * kWarpBufBytes;
+      uint64_t* my_rfull = rfull_bar + 2 * ew;
+      const int r0 = quarter * 32;                        // first tile row of this warp
+      const int dy0 = r0 >> prm.tw_log2, dx0 = r0 & (TW - 1);
+      // residual cursors (lane 0) over this warp's (tile, sub-tile) sequence: `ld` stages the box of the
+      // NEXT step into the warp's other buffer, `pf` runs kResPf steps ahead and only pulls the box into
+      // L2 (cp.async.bulk.prefetch), so that the staging load is an L2 hit - the 4 KB-per-warp staging
+      // buffers alone keep far too few bytes in flight to cover HBM latency
+      constexpr int kResPf = 4;
+      struct ResCursor { int tile, st, cnt; };
+      ResCursor ld = {(int)blockIdx.x, cgrp, 0}, pf = {(int)blockIdx.x, cgrp, 0};
+      auto next_residual = [&](ResCursor& c, bool stage) {
+        while (c.tile < prm.total_tiles) {
+          int n, p0, q0, k0;
+          decode_tile<BN>(prm, c.tile, n, p0, q0, k0);
+          if (c.st < num_subtiles<BN>(prm, k0)) {
+            const int cx = (q0 + dx0) * prm.res_stride, cy = (p0 + dy0) * prm.res_stride;
+            if (stage) {
+              const uint32_t bar = smem_u32(my_rfull + (c.cnt & 1));
+              mbar_arrive_expect_tx(bar, kWarpBufBytes);
+              tma_load_4d(smem_u32(wbuf + (c.cnt & 1) * kWarpBufBytes), &prm.map_r, bar, k0 + c.st * kSubW, cx, cy, n);
+            } else {
+              tma_prefetch_4d(&prm.map_r, k0 + c.st * kSubW, cx, cy, n);
+            }
+            ++c.cnt;
+            c.st += CG;
+            return;
+          }
+          c.st = cgrp;
+          c.tile += gridDim.x;
+        }
       };
-      if (has_res && leader)
-        for (int i = 0; i < nb - 1; ++i) issue_residual();
-      int seq = 0;
+      if (has_res && lane == 0) {
+        for (int i = 0; i < kResPf; ++i) next_residual(pf, false);
+        next_residual(ld, true);   // step 0 -> buffer 0
+      }
+      // BN statistic partials of this warp's rows, kept in registers for the whole kernel (the host
+      // sizes the grid as a multiple of the N-tile count, so a CTA never changes its N tile):
+      // lane = channel pair, slot = which of the warp's sub-tiles
+      constexpr int kSlots = (BN / kSubW + CG - 1) / CG;
+      float a1x[kSlots], a1y[kSlots], a2x[kSlots], a2y[kSlots];
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) a1x[i] = a1y[i] = a2x[i] = a2y[i] = 0.f;
+      int stat_k0 = -1;
+      int cnt = 0;
       for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
         int n, p0, q0, k0;
         decode_tile<BN>(prm, tile, n, p0, q0, k0);
@@ -281,35 +319,43 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         const int nsub = num_subtiles<BN>(prm, k0);
-        // this tile's scale / shift vectors (readers of the previous tile's are past its last barrier)
-        if (prm.scale != nullptr) {
-          for (int j = row; j < BN; j += 128) {
-            const bool in = (k0 + j < prm.K);
-            s_scale[j] = in ? __ldg(prm.scale + k0 + j) : 0.f;
-            s_shift[j] = in ? __ldg(prm.shift + k0 + j) : 0.f;
-          }
+        if (has_stat) {
+          if (stat_k0 >= 0 && k0 != stat_k0) __trap();  // grid not a multiple of the N-tile count
+          stat_k0 = k0;
         }
         mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
         tc_fence_after();
-        for (int st = 0; st < nsub; ++st, ++seq) {
-          const int b = seq & nb_mask;
-          uint8_t* buf = epi_smem + b * kSubBytes;
-          if (has_res) {
-            mbar_wait(smem_u32(rfull_bar + b), (uint32_t)((seq >> nb_shift) & 1));
-          } else if (leader) {
-            // the store that last left from this buffer (nb sub-tiles ago) must have read it
-            if (nb == 2) bulk_wait_read<1>(); else bulk_wait_read<3>();
+        if (cgrp >= nsub) {
+          // nothing to do in this tile: still one arrival per warp and tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        }
+#pragma unroll
+        for (int slot = 0; slot < kSlots; ++slot) {
+          const int st = cgrp + slot * CG;
+          if (st >= nsub) break;
+          uint8_t* buf = wbuf + (has_res ? (cnt & 1) * kWarpBufBytes : 0);
+          // the store that last left from the buffer about to be (re)written must have read it:
+          // without a residual that is this step's buffer, with one it is the NEXT step's
+          if (lane == 0) {
+            bulk_wait_read<0>();
+            if (has_res) {
+              next_residual(ld, true);    // step cnt + 1 -> the other buffer
+              next_residual(pf, false);   // step cnt + 1 + kResPf -> L2
+            }
           }
-          epi_barrier();  // buffer writable by everyone; scale / shift visible
-          uint8_t* myrow = buf + row * 128;
+          __syncwarp();
+          if (has_res) mbar_wait(smem_u32(my_rfull + (cnt & 1)), (uint32_t)((cnt >> 1) & 1));
+          uint8_t* myrow = buf + lane * 128;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int col = st * kSubW + half * 32;   // column inside the BN-wide tile
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + col), v);
+            tmem_ld<32>(lane_addr + (uint32_t)(acc * BN + col), v);
             tmem_ld_wait();
-            if (half == 1 && st == nsub - 1) {
-              // last TMEM read of this tile: hand the accumulator back to the MMA warp
+            if (half == 1 && st + CG >= nsub) {
+              // this warp's last TMEM read of the tile: hand the accumulator back to the MMA warp
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
@@ -317,39 +363,32 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (prm.bn_sum != nullptr) {
-              // training-mode BN statistics of the raw fp32 accumulators (rows outside the image masked)
-              float s1[32], s2[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                s1[j] = valid ? f[j] : 0.f;
-                s2[j] = s1[j] * s1[j];
-              }
-              warp_column_sums(s1, lane);
-              warp_column_sums(s2, lane);
-              if (k0 + col + lane < prm.K) {
-                atomicAdd(prm.bn_sum + k0 + col + lane, (double)s1[0]);
-                atomicAdd(prm.bn_sqsum + k0 + col + lane, (double)s2[0]);
-              }
-            }
             if (prm.scale != nullptr) {
+              // folded batch norm; warp-uniform addresses (broadcast, L1 resident)
+              const float4* sc4 = reinterpret_cast<const float4*>(prm.scale + k0 + col);
+              const float4* sh4 = reinterpret_cast<const float4*>(prm.shift + k0 + col);
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
-                const float4 sc = *reinterpret_cast<const float4*>(s_scale + col + g * 4);
-                const float4 sh = *reinterpret_cast<const float4*>(s_shift + col + g * 4);
-                f[g * 4 + 0] = f[g * 4 + 0] * sc.x + sh.x;
-                f[g * 4 + 1] = f[g * 4 + 1] * sc.y + sh.y;
-                f[g * 4 + 2] = f[g * 4 + 2] * sc.z + sh.z;
-                f[g * 4 + 3] = f[g * 4 + 3] * sc.w + sh.w;
+                const float4 sc = __ldg(sc4 + g);
+                const float4 sh = __ldg(sh4 + g);
+                f[g * 4 + 0] = fmaf(f[g * 4 + 0], sc.x, sh.x);
+                f[g * 4 + 1] = fmaf(f[g * 4 + 1], sc.y, sh.y);
+                f[g * 4 + 2] = fmaf(f[g * 4 + 2], sc.z, sh.z);
+                f[g * 4 + 3] = fmaf(f[g * 4 + 3], sc.w, sh.w);
               }
             }
+            uint4* slot4[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              // 16-byte chunk (half*4 + g) of this row sits at the XOR-swizzled position
-              uint4* slot = reinterpret_cast<uint4*>(myrow + ((((uint32_t)(half * 4 + g)) ^ sw) << 4));
-              if (has_res) {
-                const uint4 raw = *slot;
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            for (int g = 0; g < 4; ++g)
+              slot4[g] = reinterpret_cast<uint4*>(myrow + ((((uint32_t)(half * 4 + g)) ^ sw) << 4));
+            if (has_res) {
+              // all 16-byte chunks are loaded before any is rewritten (no false aliasing stalls)
+              uint4 raw[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) raw[g] = *slot4[g];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[g]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 t = __bfloat1622float2(h[e]);
@@ -357,33 +396,72 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
                   f[g * 8 + 2 * e + 1] += t.y;
                 }
               }
-              if (prm.relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[g * 8 + e] = fmaxf(f[g * 8 + e], 0.f);
-              }
-              uint4 outv;
-              __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
-              *slot = outv;
             }
+            if (has_stat && !valid) {
+              // pixels outside the image must not reach the statistics (TMA clips them from the store)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;
+            }
+            uint4 outv[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv[g]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                ho[e] = __floats2bfloat162_rn(fmaxf(f[g * 8 + 2 * e], lo), fmaxf(f[g * 8 + 2 * e + 1], lo));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *slot4[g] = outv[g];
           }
           fence_async_smem();   // my generic-proxy writes -> visible to the TMA store
-          epi_barrier();        // whole sub-tile written
-          if (leader) {
-            tma_store_4d(&prm.map_y, smem_u32(buf), k0 + st * kSubW, q0, p0, n);
+          __syncwarp();         // the warp's 32 rows are written
+          if (lane == 0) {
+            tma_store_4d(&prm.map_y, smem_u32(buf), k0 + st * kSubW, q0 + dx0, p0 + dy0, n);
             bulk_commit();
-            if (has_res) {
-              // refill the buffer used one sub-tile ago: its store must have finished reading it
-              bulk_wait_read<1>();
-              issue_residual();
+          }
+          if (has_stat) {
+            // training-mode BN statistics of the STORED (bf16) activations, read back column-wise from
+            // the staging buffer: lane = channel pair; conflict-free under the swizzle
+            const uint8_t* base = buf + ((lane & 3) << 2);
+            float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(
+                  base + r * 128 + ((((uint32_t)(lane >> 2)) ^ (uint32_t)(r & 7)) << 4));
+              const float2 t = __bfloat1622float2(h);
+              s1x += t.x; s1y += t.y;
+              s2x = fmaf(t.x, t.x, s2x); s2y = fmaf(t.y, t.y, s2y);
+            }
+            a1x[slot] += s1x; a1y[slot] += s1y; a2x[slot] += s2x; a2y[slot] += s2y;
+          }
+          ++cnt;
+        }
+      }
+      if (has_stat) {
+        // combine the 8 warps' partials in shared memory, then ONE fp64 atomic per channel and CTA
+        // (same-address L2 atomics serialise: per-warp flushes cost more than the layer's math)
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+          const int c = (cgrp + i * CG) * kSubW + 2 * lane;
+          if (c < BN) {
+            atomicAdd(s_stat + c, a1x[i]); atomicAdd(s_stat + c + 1, a1y[i]);
+            atomicAdd(s_stat + BN + c, a2x[i]); atomicAdd(s_stat + BN + c + 1, a2y[i]);
+          }
+        }
+        epi_barrier<32 * EW>();
+        if (stat_k0 >= 0) {
+          for (int j = et; j < BN; j += 32 * EW) {
+            if (stat_k0 + j < prm.K) {
+              atomicAdd(prm.bn_sum + stat_k0 + j, (double)s_stat[j]);
+              atomicAdd(prm.bn_sqsum + stat_k0 + j, (double)s_stat[BN + j]);
             }
           }
         }
       }
-      if (leader) bulk_wait_all();  // outstanding stores complete before the CTA retires
+      if (lane == 0) bulk_wait_all();  // outstanding stores complete before the CTA retires
     } else {
-      // ---- direct epilogue: per-thread global stores (fp32 logits, odd channel counts)
+      // ---- direct epilogue: per-thread global stores (fp32 logits, odd channel counts); 32-column
+      // chunks are dealt round-robin to the column groups
       for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
         int n, p0, q0, k0;
         decode_tile<BN>(prm, tile, n, p0, q0, k0);
@@ -402,11 +480,11 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
                  (((int64_t)n * prm.res_H + (int64_t)p * prm.res_stride) * prm.res_W + (int64_t)q * prm.res_stride) *
                      prm.res_pitch;
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = cgrp; ch < BN / 32; ch += CG) {
           const int kbase = k0 + ch * 32;
           if (kbase >= prm.K) break;  // warp-uniform
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+          tmem_ld<32>(lane_addr + (uint32_t)(acc * BN + ch * 32), v);
           tmem_ld_wait();
           float f[32];
 #pragma unroll
@@ -479,6 +557,11 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
 }
 
 // ----------------------------------------------------------------------------- host side
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -547,27 +630,34 @@ static bool igemm_supported(const wlseg_conv_params* p) {
   return true;
 }
 
-template <int BN, typename TY, bool kTmaEpi>
-static int launch_igemm(IgemmParams& prm, cudaStream_t s) {
+template <int BN, typename TY, bool kTmaEpi, int EW>
+static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   using Cfg = IgemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSmemMax));
+    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi, EW>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
-  // shared memory plan: [stages x {A,B}] [epi_bufs x 16 KB] [scale | shift] [barriers]
-  prm.epi_bufs = kTmaEpi ? (prm.res != nullptr ? 4 : 2) : 0;
-  const int fixed = prm.epi_bufs * kSubBytes + Cfg::kVecBytes + kBarBytes;
+  // shared memory plan: [stages x {A,B}] [epi_bufs x 4 KB] [barriers]
+  prm.epi_bufs = kTmaEpi ? (prm.res != nullptr ? 2 * EW : EW) : 0;
+  const int fixed = prm.epi_bufs * kWarpBufBytes + kBarBytes + (kTmaEpi ? 2 * BN * 4 : 0);
   int stages = (kSmemMax - fixed) / Cfg::kStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   WLSEG_CHECK_ARG(stages >= 2, "conv(tcgen05): shared memory plan leaves fewer than 2 pipeline stages");
   prm.stages = stages;
   const int smem_bytes = stages * Cfg::kStageBytes + fixed;
   int grid = prm.total_tiles < kNumSMs ? prm.total_tiles : kNumSMs;
-  conv_igemm_kernel<BN, TY, kTmaEpi><<<grid, kIgemmThreads, smem_bytes, s>>>(prm);
+  // fused BN statistics live in registers across tiles: every CTA must stay on one N tile
+  if (kTmaEpi && prm.bn_sum != nullptr && grid % prm.n_tiles != 0) grid -= grid % prm.n_tiles;
+  conv_igemm_kernel<BN, TY, kTmaEpi, EW><<<grid, 128 + 32 * EW, smem_bytes, s>>>(prm);
   WLSEG_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, typename TY, bool kTmaEpi>
+static int launch_igemm(IgemmParams& prm, cudaStream_t s) {
+  return launch_igemm_ew<BN, TY, kTmaEpi, 8>(prm, s);
 }
 
 static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const void* w, void* y, const float* scale,
@@ -600,16 +690,20 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   }
   const bool f32out = (p->y_dtype == WLSEG_F32);
   // staged (TMA) epilogue: bf16 output whose pixel pitch and base keep every 64-channel row 16-byte aligned
-  bool tma_epi = !f32out && BN >= kSubW && (p->y_pitch % 8 == 0) && ((((uintptr_t)y) & 15) == 0);
+  // (whole 64-channel sub-tiles only; scale / shift are read as float4)
+  bool tma_epi = !f32out && BN >= kSubW && (p->K % kSubW == 0) && (p->y_pitch % 8 == 0) &&
+                 ((((uintptr_t)y) & 15) == 0) && ((((uintptr_t)scale) & 15) == 0) && ((((uintptr_t)shift) & 15) == 0);
+  // one epilogue warp stores (and loads the residual of) its 32 tile rows: bw x bh pixels
+  const int bw = TW < 32 ? TW : 32, bh = 32 / bw;
   if (residual != nullptr && ((p->res_pitch % 8 != 0) || ((((uintptr_t)residual) & 15) != 0) ||
-                              TW * p->res_stride > 256 || TH * p->res_stride > 256))
+                              bw * p->res_stride > 256 || bh * p->res_stride > 256))
     tma_epi = false;
   if (tma_epi) {
     {
       uint64_t dims[4] = {(uint64_t)p->K, (uint64_t)p->Q, (uint64_t)p->P, (uint64_t)p->N};
       uint64_t strides[3] = {(uint64_t)p->y_pitch * 2, (uint64_t)p->y_pitch * 2 * p->Q,
                              (uint64_t)p->y_pitch * 2 * p->Q * p->P};
-      uint32_t box[4] = {(uint32_t)kSubW, (uint32_t)TW, (uint32_t)TH, 1};
+      uint32_t box[4] = {(uint32_t)kSubW, (uint32_t)bw, (uint32_t)bh, 1};
       uint32_t estr[4] = {1, 1, 1, 1};
       if (int e = encode_tensor_map(&prm.map_y, y, 2, 4, dims, strides, box, estr, 2)) return e;
     }
@@ -618,7 +712,7 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
       uint64_t dims[4] = {(uint64_t)p->K, (uint64_t)p->res_W, (uint64_t)p->res_H, (uint64_t)p->N};
       uint64_t strides[3] = {(uint64_t)p->res_pitch * 2, (uint64_t)p->res_pitch * 2 * p->res_W,
                              (uint64_t)p->res_pitch * 2 * p->res_W * p->res_H};
-      uint32_t box[4] = {(uint32_t)kSubW, (uint32_t)(TW * rs), (uint32_t)(TH * rs), 1};
+      uint32_t box[4] = {(uint32_t)kSubW, (uint32_t)(bw * rs), (uint32_t)(bh * rs), 1};
       uint32_t estr[4] = {1, (uint32_t)rs, (uint32_t)rs, 1};
       if (int e = encode_tensor_map(&prm.map_r, residual, 2, 4, dims, strides, box, estr, 3)) return e;
     }

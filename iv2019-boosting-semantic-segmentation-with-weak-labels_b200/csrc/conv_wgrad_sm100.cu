@@ -252,14 +252,14 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
         if (leader) {
           if (nb == 2) bulk_wait_read<1>(); else bulk_wait_read<3>();
         }
-        epi_barrier();
+        epi_barrier<128>();
         uint8_t* myrow = buf + row * 128;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<uint4*>(myrow + ((((uint32_t)g) ^ sw) << 4)) =
               make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
         fence_async_smem();
-        epi_barrier();
+        epi_barrier<128>();
         if (leader) {
           tma_reduce_add_3d(&prm.map_dw, smem_u32(buf), c0, tap, k0);
           bulk_commit();

@@ -233,6 +233,7 @@ class Network:
              'flops': 2.0 * N * out_hw[0] * out_hw[1] * w.shape[1] * w.shape[2] * C * K,
              'bytes': float(esz * (N * H * W * C + w.numel()) + y.element_size() * N * out_hw[0] * out_hw[1] * K +
                             (esz * N * out_hw[0] * out_hw[1] * K if residual is not None else 0)),
+             'sig': (N, H, W, C, K, w.shape[1], stride, dilation, residual is not None, bn_sum is not None, 'fprop'),
              'e0': torch.cuda.Event(enable_timing=True), 'e1': torch.cuda.Event(enable_timing=True)}
       rec['e0'].record()
     if bn_sum is not None and not tc:
@@ -488,6 +489,7 @@ class TrainNetwork(Network):
         prof = {'cls': 'wgrad_tc' if (self.dtype == torch.bfloat16 and C % 8 == 0) else 'wgrad_direct',
                 'flops': 2.0 * N * out_hw[0] * out_hw[1] * Rr * Ss * C * K,
                 'bytes': float(2 * (N * H * W * C + N * out_hw[0] * out_hw[1] * K) + 4 * K * Rr * Ss * C),
+                'sig': (N, H, W, C, K, Rr, stride, dilation, False, False, 'wgrad'),
                 'e0': torch.cuda.Event(enable_timing=True), 'e1': torch.cuda.Event(enable_timing=True)}
         prof['e0'].record()
       ops.conv2d_wgrad(prm, rec.x, dz, self._wgrad_view(scope, (K,) + tuple(rec.w.shape[1:])))

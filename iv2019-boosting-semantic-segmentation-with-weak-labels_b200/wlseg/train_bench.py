@@ -47,15 +47,14 @@ def run(args, cpu_train_sample=None):
     f, l = batches[i % 2]
     return tr.step(f, {k: v for k, v in l.items() if v is not None}, 0.01)
 
-  for i in range(args.warmup):
+  for i in range(max(args.warmup, 3)):  # two eager steps + the graph capture happen here
     step(i)
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
   torch.cuda.synchronize()
-  tr.net.profile = []
+  # timed region: the step as the product runs it (one CUDA-graph replay per step after the warm-up)
   sampler = ClockSampler(local_rank) if rank == 0 else None
-  l0 = ops.launches
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
   for i in range(args.steps):
@@ -67,8 +66,20 @@ def run(args, cpu_train_sample=None):
   torch.cuda.synchronize()
   clocks = sampler.stop() if sampler else None
   ms = e0.elapsed_time(e1)
-  launches = ops.launches - l0
+  # roofline pass, live, right after the timed region: the same steps launched eagerly with a CUDA
+  # event pair around every convolution launch (events cannot sit inside a replayed graph)
+  prof_steps = min(3, args.steps)
+  tr.net.profile = []
+  l0 = ops.launches
+  pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  pe0.record()
+  for i in range(prof_steps):
+    step(i)
+  pe1.record()
+  torch.cuda.synchronize()
+  launches = (ops.launches - l0) // prof_steps * args.steps
   prof, tr.net.profile = tr.net.profile, None
+  prof_ms = pe0.elapsed_time(pe1)
   t = torch.tensor([ms], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -93,14 +104,14 @@ def run(args, cpu_train_sample=None):
     roofline = {'bound': 'tensor', 'kernel': name, 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
                 'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)', 'launches': dom['launches'],
-                'share_of_step': dom['ms'] / ms}
+                'share_of_step': dom['ms'] / prof_ms, 'timed_over': f'{prof_steps} eagerly launched steps after the timed region'}
   if args.detail and rank == 0:
-    table = {k: {'launches': v['launches'], 'ms_per_step': v['ms'] / args.steps,
+    table = {k: {'launches': v['launches'], 'ms_per_step': v['ms'] / prof_steps,
                  'tflops': v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] else None,
                  'gbs_algorithmic': v['bytes'] / (v['ms'] / 1e3) / 1e9 if v['ms'] else None}
              for k, v in sorted(classes.items())}
     with open(args.detail, 'w') as fp:
-      json.dump({'ms_per_step': ms / args.steps, 'classes': table}, fp, indent=1)
+      json.dump({'ms_per_step': ms / args.steps, 'ms_per_step_eager_profiled': prof_ms / prof_steps, 'classes': table}, fp, indent=1)
 
   # ---- end to end: host batches (pinned fp32 images + int32 labels) -> step -> loss back to the host
   e2e = None
@@ -122,8 +133,11 @@ def run(args, cpu_train_sample=None):
     est.settings, est.hier, est.device, est.dtype, est.params = st, hier, dev, torch.bfloat16, params
     est.global_step, est.trainer = tr.global_step, tr
 
+    stamps = []
+
     def gen(n):
       for i in range(n):
+        stamps.append(time.perf_counter())
         yield host[i % 2]
     est.train(gen(2), 2)
     torch.cuda.synchronize()
@@ -133,6 +147,10 @@ def run(args, cpu_train_sample=None):
     est.train(gen(args.steps), args.steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if os.environ.get('WLSEG_BENCH_DEBUG'):
+      import sys
+      print('e2e batch-fetch stamps (ms):', [round(1e3 * (x - t0), 2) for x in stamps[-args.steps:]], 'total', 1e3 * dt,
+            'graphs', len(tr._graphs), file=sys.stderr)
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
       dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -153,6 +171,7 @@ def run(args, cpu_train_sample=None):
                                    f'hierarchical heads, fwd (batch-stat BN) + masked strong{"+weak" if mixed else ""} loss + bwd + '
                                    f'SGD-momentum, {H}x{W} crops, {NB} strong + {npb} bbox + {npi} image-level images/GPU, random init',
                        'l2': 'two rotating input batches; activations + gradients (GBs) exceed the 126 MB L2',
+                       'launch': 'whole step replayed as one CUDA graph',
                        'parallelism': f'data parallel x{world}, NCCL gradient all-reduce bucketed behind backward' if world > 1 else 'single GPU',
                        'fwd_gflop_per_image': fwd, 'last_loss': [float(x) for x in out.tolist()]},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * world, 'roofline': roofline, 'cpu_baseline': cpu}
