@@ -65,6 +65,7 @@ typedef struct wlseg_conv_params {
   int32_t dtype;            /* WLSEG_F32 | WLSEG_BF16: x, w, residual (and y) storage */
   int32_t y_dtype;          /* storage of y; WLSEG_F32 lets a bf16 layer emit fp32 (logits) */
   int32_t algo;             /* WLSEG_ALGO_* */
+  int32_t accumulate;       /* wgrad only: 0 = dw is overwritten, 1 = dw += (the caller zeroed it) */
 } wlseg_conv_params;
 
 /* 1 if the tcgen05 implicit-GEMM kernel covers this configuration, else 0. */
@@ -80,7 +81,8 @@ int wlseg_conv2d_dgrad(const wlseg_conv_params* p, const void* dy, const void* w
                        wlseg_stream_t stream);
 
 /* dw[k,r,s,c] = sum_{n,p,q} dy[n,p,q,k] * x[...]  (TF Conv2DBackpropFilter); dw is fp32 KRSC,
- * fully written (beta = 0). */
+ * fully written (beta = 0) unless p->accumulate is set (then added to: one memset of the whole
+ * gradient arena per step replaces one per layer). */
 int wlseg_conv2d_wgrad(const wlseg_conv_params* p, const void* x, const void* dy, float* dw,
                        wlseg_stream_t stream);
 
@@ -226,6 +228,15 @@ int wlseg_cast_bf16_to_f32(const void* src, float* dst, int64_t n, wlseg_stream_
  * stride-1 dgrad runs as an fprop) from src KRSC. */
 int wlseg_weights_transpose_flip(const void* src, void* dst, int32_t K, int32_t R, int32_t S,
                                  int32_t C, int32_t dtype, wlseg_stream_t stream);
+/* The same for every layer of the network in one launch: `table` is int32[n_layers][6] on the
+ * device, rows {src_off, dst_off, K, R, S, C} (element offsets into the two arenas). */
+int wlseg_weights_transpose_flip_batched(const void* src_arena, void* dst_arena, const int32_t* table,
+                                         int32_t n_layers, int32_t dtype, wlseg_stream_t stream);
+/* dst[N,Hu,Wu,C] = src[N,P,Q,C] with stride-1 zeros inserted between the pixels (dst fully written).
+ * The input gradient of a strided convolution (TF Conv2DBackpropInput) is a stride-1 convolution
+ * over this tensor, which runs on the tensor cores. */
+int wlseg_zero_insert(const void* src, void* dst, int32_t N, int32_t P, int32_t Q, int32_t C, int32_t stride,
+                      int32_t Hu, int32_t Wu, int32_t dtype, wlseg_stream_t stream);
 /* Packs a 3-channel NHWC image (fp32 or bf16) for the ResNet root convolution
  * (7x7 stride 2, models/resnet50_extended_feature_extractor.py:25-30) into the bf16 tensor
  * out[N, ceil(H/2), ceil(W/2), 64] = space-to-depth(2) with the 4 horizontal taps unrolled into

@@ -236,7 +236,7 @@ extern "C" int wlseg_conv2d_wgrad(const wlseg_conv_params* p, const void* x, con
   if (int e = check_conv_params(p)) return e;
   WLSEG_CHECK_ARG(dw != nullptr, "conv_wgrad: dw is NULL");
   const int64_t total = (int64_t)p->K * p->R * p->S * p->C;
-  WLSEG_CUDA(cudaMemsetAsync(dw, 0, total * sizeof(float), (cudaStream_t)stream));
+  if (!p->accumulate) WLSEG_CUDA(cudaMemsetAsync(dw, 0, total * sizeof(float), (cudaStream_t)stream));
   if (p->N == 0) return 0;
   WLSEG_CHECK_ARG(x && dy, "conv_wgrad: null pointer");
   WLSEG_CHECK_ARG(p->y_dtype == p->dtype, "conv_wgrad: dy must be stored in dtype");

@@ -17,12 +17,12 @@
 //   one pipeline stage = one patch of 64 pixels = 4 MMAs (K = 16 pixels each)
 //   D = fp32 128 x 256 in TMEM, double buffered
 // Work unit = (output tile, pixel split): the pixel range is split so that ~2 x 148 units exist;
-// partial tiles are combined by the TMA itself: the epilogue stages 128 x 32 fp32 sub-tiles in
-// swizzled shared memory and issues cp.reduce.async.bulk.tensor (.add) into dw, which the caller
+// partial tiles are combined by the TMA itself: every epilogue warp stages its 32 x 32 fp32 sub-tiles
+// in swizzled shared memory and issues cp.reduce.async.bulk.tensor (.add) into dw, which the caller
 // (this file's entry point) zeroes first.
 //
 // Warp roles as in conv_igemm_sm100.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue.
+// allocator, warps 4-11 epilogue (independent per-warp drains).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -34,12 +34,13 @@ int check_conv_params(const wlseg_conv_params* p);
 int encode_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, int kind);
 
-constexpr int kWgThreads = 256;
+constexpr int kWgEpiWarps = 8;
+constexpr int kWgThreads = 128 + 32 * kWgEpiWarps;
 constexpr int kWgEpiWarp0 = 4;
+constexpr int kWgWarpBufBytes = 32 * 128;   // epilogue staging per warp: 32 rows x 32 fp32
 constexpr int kPix = 64;                    // pixels per stage (reduction depth of one stage)
 constexpr int kChunkBytes = kPix * 128;     // one {64 ch x 64 pix} bf16 box = 8 KB
 constexpr int kWgABytes = 2 * kChunkBytes;  // M = 128 output channels
-constexpr int kWgSubBytes = 128 * 128;      // epilogue staging: 128 rows x 32 fp32
 constexpr int kWgMaxStages = 8;
 constexpr int kWgSmemMax = 227 * 1024;
 
@@ -93,7 +94,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int stages = prm.stages;
   uint8_t* epi_smem = smem + stages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + prm.epi_bufs * kWgSubBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kWgEpiWarps * kWgWarpBufBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kWgMaxStages;
   uint64_t* tfull_bar = bars + 2 * kWgMaxStages;
@@ -115,7 +116,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(tfull_bar + a), 1);
-      mbar_init(smem_u32(tempty_bar + a), 4);
+      mbar_init(smem_u32(tempty_bar + a), kWgEpiWarps);
     }
     fence_barrier_init();
   }
@@ -211,12 +212,16 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
     }
   } else if (warp >= kWgEpiWarp0) {
     // ===================== epilogue: TMEM -> swizzled smem -> TMA reduce-add into dw =====================
+    // one independent pipeline per warp (as in conv_igemm_sm100.cu): warp e owns the 32 output channels
+    // of TMEM lane quarter e % 4 and every second 32-column sub-tile; its own 4 KB staging buffer and
+    // its own cp.reduce.async.bulk.tensor - no CTA-wide barrier in the drain
     const int ew = warp - kWgEpiWarp0;
-    const int row = ew * 32 + lane;             // output channel within the tile
-    const bool leader = (row == 0);
-    const uint32_t sw = (uint32_t)(row & 7);
-    const int nb = prm.epi_bufs;                // 2 or 4
-    int iter = 0, seq = 0;
+    const int quarter = ew & 3, cgrp = ew >> 2;
+    constexpr int CG = kWgEpiWarps / 4;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    uint8_t* buf = epi_smem + ew * kWgWarpBufBytes;
+    uint8_t* myrow = buf + lane * 128;
+    int iter = 0;
     for (int unit = blockIdx.x; unit < prm.units; unit += gridDim.x, ++iter) {
       const int tile = unit % prm.tiles;
       const int nt = tile % prm.n_tiles, mt = tile / prm.n_tiles;
@@ -233,45 +238,42 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
         const int tap = id / prm.cchunks;
         if ((id - tap * prm.cchunks) * 64 + (j & 1) * 32 < prm.C) nsub = j + 1;
       }
-      for (int j = 0; j < nsub; ++j) {
+      // this warp's last sub-tile index (its final TMEM read of the unit)
+      int last = -1;
+      for (int j = cgrp; j < nsub; j += CG) last = j;
+      if (last < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+      }
+      for (int j = cgrp; j < nsub; j += CG) {
         const int id = nt * CH + (j >> 1);
         const int tap = id / prm.cchunks;
         const int c0 = (id - tap * prm.cchunks) * 64 + (j & 1) * 32;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
         tmem_ld_wait();
-        if (j == nsub - 1) {
+        if (j == last) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
         }
-        if (c0 >= prm.C) continue;  // uniform across the CTA (odd C chunk): nothing to store
-        const int b = seq & (nb - 1);
-        ++seq;
-        uint8_t* buf = epi_smem + b * kWgSubBytes;
-        if (leader) {
-          if (nb == 2) bulk_wait_read<1>(); else bulk_wait_read<3>();
-        }
-        epi_barrier<128>();
-        uint8_t* myrow = buf + row * 128;
+        if (c0 >= prm.C) continue;  // warp-uniform (odd C chunk): nothing to store
+        if (lane == 0) bulk_wait_read<0>();   // the reduce that last left from this buffer has read it
+        __syncwarp();
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<uint4*>(myrow + ((((uint32_t)g) ^ sw) << 4)) =
               make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
         fence_async_smem();
-        epi_barrier<128>();
-        if (leader) {
-          tma_reduce_add_3d(&prm.map_dw, smem_u32(buf), c0, tap, k0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_3d(&prm.map_dw, smem_u32(buf), c0, tap, k0 + quarter * 32);
           bulk_commit();
         }
       }
-      if (nsub == 0) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-      }
     }
-    if (leader) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -298,8 +300,8 @@ static int launch_wgrad(WgradParams& prm, cudaStream_t s) {
     WLSEG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemMax));
     configured = true;
   }
-  prm.epi_bufs = 2;
-  const int fixed = prm.epi_bufs * kWgSubBytes + 256;
+  prm.epi_bufs = kWgEpiWarps;
+  const int fixed = kWgEpiWarps * kWgWarpBufBytes + 256;
   int stages = (kWgSmemMax - fixed) / kStageBytes;
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   prm.stages = stages;
@@ -340,7 +342,7 @@ int conv_wgrad_tcgen05(const wlseg_conv_params* p, const void* x, const void* dy
   {
     uint64_t dims[3] = {(uint64_t)p->C, (uint64_t)(p->R * p->S), (uint64_t)p->K};
     uint64_t strides[2] = {(uint64_t)p->C * 4, (uint64_t)p->C * 4 * p->R * p->S};
-    uint32_t box[3] = {32, 1, 128};
+    uint32_t box[3] = {32, 1, 32};   // one epilogue warp's 32 output channels x 32 fp32
     uint32_t estr[3] = {1, 1, 1};
     if (int e = encode_tensor_map(&prm.map_dw, dw, 4, 3, dims, strides, box, estr, 12)) return e;
   }

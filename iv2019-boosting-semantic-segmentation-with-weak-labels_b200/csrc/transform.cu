@@ -44,9 +44,92 @@ conv1_pack_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ out, in
   }
 }
 
+// dst[n, h, w, :] = (h % s == 0 && w % s == 0 && h/s < P && w/s < Q) ? src[n, h/s, w/s, :] : 0
+// The gradient of a stride-s convolution wrt its input is a stride-1 convolution over this
+// zero-inserted dy, which the tensor-core fprop kernel runs (3 of 4 MMAs multiply zeros: the only
+// strided layer with an input gradient is block1/unit_3/conv2, 0.6 % of the network's FLOPs).
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_insert_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int P, int Q, int C, int s, int Hu, int Wu) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)N * Hu * Wu * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t t = i / cv;
+    const int w = (int)(t % Wu); t /= Wu;
+    const int h = (int)(t % Hu);
+    const int n = (int)(t / Hu);
+    Vec8<T> v;
+    const int p = h / s, q = w / s;
+    if (h - p * s == 0 && w - q * s == 0 && p < P && q < Q) {
+      v.load(src + (((int64_t)n * P + p) * Q + q) * C + c8 * 8);
+    } else {
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      v.pack(z);
+    }
+    v.store(dst + i * 8);
+  }
+}
+
+// All dgrad filter banks of the network in ONE launch: blockIdx.y = layer (table row
+// {src_off, dst_off, K, R, S, C}), dst[c][R-1-r][S-1-s][k] = src[k][r][s][c].
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_flip_batched_kernel(const T* __restrict__ src, T* __restrict__ dst, const int32_t* __restrict__ table) {
+  const int32_t* e = table + 6 * blockIdx.y;
+  const int64_t so = e[0], dofs = e[1];
+  const int K = e[2], R = e[3], S = e[4], C = e[5];
+  const int64_t n = (int64_t)K * R * S * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    int64_t t = i / K;
+    const int s2 = (int)(t % S); t /= S;
+    const int r2 = (int)(t % R);
+    const int c = (int)(t / R);
+    dst[dofs + i] = src[so + (((int64_t)k * R + (R - 1 - r2)) * S + (S - 1 - s2)) * C + c];
+  }
+}
+
 }  // namespace wlseg
 
 using namespace wlseg;
+
+extern "C" int wlseg_zero_insert(const void* src, void* dst, int32_t N, int32_t P, int32_t Q, int32_t C,
+                                 int32_t stride, int32_t Hu, int32_t Wu, int32_t dtype, wlseg_stream_t stream) {
+  WLSEG_CHECK_ARG(N >= 0 && P > 0 && Q > 0 && C > 0 && stride > 0 && Hu > 0 && Wu > 0, "zero_insert: bad shape");
+  WLSEG_CHECK_ARG(C % 8 == 0, "zero_insert: C (%d) must be a multiple of 8", C);
+  if (N == 0) return 0;
+  WLSEG_CHECK_ARG(src && dst, "zero_insert: null pointer");
+  const int64_t total = (int64_t)N * Hu * Wu * (C / 8);
+  const int grid = bw_grid(total, 256, 8);
+  if (dtype == WLSEG_BF16)
+    zero_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, N, P, Q, C,
+                                                               stride, Hu, Wu);
+  else if (dtype == WLSEG_F32)
+    zero_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, N, P, Q, C, stride, Hu, Wu);
+  else
+    WLSEG_CHECK_ARG(false, "zero_insert: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wlseg_weights_transpose_flip_batched(const void* src_arena, void* dst_arena, const int32_t* table,
+                                                    int32_t n_layers, int32_t dtype, wlseg_stream_t stream) {
+  WLSEG_CHECK_ARG(n_layers >= 0, "transpose_flip_batched: bad layer count");
+  if (n_layers == 0) return 0;
+  WLSEG_CHECK_ARG(src_arena && dst_arena && table, "transpose_flip_batched: null pointer");
+  WLSEG_CHECK_ARG(n_layers <= 65535, "transpose_flip_batched: too many layers");
+  dim3 grid(32, n_layers);
+  if (dtype == WLSEG_BF16)
+    transpose_flip_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_arena,
+                                                                          (__nv_bfloat16*)dst_arena, table);
+  else if (dtype == WLSEG_F32)
+    transpose_flip_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src_arena, (float*)dst_arena, table);
+  else
+    WLSEG_CHECK_ARG(false, "transpose_flip_batched: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int wlseg_conv1_pack(const void* img, int32_t dtype, int32_t N, int32_t H, int32_t W, void* out,
                                 wlseg_stream_t stream) {

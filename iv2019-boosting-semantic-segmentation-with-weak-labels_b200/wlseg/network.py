@@ -174,6 +174,31 @@ class Params:
       self._derived[key] = (scale.contiguous(), shift.contiguous())
     return self._derived[key]
 
+  def flip_plan(self):
+    """(table, arena, views) for the one-launch refresh of every stride-1/2 dgrad filter bank
+    ([C, R, S, K], rotated 180 degrees) from the bf16 operand arena.  The three adaptation conv1
+    kernels form ONE bank (they run as one 256 -> 768 GEMM); the root convolution has no input
+    gradient; the logits layers (K = 14 / 7 / 3, padded to 8 / 16) keep their per-layer path."""
+    if getattr(self, '_flip', None) is None:
+      rows, views = [], {}
+      arena = torch.zeros(self.n_total, dtype=torch.bfloat16, device=self.device)
+      fused = [s.scope for s in self.specs if s.scope.startswith('adaptation_module/') and s.scope.endswith('/conv1')]
+      for s in self.specs:
+        if s.scope.endswith('resnet_v1_50/conv1') or s.K % 8 != 0:
+          continue
+        o = self.w_off[s.scope]
+        if s.scope in fused:
+          if s.scope != fused[0]:
+            continue
+          K = s.K * len(fused)
+        else:
+          K = s.K
+        rows.append([o, o, K, s.R, s.S, s.C])
+        views[s.scope] = arena[o:o + K * s.R * s.S * s.C].view(s.C, s.R, s.S, K)
+      table = torch.tensor(rows, dtype=torch.int32, device=self.device)
+      self._flip = (table, arena, views)
+    return self._flip
+
   def flipped(self, scope, dtype):
     """Filter bank of the stride-1 dgrad-as-fprop: [C, R, S, K], rotated 180 degrees."""
     key = ('flip', scope, dtype)
@@ -397,6 +422,7 @@ class TrainNetwork(Network):
     self.ws = TrainWorkspace(params)
     self.grad_ready = None  # callback(lo): every conv-kernel gradient at arena offset >= lo is final
     self.keep = False       # tests: keep per-layer gradient tensors on the tape
+    self._flipped = None    # {scope: dgrad filter bank view}, refreshed at the start of backward()
     self._order = {s.scope: i for i, s in enumerate(params.specs)}
 
   def _mark_done(self, scope, n_elems):
@@ -482,7 +508,8 @@ class TrainNetwork(Network):
       self._root_wgrad(rec, dz)
     else:
       prm = ops.conv_params((N, H, W, C), (K,) + tuple(rec.w.shape[1:]), stride=stride, dilation=dilation, pad=pad,
-                            out_hw=out_hw, x_pitch=rec.x.stride(2), y_pitch=dz.stride(2), dtype=self.code)
+                            out_hw=out_hw, x_pitch=rec.x.stride(2), y_pitch=dz.stride(2), dtype=self.code,
+                            accumulate=True)  # the gradient arena was zeroed once, at the start of backward()
       prof = None
       if self.profile is not None:
         Rr, Ss = rec.w.shape[1], rec.w.shape[2]
@@ -505,17 +532,26 @@ class TrainNetwork(Network):
     dx = dx_out if dx_out is not None else torch.empty((N, H, W, C), dtype=self.dtype, device=self.dev)
     R, S = rec.w.shape[1], rec.w.shape[2]
     done = False
-    if stride == 1 and self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT:
-      # stride-1 dgrad == fprop over dz with the 180-degree rotated, transposed filter bank
+    if self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT:
+      # dgrad == stride-1 fprop over dz (zero-inserted when the layer was strided) with the 180-degree
+      # rotated, transposed filter bank
       Kp = dz.shape[-1]
-      wf = torch.empty((C, R, S, K), dtype=self.dtype, device=self.dev)
-      ops.weights_transpose_flip(wsrc, wf)
+      wf = self._flipped.get(scope) if self._flipped is not None else None
+      if wf is None or tuple(wf.shape) != (C, R, S, K):
+        wf = torch.empty((C, R, S, K), dtype=self.dtype, device=self.dev)
+        ops.weights_transpose_flip(wsrc, wf)
       if Kp != K:
         wfp = torch.zeros((C, R, S, Kp), dtype=self.dtype, device=self.dev)
         wfp[..., :K] = wf
         wf = wfp
+      if stride > 1:
+        dzu = torch.empty((N, (out_hw[0] - 1) * stride + 1, (out_hw[1] - 1) * stride + 1, Kp), dtype=self.dtype,
+                          device=self.dev)
+        ops.zero_insert(dz, dzu, stride)
+      else:
+        dzu = dz
       fpad = (dilation * (R - 1) - pad[0], dilation * (S - 1) - pad[1])
-      self._conv(dz, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx)
+      self._conv(dzu, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx)
       done = True
     if not done:
       prm = ops.conv_params((N, H, W, C), tuple(rec.w.shape), stride=stride, dilation=dilation, pad=pad,
@@ -633,6 +669,12 @@ class TrainNetwork(Network):
     """dlogits: fp32 [N, h, w, logits_pitch] gradient wrt the post-BN low-res logits.  Fills the
     gradient arena (conv kernels, gammas, betas)."""
     ws = self.ws
+    ws.grads.zero_()  # one memset: every wgrad below accumulates (split-K partial sums) into the arena
+    self._flipped = None
+    if self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT:
+      table, arena, views = self.p.flip_plan()
+      ops.weights_transpose_flip_batched(self.p.operand, arena, table)  # every dgrad bank, one launch
+      self._flipped = views
     self._done = [False] * len(self.p.specs)
     self._tail = len(self.p.specs)
     f = self.tape['features']

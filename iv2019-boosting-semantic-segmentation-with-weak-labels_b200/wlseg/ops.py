@@ -29,7 +29,8 @@ class WlsegError(RuntimeError):
 class ConvParams(ctypes.Structure):
   _fields_ = [(n, _c_int) for n in (
       'N', 'H', 'W', 'C', 'K', 'R', 'S', 'P', 'Q', 'stride', 'dilation', 'pad_top', 'pad_left',
-      'x_pitch', 'y_pitch', 'res_pitch', 'res_stride', 'res_H', 'res_W', 'relu', 'dtype', 'y_dtype', 'algo')]
+      'x_pitch', 'y_pitch', 'res_pitch', 'res_stride', 'res_H', 'res_W', 'relu', 'dtype', 'y_dtype', 'algo',
+      'accumulate')]
 
 
 class Hierarchy(ctypes.Structure):
@@ -72,6 +73,8 @@ _SIGNATURES = {
     'wlseg_cast_f32_to_bf16': (ctypes.c_int, [_vp, _vp, _c_i64, _vp]),
     'wlseg_cast_bf16_to_f32': (ctypes.c_int, [_vp, _vp, _c_i64, _vp]),
     'wlseg_weights_transpose_flip': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    'wlseg_weights_transpose_flip_batched': (ctypes.c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
+    'wlseg_zero_insert': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
     'wlseg_conv1_pack': (ctypes.c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
 }
 
@@ -130,7 +133,7 @@ def _count(n=1):
 
 # ------------------------------------------------------------------------------------ convolution
 def conv_params(x_shape, w_shape, stride=1, dilation=1, pad=(0, 0), out_hw=None, x_pitch=None, y_pitch=None,
-                relu=False, dtype=BF16, y_dtype=None, algo=ALGO_AUTO, res=None, res_stride=1):
+                relu=False, dtype=BF16, y_dtype=None, algo=ALGO_AUTO, res=None, res_stride=1, accumulate=False):
   N, H, W, C = x_shape
   K, R, S, Cw = w_shape
   assert Cw == C, f'filter channels {Cw} != input channels {C}'
@@ -154,6 +157,7 @@ def conv_params(x_shape, w_shape, stride=1, dilation=1, pad=(0, 0), out_hw=None,
   p.dtype = dtype
   p.y_dtype = dtype if y_dtype is None else y_dtype
   p.algo = algo
+  p.accumulate = int(accumulate)
   return p
 
 
@@ -192,6 +196,26 @@ def weights_transpose_flip(src, dst):
   K, R, S, C = src.shape
   _check(lib().wlseg_weights_transpose_flip(_ptr(src), _ptr(dst), K, R, S, C, dtype_code(src.dtype), _stream()),
          'wlseg_weights_transpose_flip')
+  _count()
+  return dst
+
+
+def weights_transpose_flip_batched(src_arena, dst_arena, table):
+  """table: int32 [L, 6] device tensor of {src_off, dst_off, K, R, S, C} rows."""
+  assert table.dtype == torch.int32 and table.is_contiguous() and src_arena.dtype == dst_arena.dtype
+  _check(lib().wlseg_weights_transpose_flip_batched(_ptr(src_arena), _ptr(dst_arena), _ptr(table), table.shape[0],
+                                                    dtype_code(src_arena.dtype), _stream()),
+         'wlseg_weights_transpose_flip_batched')
+  _count()
+  return dst_arena
+
+
+def zero_insert(src, dst, stride):
+  N, P, Q, C = src.shape
+  _, Hu, Wu, _ = dst.shape
+  assert src.is_contiguous() and dst.is_contiguous() and dst.shape[3] == C and src.dtype == dst.dtype
+  _check(lib().wlseg_zero_insert(_ptr(src), _ptr(dst), N, P, Q, C, stride, Hu, Wu, dtype_code(src.dtype), _stream()),
+         'wlseg_zero_insert')
   _count()
   return dst
 

@@ -139,7 +139,7 @@ def run(args, cpu_train_sample=None):
       for i in range(n):
         stamps.append(time.perf_counter())
         yield host[i % 2]
-    est.train(gen(2), 2)
+    est.train(gen(args.steps), args.steps)  # same step count: same pinned result buffer size
     torch.cuda.synchronize()
     if world > 1:
       dist.barrier()
@@ -177,4 +177,13 @@ def run(args, cpu_train_sample=None):
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * world, 'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line), flush=True)
   if world > 1:
-    dist.destroy_process_group()
+    # captured NCCL collectives keep the communicator busy: drop the graphs, drain, and leave without
+    # running the process-group destructor (it can wait forever on a communicator a graph still holds)
+    tr._graphs.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    import sys
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)

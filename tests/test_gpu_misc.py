@@ -145,3 +145,30 @@ def test_conv1_pack_is_exact_rewrite(cuda):
   got = tfops.conv2d(packed.float().cpu().double(), w2.permute(1, 2, 3, 0).double(), 1, 1, (2, 1, 0, 0))
   assert got.shape == ref.shape
   assert float((got - ref).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_zero_insert_and_batched_flip(cuda, dtype):
+  """Bit-exact data movement: stride-2 zero insertion (strided dgrad on the tensor cores) and the
+  one-launch refresh of several dgrad filter banks."""
+  from wlseg import ops
+  g = torch.Generator().manual_seed(3)
+  src = torch.randn((2, 5, 7, 16), generator=g).to(dtype)
+  dst = torch.full((2, 9, 13, 16), 7.0, dtype=dtype, device=cuda)
+  ops.zero_insert(src.to(cuda), dst, 2)
+  want = torch.zeros((2, 9, 13, 16), dtype=dtype)
+  want[:, ::2, ::2, :] = src
+  assert torch.equal(dst.cpu(), want)
+  shapes = [(8, 3, 3, 16), (24, 1, 1, 8), (16, 4, 1, 8)]
+  offs, n = [], 0
+  for s in shapes:
+    offs.append(n)
+    n += s[0] * s[1] * s[2] * s[3]
+  arena = torch.randn(n, generator=g).to(dtype)
+  out = torch.zeros(n, dtype=dtype, device=cuda)
+  table = torch.tensor([[o, o, *s] for o, s in zip(offs, shapes)], dtype=torch.int32, device=cuda)
+  ops.weights_transpose_flip_batched(arena.to(cuda), out, table)
+  for o, (K, R, S, C) in zip(offs, shapes):
+    w = arena[o:o + K * R * S * C].view(K, R, S, C)
+    ref = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()
+    assert torch.equal(out[o:o + K * R * S * C].view(C, R, S, K).cpu(), ref)
