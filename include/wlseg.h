@@ -103,6 +103,14 @@ int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t count, int
                       float* moving_mean, float* moving_var, float* scale, float* shift,
                       float* saved_mean, float* saved_invstd, wlseg_stream_t stream);
 
+/* wlseg_bn_finalize + wlseg_bn_apply in one launch (C % 8 == 0, C <= 2048): every CTA derives
+ * scale / shift from the sums; CTA 0 publishes them (+ saved mean / invstd, moving statistics). */
+int wlseg_bn_finalize_apply(const double* sum, const double* sqsum, int64_t count, int32_t C,
+                            const float* gamma, const float* beta, float eps, float decay,
+                            float* moving_mean, float* moving_var, float* scale, float* shift,
+                            float* saved_mean, float* saved_invstd, const void* z, const void* residual,
+                            void* y, int32_t relu, int32_t dtype, wlseg_stream_t stream);
+
 /* y = relu?( z*scale[c] + shift[c] + residual ), elementwise over count x C. */
 int wlseg_bn_apply(const void* z, const float* scale, const float* shift, const void* residual,
                    void* y, int64_t count, int32_t C, int32_t relu, int32_t dtype,
@@ -111,14 +119,22 @@ int wlseg_bn_apply(const void* z, const float* scale, const float* shift, const 
 /* Backward of y = relu?(bn(z) + residual).  Pass 1 (reduce): with g = dy * (y > 0 if relu),
  * dbeta[c] += sum g, dgamma[c] += sum g * (z - mean)*invstd  (double[C], caller zeroes).
  * Pass 2 (apply): dz = gamma*invstd*(g - dbeta/count - zhat*dgamma/count); if dres != NULL the
- * masked gradient g is also written there (gradient of the residual input). */
+ * masked gradient g is also written there (gradient of the residual input).
+ * `y` may be NULL for a ReLU layer WITHOUT a residual input: the mask is then the sign of
+ * fmaf(z, scale[c], shift[c]) - the fp32 value the forward pass rounded to y - and y is not read.
+ * `pitch` = elements between consecutive rows of dy / y / z / dz / dres (all share it): a channel
+ * slice [c0, c0 + C) of a wider tensor is processed by passing pointers offset by c0 and the full
+ * width as pitch; the host mirror runs reduce + apply slice by slice so that the second pass reads
+ * its three inputs from L2 instead of HBM. */
 int wlseg_bn_bwd_reduce(const void* dy, const void* y, const void* z, const float* mean,
-                        const float* invstd, int64_t count, int32_t C, int32_t relu,
-                        int32_t dtype, double* dgamma, double* dbeta, wlseg_stream_t stream);
+                        const float* invstd, const float* scale, const float* shift, int64_t count,
+                        int32_t C, int32_t pitch, int32_t relu, int32_t dtype, double* dgamma,
+                        double* dbeta, wlseg_stream_t stream);
 int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* mean,
-                       const float* invstd, const float* gamma, const double* dgamma,
-                       const double* dbeta, int64_t count, int32_t C, int32_t relu, int32_t dtype,
-                       void* dz, void* dres, wlseg_stream_t stream);
+                       const float* invstd, const float* gamma, const float* scale, const float* shift,
+                       const double* dgamma, const double* dbeta, int64_t count, int32_t C,
+                       int32_t pitch, int32_t relu, int32_t dtype, void* dz, void* dres,
+                       wlseg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Max pool, TF 'SAME' padding (replaces slim.max_pool2d: resnet pool1 3x3 s2 and the 1x1 s2

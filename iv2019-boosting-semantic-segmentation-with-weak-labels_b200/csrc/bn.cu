@@ -19,10 +19,13 @@ constexpr int kBnThreads = 256;
 template <typename T, bool kBackward>
 __global__ void __launch_bounds__(kBnThreads)
 bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* __restrict__ z,
-                 const float* __restrict__ mean, const float* __restrict__ invstd, int64_t count, int C, int pitch,
-                 int relu, double* __restrict__ out0, double* __restrict__ out1) {
+                 const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
+                 const float* __restrict__ shift, int64_t count, int C, int pitch, int relu,
+                 double* __restrict__ out0, double* __restrict__ out1) {
   // forward (kBackward=false): a = z;  out0 += sum z, out1 += sum z^2
-  // backward: a = dy; g = dy*(yact>0 if relu); out0 += sum g*(z-mean)*invstd (dgamma), out1 += sum g (dbeta)
+  // backward: a = dy; g = dy*(y>0 if relu); out0 += sum g*(z-mean)*invstd (dgamma), out1 += sum g (dbeta)
+  //   the ReLU mask comes from yact, or - when yact is NULL (layers without a residual input) - from the
+  //   sign of fmaf(z, scale, shift), the exact fp32 value the forward pass rounded to y
   extern __shared__ float part[];  // [lanes][2][C]
   const int cv = C / 8;
   const int lanes = kBnThreads / cv;
@@ -30,10 +33,15 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* _
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
-  float mu[8], is[8];
+  float mu[8], is[8], sc[8], sh[8];
+  const bool zmask = kBackward && relu && yact == nullptr;
   if (kBackward) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mu[j] = mean[tx * 8 + j]; is[j] = invstd[tx * 8 + j]; }
+    if (zmask) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = scale[tx * 8 + j]; sh[j] = shift[tx * 8 + j]; }
+    }
   }
   if (ty < lanes) {
     for (int64_t row = (int64_t)blockIdx.x * lanes + ty; row < count; row += (int64_t)gridDim.x * lanes) {
@@ -49,7 +57,10 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* _
         Vec8<T> vz;
         vz.load(z + row * pitch + tx * 8);
         vz.unpack(zz);
-        if (relu) {
+        if (zmask) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(zz[j], sc[j], sh[j]) > 0.f ? f[j] : 0.f;
+        } else if (relu) {
           float yy[8];
           Vec8<T> vy;
           vy.load(yact + row * pitch + tx * 8);
@@ -138,6 +149,76 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const 
   }
 }
 
+// bn_finalize fused into bn_apply: every CTA derives scale / shift of all C channels from the fp64
+// sums into shared memory (C <= 2048: a few flops per thread); CTA 0 also publishes scale / shift /
+// saved mean / inverse std for the backward pass and updates the moving statistics.  One launch per
+// layer less, and the apply loop reads its constants from shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_finalize_apply_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, int64_t count, int C,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float decay,
+                         float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale,
+                         float* __restrict__ shift, float* __restrict__ saved_mean, float* __restrict__ saved_invstd,
+                         const T* __restrict__ z, const T* __restrict__ res, T* __restrict__ y, int relu) {
+  extern __shared__ float sconst[];  // [2][C]: scale | shift
+  float* ssc = sconst;
+  float* ssh = sconst + C;
+  const double n = (double)count;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double m = sum[c] / n;
+    double var = sqsum[c] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)m, vf = (float)var;
+    const float inv = rsqrtf(vf + eps);
+    const float sc = gamma[c] * inv;
+    const float sh = beta[c] - mf * sc;
+    ssc[c] = sc;
+    ssh[c] = sh;
+    if (blockIdx.x == 0) {
+      scale[c] = sc;
+      shift[c] = sh;
+      saved_mean[c] = mf;
+      saved_invstd[c] = inv;
+      if (moving_mean != nullptr) {
+        const float unbiased = count > 1 ? (float)(var * (n / (n - 1.0))) : vf;
+        moving_mean[c] -= (1.0f - decay) * (moving_mean[c] - mf);
+        moving_var[c] -= (1.0f - decay) * (moving_var[c] - unbiased);
+      }
+    }
+  }
+  __syncthreads();
+  const int cv = C / 8;
+  const int64_t total = count * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    float f[8];
+    Vec8<T> v;
+    v.load(z + i * 8);
+    v.unpack(f);
+    const float4 sa = *reinterpret_cast<const float4*>(ssc + c0), sb = *reinterpret_cast<const float4*>(ssc + c0 + 4);
+    const float4 ha = *reinterpret_cast<const float4*>(ssh + c0), hb = *reinterpret_cast<const float4*>(ssh + c0 + 4);
+    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+    if (res != nullptr) {
+      float r[8];
+      Vec8<T> vr;
+      vr.load(res + i * 8);
+      vr.unpack(r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    Vec8<T> o;
+    o.pack(f);
+    o.store(y + i * 8);
+  }
+}
+
 // dz = gamma*invstd*(g - dbeta/n - zhat*dgamma/n) = A*g + c1*z + c0 with per-channel constants
 //   A = gamma*invstd, c1 = -A*invstd*dgamma/n, c0 = -A*dbeta/n - c1*mean
 // computed once per CTA into shared memory (the fp64 sums are touched C times, not count*C times).
@@ -145,12 +226,16 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
                     const double* __restrict__ dgamma, const double* __restrict__ dbeta, int64_t count, int C,
-                    int relu, T* __restrict__ dz, T* __restrict__ dres) {
-  extern __shared__ float bconst[];  // [3][C]: A | c1 | c0
+                    int pitch, int relu, T* __restrict__ dz, T* __restrict__ dres) {
+  extern __shared__ float bconst[];  // [5][C]: A | c1 | c0 | scale | shift
   float* sA = bconst;
   float* s1 = bconst + C;
   float* s0 = bconst + 2 * C;
+  float* ssc = bconst + 3 * C;
+  float* ssh = bconst + 4 * C;
+  const bool zmask = relu && yact == nullptr;
   const double invn = 1.0 / (double)count;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float is = invstd[c];
@@ -159,21 +244,27 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
     sA[c] = A;
     s1[c] = c1;
     s0[c] = -A * (float)(dbeta[c] * invn) - c1 * mean[c];
+    if (zmask) { ssc[c] = scale[c]; ssh[c] = shift[c]; }
   }
   __syncthreads();
   const int cv = C / 8;
   const int64_t total = count * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cv) * 8;
+    const int64_t e = (i / cv) * pitch + c0;   // element offset: row * pitch + channel
     float g[8], zz[8];
     Vec8<T> v, vz;
-    v.load(dy + i * 8);
-    vz.load(z + i * 8);
+    v.load(dy + e);
+    vz.load(z + e);
     v.unpack(g);
-    if (relu) {
+    vz.unpack(zz);
+    if (zmask) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = fmaf(zz[j], ssc[c0 + j], ssh[c0 + j]) > 0.f ? g[j] : 0.f;
+    } else if (relu) {
       float yy[8];
       Vec8<T> vy;
-      vy.load(yact + i * 8);
+      vy.load(yact + e);
       vy.unpack(yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = yy[j] > 0.f ? g[j] : 0.f;
@@ -181,9 +272,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
     if (dres != nullptr) {
       Vec8<T> o;
       o.pack(g);
-      o.store(dres + i * 8);
+      o.store(dres + e);
     }
-    vz.unpack(zz);
     const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(s1 + c0), b1 = *reinterpret_cast<const float4*>(s1 + c0 + 4);
     const float4 d0 = *reinterpret_cast<const float4*>(s0 + c0), d1 = *reinterpret_cast<const float4*>(s0 + c0 + 4);
@@ -195,7 +285,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
     for (int j = 0; j < 8; ++j) out[j] = fmaf(A[j], g[j], fmaf(B[j], zz[j], D[j]));
     Vec8<T> o;
     o.pack(out);
-    o.store(dz + i * 8);
+    o.store(dz + e);
   }
 }
 
@@ -277,7 +367,8 @@ static int check_bn_shape(int64_t count, int C, const char* who) {
 
 template <typename T, bool kBackward>
 static int launch_reduce(const void* a, const void* y, const void* z, const float* mean, const float* invstd,
-                         int64_t count, int C, int pitch, int relu, double* o0, double* o1, cudaStream_t s) {
+                         const float* scale, const float* shift, int64_t count, int C, int pitch, int relu,
+                         double* o0, double* o1, cudaStream_t s) {
   if (C % 8 != 0) {
     int grid = bw_grid(count * C, kBnThreads, 4);
     bn_reduce_small_kernel<T, kBackward><<<grid, kBnThreads, 0, s>>>((const T*)a, (const T*)y, (const T*)z, mean,
@@ -290,7 +381,7 @@ static int launch_reduce(const void* a, const void* y, const void* z, const floa
   size_t smem = (size_t)lanes * 2 * C * sizeof(float);
   int grid = bw_grid(count * cv, kBnThreads, 4);
   bn_reduce_kernel<T, kBackward><<<grid, kBnThreads, smem, s>>>((const T*)a, (const T*)y, (const T*)z, mean, invstd,
-                                                                count, C, pitch, relu, o0, o1);
+                                                                scale, shift, count, C, pitch, relu, o0, o1);
   WLSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -306,11 +397,11 @@ extern "C" int wlseg_bn_stats(const void* z, int64_t count, int32_t C, int32_t p
   if (count == 0) return 0;
   WLSEG_CHECK_ARG(z && sum && sqsum, "bn_stats: null pointer");
   if (dtype == WLSEG_BF16)
-    return launch_reduce<__nv_bfloat16, false>(z, nullptr, nullptr, nullptr, nullptr, count, C, pitch, 0, sum, sqsum,
-                                               (cudaStream_t)stream);
+    return launch_reduce<__nv_bfloat16, false>(z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, count, C, pitch,
+                                               0, sum, sqsum, (cudaStream_t)stream);
   if (dtype == WLSEG_F32)
-    return launch_reduce<float, false>(z, nullptr, nullptr, nullptr, nullptr, count, C, pitch, 0, sum, sqsum,
-                                       (cudaStream_t)stream);
+    return launch_reduce<float, false>(z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, count, C, pitch, 0, sum,
+                                       sqsum, (cudaStream_t)stream);
   WLSEG_CHECK_ARG(false, "bn_stats: bad dtype %d", dtype);
 }
 
@@ -323,6 +414,31 @@ extern "C" int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, count, C, gamma, beta, eps, decay,
                                                                         moving_mean, moving_var, scale, shift,
                                                                         saved_mean, saved_invstd);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wlseg_bn_finalize_apply(const double* sum, const double* sqsum, int64_t count, int32_t C,
+                                       const float* gamma, const float* beta, float eps, float decay,
+                                       float* moving_mean, float* moving_var, float* scale, float* shift,
+                                       float* saved_mean, float* saved_invstd, const void* z, const void* residual,
+                                       void* y, int32_t relu, int32_t dtype, wlseg_stream_t stream) {
+  WLSEG_CHECK_ARG(count > 0 && C > 0 && C % 8 == 0 && C <= 2048, "bn_finalize_apply: C (%d) must be a multiple of 8, <= 2048", C);
+  WLSEG_CHECK_ARG(sum && sqsum && gamma && beta && scale && shift && saved_mean && saved_invstd && z && y,
+                  "bn_finalize_apply: null pointer");
+  WLSEG_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize_apply: moving stats must come in pairs");
+  const int grid = bw_grid(count * (C / 8), 256, 8);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (dtype == WLSEG_BF16)
+    bn_finalize_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+        sum, sqsum, count, C, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, saved_mean, saved_invstd,
+        (const __nv_bfloat16*)z, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, relu);
+  else if (dtype == WLSEG_F32)
+    bn_finalize_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+        sum, sqsum, count, C, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, saved_mean, saved_invstd,
+        (const float*)z, (const float*)residual, (float*)y, relu);
+  else
+    WLSEG_CHECK_ARG(false, "bn_finalize_apply: bad dtype %d", dtype);
   WLSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -360,28 +476,35 @@ extern "C" int wlseg_bn_apply(const void* z, const float* scale, const float* sh
 }
 
 extern "C" int wlseg_bn_bwd_reduce(const void* dy, const void* y, const void* z, const float* mean,
-                                   const float* invstd, int64_t count, int32_t C, int32_t relu, int32_t dtype,
-                                   double* dgamma, double* dbeta, wlseg_stream_t stream) {
+                                   const float* invstd, const float* scale, const float* shift, int64_t count,
+                                   int32_t C, int32_t pitch, int32_t relu, int32_t dtype, double* dgamma,
+                                   double* dbeta, wlseg_stream_t stream) {
   if (int e = check_bn_shape(count, C, "bn_bwd_reduce")) return e;
   if (count == 0) return 0;
-  WLSEG_CHECK_ARG(dy && z && mean && invstd && dgamma && dbeta && (!relu || y), "bn_bwd_reduce: null pointer");
+  WLSEG_CHECK_ARG(dy && z && mean && invstd && dgamma && dbeta && (!relu || y || (scale && shift)),
+                  "bn_bwd_reduce: null pointer");
+  WLSEG_CHECK_ARG(pitch >= C && (C % 8 != 0 ? pitch == C : pitch % 8 == 0), "bn_bwd_reduce: bad pitch %d", pitch);
+  WLSEG_CHECK_ARG(C % 8 == 0 || !relu || y, "bn_bwd_reduce: the small-C path needs y for the ReLU mask");
   if (dtype == WLSEG_BF16)
-    return launch_reduce<__nv_bfloat16, true>(dy, y, z, mean, invstd, count, C, C, relu, dgamma, dbeta,
+    return launch_reduce<__nv_bfloat16, true>(dy, y, z, mean, invstd, scale, shift, count, C, pitch, relu, dgamma, dbeta,
                                               (cudaStream_t)stream);
   if (dtype == WLSEG_F32)
-    return launch_reduce<float, true>(dy, y, z, mean, invstd, count, C, C, relu, dgamma, dbeta, (cudaStream_t)stream);
+    return launch_reduce<float, true>(dy, y, z, mean, invstd, scale, shift, count, C, pitch, relu, dgamma, dbeta,
+                                      (cudaStream_t)stream);
   WLSEG_CHECK_ARG(false, "bn_bwd_reduce: bad dtype %d", dtype);
 }
 
 extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* mean, const float* invstd,
-                                  const float* gamma, const double* dgamma, const double* dbeta, int64_t count,
-                                  int32_t C, int32_t relu, int32_t dtype, void* dz, void* dres,
-                                  wlseg_stream_t stream) {
+                                  const float* gamma, const float* scale, const float* shift, const double* dgamma,
+                                  const double* dbeta, int64_t count, int32_t C, int32_t pitch, int32_t relu,
+                                  int32_t dtype, void* dz, void* dres, wlseg_stream_t stream) {
   if (int e = check_bn_shape(count, C, "bn_bwd_apply")) return e;
   if (count == 0) return 0;
-  WLSEG_CHECK_ARG(dy && z && mean && invstd && gamma && dgamma && dbeta && dz && (!relu || y),
+  WLSEG_CHECK_ARG(dy && z && mean && invstd && gamma && dgamma && dbeta && dz && (!relu || y || (scale && shift)),
                   "bn_bwd_apply: null pointer");
+  WLSEG_CHECK_ARG(pitch >= C && (C % 8 != 0 ? pitch == C : pitch % 8 == 0), "bn_bwd_apply: bad pitch %d", pitch);
   if (C % 8 != 0) {
+    WLSEG_CHECK_ARG(!relu || y, "bn_bwd_apply: the small-C path needs y for the ReLU mask");
     const int64_t total = count * C;
     int g = bw_grid(total, 256, 8);
     if (dtype == WLSEG_BF16)
@@ -398,14 +521,15 @@ extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, 
     return 0;
   }
   int grid = bw_grid(count * (C / 8), 256, 8);
+  const size_t smem = 5 * (size_t)C * sizeof(float);
   if (dtype == WLSEG_BF16)
-    bn_bwd_apply_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, invstd, gamma, dgamma, dbeta,
-        count, C, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
+    bn_bwd_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, invstd, gamma, scale, shift,
+        dgamma, dbeta, count, C, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
   else if (dtype == WLSEG_F32)
-    bn_bwd_apply_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z, mean,
-                                                                invstd, gamma, dgamma, dbeta, count, C, relu,
-                                                                (float*)dz, (float*)dres);
+    bn_bwd_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z,
+                                                                   mean, invstd, gamma, scale, shift, dgamma, dbeta, count,
+                                                                   C, pitch, relu, (float*)dz, (float*)dres);
   else
     WLSEG_CHECK_ARG(false, "bn_bwd_apply: bad dtype %d", dtype);
   WLSEG_LAUNCH_CHECK();

@@ -72,21 +72,37 @@ zero_insert_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int P,
 }
 
 // All dgrad filter banks of the network in ONE launch: blockIdx.y = layer (table row
-// {src_off, dst_off, K, R, S, C}), dst[c][R-1-r][S-1-s][k] = src[k][r][s][c].
+// {src_off, dst_off, K, R, S, C}), dst[c][R-1-r][S-1-s][k] = src[k][r][s][c]: per tap a K x C -> C x K
+// transpose, done in 64 x 64 tiles through shared memory (reads coalesced along c, writes along k).
 template <typename T>
 __global__ void __launch_bounds__(256)
 transpose_flip_batched_kernel(const T* __restrict__ src, T* __restrict__ dst, const int32_t* __restrict__ table) {
+  __shared__ T tile[64][66];
   const int32_t* e = table + 6 * blockIdx.y;
   const int64_t so = e[0], dofs = e[1];
   const int K = e[2], R = e[3], S = e[4], C = e[5];
-  const int64_t n = (int64_t)K * R * S * C;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % K);
-    int64_t t = i / K;
-    const int s2 = (int)(t % S); t /= S;
-    const int r2 = (int)(t % R);
-    const int c = (int)(t / R);
-    dst[dofs + i] = src[so + (((int64_t)k * R + (R - 1 - r2)) * S + (S - 1 - s2)) * C + c];
+  const int RS = R * S;
+  const int kt = (K + 63) / 64, ct = (C + 63) / 64;
+  const int units = RS * kt * ct;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int tap = u / (kt * ct);
+    const int rem = u - tap * (kt * ct);
+    const int k0 = (rem / ct) * 64, c0 = (rem % ct) * 64;
+    const int tap2 = RS - 1 - tap;  // (R-1-r)*S + (S-1-s)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      const int kk = idx >> 6, cc = idx & 63;
+      if (k0 + kk < K && c0 + cc < C) tile[kk][cc] = src[so + ((int64_t)(k0 + kk) * RS + tap) * C + c0 + cc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      const int cc = idx >> 6, kk = idx & 63;
+      if (k0 + kk < K && c0 + cc < C) dst[dofs + ((int64_t)(c0 + cc) * RS + tap2) * K + k0 + kk] = tile[kk][cc];
+    }
+    __syncthreads();
   }
 }
 
@@ -119,7 +135,7 @@ extern "C" int wlseg_weights_transpose_flip_batched(const void* src_arena, void*
   if (n_layers == 0) return 0;
   WLSEG_CHECK_ARG(src_arena && dst_arena && table, "transpose_flip_batched: null pointer");
   WLSEG_CHECK_ARG(n_layers <= 65535, "transpose_flip_batched: too many layers");
-  dim3 grid(32, n_layers);
+  dim3 grid(48, n_layers);
   if (dtype == WLSEG_BF16)
     transpose_flip_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_arena,
                                                                           (__nv_bfloat16*)dst_arena, table);

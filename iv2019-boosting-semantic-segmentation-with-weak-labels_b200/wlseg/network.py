@@ -423,6 +423,13 @@ class TrainNetwork(Network):
     self.grad_ready = None  # callback(lo): every conv-kernel gradient at arena offset >= lo is final
     self.keep = False       # tests: keep per-layer gradient tensors on the tape
     self._flipped = None    # {scope: dgrad filter bank view}, refreshed at the start of backward()
+    # one launch for bn_finalize + bn_apply: measured 0.15 ms/step SLOWER than two launches inside the
+    # step graph (every CTA redoes the fp64 finalisation), so off by default; kept for eager use
+    self.fused_bn_finalize = False
+    # per-slice working set of the two BN backward passes.  Measured on B200 (profiles/): 64 MB slices
+    # (second pass from L2) LOSE to whole-tensor passes - 512-byte row segments at a 4 KB pitch halve
+    # the HBM efficiency of the first pass - so slicing is off by default.
+    self.bn_bwd_l2_bytes = 1 << 40
     self._order = {s.scope: i for i, s in enumerate(params.specs)}
 
   def _mark_done(self, scope, n_elems):
@@ -461,11 +468,16 @@ class TrainNetwork(Network):
                    bn_sum=s1, bn_sqsum=s2)
     scale, shift = ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K)
     mean, invstd = ws.view(ws.bn, 2, off, K), ws.view(ws.bn, 3, off, K)
-    ops.bn_finalize(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
-                    self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd)
     a = torch.empty_like(z)
     do_relu = spec.relu if relu is None else relu
-    ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu)
+    if self.fused_bn_finalize and K % 8 == 0 and K <= 2048:
+      ops.bn_finalize_apply(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
+                            self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd,
+                            z, residual, a, do_relu)
+    else:
+      ops.bn_finalize(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
+                      self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd)
+      ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu)
     rec = _Rec()
     rec.scope, rec.spec, rec.x, rec.w, rec.z, rec.a = scope, spec, x, w, z, a
     rec.relu, rec.has_res, rec.geom, rec.nch, rec.kind = do_relu, residual is not None, (pad, out_hw, stride, dilation), K, kind
@@ -491,10 +503,27 @@ class TrainNetwork(Network):
     count = N * out_hw[0] * out_hw[1]
     mean, invstd = ws.view(ws.bn, 2, off, K), ws.view(ws.bn, 3, off, K)
     dgamma, dbeta = ws.view(ws.stat, 2, off, K), ws.view(ws.stat, 3, off, K)
-    ops.bn_bwd_reduce(da, rec.a, rec.z, mean, invstd, count, K, rec.relu, dgamma, dbeta)
+    scale, shift = ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K)
+    gamma = self.p.gamma(scope, K)
     dz = torch.empty_like(rec.z)
     dres = torch.empty_like(rec.z) if rec.has_res else None
-    ops.bn_bwd_apply(da, rec.a, rec.z, mean, invstd, self.p.gamma(scope, K), dgamma, dbeta, count, K, rec.relu, dz, dres)
+    # the ReLU mask of a layer without a residual input is recomputed from z (y is not read at all)
+    y = rec.a if (rec.relu and (rec.has_res or K % 8 != 0)) else None
+    # channel slices sized so that one slice of dy / y / z stays L2 resident between the two passes
+    esz = rec.z.element_size()
+    Kg = K
+    if K % 8 == 0 and da.is_contiguous() and rec.z.is_contiguous():
+      budget = self.bn_bwd_l2_bytes // ((3 if y is not None else 2) * esz * max(count, 1))
+      if budget < K:
+        Kg = max(64, budget // 64 * 64)
+    for c0 in range(0, K, Kg):
+      kk = min(Kg, K - c0)
+      sl = slice(c0, c0 + kk)
+      ops.bn_bwd_reduce(da[..., sl], None if y is None else y[..., sl], rec.z[..., sl], mean[sl], invstd[sl], count, kk,
+                        rec.relu, dgamma[sl], dbeta[sl], scale=scale[sl], shift=shift[sl], pitch=K)
+      ops.bn_bwd_apply(da[..., sl], None if y is None else y[..., sl], rec.z[..., sl], mean[sl], invstd[sl], gamma[sl],
+                       dgamma[sl], dbeta[sl], count, kk, rec.relu, dz[..., sl], None if dres is None else dres[..., sl],
+                       scale=scale[sl], shift=shift[sl], pitch=K)
     wsrc = rec.w
     if dz.dtype != self.dtype or (self.dtype == torch.bfloat16 and K % 8 != 0):
       # logits layers (fp32 z, 14/7/3 channels) feeding bf16 tensor-core kernels: bf16 copy of dz with

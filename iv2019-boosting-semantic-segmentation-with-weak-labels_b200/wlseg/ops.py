@@ -52,10 +52,13 @@ _SIGNATURES = {
     'wlseg_bn_stats': (ctypes.c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     'wlseg_bn_finalize': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _vp]),
+    'wlseg_bn_finalize_apply': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, _c_int, _c_int, _vp]),
     'wlseg_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp]),
-    'wlseg_bn_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
-    'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int,
-                                          _vp, _vp, _vp]),
+    'wlseg_bn_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _c_int,
+                                           _vp, _vp, _vp]),
+    'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int,
+                                          _c_int, _c_int, _vp, _vp, _vp]),
     'wlseg_maxpool_same_fwd': (ctypes.c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                               _vp]),
     'wlseg_maxpool_same_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -247,6 +250,16 @@ def bn_finalize(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mean, mov
   _count()
 
 
+def bn_finalize_apply(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, saved_mean,
+                      saved_invstd, z, residual, y, relu):
+  _check(lib().wlseg_bn_finalize_apply(_ptr(sum_), _ptr(sqsum), count, C, _ptr(gamma), _ptr(beta), eps, decay,
+                                       _ptr(moving_mean), _ptr(moving_var), _ptr(scale), _ptr(shift), _ptr(saved_mean),
+                                       _ptr(saved_invstd), _ptr(z), _ptr(residual), _ptr(y), int(relu),
+                                       dtype_code(z.dtype), _stream()), 'wlseg_bn_finalize_apply')
+  _count()
+  return y
+
+
 def bn_apply(z, scale, shift, residual, y, count, C, relu):
   _check(lib().wlseg_bn_apply(_ptr(z), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(y), count, C, int(relu),
                               dtype_code(z.dtype), _stream()), 'wlseg_bn_apply')
@@ -254,16 +267,20 @@ def bn_apply(z, scale, shift, residual, y, count, C, relu):
   return y
 
 
-def bn_bwd_reduce(dy, y, z, mean, invstd, count, C, relu, dgamma, dbeta):
-  _check(lib().wlseg_bn_bwd_reduce(_ptr(dy), _ptr(y), _ptr(z), _ptr(mean), _ptr(invstd), count, C, int(relu),
-                                   dtype_code(z.dtype), _ptr(dgamma), _ptr(dbeta), _stream()), 'wlseg_bn_bwd_reduce')
+def bn_bwd_reduce(dy, y, z, mean, invstd, count, C, relu, dgamma, dbeta, scale=None, shift=None, pitch=None):
+  """y=None on a ReLU layer: mask from sign(fmaf(z, scale, shift)).  Channel slices: pass views and pitch."""
+  _check(lib().wlseg_bn_bwd_reduce(_ptr(dy), _ptr(y), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
+                                   count, C, C if pitch is None else pitch, int(relu), dtype_code(z.dtype),
+                                   _ptr(dgamma), _ptr(dbeta), _stream()), 'wlseg_bn_bwd_reduce')
   _count()
 
 
-def bn_bwd_apply(dy, y, z, mean, invstd, gamma, dgamma, dbeta, count, C, relu, dz, dres=None):
-  _check(lib().wlseg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dgamma),
-                                  _ptr(dbeta), count, C, int(relu), dtype_code(z.dtype), _ptr(dz), _ptr(dres),
-                                  _stream()), 'wlseg_bn_bwd_apply')
+def bn_bwd_apply(dy, y, z, mean, invstd, gamma, dgamma, dbeta, count, C, relu, dz, dres=None, scale=None, shift=None,
+                 pitch=None):
+  _check(lib().wlseg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(scale),
+                                  _ptr(shift), _ptr(dgamma), _ptr(dbeta), count, C, C if pitch is None else pitch,
+                                  int(relu), dtype_code(z.dtype), _ptr(dz), _ptr(dres), _stream()),
+         'wlseg_bn_bwd_apply')
   _count()
   return dz
 

@@ -79,6 +79,15 @@ def test_batch_norm_train_fwd_bwd(cuda, C, dtype):
   y = torch.empty_like(zd)
   ops.bn_apply(zd, scale, shift, resd, y, count, C, True)
   torch.cuda.synchronize()
+  if C % 8 == 0:
+    # the fused finalize + apply launch of the training path: identical results, bit for bit
+    mm2, mv2 = mm.to(dev), mv.to(dev)
+    sc2, sh2, me2, in2 = (torch.empty(C, device=dev) for _ in range(4))
+    y2 = torch.empty_like(zd)
+    ops.bn_finalize_apply(s1, s2, count, C, gd, bd, 1e-5, 0.9, mm2, mv2, sc2, sh2, me2, in2, zd, resd, y2, True)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y) and torch.equal(sc2, scale) and torch.equal(sh2, shift)
+    assert torch.equal(me2, smean) and torch.equal(in2, sinv) and torch.equal(mm2, mmd) and torch.equal(mv2, mvd)
   assert torch.allclose(smean.cpu(), mean.detach(), rtol=1e-5, atol=1e-6)
   assert torch.allclose(sinv.cpu(), torch.rsqrt(var.detach() + 1e-5), rtol=1e-5)
   assert torch.allclose(mmd.cpu(), new_mm, rtol=1e-5, atol=1e-6)
@@ -99,6 +108,29 @@ def test_batch_norm_train_fwd_bwd(cuda, C, dtype):
   assert torch.allclose(dbt.float().cpu(), br.grad, rtol=1e-4, atol=1e-4)
   assert float((dz.float().cpu() - zr.grad).abs().max()) <= tol * float(zr.grad.abs().max()) + 1e-6
   assert float((dres.float().cpu() - rr.grad).abs().max()) <= tol * float(rr.grad.abs().max()) + 1e-6
+
+  if C % 16 == 0:
+    # training path: ReLU layer WITHOUT residual, mask recomputed from z (y not read), processed in
+    # two channel slices through `pitch` - must equal the one-shot y-masked result bit for bit
+    y2 = torch.empty_like(zd)
+    ops.bn_apply(zd, scale, shift, None, y2, count, C, True)
+    ref_dg = torch.zeros(C, dtype=torch.float64, device=dev)
+    ref_db = torch.zeros(C, dtype=torch.float64, device=dev)
+    ops.bn_bwd_reduce(dyd, y2, zd, smean, sinv, count, C, True, ref_dg, ref_db)
+    ref_dz = torch.empty_like(zd)
+    ops.bn_bwd_apply(dyd, y2, zd, smean, sinv, gd, ref_dg, ref_db, count, C, True, ref_dz)
+    dg2 = torch.zeros(C, dtype=torch.float64, device=dev)
+    db2 = torch.zeros(C, dtype=torch.float64, device=dev)
+    dz2 = torch.full_like(zd, float('nan'))
+    h = C // 2
+    for sl in (slice(0, h), slice(h, C)):
+      ops.bn_bwd_reduce(dyd[..., sl], None, zd[..., sl], smean[sl], sinv[sl], count, h, True, dg2[sl], db2[sl],
+                        scale=scale[sl], shift=shift[sl], pitch=C)
+      ops.bn_bwd_apply(dyd[..., sl], None, zd[..., sl], smean[sl], sinv[sl], gd[sl], dg2[sl], db2[sl], count, h, True,
+                       dz2[..., sl], scale=scale[sl], shift=shift[sl], pitch=C)
+    torch.cuda.synchronize()
+    assert torch.allclose(dg2, ref_dg, rtol=1e-9, atol=1e-9) and torch.allclose(db2, ref_db, rtol=1e-9, atol=1e-9)
+    assert float((dz2.float() - ref_dz.float()).abs().max()) <= 1e-2 * float(ref_dz.float().abs().max())
 
 
 @pytest.mark.parametrize('nesterov', [False, True])

@@ -248,3 +248,39 @@ def test_train_step_bf16_layerwise(cuda, dataset):
     n_checked += 1
   print(f'{dataset}: {n_checked} layers checked in situ; worst max-rel errors {worst}')
   assert n_checked == len(params.specs) - 2
+
+
+def test_trainer_graph_replay_equals_eager(cuda):
+  """The product path replays the whole step as one CUDA graph: starting from the same weights, five
+  optimizer steps (2 eager + capture + replays) must give the losses and weights of five eagerly
+  launched steps (fp64/fp32 atomics make the two runs differ in the last bits only)."""
+  from wlseg import hierarchy, network, problem_defs, trainer as wtrainer
+
+  class S:
+    momentum, use_nesterov, optimizer, regularization_weight = 0.9, False, 'SGDM', 0.00017
+    batch_norm_decay, distribute, ema_decay = 0.9, False, 0.9
+
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  g = torch.Generator().manual_seed(5)
+  batches = []
+  for _ in range(2):
+    img = (torch.rand(2, 64, 96, 3, generator=g) * 2 - 1).to(cuda)
+    lab = {'prolabels_per_pixel': torch.randint(0, 20, (2, 64, 96), generator=g, dtype=torch.int32).to(cuda)}
+    batches.append((img, lab))
+  out = {}
+  for mode in (False, True):
+    params = network.Params(hier, cuda)
+    params.init_random(3)
+    tr = wtrainer.Trainer(params, S, use_graph=mode)
+    losses = []
+    for i in range(5):
+      img, lab = batches[i % 2]
+      losses.append(tr.step({'proimages': img}, lab, 0.01 if i < 3 else 0.005).cpu().clone())
+    torch.cuda.synchronize()
+    assert (len(tr._graphs) == 1) == mode
+    out[mode] = (torch.stack(losses), params.master.cpu().clone(), params.moving.cpu().clone(),
+                 tr.ws.ema_shadow.cpu().clone())
+  for a, b, name in zip(out[False], out[True], ('losses', 'weights', 'moving statistics', 'ema shadows')):
+    assert torch.isfinite(b).all(), name
+    err = float((a - b).abs().max() / a.abs().max())
+    assert err <= 2e-3, f'{name}: graph replay differs from eager by {err:.2e}'
