@@ -60,6 +60,24 @@ def load_peaks():
   return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
 
 
+def load_traffic(workload, kernel_prefix):
+  """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the launches of
+  one step) of the dominant kernel, from the committed ncu capture of this same command
+  (profiles/rNN_traffic.json, written by tools/make_profiles.py).  None when no capture is committed."""
+  pdir = os.path.join(ROOT, 'profiles')
+  if not os.path.isdir(pdir):
+    return None, None
+  files = sorted(f for f in os.listdir(pdir) if f.endswith('_traffic.json'))
+  if not files:
+    return None, None
+  with open(os.path.join(pdir, files[-1])) as fp:
+    t = json.load(fp).get(workload, {})
+  for k, v in t.items():
+    if k.startswith(kernel_prefix):
+      return v['dram_bytes_per_launch'], files[-1]
+  return None, None
+
+
 class ClockSampler:
   """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
   Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
@@ -180,14 +198,18 @@ def run_reference(args):
     return
   h = args.height or EVAL_H
   w = args.width or EVAL_W
-  steps = max(1, min(args.steps, 3))
-  warm = min(args.warmup, 1)
+  # bounded sample of the same workload: 1 image per step (a 4-image batch takes ~12 s on 16 cores),
+  # at most 40 timed steps so that the whole run ends within a few minutes
+  steps = max(1, min(args.steps, 40))
+  warm = max(0, min(args.warmup, 2))
   r = cpu_reference_eval(args.dataset, h, w, steps, warm, images_per_step=1)
   line = {'impl': 'reference', 'metric': 'eval_mpix_per_s', 'value': r['value'], 'unit': 'Mpix/s',
           'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': r['ms_per_step'],
           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-          'config': {'workload': f'{args.dataset} eval: ResNet-50 OS8 forward + hierarchical heads + argmax + '
-                                 f'confusion matrix, {h}x{w}; reference arm = oracle port on host CPU, 1 image/step'},
+          'config': {'workload': f'{args.dataset} eval (BASELINE configs[1]): ResNet-50 OS8 forward + hierarchical '
+                                 f'heads + argmax + confusion matrix, {h}x{w}, random init',
+                     'sample': 'reference arm = the oracle port of the TF-1.12 graph (TensorFlow cannot be installed) on '
+                               'the host cores, one image per step instead of the batch of 4'},
           'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
           'e2e': {'value': r['value'], 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
           'gpu_launches': 0}
@@ -273,9 +295,14 @@ def run_wlseg_eval(args):
   if dom and dom['ms'] > 0:
     ach = dom['flops'] / (dom['ms'] / 1e3) / 1e12
     # timed inside a long step under the power cap -> sustained peak
+    traffic, tsrc = load_traffic('eval', 'conv_igemm_kernel<256')
     roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel<256, bf16>', 'achieved': ach,
                 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'],
-                'traffic': None, 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)',
+                'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu, mean over the launches of a step)',
+                'traffic_source': None if tsrc is None else 'profiles/' + tsrc,
+                'algorithmic_bytes_per_launch': dom['bytes'] / dom['launches'],
+                'flops_per_launch': dom['flops'] / dom['launches'],
+                'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)',
                 'launches': dom['launches'], 'share_of_step': dom['ms'] / ms}
   if args.detail and rank == 0:
     table = {k: {'launches': v['launches'], 'ms_per_step': v['ms'] / args.steps,

@@ -11,6 +11,8 @@
 // supports it in shared memory (read once from L2/HBM), and every thread interpolates its
 // pixels from the patch.  Algorithmic HBM bytes per output pixel: 4 (decisions) + 4*channels
 // of each requested probability map + 4*(C1+Cv+Ch)/64 (low-res logits).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace wlseg {
@@ -134,6 +136,191 @@ head_fwd_kernel(const __grid_constant__ wlseg_hierarchy hier, const HeadArgs a) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Column-walking variant (the product path for the known head widths 14/7/3 and 53/12/5):
+// thread = one output column, walking kColsTY rows.  The x-interpolated low-res rows `top` / `bot`
+// live in registers and are refreshed only when the source row changes (every ~8 output rows at x8),
+// so a pixel costs one lerp + one compare per channel instead of four shared-memory loads and three
+// lerps: the eval launch is bound by its 4 B/pixel of decisions + the fp32 pipe, not by shared memory.
+// Probability / logit maps leave through a per-warp shared-memory transpose: 32 pixels x C floats
+// are one contiguous span of the NHWC output, written with fully coalesced stores.
+constexpr int kColsTX = 128;
+constexpr int kColsTY = 32;
+
+// arg-max over v[LO, HI) as a balanced tournament (depth log2 n instead of a serial chain of n - 1
+// dependent compares).  The left operand always holds the lower indices and loses only to a
+// STRICTLY larger value, so the first maximum wins exactly as in the serial scan / tf.argmax.
+template <int LO, int HI, int CT>
+__device__ __forceinline__ void tree_argmax(const float (&v)[CT], float& m, int& d) {
+  if constexpr (HI - LO == 1) {
+    m = v[LO];
+    d = LO;
+  } else {
+    constexpr int MID = LO + (HI - LO + 1) / 2;
+    float ml, mr;
+    int dl, dr;
+    tree_argmax<LO, MID, CT>(v, ml, dl);
+    tree_argmax<MID, HI, CT>(v, mr, dr);
+    const bool right = mr > ml;
+    m = right ? mr : ml;
+    d = right ? dr : dl;
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ dst, float* __restrict__ stage, const float (&v)[C],
+                                                int lane, int n_valid) {
+  // stage[lane][c] (row pitch C + 1: conflict-free), then linear coalesced copy of n_valid * C floats
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < C; ++c) stage[lane * (C + 1) + c] = v[c];
+  __syncwarp();
+  const int total = n_valid * C;
+  for (int i = lane; i < total; i += 32) dst[i] = stage[(i / C) * (C + 1) + (i % C)];
+}
+
+template <int C1, int CV, int CH>
+__global__ void __launch_bounds__(kColsTX)
+head_fwd_cols_kernel(const __grid_constant__ wlseg_hierarchy hier, const HeadArgs a) {
+  constexpr int CT = C1 + CV + CH;
+  constexpr int CMAX = C1 > CT ? C1 : CT;   // staging row width (the full-logits map is the widest)
+  extern __shared__ float patch[];  // [ph][pw][CT] then per-warp staging [4][32][CMAX + 1]
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * kColsTY, x0 = blockIdx.x * kColsTX;
+  const int yl0 = (int)floorf(y0 * a.sy), xl0 = (int)floorf(x0 * a.sx);
+  const int cells = a.ph * a.pw;
+  const float* src = a.logits + (int64_t)n * a.h * a.w * a.cp;
+  for (int i = threadIdx.x; i < cells * CT; i += kColsTX) {
+    const int c = i % CT;
+    const int cell = i / CT;
+    const int px = cell % a.pw, py = cell / a.pw;
+    const int yy = min(yl0 + py, a.h - 1), xx = min(xl0 + px, a.w - 1);
+    patch[i] = __ldg(src + ((int64_t)yy * a.w + xx) * a.cp + c);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* stage = patch + cells * CT + warp * 32 * (CMAX + 1);
+  const int x = x0 + threadIdx.x;
+  const bool live = x < a.W;
+  const int xc = live ? x : a.W - 1;
+  const float fx = xc * a.sx;
+  const int xl = (int)floorf(fx);
+  const int xh = min(xl + 1, a.w - 1);
+  const float lx = fx - (float)xl;
+  const int o0 = (xl - xl0) * CT, o1 = (xh - xl0) * CT;
+  const int warp_x0 = x0 + warp * 32;
+  const int n_valid = min(32, a.W - warp_x0);   // <= 0: the whole warp is outside the image
+  const bool want_maps = a.l1_probs || a.l2v_probs || a.l2h_probs || a.full_logits;
+
+  float top[CT], bot[CT];
+  int trow = -1, brow = -1;
+  auto load_row = [&](int r, float (&dst)[CT]) {
+    const float* base = patch + (r - yl0) * a.pw * CT;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const float tl = base[o0 + c], tr = base[o1 + c];
+      dst[c] = tl + (tr - tl) * lx;   // TF ResizeBilinear: top = tl + (tr - tl) * x_lerp
+    }
+  };
+
+  for (int ry = 0; ry < kColsTY; ++ry) {
+    const int y = y0 + ry;
+    if (y >= a.H) break;
+    const float fy = y * a.sy;
+    const int yl = (int)floorf(fy);
+    const int yh = min(yl + 1, a.h - 1);
+    const float ly = fy - (float)yl;
+    if (yl != trow) {
+      if (yl == brow) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) top[c] = bot[c];
+      } else {
+        load_row(yl, top);
+      }
+      trow = yl;
+    }
+    if (yh != brow) {
+      load_row(yh, bot);
+      brow = yh;
+    }
+    float v[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) v[c] = top[c] + (bot[c] - top[c]) * ly;
+    // three arg-maxima, strict '>' : the first maximum wins, as tf.argmax
+    int d1, dv, dh;
+    float m1, mv, mh;
+    tree_argmax<0, C1, CT>(v, m1, d1);
+    tree_argmax<C1, C1 + CV, CT>(v, mv, dv);
+    tree_argmax<C1 + CV, CT, CT>(v, mh, dh);
+    dv -= C1;
+    dh -= C1 + CV;
+    int dec;
+    if (d1 == hier.cid_l1_vehicle) dec = hier.veh_to_common[dv];
+    else if (d1 == hier.cid_l1_human) dec = hier.hum_to_common[dh];
+    else dec = hier.l1_to_common[d1];
+    const int64_t pix = ((int64_t)n * a.H + y) * a.W + x;
+    if (live) {
+      if (a.decisions) a.decisions[pix] = dec;
+      if (a.l1_dec) a.l1_dec[pix] = d1;
+      if (a.l2v_dec) a.l2v_dec[pix] = dv;
+      if (a.l2h_dec) a.l2h_dec[pix] = dh;
+    }
+    if (want_maps && n_valid > 0) {
+      const int64_t wpix = ((int64_t)n * a.H + y) * a.W + warp_x0;   // first pixel of this warp's span
+      if (a.full_logits) warp_store_rows<CT>(a.full_logits + wpix * CT, stage, v, lane, n_valid);
+      if (a.l1_probs) {
+        float e[C1];
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < C1; ++c) { e[c] = expf(v[c] - m1); s += e[c]; }
+        const float inv = 1.0f / s;
+#pragma unroll
+        for (int c = 0; c < C1; ++c) e[c] *= inv;
+        warp_store_rows<C1>(a.l1_probs + wpix * C1, stage, e, lane, n_valid);
+      }
+      if (a.l2v_probs) {
+        float e[CV];
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CV; ++c) { e[c] = expf(v[C1 + c] - mv); s += e[c]; }
+        const float inv = 1.0f / s;
+#pragma unroll
+        for (int c = 0; c < CV; ++c) e[c] *= inv;
+        warp_store_rows<CV>(a.l2v_probs + wpix * CV, stage, e, lane, n_valid);
+      }
+      if (a.l2h_probs) {
+        float e[CH];
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { e[c] = expf(v[C1 + CV + c] - mh); s += e[c]; }
+        const float inv = 1.0f / s;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) e[c] *= inv;
+        warp_store_rows<CH>(a.l2h_probs + wpix * CH, stage, e, lane, n_valid);
+      }
+    }
+  }
+}
+
+template <int C1, int CV, int CH>
+static int launch_head_cols(const wlseg_hierarchy* hier, HeadArgs& a, cudaStream_t stream) {
+  constexpr int CT = C1 + CV + CH;
+  a.ph = (int)fminf((float)a.h, floorf(kColsTY * a.sy) + 3.f);
+  a.pw = (int)fminf((float)a.w, floorf(kColsTX * a.sx) + 3.f);
+  const size_t smem = ((size_t)a.ph * a.pw * CT + (size_t)(kColsTX / 32) * 32 * (CT + 1)) * sizeof(float);
+  if (smem > 200 * 1024) return 1;  // not covered: the caller falls back to the generic kernel
+  static bool configured = false;
+  if (!configured) {
+    WLSEG_CUDA(cudaFuncSetAttribute(head_fwd_cols_kernel<C1, CV, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(a.W, kColsTX), (unsigned)ceil_div(a.H, kColsTY), (unsigned)a.N);
+  head_fwd_cols_kernel<C1, CV, CH><<<grid, kColsTX, smem, stream>>>(*hier, a);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 int check_hierarchy(const wlseg_hierarchy* hier) {
   WLSEG_CHECK_ARG(hier != nullptr, "hierarchy is NULL");
   WLSEG_CHECK_ARG(hier->C1 > 0 && hier->C1 <= 64 && hier->Cv > 0 && hier->Cv <= 16 && hier->Ch > 0 && hier->Ch <= 8,
@@ -169,10 +356,19 @@ extern "C" int wlseg_head_fwd(const wlseg_hierarchy* hier, const float* logits, 
   a.cp = logits_pitch;
   a.sy = resize_scale(h, H);
   a.sx = resize_scale(w, W);
-  a.ph = (int)fminf((float)h, floorf(kHeadTY * a.sy) + 3.f);
-  a.pw = (int)fminf((float)w, floorf(kHeadTX * a.sx) + 3.f);
   a.decisions = decisions; a.l1_dec = l1_decisions; a.l2v_dec = l2v_decisions; a.l2h_dec = l2h_decisions;
   a.l1_probs = l1_probs; a.l2v_probs = l2v_probs; a.l2h_probs = l2h_probs; a.full_logits = fullres_logits;
+  // the column-walking kernel is instantiated for the two label hierarchies the reference ships
+  // (cityscapes 14/7/3, vistas 53/12/5) when the upsampling factor is >= 2; anything else takes the
+  // generic kernel below
+  if (a.sy <= 0.5f && a.sx <= 0.5f && getenv("WLSEG_HEAD_GENERIC") == nullptr) {
+    int rc = 1;
+    if (hier->C1 == 14 && hier->Cv == 7 && hier->Ch == 3) rc = launch_head_cols<14, 7, 3>(hier, a, (cudaStream_t)stream);
+    else if (hier->C1 == 53 && hier->Cv == 12 && hier->Ch == 5) rc = launch_head_cols<53, 12, 5>(hier, a, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
+  a.ph = (int)fminf((float)h, floorf(kHeadTY * a.sy) + 3.f);
+  a.pw = (int)fminf((float)w, floorf(kHeadTX * a.sx) + 3.f);
   const int Ct = hier->C1 + hier->Cv + hier->Ch;
   size_t smem = (size_t)a.ph * a.pw * Ct * sizeof(float);
   WLSEG_CHECK_ARG(smem <= 200 * 1024, "head_fwd: low-res patch (%zu B) does not fit shared memory; "

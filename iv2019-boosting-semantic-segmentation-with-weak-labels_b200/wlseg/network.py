@@ -232,6 +232,24 @@ class Network:
     self.profile = None  # bench.py: list receiving one CUDA-event record per convolution launch
 
   # ---- helpers ---------------------------------------------------------------------------------
+  class _Timed:
+    """bench.py: CUDA-event pair around one launch of a bandwidth kernel (algorithmic bytes given)."""
+
+    def __init__(self, net, cls, nbytes):
+      self.net, self.rec = net, None
+      if getattr(net, 'profile', None) is not None:
+        self.rec = {'cls': cls, 'flops': 0.0, 'bytes': float(nbytes), 'sig': (cls,),
+                    'e0': torch.cuda.Event(enable_timing=True), 'e1': torch.cuda.Event(enable_timing=True)}
+
+    def __enter__(self):
+      if self.rec is not None:
+        self.rec['e0'].record()
+
+    def __exit__(self, *exc):
+      if self.rec is not None:
+        self.rec['e1'].record()
+        self.net.profile.append(self.rec)
+
   def _weights(self, scope):
     return self.p.wbf(scope) if self.dtype == torch.bfloat16 else self.p.w32(scope)
 
@@ -366,9 +384,13 @@ class Network:
     full = None
     if any(k in want for k in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits', 'logits')):
       full = torch.empty((N, H, W, C1 + Cv + Ch), dtype=torch.float32, device=dev)
-    ops.head_fwd(self.hstruct, logits, H, W, res['decisions'], res['l1_decisions'], res['l2_vehicle_decisions'],
-                 res['l2_human_decisions'], res['l1_probabilities'], res['l2_vehicle_probabilities'],
-                 res['l2_human_probabilities'], full)
+    # algorithmic HBM bytes: every requested full-resolution map written once + the low-res logits
+    out_bytes = sum(v.numel() * v.element_size() for v in res.values() if v is not None)
+    out_bytes += 0 if full is None else full.numel() * 4
+    with self._Timed(self, 'head_fwd', out_bytes + N * logits.shape[1] * logits.shape[2] * (C1 + Cv + Ch) * 4):
+      ops.head_fwd(self.hstruct, logits, H, W, res['decisions'], res['l1_decisions'], res['l2_vehicle_decisions'],
+                   res['l2_human_decisions'], res['l1_probabilities'], res['l2_vehicle_probabilities'],
+                   res['l2_human_probabilities'], full)
     out = {k: v for k, v in res.items() if v is not None}
     if full is not None:
       out['l1_logits'] = full[..., :C1]
@@ -739,8 +761,12 @@ class TrainNetwork(Network):
     ws.loss_sums.zero_()
     ws.loss_counts.zero_()
     dlogits = torch.zeros_like(logits)
-    ops.loss_fwd_bwd(self.hstruct, logits, H, W, labels.get('prolabels_per_pixel'),
-                     labels.get('prolabels_per_bbox'), labels.get('prolabels_per_image'), ws.loss_sums,
-                     ws.loss_counts, dlogits)
+    # algorithmic HBM bytes: the labels once + low-res logits read + low-res gradient written
+    nbytes = sum(v.numel() * v.element_size() for v in labels.values() if v is not None)
+    nbytes += 2 * logits.shape[0] * logits.shape[1] * logits.shape[2] * sum(self.hier.head_widths) * 4
+    with self._Timed(self, 'loss_fwd_bwd', nbytes):
+      ops.loss_fwd_bwd(self.hstruct, logits, H, W, labels.get('prolabels_per_pixel'),
+                       labels.get('prolabels_per_bbox'), labels.get('prolabels_per_image'), ws.loss_sums,
+                       ws.loss_counts, dlogits)
     ops.loss_finalize(self.hstruct, ws.loss_sums, ws.loss_counts, l2_coef, grad_scale, dlogits, ws.losses)
     return ws.losses, dlogits

@@ -101,8 +101,12 @@ def run(args, cpu_train_sample=None):
   if tc:
     name, dom = max(tc.items(), key=lambda kv: kv[1]['ms'])
     ach = dom['flops'] / (dom['ms'] / 1e3) / 1e12
+    from bench import load_traffic
+    traffic, tsrc = load_traffic('train', 'conv_igemm_kernel<256' if name == 'igemm_bn256' else 'conv_wgrad_kernel<256')
     roofline = {'bound': 'tensor', 'kernel': name, 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
-                'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': traffic,
+                'traffic_source': None if tsrc is None else 'profiles/' + tsrc,
+                'algorithmic_bytes_per_launch': dom['bytes'] / dom['launches'],
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)', 'launches': dom['launches'],
                 'share_of_step': dom['ms'] / prof_ms, 'timed_over': f'{prof_steps} eagerly launched steps after the timed region'}
   if args.detail and rank == 0:

@@ -267,8 +267,8 @@ def test_trainer_graph_replay_equals_eager(cuda):
     img = (torch.rand(2, 64, 96, 3, generator=g) * 2 - 1).to(cuda)
     lab = {'prolabels_per_pixel': torch.randint(0, 20, (2, 64, 96), generator=g, dtype=torch.int32).to(cuda)}
     batches.append((img, lab))
-  out = {}
-  for mode in (False, True):
+  out = []
+  for mode in (False, False, True):
     params = network.Params(hier, cuda)
     params.init_random(3)
     tr = wtrainer.Trainer(params, S, use_graph=mode)
@@ -278,9 +278,15 @@ def test_trainer_graph_replay_equals_eager(cuda):
       losses.append(tr.step({'proimages': img}, lab, 0.01 if i < 3 else 0.005).cpu().clone())
     torch.cuda.synchronize()
     assert (len(tr._graphs) == 1) == mode
-    out[mode] = (torch.stack(losses), params.master.cpu().clone(), params.moving.cpu().clone(),
-                 tr.ws.ema_shadow.cpu().clone())
-  for a, b, name in zip(out[False], out[True], ('losses', 'weights', 'moving statistics', 'ema shadows')):
-    assert torch.isfinite(b).all(), name
-    err = float((a - b).abs().max() / a.abs().max())
-    assert err <= 2e-3, f'{name}: graph replay differs from eager by {err:.2e}'
+    out.append((torch.stack(losses), params.master.cpu().clone(), params.moving.cpu().clone(),
+                tr.ws.ema_shadow.cpu().clone()))
+  # Not bit-exact: fp32 / fp64 atomics (BN statistics, split-K wgrad, loss scatter) commit in a different
+  # order from run to run and a train-mode BN ResNet at random init amplifies that (see the file header).
+  # The yardstick is therefore the difference between two EAGER runs of the same five steps.
+  for e1, e2, gr, name in zip(out[0], out[1], out[2], ('losses', 'weights', 'moving statistics', 'ema shadows')):
+    assert torch.isfinite(gr).all(), name
+    scale = float(e1.abs().max())
+    noise = float((e1 - e2).abs().max()) / scale
+    err = float((e1 - gr).abs().max()) / scale
+    print(f'{name}: eager-vs-eager {noise:.2e}, graph-vs-eager {err:.2e}')
+    assert err <= max(4.0 * noise, 1e-5), f'{name}: graph replay differs from eager by {err:.2e} (run-to-run noise {noise:.2e})'

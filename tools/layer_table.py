@@ -47,8 +47,14 @@ for r in recs:
   a = agg.setdefault(r['sig'], {'n': 0, 'ms': 0.0, 'flops': r['flops'], 'bytes': r['bytes'], 'cls': r['cls']})
   a['n'] += 1
   a['ms'] += r['e0'].elapsed_time(r['e1'])
+bw = {k: v for k, v in agg.items() if len(k) < 11}
+agg = {k: v for k, v in agg.items() if len(k) >= 11}
 tot = sum(a['ms'] for a in agg.values()) / reps
 print(f'{mode} {N}x{H}x{W}: conv kernels {tot:.3f} ms/step')
+for sig, a in bw.items():
+  us = 1e3 * a['ms'] / a['n']
+  print(f'  bandwidth kernel {sig[0]}: {a["n"] / reps:.1f}/step, {us:.1f} us, algorithmic {a["bytes"] / 1e6:.1f} MB -> '
+        f'{a["bytes"] / us / 1e3:.0f} GB/s = {a["bytes"] / us / 1e3 / peaks["hbm_gbs"]:.3f} of the measured HBM peak')
 print('   N    H    W    C    K R s d res bn kind    cls          n/step   us    TF/s   GB/s  bound_us  eff')
 for sig, a in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
   us = 1e3 * a['ms'] / a['n']
