@@ -228,6 +228,8 @@ def run_wlseg_eval(args):
     raise SystemExit('bench.py: no CUDA device; wlseg has no CPU fallback')
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
+  quiet = StdoutToStderr()
+  quiet.__enter__()
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 
@@ -251,8 +253,10 @@ def run_wlseg_eval(args):
     step(i)
   torch.cuda.synchronize()
   if world > 1:
+    dist.all_reduce(torch.zeros(1, device=dev))  # first collective (communicator set-up) outside the timed region
     dist.barrier()
   torch.cuda.synchronize()
+  quiet.__exit__()
 
   net.profile = []
   sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -381,23 +385,46 @@ def measure_e2e(args, dev, rank, world, H, W, NB):
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
-  t0 = time.perf_counter()
-  m = est.evaluate(input_fn(None, st), ncls)
-  if world > 1:
-    system._reduce_across_ranks(m)
-  torch.cuda.synchronize()
-  dt = time.perf_counter() - t0
-  t = torch.tensor([dt], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  dt = float(t.item())
-  assert int(m['confusion_matrix_int64'].sum()) == world * args.steps * NB * H * W
+  # wall clock around the public call, max over ranks; the K-step region is short (tens of ms), so it
+  # is repeated three times and the MEDIAN is reported (a single host hiccup would otherwise halve it)
+  dts = []
+  for _ in range(3):
+    if world > 1:
+      dist.barrier()
+    t0 = time.perf_counter()
+    m = est.evaluate(input_fn(None, st), ncls)
+    if world > 1:
+      system._reduce_across_ranks(m)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dts.append(float(t.item()))
+    assert int(m['confusion_matrix_int64'].sum()) == world * args.steps * NB * H * W
+  dt = statistics.median(dts)
   import shutil
   shutil.rmtree(tmp, ignore_errors=True)
   del types
   return {'value': world * args.steps * NB * H * W / 1e6 / dt, 'unit': 'Mpix/s',
           'h2d_bytes_per_step': est.last_h2d_bytes // args.steps, 'd2h_bytes_per_step': est.last_d2h_bytes // args.steps,
-          'ms_per_step': 1e3 * dt / args.steps}
+          'ms_per_step': 1e3 * dt / args.steps, 'repeats': 3, 'stat': 'median of 3 repeats of the K-step region'}
+
+
+class StdoutToStderr:
+  """NCCL prints its version banner on stdout when the first communicator comes up; the contract is
+  ONE JSON line on stdout, so file descriptor 1 points at stderr until the warm-up is over."""
+
+  def __enter__(self):
+    sys.stdout.flush()
+    self.saved = os.dup(1)
+    os.dup2(2, 1)
+    return self
+
+  def __exit__(self, *exc):
+    sys.stdout.flush()
+    os.dup2(self.saved, 1)
+    os.close(self.saved)
 
 
 def main():

@@ -14,6 +14,7 @@
 namespace wlseg {
 
 constexpr int kBnThreads = 256;
+constexpr int kBnUnroll = 4;
 
 // thread (tx, ty): tx = channel-vector index within C/8 (<= 256), ty = row lane
 template <typename T, bool kBackward>
@@ -44,32 +45,47 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* _
     }
   }
   if (ty < lanes) {
-    for (int64_t row = (int64_t)blockIdx.x * lanes + ty; row < count; row += (int64_t)gridDim.x * lanes) {
-      float f[8];
-      Vec8<T> v;
-      v.load(a + row * pitch + tx * 8);
-      v.unpack(f);
-      if (!kBackward) {
+    // kBnUnroll independent rows per iteration: all their 16-byte loads are issued before any is used,
+    // so a thread keeps up to 3 x kBnUnroll requests in flight (one row at a time left the kernel
+    // latency-bound at 2.9 TB/s on the widest layers)
+    const int64_t step = (int64_t)gridDim.x * lanes;
+    for (int64_t row0 = (int64_t)blockIdx.x * lanes + ty; row0 < count; row0 += step * kBnUnroll) {
+      Vec8<T> va[kBnUnroll], vzz[kBnUnroll], vyy[kBnUnroll];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] += f[j] * f[j]; }
-      } else {
-        float zz[8];
-        Vec8<T> vz;
-        vz.load(z + row * pitch + tx * 8);
-        vz.unpack(zz);
-        if (zmask) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaf(zz[j], sc[j], sh[j]) > 0.f ? f[j] : 0.f;
-        } else if (relu) {
-          float yy[8];
-          Vec8<T> vy;
-          vy.load(yact + row * pitch + tx * 8);
-          vy.unpack(yy);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = yy[j] > 0.f ? f[j] : 0.f;
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int64_t row = row0 + u * step;
+        if (row < count) {
+          va[u].load(a + row * pitch + tx * 8);
+          if (kBackward) {
+            vzz[u].load(z + row * pitch + tx * 8);
+            if (relu && !zmask) vyy[u].load(yact + row * pitch + tx * 8);
+          }
         }
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s0[j] += f[j] * (zz[j] - mu[j]) * is[j]; s1[j] += f[j]; }
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int64_t row = row0 + u * step;
+        if (row >= count) break;
+        float f[8];
+        va[u].unpack(f);
+        if (!kBackward) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] += f[j] * f[j]; }
+        } else {
+          float zz[8];
+          vzz[u].unpack(zz);
+          if (zmask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(zz[j], sc[j], sh[j]) > 0.f ? f[j] : 0.f;
+          } else if (relu) {
+            float yy[8];
+            vyy[u].unpack(yy);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = yy[j] > 0.f ? f[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += f[j] * (zz[j] - mu[j]) * is[j]; s1[j] += f[j]; }
+        }
       }
     }
 #pragma unroll
@@ -379,7 +395,9 @@ static int launch_reduce(const void* a, const void* y, const void* z, const floa
   const int cv = C / 8;
   const int lanes = kBnThreads / cv;
   size_t smem = (size_t)lanes * 2 * C * sizeof(float);
-  int grid = bw_grid(count * cv, kBnThreads, 4);
+  // 2 CTAs per SM: with kBnUnroll rows in flight per thread that saturates HBM, and it halves the number
+  // of CTAs queueing on the same C fp64 accumulators at the end
+  int grid = bw_grid(ceil_div(count * cv, kBnUnroll), kBnThreads, 2);
   bn_reduce_kernel<T, kBackward><<<grid, kBnThreads, smem, s>>>((const T*)a, (const T*)y, (const T*)z, mean, invstd,
                                                                 scale, shift, count, C, pitch, relu, o0, o1);
   WLSEG_LAUNCH_CHECK();

@@ -129,7 +129,8 @@ def test_batch_norm_train_fwd_bwd(cuda, C, dtype):
       ops.bn_bwd_apply(dyd[..., sl], None, zd[..., sl], smean[sl], sinv[sl], gd[sl], dg2[sl], db2[sl], count, h, True,
                        dz2[..., sl], scale=scale[sl], shift=shift[sl], pitch=C)
     torch.cuda.synchronize()
-    assert torch.allclose(dg2, ref_dg, rtol=1e-9, atol=1e-9) and torch.allclose(db2, ref_db, rtol=1e-9, atol=1e-9)
+    # per-thread partial sums are fp32 and the row partition differs between the two launches
+    assert torch.allclose(dg2, ref_dg, rtol=1e-4, atol=1e-4) and torch.allclose(db2, ref_db, rtol=1e-4, atol=1e-4)
     assert float((dz2.float() - ref_dz.float()).abs().max()) <= 1e-2 * float(ref_dz.float().abs().max())
 
 

@@ -83,6 +83,19 @@ if len(sys.argv) > 2 and sys.argv[2] == 'sweep':
     fprop(4, 96, 96, 512, 512, 3, 4, stats=True, relu=False)
   sys.exit(0)
 
+if len(sys.argv) > 2 and sys.argv[2] == 'stats':
+  for na in ('0', '1'):
+    os.environ['WLSEG_NO_STAT_ATOMICS'] = na
+    print('--- WLSEG_NO_STAT_ATOMICS=' + na)
+    for st in (False, True):
+      fprop(4, 96, 96, 256, 256, 3, 2, stats=st, relu=False)
+      fprop(4, 96, 96, 128, 128, 3, 1, stats=st, relu=False)
+      fprop(4, 96, 96, 1024, 256, 1, 1, stats=st, relu=False)
+      fprop(4, 96, 96, 256, 1024, 1, 1, stats=st, relu=False)
+      fprop(4, 96, 96, 512, 2048, 1, 1, stats=st, relu=False)
+      fprop(4, 192, 192, 64, 256, 1, 1, stats=st, relu=False)
+  sys.exit(0)
+
 if len(sys.argv) > 2 and sys.argv[2] == 'membound':
   for kw in MEMBOUND:
     fprop(**kw)
