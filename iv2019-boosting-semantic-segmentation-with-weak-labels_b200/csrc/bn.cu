@@ -265,43 +265,56 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
   __syncthreads();
   const int cv = C / 8;
   const int64_t total = count * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) * 8;
-    const int64_t e = (i / cv) * pitch + c0;   // element offset: row * pitch + channel
-    float g[8], zz[8];
-    Vec8<T> v, vz;
-    v.load(dy + e);
-    vz.load(z + e);
-    v.unpack(g);
-    vz.unpack(zz);
-    if (zmask) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;  // two independent 8-channel vectors per iteration: 6 loads in flight per thread
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += step * U) {
+    Vec8<T> v[U], vz[U], vy[U];
+    int64_t e[U];
+    int c0[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = fmaf(zz[j], ssc[c0 + j], ssh[c0 + j]) > 0.f ? g[j] : 0.f;
-    } else if (relu) {
-      float yy[8];
-      Vec8<T> vy;
-      vy.load(yact + e);
-      vy.unpack(yy);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = yy[j] > 0.f ? g[j] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * step;
+      if (i < total) {
+        c0[u] = (int)(i % cv) * 8;
+        e[u] = (i / cv) * pitch + c0[u];   // element offset: row * pitch + channel
+        v[u].load(dy + e[u]);
+        vz[u].load(z + e[u]);
+        if (relu && !zmask) vy[u].load(yact + e[u]);
+      }
     }
-    if (dres != nullptr) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * step >= total) break;
+      float g[8], zz[8];
+      v[u].unpack(g);
+      vz[u].unpack(zz);
+      if (zmask) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(zz[j], ssc[c0[u] + j], ssh[c0[u] + j]) > 0.f ? g[j] : 0.f;
+      } else if (relu) {
+        float yy[8];
+        vy[u].unpack(yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = yy[j] > 0.f ? g[j] : 0.f;
+      }
+      if (dres != nullptr) {
+        Vec8<T> o;
+        o.pack(g);
+        o.store(dres + e[u]);
+      }
+      const float4 a0 = *reinterpret_cast<const float4*>(sA + c0[u]), a1 = *reinterpret_cast<const float4*>(sA + c0[u] + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s1 + c0[u]), b1 = *reinterpret_cast<const float4*>(s1 + c0[u] + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(s0 + c0[u]), d1 = *reinterpret_cast<const float4*>(s0 + c0[u] + 4);
+      const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] = fmaf(A[j], g[j], fmaf(B[j], zz[j], D[j]));
       Vec8<T> o;
-      o.pack(g);
-      o.store(dres + e);
+      o.pack(out);
+      o.store(dz + e[u]);
     }
-    const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(s1 + c0), b1 = *reinterpret_cast<const float4*>(s1 + c0 + 4);
-    const float4 d0 = *reinterpret_cast<const float4*>(s0 + c0), d1 = *reinterpret_cast<const float4*>(s0 + c0 + 4);
-    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    float out[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = fmaf(A[j], g[j], fmaf(B[j], zz[j], D[j]));
-    Vec8<T> o;
-    o.pack(out);
-    o.store(dz + e);
   }
 }
 
