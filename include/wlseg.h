@@ -97,11 +97,15 @@ int wlseg_bn_stats(const void* z, int64_t count, int32_t C, int32_t pitch, int32
 
 /* mean = sum/count, var = sqsum/count - mean^2 (biased); scale = gamma*rsqrt(var+eps),
  * shift = beta - mean*scale; moving stats updated in place with `decay` and the unbiased
- * variance (skipped if moving_mean is NULL); saved_mean / saved_invstd for the backward. */
+ * variance (skipped if moving_mean is NULL); saved_mean / saved_invstd for the backward.
+ * moving_var_factor < 0: the moving variance takes var * count / (count - 1) (tf.contrib.layers
+ * .batch_norm, fused); >= 0: it takes var * moving_var_factor.  --cross_replica_norm passes the
+ * all-reduced sums with count = replicas * n_local and the factor (n_local - 1) / n_local, the
+ * "Bessel removal" of utils/cross_replica_batch_normalization.py:452-459. */
 int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t count, int32_t C,
                       const float* gamma, const float* beta, float eps, float decay,
-                      float* moving_mean, float* moving_var, float* scale, float* shift,
-                      float* saved_mean, float* saved_invstd, wlseg_stream_t stream);
+                      float moving_var_factor, float* moving_mean, float* moving_var, float* scale,
+                      float* shift, float* saved_mean, float* saved_invstd, wlseg_stream_t stream);
 
 /* wlseg_bn_finalize + wlseg_bn_apply in one launch (C % 8 == 0, C <= 2048): every CTA derives
  * scale / shift from the sums; CTA 0 publishes them (+ saved mean / invstd, moving statistics). */
@@ -125,15 +129,18 @@ int wlseg_bn_apply(const void* z, const float* scale, const float* shift, const 
  * `pitch` = elements between consecutive rows of dy / y / z / dz / dres (all share it): a channel
  * slice [c0, c0 + C) of a wider tensor is processed by passing pointers offset by c0 and the full
  * width as pitch; the host mirror runs reduce + apply slice by slice so that the second pass reads
- * its three inputs from L2 instead of HBM. */
+ * its three inputs from L2 instead of HBM.
+ * `stat_count` (apply) = number of pixels dgamma / dbeta were summed over: equal to `count` (the
+ * rows of THIS tensor) except under --cross_replica_norm, where the sums are all-reduced over the
+ * replicas and stat_count = replicas * count. */
 int wlseg_bn_bwd_reduce(const void* dy, const void* y, const void* z, const float* mean,
                         const float* invstd, const float* scale, const float* shift, int64_t count,
                         int32_t C, int32_t pitch, int32_t relu, int32_t dtype, double* dgamma,
                         double* dbeta, wlseg_stream_t stream);
 int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* mean,
                        const float* invstd, const float* gamma, const float* scale, const float* shift,
-                       const double* dgamma, const double* dbeta, int64_t count, int32_t C,
-                       int32_t pitch, int32_t relu, int32_t dtype, void* dz, void* dres,
+                       const double* dgamma, const double* dbeta, int64_t count, int64_t stat_count,
+                       int32_t C, int32_t pitch, int32_t relu, int32_t dtype, void* dz, void* dres,
                        wlseg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

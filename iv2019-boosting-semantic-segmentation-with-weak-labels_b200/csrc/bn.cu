@@ -105,9 +105,9 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* _
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, int64_t count,
                                    int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ saved_mean,
-                                   float* __restrict__ saved_invstd) {
+                                   float decay, float moving_var_factor, float* __restrict__ moving_mean,
+                                   float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ saved_mean, float* __restrict__ saved_invstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double n = (double)count;
@@ -122,8 +122,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
   if (saved_mean) saved_mean[c] = mf;
   if (saved_invstd) saved_invstd[c] = inv;
   if (moving_mean) {
-    // TF: moving <- moving - (1 - decay) * (moving - stat); variance with Bessel's correction
-    float unbiased = count > 1 ? (float)(var * (n / (n - 1.0))) : vf;
+    // TF: moving <- moving - (1 - decay) * (moving - stat); variance with Bessel's correction, or - under
+    // --cross_replica_norm - the biased GLOBAL variance times (n_local - 1) / n_local
+    // (utils/cross_replica_batch_normalization.py:452-459), passed in as moving_var_factor >= 0
+    float unbiased = moving_var_factor >= 0.f ? vf * moving_var_factor : (count > 1 ? (float)(var * (n / (n - 1.0))) : vf);
     moving_mean[c] -= (1.0f - decay) * (moving_mean[c] - mf);
     moving_var[c] -= (1.0f - decay) * (moving_var[c] - unbiased);
   }
@@ -243,8 +245,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ scale, const float* __restrict__ shift,
-                    const double* __restrict__ dgamma, const double* __restrict__ dbeta, int64_t count, int C,
-                    int pitch, int relu, T* __restrict__ dz, T* __restrict__ dres) {
+                    const double* __restrict__ dgamma, const double* __restrict__ dbeta, int64_t count,
+                    int64_t stat_count, int C, int pitch, int relu, T* __restrict__ dz, T* __restrict__ dres) {
   extern __shared__ float bconst[];  // [5][C]: A | c1 | c0 | scale | shift
   float* sA = bconst;
   float* s1 = bconst + C;
@@ -252,7 +254,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
   float* ssc = bconst + 3 * C;
   float* ssh = bconst + 4 * C;
   const bool zmask = relu && yact == nullptr;
-  const double invn = 1.0 / (double)count;
+  const double invn = 1.0 / (double)stat_count;   // pixels the sums were taken over (all replicas under sync BN)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float is = invstd[c];
     const float A = gamma[c] * is;
@@ -266,7 +268,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
   const int cv = C / 8;
   const int64_t total = count * cv;
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  constexpr int U = 2;  // two independent 8-channel vectors per iteration: 6 loads in flight per thread
+  constexpr int U = 1;  // U = 2 (6 loads in flight per thread) measured 6 % SLOWER: occupancy matters more here
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += step * U) {
     Vec8<T> v[U], vz[U], vy[U];
     int64_t e[U];
@@ -374,9 +376,9 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_small_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ z,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ gamma, const double* __restrict__ dgamma,
-                          const double* __restrict__ dbeta, int64_t total, int64_t count, int C, int relu,
+                          const double* __restrict__ dbeta, int64_t total, int64_t stat_count, int C, int relu,
                           T* __restrict__ dz, T* __restrict__ dres) {
-  const float invn = 1.0f / (float)count;
+  const float invn = 1.0f / (float)stat_count;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     float g = to_f32<T>(dy[i]);
@@ -437,14 +439,14 @@ extern "C" int wlseg_bn_stats(const void* z, int64_t count, int32_t C, int32_t p
 }
 
 extern "C" int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t count, int32_t C, const float* gamma,
-                                 const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
-                                 float* scale, float* shift, float* saved_mean, float* saved_invstd,
-                                 wlseg_stream_t stream) {
+                                 const float* beta, float eps, float decay, float moving_var_factor,
+                                 float* moving_mean, float* moving_var, float* scale, float* shift, float* saved_mean,
+                                 float* saved_invstd, wlseg_stream_t stream) {
   WLSEG_CHECK_ARG(sum && sqsum && gamma && beta && count > 0 && C > 0, "bn_finalize: bad args");
   WLSEG_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving stats must come in pairs");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, count, C, gamma, beta, eps, decay,
-                                                                        moving_mean, moving_var, scale, shift,
-                                                                        saved_mean, saved_invstd);
+                                                                        moving_var_factor, moving_mean, moving_var, scale,
+                                                                        shift, saved_mean, saved_invstd);
   WLSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -527,10 +529,12 @@ extern "C" int wlseg_bn_bwd_reduce(const void* dy, const void* y, const void* z,
 
 extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, const float* mean, const float* invstd,
                                   const float* gamma, const float* scale, const float* shift, const double* dgamma,
-                                  const double* dbeta, int64_t count, int32_t C, int32_t pitch, int32_t relu,
-                                  int32_t dtype, void* dz, void* dres, wlseg_stream_t stream) {
+                                  const double* dbeta, int64_t count, int64_t stat_count, int32_t C, int32_t pitch,
+                                  int32_t relu, int32_t dtype, void* dz, void* dres, wlseg_stream_t stream) {
   if (int e = check_bn_shape(count, C, "bn_bwd_apply")) return e;
   if (count == 0) return 0;
+  WLSEG_CHECK_ARG(stat_count >= count, "bn_bwd_apply: stat_count (%lld) < count (%lld)", (long long)stat_count,
+                  (long long)count);
   WLSEG_CHECK_ARG(dy && z && mean && invstd && gamma && dgamma && dbeta && dz && (!relu || y || (scale && shift)),
                   "bn_bwd_apply: null pointer");
   WLSEG_CHECK_ARG(pitch >= C && (C % 8 != 0 ? pitch == C : pitch % 8 == 0), "bn_bwd_apply: bad pitch %d", pitch);
@@ -541,11 +545,11 @@ extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, 
     if (dtype == WLSEG_BF16)
       bn_bwd_apply_small_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, invstd, gamma, dgamma, dbeta,
-          total, count, C, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
+          total, stat_count, C, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
     else if (dtype == WLSEG_F32)
       bn_bwd_apply_small_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z,
-                                                                     mean, invstd, gamma, dgamma, dbeta, total, count, C,
-                                                                     relu, (float*)dz, (float*)dres);
+                                                                     mean, invstd, gamma, dgamma, dbeta, total, stat_count,
+                                                                     C, relu, (float*)dz, (float*)dres);
     else
       WLSEG_CHECK_ARG(false, "bn_bwd_apply: bad dtype %d", dtype);
     WLSEG_LAUNCH_CHECK();
@@ -556,11 +560,11 @@ extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, 
   if (dtype == WLSEG_BF16)
     bn_bwd_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, invstd, gamma, scale, shift,
-        dgamma, dbeta, count, C, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
+        dgamma, dbeta, count, stat_count, C, pitch, relu, (__nv_bfloat16*)dz, (__nv_bfloat16*)dres);
   else if (dtype == WLSEG_F32)
     bn_bwd_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z,
                                                                    mean, invstd, gamma, scale, shift, dgamma, dbeta, count,
-                                                                   C, pitch, relu, (float*)dz, (float*)dres);
+                                                                   stat_count, C, pitch, relu, (float*)dz, (float*)dres);
   else
     WLSEG_CHECK_ARG(false, "bn_bwd_apply: bad dtype %d", dtype);
   WLSEG_LAUNCH_CHECK();

@@ -27,6 +27,23 @@ def _dist_env(st):
   return st
 
 
+def _dist_shutdown(st, system):
+  """Multi-rank exit: the step graph holds captured NCCL collectives, so it is dropped and the device
+  drained before the process group goes away (destroying the group under a live graph can hang)."""
+  if getattr(st, 'world_size', 1) <= 1:
+    return
+  import torch
+  import torch.distributed as dist
+  tr = getattr(getattr(system, 'estimator', None), 'trainer', None)
+  if tr is not None:
+    tr._graphs.clear()
+  torch.cuda.synchronize()
+  if dist.is_initialized():
+    dist.barrier()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+
+
 def train_main(argv):
   ss = wsettings.build_parser(wsettings.TRAIN)
   st = ss.parse_args(argv)
@@ -35,7 +52,9 @@ def train_main(argv):
   wsettings.train_extra_args(st)
   _dist_env(st)
   system = SemanticSegmentation({'train': synthetic.train_input_fn}, None, st)
-  return system.train()
+  out = system.train()
+  _dist_shutdown(st, system)
+  return out
 
 
 def evaluate_main(argv):
@@ -57,6 +76,7 @@ def evaluate_main(argv):
         metrics.print_metrics_from_confusion_matrix(m['confusion_matrix'], labels, printfile=f)
     with open(os.path.join(system.settings.eval_res_dir, 'all_metrics.p'), 'wb') as f:
       pickle.dump([{k: m[k] for k in ('global_step', 'loss', 'confusion_matrix')} for m in all_metrics], f)
+  _dist_shutdown(st, system)
   return all_metrics
 
 

@@ -437,11 +437,16 @@ class TrainWorkspace:
 class TrainNetwork(Network):
   """Forward with batch statistics + backward.  BN follows every convolution (also the logits
   convolutions, code/models/resnet50_extended_model_hierarchical.py:76-83); statistics are per
-  replica (the reference's default without --cross_replica_norm)."""
+  replica (the reference's default) or, with `cross_replica=(world_size, process_group)`
+  (--cross_replica_norm, code/utils/cross_replica_batch_normalization.py:398-459), over all replicas:
+  the per-layer fp64 [sum | sqsum] (forward) and [dgamma | dbeta] (backward) vectors are summed
+  across ranks with one small all-reduce each, between the two passes that produce and consume them."""
 
-  def __init__(self, params, dtype=torch.bfloat16, bn_decay=0.9, eps=1e-5, conv_algo=ops.ALGO_AUTO):
+  def __init__(self, params, dtype=torch.bfloat16, bn_decay=0.9, eps=1e-5, conv_algo=ops.ALGO_AUTO,
+               cross_replica=None):
     super().__init__(params, dtype, bn_decay, eps, conv_algo)
     self.ws = TrainWorkspace(params)
+    self.cross_replica = cross_replica if (cross_replica and cross_replica[0] >= 1) else None  # (1, group): tests
     self.grad_ready = None  # callback(lo): every conv-kernel gradient at arena offset >= lo is final
     self.keep = False       # tests: keep per-layer gradient tensors on the tape
     self._flipped = None    # {scope: dgrad filter bank view}, refreshed at the start of backward()
@@ -492,7 +497,15 @@ class TrainNetwork(Network):
     mean, invstd = ws.view(ws.bn, 2, off, K), ws.view(ws.bn, 3, off, K)
     a = torch.empty_like(z)
     do_relu = spec.relu if relu is None else relu
-    if self.fused_bn_finalize and K % 8 == 0 and K <= 2048:
+    if self.cross_replica is not None:
+      # global moments: one all-reduce of this layer's [sum | sqsum]; every replica has the same count
+      R = self.cross_replica[0]
+      both = self._all_reduce_pair(s1, s2)
+      ops.bn_finalize(both[:K], both[K:], count * R, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps,
+                      self.bn_decay, self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean,
+                      invstd, moving_var_factor=(count - 1.0) / count)
+      ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu)
+    elif self.fused_bn_finalize and K % 8 == 0 and K <= 2048:
       ops.bn_finalize_apply(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
                             self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd,
                             z, residual, a, do_relu)
@@ -506,6 +519,13 @@ class TrainNetwork(Network):
     rec.res = residual if self.keep else None
     self.tape[scope] = rec
     return a
+
+  def _all_reduce_pair(self, a, b):
+    """SUM over replicas of two per-channel fp64 vectors with ONE collective; returns [a | b] summed."""
+    import torch.distributed as dist
+    both = torch.cat([a, b])
+    dist.all_reduce(both, op=dist.ReduceOp.SUM, group=self.cross_replica[1])
+    return both
 
   def _wgrad_view(self, scope, shape):
     o = self.p.w_off[scope]
@@ -538,7 +558,16 @@ class TrainNetwork(Network):
       budget = self.bn_bwd_l2_bytes // ((3 if y is not None else 2) * esz * max(count, 1))
       if budget < K:
         Kg = max(64, budget // 64 * 64)
-    for c0 in range(0, K, Kg):
+    if self.cross_replica is not None:
+      # the dz formula needs the sums over ALL replicas' pixels (the all-reduce of the forward moments is its
+      # own transpose); the parameter gradients stay the local sums and are averaged with the other gradients
+      R = self.cross_replica[0]
+      ops.bn_bwd_reduce(da, y, rec.z, mean, invstd, count, K, rec.relu, dgamma, dbeta, scale=scale, shift=shift, pitch=K)
+      both = self._all_reduce_pair(dgamma, dbeta)
+      ops.bn_bwd_apply(da, y, rec.z, mean, invstd, gamma, both[:K], both[K:], count, K, rec.relu, dz, dres,
+                       scale=scale, shift=shift, pitch=K, stat_count=count * R)
+      Kg = 0
+    for c0 in (range(0, K, Kg) if Kg else ()):
       kk = min(Kg, K - c0)
       sl = slice(c0, c0 + kk)
       ops.bn_bwd_reduce(da[..., sl], None if y is None else y[..., sl], rec.z[..., sl], mean[sl], invstd[sl], count, kk,

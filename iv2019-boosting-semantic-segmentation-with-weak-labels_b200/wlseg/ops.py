@@ -50,14 +50,14 @@ _SIGNATURES = {
     'wlseg_conv2d_dgrad': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp]),
     'wlseg_conv2d_wgrad': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp]),
     'wlseg_bn_stats': (ctypes.c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
-    'wlseg_bn_finalize': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
+    'wlseg_bn_finalize': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _vp]),
     'wlseg_bn_finalize_apply': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
                                                _vp, _vp, _vp, _vp, _c_int, _c_int, _vp]),
     'wlseg_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp]),
     'wlseg_bn_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _c_int,
                                            _vp, _vp, _vp]),
-    'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int,
+    'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, _c_int,
                                           _c_int, _c_int, _vp, _vp, _vp]),
     'wlseg_maxpool_same_fwd': (ctypes.c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                               _vp]),
@@ -243,10 +243,11 @@ def bn_stats(z, count, C, pitch, sum_, sqsum):
 
 
 def bn_finalize(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, saved_mean,
-                saved_invstd):
+                saved_invstd, moving_var_factor=-1.0):
+  """moving_var_factor < 0: unbiased moving variance (default); >= 0: var * factor (--cross_replica_norm)."""
   _check(lib().wlseg_bn_finalize(_ptr(sum_), _ptr(sqsum), count, C, _ptr(gamma), _ptr(beta), eps, decay,
-                                 _ptr(moving_mean), _ptr(moving_var), _ptr(scale), _ptr(shift), _ptr(saved_mean),
-                                 _ptr(saved_invstd), _stream()), 'wlseg_bn_finalize')
+                                 moving_var_factor, _ptr(moving_mean), _ptr(moving_var), _ptr(scale), _ptr(shift),
+                                 _ptr(saved_mean), _ptr(saved_invstd), _stream()), 'wlseg_bn_finalize')
   _count()
 
 
@@ -276,9 +277,11 @@ def bn_bwd_reduce(dy, y, z, mean, invstd, count, C, relu, dgamma, dbeta, scale=N
 
 
 def bn_bwd_apply(dy, y, z, mean, invstd, gamma, dgamma, dbeta, count, C, relu, dz, dres=None, scale=None, shift=None,
-                 pitch=None):
+                 pitch=None, stat_count=None):
+  """stat_count: pixels dgamma / dbeta were summed over (replicas * count under --cross_replica_norm)."""
   _check(lib().wlseg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(scale),
-                                  _ptr(shift), _ptr(dgamma), _ptr(dbeta), count, C, C if pitch is None else pitch,
+                                  _ptr(shift), _ptr(dgamma), _ptr(dbeta), count, count if stat_count is None else stat_count,
+                                  C, C if pitch is None else pitch,
                                   int(relu), dtype_code(z.dtype), _ptr(dz), _ptr(dres), _stream()),
          'wlseg_bn_bwd_apply')
   _count()

@@ -99,9 +99,8 @@ class SemanticSegmentation(object):
     if getattr(s, 'name_feature_extractor', 'resnet_v1_50') == 'resnet_v1_101':
       # code/estimator/define_estimator_hierarchical.py:57-61
       raise NotImplementedError('Use of resnet_v1_101 as base feature extractor is not yet implemented.')
-    for flag in ('psp_module', 'cross_replica_norm'):
-      if getattr(s, flag, False):
-        raise NotImplementedError(f'--{flag} is not implemented yet in the B200 path.')
+    if getattr(s, 'psp_module', False):
+      raise NotImplementedError('--psp_module is not implemented yet in the B200 path.')
     if getattr(s, 'upsampling_method', 'bilinear') != 'bilinear' or getattr(s, 'norm_layer', 'batch') != 'batch':
       raise NotImplementedError('only --upsampling_method bilinear and --norm_layer batch are implemented.')
     self._estimator = est.Estimator(s, self._hier, device=getattr(s, 'device', 'cuda'))
@@ -140,11 +139,13 @@ class SemanticSegmentation(object):
 
     settings_dict = collections.OrderedDict(sorted(vars(s).items()))
     settings_filename = join(s.log_dir, 'settings.txt')
-    assert not exists(settings_filename), (
-        f"Previous settings.txt found in {s.log_dir}. Rename or delete it manually and restart training.")
-    with open(settings_filename, 'w') as f:
-      for k, v in enumerate(settings_dict):
-        print(f"{k:2} : {v} : {settings_dict[v]}", file=f)
+    if getattr(s, 'rank', 0) == 0:
+      # one process per GPU: rank 0 owns the log directory (the reference is a single process)
+      assert not exists(settings_filename), (
+          f"Previous settings.txt found in {s.log_dir}. Rename or delete it manually and restart training.")
+      with open(settings_filename, 'w') as f:
+        for k, v in enumerate(settings_dict):
+          print(f"{k:2} : {v} : {settings_dict[v]}", file=f)
 
     self._create_estimator()
     max_steps = s.num_training_steps if not getattr(s, 'steps', None) else min(s.steps, s.num_training_steps)
@@ -171,12 +172,13 @@ class SemanticSegmentation(object):
 
     eval_res_dir = s.eval_res_dir
     print(f"\nWriting results in {eval_res_dir}.\n")
-    os.makedirs(eval_res_dir)
-    if exists(join(eval_res_dir, 'settings.txt')):
-      print(f"WARNING: previous settings.txt in {eval_res_dir} is ovewritten.")
-    with open(join(eval_res_dir, 'settings.txt'), 'w') as f:
-      for k, v in vars(s).items():
-        print(f"{k} : {v}", file=f)
+    if getattr(s, 'rank', 0) == 0:
+      os.makedirs(eval_res_dir)
+      if exists(join(eval_res_dir, 'settings.txt')):
+        print(f"WARNING: previous settings.txt in {eval_res_dir} is ovewritten.")
+      with open(join(eval_res_dir, 'settings.txt'), 'w') as f:
+        for k, v in vars(s).items():
+          print(f"{k} : {v}", file=f)
 
     labels = s.evaluation_problem_def['cids2labels']
     void_exists = -1 in s.evaluation_problem_def['lids2cids']

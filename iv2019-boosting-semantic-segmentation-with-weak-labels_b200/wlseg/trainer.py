@@ -93,7 +93,10 @@ class Trainer:
     self.p = params
     self.s = settings
     self.rank, self.world = rank, world_size
-    self.net = network.TrainNetwork(params, dtype=dtype, bn_decay=getattr(settings, 'batch_norm_decay', 0.9))
+    # --cross_replica_norm (models/resnet50_extended_model_hierarchical.py:257,327-328): BN moments over all replicas
+    xr = (world_size, None) if (getattr(settings, 'cross_replica_norm', False) and world_size > 1) else None
+    self.net = network.TrainNetwork(params, dtype=dtype, bn_decay=getattr(settings, 'batch_norm_decay', 0.9),
+                                    cross_replica=xr)
     self.ws = self.net.ws
     self.momentum = float(getattr(settings, 'momentum', 0.9))
     self.nesterov = bool(getattr(settings, 'use_nesterov', False))

@@ -102,6 +102,29 @@ def batch_norm(x, gamma, beta, moving_mean, moving_var, training, decay=0.9, eps
   return y, moving_mean, moving_var, moving_mean, moving_var
 
 
+def cross_replica_batch_norm(xs, gamma, beta, moving_mean, moving_var, decay=0.9, eps=1e-5):
+  """--cross_replica_norm, training mode: `xs` is the list of per-replica NHWC inputs.
+  code/utils/cross_replica_batch_normalization.py:398-459:
+    global_mean = sum_r mean_r / R ; global_sq_mean = sum_r E_r[x^2] / R (:404-427, each replica
+    divides its moments by num_towers before the SUM reduction); variance = global_sq_mean -
+    global_mean^2 (biased); y_r = batch_normalization(x_r, global mean / variance) (:430-431);
+    the moving variance takes variance * (n - 1) / n with n the PER-REPLICA sample size - the
+    "Bessel removal" that the layer applies although this variance never had the correction
+    (:452-459); moving <- moving - (moving - value) * (1 - momentum) (:381-389).
+  Gradients flow through the reduced moments (the SUM all-reduce is its own transpose).
+  Returns (list of y_r, new_moving_mean, new_moving_var, global_mean, global_var)."""
+  R = len(xs)
+  mean = sum(x.mean(dim=(0, 1, 2)) / R for x in xs)
+  sq = sum((x * x).mean(dim=(0, 1, 2)) / R for x in xs)
+  var = sq - mean * mean
+  ys = [(x - mean) * torch.rsqrt(var + eps) * gamma + beta for x in xs]
+  with torch.no_grad():
+    n = xs[0].shape[0] * xs[0].shape[1] * xs[0].shape[2]
+    new_mm = moving_mean - (1.0 - decay) * (moving_mean - mean)
+    new_mv = moving_var - (1.0 - decay) * (moving_var - var * ((n - 1.0) / n))
+  return ys, new_mm, new_mv, mean, var
+
+
 def _interp_coords(in_size, out_size, align_corners):
   if align_corners and out_size > 1:
     scale = (in_size - 1) / (out_size - 1)

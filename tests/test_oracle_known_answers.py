@@ -191,3 +191,25 @@ def test_golden_fixture_matches_oracle():
     a, b = np.asarray(val, dtype=np.float64), np.asarray(now[key], dtype=np.float64)
     assert a.shape == b.shape, key
     assert np.allclose(a, b, rtol=1e-5, atol=1e-6), key
+
+
+def test_cross_replica_batch_norm_restatement():
+  """--cross_replica_norm (utils/cross_replica_batch_normalization.py:398-459): with equal per-replica
+  batch sizes the global moments are those of the concatenated batch, so the outputs equal ordinary
+  batch norm over the concatenation; the moving variance takes the BIASED global variance times
+  (n_local - 1) / n_local - not Bessel's correction over the global sample."""
+  import torch
+  from oracle import tfops
+  g = torch.Generator().manual_seed(2)
+  xs = [torch.randn(2, 3, 5, 4, generator=g) * (r + 1) + r for r in range(2)]
+  gamma, beta = torch.rand(4, generator=g) + 0.5, torch.randn(4, generator=g)
+  mm, mv = torch.randn(4, generator=g), torch.rand(4, generator=g) + 0.5
+  ys, new_mm, new_mv, mean, var = tfops.cross_replica_batch_norm(xs, gamma, beta, mm, mv, decay=0.9, eps=1e-5)
+  cat = torch.cat(xs, 0)
+  y_ref, ref_mm, ref_mv, ref_mean, ref_var = tfops.batch_norm(cat, gamma, beta, mm, mv, True, decay=0.9, eps=1e-5)
+  assert torch.allclose(torch.cat(ys, 0), y_ref, rtol=1e-5, atol=1e-5)
+  assert torch.allclose(mean, ref_mean, atol=1e-6) and torch.allclose(var, ref_var, rtol=1e-5, atol=1e-6)
+  assert torch.allclose(new_mm, ref_mm, atol=1e-6)
+  n_local = 2 * 3 * 5
+  assert torch.allclose(new_mv, mv - 0.1 * (mv - ref_var * (n_local - 1) / n_local), rtol=1e-5, atol=1e-6)
+  assert not torch.allclose(new_mv, ref_mv, rtol=1e-4)  # it is NOT the single-process update
