@@ -159,6 +159,21 @@ int wlseg_maxpool_same_bwd(const void* x, const uint8_t* argmax, const void* dy,
                            int32_t dtype, wlseg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Weak labels from their compact form (the reference builds them on the host:
+ * input_pipelines/open_images/input_subset_bboxes_v2.py:74-98 `_generate_rla`,
+ * input_pipelines/open_images/input_subset_image_labels.py:73-107).  Bit-exact with the numpy code.
+ *   coords float32 [N, max_boxes, 4] = (xmin, xmax, ymin, ymax) normalised to [0, 1];
+ *   cids   int32   [N, max_boxes]    = class id 0..13, anything else = padding / unknown label (skipped);
+ *   out    float32 [N, H, W, 15]: per pixel the box counts per class divided by their sum, or
+ *   void (channel 14) = 1 where no box covers the pixel.
+ * wlseg_tile_image_labels: out[n, :, :, :] = vec[n, :] (the image-level multinomial, tiled).
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_rasterize_bbox_labels(const float* coords, const int32_t* cids, int32_t N, int32_t max_boxes,
+                                int32_t H, int32_t W, float* out, wlseg_stream_t stream);
+int wlseg_tile_image_labels(const float* vec, int32_t N, int32_t H, int32_t W, float* out,
+                            wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Hierarchical head, forward (replaces _create_upsampler + softmax x3 + argmax x3 + gather /
  * where composition, models/resnet50_extended_model_hierarchical.py:84-117,143-184).
  * logits: fp32 [N, h, w, logits_pitch] low-resolution logits of the three heads, concatenated

@@ -63,6 +63,8 @@ _SIGNATURES = {
                                               _vp]),
     'wlseg_maxpool_same_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                               _c_int, _vp]),
+    'wlseg_rasterize_bbox_labels': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    'wlseg_tile_image_labels': (ctypes.c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
     'wlseg_head_fwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'wlseg_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -304,6 +306,32 @@ def maxpool_same_bwd(x, dy, dx, ksize, stride, argmax=None):
                                       dtype_code(dx.dtype), _stream()), 'wlseg_maxpool_same_bwd')
   _count()
   return dx
+
+
+# ------------------------------------------------------------------------------------ weak labels
+def rasterize_bbox_labels(coords, cids, H, W, out=None):
+  """coords fp32 [N, B, 4] (xmin, xmax, ymin, ymax, normalised), cids int32 [N, B] (-1 = padding) ->
+  fp32 [N, H, W, 15] per-pixel multinomial (input_subset_bboxes_v2.py:74-98)."""
+  N, B = cids.shape
+  assert coords.dtype == torch.float32 and cids.dtype == torch.int32 and coords.is_contiguous() and cids.is_contiguous()
+  assert tuple(coords.shape) == (N, B, 4)
+  if out is None:
+    out = torch.empty((N, H, W, 15), dtype=torch.float32, device=cids.device)
+  _check(lib().wlseg_rasterize_bbox_labels(_ptr(coords), _ptr(cids), N, B, H, W, _ptr(out), _stream()),
+         'wlseg_rasterize_bbox_labels')
+  _count()
+  return out
+
+
+def tile_image_labels(vec, H, W, out=None):
+  """vec fp32 [N, 15] -> fp32 [N, H, W, 15] (input_subset_image_labels.py:73-107)."""
+  N = vec.shape[0]
+  assert vec.dtype == torch.float32 and vec.is_contiguous() and vec.shape[1] == 15
+  if out is None:
+    out = torch.empty((N, H, W, 15), dtype=torch.float32, device=vec.device)
+  _check(lib().wlseg_tile_image_labels(_ptr(vec), N, H, W, _ptr(out), _stream()), 'wlseg_tile_image_labels')
+  _count()
+  return out
 
 
 # ------------------------------------------------------------------------------------ head / loss / metrics

@@ -36,31 +36,36 @@ class SyntheticInputs:
     full = cls.repeat_interleave(block, 1).repeat_interleave(block, 2)
     return full[:, :h, :w].contiguous()
 
+  def bbox_lists(self, n, max_boxes=12):
+    """Compact Open Images-style annotation: per image k ~ U{1..max_boxes} boxes of class ~ U{0..13} with
+    uniform corners; -> (coords fp32 [n, max_boxes, 4] = xmin, xmax, ymin, ymax normalised,
+    cids int32 [n, max_boxes], -1 = padding) - the form input_subset_bboxes_v2.py:60-72 yields."""
+    k = torch.randint(1, max_boxes + 1, (n, 1), generator=self.gen, device=self.device)
+    cids = torch.randint(0, NUM_WEAK - 1, (n, max_boxes), generator=self.gen, device=self.device, dtype=torch.int32)
+    slot = torch.arange(max_boxes, device=self.device).unsqueeze(0)
+    cids = torch.where(slot < k, cids, torch.full_like(cids, -1))
+    c = torch.rand((n, max_boxes, 4), generator=self.gen, device=self.device)
+    xs, _ = torch.sort(c[..., 0:2], dim=-1)
+    ys, _ = torch.sort(c[..., 2:4], dim=-1)
+    return torch.cat([xs, ys], dim=-1).contiguous(), cids.contiguous()
+
   def bbox_labels(self, n, h, w, max_boxes=12):
-    rla = torch.zeros((n, h, w, NUM_WEAK), dtype=torch.float32, device=self.device)
-    for i in range(n):
-      k = int(torch.randint(1, max_boxes + 1, (1,), generator=self.gen, device=self.device))
-      cids = torch.randint(0, NUM_WEAK - 1, (k,), generator=self.gen, device=self.device).tolist()
-      c = torch.rand((k, 4), generator=self.gen, device=self.device).tolist()
-      for cid, (a, b, cc, d) in zip(cids, c):
-        xmin, xmax = sorted((a, b))
-        ymin, ymax = sorted((cc, d))
-        x0, x1, y0, y1 = int(xmin * w), int(xmax * w), int(ymin * h), int(ymax * h)
-        rla[i, y0:y1 + 1, x0:x1 + 1, cid] += 1
-    s = rla.sum(-1, keepdim=True)
-    void = torch.zeros(NUM_WEAK, device=self.device)
-    void[-1] = 1.0
-    return torch.where(s > 0.5, rla / s.clamp(min=1.0), void.expand_as(rla)).contiguous()
+    """Dense per-pixel multinomials rasterised ON THE DEVICE from the box lists
+    (csrc/weak_labels.cu; bit-exact with `_generate_rla`, input_subset_bboxes_v2.py:74-98)."""
+    from wlseg import ops
+    coords, cids = self.bbox_lists(n, max_boxes)
+    return ops.rasterize_bbox_labels(coords, cids, h, w)
 
   def image_labels(self, n, h, w, max_classes=3):
-    out = torch.zeros((n, h, w, NUM_WEAK), dtype=torch.float32, device=self.device)
+    """m ~ U{1..max_classes} classes per image, value 1/m, tiled over the image on the device
+    (input_subset_image_labels.py:73-107)."""
+    from wlseg import ops
+    vec = torch.zeros((n, NUM_WEAK), dtype=torch.float32, device=self.device)
     for i in range(n):
       m = int(torch.randint(1, max_classes + 1, (1,), generator=self.gen, device=self.device))
       cids = torch.randperm(NUM_WEAK - 1, generator=self.gen, device=self.device)[:m]
-      v = torch.zeros(NUM_WEAK, device=self.device)
-      v[cids] = 1.0 / m
-      out[i] = v
-    return out
+      vec[i, cids] = 1.0 / m
+    return ops.tile_image_labels(vec, h, w)
 
   # ---- batches in the reference's (features, labels) form ------------------------------------
   def train_batch(self, npp, npb, npi, h, w):

@@ -205,3 +205,55 @@ def test_zero_insert_and_batched_flip(cuda, dtype):
     w = arena[o:o + K * R * S * C].view(K, R, S, C)
     ref = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()
     assert torch.equal(out[o:o + K * R * S * C].view(C, R, S, K).cpu(), ref)
+
+
+def test_weak_label_rasteriser_bit_exact_with_generate_rla(cuda):
+  """Device-side box rasterisation + per-pixel normalisation (csrc/weak_labels.cu) against the numpy
+  restatement of `_generate_rla` (input_subset_bboxes_v2.py:74-98) - bit-exact - including the worked
+  examples of its comment (:87-95): [1,0,0]->[1,0,0], [2,0,0]->[1,0,0], [1,1,0]->[1/2,1/2,0],
+  [2,1,0]->[2/3,1/3,0], no box -> void = 1; every pixel sums to 1 (input_subset_bboxes_v2_test.py:40-43)."""
+  from oracle import weak_labels as oweak
+  from wlseg import ops
+  H, W = 37, 53
+  g = torch.Generator().manual_seed(21)
+  lists = []
+  # image 0: the comment's cases laid out as overlapping boxes of classes 0 (car), 1 (bus)
+  lists.append([(0, 0.0, 0.2, 0.0, 0.2),                                  # [1,0,0]
+                (0, 0.3, 0.5, 0.0, 0.2), (0, 0.3, 0.5, 0.0, 0.2),         # [2,0,0]
+                (0, 0.6, 0.8, 0.0, 0.2), (1, 0.6, 0.8, 0.0, 0.2),         # [1,1,0]
+                (0, 0.0, 0.2, 0.5, 0.7), (0, 0.0, 0.2, 0.5, 0.7), (1, 0.0, 0.2, 0.5, 0.7)])  # [2,1,0]
+  # image 1: random boxes incl. degenerate ones, full-image box, xmax = 1.0 (stop index past the border)
+  k = 40
+  c = torch.rand(k, 4, generator=g)
+  boxes = [(int(torch.randint(0, 14, (1,), generator=g)), float(min(a, b)), float(max(a, b)), float(min(cc, d)), float(max(cc, d)))
+           for a, b, cc, d in c.tolist()]
+  boxes += [(3, 0.0, 1.0, 0.0, 1.0), (5, 0.5, 0.5, 0.2, 0.9), (7, 0.99, 1.0, 0.99, 1.0)]
+  lists.append(boxes)
+  lists.append([])   # image 2: no box at all -> void everywhere
+  B = max(len(b) for b in lists)
+  coords = torch.zeros(len(lists), B, 4)
+  cids = torch.full((len(lists), B), -1, dtype=torch.int32)
+  for i, bl in enumerate(lists):
+    for j, (cid, x0, x1, y0, y1) in enumerate(bl):
+      coords[i, j] = torch.tensor([x0, x1, y0, y1])
+      cids[i, j] = cid
+  got = ops.rasterize_bbox_labels(coords.to(cuda), cids.to(cuda), H, W).cpu()
+  for i, bl in enumerate(lists):
+    # the oracle sees the float32-rounded coordinates the device sees
+    bl32 = [(cid, *[float(v) for v in coords[i, j]]) for j, (cid, *_r) in enumerate(bl)]
+    want = torch.from_numpy(oweak.bbox_labels(bl32, H, W))
+    assert torch.equal(got[i], want), f'image {i}'
+  assert float((got.sum(-1) - 1.0).abs().max()) < 1e-3
+  px = got[0, int(0.1 * H), :, :3]
+  assert px[int(0.1 * W)].tolist() == [1.0, 0.0, 0.0] and px[int(0.4 * W)].tolist() == [1.0, 0.0, 0.0]
+  assert px[int(0.7 * W)].tolist() == [0.5, 0.5, 0.0]
+  q = got[0, int(0.6 * H), int(0.1 * W), :3].tolist()
+  assert q == [float(np.float32(2) / np.float32(3)), float(np.float32(1) / np.float32(3)), 0.0]
+  assert got[2, ..., 14].min() == 1.0 and got[2, ..., :14].abs().max() == 0.0
+  # image-level labels: the vector tiled over the image
+  vec = torch.zeros(2, 15)
+  vec[0, [2, 9]] = 0.5
+  vec[1, 14] = 1.0
+  tiled = ops.tile_image_labels(vec.to(cuda), H, W).cpu()
+  assert torch.equal(tiled[0], torch.from_numpy(oweak.image_labels([2, 9], H, W)))
+  assert torch.equal(tiled[1], torch.from_numpy(oweak.image_labels([], H, W)))
