@@ -159,6 +159,24 @@ int wlseg_maxpool_same_bwd(const void* x, const uint8_t* argmax, const void* dy,
                            int32_t dtype, wlseg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Pyramid (PSP) module pieces, `--psp_module` (models/resnet50_extended_model_hierarchical.py:186-207):
+ * slim.layers.avg_pool2d VALID (:191-200), tf.image.resize_images(bilinear, align_corners=True) of
+ * the pooled branches back to the feature size (:193-202), and their gradients.  NHWC, C % 8 == 0.
+ *   avgpool fwd: y[N, P, Q, C], P = (H - kh) / sh + 1 (windows that do not fit are dropped).
+ *   avgpool bwd (kernel == stride): dx (+)= dy[h / kh, w / kw] / (kh * kw); accumulate != 0 adds to dx.
+ *   resize fwd writes y with pixel pitch y_pitch (a channel slice of the 5 * C concatenation);
+ *   resize bwd reads dy with pixel pitch dy_pitch and fully writes dx[N, h, w, C].
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_avgpool_valid_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t kh,
+                            int32_t kw, int32_t sh, int32_t sw, int32_t dtype, wlseg_stream_t stream);
+int wlseg_avgpool_valid_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t kh,
+                            int32_t kw, int32_t accumulate, int32_t dtype, wlseg_stream_t stream);
+int wlseg_resize_bilinear_fwd(const void* x, void* y, int32_t N, int32_t h, int32_t w, int32_t C, int32_t H,
+                              int32_t W, int32_t y_pitch, int32_t dtype, wlseg_stream_t stream);
+int wlseg_resize_bilinear_bwd(const void* dy, void* dx, int32_t N, int32_t h, int32_t w, int32_t C, int32_t H,
+                              int32_t W, int32_t dy_pitch, int32_t dtype, wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Weak labels from their compact form (the reference builds them on the host:
  * input_pipelines/open_images/input_subset_bboxes_v2.py:74-98 `_generate_rla`,
  * input_pipelines/open_images/input_subset_image_labels.py:73-107).  Bit-exact with the numpy code.

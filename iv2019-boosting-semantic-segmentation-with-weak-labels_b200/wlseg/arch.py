@@ -44,9 +44,20 @@ def adaptation_units(d=256):
   return [UnitSpec(f'adaptation_module/{br}/bottleneck_v1', d, d, d, 1, 1, False) for br, _ in BRANCHES]
 
 
-def conv_specs(head_widths, output_stride=8, d=256):
+PSP_SCOPES = tuple('feature_extractor/pyramid_module/Conv' + ('' if i == 0 else f'_{i}') for i in range(5))
+PSP_BINS = (1, 2, 3, 6)
+
+
+FOV_SCOPE = 'feature_extractor/extension/increase_fov'
+
+
+def conv_specs(head_widths, output_stride=8, d=256, psp=False, fov=None):
   """All convolutions in parameter-arena order.  The three adaptation conv1 kernels are adjacent
-  so that they form one [3*d, 1, 1, d] filter bank (one GEMM over the shared input)."""
+  so that they form one [3*d, 1, 1, d] filter bank (one GEMM over the shared input).  psp=True adds the
+  five 1x1 convolutions of the pyramid module (slim's default scopes Conv .. Conv_4 under
+  feature_extractor/pyramid_module, resnet50_extended_model_hierarchical.py:55-57,186-207).  fov=(kernel
+  size, rate) adds the dilated `increase_fov` convolution (--fov_expansion_kernel_size / _rate,
+  resnet50_extended_feature_extractor.py:44-49)."""
   specs = [ConvSpec(f'{RES}/conv1', 7, 7, 3, 64, 2, 1, True)]
   for u in units(output_stride):
     if u.has_shortcut_conv:
@@ -55,6 +66,12 @@ def conv_specs(head_widths, output_stride=8, d=256):
     specs.append(ConvSpec(f'{u.scope}/conv2', 3, 3, u.bottleneck, u.bottleneck, u.stride, u.rate, True))
     specs.append(ConvSpec(f'{u.scope}/conv3', 1, 1, u.bottleneck, u.depth, 1, 1, False))
   specs.append(ConvSpec('feature_extractor/extension/decrease_fdims', 1, 1, 2048, d, 1, 1, True))
+  if fov:
+    specs.append(ConvSpec(FOV_SCOPE, fov[0], fov[0], d, d, 1, fov[1], True))
+  if psp:
+    for sc in PSP_SCOPES[:4]:
+      specs.append(ConvSpec(sc, 1, 1, d, d, 1, 1, True))
+    specs.append(ConvSpec(PSP_SCOPES[4], 1, 1, 5 * d, d, 1, 1, True))
   au = adaptation_units(d)
   for u in au:
     specs.append(ConvSpec(f'{u.scope}/conv1', 1, 1, d, d, 1, 1, True))

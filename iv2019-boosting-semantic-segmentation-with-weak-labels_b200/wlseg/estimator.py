@@ -128,7 +128,10 @@ class Estimator:
     self.hier = hier
     self.device = torch.device(device)
     self.dtype = torch.bfloat16 if getattr(params, 'dtype', 'bf16') == 'bf16' else torch.float32
-    self.params = network.Params(hier, self.device, getattr(params, 'stride_feature_extractor', 8))
+    self.params = network.Params(hier, self.device, getattr(params, 'stride_feature_extractor', 8),
+                                 psp=getattr(params, 'psp_module', False),
+                                 fov=(getattr(params, 'fov_expansion_kernel_size', 0),
+                                      getattr(params, 'fov_expansion_kernel_rate', 0)))
     self.global_step = 0
     self.net = None
     self.last_h2d_bytes = 0

@@ -26,10 +26,13 @@ def _trunc_normal_(t, std, gen):
 class Params:
   """All trainable variables + BN moving statistics, addressable by TF variable name."""
 
-  def __init__(self, hier, device, output_stride=8):
+  def __init__(self, hier, device, output_stride=8, psp=False, fov=None):
     self.hier = hier
     self.device = torch.device(device)
-    self.specs = arch.conv_specs(hier.head_widths, output_stride)
+    self.psp = bool(psp)  # --psp_module: five more convolutions (arch.PSP_SCOPES)
+    # --fov_expansion_kernel_size / --fov_expansion_kernel_rate: one dilated convolution (arch.FOV_SCOPE)
+    self.fov = tuple(fov) if fov and fov[0] > 0 and fov[1] > 0 else None
+    self.specs = arch.conv_specs(hier.head_widths, output_stride, psp=self.psp, fov=self.fov)
     self.by_scope = {s.scope: s for s in self.specs}
     self.w_off, self.c_off = {}, {}
     off = 0
@@ -330,7 +333,30 @@ class Network:
     x = self._root_infer(images)
     for u in arch.units():
       x = self._unit_infer(x, u)
-    return self._conv_bn_infer(x, 'feature_extractor/extension/decrease_fdims')
+    f = self._conv_bn_infer(x, 'feature_extractor/extension/decrease_fdims')
+    if self.p.fov:
+      f = self._conv_bn_infer(f, arch.FOV_SCOPE)
+    return self._psp(f, self._conv_bn_infer) if self.p.psp else f
+
+  def _psp(self, bottom, layer):
+    """_create_psp_module (models/resnet50_extended_model_hierarchical.py:186-207): VALID average pooling
+    into 1 / 2 / 3 / 6 bins -> 1x1 conv (+BN+ReLU) -> bilinear (align_corners) back to h x w, written
+    straight into its channel slice of the [N, h, w, 5d] concatenation -> 1x1 conv.  `layer(x, scope)` is
+    the conv+BN(+ReLU) driver of the calling mode (inference or training)."""
+    N, h, w, d = bottom.shape
+    cat = torch.empty((N, h, w, 5 * d), dtype=bottom.dtype, device=self.dev)
+    cat[..., :d].copy_(bottom)
+    pooled_shapes = []
+    for i, (sc, b) in enumerate(zip(arch.PSP_SCOPES[:4], arch.PSP_BINS)):
+      kh, kw = h // b, w // b
+      assert kh > 0 and kw > 0, f'--psp_module: the {h}x{w} feature map is too small for {b} bins'
+      pooled = torch.empty((N, (h - kh) // kh + 1, (w - kw) // kw + 1, d), dtype=bottom.dtype, device=self.dev)
+      ops.avgpool_valid_fwd(bottom, pooled, kh, kw)
+      c = layer(pooled, sc)
+      ops.resize_bilinear_fwd(c, cat[..., (i + 1) * d:(i + 2) * d])
+      pooled_shapes.append((kh, kw, tuple(pooled.shape)))
+    self._psp_geom = pooled_shapes
+    return layer(cat, arch.PSP_SCOPES[4])
 
   def lowres_logits_infer(self, images):
     """fp32 [N, h, w, logits_pitch]: the three heads' logits, concatenated along channels."""
@@ -724,6 +750,10 @@ class TrainNetwork(Network):
     for u in arch.units():
       x = self._unit_fwd(x, u)
     f = self._layer_fwd(x, 'feature_extractor/extension/decrease_fdims')
+    if self.p.fov:
+      f = self._layer_fwd(f, arch.FOV_SCOPE)
+    if self.p.psp:
+      f = self._psp(f, self._layer_fwd)
     N, h, w, d = f.shape
     au = arch.adaptation_units(d)
     s0 = f'{au[0].scope}/conv1'
@@ -774,6 +804,10 @@ class TrainNetwork(Network):
       df = dres if df is None else ops.add_inplace(df, dres)
     s0 = f'{au[0].scope}/conv1'
     dx, _ = self._layer_bwd(s0, da1, dx_add=df)
+    if self.p.psp:
+      dx = self._psp_bwd(dx)
+    if self.p.fov:
+      dx, _ = self._layer_bwd(arch.FOV_SCOPE, dx)
     dx, _ = self._layer_bwd('feature_extractor/extension/decrease_fdims', dx)
     for u in reversed(arch.units()):
       dx = self._unit_bwd(dx, u)
@@ -783,6 +817,20 @@ class TrainNetwork(Network):
     ws.grads[self.p.n_conv_pad:self.p.n_conv_pad + n] = ws.stat[2 * n:3 * n].to(torch.float32)
     ws.grads[self.p.n_conv_pad + n:self.p.n_conv_pad + 2 * n] = ws.stat[3 * n:4 * n].to(torch.float32)
     return ws.grads
+
+  def _psp_bwd(self, dout):
+    """Backward of _psp: the 1x1 fusion conv, then per branch ResizeBilinearGrad -> conv/BN backward ->
+    AvgPoolGrad accumulated onto the concatenation's pass-through slice."""
+    dcat, _ = self._layer_bwd(arch.PSP_SCOPES[4], dout)       # [N, h, w, 5d]
+    N, h, w, d5 = dcat.shape
+    d = d5 // 5
+    dbottom = dcat[..., :d].contiguous()
+    for i, (sc, (kh, kw, pshape)) in enumerate(zip(arch.PSP_SCOPES[:4], self._psp_geom)):
+      dc = torch.empty(pshape, dtype=dcat.dtype, device=self.dev)
+      ops.resize_bilinear_bwd(dcat[..., (i + 1) * d:(i + 2) * d], dc)
+      dpooled, _ = self._layer_bwd(sc, dc)
+      ops.avgpool_valid_bwd(dpooled, dbottom, kh, kw, accumulate=True)
+    return dbottom
 
   def loss_and_grad(self, logits, labels, H, W, l2_coef=0.1, grad_scale=1.0):
     """define_losses (TRAIN) + its gradient wrt the low-res logits, one fused kernel + finalize."""

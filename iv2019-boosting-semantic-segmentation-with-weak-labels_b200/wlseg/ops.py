@@ -63,6 +63,10 @@ _SIGNATURES = {
                                               _vp]),
     'wlseg_maxpool_same_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                               _c_int, _vp]),
+    'wlseg_avgpool_valid_fwd': (ctypes.c_int, [_vp, _vp] + [_c_int] * 9 + [_vp]),
+    'wlseg_avgpool_valid_bwd': (ctypes.c_int, [_vp, _vp] + [_c_int] * 8 + [_vp]),
+    'wlseg_resize_bilinear_fwd': (ctypes.c_int, [_vp, _vp] + [_c_int] * 8 + [_vp]),
+    'wlseg_resize_bilinear_bwd': (ctypes.c_int, [_vp, _vp] + [_c_int] * 8 + [_vp]),
     'wlseg_rasterize_bbox_labels': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     'wlseg_tile_image_labels': (ctypes.c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
     'wlseg_head_fwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -304,6 +308,47 @@ def maxpool_same_bwd(x, dy, dx, ksize, stride, argmax=None):
   N, H, W, C = dx.shape
   _check(lib().wlseg_maxpool_same_bwd(_ptr(x), _ptr(argmax), _ptr(dy), _ptr(dx), N, H, W, C, ksize, stride,
                                       dtype_code(dx.dtype), _stream()), 'wlseg_maxpool_same_bwd')
+  _count()
+  return dx
+
+
+# ------------------------------------------------------------------------------------ pyramid (PSP) module
+def avgpool_valid_fwd(x, y, kh, kw):
+  """VALID average pooling with stride == kernel (the PSP bins); y: [N, H // kh, W // kw, C]."""
+  N, H, W, C = x.shape
+  assert x.is_contiguous() and y.is_contiguous() and tuple(y.shape) == (N, (H - kh) // kh + 1, (W - kw) // kw + 1, C)
+  _check(lib().wlseg_avgpool_valid_fwd(_ptr(x), _ptr(y), N, H, W, C, kh, kw, kh, kw, dtype_code(x.dtype), _stream()),
+         'wlseg_avgpool_valid_fwd')
+  _count()
+  return y
+
+
+def avgpool_valid_bwd(dy, dx, kh, kw, accumulate=False):
+  N, H, W, C = dx.shape
+  assert dy.is_contiguous() and dx.is_contiguous()
+  _check(lib().wlseg_avgpool_valid_bwd(_ptr(dy), _ptr(dx), N, H, W, C, kh, kw, int(accumulate), dtype_code(dx.dtype),
+                                       _stream()), 'wlseg_avgpool_valid_bwd')
+  _count()
+  return dx
+
+
+def resize_bilinear_fwd(x, y):
+  """x [N, h, w, C] dense -> y [N, H, W, C], possibly a channel slice of a wider tensor (pixel pitch)."""
+  N, h, w, C = x.shape
+  _, H, W, _ = y.shape
+  assert x.is_contiguous() and y.shape[3] == C and y.stride(3) == 1
+  _check(lib().wlseg_resize_bilinear_fwd(_ptr(x), _ptr(y), N, h, w, C, H, W, y.stride(2), dtype_code(x.dtype), _stream()),
+         'wlseg_resize_bilinear_fwd')
+  _count()
+  return y
+
+
+def resize_bilinear_bwd(dy, dx):
+  N, h, w, C = dx.shape
+  _, H, W, _ = dy.shape
+  assert dx.is_contiguous() and dy.shape[3] == C and dy.stride(3) == 1
+  _check(lib().wlseg_resize_bilinear_bwd(_ptr(dy), _ptr(dx), N, h, w, C, H, W, dy.stride(2), dtype_code(dx.dtype), _stream()),
+         'wlseg_resize_bilinear_bwd')
   _count()
   return dx
 

@@ -99,8 +99,10 @@ class SemanticSegmentation(object):
     if getattr(s, 'name_feature_extractor', 'resnet_v1_50') == 'resnet_v1_101':
       # code/estimator/define_estimator_hierarchical.py:57-61
       raise NotImplementedError('Use of resnet_v1_101 as base feature extractor is not yet implemented.')
-    if getattr(s, 'psp_module', False):
-      raise NotImplementedError('--psp_module is not implemented yet in the B200 path.')
+    if bool(getattr(s, 'fov_expansion_kernel_rate', 0)) != bool(getattr(s, 'fov_expansion_kernel_size', 0)):
+      # _validate_params, code/models/resnet50_extended_model_hierarchical.py:271-276
+      raise ValueError('One of params.{fov_expansion_kernel_rate, fov_expansion_kernel_size} '
+                       'is set. In order to take effect both should be set.')
     if getattr(s, 'upsampling_method', 'bilinear') != 'bilinear' or getattr(s, 'norm_layer', 'batch') != 'batch':
       raise NotImplementedError('only --upsampling_method bilinear and --norm_layer batch are implemented.')
     self._estimator = est.Estimator(s, self._hier, device=getattr(s, 'device', 'cuda'))

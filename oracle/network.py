@@ -25,8 +25,17 @@ _BLOCKS = [('block1', 64, 3, 2), ('block2', 128, 4, 2), ('block3', 256, 6, 2), (
 _RES = 'feature_extractor/base/resnet_v1_50'
 
 
-def conv_specs(dataset='cityscapes', feature_dims_decreased=256):
-  """Ordered {scope: (kh, kw, cin, cout)} for the 66 convs of the default model."""
+PSP_SCOPES = tuple('feature_extractor/pyramid_module/Conv' + ('' if i == 0 else f'_{i}') for i in range(5))
+PSP_BINS = (1, 2, 3, 6)
+
+
+FOV_SCOPE = 'feature_extractor/extension/increase_fov'
+
+
+def conv_specs(dataset='cityscapes', feature_dims_decreased=256, psp=False, fov=None):
+  """Ordered {scope: (kh, kw, cin, cout)} for the 66 convs of the default model (+5 with --psp_module:
+  slim's default scopes Conv, Conv_1 .. Conv_4 under feature_extractor/pyramid_module,
+  resnet50_extended_model_hierarchical.py:55-57,186-207)."""
   c1, cv, ch = TABLES[dataset]['head_widths']
   specs = collections.OrderedDict()
   specs[f'{_RES}/conv1'] = (7, 7, 3, 64)
@@ -42,6 +51,12 @@ def conv_specs(dataset='cityscapes', feature_dims_decreased=256):
       cin = base * 4
   d = feature_dims_decreased
   specs['feature_extractor/extension/decrease_fdims'] = (1, 1, cin, d)
+  if fov:  # --fov_expansion_kernel_size / _rate (resnet50_extended_feature_extractor.py:44-49)
+    specs[FOV_SCOPE] = (fov[0], fov[0], d, d)
+  if psp:
+    for sc in PSP_SCOPES[:4]:
+      specs[sc] = (1, 1, d, d)
+    specs[PSP_SCOPES[4]] = (1, 1, 5 * d, d)
   for br in ('l1_features', 'l2_vehicle_features', 'l2_human_features'):
     sc = f'adaptation_module/{br}/bottleneck_v1'
     specs[f'{sc}/conv1'] = (1, 1, d, d)
@@ -53,7 +68,7 @@ def conv_specs(dataset='cityscapes', feature_dims_decreased=256):
   return specs
 
 
-def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False):
+def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False, psp=False, fov=None):
   """Random init as the reference's arg scope does (variance scaling conv
   kernels, gamma=1, beta=0, moving_mean=0, moving_var=1;
   resnet50_extended_model_hierarchical.py:335-340).  `randomize_bn=True`
@@ -63,7 +78,7 @@ def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False):
   moving stats 0/1 is otherwise an identity and the residual sums grow)."""
   g = torch.Generator().manual_seed(seed)
   params = collections.OrderedDict()
-  for scope, shape in conv_specs(dataset).items():
+  for scope, shape in conv_specs(dataset, psp=psp, fov=fov).items():
     params[f'{scope}/weights'] = tfops.variance_scaling_trunc_normal(shape, g)
     c = shape[3]
     if randomize_bn:
@@ -110,7 +125,7 @@ class Net:
 
   storage='bf16' restates the SAME graph with the storage roundings of the product path made
   explicit (images, conv kernels, pre-BN conv outputs and activations rounded to bf16 with
-  straight-through gradients; batch statistics taken from the fp32 conv output; activation and
+  straight-through gradients; batch statistics taken from the bf16-stored conv output; activation and
   pre-BN gradients rounded to bf16; the logits layers stay fp32).  A train-mode batch-norm network
   at random init amplifies a 1e-3 perturbation by ~10^2 (measured: tests/test_gpu_train.py), so
   comparing a bf16 pipeline with the fp32 graph end to end says nothing; comparing it with the
@@ -121,8 +136,11 @@ class Net:
   moving statistics in `self.new_moving`.
   """
 
-  def __init__(self, params, dataset='cityscapes', training=False, bn_decay=0.9, eps=1e-5, storage='fp32'):
+  def __init__(self, params, dataset='cityscapes', training=False, bn_decay=0.9, eps=1e-5, storage='fp32',
+               psp=False, fov=None):
     assert storage in ('fp32', 'bf16')
+    self.psp = psp
+    self.fov = fov  # (kernel size, dilation rate) of extension/increase_fov, or None
     self.storage = storage
     self.p = params
     self.dataset = dataset
@@ -163,9 +181,11 @@ class Net:
       z = self._qg(z)
       bn = f'{scope}/BatchNorm'
       n = z.shape[0] * z.shape[1] * z.shape[2]
-      mean = z.mean(dim=(0, 1, 2))
-      var = ((z - mean) ** 2).mean(dim=(0, 1, 2))
       zs = z if fp32_out else self._q(z)
+      # the product takes the batch statistics of the STORED (bf16) conv output - the tensor the
+      # normalisation is applied to (csrc/conv_igemm_sm100.cu); gradients pass straight through the rounding
+      mean = zs.mean(dim=(0, 1, 2))
+      var = ((zs - mean) ** 2).mean(dim=(0, 1, 2))
       y = (zs - mean) * torch.rsqrt(var + self.eps) * self.p[f'{bn}/gamma'] + self.p[f'{bn}/beta']
       with torch.no_grad():
         self.new_moving[f'{bn}/moving_mean'] = self.p[f'{bn}/moving_mean'] - (1.0 - self.bn_decay) * (
@@ -215,7 +235,27 @@ class Net:
       self.taps[name] = x
     x = self._conv_bn(x, 'feature_extractor/extension/decrease_fdims')
     self.taps['decrease_fdims'] = x
+    if self.fov:
+      # slim.conv2d(fe, C, kernel_size, rate=rate): stride 1, SAME padding, BN + ReLU from the arg scope
+      x = self._conv_bn(x, FOV_SCOPE, rate=self.fov[1])
+      self.taps['increase_fov'] = x
+    if self.psp:
+      x = self._psp(x)
+      self.taps['pyramid_module'] = x
     return x
+
+  def _psp(self, bottom):
+    """_create_psp_module (resnet50_extended_model_hierarchical.py:186-207): VALID average pooling into
+    bins {1, 2, 3, 6} (kernel = stride = feature size // bins), 1x1 conv (+BN+ReLU from the arg scope),
+    bilinear align_corners back to the feature size, concat with the input, 1x1 conv."""
+    h, w = bottom.shape[1], bottom.shape[2]
+    outs = [bottom]
+    for sc, b in zip(PSP_SCOPES[:4], PSP_BINS):
+      k = (h // b, w // b)
+      pooled = self._qg(self._q(tfops.avg_pool_valid(bottom, k, k)))
+      c = self._conv_bn(pooled, sc)
+      outs.append(self._qg(self._q(tfops.resize_bilinear(c, h, w, align_corners=True))))
+    return self._conv_bn(torch.cat(outs, -1), PSP_SCOPES[4])
 
   def lowres_logits(self, images):
     f = self.features(images)

@@ -79,6 +79,14 @@ def max_pool_same(x, k, stride):
   return y.permute(0, 2, 3, 1)
 
 
+def avg_pool_valid(x, ksize, stride):
+  """slim.layers.avg_pool2d (default padding='VALID'): windows that do not fit are dropped.
+  code/models/resnet50_extended_model_hierarchical.py:191-200 (the PSP bins)."""
+  xn = x.permute(0, 3, 1, 2)
+  y = F.avg_pool2d(xn, kernel_size=tuple(ksize), stride=tuple(stride), padding=0)
+  return y.permute(0, 2, 3, 1)
+
+
 def batch_norm(x, gamma, beta, moving_mean, moving_var, training, decay=0.9, eps=1e-5):
   """tf.contrib.layers.batch_norm (fused, NHWC) [TF-1.12].
 

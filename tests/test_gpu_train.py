@@ -160,8 +160,9 @@ def _close(got, ref, tol, what):
   return err
 
 
-@pytest.mark.parametrize('dataset', ['cityscapes', 'vistas'])
-def test_train_step_bf16_layerwise(cuda, dataset):
+@pytest.mark.parametrize('dataset,psp,fov', [('cityscapes', False, None), ('vistas', False, None),
+                                             ('cityscapes', True, (3, 2))])
+def test_train_step_bf16_layerwise(cuda, dataset, psp, fov):
   """bf16 product path, every layer checked IN SITU against a plain fp32 restatement fed with the
   pipeline's own (bf16) inputs: forward conv, batch statistics, BN+residual+ReLU, BN backward,
   filter gradient, data gradient (+ fused gradient fan-in).  End-to-end comparison with the oracle is
@@ -171,8 +172,8 @@ def test_train_step_bf16_layerwise(cuda, dataset):
   outputs (dw, dgamma, dbeta, statistics)."""
   from wlseg import hierarchy, network, problem_defs
   hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
-  tf_params = onet.init_params(dataset, seed=11, randomize_bn=True, tame=True)
-  params = network.Params(hier, cuda)
+  tf_params = onet.init_params(dataset, seed=11, randomize_bn=True, tame=True, psp=psp, fov=fov)
+  params = network.Params(hier, cuda, psp=psp, fov=fov)   # + the pyramid module and increase_fov layers
   params.load_tf_dict(tf_params)
   net = network.TrainNetwork(params, dtype=torch.bfloat16)
   net.keep = True
@@ -198,8 +199,11 @@ def test_train_step_bf16_layerwise(cuda, dataset):
     e = {}
     e['z'] = _close(zq, z_ref.detach(), 1e-2, f'{spec.scope} conv output')
     n = z_ref.shape[0] * z_ref.shape[1] * z_ref.shape[2]
-    mean_ref = z_ref.detach().double().mean((0, 1, 2))
-    var_ref = z_ref.detach().double().var((0, 1, 2), unbiased=False)
+    # batch statistics are DEFINED over the stored (bf16-rounded) conv output, the tensor the normalisation
+    # is applied to; with few samples per channel (the 1-bin pyramid branch has
+    # n = batch size) the statistics of the unrounded z_ref differ by the rounding itself
+    mean_ref = zq.double().mean((0, 1, 2))
+    var_ref = zq.double().var((0, 1, 2), unbiased=False)
     mean = ws.view(ws.bn, 2, off, K).cpu()
     invstd = ws.view(ws.bn, 3, off, K).cpu()
     assert torch.allclose(mean.double(), mean_ref, rtol=2e-3, atol=2e-3 * float(var_ref.sqrt().max())), spec.scope
