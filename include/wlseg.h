@@ -219,6 +219,25 @@ int wlseg_head_fwd(const wlseg_hierarchy* hier, const float* logits, int32_t log
                    wlseg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Prediction post-processing (estimator/define_estimator_hierarchical.py:530-571 `_resize_predictions`,
+ * :573-630 `_replace_voids`), used by the EVAL branch when labels and network differ in size and by the
+ * PREDICT branch for --height_system / --width_system or the raw image size (:219-232).
+ *   probabilities fp32 [N, h, w, C] -> [N, H, W, C]: tf.image.resize_images bilinear, align_corners=True
+ *   decisions int32 [N, h, w] -> [N, H, W]: NEAREST_NEIGHBOR, align_corners=True, in = min(roundf(out * scale), in - 1)
+ *   replace_voids: decisions (in place, n_pixels of them) equal to void_cid are recomposed from the three
+ *   probability maps with every head restricted to its non-void classes (its last channel is void): the
+ *   reference's "runner-up of top_k(probs, 2) where the decision is void", applied per head.  The reference
+ *   itself stops at the key-set assert of :589-592 on this model.
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_resize_probabilities(const float* x, float* y, int32_t N, int32_t h, int32_t w, int32_t C, int32_t H,
+                               int32_t W, wlseg_stream_t stream);
+int wlseg_resize_decisions(const int32_t* x, int32_t* y, int32_t N, int32_t h, int32_t w, int32_t H, int32_t W,
+                           wlseg_stream_t stream);
+int wlseg_replace_voids(const wlseg_hierarchy* hier, const float* l1_probs, const float* l2v_probs,
+                        const float* l2h_probs, int32_t* decisions, int64_t n_pixels, int32_t void_cid,
+                        wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Hierarchical strong + weak masked cross-entropy, forward and backward fused with the
  * bilinear upsample and its transpose (replaces estimator/define_losses_hierarchical.py:97-203
  * and ResizeBilinearGrad).  Batch order: n_strong images with per-pixel labels int32 [.,H,W],

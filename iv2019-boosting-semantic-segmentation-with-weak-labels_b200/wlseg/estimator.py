@@ -58,17 +58,23 @@ def mean_iou_from_cm(cm, num_classes):
 
 def resize_decisions_nearest(decs, new_h, new_w):
   """`_resize_predictions` for decisions: NEAREST_NEIGHBOR, align_corners=True, roundf
-  (define_estimator_hierarchical.py:559-563).  Identity at every BASELINE configuration; index
-  plumbing otherwise."""
-  n, h, w = decs.shape
-  if (h, w) == (new_h, new_w):
-    return decs
-  sy = (h - 1) / (new_h - 1) if new_h > 1 else h / new_h
-  sx = (w - 1) / (new_w - 1) if new_w > 1 else w / new_w
-  dev = decs.device
-  yi = torch.clamp(torch.floor(torch.arange(new_h, device=dev, dtype=torch.float32) * np.float32(sy) + 0.5).long(), max=h - 1)
-  xi = torch.clamp(torch.floor(torch.arange(new_w, device=dev, dtype=torch.float32) * np.float32(sx) + 0.5).long(), max=w - 1)
-  return decs[:, yi][:, :, xi].contiguous()
+  (define_estimator_hierarchical.py:559-563).  Identity at every BASELINE configuration."""
+  return ops.resize_decisions(decs, new_h, new_w)
+
+
+def resize_predictions(predictions, new_h, new_w):
+  """`_resize_predictions` (define_estimator_hierarchical.py:530-571): the three probability maps bilinearly,
+  the decisions by nearest neighbour, both with align_corners=True; other keys pass through."""
+  out = dict(predictions)
+  for k in ('l1_probabilities', 'l2_vehicle_probabilities', 'l2_human_probabilities'):
+    if k in out:
+      out[k] = ops.resize_probabilities(out[k], new_h, new_w)
+  if 'decisions' in out:
+    out['decisions'] = ops.resize_decisions(out['decisions'], new_h, new_w)
+  return out
+
+
+_PROB_KEYS = ('l1_probabilities', 'l2_vehicle_probabilities', 'l2_human_probabilities')
 
 
 class _Prefetcher:
@@ -214,9 +220,13 @@ class Estimator:
     pre = _Prefetcher(batches, dev)
     steps = 0
     host_cm = torch.zeros((num_classes, num_classes), dtype=torch.int64).pin_memory()
+    replace_voids = bool(getattr(self.settings, 'replace_voids', False))
     for features, labels in pre:
-      out = self.net.predict(features['proimages'], want=('decisions',))
+      out = self.net.predict(features['proimages'], want=('decisions',) + (_PROB_KEYS if replace_voids else ()))
       lab = labels['prolabels']
+      if replace_voids:
+        # EVAL order of the reference: (cid map ->) _replace_voids -> _resize_predictions (:175-183)
+        ops.replace_voids(self.net.hstruct, *(out[k] for k in _PROB_KEYS), out['decisions'], self.hier.void_cid)
       decs = resize_decisions_nearest(out['decisions'], lab.shape[1], lab.shape[2])
       ops.confmat_accumulate(lab.contiguous(), decs, num_classes, cm, lut_t, invalid)
       # the step's result (running metric) goes back to the host every step, asynchronously
@@ -234,13 +244,24 @@ class Estimator:
 
   # ---- PREDICT ------------------------------------------------------------------------------------
   def predict(self, batches, predict_keys):
-    """define_estimator PREDICT branch: yields one dict per example with the requested keys."""
+    """define_estimator PREDICT branch (define_estimator_hierarchical.py:204-237): yields one dict per example
+    with the requested keys, resized to (height_system, width_system) - or, when either is unset, to the size
+    of the raw image (:219-229) - and, with --replace_voids, void decisions replaced afterwards (:232-233)."""
     want = tuple(k for k in predict_keys if k not in ('rawimages', 'rawimagespaths'))
+    s = self.settings
+    replace_voids = bool(getattr(s, 'replace_voids', False))
+    need = tuple(dict.fromkeys(want + (_PROB_KEYS + ('decisions',) if replace_voids else ())))
     for features, _ in batches:
       pro = features['proimages']
       if not pro.is_cuda:
         pro = pro.to(self.device, non_blocking=True)
-      out = self.net.predict(pro, want=want)
+      out = self.net.predict(pro, want=need)
+      new_size = (getattr(s, 'height_system', None), getattr(s, 'width_system', None))
+      if not all(new_size):
+        new_size = tuple(features['rawimages'].shape[1:3]) if 'rawimages' in features else tuple(pro.shape[1:3])
+      out = resize_predictions(out, int(new_size[0]), int(new_size[1]))
+      if replace_voids:
+        ops.replace_voids(self.net.hstruct, *(out[k] for k in _PROB_KEYS), out['decisions'], self.hier.void_cid)
       host = {k: out[k].cpu().numpy() for k in want}
       n = pro.shape[0]
       for i in range(n):

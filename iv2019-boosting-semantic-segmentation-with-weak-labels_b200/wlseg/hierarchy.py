@@ -100,6 +100,11 @@ class Hierarchy:
     return self.C1, self.Cv, self.Ch
 
   @property
+  def void_cid(self):
+    """Common (strong-label) id of the void class: the last one."""
+    return self.num_classes - 1
+
+  @property
   def total_channels(self):
     return self.C1 + self.Cv + self.Ch
 

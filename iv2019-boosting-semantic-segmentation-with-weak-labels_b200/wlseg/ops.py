@@ -71,6 +71,9 @@ _SIGNATURES = {
     'wlseg_tile_image_labels': (ctypes.c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
     'wlseg_head_fwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'wlseg_resize_probabilities': (ctypes.c_int, [_vp, _vp] + [_c_int] * 6 + [_vp]),
+    'wlseg_resize_decisions': (ctypes.c_int, [_vp, _vp] + [_c_int] * 5 + [_vp]),
+    'wlseg_replace_voids': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _vp, _vp, _vp, _c_i64, _c_int, _vp]),
     'wlseg_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                           _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'wlseg_loss_finalize': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _vp, _c_f, _c_f, _vp, _c_int, _c_i64, _vp,
@@ -388,6 +391,45 @@ def head_fwd(hier, logits, H, W, decisions=None, l1_decisions=None, l2v_decision
                               _ptr(l1_decisions), _ptr(l2v_decisions), _ptr(l2h_decisions), _ptr(l1_probs),
                               _ptr(l2v_probs), _ptr(l2h_probs), _ptr(fullres_logits), _stream()), 'wlseg_head_fwd')
   _count()
+
+
+def resize_probabilities(probs, H, W):
+  """`_resize_predictions` for a probability map (define_estimator_hierarchical.py:552-558): bilinear,
+  align_corners=True.  fp32 [N, h, w, C] -> [N, H, W, C]; the same tensor when the size is unchanged."""
+  N, h, w, C = probs.shape
+  if (h, w) == (H, W):
+    return probs
+  assert probs.dtype == torch.float32 and probs.is_contiguous()
+  out = torch.empty((N, H, W, C), dtype=torch.float32, device=probs.device)
+  _check(lib().wlseg_resize_probabilities(_ptr(probs), _ptr(out), N, h, w, C, H, W, _stream()),
+         'wlseg_resize_probabilities')
+  _count()
+  return out
+
+
+def resize_decisions(decs, H, W):
+  """`_resize_predictions` for decisions (define_estimator_hierarchical.py:559-563): NEAREST_NEIGHBOR,
+  align_corners=True.  int32 [N, h, w] -> [N, H, W]."""
+  N, h, w = decs.shape
+  if (h, w) == (H, W):
+    return decs
+  assert decs.dtype == torch.int32 and decs.is_contiguous()
+  out = torch.empty((N, H, W), dtype=torch.int32, device=decs.device)
+  _check(lib().wlseg_resize_decisions(_ptr(decs), _ptr(out), N, h, w, H, W, _stream()), 'wlseg_resize_decisions')
+  _count()
+  return out
+
+
+def replace_voids(hier, l1_probs, l2v_probs, l2h_probs, decisions, void_cid):
+  """`_replace_voids` (define_estimator_hierarchical.py:573-630) for the hierarchical classifier, in place."""
+  n = decisions.numel()
+  for t, c in ((l1_probs, hier.C1), (l2v_probs, hier.Cv), (l2h_probs, hier.Ch)):
+    assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n * c
+  assert decisions.dtype == torch.int32 and decisions.is_contiguous()
+  _check(lib().wlseg_replace_voids(ctypes.byref(hier), _ptr(l1_probs), _ptr(l2v_probs), _ptr(l2h_probs), _ptr(decisions),
+                                   n, int(void_cid), _stream()), 'wlseg_replace_voids')
+  _count()
+  return decisions
 
 
 def loss_fwd_bwd(hier, logits, H, W, strong_labels, bbox_labels, image_labels, sums, counts, dlogits):

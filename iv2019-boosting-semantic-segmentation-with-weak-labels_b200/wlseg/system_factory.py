@@ -187,8 +187,6 @@ class SemanticSegmentation(object):
     if void_exists and not s.train_void_class:
       labels = labels[:-1]
 
-    if getattr(s, 'replace_voids', False):
-      raise NotImplementedError('--replace_voids asserts upstream for this model and is not implemented.')
     if getattr(s, 'preserve_aspect_ratio', False):
       raise NotImplementedError('evaluation with preserving aspect ratio is not implemented.')
 

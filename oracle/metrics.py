@@ -31,6 +31,29 @@ def map_probabilities_to_new_cids(probs, old_cids2new_cids):
   return out
 
 
+def replace_voids_hierarchical(l1_probs, l2v_probs, l2h_probs, decisions, tables):
+  """`_replace_voids` (code/estimator/define_estimator_hierarchical.py:573-630) carried over to the
+  hierarchical classifier.  The reference takes tf.nn.top_k(probs, 2) of a flat classifier whose LAST
+  channel is void and, where the decision is void, the runner-up `indices[..., 1]` (:611-622); on this
+  model it stops at its own key-set assert (:589-592: the l2_human_* keys are not in `supported_keys`).
+  Per head the same rule reads: a head that chose its void channel (its last one) takes its best non-void
+  class instead; the pixel's decision is then composed again
+  (code/models/resnet50_extended_model_hierarchical.py:95-117).  Only void decisions change.
+  `tables` is oracle.tables.TABLES[dataset]."""
+  p1, pv, ph = (np.asarray(a, dtype=np.float32) for a in (l1_probs, l2v_probs, l2h_probs))
+  decs = np.asarray(decisions).astype(np.int32).copy()
+  l1_to_common = np.asarray(tables['l1_cids2common_cids'], dtype=np.int32)
+  veh_to_common = np.asarray(tables['l2_vehicle_cids2common_cids'], dtype=np.int32)
+  hum_to_common = np.asarray(tables['l2_human_cids2common_cids'], dtype=np.int32)
+  void_cid = int(l1_to_common[-1])
+  d1 = np.argmax(p1[..., :-1], -1)   # np.argmax: first maximum, as tf.argmax / top_k
+  dv = np.argmax(pv[..., :-1], -1)
+  dh = np.argmax(ph[..., :-1], -1)
+  new = np.where(d1 == tables['cid_l1_vehicle'], veh_to_common[dv],
+                 np.where(d1 == tables['cid_l1_human'], hum_to_common[dh], l1_to_common[d1]))
+  return np.where(decs == void_cid, new, decs).astype(np.int32)
+
+
 def confusion_matrix(labels, decisions, num_classes):
   """[TF-1.12] metrics_impl._streaming_confusion_matrix update for one batch:
   cm[label, prediction] += 1 over all pixels

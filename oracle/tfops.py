@@ -176,9 +176,10 @@ def resize_nearest(x, out_h, out_w, align_corners=True):
   ys = torch.arange(out_h, dtype=torch.float32) * sh
   xs = torch.arange(out_w, dtype=torch.float32) * sw
   if align_corners:
-    # roundf: half away from zero (coords are non-negative)
-    yi = torch.floor(ys + 0.5).long()
-    xi = torch.floor(xs + 0.5).long()
+    # roundf: half away from zero (coords are non-negative); floor(x) + (x - floor(x) >= 0.5) is exact in
+    # fp32 where floor(x + 0.5) can round a fraction just below one half upwards
+    yi = (torch.floor(ys) + (ys - torch.floor(ys) >= 0.5).float()).long()
+    xi = (torch.floor(xs) + (xs - torch.floor(xs) >= 0.5).float()).long()
   else:
     yi = torch.floor(ys).long()
     xi = torch.floor(xs).long()

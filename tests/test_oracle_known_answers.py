@@ -213,3 +213,41 @@ def test_cross_replica_batch_norm_restatement():
   n_local = 2 * 3 * 5
   assert torch.allclose(new_mv, mv - 0.1 * (mv - ref_var * (n_local - 1) / n_local), rtol=1e-5, atol=1e-6)
   assert not torch.allclose(new_mv, ref_mv, rtol=1e-4)  # it is NOT the single-process update
+
+
+def test_replace_voids_hierarchical_known_answers():
+  """`_replace_voids` (define_estimator_hierarchical.py:573-630) per head on hand-made probabilities:
+  only void decisions change; an L1 void falls to the L1 runner-up (composed through L2 when that is a
+  super-class); an L2 void under a vehicle / human decision falls to that head's runner-up."""
+  import numpy as np
+  from oracle import metrics as ometrics
+  from oracle.tables import TABLES
+  t = TABLES['cityscapes']
+  C1, Cv, Ch = t['head_widths']
+
+  def onehotish(c, idx, second=None):
+    p = np.full(c, 0.01, np.float32)
+    p[idx] = 0.6
+    if second is not None:
+      p[second] = 0.3
+    return p / p.sum()
+  # pixel 0: road (0), not void -> unchanged.  pixel 1: L1 void, runner-up sky-ish class 10 -> 10.
+  # pixel 2: L1 void, runner-up vehicle (12), vehicle head best non-void = 2 -> common 15.
+  # pixel 3: L1 vehicle, vehicle head void (6), runner-up 4 -> common 17.
+  # pixel 4: L1 human (11), human head void (2), runner-up 1 -> common 12 (rider).
+  p1 = np.stack([onehotish(C1, 0), onehotish(C1, 13, 10), onehotish(C1, 13, 12), onehotish(C1, 12), onehotish(C1, 11)])
+  pv = np.stack([onehotish(Cv, 6), onehotish(Cv, 6), onehotish(Cv, 6, 2), onehotish(Cv, 6, 4), onehotish(Cv, 0)])
+  ph = np.stack([onehotish(Ch, 2), onehotish(Ch, 2), onehotish(Ch, 2), onehotish(Ch, 0), onehotish(Ch, 2, 1)])
+  decs = np.array([0, 19, 19, 19, 19], np.int32)
+  got = ometrics.replace_voids_hierarchical(p1[None, None], pv[None, None], ph[None, None], decs[None, None], t)
+  assert got.reshape(-1).tolist() == [0, 10, 15, 17, 12]
+
+
+def test_resize_nearest_is_roundf():
+  """[TF-1.12] ResizeNearestNeighbor, align_corners: src = min(roundf(dst * scale), in - 1); a 4 -> 7 resize
+  has scale 0.5: dst 1 -> roundf(0.5) = 1 (half away from zero), dst 3 -> roundf(1.5) = 2."""
+  import torch
+  from oracle import tfops
+  x = torch.arange(4, dtype=torch.int32).view(1, 4, 1)
+  got = tfops.resize_nearest(x, 7, 1, align_corners=True).reshape(-1).tolist()
+  assert got == [0, 1, 1, 2, 2, 3, 3]
