@@ -13,7 +13,7 @@ import os
 import numpy as np
 import torch
 
-from wlseg import network, ops
+from wlseg import checkpoints, network, ops
 
 
 def _replacevoids(mappings):
@@ -143,7 +143,7 @@ class Estimator:
     self.last_h2d_bytes = 0
     self.last_d2h_bytes = 0
 
-  # ---- checkpoints (torch files keyed by TF variable names) -------------------------------------
+  # ---- checkpoints ({TF variable name: tensor} files, wlseg/checkpoints.py) ---------------------------
   def latest_checkpoint(self, log_dir):
     cands = glob.glob(os.path.join(log_dir, 'model.ckpt-*.pt'))
     if not cands:
@@ -151,22 +151,39 @@ class Estimator:
     return max(cands, key=lambda p: int(p.rsplit('-', 1)[1].split('.')[0]))
 
   def save(self, log_dir):
-    os.makedirs(log_dir, exist_ok=True)
+    """train_saver (code/estimator/define_savers.py:3-36): every global variable - model variables, Momentum
+    slots, EMA shadows, global_step - under its TF name."""
     path = os.path.join(log_dir, f'model.ckpt-{self.global_step}.pt')
-    torch.save({'global_step': self.global_step, 'variables': self.params.to_tf_dict()}, path)
-    return path
+    return checkpoints.save_file(path, checkpoints.export_train_state(self.params, getattr(self, 'trainer', None)),
+                                 self.global_step)
 
-  def restore(self, path):
-    blob = torch.load(path, map_location='cpu')
-    self.params.load_tf_dict(blob['variables'])
-    self.global_step = int(blob.get('global_step', 0))
-
-  def initialize(self, ckpt_path=None, log_dir=None, seed=0):
-    path = ckpt_path or (self.latest_checkpoint(log_dir) if log_dir else None)
-    if path:
-      self.restore(path)
+  def restore(self, path, for_training=False):
+    """EVAL / PREDICT: predict_saver (define_savers.py:38-66; --restore_emas reads the EMA shadows into the
+    model variables).  TRAIN: continue from log_dir with the optimizer / EMA slots."""
+    variables, step = checkpoints.load_file(path)
+    if for_training:
+      self._resume = variables   # slots are imported once the trainer exists
+      self.params.load_tf_dict(variables)
     else:
-      self.params.init_random(seed)  # no checkpoint: random init (BASELINE configs use random weights)
+      self.params.load_tf_dict(checkpoints.select_for_predict(
+          self.params, variables, restore_emas=bool(getattr(self.settings, 'restore_emas', False))))
+    self.global_step = step
+
+  def initialize(self, ckpt_path=None, log_dir=None, seed=0, for_training=False):
+    """TRAIN: latest checkpoint of log_dir, else warm start from --init_ckpt_path when that file exists
+    (replace_initializers, code/estimator/define_initializers.py:72-131), else random init.  EVAL / PREDICT:
+    --ckpt_path or the latest checkpoint of log_dir."""
+    path = ckpt_path or (self.latest_checkpoint(log_dir) if log_dir else None)
+    self._resume = None
+    if path:
+      self.restore(path, for_training=for_training)
+    else:
+      self.params.init_random(seed)  # BASELINE configs use random weights
+      init = getattr(self.settings, 'init_ckpt_path', None)
+      if for_training and init and os.path.isfile(init):
+        variables, _ = checkpoints.load_file(init)
+        mapping = checkpoints.warm_start(self.params, variables, psp_module=getattr(self.settings, 'psp_module', False))
+        print(f'initialised {len(mapping)} variables from {init}', flush=True)
     self.net = network.Network(self.params, dtype=self.dtype,
                                bn_decay=getattr(self.settings, 'batch_norm_decay', 0.9))
     return path
@@ -185,6 +202,9 @@ class Estimator:
       self.trainer = wtrainer.Trainer(self.params, s, dtype=self.dtype, rank=getattr(s, 'rank', 0),
                                       world_size=getattr(s, 'world_size', 1) if getattr(s, 'distribute', False) else 1)
       self.trainer.global_step = self.global_step
+      if getattr(self, '_resume', None) is not None:
+        checkpoints.import_train_state(self.params, self.trainer, self._resume)
+        self._resume = None
     tr = self.trainer
     pre = _Prefetcher(batches, dev)
     host = torch.zeros((max(1, max_steps), 6), dtype=torch.float32).pin_memory()

@@ -133,6 +133,32 @@ class Params:
       out[f'{s.scope}/BatchNorm/moving_variance'] = self.moving_var(s.scope).cpu().clone()
     return out
 
+  def arena_to_tf_dict(self, arena):
+    """An arena with the master layout (momentum, EMA shadows, gradients) as {model variable name: tensor},
+    conv kernels back in TF's HWIO layout (wlseg/checkpoints.py names the slots)."""
+    out = {}
+    for s in self.specs:
+      out[f'{s.scope}/weights'] = self._wview(arena, s.scope).permute(1, 2, 3, 0).contiguous().cpu()
+      out[f'{s.scope}/BatchNorm/gamma'] = self._cview(arena, self.n_conv_pad, s.scope).cpu().clone()
+      out[f'{s.scope}/BatchNorm/beta'] = self._cview(arena, self.n_conv_pad + self.n_chan_pad, s.scope).cpu().clone()
+    return out
+
+  def load_into_arena(self, arena, named):
+    """Inverse of arena_to_tf_dict for the names present in `named`; the rest of the arena is kept."""
+    host = arena.cpu()
+    for s in self.specs:
+      t = named.get(f'{s.scope}/weights')
+      if t is not None:
+        assert tuple(t.shape) == (s.R, s.S, s.C, s.K), (s.scope, tuple(t.shape))
+        o = self.w_off[s.scope]
+        host[o:o + t.numel()] = t.to(torch.float32).permute(3, 0, 1, 2).reshape(-1)
+      c = self.c_off[s.scope]
+      for v, base in (('gamma', self.n_conv_pad), ('beta', self.n_conv_pad + self.n_chan_pad)):
+        t = named.get(f'{s.scope}/BatchNorm/{v}')
+        if t is not None:
+          host[base + c:base + c + s.K] = t.to(torch.float32)
+    arena.copy_(host)
+
   def sync_operands(self):
     """bf16 operand copy of the master arena (the optimizer kernel keeps it in sync afterwards)."""
     ops.cast_f32_to_bf16(self.master, self.operand)

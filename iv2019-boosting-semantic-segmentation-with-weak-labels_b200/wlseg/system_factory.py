@@ -94,7 +94,7 @@ class SemanticSegmentation(object):
   def estimator(self):
     return self._estimator
 
-  def _create_estimator(self, ckpt_path=None):
+  def _create_estimator(self, ckpt_path=None, for_training=False):
     s = self._settings
     if getattr(s, 'name_feature_extractor', 'resnet_v1_50') == 'resnet_v1_101':
       # code/estimator/define_estimator_hierarchical.py:57-61
@@ -106,7 +106,8 @@ class SemanticSegmentation(object):
     if getattr(s, 'upsampling_method', 'bilinear') != 'bilinear' or getattr(s, 'norm_layer', 'batch') != 'batch':
       raise NotImplementedError('only --upsampling_method bilinear and --norm_layer batch are implemented.')
     self._estimator = est.Estimator(s, self._hier, device=getattr(s, 'device', 'cuda'))
-    self._estimator.initialize(ckpt_path=ckpt_path, log_dir=s.log_dir, seed=getattr(s, 'seed', 0))
+    self._estimator.initialize(ckpt_path=ckpt_path, log_dir=s.log_dir, seed=getattr(s, 'seed', 0),
+                               for_training=for_training)
     return self._estimator
 
   # ------------------------------------------------------------------------------------------ train
@@ -149,7 +150,7 @@ class SemanticSegmentation(object):
         for k, v in enumerate(settings_dict):
           print(f"{k:2} : {v} : {settings_dict[v]}", file=f)
 
-    self._create_estimator()
+    self._create_estimator(for_training=True)
     max_steps = s.num_training_steps if not getattr(s, 'steps', None) else min(s.steps, s.num_training_steps)
     return self._estimator.train(self._input_fns['train'](None, s), max_steps)
 
