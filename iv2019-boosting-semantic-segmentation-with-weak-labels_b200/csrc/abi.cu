@@ -1,5 +1,6 @@
 // Version / error plumbing and small layout helpers of the C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// Opt-in (WLSEG_PDL=1): measured on B200 the training step got SLOWER with it, 12.12 -> 12.53 ms (the
+// early-resident, waiting CTAs of the batch-norm kernels take thread / register slots from the running grid),
+// and the evaluation step did not move (9.00 vs 9.02 ms: its 200 KB persistent convolution CTAs cannot
+// co-reside anyway).  Read per launch so that one process can A/B both modes.
+bool pdl_enabled() { return getenv("WLSEG_PDL") != nullptr; }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -9,6 +9,8 @@
 // All kernels are HBM-bound passes over [count x C] NHWC activations, 8 channels per thread.
 // Statistics are reduced per thread in fp32 over a few rows, per CTA in shared memory, and
 // across CTAs with fp64 global atomics (sums of up to 10^5..10^6 values per channel).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace wlseg {
@@ -28,6 +30,8 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* _
   //   the ReLU mask comes from yact, or - when yact is NULL (layers without a residual input) - from the
   //   sign of fmaf(z, scale, shift), the exact fp32 value the forward pass rounded to y
   extern __shared__ float part[];  // [lanes][2][C]
+  pdl_launch_dependents();
+  pdl_wait();   // mean / invstd / dy all come from earlier kernels of the chain
   const int cv = C / 8;
   const int lanes = kBnThreads / cv;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
@@ -108,6 +112,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
                                    float decay, float moving_var_factor, float* __restrict__ moving_mean,
                                    float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ saved_mean, float* __restrict__ saved_invstd) {
+  pdl_launch_dependents();
+  pdl_wait();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double n = (double)count;
@@ -320,6 +326,181 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
   }
 }
 
+// ---- row-mapped variants of bn_apply / bn_bwd_apply (C % 8 == 0, C <= 2048) ----------------------------
+// thread (tx, ty) keeps ONE channel vector for its whole life: tx = vector index within the row (C / 8 of
+// them), ty = row lane; a CTA walks `lanes` = 256 / (C / 8) consecutive rows per iteration.  The per-channel
+// constants therefore live in registers (no shared-memory staging, no __syncthreads) and the element index
+// is a multiply-add instead of the 64-bit divide + modulo per 16-byte vector of the flat-index kernels
+// above; kRowsU independent rows are in flight per thread.  A warp still touches 512 contiguous bytes
+// (C >= 256) or 32 * 16 contiguous bytes spanning consecutive rows (C < 256, dense rows).
+template <typename T, int kRowsU>
+__global__ void __launch_bounds__(256)
+bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const T* __restrict__ res, T* __restrict__ y, int64_t count, int C, int relu) {
+  pdl_launch_dependents();
+  pdl_wait();   // scale / shift were written by bn_finalize, the kernel right before this one
+  const int cv = C / 8;
+  const int lanes = 256 / cv;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  if (ty >= lanes) return;
+  const int c0 = tx * 8;
+  const float4 sa = *reinterpret_cast<const float4*>(scale + c0), sb = *reinterpret_cast<const float4*>(scale + c0 + 4);
+  const float4 ha = *reinterpret_cast<const float4*>(shift + c0), hb = *reinterpret_cast<const float4*>(shift + c0 + 4);
+  const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+  const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+  const int64_t step = (int64_t)gridDim.x * lanes;
+  for (int64_t row0 = (int64_t)blockIdx.x * lanes + ty; row0 < count; row0 += step * kRowsU) {
+    Vec8<T> v[kRowsU], vr[kRowsU];
+#pragma unroll
+    for (int u = 0; u < kRowsU; ++u) {
+      const int64_t row = row0 + u * step;
+      if (row < count) {
+        v[u].load(z + row * C + c0);
+        if (res != nullptr) vr[u].load(res + row * C + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowsU; ++u) {
+      const int64_t row = row0 + u * step;
+      if (row >= count) break;
+      float f[8];
+      v[u].unpack(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+      if (res != nullptr) {
+        float r[8];
+        vr[u].unpack(r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      Vec8<T> o;
+      o.pack(f);
+      o.store(y + row * C + c0);
+    }
+  }
+}
+
+template <typename T, int kBwdRowsU>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_rows_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ z,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ gamma, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const double* __restrict__ dgamma,
+                         const double* __restrict__ dbeta, int64_t count, int64_t stat_count, int C, int pitch, int relu,
+                         T* __restrict__ dz, T* __restrict__ dres) {
+  pdl_launch_dependents();
+  pdl_wait();   // dgamma / dbeta were accumulated by bn_reduce, the kernel right before this one
+  const int cv = C / 8;
+  const int lanes = 256 / cv;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  if (ty >= lanes) return;
+  const int c0 = tx * 8;
+  const bool zmask = relu && yact == nullptr;
+  const double invn = 1.0 / (double)stat_count;
+  // dz = A*g + c1*z + c0 (see bn_bwd_apply_kernel); this thread's 8 channels only
+  float A[8], B[8], D[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float is = invstd[c];
+    A[j] = gamma[c] * is;
+    B[j] = -A[j] * is * (float)(dgamma[c] * invn);
+    D[j] = -A[j] * (float)(dbeta[c] * invn) - B[j] * mean[c];
+    sc[j] = zmask ? scale[c] : 0.f;
+    sh[j] = zmask ? shift[c] : 0.f;
+  }
+  const int64_t step = (int64_t)gridDim.x * lanes;
+  for (int64_t row0 = (int64_t)blockIdx.x * lanes + ty; row0 < count; row0 += step * kBwdRowsU) {
+    Vec8<T> v[kBwdRowsU], vz[kBwdRowsU], vy[kBwdRowsU];
+#pragma unroll
+    for (int u = 0; u < kBwdRowsU; ++u) {
+      const int64_t row = row0 + u * step;
+      if (row < count) {
+        const int64_t e = row * pitch + c0;
+        v[u].load(dy + e);
+        vz[u].load(z + e);
+        if (relu && !zmask) vy[u].load(yact + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBwdRowsU; ++u) {
+      const int64_t row = row0 + u * step;
+      if (row >= count) break;
+      const int64_t e = row * pitch + c0;
+      float g[8], zz[8];
+      v[u].unpack(g);
+      vz[u].unpack(zz);
+      if (zmask) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(zz[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+      } else if (relu) {
+        float yy[8];
+        vy[u].unpack(yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = yy[j] > 0.f ? g[j] : 0.f;
+      }
+      if (dres != nullptr) {
+        Vec8<T> o;
+        o.pack(g);
+        o.store(dres + e);
+      }
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] = fmaf(A[j], g[j], fmaf(B[j], zz[j], D[j]));
+      Vec8<T> o;
+      o.pack(out);
+      o.store(dz + e);
+    }
+  }
+}
+
+// WLSEG_BN_FLAT=1 selects the flat-index kernels (A/B measurements; both forms are bit-identical)
+static bool bn_rows_enabled() { return getenv("WLSEG_BN_FLAT") == nullptr; }
+// tuning knobs of the row-mapped kernels (tools/bn_sweep.py): rows in flight per thread and CTAs per SM
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int bn_apply_u() { return env_int("WLSEG_BN_APPLY_U", 2); }
+static int bn_apply_ctas() { return env_int("WLSEG_BN_APPLY_CTAS", 4); }
+static int bn_bwd_u() { return env_int("WLSEG_BN_BWD_U", 2); }
+static int bn_bwd_ctas() { return env_int("WLSEG_BN_BWD_CTAS", 2); }
+
+template <typename T>
+static void launch_apply_rows(const void* z, const float* scale, const float* shift, const void* res, void* y, int64_t count,
+                              int C, int relu, cudaStream_t s) {
+  const int lanes = 256 / (C / 8);
+  const int U = bn_apply_u();
+  const int g = bw_grid(ceil_div(count, (int64_t)lanes * U) * 256, 256, bn_apply_ctas());
+  cudaError_t e;
+  if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
+  else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
+  else e = launch_pdl(bn_apply_rows_kernel<T, 2>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
+  (void)e;   // reported by the caller's WLSEG_LAUNCH_CHECK (cudaGetLastError)
+}
+
+template <typename T>
+static void launch_bwd_apply_rows(const void* dy, const void* y, const void* z, const float* mean, const float* invstd,
+                                  const float* gamma, const float* scale, const float* shift, const double* dgamma,
+                                  const double* dbeta, int64_t count, int64_t stat_count, int C, int pitch, int relu,
+                                  void* dz, void* dres, cudaStream_t s) {
+  const int lanes = 256 / (C / 8);
+  const int U = bn_bwd_u();
+  const int g = bw_grid(ceil_div(count, (int64_t)lanes * U) * 256, 256, bn_bwd_ctas());
+#define WLSEG_BWD_ROWS(UU)                                                                                          \
+  (void)launch_pdl(bn_bwd_apply_rows_kernel<T, UU>, dim3(g), dim3(256), 0, s, (const T*)dy, (const T*)y, (const T*)z,  \
+                   mean, invstd, gamma, scale, shift, dgamma, dbeta, count, stat_count, C, pitch, relu, (T*)dz,        \
+                   (T*)dres)
+  if (U == 1) WLSEG_BWD_ROWS(1);
+  else if (U == 4) WLSEG_BWD_ROWS(4);
+  else WLSEG_BWD_ROWS(2);
+#undef WLSEG_BWD_ROWS
+}
+
 // ---- generic path for channel counts that are not a multiple of 8 (the logits layers: 14/7/3 and
 // 53/12/5 channels).  Tiny tensors; one thread per (row lane, channel), fp64 partial sums.
 constexpr int kSmallMaxC = 64;
@@ -413,9 +594,8 @@ static int launch_reduce(const void* a, const void* y, const void* z, const floa
   // 2 CTAs per SM: with kBnUnroll rows in flight per thread that saturates HBM, and it halves the number
   // of CTAs queueing on the same C fp64 accumulators at the end
   int grid = bw_grid(ceil_div(count * cv, kBnUnroll), kBnThreads, 2);
-  bn_reduce_kernel<T, kBackward><<<grid, kBnThreads, smem, s>>>((const T*)a, (const T*)y, (const T*)z, mean, invstd,
-                                                                scale, shift, count, C, pitch, relu, o0, o1);
-  WLSEG_LAUNCH_CHECK();
+  WLSEG_CUDA(launch_pdl(bn_reduce_kernel<T, kBackward>, dim3(grid), dim3(kBnThreads), smem, s, (const T*)a, (const T*)y,
+                        (const T*)z, mean, invstd, scale, shift, count, C, pitch, relu, o0, o1));
   return 0;
 }
 
@@ -444,10 +624,9 @@ extern "C" int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t
                                  float* saved_invstd, wlseg_stream_t stream) {
   WLSEG_CHECK_ARG(sum && sqsum && gamma && beta && count > 0 && C > 0, "bn_finalize: bad args");
   WLSEG_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving stats must come in pairs");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, count, C, gamma, beta, eps, decay,
-                                                                        moving_var_factor, moving_mean, moving_var, scale,
-                                                                        shift, saved_mean, saved_invstd);
-  WLSEG_LAUNCH_CHECK();
+  WLSEG_CUDA(launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, sum, sqsum, count, C,
+                        gamma, beta, eps, decay, moving_var_factor, moving_mean, moving_var, scale, shift, saved_mean,
+                        saved_invstd));
   return 0;
 }
 
@@ -492,6 +671,13 @@ extern "C" int wlseg_bn_apply(const void* z, const float* scale, const float* sh
                                                                  (float*)y, total, C, relu);
     else
       WLSEG_CHECK_ARG(false, "bn_apply: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
+  if (C <= 2048 && bn_rows_enabled()) {
+    if (dtype == WLSEG_BF16) launch_apply_rows<__nv_bfloat16>(z, scale, shift, residual, y, count, C, relu, (cudaStream_t)stream);
+    else if (dtype == WLSEG_F32) launch_apply_rows<float>(z, scale, shift, residual, y, count, C, relu, (cudaStream_t)stream);
+    else WLSEG_CHECK_ARG(false, "bn_apply: bad dtype %d", dtype);
     WLSEG_LAUNCH_CHECK();
     return 0;
   }
@@ -550,6 +736,18 @@ extern "C" int wlseg_bn_bwd_apply(const void* dy, const void* y, const void* z, 
       bn_bwd_apply_small_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)y, (const float*)z,
                                                                      mean, invstd, gamma, dgamma, dbeta, total, stat_count,
                                                                      C, relu, (float*)dz, (float*)dres);
+    else
+      WLSEG_CHECK_ARG(false, "bn_bwd_apply: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
+  if (C <= 2048 && bn_rows_enabled()) {
+    if (dtype == WLSEG_BF16)
+      launch_bwd_apply_rows<__nv_bfloat16>(dy, y, z, mean, invstd, gamma, scale, shift, dgamma, dbeta, count, stat_count, C,
+                                           pitch, relu, dz, dres, (cudaStream_t)stream);
+    else if (dtype == WLSEG_F32)
+      launch_bwd_apply_rows<float>(dy, y, z, mean, invstd, gamma, scale, shift, dgamma, dbeta, count, stat_count, C, pitch,
+                                   relu, dz, dres, (cudaStream_t)stream);
     else
       WLSEG_CHECK_ARG(false, "bn_bwd_apply: bad dtype %d", dtype);
     WLSEG_LAUNCH_CHECK();

@@ -111,6 +111,35 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// One training step is ~520 dependent launches of 10-50 us kernels; without PDL every kernel boundary costs the
+// launch latency plus the ramp-up of the next grid.  Kernels on the hot chain (convolutions, batch-norm passes)
+// call pdl_launch_dependents() first thing - the NEXT kernel's CTAs may then become resident and run their
+// prologue (barrier init, TMEM allocation, constant loads) as SM resources free up - and pdl_wait() before
+// their first access to global memory, which returns once the PREVIOUS kernel has completed and flushed.
+// Both are no-ops when the launch does not carry the attribute - the default: see pdl_enabled() in abi.cu for
+// the measurement that made this opt-in (WLSEG_PDL=1).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // abi.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // grid size for grid-stride bandwidth kernels: a multiple of the SM count

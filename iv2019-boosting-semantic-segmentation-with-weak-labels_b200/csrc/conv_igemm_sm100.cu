@@ -145,6 +145,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   using Cfg = IgemmCfg<BN>;
   constexpr int CG = EW / 4;             // warps per TMEM lane quarter: each takes every CG-th sub-tile
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();   // the next kernel may stage its CTAs; it waits for this grid before touching memory
   // SWIZZLE_128B operands need 1024-byte aligned stages (the kernel has no static shared memory,
   // so the dynamic window starts at offset 0 of the CTA's shared space)
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -189,6 +190,9 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's shared memory / TMEM and the kernel parameters; from here on
+  // the previous kernel's output is read (and buffers it may still be reading are overwritten)
+  pdl_wait();
 
   const int TW = 1 << prm.tw_log2;
 
@@ -650,8 +654,7 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   int grid = prm.total_tiles < kNumSMs ? prm.total_tiles : kNumSMs;
   // fused BN statistics live in registers across tiles: every CTA must stay on one N tile
   if (kTmaEpi && prm.bn_sum != nullptr && grid % prm.n_tiles != 0) grid -= grid % prm.n_tiles;
-  conv_igemm_kernel<BN, TY, kTmaEpi, EW><<<grid, 128 + 32 * EW, smem_bytes, s>>>(prm);
-  WLSEG_LAUNCH_CHECK();
+  WLSEG_CUDA(launch_pdl(conv_igemm_kernel<BN, TY, kTmaEpi, EW>, dim3(grid), dim3(128 + 32 * EW), smem_bytes, s, prm));
   return 0;
 }
 

@@ -91,6 +91,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
   constexpr int kStageBytes = kWgABytes + CH * kChunkBytes;
   constexpr int kTmemCols = 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int stages = prm.stages;
   uint8_t* epi_smem = smem + stages * kStageBytes;
@@ -125,6 +126,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // prologue done; dz / x of the previous kernels are read from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -307,8 +309,7 @@ static int launch_wgrad(WgradParams& prm, cudaStream_t s) {
   prm.stages = stages;
   const int smem_bytes = stages * kStageBytes + fixed;
   const int grid = prm.units < kNumSMs ? prm.units : kNumSMs;
-  conv_wgrad_kernel<BN><<<grid, kWgThreads, smem_bytes, s>>>(prm);
-  WLSEG_LAUNCH_CHECK();
+  WLSEG_CUDA(launch_pdl(conv_wgrad_kernel<BN>, dim3(grid), dim3(kWgThreads), smem_bytes, s, prm));
   return 0;
 }
 

@@ -9,6 +9,8 @@
 // MaxPoolGrad); implemented as a gather per input element so no atomics are needed.
 //
 // HBM-bound: 8 channels (16 B for bf16) per thread, channels innermost => coalesced.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace wlseg {
@@ -59,6 +61,84 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restri
       packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
       packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
       *reinterpret_cast<uint2*>(argmax + oi) = packed;
+    }
+  }
+}
+
+// pool1 (3x3, stride 2) specialisation: a thread owns one (row p, channel vector) and walks kPoolRun consecutive
+// output columns, so the window column shared by neighbouring outputs (input column 2q + 2 - pad) is loaded once
+// and carried in registers; the three row loads of a column are issued together.  6 + 6 per run instead of 9
+// loads per output, compile-time tap loops, no 64-bit divisions per output.  Same comparison order as the
+// generic kernel (row-major scan, strict '>'), hence the same arg-max map bit for bit.
+constexpr int kPoolRun = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ argmax, PoolGeom g) {
+  const int cv = g.C / 8;
+  const int runs = (g.Q + kPoolRun - 1) / kPoolRun;
+  const int64_t total = (int64_t)g.N * g.P * runs * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t t = i / cv;
+    const int run = (int)(t % runs); t /= runs;
+    const int p = (int)(t % g.P);
+    const int n = (int)(t / g.P);
+    const int q0 = run * kPoolRun;
+    const int h0 = p * 2 - g.pad_t;
+    const T* base = x + (int64_t)n * g.H * g.W * g.C + c8 * 8;
+    // column ww of the three window rows -> col[r][8]; invalid cells are flagged, never compared
+    Vec8<T> col[3][3];     // [window column s][row r], kept packed (4 registers per bf16 vector)
+    bool okc[3], okr[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) okr[r] = (h0 + r >= 0) && (h0 + r < g.H);
+    auto load_col = [&](int ww, int slot) {
+      okc[slot] = ww >= 0 && ww < g.W;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (okc[slot] && okr[r]) col[slot][r].load(base + ((int64_t)(h0 + r) * g.W + ww) * g.C);
+    };
+    const int w0 = q0 * 2 - g.pad_l;
+    load_col(w0, 0);
+#pragma unroll
+    for (int u = 0; u < kPoolRun; ++u) {
+      const int q = q0 + u;
+      if (q >= g.Q) break;
+      const int ww = q * 2 - g.pad_l;
+      load_col(ww + 1, 1);
+      load_col(ww + 2, 2);
+      float best[8];
+      uint32_t arg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 255u; }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int s_ = 0; s_ < 3; ++s_) {
+          if (!(okr[r] && okc[s_])) continue;
+          const uint32_t pos = (uint32_t)(r * 3 + s_);
+          float f[8];
+          col[s_][r].unpack(f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (f[j] > best[j] || arg[j] == 255u) { best[j] = f[j]; arg[j] = pos; }
+          }
+        }
+      }
+      Vec8<T> o;
+      o.pack(best);
+      const int64_t oi = (((int64_t)n * g.P + p) * g.Q + q) * g.C + c8 * 8;
+      o.store(y + oi);
+      if (argmax != nullptr) {
+        uint2 packed;
+        packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+        packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+        *reinterpret_cast<uint2*>(argmax + oi) = packed;
+      }
+      // the last window column becomes the first one of the next output
+      okc[0] = okc[2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) col[0][r] = col[2][r];
     }
   }
 }
@@ -199,6 +279,18 @@ extern "C" int wlseg_maxpool_same_fwd(const void* x, void* y, uint8_t* argmax, i
   if (N == 0) return 0;
   WLSEG_CHECK_ARG(x && y, "maxpool_fwd: null pointer");
   WLSEG_CHECK_ARG(argmax == nullptr || ksize * ksize < 255, "maxpool_fwd: window too large for the uint8 argmax map");
+  if (ksize == 3 && stride == 2 && getenv("WLSEG_POOL_GENERIC") == nullptr) {
+    const int64_t items3 = (int64_t)N * g.P * ((g.Q + kPoolRun - 1) / kPoolRun) * (C / 8);
+    const int grid3 = bw_grid(items3, 256, 2);
+    if (dtype == WLSEG_BF16)
+      maxpool3x3s2_fwd_kernel<<<grid3, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, g);
+    else if (dtype == WLSEG_F32)
+      maxpool3x3s2_fwd_kernel<<<grid3, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, argmax, g);
+    else
+      WLSEG_CHECK_ARG(false, "maxpool_fwd: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
   int64_t items = (int64_t)N * g.P * g.Q * (C / 8);
   int grid = bw_grid(items, 256, 8);
   if (dtype == WLSEG_BF16)

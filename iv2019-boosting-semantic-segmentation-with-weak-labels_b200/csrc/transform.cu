@@ -13,34 +13,60 @@
 
 namespace wlseg {
 
+// One CTA = kPackTX consecutive packed pixels of one packed row (n, y): the two image rows 2y, 2y + 1 that
+// feed it are staged ONCE in shared memory with fully coalesced loads (2 * (2 * kPackTX + 6) * 3 values,
+// zero outside the image), then every thread composes 16-byte output vectors from the staged rows
+// (compile-time tap tables, no global gathers, no divisions in the inner loop).  The flat-index form it
+// replaces issued 8 scalar global loads with 64-bit index arithmetic per output vector and ran at
+// 1.8 TB/s; output traffic dominates (64 bf16 channels per packed pixel vs 12 image values).
+constexpr int kPackTX = 128;
+constexpr int kPackCols = 2 * kPackTX + 6;   // image columns 2 * (x0 - 2) .. 2 * (x0 + kPackTX + 1) - 1
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv1_pack_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W, int Hs, int Ws) {
-  const int64_t total = (int64_t)N * Hs * Ws * 8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 7);
-    int64_t t = i >> 3;
-    const int x = (int)(t % Ws); t /= Ws;
-    const int y = (int)(t % Hs);
-    const int n = (int)(t / Hs);
+  __shared__ float rows[2][kPackCols * 3];
+  const int x0 = blockIdx.x * kPackTX;
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;
+  const int wbase = 2 * (x0 - 2);
+  for (int i = threadIdx.x; i < 2 * kPackCols * 3; i += 256) {
+    const int ii = i / (kPackCols * 3);
+    const int k = i - ii * (kPackCols * 3);
+    const int ww = wbase + k / 3;
+    const int hh = 2 * y + ii;
+    float v = 0.f;
+    if (hh < H && ww >= 0 && ww < W) v = to_f32<T>(img[(((int64_t)n * H + hh) * W + wbase) * 3 + k]);
+    rows[ii][k] = v;
+  }
+  __syncthreads();
+  // output vector (x, g): g = 8-channel group of the packed pixel; channel = b * 16 + slot,
+  // slot = (ii * 2 + jj) * 3 + c for slot < 12 (zero above), b = horizontal tap, image column 2 * (x - 2 + b) + jj
+  const int nx = min(kPackTX, Ws - x0);
+  __nv_bfloat16* orow = out + (((int64_t)n * Hs + y) * Ws + x0) * 64;
+  for (int v = threadIdx.x; v < nx * 8; v += 256) {
+    const int g = v & 7, xl = v >> 3;
     const int b = g >> 1;
-    const int slot0 = (g & 1) * 8;
+    const float* r0 = &rows[0][(2 * (xl + b)) * 3];   // column 2 * (x - 2 + b) - wbase = 2 * (xl + b)
+    const float* r1 = &rows[1][(2 * (xl + b)) * 3];
     float f[8];
+    if ((g & 1) == 0) {
+      // slots 0..7: (ii=0: jj=0 c0..2, jj=1 c0..2) = r0[0..5], then (ii=1, jj=0, c0..1) = r1[0..1]
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int slot = slot0 + e;
-      float v = 0.f;
-      if (slot < 12) {
-        const int ii = slot / 6, jj = (slot / 3) & 1, c = slot % 3;
-        const int hh = 2 * y + ii;
-        const int ww = 2 * (x - 2 + b) + jj;
-        if (hh < H && ww >= 0 && ww < W) v = to_f32<T>(img[(((int64_t)n * H + hh) * W + ww) * 3 + c]);
-      }
-      f[e] = v;
+      for (int e = 0; e < 6; ++e) f[e] = r0[e];
+      f[6] = r1[0];
+      f[7] = r1[1];
+    } else {
+      // slots 8..15: (ii=1, jj=0, c2) = r1[2], (ii=1, jj=1, c0..2) = r1[3..5], slots 12..15 zero
+      f[0] = r1[2];
+      f[1] = r1[3];
+      f[2] = r1[4];
+      f[3] = r1[5];
+      f[4] = f[5] = f[6] = f[7] = 0.f;
     }
     Vec8<__nv_bfloat16> o;
     o.pack(f);
-    o.store(out + i * 8);
+    o.store(orow + (int64_t)v * 8);
   }
 }
 
@@ -153,8 +179,8 @@ extern "C" int wlseg_conv1_pack(const void* img, int32_t dtype, int32_t N, int32
   if (N == 0) return 0;
   WLSEG_CHECK_ARG(img && out, "conv1_pack: null pointer");
   const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
-  const int64_t total = (int64_t)N * Hs * Ws * 8;
-  const int grid = bw_grid(total, 256, 8);
+  WLSEG_CHECK_ARG(Hs <= 65535 && N <= 65535, "conv1_pack: image too large for the launch grid");
+  const dim3 grid((unsigned)ceil_div(Ws, kPackTX), (unsigned)Hs, (unsigned)N);
   if (dtype == WLSEG_F32)
     conv1_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)img, (__nv_bfloat16*)out, N, H, W, Hs, Ws);
   else if (dtype == WLSEG_BF16)

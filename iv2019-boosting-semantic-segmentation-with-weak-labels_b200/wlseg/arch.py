@@ -49,9 +49,13 @@ PSP_BINS = (1, 2, 3, 6)
 
 
 FOV_SCOPE = 'feature_extractor/extension/increase_fov'
+# --upsampling_method hybrid: one 3x3 slim.conv2d_transpose (stride 1, SAME, + bias, NO normaliser: the arg scope
+# only configures slim.conv2d) per head before the bilinear resize, default scopes inside
+# variable_scope('upsampling') (models/resnet50_extended_model_hierarchical.py:84-86,161-179)
+UPSAMPLING_SCOPES = tuple('softmax_classifier/upsampling/Conv2d_transpose' + ('' if i == 0 else f'_{i}') for i in range(3))
 
 
-def conv_specs(head_widths, output_stride=8, d=256, psp=False, fov=None):
+def conv_specs(head_widths, output_stride=8, d=256, psp=False, fov=None, upsampling='bilinear'):
   """All convolutions in parameter-arena order.  The three adaptation conv1 kernels are adjacent
   so that they form one [3*d, 1, 1, d] filter bank (one GEMM over the shared input).  psp=True adds the
   five 1x1 convolutions of the pyramid module (slim's default scopes Conv .. Conv_4 under
@@ -80,6 +84,10 @@ def conv_specs(head_widths, output_stride=8, d=256, psp=False, fov=None):
     specs.append(ConvSpec(f'{u.scope}/conv3', 1, 1, d, d, 1, 1, False))
   for (_, lg), c in zip(BRANCHES, head_widths):
     specs.append(ConvSpec(f'softmax_classifier/{lg}', 1, 1, d, c, 1, 1, False))
+  if upsampling == 'hybrid':
+    # stored as the equivalent stride-1 correlation kernel (KRSC, rotated 180 degrees); bias in the beta slot
+    for sc, c in zip(UPSAMPLING_SCOPES, head_widths):
+      specs.append(ConvSpec(sc, 3, 3, c, c, 1, 1, False))
   return specs
 
 

@@ -49,7 +49,11 @@ def model_variables(params):
   """[(TF name, TF shape)] of tf.model_variables() in creation order: per convolution `weights` (HWIO) then
   its BatchNorm beta, gamma, moving_mean, moving_variance (slim creates beta before gamma)."""
   out = []
+  plain = getattr(params, 'plain', ())
   for s in params.specs:
+    if s.scope in plain:   # slim.conv2d_transpose of --upsampling_method hybrid: [kh, kw, out, in] + biases, no BN
+      out += [(f'{s.scope}/weights', (s.R, s.S, s.K, s.C)), (f'{s.scope}/biases', (s.K,))]
+      continue
     out.append((f'{s.scope}/weights', (s.R, s.S, s.C, s.K)))
     for v in ('beta', 'gamma', 'moving_mean', 'moving_variance'):
       out.append((f'{s.scope}/BatchNorm/{v}', (s.K,)))

@@ -137,7 +137,8 @@ class Estimator:
     self.params = network.Params(hier, self.device, getattr(params, 'stride_feature_extractor', 8),
                                  psp=getattr(params, 'psp_module', False),
                                  fov=(getattr(params, 'fov_expansion_kernel_size', 0),
-                                      getattr(params, 'fov_expansion_kernel_rate', 0)))
+                                      getattr(params, 'fov_expansion_kernel_rate', 0)),
+                                 upsampling=getattr(params, 'upsampling_method', 'bilinear'))
     self.global_step = 0
     self.net = None
     self.last_h2d_bytes = 0

@@ -26,13 +26,19 @@ def _trunc_normal_(t, std, gen):
 class Params:
   """All trainable variables + BN moving statistics, addressable by TF variable name."""
 
-  def __init__(self, hier, device, output_stride=8, psp=False, fov=None):
+  def __init__(self, hier, device, output_stride=8, psp=False, fov=None, upsampling='bilinear'):
     self.hier = hier
     self.device = torch.device(device)
     self.psp = bool(psp)  # --psp_module: five more convolutions (arch.PSP_SCOPES)
     # --fov_expansion_kernel_size / --fov_expansion_kernel_rate: one dilated convolution (arch.FOV_SCOPE)
     self.fov = tuple(fov) if fov and fov[0] > 0 and fov[1] > 0 else None
-    self.specs = arch.conv_specs(hier.head_widths, output_stride, psp=self.psp, fov=self.fov)
+    # --upsampling_method: 'bilinear' | 'no' (predictions stay at the feature resolution) | 'hybrid' (three more
+    # layers, arch.UPSAMPLING_SCOPES: transposed convolutions with a bias and no batch norm, kept in fp32)
+    if upsampling not in ('bilinear', 'no', 'hybrid'):
+      raise ValueError('No such upsampling method.')   # models/resnet50_extended_model_hierarchical.py:181-182
+    self.upsampling = upsampling
+    self.specs = arch.conv_specs(hier.head_widths, output_stride, psp=self.psp, fov=self.fov, upsampling=upsampling)
+    self.plain = set(arch.UPSAMPLING_SCOPES) if upsampling == 'hybrid' else set()   # layers without batch norm
     self.by_scope = {s.scope: s for s in self.specs}
     self.w_off, self.c_off = {}, {}
     off = 0
@@ -110,10 +116,17 @@ class Params:
     mov = self.moving.cpu()
     for s in self.specs:
       w = tensors[f'{s.scope}/weights'].to(torch.float32)
-      assert tuple(w.shape) == (s.R, s.S, s.C, s.K), (s.scope, tuple(w.shape))
       o = self.w_off[s.scope]
-      host[o:o + w.numel()] = w.permute(3, 0, 1, 2).reshape(-1)
       c = self.c_off[s.scope]
+      if s.scope in self.plain:
+        # conv2d_transpose filter [kh, kw, out, in] -> the stride-1 correlation kernel it equals:
+        # W[o, r, s, i] = f[kh-1-r, kw-1-s, o, i]; its bias lives in the beta slot (gamma stays 1, unused)
+        assert tuple(w.shape) == (s.R, s.S, s.K, s.C), (s.scope, tuple(w.shape))
+        host[o:o + w.numel()] = w.flip(0, 1).permute(2, 0, 1, 3).reshape(-1)
+        host[self.n_conv_pad + self.n_chan_pad + c:self.n_conv_pad + self.n_chan_pad + c + s.K] = tensors[f'{s.scope}/biases']
+        continue
+      assert tuple(w.shape) == (s.R, s.S, s.C, s.K), (s.scope, tuple(w.shape))
+      host[o:o + w.numel()] = w.permute(3, 0, 1, 2).reshape(-1)
       host[self.n_conv_pad + c:self.n_conv_pad + c + s.K] = tensors[f'{s.scope}/BatchNorm/gamma']
       host[self.n_conv_pad + self.n_chan_pad + c:self.n_conv_pad + self.n_chan_pad + c + s.K] = \
           tensors[f'{s.scope}/BatchNorm/beta']
@@ -126,6 +139,10 @@ class Params:
   def to_tf_dict(self):
     out = {}
     for s in self.specs:
+      if s.scope in self.plain:
+        out[f'{s.scope}/weights'] = self.w32(s.scope).permute(1, 2, 0, 3).flip(0, 1).contiguous().cpu()
+        out[f'{s.scope}/biases'] = self.beta(s.scope).cpu().clone()
+        continue
       out[f'{s.scope}/weights'] = self.w32(s.scope).permute(1, 2, 3, 0).contiguous().cpu()
       out[f'{s.scope}/BatchNorm/gamma'] = self.gamma(s.scope).cpu().clone()
       out[f'{s.scope}/BatchNorm/beta'] = self.beta(s.scope).cpu().clone()
@@ -138,6 +155,10 @@ class Params:
     conv kernels back in TF's HWIO layout (wlseg/checkpoints.py names the slots)."""
     out = {}
     for s in self.specs:
+      if s.scope in self.plain:
+        out[f'{s.scope}/weights'] = self._wview(arena, s.scope).permute(1, 2, 0, 3).flip(0, 1).contiguous().cpu()
+        out[f'{s.scope}/biases'] = self._cview(arena, self.n_conv_pad + self.n_chan_pad, s.scope).cpu().clone()
+        continue
       out[f'{s.scope}/weights'] = self._wview(arena, s.scope).permute(1, 2, 3, 0).contiguous().cpu()
       out[f'{s.scope}/BatchNorm/gamma'] = self._cview(arena, self.n_conv_pad, s.scope).cpu().clone()
       out[f'{s.scope}/BatchNorm/beta'] = self._cview(arena, self.n_conv_pad + self.n_chan_pad, s.scope).cpu().clone()
@@ -147,6 +168,15 @@ class Params:
     """Inverse of arena_to_tf_dict for the names present in `named`; the rest of the arena is kept."""
     host = arena.cpu()
     for s in self.specs:
+      if s.scope in self.plain:
+        t, b = named.get(f'{s.scope}/weights'), named.get(f'{s.scope}/biases')
+        if t is not None:
+          o = self.w_off[s.scope]
+          host[o:o + t.numel()] = t.to(torch.float32).flip(0, 1).permute(2, 0, 1, 3).reshape(-1)
+        if b is not None:
+          base = self.n_conv_pad + self.n_chan_pad + self.c_off[s.scope]
+          host[base:base + s.K] = b.to(torch.float32)
+        continue
       t = named.get(f'{s.scope}/weights')
       if t is not None:
         assert tuple(t.shape) == (s.R, s.S, s.C, s.K), (s.scope, tuple(t.shape))
@@ -408,13 +438,33 @@ class Network:
       self._conv(r, self._weights(scope), out_hw=(h, w), scale=sc, shift=sh, relu=False,
                  y=logits[..., c0:c0 + ck])
       c0 += ck
-    return logits
+    return self._hybrid_upsampler_fwd(logits) if self.p.upsampling == 'hybrid' else logits
+
+  def _hybrid_upsampler_fwd(self, logits):
+    """`--upsampling_method hybrid` (models/resnet50_extended_model_hierarchical.py:168-180): per head a 3x3
+    slim.conv2d_transpose (stride 1, SAME, + bias) on the low-resolution logits, before the bilinear resize the
+    head / loss kernels do.  fp32 on the direct kernel (14 / 7 / 3 channels), reading and writing channel slices
+    of the pitched logits buffers; the transposed convolution is run as the stride-1 correlation it equals."""
+    N, h, w, pitch = logits.shape
+    out = torch.zeros_like(logits)
+    ones = torch.ones(64, dtype=torch.float32, device=self.dev)
+    c0 = 0
+    for sc in arch.UPSAMPLING_SCOPES:
+      spec = self.p.by_scope[sc]
+      ck = spec.K
+      prm = ops.conv_params((N, h, w, ck), (ck, 3, 3, ck), pad=(1, 1), out_hw=(h, w), x_pitch=pitch, y_pitch=pitch,
+                            dtype=ops.F32, algo=ops.ALGO_DIRECT)
+      ops.conv2d_fprop(prm, logits[..., c0:c0 + ck], self.p.w32(sc), out[..., c0:c0 + ck], ones[:ck], self.p.beta(sc))
+      c0 += ck
+    return out
 
   def predict(self, images, want=('decisions',)):
     """Forward pass -> dict with the requested keys of the reference's predictions dict
     (code/models/resnet50_extended_model_hierarchical.py:121-130)."""
     N, H, W, _ = images.shape
     logits = self.lowres_logits_infer(images)
+    if self.p.upsampling == 'no':   # `upsampled = bottom` (:164-165): predictions at the feature resolution
+      H, W = logits.shape[1], logits.shape[2]
     out = {'lowres_logits': logits}
     out.update(self.head(logits, H, W, want))
     return out
@@ -510,6 +560,11 @@ class TrainNetwork(Network):
     # the HBM efficiency of the first pass - so slicing is off by default.
     self.bn_bwd_l2_bytes = 1 << 40
     self._order = {s.scope: i for i, s in enumerate(params.specs)}
+    # filter gradients on a second stream: wgrad of layer L only needs dz_L, while the chain dgrad_L ->
+    # BN backward of layer L-1 -> ... does not need it, so the (tensor-core) wgrad kernels can fill the SMs
+    # next to the (bandwidth) BN backward kernels of the layers below.  None = everything on one stream.
+    self.wgrad_stream = None
+    self._side_keep = []
 
   def _mark_done(self, scope, n_elems):
     """Bookkeeping for the gradient exchange: backward completes the arena roughly tail first."""
@@ -651,7 +706,14 @@ class TrainNetwork(Network):
                 'sig': (N, H, W, C, K, Rr, stride, dilation, False, False, 'wgrad'),
                 'e0': torch.cuda.Event(enable_timing=True), 'e1': torch.cuda.Event(enable_timing=True)}
         prof['e0'].record()
-      ops.conv2d_wgrad(prm, rec.x, dz, self._wgrad_view(scope, (K,) + tuple(rec.w.shape[1:])))
+      side = self.wgrad_stream if (prof is None and not self.keep) else None
+      if side is None:
+        ops.conv2d_wgrad(prm, rec.x, dz, self._wgrad_view(scope, (K,) + tuple(rec.w.shape[1:])))
+      else:
+        side.wait_event(torch.cuda.current_stream().record_event())   # dz (and the zeroed arena) are ready
+        with torch.cuda.stream(side):
+          ops.conv2d_wgrad(prm, rec.x, dz, self._wgrad_view(scope, (K,) + tuple(rec.w.shape[1:])))
+        self._side_keep.append(dz)   # the allocator must not hand dz out again before the join in backward()
       if prof is not None:
         prof['e1'].record()
         self.profile.append(prof)
@@ -799,13 +861,39 @@ class TrainNetwork(Network):
       lz = self._layer_fwd(r, scope, y_f32=True, relu=False)
       logits[..., c0:c0 + ck] = lz  # tiny [N,h,w,ck] placement into the pitched logits buffer
       c0 += ck
+    if self.p.upsampling == 'hybrid':
+      self.tape['pre_upsampler_logits'] = logits
+      logits = self._hybrid_upsampler_fwd(logits)
     return logits
+
+  def _hybrid_upsampler_bwd(self, dlogits):
+    """Backward of _hybrid_upsampler_fwd: bias gradient (a per-channel sum, into the layer's dbeta accumulator),
+    filter gradient (into the arena, in the stored correlation-kernel layout) and the gradient wrt the
+    pre-upsampler logits.  fp32 direct kernels on channel slices of the pitched buffers."""
+    x = self.tape['pre_upsampler_logits']
+    N, h, w, pitch = x.shape
+    dx = torch.zeros_like(x)
+    ws = self.ws
+    scratch = torch.zeros(64, dtype=torch.float64, device=self.dev)
+    c0 = 0
+    for sc in arch.UPSAMPLING_SCOPES:
+      ck = self.p.by_scope[sc].K
+      dy = dlogits[..., c0:c0 + ck].contiguous()
+      ops.bn_stats(dy, N * h * w, ck, ck, ws.view(ws.stat, 3, self.p.c_off[sc], ck), scratch[:ck])   # dbias = sum dy
+      prm = ops.conv_params((N, h, w, ck), (ck, 3, 3, ck), pad=(1, 1), out_hw=(h, w), x_pitch=pitch, y_pitch=ck,
+                            dtype=ops.F32, algo=ops.ALGO_DIRECT, accumulate=True)
+      ops.conv2d_wgrad(prm, x[..., c0:c0 + ck], dy, self._wgrad_view(sc, (ck, 3, 3, ck)))
+      ops.conv2d_dgrad(prm, dy, self.p.w32(sc), dx[..., c0:c0 + ck])
+      self._mark_done(sc, ck * 9 * ck)
+      c0 += ck
+    return dx
 
   def backward(self, dlogits):
     """dlogits: fp32 [N, h, w, logits_pitch] gradient wrt the post-BN low-res logits.  Fills the
     gradient arena (conv kernels, gammas, betas)."""
     ws = self.ws
     ws.grads.zero_()  # one memset: every wgrad below accumulates (split-K partial sums) into the arena
+    self._side_keep = []
     self._flipped = None
     if self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT:
       table, arena, views = self.p.flip_plan()
@@ -813,6 +901,8 @@ class TrainNetwork(Network):
       self._flipped = views
     self._done = [False] * len(self.p.specs)
     self._tail = len(self.p.specs)
+    if self.p.upsampling == 'hybrid':
+      dlogits = self._hybrid_upsampler_bwd(dlogits)
     f = self.tape['features']
     N, h, w, d = f.shape
     au = arch.adaptation_units(d)
@@ -838,6 +928,9 @@ class TrainNetwork(Network):
     for u in reversed(arch.units()):
       dx = self._unit_bwd(dx, u)
     self._root_bwd(dx)
+    if self.wgrad_stream is not None:
+      torch.cuda.current_stream().wait_stream(self.wgrad_stream)   # join: every filter gradient is in the arena
+      self._side_keep = []
     # BN parameter gradients: fp64 accumulators -> fp32 gradient arena
     n = self.p.n_chan_pad
     ws.grads[self.p.n_conv_pad:self.p.n_conv_pad + n] = ws.stat[2 * n:3 * n].to(torch.float32)

@@ -103,8 +103,11 @@ class SemanticSegmentation(object):
       # _validate_params, code/models/resnet50_extended_model_hierarchical.py:271-276
       raise ValueError('One of params.{fov_expansion_kernel_rate, fov_expansion_kernel_size} '
                        'is set. In order to take effect both should be set.')
-    if getattr(s, 'upsampling_method', 'bilinear') != 'bilinear' or getattr(s, 'norm_layer', 'batch') != 'batch':
-      raise NotImplementedError('only --upsampling_method bilinear and --norm_layer batch are implemented.')
+    if getattr(s, 'norm_layer', 'batch') != 'batch':
+      raise NotImplementedError('only --norm_layer batch is implemented.')
+    if for_training and getattr(s, 'upsampling_method', 'bilinear') == 'no':
+      # the reference's graph fails here too: per-pixel labels (hf x wf) against logits at hf/8 x wf/8
+      raise ValueError('--upsampling_method no: labels and logits differ in size, training is not possible.')
     self._estimator = est.Estimator(s, self._hier, device=getattr(s, 'device', 'cuda'))
     self._estimator.initialize(ckpt_path=ckpt_path, log_dir=s.log_dir, seed=getattr(s, 'seed', 0),
                                for_training=for_training)

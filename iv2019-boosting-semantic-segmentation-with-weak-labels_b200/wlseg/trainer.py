@@ -12,6 +12,8 @@ gets from `RunConfig(train_distribute=...)` (code/system_factory.py:279-295).
 Launch sequencing and buffer ownership only; the arithmetic is in libwlseg.
 """
 
+import os
+
 import torch
 
 from wlseg import network, ops
@@ -28,6 +30,7 @@ class GradientBuckets:
   def __init__(self, flat, bucket_elems, world_size, process_group=None, comm_stream=None, extra=()):
     self.flat = flat
     self.extra = list(extra)  # tensors that only become final at the very end (BN gamma / beta gradients)
+    self.also_wait = []       # further streams whose work a bucket depends on (the wgrad side stream)
     self.n = flat.numel()
     self.world = world_size
     self.group = process_group
@@ -57,6 +60,8 @@ class GradientBuckets:
       return
     if self.stream is not None:
       self.stream.wait_stream(torch.cuda.current_stream())
+      for st in self.also_wait:
+        self.stream.wait_stream(st)
       with torch.cuda.stream(self.stream):
         dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
     else:
@@ -113,6 +118,9 @@ class Trainer:
     self.buckets = GradientBuckets(self.ws.grads[:params.n_conv_pad], bucket_mb * (1 << 20) // 4, world_size,
                                    comm_stream=self.comm_stream, extra=[self.ws.grads[params.n_conv_pad:]])
     self.net.grad_ready = self.buckets.ready if world_size > 1 else None
+    if os.environ.get('WLSEG_WGRAD_STREAM', '0') == '1' and params.device.type == 'cuda':
+      self.net.wgrad_stream = torch.cuda.Stream(device=params.device)
+      self.buckets.also_wait.append(self.net.wgrad_stream)   # a bucket is final only when its wgrads have run
     self.global_step = 0
     self._lr_host = None
 

@@ -30,6 +30,9 @@ PSP_BINS = (1, 2, 3, 6)
 
 
 FOV_SCOPE = 'feature_extractor/extension/increase_fov'
+# --upsampling_method hybrid: one slim.conv2d_transpose per head inside variable_scope('upsampling'), default
+# scopes Conv2d_transpose, Conv2d_transpose_1, _2 (resnet50_extended_model_hierarchical.py:84-86,161-179)
+UPSAMPLING_SCOPES = tuple('softmax_classifier/upsampling/Conv2d_transpose' + ('' if i == 0 else f'_{i}') for i in range(3))
 
 
 def conv_specs(dataset='cityscapes', feature_dims_decreased=256, psp=False, fov=None):
@@ -68,7 +71,7 @@ def conv_specs(dataset='cityscapes', feature_dims_decreased=256, psp=False, fov=
   return specs
 
 
-def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False, psp=False, fov=None):
+def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False, psp=False, fov=None, upsampling='bilinear'):
   """Random init as the reference's arg scope does (variance scaling conv
   kernels, gamma=1, beta=0, moving_mean=0, moving_var=1;
   resnet50_extended_model_hierarchical.py:335-340).  `randomize_bn=True`
@@ -93,6 +96,10 @@ def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False, ps
       params[f'{scope}/BatchNorm/moving_variance'] = torch.ones(c)
     if tame and (scope.endswith('/conv3') or scope.endswith('/shortcut')):
       params[f'{scope}/BatchNorm/gamma'] = params[f'{scope}/BatchNorm/gamma'] * 0.5
+  if upsampling == 'hybrid':
+    for sc, c in zip(UPSAMPLING_SCOPES, TABLES[dataset]['head_widths']):
+      params[f'{sc}/weights'] = tfops.variance_scaling_trunc_normal((3, 3, c, c), g)   # [kh, kw, out, in]
+      params[f'{sc}/biases'] = (0.1 * torch.randn(c, generator=g)) if randomize_bn else torch.zeros(c)
   return params
 
 
@@ -137,8 +144,9 @@ class Net:
   """
 
   def __init__(self, params, dataset='cityscapes', training=False, bn_decay=0.9, eps=1e-5, storage='fp32',
-               psp=False, fov=None):
-    assert storage in ('fp32', 'bf16')
+               psp=False, fov=None, upsampling='bilinear'):
+    assert storage in ('fp32', 'bf16') and upsampling in ('bilinear', 'hybrid', 'no')
+    self.upsampling = upsampling
     self.psp = psp
     self.fov = fov  # (kernel size, dilation rate) of extension/increase_fov, or None
     self.storage = storage
@@ -266,6 +274,10 @@ class Net:
       a = self._bottleneck(f, f'adaptation_module/{br}/bottleneck_v1', d, d, 1, 1)
       # slim.conv2d(activation_fn=None) inside the arg scope: BN still applied
       out.append(self._conv_bn(a, f'softmax_classifier/{lg}', relu=False, fp32_out=True))
+    if self.upsampling == 'hybrid':
+      # _create_upsampler 'hybrid': 3x3 transposed convolution (stride 1, + bias, fp32) before the resize
+      out = [tfops.conv2d_transpose_same(z, self.p[f'{sc}/weights'], self.p[f'{sc}/biases'])
+             for z, sc in zip(out, UPSAMPLING_SCOPES)]
     return out
 
   def forward(self, images):
@@ -274,7 +286,10 @@ class Net:
     hf, wf = images.shape[1], images.shape[2]
     low = self.lowres_logits(images)
     t = TABLES[self.dataset]
-    l1, l2v, l2h = [tfops.resize_bilinear(z, hf, wf, align_corners=True) for z in low]
+    if self.upsampling == 'no':   # `upsampled = bottom`: everything downstream stays at the feature resolution
+      l1, l2v, l2h = low
+    else:
+      l1, l2v, l2h = [tfops.resize_bilinear(z, hf, wf, align_corners=True) for z in low]
     pred = compose_predictions(l1, l2v, l2h, self.dataset)
     pred['lowres_logits'] = low
     del t

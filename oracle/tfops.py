@@ -87,6 +87,18 @@ def avg_pool_valid(x, ksize, stride):
   return y.permute(0, 2, 3, 1)
 
 
+def conv2d_transpose_same(x, f_hwoi, bias=None):
+  """slim.conv2d_transpose(inputs, C, kernel_size, stride=1, padding='SAME') [TF-1.12]: the gradient of a
+  stride-1 SAME conv2d wrt its input; the filter variable has shape [kh, kw, out_channels, in_channels];
+  biases are added (the arg scope of the model only configures slim.conv2d, so this layer has no normaliser).
+  code/models/resnet50_extended_model_hierarchical.py:168-179 (`--upsampling_method hybrid`)."""
+  kh, kw = f_hwoi.shape[0], f_hwoi.shape[1]
+  assert kh % 2 == 1 and kw % 2 == 1
+  w = f_hwoi.permute(3, 2, 0, 1)   # torch: [in, out, kh, kw]
+  y = F.conv_transpose2d(x.permute(0, 3, 1, 2), w, stride=1, padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1)
+  return y if bias is None else y + bias
+
+
 def batch_norm(x, gamma, beta, moving_mean, moving_var, training, decay=0.9, eps=1e-5):
   """tf.contrib.layers.batch_norm (fused, NHWC) [TF-1.12].
 

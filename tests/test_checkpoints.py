@@ -135,16 +135,20 @@ def test_train_state_round_trip_and_restore_emas(cuda, tmp_path):
   emas = est.Estimator(settings(restore_emas=True), hier, device=cuda)
   emas.initialize(ckpt_path=path)
   assert torch.equal(emas.params.master, e.trainer.ws.ema_shadow) and torch.equal(emas.params.moving, e.params.moving)
-  # (b) TRAIN resume: same slots, and the next step equals the original's next step
+  # (b) TRAIN resume: weights, bf16 operands, Momentum and EMA slots are exactly the saved ones, and the next
+  # step gives the loss of the uninterrupted run (not bit-exact: atomics order, tests/test_gpu_train.py)
   r = est.Estimator(settings(), hier, device=cuda)
   r.initialize(log_dir=str(tmp_path), for_training=True)
   nxt = list(batches(1))
-  r.train(iter(nxt), 1)
-  e.train(iter(nxt), 1)
-  assert r.global_step == 3
-  assert torch.equal(r.trainer.ws.momentum.cpu(), e.trainer.ws.momentum.cpu()) or \
-      float((r.trainer.ws.momentum - e.trainer.ws.momentum).abs().max()) <= 1e-3 * float(e.trainer.ws.momentum.abs().max())
-  assert float((r.params.master - e.params.master).abs().max()) <= 1e-4
+  r.train(iter(nxt), 0)   # creates the trainer and imports the slots, no step
+  assert r.global_step == 2 and r.trainer.global_step == 2
+  assert torch.equal(r.params.master, e.params.master) and torch.equal(r.params.operand, e.params.operand)
+  assert torch.equal(r.trainer.ws.momentum, e.trainer.ws.momentum)
+  assert torch.equal(r.trainer.ws.ema_shadow, e.trainer.ws.ema_shadow)
+  lr_, le_ = r.train(iter(nxt), 1), e.train(iter(nxt), 1)
+  assert r.global_step == 3 and np.isfinite(lr_).all()
+  print('resumed vs uninterrupted losses', lr_[0].tolist(), le_[0].tolist())
+  assert np.allclose(lr_[0], le_[0], rtol=5e-2)
   # (c) warm start from an "ImageNet" file holding the base network under slim's names (+ a foreign variable)
   base = {k[len('feature_extractor/base/'):]: v for k, v in variables.items() if k.startswith('feature_extractor/base/')}
   base['resnet_v1_50/logits/weights'] = torch.zeros(1, 1, 2048, 1000)

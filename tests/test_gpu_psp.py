@@ -163,3 +163,87 @@ def test_train_step_with_psp_fp32(cuda, psp, fov):
     ref = gr.permute(3, 0, 1, 2).reshape(-1).double()
     c = float(torch.dot(got, ref) / (got.norm() * ref.norm()))
     assert c >= 0.999, (sc, c)               # ... and the same one here
+
+
+# ---- --upsampling_method hybrid / no (code/models/resnet50_extended_model_hierarchical.py:143-184) ---------------
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('dataset', ['cityscapes', 'vistas'])
+def test_forward_hybrid_upsampling_matches_oracle(cuda, dtype, tol, dataset):
+  from wlseg import hierarchy, network, problem_defs
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  tf_params = onet.init_params(dataset, seed=12, randomize_bn=True, tame=True, upsampling='hybrid')
+  params = network.Params(hier, cuda, upsampling='hybrid')
+  assert len(params.specs) == 69
+  params.load_tf_dict(tf_params)
+  back = params.to_tf_dict()   # the transposed-convolution filters survive the layout round trip
+  for k in tf_params:
+    assert torch.allclose(back[k], tf_params[k].float(), atol=0, rtol=0), k
+  net = network.Network(params, dtype=dtype)
+  g = torch.Generator().manual_seed(5)
+  images = torch.rand(2, 64, 96, 3, generator=g) * 2 - 1
+  out = net.predict(images.to(cuda), want=('decisions', 'l1_probabilities'))
+  torch.cuda.synchronize()
+  ref = onet.Net(tf_params, dataset, upsampling='hybrid').forward(images)
+  ref_low = torch.cat(ref['lowres_logits'], -1)
+  got_low = out['lowres_logits'][..., :hier.total_channels].cpu()
+  emax, el2 = _rel(got_low, ref_low), float((got_low - ref_low).norm() / ref_low.norm())
+  print(f'hybrid {dataset} {dtype}: post-upsampler low-res logits max-rel {emax:.3e} rel-L2 {el2:.3e}')
+  assert emax <= tol and el2 <= tol
+  plain = torch.cat(onet.Net(tf_params, dataset).forward(images)['lowres_logits'], -1)
+  assert float((plain - ref_low).norm() / ref_low.norm()) > 10 * tol   # the layer is not a no-op
+  assert float((out['decisions'].cpu() != ref['decisions']).float().mean()) <= (1e-3 if dtype == torch.float32 else 0.05)
+
+
+def test_forward_no_upsampling(cuda):
+  """`upsampled = bottom`: probabilities and decisions at the feature resolution."""
+  hier, tf_params, _, _ = _setup(cuda, torch.float32, 9, psp=False)
+  from wlseg import network
+  params = network.Params(hier, cuda, upsampling='no')
+  params.load_tf_dict(tf_params)
+  net = network.Network(params, dtype=torch.float32)
+  g = torch.Generator().manual_seed(6)
+  images = torch.rand(1, 64, 96, 3, generator=g) * 2 - 1
+  out = net.predict(images.to(cuda), want=('decisions', 'l1_probabilities'))
+  ref = onet.Net(tf_params, 'cityscapes', upsampling='no').forward(images)
+  assert tuple(out['decisions'].shape) == (1, 8, 12) == tuple(ref['decisions'].shape)
+  assert float((out['l1_probabilities'].cpu() - ref['l1_probabilities']).abs().max()) <= 1e-4
+  assert float((out['decisions'].cpu() != ref['decisions']).float().mean()) <= 0.02
+
+
+def test_train_step_hybrid_upsampling_fp32(cuda):
+  """One training step with the transposed-convolution upsampler: losses, and the gradients of its filters
+  (in TF's [kh, kw, out, in] layout) and biases against autograd of the oracle."""
+  from wlseg import hierarchy, network, problem_defs
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  tf_params = onet.init_params('cityscapes', seed=14, randomize_bn=True, tame=True, upsampling='hybrid')
+  params = network.Params(hier, cuda, upsampling='hybrid')
+  params.load_tf_dict(tf_params)
+  net = network.TrainNetwork(params, dtype=torch.float32)
+  H, W = 64, 96
+  g = torch.Generator().manual_seed(41)
+  images = torch.rand(2, H, W, 3, generator=g) * 2 - 1
+  labels = {'prolabels_per_pixel': torch.randint(0, 20, (2, H // 8, W // 8), generator=g, dtype=torch.int32)
+            .repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()}
+  logits = net.forward_train(images.to(cuda))
+  losses, dlogits = net.loss_and_grad(logits, {k: v.to(cuda) for k, v in labels.items()}, H, W)
+  net.backward(dlogits)
+  torch.cuda.synchronize()
+  p = {k: v.clone().requires_grad_(not k.endswith(('moving_mean', 'moving_variance'))) for k, v in tf_params.items()}
+  rl = olosses.define_losses(onet.Net(p, 'cityscapes', training=True, upsampling='hybrid').forward(images), labels,
+                             'cityscapes')
+  rl['total'].backward()
+  want = torch.stack([rl['l1_segmentation'], rl['l2_vehicle_segmentation'], rl['l2_human_segmentation'],
+                      rl['segmentation']]).detach()
+  assert torch.allclose(losses.cpu(), want, rtol=1e-4, atol=1e-5)
+  got = params.arena_to_tf_dict(net.ws.grads)
+  for sc in onet.UPSAMPLING_SCOPES:
+    for v in ('weights', 'biases'):
+      a, b = got[f'{sc}/{v}'].double().reshape(-1), p[f'{sc}/{v}'].grad.double().reshape(-1)
+      cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+      rel = float((a - b).norm() / b.norm())
+      print(f'{sc}/{v}: cosine {cos:.6f} rel-L2 {rel:.2e}')
+      assert cos >= 0.999 and rel <= 5e-2, (sc, v)
+  # and the gradient keeps flowing into the network below the upsampler
+  w = 'feature_extractor/base/resnet_v1_50/block3/unit_2/bottleneck_v1/conv2/weights'
+  a, b = got[w].double().reshape(-1), p[w].grad.double().reshape(-1)
+  assert float(torch.dot(a, b) / (a.norm() * b.norm())) >= 0.999
