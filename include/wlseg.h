@@ -159,6 +159,30 @@ int wlseg_maxpool_same_bwd(const void* x, const uint8_t* argmax, const void* dy,
                            int32_t dtype, wlseg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Group normalisation, `--norm_layer group` (tf.contrib.layers.group_norm, groups = 32 / 1 for the logits layers,
+ * models/resnet50_extended_model_hierarchical.py:75-77,314-333).  Statistics are per (sample, group) over
+ * H*W*(C/groups) values, biased variance, no moving statistics.  The per-sample passes over the activations are
+ * the batch-norm entry points above called on one sample's H*W rows (wlseg_bn_stats, wlseg_bn_apply,
+ * wlseg_bn_bwd_reduce); these three turn their per-(sample, channel) results into the per-(sample, channel)
+ * affine forms.  All arrays indexed [n * C + c].
+ *   gn_finalize:     sum / sqsum (double) -> scale, shift (y = z * scale + shift), mean, invstd
+ *   gn_bwd_finalize: dgamma_nc = sum g * xhat, dbeta_nc = sum g (double, from wlseg_bn_bwd_reduce with the mean /
+ *                    invstd rows of gn_finalize) -> cA, c1, c0 with dz = cA * g + c1 * z + c0, and
+ *                    dgamma[c] += sum_n dgamma_nc, dbeta[c] += sum_n dbeta_nc (double, accumulated into)
+ *   gn_bwd_apply:    dz (and dres = masked g) for the whole batch [N, hw, C]; ReLU mask from y, or from
+ *                    sign(fmaf(z, scale, shift)) when y is NULL
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_gn_finalize(const double* sum, const double* sqsum, int32_t N, int32_t C, int32_t groups, int64_t hw,
+                      const float* gamma, const float* beta, float eps, float* scale, float* shift, float* mean,
+                      float* invstd, wlseg_stream_t stream);
+int wlseg_gn_bwd_finalize(const double* dgamma_nc, const double* dbeta_nc, int32_t N, int32_t C, int32_t groups,
+                          int64_t hw, const float* gamma, const float* mean, const float* invstd, float* cA,
+                          float* c1, float* c0, double* dgamma, double* dbeta, wlseg_stream_t stream);
+int wlseg_gn_bwd_apply(const void* dy, const void* y, const void* z, const float* cA, const float* c1,
+                       const float* c0, const float* scale, const float* shift, int32_t N, int64_t hw, int32_t C,
+                       int32_t relu, int32_t dtype, void* dz, void* dres, wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Pyramid (PSP) module pieces, `--psp_module` (models/resnet50_extended_model_hierarchical.py:186-207):
  * slim.layers.avg_pool2d VALID (:191-200), tf.image.resize_images(bilinear, align_corners=True) of
  * the pooled branches back to the feature size (:193-202), and their gradients.  NHWC, C % 8 == 0.

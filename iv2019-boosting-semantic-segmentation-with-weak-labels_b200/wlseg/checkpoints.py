@@ -55,6 +55,9 @@ def model_variables(params):
       out += [(f'{s.scope}/weights', (s.R, s.S, s.K, s.C)), (f'{s.scope}/biases', (s.K,))]
       continue
     out.append((f'{s.scope}/weights', (s.R, s.S, s.C, s.K)))
+    if getattr(params, 'norm', 'batch') == 'group':   # tf.contrib.layers.group_norm: beta, gamma, no moving statistics
+      out += [(f'{s.scope}/GroupNorm/beta', (s.K,)), (f'{s.scope}/GroupNorm/gamma', (s.K,))]
+      continue
     for v in ('beta', 'gamma', 'moving_mean', 'moving_variance'):
       out.append((f'{s.scope}/BatchNorm/{v}', (s.K,)))
   return out

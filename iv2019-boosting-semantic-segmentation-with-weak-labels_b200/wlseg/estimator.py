@@ -138,7 +138,8 @@ class Estimator:
                                  psp=getattr(params, 'psp_module', False),
                                  fov=(getattr(params, 'fov_expansion_kernel_size', 0),
                                       getattr(params, 'fov_expansion_kernel_rate', 0)),
-                                 upsampling=getattr(params, 'upsampling_method', 'bilinear'))
+                                 upsampling=getattr(params, 'upsampling_method', 'bilinear'),
+                                 norm=getattr(params, 'norm_layer', 'batch'))
     self.global_step = 0
     self.net = None
     self.last_h2d_bytes = 0
@@ -185,8 +186,9 @@ class Estimator:
         variables, _ = checkpoints.load_file(init)
         mapping = checkpoints.warm_start(self.params, variables, psp_module=getattr(self.settings, 'psp_module', False))
         print(f'initialised {len(mapping)} variables from {init}', flush=True)
-    self.net = network.Network(self.params, dtype=self.dtype,
-                               bn_decay=getattr(self.settings, 'batch_norm_decay', 0.9))
+    # group norm has no folded inference form: its evaluation forward is the training forward (network.py)
+    cls = network.TrainNetwork if self.params.norm == 'group' else network.Network
+    self.net = cls(self.params, dtype=self.dtype, bn_decay=getattr(self.settings, 'batch_norm_decay', 0.9))
     return path
 
   # ---- TRAIN --------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ def _trunc_normal_(t, std, gen):
 class Params:
   """All trainable variables + BN moving statistics, addressable by TF variable name."""
 
-  def __init__(self, hier, device, output_stride=8, psp=False, fov=None, upsampling='bilinear'):
+  def __init__(self, hier, device, output_stride=8, psp=False, fov=None, upsampling='bilinear', norm='batch'):
     self.hier = hier
     self.device = torch.device(device)
     self.psp = bool(psp)  # --psp_module: five more convolutions (arch.PSP_SCOPES)
@@ -39,6 +39,12 @@ class Params:
     self.upsampling = upsampling
     self.specs = arch.conv_specs(hier.head_widths, output_stride, psp=self.psp, fov=self.fov, upsampling=upsampling)
     self.plain = set(arch.UPSAMPLING_SCOPES) if upsampling == 'hybrid' else set()   # layers without batch norm
+    # --norm_layer: 'batch' | 'group' (tf.contrib.layers.group_norm: variables <scope>/GroupNorm/{beta,gamma}, no moving
+    # statistics; 32 groups, 1 for the logits layers - models/resnet50_extended_model_hierarchical.py:75-77,314-333)
+    if norm not in ('batch', 'group'):
+      raise ValueError('norm_type not valid.')   # module_arg_scope, :296-297
+    self.norm = norm
+    self.norm_scope = 'BatchNorm' if norm == 'batch' else 'GroupNorm'
     self.by_scope = {s.scope: s for s in self.specs}
     self.w_off, self.c_off = {}, {}
     off = 0
@@ -93,6 +99,13 @@ class Params:
   def moving_var(self, scope, n=None):
     return self._cview(self.moving, self.n_chan_pad, scope, n)
 
+  def groups(self, scope, K=None):
+    """Number of normalisation groups of the layer `scope` covering K channels (K > the layer's own width for the
+    merged adaptation conv1 layers: every branch keeps its own 32 groups)."""
+    width = self.by_scope[scope].K
+    gs = width if scope.startswith('softmax_classifier/') else width // 32
+    return (width if K is None else K) // gs
+
   # ---- initialisation / import --------------------------------------------------------------
   def init_random(self, seed=0):
     """variance_scaling_initializer() defaults: truncated normal, stddev sqrt(1.3*2/fan_in)
@@ -127,11 +140,13 @@ class Params:
         continue
       assert tuple(w.shape) == (s.R, s.S, s.C, s.K), (s.scope, tuple(w.shape))
       host[o:o + w.numel()] = w.permute(3, 0, 1, 2).reshape(-1)
-      host[self.n_conv_pad + c:self.n_conv_pad + c + s.K] = tensors[f'{s.scope}/BatchNorm/gamma']
+      ns = self.norm_scope
+      host[self.n_conv_pad + c:self.n_conv_pad + c + s.K] = tensors[f'{s.scope}/{ns}/gamma']
       host[self.n_conv_pad + self.n_chan_pad + c:self.n_conv_pad + self.n_chan_pad + c + s.K] = \
-          tensors[f'{s.scope}/BatchNorm/beta']
-      mov[c:c + s.K] = tensors[f'{s.scope}/BatchNorm/moving_mean']
-      mov[self.n_chan_pad + c:self.n_chan_pad + c + s.K] = tensors[f'{s.scope}/BatchNorm/moving_variance']
+          tensors[f'{s.scope}/{ns}/beta']
+      if self.norm == 'batch':
+        mov[c:c + s.K] = tensors[f'{s.scope}/BatchNorm/moving_mean']
+        mov[self.n_chan_pad + c:self.n_chan_pad + c + s.K] = tensors[f'{s.scope}/BatchNorm/moving_variance']
     self.master.copy_(host)
     self.moving.copy_(mov)
     self.sync_operands()
@@ -144,10 +159,11 @@ class Params:
         out[f'{s.scope}/biases'] = self.beta(s.scope).cpu().clone()
         continue
       out[f'{s.scope}/weights'] = self.w32(s.scope).permute(1, 2, 3, 0).contiguous().cpu()
-      out[f'{s.scope}/BatchNorm/gamma'] = self.gamma(s.scope).cpu().clone()
-      out[f'{s.scope}/BatchNorm/beta'] = self.beta(s.scope).cpu().clone()
-      out[f'{s.scope}/BatchNorm/moving_mean'] = self.moving_mean(s.scope).cpu().clone()
-      out[f'{s.scope}/BatchNorm/moving_variance'] = self.moving_var(s.scope).cpu().clone()
+      out[f'{s.scope}/{self.norm_scope}/gamma'] = self.gamma(s.scope).cpu().clone()
+      out[f'{s.scope}/{self.norm_scope}/beta'] = self.beta(s.scope).cpu().clone()
+      if self.norm == 'batch':
+        out[f'{s.scope}/BatchNorm/moving_mean'] = self.moving_mean(s.scope).cpu().clone()
+        out[f'{s.scope}/BatchNorm/moving_variance'] = self.moving_var(s.scope).cpu().clone()
     return out
 
   def arena_to_tf_dict(self, arena):
@@ -160,8 +176,8 @@ class Params:
         out[f'{s.scope}/biases'] = self._cview(arena, self.n_conv_pad + self.n_chan_pad, s.scope).cpu().clone()
         continue
       out[f'{s.scope}/weights'] = self._wview(arena, s.scope).permute(1, 2, 3, 0).contiguous().cpu()
-      out[f'{s.scope}/BatchNorm/gamma'] = self._cview(arena, self.n_conv_pad, s.scope).cpu().clone()
-      out[f'{s.scope}/BatchNorm/beta'] = self._cview(arena, self.n_conv_pad + self.n_chan_pad, s.scope).cpu().clone()
+      out[f'{s.scope}/{self.norm_scope}/gamma'] = self._cview(arena, self.n_conv_pad, s.scope).cpu().clone()
+      out[f'{s.scope}/{self.norm_scope}/beta'] = self._cview(arena, self.n_conv_pad + self.n_chan_pad, s.scope).cpu().clone()
     return out
 
   def load_into_arena(self, arena, named):
@@ -184,7 +200,7 @@ class Params:
         host[o:o + t.numel()] = t.to(torch.float32).permute(3, 0, 1, 2).reshape(-1)
       c = self.c_off[s.scope]
       for v, base in (('gamma', self.n_conv_pad), ('beta', self.n_conv_pad + self.n_chan_pad)):
-        t = named.get(f'{s.scope}/BatchNorm/{v}')
+        t = named.get(f'{s.scope}/{self.norm_scope}/{v}')
         if t is not None:
           host[base + c:base + c + s.K] = t.to(torch.float32)
     arena.copy_(host)
@@ -506,7 +522,7 @@ class Network:
 # ================================================================================================
 class _Rec:
   """Tape entry of one conv + BN (+ residual) (+ ReLU) layer."""
-  __slots__ = ('scope', 'spec', 'x', 'w', 'z', 'a', 'relu', 'has_res', 'geom', 'nch', 'kind',
+  __slots__ = ('scope', 'spec', 'x', 'w', 'z', 'a', 'relu', 'has_res', 'geom', 'nch', 'kind', 'gn',
                'res', 'da', 'dz', 'dx', 'dx_add')  # the last five only when TrainNetwork.keep (tests)
 
 
@@ -598,13 +614,17 @@ class TrainNetwork(Network):
     ws, off = self.ws, self.p.c_off[scope]
     s1, s2 = ws.view(ws.stat, 0, off, K), ws.view(ws.stat, 1, off, K)
     zdt = torch.float32 if y_f32 else self.dtype
+    group = self.p.norm == 'group'
     z = self._conv(x, w, stride=stride, dilation=dilation, pad=pad, out_hw=out_hw, y_dtype=zdt,
-                   bn_sum=s1, bn_sqsum=s2)
+                   bn_sum=None if group else s1, bn_sqsum=None if group else s2)
     scale, shift = ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K)
     mean, invstd = ws.view(ws.bn, 2, off, K), ws.view(ws.bn, 3, off, K)
     a = torch.empty_like(z)
     do_relu = spec.relu if relu is None else relu
-    if self.cross_replica is not None:
+    gn = None
+    if group:
+      gn = self._gn_forward(z, scope, K, do_relu, residual, a)
+    elif self.cross_replica is not None:
       # global moments: one all-reduce of this layer's [sum | sqsum]; every replica has the same count
       R = self.cross_replica[0]
       both = self._all_reduce_pair(s1, s2)
@@ -623,9 +643,52 @@ class TrainNetwork(Network):
     rec = _Rec()
     rec.scope, rec.spec, rec.x, rec.w, rec.z, rec.a = scope, spec, x, w, z, a
     rec.relu, rec.has_res, rec.geom, rec.nch, rec.kind = do_relu, residual is not None, (pad, out_hw, stride, dilation), K, kind
+    rec.gn = gn
     rec.res = residual if self.keep else None
     self.tape[scope] = rec
     return a
+
+  # ---- group norm (--norm_layer group): the per-sample passes are the batch-norm kernels on one sample's rows ----
+  def _gn_forward(self, z, scope, K, relu, residual, a):
+    """z [N, P, Q, K] -> a = relu?(group_norm(z) (+ residual)); returns the per-(sample, channel) rows
+    [scale | shift | mean | invstd] (fp32 [4, N, K]) the backward pass needs."""
+    N, P, Q, _ = z.shape
+    hw = P * Q
+    sums = torch.zeros((2, N, K), dtype=torch.float64, device=self.dev)
+    for n in range(N):
+      ops.bn_stats(z[n], hw, K, z.stride(2), sums[0, n], sums[1, n])
+    coef = torch.empty((4, N, K), dtype=torch.float32, device=self.dev)
+    ops.gn_finalize(sums[0], sums[1], N, K, self.p.groups(scope, K), hw, self.p.gamma(scope, K), self.p.beta(scope, K),
+                    self.eps, coef[0], coef[1], coef[2], coef[3])
+    for n in range(N):
+      ops.bn_apply(z[n], coef[0, n], coef[1, n], None if residual is None else residual[n], a[n], hw, K, relu)
+    return coef
+
+  def _gn_backward(self, rec, da, scope, K, dgamma, dbeta):
+    """-> (dz, dres) of a group-normalised layer; dgamma / dbeta (fp64 accumulators) receive the parameter sums."""
+    N, P, Q, _ = rec.z.shape
+    hw = P * Q
+    coef = rec.gn
+    y = rec.a if (rec.relu and (rec.has_res or K % 8 != 0)) else None
+    da = da.contiguous()
+    part = torch.zeros((2, N, K), dtype=torch.float64, device=self.dev)
+    for n in range(N):
+      ops.bn_bwd_reduce(da[n], None if y is None else y[n], rec.z[n], coef[2, n], coef[3, n], hw, K, rec.relu,
+                        part[0, n], part[1, n], scale=coef[0, n], shift=coef[1, n], pitch=K)
+    k = torch.empty((3, N, K), dtype=torch.float32, device=self.dev)
+    ops.gn_bwd_finalize(part[0], part[1], N, K, self.p.groups(scope, K), hw, self.p.gamma(scope, K), coef[2], coef[3],
+                        k[0], k[1], k[2], dgamma, dbeta)
+    dz = torch.empty_like(rec.z)
+    dres = torch.empty_like(rec.z) if rec.has_res else None
+    ops.gn_bwd_apply(da, y, rec.z, k[0], k[1], k[2], coef[0], coef[1], N, hw, K, rec.relu, dz, dres)
+    return dz, dres
+
+  def lowres_logits_infer(self, images):
+    """Group norm has no inference form of its own (no moving statistics): the evaluation forward IS the
+    training forward.  Batch norm keeps the folded-scale/shift path of the base class."""
+    if self.p.norm == 'group':
+      return self.forward_train(images)
+    return super().lowres_logits_infer(images)
 
   def _all_reduce_pair(self, a, b):
     """SUM over replicas of two per-channel fp64 vectors with ONE collective; returns [a | b] summed."""
@@ -654,6 +717,9 @@ class TrainNetwork(Network):
     dgamma, dbeta = ws.view(ws.stat, 2, off, K), ws.view(ws.stat, 3, off, K)
     scale, shift = ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K)
     gamma = self.p.gamma(scope, K)
+    if self.p.norm == 'group':
+      dz, dres = self._gn_backward(rec, da, scope, K, dgamma, dbeta)
+      return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add)
     dz = torch.empty_like(rec.z)
     dres = torch.empty_like(rec.z) if rec.has_res else None
     # the ReLU mask of a layer without a residual input is recomputed from z (y is not read at all)
@@ -682,6 +748,12 @@ class TrainNetwork(Network):
       ops.bn_bwd_apply(da[..., sl], None if y is None else y[..., sl], rec.z[..., sl], mean[sl], invstd[sl], gamma[sl],
                        dgamma[sl], dbeta[sl], count, kk, rec.relu, dz[..., sl], None if dres is None else dres[..., sl],
                        scale=scale[sl], shift=shift[sl], pitch=K)
+    return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add)
+
+  def _layer_bwd_convs(self, rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add):
+    """Second half of _layer_bwd: filter gradient and data gradient from dz (normaliser independent)."""
+    pad, out_hw, stride, dilation = rec.geom
+    N, H, W, C = rec.x.shape
     wsrc = rec.w
     if dz.dtype != self.dtype or (self.dtype == torch.bfloat16 and K % 8 != 0):
       # logits layers (fp32 z, 14/7/3 channels) feeding bf16 tensor-core kernels: bf16 copy of dz with

@@ -63,6 +63,9 @@ _SIGNATURES = {
                                               _vp]),
     'wlseg_maxpool_same_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                               _c_int, _vp]),
+    'wlseg_gn_finalize': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_i64, _vp, _vp, _c_f, _vp, _vp, _vp, _vp, _vp]),
+    'wlseg_gn_bwd_finalize': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_i64] + [_vp] * 9),
+    'wlseg_gn_bwd_apply': (ctypes.c_int, [_vp] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     'wlseg_avgpool_valid_fwd': (ctypes.c_int, [_vp, _vp] + [_c_int] * 9 + [_vp]),
     'wlseg_avgpool_valid_bwd': (ctypes.c_int, [_vp, _vp] + [_c_int] * 8 + [_vp]),
     'wlseg_resize_bilinear_fwd': (ctypes.c_int, [_vp, _vp] + [_c_int] * 8 + [_vp]),
@@ -293,6 +296,28 @@ def bn_bwd_apply(dy, y, z, mean, invstd, gamma, dgamma, dbeta, count, C, relu, d
                                   C, C if pitch is None else pitch,
                                   int(relu), dtype_code(z.dtype), _ptr(dz), _ptr(dres), _stream()),
          'wlseg_bn_bwd_apply')
+  _count()
+  return dz
+
+
+# ------------------------------------------------------------------------------------ group norm
+def gn_finalize(sum_nc, sqsum_nc, N, C, groups, hw, gamma, beta, eps, scale, shift, mean, invstd):
+  _check(lib().wlseg_gn_finalize(_ptr(sum_nc), _ptr(sqsum_nc), N, C, groups, hw, _ptr(gamma), _ptr(beta), eps, _ptr(scale),
+                                 _ptr(shift), _ptr(mean), _ptr(invstd), _stream()), 'wlseg_gn_finalize')
+  _count()
+
+
+def gn_bwd_finalize(dgamma_nc, dbeta_nc, N, C, groups, hw, gamma, mean, invstd, cA, c1, c0, dgamma, dbeta):
+  _check(lib().wlseg_gn_bwd_finalize(_ptr(dgamma_nc), _ptr(dbeta_nc), N, C, groups, hw, _ptr(gamma), _ptr(mean),
+                                     _ptr(invstd), _ptr(cA), _ptr(c1), _ptr(c0), _ptr(dgamma), _ptr(dbeta), _stream()),
+         'wlseg_gn_bwd_finalize')
+  _count()
+
+
+def gn_bwd_apply(dy, y, z, cA, c1, c0, scale, shift, N, hw, C, relu, dz, dres=None):
+  assert dy.is_contiguous() and z.is_contiguous() and dz.is_contiguous()
+  _check(lib().wlseg_gn_bwd_apply(_ptr(dy), _ptr(y), _ptr(z), _ptr(cA), _ptr(c1), _ptr(c0), _ptr(scale), _ptr(shift), N, hw,
+                                  C, int(relu), dtype_code(z.dtype), _ptr(dz), _ptr(dres), _stream()), 'wlseg_gn_bwd_apply')
   _count()
   return dz
 

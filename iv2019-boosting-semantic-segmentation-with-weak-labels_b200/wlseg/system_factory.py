@@ -103,8 +103,9 @@ class SemanticSegmentation(object):
       # _validate_params, code/models/resnet50_extended_model_hierarchical.py:271-276
       raise ValueError('One of params.{fov_expansion_kernel_rate, fov_expansion_kernel_size} '
                        'is set. In order to take effect both should be set.')
-    if getattr(s, 'norm_layer', 'batch') != 'batch':
-      raise NotImplementedError('only --norm_layer batch is implemented.')
+    if getattr(s, 'norm_layer', 'batch') == 'group' and getattr(s, 'cross_replica_norm', False):
+      # module_arg_scope, code/models/resnet50_extended_model_hierarchical.py:331-333
+      raise ValueError('cross_replica_norm is supported only for batch normalization for now.')
     if for_training and getattr(s, 'upsampling_method', 'bilinear') == 'no':
       # the reference's graph fails here too: per-pixel labels (hf x wf) against logits at hf/8 x wf/8
       raise ValueError('--upsampling_method no: labels and logits differ in size, training is not possible.')

@@ -71,7 +71,8 @@ def conv_specs(dataset='cityscapes', feature_dims_decreased=256, psp=False, fov=
   return specs
 
 
-def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False, psp=False, fov=None, upsampling='bilinear'):
+def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False, psp=False, fov=None, upsampling='bilinear',
+                norm='batch'):
   """Random init as the reference's arg scope does (variance scaling conv
   kernels, gamma=1, beta=0, moving_mean=0, moving_var=1;
   resnet50_extended_model_hierarchical.py:335-340).  `randomize_bn=True`
@@ -96,6 +97,11 @@ def init_params(dataset='cityscapes', seed=0, randomize_bn=False, tame=False, ps
       params[f'{scope}/BatchNorm/moving_variance'] = torch.ones(c)
     if tame and (scope.endswith('/conv3') or scope.endswith('/shortcut')):
       params[f'{scope}/BatchNorm/gamma'] = params[f'{scope}/BatchNorm/gamma'] * 0.5
+    if norm == 'group':
+      # --norm_layer group: tf.contrib.layers.group_norm variables <scope>/GroupNorm/{beta,gamma}, no moving statistics
+      for v in ('gamma', 'beta'):
+        params[f'{scope}/GroupNorm/{v}'] = params.pop(f'{scope}/BatchNorm/{v}')
+      del params[f'{scope}/BatchNorm/moving_mean'], params[f'{scope}/BatchNorm/moving_variance']
   if upsampling == 'hybrid':
     for sc, c in zip(UPSAMPLING_SCOPES, TABLES[dataset]['head_widths']):
       params[f'{sc}/weights'] = tfops.variance_scaling_trunc_normal((3, 3, c, c), g)   # [kh, kw, out, in]
@@ -144,8 +150,10 @@ class Net:
   """
 
   def __init__(self, params, dataset='cityscapes', training=False, bn_decay=0.9, eps=1e-5, storage='fp32',
-               psp=False, fov=None, upsampling='bilinear'):
-    assert storage in ('fp32', 'bf16') and upsampling in ('bilinear', 'hybrid', 'no')
+               psp=False, fov=None, upsampling='bilinear', norm='batch'):
+    assert storage in ('fp32', 'bf16') and upsampling in ('bilinear', 'hybrid', 'no') and norm in ('batch', 'group')
+    assert norm == 'batch' or storage == 'fp32', 'the bf16-storage restatement covers batch norm only'
+    self.norm = norm
     self.upsampling = upsampling
     self.psp = psp
     self.fov = fov  # (kernel size, dilation rate) of extension/increase_fov, or None
@@ -161,6 +169,11 @@ class Net:
     self.layer_taps = {}  # scope -> (pre-BN conv output, layer output), filled when record_layers
 
   def _bn(self, x, scope):
+    if self.norm == 'group':
+      # module_arg_scope: groups = 32, and 1 under softmax_classifier (resnet50_extended_model_hierarchical.py:75-77);
+      # the same computation in every mode
+      groups = 1 if scope.startswith('softmax_classifier/') else 32
+      return tfops.group_norm(x, self.p[f'{scope}/GroupNorm/gamma'], self.p[f'{scope}/GroupNorm/beta'], groups, self.eps)
     bn = f'{scope}/BatchNorm'
     y, mm, mv, _, _ = tfops.batch_norm(
         x, self.p[f'{bn}/gamma'], self.p[f'{bn}/beta'],

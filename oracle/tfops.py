@@ -122,6 +122,19 @@ def batch_norm(x, gamma, beta, moving_mean, moving_var, training, decay=0.9, eps
   return y, moving_mean, moving_var, moving_mean, moving_var
 
 
+def group_norm(x, gamma, beta, groups, eps=1e-5):
+  """tf.contrib.layers.group_norm(x, groups, channels_axis=-1, reduction_axes=(-3, -2), epsilon) [TF-1.12]:
+  x [N, H, W, C] -> [N, H, W, G, C/G]; nn.moments over (H, W, C/G) (biased variance); gain = rsqrt(var + eps)
+  * gamma, offset = beta - mean * gain; y = x * gain + offset.  No moving statistics.
+  code/models/resnet50_extended_model_hierarchical.py:314-333 (`--norm_layer group`)."""
+  N, H, W, C = x.shape
+  xg = x.reshape(N, H, W, groups, C // groups)
+  mean = xg.mean(dim=(1, 2, 4), keepdim=True)
+  var = ((xg - mean) ** 2).mean(dim=(1, 2, 4), keepdim=True)
+  y = ((xg - mean) * torch.rsqrt(var + eps)).reshape(N, H, W, C)
+  return y * gamma + beta
+
+
 def cross_replica_batch_norm(xs, gamma, beta, moving_mean, moving_var, decay=0.9, eps=1e-5):
   """--cross_replica_norm, training mode: `xs` is the list of per-replica NHWC inputs.
   code/utils/cross_replica_batch_normalization.py:398-459:
