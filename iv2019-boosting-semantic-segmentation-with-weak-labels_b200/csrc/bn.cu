@@ -15,6 +15,11 @@
 
 namespace wlseg {
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 constexpr int kBnThreads = 256;
 constexpr int kBnUnroll = 4;
 
@@ -24,7 +29,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* __restrict__ z,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
                  const float* __restrict__ shift, int64_t count, int C, int pitch, int relu,
-                 double* __restrict__ out0, double* __restrict__ out1) {
+                 double* __restrict__ out0, double* __restrict__ out1, int cspan) {
   // forward (kBackward=false): a = z;  out0 += sum z, out1 += sum z^2
   // backward: a = dy; g = dy*(y>0 if relu); out0 += sum g*(z-mean)*invstd (dgamma), out1 += sum g (dbeta)
   //   the ReLU mask comes from yact, or - when yact is NULL (layers without a residual input) - from the
@@ -32,6 +37,19 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* _
   extern __shared__ float part[];  // [lanes][2][C]
   pdl_launch_dependents();
   pdl_wait();   // mean / invstd / dy all come from earlier kernels of the chain
+  // channel split: blockIdx.y owns the channels [blockIdx.y * cspan, + cspan) of every row it visits, so a
+  // channel's fp64 accumulator is hit by gridDim.x CTAs instead of by the whole grid (same-address L2 atomics
+  // serialise); a warp still reads 16 * cspan / 8 >= 512 contiguous bytes of a row
+  if (cspan < C) {
+    const int cb = blockIdx.y * cspan;
+    a += cb;
+    if (yact != nullptr) yact += cb;
+    if (z != nullptr) z += cb;
+    if (kBackward) { mean += cb; invstd += cb; if (scale != nullptr) { scale += cb; shift += cb; } }
+    out0 += cb;
+    out1 += cb;
+    C = cspan;
+  }
   const int cv = C / 8;
   const int lanes = kBnThreads / cv;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
@@ -461,10 +479,6 @@ bn_bwd_apply_rows_kernel(const T* __restrict__ dy, const T* __restrict__ yact, c
 // WLSEG_BN_FLAT=1 selects the flat-index kernels (A/B measurements; both forms are bit-identical)
 static bool bn_rows_enabled() { return getenv("WLSEG_BN_FLAT") == nullptr; }
 // tuning knobs of the row-mapped kernels (tools/bn_sweep.py): rows in flight per thread and CTAs per SM
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 static int bn_apply_u() { return env_int("WLSEG_BN_APPLY_U", 2); }
 static int bn_apply_ctas() { return env_int("WLSEG_BN_APPLY_CTAS", 4); }
 static int bn_bwd_u() { return env_int("WLSEG_BN_BWD_U", 2); }
@@ -474,8 +488,11 @@ template <typename T>
 static void launch_apply_rows(const void* z, const float* scale, const float* shift, const void* res, void* y, int64_t count,
                               int C, int relu, cudaStream_t s) {
   const int lanes = 256 / (C / 8);
-  const int U = bn_apply_u();
-  const int g = bw_grid(ceil_div(count, (int64_t)lanes * U) * 256, 256, bn_apply_ctas());
+  // measured (tools/bn_sweep.py, graph-timed, HBM-cold): without a residual one row per thread at full occupancy
+  // wins (871 vs 902 us per step-equivalent); with a residual stream two rows at 4 CTAs / SM do
+  const int U = res != nullptr ? bn_apply_u() : env_int("WLSEG_BN_APPLY_U_PLAIN", 1);
+  const int g = bw_grid(ceil_div(count, (int64_t)lanes * U) * 256, 256,
+                        res != nullptr ? bn_apply_ctas() : env_int("WLSEG_BN_APPLY_CTAS_PLAIN", 8));
   cudaError_t e;
   if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
   else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
@@ -588,14 +605,19 @@ static int launch_reduce(const void* a, const void* y, const void* z, const floa
     WLSEG_LAUNCH_CHECK();
     return 0;
   }
-  const int cv = C / 8;
-  const int lanes = kBnThreads / cv;
-  size_t smem = (size_t)lanes * 2 * C * sizeof(float);
   // 2 CTAs per SM: with kBnUnroll rows in flight per thread that saturates HBM, and it halves the number
   // of CTAs queueing on the same C fp64 accumulators at the end
-  int grid = bw_grid(ceil_div(count * cv, kBnUnroll), kBnThreads, 2);
-  WLSEG_CUDA(launch_pdl(bn_reduce_kernel<T, kBackward>, dim3(grid), dim3(kBnThreads), smem, s, (const T*)a, (const T*)y,
-                        (const T*)z, mean, invstd, scale, shift, count, C, pitch, relu, o0, o1));
+  const int per_sm = env_int("WLSEG_BN_RED_CTAS", 2);
+  int cspan = env_int("WLSEG_BN_RED_SPAN", 128);          // channels per CTA (0 = all of them); tools/bn_sweep.py
+  if (cspan <= 0 || cspan >= C || C % cspan != 0 || cspan % 8 != 0) cspan = C;
+  const int cv = cspan / 8;
+  const int lanes = kBnThreads / cv;
+  size_t smem = (size_t)lanes * 2 * cspan * sizeof(float);
+  const int ny = C / cspan;
+  int gx = bw_grid(ceil_div(count * cv, kBnUnroll), kBnThreads, per_sm) / ny;
+  if (gx < 1) gx = 1;
+  WLSEG_CUDA(launch_pdl(bn_reduce_kernel<T, kBackward>, dim3(gx, ny), dim3(kBnThreads), smem, s, (const T*)a, (const T*)y,
+                        (const T*)z, mean, invstd, scale, shift, count, C, pitch, relu, o0, o1, cspan));
   return 0;
 }
 

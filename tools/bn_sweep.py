@@ -19,17 +19,25 @@ def bufs(rows, C, n):
   return [[torch.randn(rows, C, device=dev).to(torch.bfloat16) for _ in range(n)] for _ in range(k)]
 
 
-def timed(fn, sets, reps=30):
-  for i in range(5):
+def timed(fn, sets, reps=24):
+  """GPU time per launch: the launches are captured into one CUDA graph (Python + ctypes launch overhead is
+  ~10 us per call and would hide every kernel shorter than that) and the graph is replayed."""
+  for i in range(3):
     fn(sets[i % len(sets)])
+  torch.cuda.synchronize()
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    for i in range(reps):
+      fn(sets[i % len(sets)])
+  g.replay()
   torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
-  for i in range(reps):
-    fn(sets[i % len(sets)])
+  for _ in range(3):
+    g.replay()
   e1.record()
   torch.cuda.synchronize()
-  return e0.elapsed_time(e1) * 1e3 / reps
+  return e0.elapsed_time(e1) * 1e3 / (3 * reps)
 
 
 def run(kind, rows, C):
@@ -57,7 +65,7 @@ def sweep(kind, configs):
   print(f'== {kind}: us per launch (GB/s algorithmic); last column = weighted us per step')
   print('config'.ljust(28) + ''.join(f'{r}x{c}'.rjust(18) for r, c, _ in SHAPES) + '   step_us')
   for name, env in configs:
-    for k in ('WLSEG_BN_FLAT', 'WLSEG_BN_APPLY_U', 'WLSEG_BN_APPLY_CTAS', 'WLSEG_BN_BWD_U', 'WLSEG_BN_BWD_CTAS'):
+    for k in KNOBS:
       os.environ.pop(k, None)
     os.environ.update(env)
     line, tot = name.ljust(28), 0.0
@@ -68,11 +76,15 @@ def sweep(kind, configs):
     print(line + f'{tot:10.0f}', flush=True)
 
 
+KNOBS = ('WLSEG_BN_FLAT', 'WLSEG_BN_APPLY_U', 'WLSEG_BN_APPLY_CTAS', 'WLSEG_BN_BWD_U', 'WLSEG_BN_BWD_CTAS',
+         'WLSEG_BN_RED_CTAS', 'WLSEG_BN_RED_SPAN')
+
 if __name__ == '__main__':
+  sweep('reduce', [(f'span={sp} ctas={c}', {'WLSEG_BN_RED_SPAN': str(sp), 'WLSEG_BN_RED_CTAS': str(c)})
+                   for sp, c in ((0, 2), (0, 1), (0, 4), (256, 2), (256, 4), (512, 2), (128, 2))])
   sweep('apply', [('flat', {'WLSEG_BN_FLAT': '1'})] + [(f'rows U={u} ctas={c}', {'WLSEG_BN_APPLY_U': str(u), 'WLSEG_BN_APPLY_CTAS': str(c)})
                                                      for u, c in ((1, 8), (2, 4), (2, 8), (4, 2), (4, 4))])
   sweep('apply_res', [('flat', {'WLSEG_BN_FLAT': '1'})] + [(f'rows U={u} ctas={c}', {'WLSEG_BN_APPLY_U': str(u), 'WLSEG_BN_APPLY_CTAS': str(c)})
                                                          for u, c in ((1, 8), (2, 4), (4, 2))])
   sweep('bwd', [('flat', {'WLSEG_BN_FLAT': '1'})] + [(f'rows U={u} ctas={c}', {'WLSEG_BN_BWD_U': str(u), 'WLSEG_BN_BWD_CTAS': str(c)})
-                                                   for u, c in ((1, 3), (1, 6), (2, 2), (2, 4), (4, 1), (4, 2))])
-  sweep('reduce', [('current', {})])
+                                                   for u, c in ((1, 3), (1, 6), (2, 2), (2, 3), (2, 4), (4, 1), (4, 2))])

@@ -1,0 +1,69 @@
+"""In-situ kernel timeline of the replayed training / evaluation step (CUPTI activity records through
+torch.profiler: kernels run back to back inside the CUDA graph exactly as in the bench, unlike ncu's serialised
+cold-cache replays).  Prints per-kernel totals per step, the busy time and the idle gaps between kernels."""
+import collections
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'iv2019-boosting-semantic-segmentation-with-weak-labels_b200'))
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+from wlseg import hierarchy, network, ops, problem_defs, synthetic, trainer as wtrainer  # noqa: E402
+
+mode = sys.argv[1] if len(sys.argv) > 1 else 'train'
+dev = torch.device('cuda:0')
+hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+params = network.Params(hier, dev)
+params.init_random(0)
+src = synthetic.SyntheticInputs(hier.num_classes, dev)
+STEPS = 3
+if mode == 'train':
+  class S:
+    momentum, use_nesterov, optimizer, regularization_weight = 0.9, False, 'SGDM', 0.00017
+    batch_norm_decay, distribute, ema_decay = 0.9, False, 0.0
+  tr = wtrainer.Trainer(params, S, dtype=torch.bfloat16)
+  batches = [src.train_batch(4, 0, 0, 768, 768) for _ in range(2)]
+
+  def step(i):
+    f, l = batches[i % 2]
+    return tr.step(f, {k: v for k, v in l.items() if v is not None}, 0.01)
+else:
+  net = network.Network(params, dtype=torch.bfloat16)
+  batches = [src.eval_batch(4, 1024, 2048) for _ in range(2)]
+  cm = torch.zeros(20, 20, dtype=torch.int64, device=dev)
+
+  def step(i):
+    f, l = batches[i % 2]
+    out = net.predict(f['proimages'], want=('decisions',))
+    ops.confmat_accumulate(l['prolabels'], out['decisions'], 20, cm)
+for i in range(5):
+  step(i)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+  for i in range(STEPS):
+    step(i)
+  torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ev.sort(key=lambda e: e.time_range.start)
+busy, span0, span1 = 0.0, ev[0].time_range.start, max(e.time_range.end for e in ev)
+agg = collections.OrderedDict()
+gaps, last_end = [], None
+for e in ev:
+  d = e.time_range.end - e.time_range.start
+  name = re.sub(r'\(.*', '', e.name)[:70]
+  a = agg.setdefault(name, [0, 0.0])
+  a[0] += 1
+  a[1] += d
+  busy += d
+  if last_end is not None:
+    gaps.append(max(0.0, e.time_range.start - last_end))
+  last_end = max(last_end or 0, e.time_range.end)
+span = span1 - span0
+print(f'{mode}: {STEPS} steps, span {span / STEPS / 1e3:.3f} ms/step, kernel busy {busy / STEPS / 1e3:.3f} ms/step, '
+      f'{len(ev) // STEPS} kernels/step, idle between kernels {sum(gaps) / STEPS / 1e3:.3f} ms/step '
+      f'(median gap {sorted(gaps)[len(gaps) // 2]:.2f} us)')
+print(f'{"us/step":>10} {"n/step":>7} {"share":>6}  kernel')
+for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+  print(f'{t / STEPS:10.1f} {n / STEPS:7.1f} {100 * t / busy:5.1f}%  {name}')
