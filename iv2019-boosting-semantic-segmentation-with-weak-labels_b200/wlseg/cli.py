@@ -84,15 +84,49 @@ def predict_main(argv):
   ss = wsettings.build_parser(wsettings.PREDICT)
   st = wsettings.predict_extra_args(ss.parse_args(argv))
   _dist_env(st)
-  for flag in ('plotting', 'plotting_overlapped', 'export_color_decisions', 'export_overlapped_color_decisions',
-               'export_lids_images'):
+  for flag in ('plotting', 'plotting_overlapped'):
     if getattr(st, flag, False):
-      raise NotImplementedError(f'--{flag}: plotting / export is outside the B200 hot path')
+      raise NotImplementedError(f'--{flag}: live matplotlib plotting is outside the B200 hot path')
   system = SemanticSegmentation({'predict': synthetic.predict_input_fn}, None, st)
+  s = system.settings
+  exporting = any(getattr(s, f, False) for f in ('export_lids_images', 'export_color_decisions',
+                                                 'export_overlapped_color_decisions'))
+  if exporting:
+    # code/predict.py:213-219 (_validate_settings) and :78-83 (palettes from the inference problem definition)
+    if not s.results_dir or not os.path.isdir(s.results_dir):
+      raise ValueError('results_dir must be an existing directory when an export flag is given.')
+    idspalette = np.array(s.inference_problem_def.get('cids2lids', []), dtype=np.uint8)
+    colorpalette = np.array(s.inference_problem_def['cids2colors'], dtype=np.uint8)
   start = total = datetime.now()
   n = 0
   for outputs in system.predict():
     n += 1
     print(f"\nTime per image (input pipeline + network): {datetime.now() - start}", outputs['decisions'].shape)
+    if exporting:
+      export_outputs(outputs, s, idspalette, colorpalette)
     start = datetime.now()
   print('\nTotal time (input pipeline + network):', datetime.now() - total, 'for', n, 'image(s)')
+
+
+def export_outputs(outputs, s, idspalette, colorpalette):
+  """code/predict.py:137-164: label-id PNG, colour PNG, and the colour map blended 50:50 over the raw image.
+  Host-side palette look-ups on the decisions `SemanticSegmentation.predict()` already returned."""
+  from PIL import Image
+  decs = outputs['decisions']
+  path = outputs['rawimagespaths']
+  stem = os.path.splitext(os.path.basename(path.decode() if isinstance(path, bytes) else str(path)))[0]
+
+  def save(arr, suffix):
+    out_fname = os.path.join(s.results_dir, stem + suffix)
+    assert not os.path.exists(out_fname), f'Output filename ({out_fname}) already exists.'
+    Image.fromarray(arr).save(out_fname)
+  if s.export_lids_images:
+    save(idspalette[decs], '_result_lids.png')
+  if s.export_color_decisions:
+    save(colorpalette[decs], '_result_color.png')
+  if s.export_overlapped_color_decisions:
+    raw = outputs['rawimages']
+    col = colorpalette[decs]
+    if raw.shape[:2] != col.shape[:2]:
+      raise ValueError(f'raw image {raw.shape[:2]} and decisions {col.shape[:2]} differ in size')
+    save((0.5 * raw + 0.5 * col).astype(np.uint8), '_result_overlapped_color.png')

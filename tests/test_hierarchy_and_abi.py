@@ -83,3 +83,24 @@ def test_product_does_not_import_the_oracle():
       if f.endswith('.py'):
         src = open(os.path.join(dirpath, f)).read()
         assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f'{f} imports the oracle'
+
+
+def test_predict_exports_palette_pngs(tmp_path):
+  """code/predict.py:137-164: label-id, colour and overlapped PNG exports are palette look-ups on the decisions."""
+  import argparse
+  import numpy as np
+  from PIL import Image
+  from wlseg import cli, problem_defs
+  pd = problem_defs.cityscapes()
+  s = argparse.Namespace(results_dir=str(tmp_path), export_lids_images=True, export_color_decisions=True,
+                         export_overlapped_color_decisions=True, inference_problem_def=pd)
+  rng = np.random.default_rng(0)
+  decs = rng.integers(0, 20, (6, 9), dtype=np.int32)
+  raw = rng.integers(0, 256, (6, 9, 3), dtype=np.uint8)
+  ids = np.array(pd['cids2lids'], dtype=np.uint8)
+  col = np.array(pd['cids2colors'], dtype=np.uint8)
+  cli.export_outputs({'decisions': decs, 'rawimages': raw, 'rawimagespaths': b'/data/frankfurt_000001.png'}, s, ids, col)
+  assert np.array_equal(np.asarray(Image.open(tmp_path / 'frankfurt_000001_result_lids.png')), ids[decs])
+  assert np.array_equal(np.asarray(Image.open(tmp_path / 'frankfurt_000001_result_color.png')), col[decs])
+  want = (0.5 * raw + 0.5 * col[decs]).astype(np.uint8)
+  assert np.array_equal(np.asarray(Image.open(tmp_path / 'frankfurt_000001_result_overlapped_color.png')), want)

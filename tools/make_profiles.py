@@ -98,7 +98,9 @@ def full_summary(rep, dst):
 
 def main():
   for name in ('bench_eval.json', 'bench_train.json', 'bench_reference.json', 'layers_eval.txt', 'layers_train.txt',
-               'eval_classes.json', 'train_classes.json', 'eval_launches.csv', 'train_launches.csv'):
+               'eval_classes.json', 'train_classes.json', 'eval_launches.csv', 'train_launches.csv',
+               'bench_train_mixed.json', 'bench_vistas_eval.json', 'bench_vistas_train.json', 'timeline_train.txt',
+               'timeline_eval.txt'):
     src = os.path.join(G, f'{R}_{name}')
     if os.path.exists(src):
       shutil.copy(src, os.path.join(P, f'{R}_{name}'))
