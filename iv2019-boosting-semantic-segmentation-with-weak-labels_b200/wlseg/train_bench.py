@@ -111,7 +111,10 @@ def run(args, cpu_train_sample=None):
                 'traffic_source': None if tsrc is None else 'profiles/' + tsrc,
                 'algorithmic_bytes_per_launch': dom['bytes'] / dom['launches'],
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)', 'launches': dom['launches'],
-                'share_of_step': dom['ms'] / prof_ms, 'timed_over': f'{prof_steps} eagerly launched steps after the timed region'}
+                # kernel time per step (event pairs of the eager pass) over the step time of the timed region (graph
+                # replay): the eager pass's own wall time is inflated by Python launch gaps and is not the step
+                'share_of_step': (dom['ms'] / prof_steps) / (ms_max / args.steps),
+                'timed_over': f'{prof_steps} eagerly launched steps after the timed region'}
   if args.detail and rank == 0:
     table = {k: {'launches': v['launches'], 'ms_per_step': v['ms'] / prof_steps,
                  'tflops': v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] else None,
