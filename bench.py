@@ -342,6 +342,29 @@ def run_wlseg_eval(args):
     dist.destroy_process_group()
 
 
+def host_link_probe(dev, world):
+  """What the end-to-end number rides on besides the step: pinned host -> device copy bandwidth of this rank's
+  PCIe path (128 MB, best of 3, CUDA events) and the CPUs this process may run on; the slowest rank is reported
+  (the job runs at its pace).  Explains an e2e value that falls below the device-resident one."""
+  import torch
+  import torch.distributed as dist
+  src = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
+  dst = torch.empty(128 << 20, dtype=torch.uint8, device=dev)
+  best = 0.0
+  for _ in range(4):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    best = max(best, src.numel() / (e0.elapsed_time(e1) / 1e3) / 1e9)
+  cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 0)
+  t = torch.tensor([-best, -float(cpus)], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  return {'h2d_gbs_slowest_rank': round(-float(t[0]), 2), 'cpus_per_rank_min': int(-float(t[1]))}
+
+
 def measure_e2e(args, dev, rank, world, H, W, NB):
   """Same metric through the reference-facing API (`SemanticSegmentation.evaluate` machinery) with
   HOST buffers: every step copies its fp32 images + int32 labels from pinned host memory and reads
@@ -408,7 +431,8 @@ def measure_e2e(args, dev, rank, world, H, W, NB):
   del types
   return {'value': world * args.steps * NB * H * W / 1e6 / dt, 'unit': 'Mpix/s',
           'h2d_bytes_per_step': est.last_h2d_bytes // args.steps, 'd2h_bytes_per_step': est.last_d2h_bytes // args.steps,
-          'ms_per_step': 1e3 * dt / args.steps, 'repeats': 3, 'stat': 'median of 3 repeats of the K-step region'}
+          'ms_per_step': 1e3 * dt / args.steps, 'repeats': 3, 'stat': 'median of 3 repeats of the K-step region',
+          'repeat_ms_per_step': [round(1e3 * d / args.steps, 3) for d in dts], 'host_link': host_link_probe(dev, world)}
 
 
 class StdoutToStderr:

@@ -166,11 +166,15 @@ def run(args, cpu_train_sample=None):
       if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
       dts.append(float(tt.item()))
+    raw_dts = list(dts)
     dts.sort()
     dt = dts[1]
     e2e = {'value': world * args.steps * nimg / dt, 'unit': 'images/s', 'h2d_bytes_per_step': est.last_h2d_bytes // args.steps,
            'd2h_bytes_per_step': est.last_d2h_bytes // args.steps, 'ms_per_step': 1e3 * dt / args.steps,
-           'repeats': 3, 'stat': 'median of 3 repeats of the K-step region'}
+           'repeats': 3, 'stat': 'median of 3 repeats of the K-step region',
+           'repeat_ms_per_step': [round(1e3 * d / args.steps, 3) for d in raw_dts]}
+    from bench import host_link_probe
+    e2e['host_link'] = host_link_probe(dev, world)
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline and cpu_train_sample is not None:
