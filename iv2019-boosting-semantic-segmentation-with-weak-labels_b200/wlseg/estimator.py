@@ -78,34 +78,52 @@ _PROB_KEYS = ('l1_probabilities', 'l2_vehicle_probabilities', 'l2_human_probabil
 
 
 class _Prefetcher:
-  """Double-buffered host->device staging: batch i+1 is copied (pinned memory, side stream) while
-  batch i computes.  Device-resident batches pass through untouched."""
+  """Host -> device staging: batch i+1 is copied (pinned memory, side stream) while batch i computes, into a
+  ring of `depth` device buffers per input, so the consumer sees a few RECURRING addresses (network.EvalStep
+  replays a CUDA graph per address set without copying) and nothing is allocated per step.  A ring slot is
+  overwritten only after the step that read it has finished (event on the consumer's stream).  Device-resident
+  batches pass through untouched."""
 
-  def __init__(self, it, device):
+  def __init__(self, it, device, depth=3, rings=None):
     self.it = iter(it)
     self.device = device
-    self.stream = torch.cuda.Stream(device=device)
+    # one copy stream per Estimator (kept with the rings): creating a stream per call is not free
+    holder = {} if rings is None else rings
+    self.stream = holder.get('__stream__')
+    if self.stream is None:
+      self.stream = holder['__stream__'] = torch.cuda.Stream(device=device)
     self.h2d_bytes = 0
+    self.depth = depth
+    self.rings = {} if rings is None else rings   # shared across calls by the Estimator: addresses stay put
+    self.count = 0
     self.next = None
-    self._advance()
+    self._advance(None)
 
-  def _to_dev(self, t):
+  def _to_dev(self, key, t, slot):
     if not torch.is_tensor(t) or t.is_cuda:
       return t
     if not t.is_pinned():
       t = t.pin_memory()
     self.h2d_bytes += t.numel() * t.element_size()
-    return t.to(self.device, non_blocking=True)
+    ring = self.rings.setdefault((key, tuple(t.shape), t.dtype), [None] * self.depth)
+    if ring[slot] is None:
+      ring[slot] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+    ring[slot].copy_(t, non_blocking=True)
+    return ring[slot]
 
-  def _advance(self):
+  def _advance(self, consumed):
     try:
       features, labels = next(self.it)
     except StopIteration:
       self.next = None
       return
+    slot = self.count % self.depth
+    self.count += 1
+    if consumed is not None:
+      self.stream.wait_event(consumed)   # every step that read this ring slot has completed
     with torch.cuda.stream(self.stream):
-      f = {k: self._to_dev(v) for k, v in features.items()}
-      l = None if labels is None else {k: self._to_dev(v) for k, v in labels.items()}
+      f = {k: self._to_dev(('f', k), v, slot) for k, v in features.items()}
+      l = None if labels is None else {k: self._to_dev(('l', k), v, slot) for k, v in labels.items()}
       ev = torch.cuda.Event()
       ev.record(self.stream)
     self.next = (f, l, ev)
@@ -117,12 +135,13 @@ class _Prefetcher:
     if self.next is None:
       raise StopIteration
     f, l, ev = self.next
-    torch.cuda.current_stream().wait_event(ev)
-    for d in (f, l or {}):
-      for v in d.values():
-        if torch.is_tensor(v) and v.is_cuda:
-          v.record_stream(torch.cuda.current_stream())
-    self._advance()
+    cur = torch.cuda.current_stream()
+    # the consumer has enqueued every earlier step by now: the copy of the NEXT batch (into the slot the batch
+    # depth - 1 steps back used) may start once all of that has run
+    consumed = torch.cuda.Event()
+    consumed.record(cur)
+    cur.wait_event(ev)
+    self._advance(consumed)
     return f, l
 
 
@@ -209,7 +228,7 @@ class Estimator:
         checkpoints.import_train_state(self.params, self.trainer, self._resume)
         self._resume = None
     tr = self.trainer
-    pre = _Prefetcher(batches, dev)
+    pre = _Prefetcher(batches, dev, rings=self.__dict__.setdefault('_rings', {}))
     host = torch.zeros((max(1, max_steps), 6), dtype=torch.float32).pin_memory()
     steps = 0
     save_every = getattr(s, 'save_checkpoints_steps', None)
@@ -237,21 +256,33 @@ class Estimator:
     matrix.  `batches` yields (features, labels) with host or device tensors.  Returns the
     reference's metrics dict {'confusion_matrix': np.int32[C, C], 'loss': 0.0, 'global_step'}."""
     dev = self.device
-    cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=dev)
-    invalid = torch.zeros(1, dtype=torch.int64, device=dev)
     lut_t = None if lut is None else torch.tensor(lut, dtype=torch.int32, device=dev)
-    pre = _Prefetcher(batches, dev)
-    steps = 0
-    host_cm = torch.zeros((num_classes, num_classes), dtype=torch.int64).pin_memory()
     replace_voids = bool(getattr(self.settings, 'replace_voids', False))
+    # forward + decisions + confusion-matrix update, replayed as one CUDA graph per input shape (network.EvalStep);
+    # kept across calls (the graphs are), counters zeroed
+    cache = self.__dict__.setdefault('_eval_steps', {})
+    key = (id(self.net), num_classes, None if lut is None else tuple(lut), replace_voids)
+    step = cache.get(key)
+    if step is None:
+      step = cache[key] = network.EvalStep(self.net, num_classes, lut_t, replace_voids, self.hier.void_cid)
+    step.reset()
+    cm, invalid = step.cm, step.invalid
+    pre = _Prefetcher(batches, dev, rings=self.__dict__.setdefault('_rings', {}))
+    steps = 0
+    host_cm = self.__dict__.setdefault('_host_cm', {}).get(num_classes)
+    if host_cm is None:   # pinned once: cudaHostAlloc per call costs more than a step's worth of launches
+      host_cm = self._host_cm[num_classes] = torch.zeros((num_classes, num_classes), dtype=torch.int64).pin_memory()
     for features, labels in pre:
-      out = self.net.predict(features['proimages'], want=('decisions',) + (_PROB_KEYS if replace_voids else ()))
       lab = labels['prolabels']
-      if replace_voids:
-        # EVAL order of the reference: (cid map ->) _replace_voids -> _resize_predictions (:175-183)
-        ops.replace_voids(self.net.hstruct, *(out[k] for k in _PROB_KEYS), out['decisions'], self.hier.void_cid)
-      decs = resize_decisions_nearest(out['decisions'], lab.shape[1], lab.shape[2])
-      ops.confmat_accumulate(lab.contiguous(), decs, num_classes, cm, lut_t, invalid)
+      if tuple(lab.shape[1:3]) == tuple(features['proimages'].shape[1:3]) and self.params.upsampling != 'no':
+        step(features['proimages'], lab)
+      else:
+        # labels at another size: EVAL order of the reference, (cid map ->) _replace_voids -> _resize_predictions
+        out = self.net.predict(features['proimages'], want=('decisions',) + (_PROB_KEYS if replace_voids else ()))
+        if replace_voids:
+          ops.replace_voids(self.net.hstruct, *(out[k] for k in _PROB_KEYS), out['decisions'], self.hier.void_cid)
+        decs = resize_decisions_nearest(out['decisions'], lab.shape[1], lab.shape[2])
+        ops.confmat_accumulate(lab.contiguous(), decs, num_classes, cm, lut_t, invalid)
       # the step's result (running metric) goes back to the host every step, asynchronously
       host_cm.copy_(cm, non_blocking=True)
       steps += 1

@@ -80,3 +80,46 @@ def test_eval_confusion_matrix_bit_exact_given_decisions(cuda):
   torch.cuda.synchronize()
   want = ometrics.confusion_matrix(labels.numpy(), out['decisions'].cpu().numpy(), 20)
   assert np.array_equal(cm.cpu().numpy(), want)
+
+
+def test_eval_step_graph_replay_equals_eager(cuda):
+  """network.EvalStep replays forward + decisions + confusion-matrix update as a CUDA graph keyed by the input
+  addresses (no copy for recurring buffers), falls back to one static pair for inputs at new addresses, and
+  re-captures when the parameters change.  The forward has no atomics and the histogram is integer: the confusion
+  matrix must equal the eagerly launched one bit for bit in every mode."""
+  from wlseg import network, ops
+  hier, tf_params, net = _setup(cuda, 'cityscapes', torch.bfloat16, seed=4)
+  g = torch.Generator().manual_seed(19)
+  batches = [((torch.rand(2, 64, 96, 3, generator=g) * 2 - 1).to(cuda),
+              torch.randint(0, 20, (2, 64, 96), generator=g, dtype=torch.int32).to(cuda)) for _ in range(3)]
+
+  def eager(pairs):
+    cm = torch.zeros(20, 20, dtype=torch.int64, device=cuda)
+    for img, lab in pairs:
+      out = net.predict(img, want=('decisions',))
+      ops.confmat_accumulate(lab, out['decisions'], 20, cm)
+    return cm
+  step = network.EvalStep(net, 20)
+  seq = batches * 3
+  for img, lab in seq:
+    step(img, lab)
+  torch.cuda.synchronize()
+  assert len(step._graphs) == 3 and not step._static          # recurring addresses: one graph each, no copies
+  assert torch.equal(step.cm, eager(seq))
+  assert int(step.cm.sum()) == len(seq) * 2 * 64 * 96
+  # inputs at ever-new addresses: after MAX_POINTER_GRAPHS captures the static pair takes over
+  step.reset()
+  fresh = [(batches[i % 3][0].clone(), batches[i % 3][1].clone()) for i in range(7)]
+  for img, lab in fresh:
+    step(img, lab)
+  torch.cuda.synchronize()
+  assert len(step._static) == 1 and torch.equal(step.cm, eager(fresh))
+  # new parameters: captured graphs are dropped (their derived operands moved) and the results follow the weights
+  before = step.cm.clone()
+  net.p.load_tf_dict(onet.init_params('cityscapes', seed=5, randomize_bn=True, tame=True))
+  step.reset()
+  for img, lab in seq:
+    step(img, lab)
+  torch.cuda.synchronize()
+  want = eager(seq)
+  assert torch.equal(step.cm, want) and not torch.equal(want, before * 9 // 7)
