@@ -77,6 +77,8 @@ struct IgemmParams {
   int num_kb;         // R * S * cchunks
   int stages;         // depth of the {A,B} operand ring
   int epi_bufs;       // 4 KB per-warp epilogue staging buffers (0: direct epilogue, else EW or 2 * EW)
+  int res_mid;        // residual layers: issue the next residual box in the MIDDLE of a step (see the epilogue)
+  int epi_db;         // layers without a residual: two staging buffers per warp (else one)
 };
 
 constexpr int kSubW = 64;                       // epilogue sub-tile: 64 channels = one 128-byte row
@@ -271,7 +273,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       const bool has_stat = prm.bn_sum != nullptr;
       const float lo = prm.relu ? 0.f : -INFINITY;
       const uint32_t sw = (uint32_t)(lane & 7);           // row & 7 of this thread's staging row
-      uint8_t* wbuf = epi_smem + ew * (has_res ? 2 : 1) * kWarpBufBytes;
+      const bool dbuf = has_res || prm.epi_db;            // two staging buffers per warp
+      uint8_t* wbuf = epi_smem + ew * (dbuf ? 2 : 1) * kWarpBufBytes;
       uint64_t* my_rfull = rfull_bar + 2 * ew;
       const int r0 = quarter * 32;                        // first tile row of this warp
       const int dy0 = r0 >> prm.tw_log2, dx0 = r0 & (TW - 1);
@@ -339,22 +342,39 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         for (int slot = 0; slot < kSlots; ++slot) {
           const int st = cgrp + slot * CG;
           if (st >= nsub) break;
-          uint8_t* buf = wbuf + (has_res ? (cnt & 1) * kWarpBufBytes : 0);
+          uint8_t* buf = wbuf + (dbuf ? (cnt & 1) * kWarpBufBytes : 0);
           // the store that last left from the buffer about to be (re)written must have read it:
           // without a residual that is this step's buffer, with one it is the NEXT step's
-          if (lane == 0) {
-            bulk_wait_read<0>();
+          // res_mid: the wait for the previous step's store (it must have READ the other buffer before the next
+          // residual box may land there) and the issue of that box move from the start of the step to its middle,
+          // and the wait for THIS step's residual moves behind the first TMEM load + scale/shift: both latencies
+          // (store read ~0.5 us, L2-hit box load ~0.7 us) then run under this step's own arithmetic instead of
+          // in front of it.  Measured: 512 -> 2048 + residual 369 -> 347 us, 256 -> 1024 + residual 155 -> 152 us,
+          // the narrower ones unchanged (WLSEG_RES_MID=0 restores the old schedule)
+          const bool mid = has_res && prm.res_mid;
+          if (lane == 0 && !mid) {
+            // without a residual and with two buffers only the store from TWO steps back (this buffer's last
+            // tenant) must have been read: the previous step's store stays in flight under this step
+            if (!has_res && dbuf) bulk_wait_read<1>(); else bulk_wait_read<0>();
             if (has_res) {
               next_residual(ld, true);    // step cnt + 1 -> the other buffer
               next_residual(pf, false);   // step cnt + 1 + kResPf -> L2
             }
           }
           __syncwarp();
-          if (has_res) mbar_wait(smem_u32(my_rfull + (cnt & 1)), (uint32_t)((cnt >> 1) & 1));
+          if (has_res && !mid) mbar_wait(smem_u32(my_rfull + (cnt & 1)), (uint32_t)((cnt >> 1) & 1));
           uint8_t* myrow = buf + lane * 128;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int col = st * kSubW + half * 32;   // column inside the BN-wide tile
+            if (mid && half == 1) {
+              if (lane == 0) {
+                bulk_wait_read<0>();
+                next_residual(ld, true);    // step cnt + 1 -> the other buffer
+                next_residual(pf, false);   // step cnt + 1 + kResPf -> L2
+              }
+              __syncwarp();
+            }
             uint32_t v[32];
             tmem_ld<32>(lane_addr + (uint32_t)(acc * BN + col), v);
             tmem_ld_wait();
@@ -385,6 +405,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               slot4[g] = reinterpret_cast<uint4*>(myrow + ((((uint32_t)(half * 4 + g)) ^ sw) << 4));
+            if (mid && half == 0) mbar_wait(smem_u32(my_rfull + (cnt & 1)), (uint32_t)((cnt >> 1) & 1));
             if (has_res) {
               // all 16-byte chunks are loaded before any is rewritten (no false aliasing stalls)
               uint4 raw[4];
@@ -644,7 +665,15 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
     configured = true;
   }
   // shared memory plan: [stages x {A,B}] [epi_bufs x 4 KB] [barriers]
-  prm.epi_bufs = kTmaEpi ? (prm.res != nullptr ? 2 * EW : EW) : 0;
+  // layers without a residual: a second staging buffer per warp for the 1x1 layers, so that the previous step's
+  // store stays in flight under the current one.  OFF by default - measured on B200 (4 x 128 x 256 eval shapes): it
+  // costs the fourth operand stage, which the wide-C layers need more (1024 -> 2048: 439 -> 469 us, 2048 -> 512:
+  // 216 -> 250 us) than the narrow ones gain (256 -> 768: 83 -> 78 us); eval step 8.75 -> 8.95 ms.  The exposed
+  // store-read wait is therefore NOT what holds the bandwidth-bound layers at 0.5-0.8 of their byte bound.
+  prm.epi_db = (kTmaEpi && prm.res == nullptr && prm.R * prm.S == 1 &&
+                (getenv("WLSEG_EPI_DB") != nullptr ? atoi(getenv("WLSEG_EPI_DB")) : 0)) ? 1 : 0;
+  prm.epi_bufs = kTmaEpi ? ((prm.res != nullptr || prm.epi_db) ? 2 * EW : EW) : 0;
+  prm.res_mid = getenv("WLSEG_RES_MID") != nullptr ? atoi(getenv("WLSEG_RES_MID")) : 1;
   const int fixed = prm.epi_bufs * kWarpBufBytes + kBarBytes + (kTmaEpi ? 2 * BN * 4 : 0);
   int stages = (kSmemMax - fixed) / Cfg::kStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
