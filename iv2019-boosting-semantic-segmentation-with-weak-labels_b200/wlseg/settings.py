@@ -138,7 +138,8 @@ def add_train_input_pipeline_arguments(argparser):
 
 def add_evaluate_input_pipeline_arguments(argparser):
   """code/input_pipelines/cityscapes/input_cityscapes.py:318 (positional tfrecords_path)."""
-  argparser.add_argument('tfrecords_path', type=str, default=None)
+  argparser.add_argument('tfrecords_path', type=str,
+                         default='/media/panos/data/datasets/cityscapes/tfrecords/valFine.tfrecords')  # as upstream
   argparser.add_argument('--preserve_aspect_ratio', action='store_true')
 
 
