@@ -251,3 +251,43 @@ def test_resize_nearest_is_roundf():
   x = torch.arange(4, dtype=torch.int32).view(1, 4, 1)
   got = tfops.resize_nearest(x, 7, 1, align_corners=True).reshape(-1).tolist()
   assert got == [0, 1, 1, 2, 2, 3, 3]
+
+
+def test_new_oracle_ops_against_independent_formulations():
+  """The oracle functions added for the optional model parts, each against a second, independent statement of the
+  same [TF-1.12] op: group_norm vs torch's own group norm on the channel-permuted tensor; conv2d_transpose (stride
+  1, SAME) vs the explicit double loop over taps; VALID average pooling vs window means; align_corners bilinear
+  resize at a hand-computable size."""
+  import torch
+  import torch.nn.functional as F
+  from oracle import tfops
+  g = torch.Generator().manual_seed(0)
+  # group norm: [N, H, W, C] with contiguous channel groups == F.group_norm on NCHW
+  x = torch.randn(2, 5, 4, 64, generator=g)
+  gamma, beta = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g)
+  want = F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5).permute(0, 2, 3, 1)
+  assert torch.allclose(tfops.group_norm(x, gamma, beta, 32, 1e-5), want, atol=1e-5)
+  want1 = F.group_norm(x.permute(0, 3, 1, 2), 1, gamma, beta, eps=1e-5).permute(0, 2, 3, 1)   # logits layers: 1 group
+  assert torch.allclose(tfops.group_norm(x, gamma, beta, 1, 1e-5), want1, atol=1e-5)
+  # conv2d_transpose, filter [kh, kw, out, in]: out[y, x, o] = sum_{r, s, i} in[y + 1 - r, x + 1 - s, i] * f[r, s, o, i]
+  xin = torch.randn(1, 4, 5, 3, generator=g)
+  f = torch.randn(3, 3, 2, 3, generator=g)
+  b = torch.randn(2, generator=g)
+  want = torch.zeros(1, 4, 5, 2)
+  for y in range(4):
+    for xx in range(5):
+      for r in range(3):
+        for s in range(3):
+          yy, xs = y + 1 - r, xx + 1 - s
+          if 0 <= yy < 4 and 0 <= xs < 5:
+            want[0, y, xx] += f[r, s] @ xin[0, yy, xs]
+  assert torch.allclose(tfops.conv2d_transpose_same(xin, f, b), want + b, atol=1e-5)
+  # VALID average pooling: windows that do not fit are dropped
+  xp = torch.arange(2 * 5 * 7 * 1, dtype=torch.float32).view(2, 5, 7, 1)
+  got = tfops.avg_pool_valid(xp, (2, 3), (2, 3))
+  assert tuple(got.shape) == (2, 2, 2, 1)
+  assert float(got[1, 1, 1, 0]) == float(xp[1, 2:4, 3:6, 0].mean())
+  # align_corners bilinear 2 -> 3: the middle sample is the exact midpoint, corners are kept
+  xr = torch.tensor([[[[0.0], [4.0]], [[8.0], [12.0]]]])
+  got = tfops.resize_bilinear(xr, 3, 3, align_corners=True)[0, :, :, 0]
+  assert got.tolist() == [[0.0, 2.0, 4.0], [4.0, 6.0, 8.0], [8.0, 10.0, 12.0]]
