@@ -205,6 +205,7 @@ class Estimator:
         variables, _ = checkpoints.load_file(init)
         mapping = checkpoints.warm_start(self.params, variables, psp_module=getattr(self.settings, 'psp_module', False))
         print(f'initialised {len(mapping)} variables from {init}', flush=True)
+    self.__dict__.pop('_eval_steps', None)   # graphs captured for a previous network object
     # group norm has no folded inference form: its evaluation forward is the training forward (network.py)
     cls = network.TrainNetwork if self.params.norm == 'group' else network.Network
     self.net = cls(self.params, dtype=self.dtype, bn_decay=getattr(self.settings, 'batch_norm_decay', 0.9))
