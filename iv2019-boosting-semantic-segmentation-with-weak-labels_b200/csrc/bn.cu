@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* __restrict__ z,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
                  const float* __restrict__ shift, int64_t count, int C, int pitch, int relu,
-                 double* __restrict__ out0, double* __restrict__ out1, int cspan) {
+                 double* __restrict__ out0, double* __restrict__ out1, int cspan, int rev) {
   // forward (kBackward=false): a = z;  out0 += sum z, out1 += sum z^2
   // backward: a = dy; g = dy*(y>0 if relu); out0 += sum g*(z-mean)*invstd (dgamma), out1 += sum g (dbeta)
   //   the ReLU mask comes from yact, or - when yact is NULL (layers without a residual input) - from the
@@ -77,10 +77,13 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ yact, const T* _
       for (int u = 0; u < kBnUnroll; ++u) {
         const int64_t row = row0 + u * step;
         if (row < count) {
-          va[u].load(a + row * pitch + tx * 8);
+          // rev: walk the tensor from its END - the producer (dgrad, ascending tile order) has just written the
+          // last rows, they are the ones still in L2
+          const int64_t r = rev ? count - 1 - row : row;
+          va[u].load(a + r * pitch + tx * 8);
           if (kBackward) {
-            vzz[u].load(z + row * pitch + tx * 8);
-            if (relu && !zmask) vyy[u].load(yact + row * pitch + tx * 8);
+            vzz[u].load(z + r * pitch + tx * 8);
+            if (relu && !zmask) vyy[u].load(yact + r * pitch + tx * 8);
           }
         }
       }
@@ -354,7 +357,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
 template <typename T, int kRowsU>
 __global__ void __launch_bounds__(256)
 bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                     const T* __restrict__ res, T* __restrict__ y, int64_t count, int C, int relu) {
+                     const T* __restrict__ res, T* __restrict__ y, int64_t count, int C, int relu, int rev) {
   pdl_launch_dependents();
   pdl_wait();   // scale / shift were written by bn_finalize, the kernel right before this one
   const int cv = C / 8;
@@ -373,14 +376,18 @@ bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ scale, c
     for (int u = 0; u < kRowsU; ++u) {
       const int64_t row = row0 + u * step;
       if (row < count) {
-        v[u].load(z + row * C + c0);
-        if (res != nullptr) vr[u].load(res + row * C + c0);
+        // rev: start at the END of z (the convolution's last tiles, still in L2) and finish at the START of y
+        // (the rows the next convolution reads first)
+        const int64_t r = rev ? count - 1 - row : row;
+        v[u].load(z + r * C + c0);
+        if (res != nullptr) vr[u].load(res + r * C + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < kRowsU; ++u) {
-      const int64_t row = row0 + u * step;
+      int64_t row = row0 + u * step;
       if (row >= count) break;
+      if (rev) row = count - 1 - row;
       float f[8];
       v[u].unpack(f);
 #pragma unroll
@@ -493,10 +500,11 @@ static void launch_apply_rows(const void* z, const float* scale, const float* sh
   const int U = res != nullptr ? bn_apply_u() : env_int("WLSEG_BN_APPLY_U_PLAIN", 1);
   const int g = bw_grid(ceil_div(count, (int64_t)lanes * U) * 256, 256,
                         res != nullptr ? bn_apply_ctas() : env_int("WLSEG_BN_APPLY_CTAS_PLAIN", 8));
+  const int rev = env_int("WLSEG_BN_APPLY_REV", 1);
   cudaError_t e;
-  if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
-  else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
-  else e = launch_pdl(bn_apply_rows_kernel<T, 2>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu);
+  if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev);
+  else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev);
+  else e = launch_pdl(bn_apply_rows_kernel<T, 2>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev);
   (void)e;   // reported by the caller's WLSEG_LAUNCH_CHECK (cudaGetLastError)
 }
 
@@ -617,7 +625,8 @@ static int launch_reduce(const void* a, const void* y, const void* z, const floa
   int gx = bw_grid(ceil_div(count * cv, kBnUnroll), kBnThreads, per_sm) / ny;
   if (gx < 1) gx = 1;
   WLSEG_CUDA(launch_pdl(bn_reduce_kernel<T, kBackward>, dim3(gx, ny), dim3(kBnThreads), smem, s, (const T*)a, (const T*)y,
-                        (const T*)z, mean, invstd, scale, shift, count, C, pitch, relu, o0, o1, cspan));
+                        (const T*)z, mean, invstd, scale, shift, count, C, pitch, relu, o0, o1, cspan,
+                        kBackward ? env_int("WLSEG_BN_RED_REV", 1) : 0));
   return 0;
 }
 
