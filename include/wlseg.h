@@ -66,6 +66,9 @@ typedef struct wlseg_conv_params {
   int32_t y_dtype;          /* storage of y; WLSEG_F32 lets a bf16 layer emit fp32 (logits) */
   int32_t algo;             /* WLSEG_ALGO_* */
   int32_t accumulate;       /* wgrad only: 0 = dw is overwritten, 1 = dw += (the caller zeroed it) */
+  int32_t reverse;          /* fprop (tcgen05): output tiles are produced from the END of the tensor to its start.
+                             * Same result; a consumer that starts where its producer ended finds its first
+                             * ~L2-size of input still on chip (layers alternate directions in inference). */
 } wlseg_conv_params;
 
 /* 1 if the tcgen05 implicit-GEMM kernel covers this configuration, else 0. */

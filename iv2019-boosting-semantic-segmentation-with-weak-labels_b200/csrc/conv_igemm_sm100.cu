@@ -79,6 +79,7 @@ struct IgemmParams {
   int epi_bufs;       // 4 KB per-warp epilogue staging buffers (0: direct epilogue, else EW or 2 * EW)
   int res_mid;        // residual layers: issue the next residual box in the MIDDLE of a step (see the epilogue)
   int epi_db;         // layers without a residual: two staging buffers per warp (else one)
+  int reverse;        // walk the M tiles from the last to the first (wlseg_conv_params::reverse)
 };
 
 constexpr int kSubW = 64;                       // epilogue sub-tile: 64 channels = one 128-byte row
@@ -120,6 +121,8 @@ template <int BN>
 __device__ __forceinline__ void decode_tile(const IgemmParams& prm, int tile, int& n, int& p0, int& q0, int& k0) {
   const int nt = tile % prm.n_tiles;
   int mt = tile / prm.n_tiles;
+  // reverse: same N tile (the fused statistics keep one N tile per CTA), M tiles from the end of the tensor
+  if (prm.reverse) mt = prm.total_tiles / prm.n_tiles - 1 - mt;
   const int twi = mt % prm.tiles_w; mt /= prm.tiles_w;
   const int thi = mt % prm.tiles_h;
   n = mt / prm.tiles_h;
@@ -757,6 +760,7 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   prm.y_pitch = p->y_pitch; prm.res_pitch = p->res_pitch; prm.res_stride = p->res_stride;
   prm.res_H = p->res_H; prm.res_W = p->res_W;
   prm.relu = p->relu;
+  prm.reverse = p->reverse ? 1 : 0;
   prm.tw_log2 = tw_log2;
   prm.tiles_w = (int)ceil_div(p->Q, TW);
   prm.tiles_h = (int)ceil_div(p->P, TH);

@@ -305,6 +305,13 @@ class Network:
     self.dev = params.device
     self.tape = None
     self.profile = None  # bench.py: list receiving one CUDA-event record per convolution launch
+    # inference: consecutive convolutions may walk their tiles in alternating directions, so that a layer starts on
+    # the rows its producer wrote last (wlseg_conv_params::reverse).  OFF by default: measured on B200 it LOSES for
+    # the convolution chain (eval step 8.76 / 8.84 -> 8.85 / 9.01 ms), unlike the batch-norm passes of training,
+    # which gain from the same idea (csrc/bn.cu); WLSEG_SNAKE=1 switches it on.
+    import os
+    self.snake = os.environ.get('WLSEG_SNAKE', '0') == '1'
+    self._snake_flip = False
 
   # ---- helpers ---------------------------------------------------------------------------------
   class _Timed:
@@ -337,12 +344,17 @@ class Network:
             residual=None, res_stride=1, y=None, y_dtype=None, bn_sum=None, bn_sqsum=None):
     N, H, W, C = x.shape
     K = w.shape[0]
+    reverse = False
+    if self.snake and self.tape is None and scale is not None and bn_sum is None:
+      self._snake_flip = not self._snake_flip   # inference layers only (folded BN): alternate
+      reverse = self._snake_flip
     if y is None:
       ydt = self.dtype if y_dtype is None else y_dtype
       y = torch.empty((N, out_hw[0], out_hw[1], K), dtype=ydt, device=self.dev)
     prm = ops.conv_params((N, H, W, C), tuple(w.shape), stride=stride, dilation=dilation, pad=pad, out_hw=out_hw,
                           x_pitch=x.stride(2), y_pitch=y.stride(2), relu=relu, dtype=self.code,
-                          y_dtype=ops.dtype_code(y.dtype), algo=self.conv_algo, res=residual, res_stride=res_stride)
+                          y_dtype=ops.dtype_code(y.dtype), algo=self.conv_algo, res=residual, res_stride=res_stride,
+                          reverse=reverse)
     tc = self.conv_algo != ops.ALGO_DIRECT and ops.conv2d_tcgen05_supported(prm)
     rec = None
     if self.profile is not None:

@@ -30,7 +30,7 @@ class ConvParams(ctypes.Structure):
   _fields_ = [(n, _c_int) for n in (
       'N', 'H', 'W', 'C', 'K', 'R', 'S', 'P', 'Q', 'stride', 'dilation', 'pad_top', 'pad_left',
       'x_pitch', 'y_pitch', 'res_pitch', 'res_stride', 'res_H', 'res_W', 'relu', 'dtype', 'y_dtype', 'algo',
-      'accumulate')]
+      'accumulate', 'reverse')]
 
 
 class Hierarchy(ctypes.Structure):
@@ -148,7 +148,8 @@ def _count(n=1):
 
 # ------------------------------------------------------------------------------------ convolution
 def conv_params(x_shape, w_shape, stride=1, dilation=1, pad=(0, 0), out_hw=None, x_pitch=None, y_pitch=None,
-                relu=False, dtype=BF16, y_dtype=None, algo=ALGO_AUTO, res=None, res_stride=1, accumulate=False):
+                relu=False, dtype=BF16, y_dtype=None, algo=ALGO_AUTO, res=None, res_stride=1, accumulate=False,
+                reverse=False):
   N, H, W, C = x_shape
   K, R, S, Cw = w_shape
   assert Cw == C, f'filter channels {Cw} != input channels {C}'
@@ -173,6 +174,7 @@ def conv_params(x_shape, w_shape, stride=1, dilation=1, pad=(0, 0), out_hw=None,
   p.y_dtype = dtype if y_dtype is None else y_dtype
   p.algo = algo
   p.accumulate = int(accumulate)
+  p.reverse = int(reverse)
   return p
 
 

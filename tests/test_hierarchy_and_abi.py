@@ -59,7 +59,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert getattr(lib, name) is not None
   assert lib.wlseg_version() == 100
   assert ctypes.sizeof(ops.Hierarchy) == 4 * (5 + 64 + 16 + 8 + 1 + 240 + 30)
-  assert ctypes.sizeof(ops.ConvParams) == 4 * 24
+  assert ctypes.sizeof(ops.ConvParams) == 4 * 25   # 24 fields of round-1 start + `reverse`
 
 
 def test_invalid_arguments_are_reported_not_crashed():
