@@ -87,7 +87,10 @@ def predict_main(argv):
   for flag in ('plotting', 'plotting_overlapped'):
     if getattr(st, flag, False):
       raise NotImplementedError(f'--{flag}: live matplotlib plotting is outside the B200 hot path')
-  system = SemanticSegmentation({'predict': synthetic.predict_input_fn}, None, st)
+  # real images from predict_dir (dataset-agnostic pipeline) unless --synthetic or the directory does not exist
+  from wlseg import image_input
+  real = not getattr(st, 'synthetic', False) and st.predict_dir and os.path.isdir(st.predict_dir)
+  system = SemanticSegmentation({'predict': image_input.predict_input_fn if real else synthetic.predict_input_fn}, None, st)
   s = system.settings
   exporting = any(getattr(s, f, False) for f in ('export_lids_images', 'export_color_decisions',
                                                  'export_overlapped_color_decisions'))

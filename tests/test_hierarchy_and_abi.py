@@ -104,3 +104,40 @@ def test_predict_exports_palette_pngs(tmp_path):
   assert np.array_equal(np.asarray(Image.open(tmp_path / 'frankfurt_000001_result_color.png')), col[decs])
   want = (0.5 * raw + 0.5 * col[decs]).astype(np.uint8)
   assert np.array_equal(np.asarray(Image.open(tmp_path / 'frankfurt_000001_result_overlapped_color.png')), want)
+
+
+def test_real_image_predict_input(tmp_path):
+  """dataset_agnostic_predict_input.py:88-154: recursive image discovery, RGB conversion, [-1, 1) scaling, legacy
+  align_corners=False bilinear resize to the feature-extractor size, one image per batch with raw image and path."""
+  import argparse
+  import numpy as np
+  import torch
+  from PIL import Image
+  from wlseg import image_input
+  rng = np.random.default_rng(1)
+  (tmp_path / 'sub').mkdir()
+  a = rng.integers(0, 256, (6, 8, 3), dtype=np.uint8)
+  Image.fromarray(a).save(tmp_path / 'a.png')
+  Image.fromarray(rng.integers(0, 256, (5, 5), dtype=np.uint8), mode='L').save(tmp_path / 'sub' / 'grey.png')
+  (tmp_path / 'notes.txt').write_text('not an image')
+  params = argparse.Namespace(predict_dir=str(tmp_path), height_feature_extractor=12, width_feature_extractor=16, Nb=1)
+  batches = list(image_input.predict_input_fn(None, params))
+  assert len(batches) == 2
+  by_name = {os.path.basename(f['rawimagespaths'][0].decode()): f for f, _ in batches}
+  f = by_name['a.png']
+  assert tuple(f['proimages'].shape) == (1, 12, 16, 3) and f['proimages'].dtype == torch.float32
+  assert tuple(f['rawimages'].shape) == (1, 6, 8, 3) and np.array_equal(f['rawimages'][0].numpy(), a)
+  assert float(f['proimages'].min()) >= -1.0 and float(f['proimages'].max()) <= 1.0
+  # exact 2x upscale, legacy mapping: output (2i, 2j) is input (i, j), odd positions are midpoints, the last one is
+  # clamped to the border
+  x = a.astype(np.float32) / 255.0
+  want00 = (x[0, 0] - 0.5) / 0.5
+  assert np.allclose(f['proimages'][0, 0, 0].numpy(), want00, atol=1e-6)
+  assert np.allclose(f['proimages'][0, 2, 4].numpy(), (x[1, 2] - 0.5) / 0.5, atol=1e-6)
+  assert np.allclose(f['proimages'][0, 1, 0].numpy(), ((x[0, 0] + x[1, 0]) / 2 - 0.5) / 0.5, atol=1e-6)
+  assert np.allclose(f['proimages'][0, 11, 15].numpy(), (x[5, 7] - 0.5) / 0.5, atol=1e-6)
+  assert tuple(by_name['grey.png']['rawimages'].shape) == (1, 5, 5, 3)          # converted to RGB
+  # identity size: no resampling at all
+  params2 = argparse.Namespace(predict_dir=str(tmp_path), height_feature_extractor=6, width_feature_extractor=8, Nb=1, steps=1)
+  only = list(image_input.predict_input_fn(None, params2))
+  assert len(only) == 1
