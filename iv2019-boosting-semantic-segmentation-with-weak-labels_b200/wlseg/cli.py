@@ -51,6 +51,11 @@ def train_main(argv):
   # starts from the random initialisation unless log_dir holds a checkpoint
   wsettings.train_extra_args(st)
   _dist_env(st)
+  if st.world_size > 1 and not st.distribute:
+    # one process per GPU: without --distribute every rank would train its own unsynchronised model and only rank
+    # 0's would be saved.  The reference is one process for all GPUs and needs the flag to use more than one.
+    raise ValueError(f'WORLD_SIZE={st.world_size} but --distribute is not set: launch one process, or pass --distribute '
+                     'for data-parallel training.')
   system = SemanticSegmentation({'train': synthetic.train_input_fn}, None, st)
   out = system.train()
   _dist_shutdown(st, system)

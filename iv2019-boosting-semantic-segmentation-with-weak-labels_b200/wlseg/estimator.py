@@ -199,6 +199,11 @@ class Estimator:
     if path:
       self.restore(path, for_training=for_training)
     else:
+      if not for_training and not getattr(self.settings, 'synthetic', False):
+        # tf.estimator raises when EVAL / PREDICT find nothing to restore; metrics or PNGs of a random-init network
+        # must never be produced silently.  --synthetic (benchmarks, BASELINE configs) opts into random weights.
+        raise ValueError(f'Could not find trained model in model_dir: {log_dir} (no --ckpt_path and no '
+                         'model.ckpt-*.pt); pass --synthetic to evaluate / predict with random-init weights.')
       self.params.init_random(seed)  # BASELINE configs use random weights
       init = getattr(self.settings, 'init_ckpt_path', None)
       if for_training and init and os.path.isfile(init):
@@ -232,6 +237,7 @@ class Estimator:
     pre = _Prefetcher(batches, dev, rings=self.__dict__.setdefault('_rings', {}))
     host = torch.zeros((max(1, max_steps), 6), dtype=torch.float32).pin_memory()
     steps = 0
+    last_saved = None
     save_every = getattr(s, 'save_checkpoints_steps', None)
     for features, labels in pre:
       if steps >= max_steps:
@@ -246,7 +252,13 @@ class Estimator:
         print(f'step {tr.global_step}: total loss {float(host[steps - 1, 0]):.4f} lr {lr:g}', flush=True)
       if save_every and getattr(s, 'rank', 0) == 0 and tr.global_step % save_every == 0 and getattr(s, 'save_checkpoints', True):
         self.save(s.log_dir)
+        last_saved = tr.global_step
     torch.cuda.synchronize(dev)
+    # tf.estimator always writes a checkpoint when train() ends (CheckpointSaverHook.end): with --steps, or a cadence
+    # that does not divide the step count, the trained weights would otherwise be lost
+    if (steps and getattr(s, 'rank', 0) == 0 and getattr(s, 'save_checkpoints', True) and getattr(s, 'log_dir', None)
+            and os.path.isdir(s.log_dir) and last_saved != tr.global_step):
+      self.save(s.log_dir)
     self.last_h2d_bytes = pre.h2d_bytes
     self.last_d2h_bytes = steps * 6 * 4
     return host[:steps].numpy().copy()

@@ -146,10 +146,13 @@ class SemanticSegmentation(object):
 
     settings_dict = collections.OrderedDict(sorted(vars(s).items()))
     settings_filename = join(s.log_dir, 'settings.txt')
+    # one process per GPU: rank 0 owns the log directory (the reference is a single process); its verdict is made
+    # collective so that a failed precondition stops EVERY rank instead of leaving the others in their first collective
+    stale = bool(getattr(s, 'rank', 0) == 0 and exists(settings_filename))
+    stale = _any_rank(stale, s)
+    assert not stale, (
+        f"Previous settings.txt found in {s.log_dir}. Rename or delete it manually and restart training.")
     if getattr(s, 'rank', 0) == 0:
-      # one process per GPU: rank 0 owns the log directory (the reference is a single process)
-      assert not exists(settings_filename), (
-          f"Previous settings.txt found in {s.log_dir}. Rename or delete it manually and restart training.")
       with open(settings_filename, 'w') as f:
         for k, v in enumerate(settings_dict):
           print(f"{k:2} : {v} : {settings_dict[v]}", file=f)
@@ -231,6 +234,18 @@ class SemanticSegmentation(object):
       m['confusion_matrix_int64'] = t.cpu().numpy()
       m['confusion_matrix'] = m['confusion_matrix_int64'].astype(np.int32)
     return m
+
+
+def _any_rank(flag, settings):
+  """Logical OR of `flag` over the ranks (identity in a single process)."""
+  import torch
+  import torch.distributed as dist
+  if getattr(settings, 'world_size', 1) > 1 and dist.is_available() and dist.is_initialized():
+    dev = getattr(settings, 'device', 'cuda') if dist.get_backend() == 'nccl' else 'cpu'
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(int(t.item()))
+  return bool(flag)
 
 
 def _set_defaults(settings):

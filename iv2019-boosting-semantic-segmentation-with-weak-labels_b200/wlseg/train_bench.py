@@ -13,25 +13,22 @@ import time
 import torch
 
 
-def run(args, cpu_train_sample=None):
+def run(args, ctx, cpu_train_sample=None):
+  """-> the JSON line (dict) of the training half; `ctx` is bench.Ctx (device, ranks, NCCL already up)."""
   import torch.distributed as dist
-  from bench import ClockSampler, StdoutToStderr, load_peaks  # noqa: E402 (bench.py is the caller)
+  import bench  # noqa: E402 (bench.py is the caller)
+  from bench import ClockSampler, StdoutToStderr, load_peaks
   from wlseg import arch, hierarchy, network, ops, problem_defs, synthetic, trainer as wtrainer
 
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  rank = int(os.environ.get('RANK', '0'))
-  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-  if not torch.cuda.is_available():
-    raise SystemExit('bench.py: no CUDA device; wlseg has no CPU fallback')
-  torch.cuda.set_device(local_rank)
-  dev = torch.device('cuda', local_rank)
+  world, rank, local_rank, dev = ctx.world, ctx.rank, ctx.local_rank, ctx.dev
   quiet = StdoutToStderr()
-  quiet.__enter__()  # the NCCL banner must not land on stdout (one JSON line only)
-  if world > 1:
-    dist.init_process_group('nccl', device_id=dev)
+  quiet.__enter__()  # nothing but the one JSON line may land on stdout
   H, W, NB = args.height or 768, args.width or 768, args.batch or 4
+  if args.workload == 'both':   # the nested evaluation half owns --height / --width / --batch overrides
+    H, W, NB = 768, 768, 4
   mixed = getattr(args, 'mixed', False)
   npb, npi = (2 * NB, NB) if mixed else (0, 0)
+  boxes = bool(mixed and getattr(args, 'boxes', False))
   hier = hierarchy.Hierarchy(args.dataset, problem_defs.GENERATORS[args.dataset]()['cids2labels'])
   params = network.Params(hier, dev)
   params.init_random(0)
@@ -89,6 +86,8 @@ def run(args, cpu_train_sample=None):
   ms_max = float(t.item())
   nimg = NB + npb + npi
   value = world * args.steps * nimg / (ms_max / 1e3)
+  sustained = bench.sustained_loop(step, args.sustained_seconds, ms_max / args.steps, nimg, 'images/s', dev, world,
+                                   rank, local_rank)
 
   peaks = load_peaks()
   classes = {}
@@ -103,18 +102,21 @@ def run(args, cpu_train_sample=None):
   tc = {k: v for k, v in classes.items() if k.startswith(('igemm', 'wgrad_tc'))}
   if tc:
     name, dom = max(tc.items(), key=lambda kv: kv[1]['ms'])
-    ach = dom['flops'] / (dom['ms'] / 1e3) / 1e12
-    from bench import load_traffic
-    traffic, tsrc = load_traffic('train', 'conv_igemm_kernel<256' if name == 'igemm_bn256' else 'conv_wgrad_kernel<256')
-    roofline = {'bound': 'tensor', 'kernel': name, 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
-                'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': traffic,
-                'traffic_source': None if tsrc is None else 'profiles/' + tsrc,
-                'algorithmic_bytes_per_launch': dom['bytes'] / dom['launches'],
-                'peak_source': peaks['source'] + ' (sustained cuBLAS bf16)', 'launches': dom['launches'],
-                # kernel time per step (event pairs of the eager pass) over the step time of the timed region (graph
-                # replay): the eager pass's own wall time is inflated by Python launch gaps and is not the step
-                'share_of_step': (dom['ms'] / prof_steps) / (ms_max / args.steps),
-                'timed_over': f'{prof_steps} eagerly launched steps after the timed region'}
+    from bench import load_traffic, tensor_roofline
+    kname = 'conv_igemm_kernel<256' if name == 'igemm_bn256' else 'conv_wgrad_kernel<256'
+    traffic, tsrc = load_traffic('train', kname)
+    # kernel time per step (event pairs of the eager pass) over the step time of the timed region (graph replay):
+    # the eager pass's own wall time is inflated by Python launch gaps and is not the step
+    roofline = tensor_roofline(kname + ('' if name.endswith('256') else f' [{name}]') + ', bf16>', dom, peaks, ms_max / 1e3,
+                               traffic, tsrc, (dom['ms'] / prof_steps) / (ms_max / args.steps),
+                               f'{prof_steps} eagerly launched steps after the timed region')
+    # every tensor-core launch of the step (fprop + dgrad + wgrad) against the same peak, and the whole step
+    all_flops = sum(v['flops'] for v in tc.values())
+    all_ms = sum(v['ms'] for v in tc.values())
+    roofline['all_conv_tflops'] = all_flops / (all_ms / 1e3) / 1e12
+    roofline['all_conv_share_of_step'] = (all_ms / prof_steps) / (ms_max / args.steps)
+    roofline['whole_step_tflops'] = (all_flops / prof_steps) / (ms_max / args.steps / 1e3) / 1e12
+    roofline['whole_step_frac_burst'] = roofline['whole_step_tflops'] / peaks['bf16_tflops']
   if args.detail and rank == 0:
     table = {k: {'launches': v['launches'], 'ms_per_step': v['ms'] / prof_steps,
                  'tflops': v['flops'] / (v['ms'] / 1e3) / 1e12 if v['ms'] else None,
@@ -180,28 +182,20 @@ def run(args, cpu_train_sample=None):
   if rank == 0 and world == 1 and not args.no_cpu_baseline and cpu_train_sample is not None:
     cpu = cpu_train_sample(args.dataset, H, W)
 
-  if rank == 0:
-    fwd = arch.conv_flops(params.specs, H, W) / 1e9
-    line = {'metric': 'train_images_per_s', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': f'{args.dataset} training step (BASELINE configs[{3 if mixed else 2}]): ResNet-50 OS8 + '
-                                   f'hierarchical heads, fwd (batch-stat BN) + masked strong{"+weak" if mixed else ""} loss + bwd + '
-                                   f'SGD-momentum, {H}x{W} crops, {NB} strong + {npb} bbox + {npi} image-level images/GPU, random init',
-                       'l2': 'two rotating input batches; activations + gradients (GBs) exceed the 126 MB L2',
-                       'launch': 'whole step replayed as one CUDA graph',
-                       'parallelism': f'data parallel x{world}, NCCL gradient all-reduce bucketed behind backward' if world > 1 else 'single GPU',
-                       'fwd_gflop_per_image': fwd, 'last_loss': [float(x) for x in out.tolist()]},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * world, 'roofline': roofline, 'cpu_baseline': cpu}
-    print(json.dumps(line), flush=True)
-  if world > 1:
-    # captured NCCL collectives keep the communicator busy: drop the graphs, drain, and leave without
-    # running the process-group destructor (it can wait forever on a communicator a graph still holds)
-    tr._graphs.clear()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    import sys
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
+  fwd = arch.conv_flops(params.specs, H, W) / 1e9
+  line = {'metric': 'train_images_per_s', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+          'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+          'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+          'config': {'workload': bench.train_workload_name(args.dataset, H, W, NB, npb, npi, mixed),
+                     'l2': 'two rotating input batches; activations + gradients (GBs) exceed the 126 MB L2',
+                     'launch': 'whole step replayed as one CUDA graph',
+                     'parallelism': (f'data parallel x{world}, NCCL gradient all-reduce ({tr.grad_payload}) bucketed behind '
+                                     f'backward, inside the timed region') if world > 1 else 'single GPU',
+                     'weak_labels': ('generated in the loss kernel from box / class lists' if boxes else 'dense 60 B/pixel maps') if mixed else None,
+                     'fwd_gflop_per_image': fwd, 'last_loss': [float(x) for x in out.tolist()]},
+          'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * world, 'roofline': roofline, 'sustained': sustained,
+          'cpu_baseline': cpu}
+  # captured NCCL collectives keep the communicator busy: drop the graphs before the caller drains and exits
+  tr._graphs.clear()
+  torch.cuda.synchronize()
+  return line

@@ -121,6 +121,7 @@ class Trainer:
     if os.environ.get('WLSEG_WGRAD_STREAM', '0') == '1' and params.device.type == 'cuda':
       self.net.wgrad_stream = torch.cuda.Stream(device=params.device)
       self.buckets.also_wait.append(self.net.wgrad_stream)   # a bucket is final only when its wgrads have run
+    self.grad_payload = 'fp32'
     self.global_step = 0
     self._lr_host = None
 
@@ -156,6 +157,13 @@ class Trainer:
     images = features['proimages']
     labels = {k: v for k, v in labels.items() if v is not None}
     self.set_lr(lr)
+    if self.ema_decay > 0:
+      # ema.apply sits in UPDATE_OPS, which create_train_op runs BEFORE the gradient step
+      # (define_estimator_hierarchical.py:96-111,120-129): the shadows average the variables as they are before this
+      # step's update, with num_updates = the pre-increment global_step
+      t = self.global_step
+      d = min(self.ema_decay, (1.0 + t) / (10.0 + t))
+      ops.ema_update(self.ws.ema_shadow, self.ws.ema_shadow, self.p.master, d, 1.0)
     if not self.use_graph or self.net.profile is not None or self.net.keep:
       out = self._core(images, labels)
     else:
@@ -181,10 +189,6 @@ class Trainer:
           static_lab[k].copy_(v, non_blocking=True)
         graph.replay()
         self.p.touch()
-        out = static_out
+        out = static_out.clone()   # the graph overwrites static_out on the next replay
     self.global_step += 1
-    if self.ema_decay > 0:
-      t = self.global_step
-      d = min(self.ema_decay, (1.0 + t) / (10.0 + t))  # num_updates=global_step
-      ops.ema_update(self.ws.ema_shadow, self.ws.ema_shadow, self.p.master, d, 1.0)
     return out
