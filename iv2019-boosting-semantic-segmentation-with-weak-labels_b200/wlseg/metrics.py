@@ -35,7 +35,10 @@ def print_metrics_from_confusion_matrix(cm, labels=None, printfile=None, printcm
   m = compute_metrics(cm)
   lines = ['', f"Global accuracy: {m['global_accuracy']:5.2f}",
            'Per class accuracies (nans due to 0 #Trues) and ious (nans due to 0 #TPs):']
-  for name, acc, iou, ok in zip(labels, m['accuracies'], m['ious'], m['notnan_mask']):
+  # the reference builds a dict keyed by label name first (utils/utils.py:431): rows that share a name - the
+  # default 'unknown' labels - collapse into ONE line carrying the last row's values; kept byte for byte
+  rows = {name: (acc, iou, ok) for name, acc, iou, ok in zip(labels, m['accuracies'], m['ious'], m['notnan_mask'])}
+  for name, (acc, iou, ok) in rows.items():
     lines.append(f"{name:<30s}  {acc:>5.2f}  {iou:>5.2f}  {'' if ok else '(ignored in averages)'}")
   lines.append(f"Mean accuracy (ignoring nans): {m['mean_accuracy']:5.2f}")
   lines.append(f"Mean iou (ignoring accuracies' nans but including ious' 0s): {m['mean_iou']:5.2f}")

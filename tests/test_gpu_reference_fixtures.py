@@ -1,0 +1,160 @@
+"""The CUDA kernels (through the C ABI) against vectors produced by RUNNING THE REFERENCE'S OWN PYTHON
+(tests/golden/reference_run.npz, written by tests/golden/make_reference_fixtures.py from /root/reference/code over the
+TensorFlow-1.12 API emulation in tests/golden/tf_shim).  No oracle in between: reference output vs kernel output.
+
+Tolerances: integer work (decisions, rasterised labels up to the fp32 division, remapped ids, nearest resize) bit-exact;
+fp32 kernels 1e-4 relative (north star fp32 check mode), gradient additionally cosine >= 0.99999.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_run.npz')
+LOSS_CASES = ['losses_cityscapes_mixed', 'losses_cityscapes_strong', 'losses_vistas_mixed', 'losses_vistas_strong']
+
+
+@pytest.fixture(scope='module')
+def gold():
+  return np.load(GOLD)
+
+
+def _hier(dataset):
+  from wlseg import hierarchy, problem_defs
+  return hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+
+
+def _packed_logits(gold, tag, hier):
+  low = [torch.from_numpy(gold[f'{tag}/lowres_{k}_logits']) for k in ('l1', 'l2_vehicle', 'l2_human')]
+  B, h, w = low[0].shape[:3]
+  logits = torch.zeros(B, h, w, hier.logits_pitch)
+  logits[..., :hier.total_channels] = torch.cat(low, -1)
+  return logits
+
+
+@pytest.mark.parametrize('tag', LOSS_CASES)
+@pytest.mark.parametrize('from_boxes', [False, True])
+def test_loss_kernel_equals_the_reference_run(cuda, gold, tag, from_boxes):
+  """`define_losses` (define_losses_hierarchical.py:14-224) run by the reference: the three losses and d total /
+  d low-res logits, against wlseg_loss_fwd_bwd + wlseg_loss_finalize on the same logits and labels.  from_boxes: the
+  bbox labels are rasterised on the device from the (class, box) lists (wlseg_rasterize_bbox_labels) instead of
+  being uploaded dense, the image-level ones tiled on the device."""
+  from wlseg import ops
+  n_pp, n_pb, n_pi, h, w = (int(x) for x in gold[f'{tag}/counts'])
+  if from_boxes and n_pb + n_pi == 0:
+    pytest.skip('strong-only case has no weak labels')
+  H, W = 8 * h, 8 * w
+  hier = _hier(str(gold[f'{tag}/dataset']))
+  hs = hier.as_struct()
+  logits = _packed_logits(gold, tag, hier).to(cuda)
+  strong = torch.from_numpy(gold[f'{tag}/prolabels_per_pixel']).to(cuda)
+  bbox = image = None
+  if n_pb:
+    if from_boxes:
+      mb = max(len(gold[f'{tag}/bbox{i}_cids']) for i in range(n_pb))
+      coords = torch.zeros(n_pb, mb, 4)
+      cids = torch.full((n_pb, mb), -1, dtype=torch.int32)
+      for i in range(n_pb):
+        k = len(gold[f'{tag}/bbox{i}_cids'])
+        coords[i, :k] = torch.from_numpy(gold[f'{tag}/bbox{i}_coords'])
+        cids[i, :k] = torch.from_numpy(gold[f'{tag}/bbox{i}_cids'])
+      bbox = ops.rasterize_bbox_labels(coords.to(cuda), cids.to(cuda), H, W)
+      assert torch.equal(bbox.cpu(), torch.from_numpy(gold[f'{tag}/prolabels_per_bbox']))   # vs _generate_rla, bit-exact
+    else:
+      bbox = torch.from_numpy(gold[f'{tag}/prolabels_per_bbox']).to(cuda)
+  if n_pi:
+    vec = torch.from_numpy(gold[f'{tag}/prolabels_per_image_vectors'])
+    image = ops.tile_image_labels(vec.to(cuda), H, W) if from_boxes else vec[:, None, None, :].expand(n_pi, H, W, 15).contiguous().to(cuda)
+  dl = torch.zeros_like(logits)
+  sums = torch.zeros(3, dtype=torch.float64, device=cuda)
+  counts = torch.zeros(3, dtype=torch.float64, device=cuda)
+  out = torch.zeros(4, device=cuda)
+  ops.loss_fwd_bwd(hs, logits, H, W, strong, bbox, image, sums, counts, dl)
+  ops.loss_finalize(hs, sums, counts, 0.1, 1.0, dl, out)
+  torch.cuda.synchronize()
+  got = out.cpu().tolist()
+  ref = [float(gold[f'{tag}/loss_{k}']) for k in ('l1_segmentation', 'l2_vehicle_segmentation', 'l2_human_segmentation')]
+  seg = float(gold[f'{tag}/loss_total']) - float(gold[f'{tag}/loss_regularization'])
+  for g, r in zip(got, ref + [seg]):
+    assert abs(g - r) <= 1e-4 * max(1.0, abs(r)), (got, ref, seg)
+  g = dl.cpu()[..., :hier.total_channels]
+  gr = torch.cat([torch.from_numpy(gold[f'{tag}/grad_lowres_{k}_logits']) for k in ('l1', 'l2_vehicle', 'l2_human')], -1)
+  assert float((g - gr).abs().max()) <= 1e-4 * float(gr.abs().max()) + 1e-9
+  assert float((g * gr).sum() / (g.norm() * gr.norm() + 1e-30)) >= 0.99999
+
+
+@pytest.mark.parametrize('tag', LOSS_CASES)
+def test_head_l1_decisions_equal_the_reference_run(cuda, gold, tag):
+  """tf.image.resize_images(align_corners) -> softmax -> argmax as the reference's model code calls them
+  (resnet50_extended_model_hierarchical.py:84-93) vs wlseg_head_fwd on the same low-res logits: identical ids."""
+  from wlseg import network
+  n_pp, n_pb, n_pi, h, w = (int(x) for x in gold[f'{tag}/counts'])
+  hier = _hier(str(gold[f'{tag}/dataset']))
+  net = network.Network.__new__(network.Network)
+  net.hier, net.hstruct, net.dev = hier, hier.as_struct(), cuda
+  got = net.head(_packed_logits(gold, tag, hier).to(cuda), 8 * h, 8 * w, ('l1_decisions',))
+  assert np.array_equal(got['l1_decisions'].cpu().numpy(), gold[f'{tag}/l1_decisions'])
+
+
+def test_rasteriser_equals_generate_rla(cuda, gold):
+  """input_subset_bboxes_v2.py:74-98 run by the reference vs wlseg_rasterize_bbox_labels (bit-exact, unknown mids
+  skipped)."""
+  from wlseg import ops
+  h, w = (int(x) for x in gold['rla/size'])
+  got = ops.rasterize_bbox_labels(torch.from_numpy(gold['rla/coords'])[None].to(cuda), torch.from_numpy(gold['rla/cids'])[None].to(cuda), h, w)
+  assert np.array_equal(got.cpu().numpy()[0], gold['rla/out'])
+
+
+def test_confmat_lut_equals_the_reference_remap(cuda, gold):
+  """_map_predictions_to_new_cids (:490-528) run by the reference, then a histogram of its output, vs the LUT fused
+  into wlseg_confmat_accumulate."""
+  from wlseg import estimator as west
+  from wlseg import ops
+  for tag, n_old in (('remap', 5), ('remap_cs', 20)):
+    decs = torch.from_numpy(gold[f'{tag}/decisions'])
+    lut = torch.tensor(west._replacevoids([int(x) for x in gold[f'{tag}/map']]), dtype=torch.int32)
+    n_new = int(lut.max()) + 1
+    labels = torch.from_numpy(gold[f'{tag}/out_decisions']).to(torch.int32)   # "ground truth" = the reference's remapped ids
+    cm = torch.zeros(n_new, n_new, dtype=torch.int64, device=cuda)
+    ops.confmat_accumulate(labels.to(cuda), decs.to(cuda), n_new, cm, lut=lut.to(cuda))
+    cm = cm.cpu()
+    assert int(cm.sum()) == decs.numel() and int(torch.diagonal(cm).sum()) == decs.numel()   # every pixel on the diagonal
+
+
+@pytest.mark.parametrize('tag', ['resize_up', 'resize_down'])
+def test_resize_predictions_equals_the_reference_run(cuda, gold, tag):
+  """_resize_predictions (:530-571) run by the reference vs wlseg_resize_nearest / wlseg_resize_probs."""
+  from wlseg import ops
+  oh, ow = (int(x) for x in gold[f'{tag}/size'])
+  got = ops.resize_decisions(torch.from_numpy(gold[f'{tag}/in_decisions']).to(cuda), oh, ow)
+  assert np.array_equal(got.cpu().numpy(), gold[f'{tag}/out_decisions'])
+  for k in ('l1_probabilities', 'l2_vehicle_probabilities', 'l2_human_probabilities'):
+    got = ops.resize_probabilities(torch.from_numpy(gold[f'{tag}/in_{k}']).to(cuda), oh, ow)
+    np.testing.assert_allclose(got.cpu().numpy(), gold[f'{tag}/out_{k}'], rtol=0, atol=1e-6)
+
+
+def test_batch_mean_iou_on_device_equals_the_reference_run(cuda, gold):
+  """define_metrics.mean_iou run by the reference vs confmat kernel + estimator.mean_iou_from_cm on device tensors."""
+  from wlseg import estimator as west
+  from wlseg import ops
+  cm = torch.zeros(20, 20, dtype=torch.int64, device=cuda)
+  ops.confmat_accumulate(torch.from_numpy(gold['mean_iou/labels']).to(cuda), torch.from_numpy(gold['mean_iou/decisions']).to(cuda), 20, cm)
+  assert abs(float(west.mean_iou_from_cm(cm, 20)) - float(gold['mean_iou/out'])) <= 1e-6
+
+
+@pytest.mark.parametrize('name,nesterov', [('plain', False), ('nesterov', True)])
+def test_sgdm_kernel_equals_the_reference_optimizer(cuda, gold, name, nesterov):
+  """Three updates through the optimizer object `define_optimizer` returns (define_optimizer.py:17-20) vs
+  wlseg_sgdm_step (no weight decay: the L2 term is part of the gradient in the reference)."""
+  from wlseg import ops
+  w = torch.from_numpy(gold['sgdm/w0']).clone().to(cuda)
+  acc = torch.zeros_like(w)
+  wb = torch.zeros(w.numel(), dtype=torch.bfloat16, device=cuda)
+  lr = torch.full((1,), 0.01, device=cuda)
+  for g in torch.from_numpy(gold['sgdm/grads']):
+    ops.sgdm_step(w, g.clone().to(cuda), acc, wb, 0, lr, 0.9, nesterov, 0.0)
+  np.testing.assert_allclose(w.cpu().numpy(), gold[f'sgdm/{name}'], rtol=0, atol=1e-6)

@@ -1,0 +1,164 @@
+"""The oracle (and the product's host-side helpers) against vectors produced by RUNNING THE REFERENCE'S OWN PYTHON.
+
+tests/golden/reference_run.npz is written by tests/golden/make_reference_fixtures.py, which imports
+/root/reference/code over a small TensorFlow-1.12 API emulation (tests/golden/tf_shim) and calls the reference's own
+`define_losses`, `_segment_sum`, `_generate_rla`, `_map_predictions_to_new_cids`, `_resize_predictions`,
+`_replace_voids`, `mean_iou`, `define_optimizer`, `_replacevoids`, `get_temp_Nb`,
+`print_metrics_from_confusion_matrix`.  This pins the oracle's restatement of the reference's Python (tables,
+gathers, masks, weights, normalisation, remaps, resize calls); TensorFlow's own kernels stay restated.
+"""
+
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import metrics as ometrics
+from oracle import optimizer as oopt
+from oracle import tfops
+from oracle import weak_labels as oweak
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_run.npz')
+LOSS_CASES = ['losses_cityscapes_mixed', 'losses_cityscapes_strong', 'losses_vistas_mixed', 'losses_vistas_strong']
+
+
+@pytest.fixture(scope='module')
+def gold():
+  return np.load(GOLD)
+
+
+def _loss_inputs(gold, tag):
+  n_pp, n_pb, n_pi, h, w = (int(x) for x in gold[f'{tag}/counts'])
+  H, W = 8 * h, 8 * w
+  low = [torch.from_numpy(gold[f'{tag}/lowres_{k}_logits']).clone().requires_grad_(True) for k in ('l1', 'l2_vehicle', 'l2_human')]
+  labels = {'prolabels_per_pixel': torch.from_numpy(gold[f'{tag}/prolabels_per_pixel'])}
+  if n_pb:
+    labels['prolabels_per_bbox'] = torch.from_numpy(gold[f'{tag}/prolabels_per_bbox'])
+  if n_pi:
+    vec = torch.from_numpy(gold[f'{tag}/prolabels_per_image_vectors'])
+    labels['prolabels_per_image'] = vec[:, None, None, :].expand(n_pi, H, W, 15).contiguous()
+  return str(gold[f'{tag}/dataset']), (n_pp, n_pb, n_pi, H, W), low, labels
+
+
+@pytest.mark.parametrize('tag', LOSS_CASES)
+def test_oracle_losses_and_gradients_equal_the_reference_run(gold, tag):
+  """define_losses_hierarchical.py:14-224 executed by the reference itself vs oracle/losses.py: the five losses and
+  the gradient of `total` w.r.t. the low-resolution logits (fp32, 1e-5 / 1e-4 of the gradient's max)."""
+  from oracle import network as onet
+  dataset, (n_pp, n_pb, n_pi, H, W), low, labels = _loss_inputs(gold, tag)
+  full = [tfops.resize_bilinear(z, H, W, align_corners=True) for z in low]
+  pred = onet.compose_predictions(*full, dataset)
+  assert np.array_equal(pred['l1_decisions'].numpy(), gold[f'{tag}/l1_decisions'])
+  got = olosses.define_losses(pred, labels, dataset)
+  for k in ('l1_segmentation', 'l2_vehicle_segmentation', 'l2_human_segmentation'):
+    ref = float(gold[f'{tag}/loss_{k}'])
+    assert abs(float(got[k].detach()) - ref) <= 1e-5 * max(1.0, abs(ref)), (k, float(got[k].detach()), ref)
+  reg = float(gold[f'{tag}/loss_regularization'])
+  assert abs(float(got['segmentation'].detach()) + reg - float(gold[f'{tag}/loss_total'])) <= 1e-5
+  assert float(gold[f'{tag}/loss_l1_segmentation_hot']) == 0.0
+  got['segmentation'].backward()
+  for z, k in zip(low, ('l1', 'l2_vehicle', 'l2_human')):
+    ref = torch.from_numpy(gold[f'{tag}/grad_lowres_{k}_logits'])
+    assert float((z.grad - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-9, k
+
+
+def test_rasteriser_equals_generate_rla(gold):
+  """input_subset_bboxes_v2.py:74-98 `_generate_rla` run by the reference vs oracle/weak_labels.py (bit-exact), on
+  the docstring's normalisation cases and on every box list of the loss fixtures."""
+  h, w = (int(x) for x in gold['rla/size'])
+  boxes = [(int(c),) + tuple(float(v) for v in xy) for c, xy in zip(gold['rla/cids'], gold['rla/coords']) if c >= 0]
+  got = oweak.bbox_labels(boxes, h, w)
+  assert np.array_equal(got, gold['rla/out'])
+  assert np.all(np.abs(got.sum(-1) - 1.0) < 1e-3)          # input_subset_bboxes_v2_test.py:40-43
+  for tag in LOSS_CASES:
+    n_pp, n_pb, n_pi, hh, ww = (int(x) for x in gold[f'{tag}/counts'])
+    for i in range(n_pb):
+      boxes = [(int(c),) + tuple(float(v) for v in xy)
+               for c, xy in zip(gold[f'{tag}/bbox{i}_cids'], gold[f'{tag}/bbox{i}_coords']) if c >= 0]
+      assert np.array_equal(oweak.bbox_labels(boxes, 8 * hh, 8 * ww), gold[f'{tag}/prolabels_per_bbox'][i]), (tag, i)
+
+
+def test_segment_sum_worked_example(gold):
+  """:112-113, 219-224: half a vehicle + half a human on one pixel -> 1/2 car + 1/2 void for the vehicle head."""
+  lab = torch.from_numpy(gold['segment_sum/labels'])
+  got = tfops.unsorted_segment_sum_last(lab, [int(x) for x in gold['segment_sum/ids']], 7)
+  assert np.array_equal(got.numpy(), gold['segment_sum/out'])
+  assert got[0, 0, 0].tolist() == [0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 0.5]   # car -> vehicle class 0, human -> void
+
+
+def test_cid_remap_equals_reference(gold):
+  m = [int(x) for x in gold['remap/map']]
+  assert np.array_equal(ometrics.map_decisions_to_new_cids(gold['remap/decisions'], m), gold['remap/out_decisions'])
+  np.testing.assert_allclose(ometrics.map_probabilities_to_new_cids(gold['remap/probs'], m), gold['remap/out_probs'], rtol=0, atol=1e-7)
+  m = [int(x) for x in gold['remap_cs/map']]
+  assert np.array_equal(ometrics.map_decisions_to_new_cids(gold['remap_cs/decisions'], m), gold['remap_cs/out_decisions'])
+  assert bool(gold['remap_cs/probs_untouched'])   # 14 channels vs a 20-entry map: the reference's try/except skips them
+  from wlseg import estimator as west
+  assert west._replacevoids([int(x) for x in gold['replacevoids/in']]) == [int(x) for x in gold['replacevoids/out']]
+  assert ometrics.replacevoids([int(x) for x in gold['replacevoids/in']]) == [int(x) for x in gold['replacevoids/out']]
+
+
+@pytest.mark.parametrize('tag', ['resize_up', 'resize_down'])
+def test_resize_predictions_equals_reference(gold, tag):
+  oh, ow = (int(x) for x in gold[f'{tag}/size'])
+  got = tfops.resize_nearest(torch.from_numpy(gold[f'{tag}/in_decisions'])[..., None], oh, ow, align_corners=True)[..., 0]
+  assert np.array_equal(got.numpy(), gold[f'{tag}/out_decisions'])
+  for k in ('l1_probabilities', 'l2_vehicle_probabilities', 'l2_human_probabilities'):
+    got = tfops.resize_bilinear(torch.from_numpy(gold[f'{tag}/in_{k}']), oh, ow, align_corners=True)
+    np.testing.assert_allclose(got.numpy(), gold[f'{tag}/out_{k}'], rtol=0, atol=1e-6)
+
+
+def test_replace_voids_flat_classifier(gold):
+  """:573-630 on the key set it accepts: a void decision (last channel) becomes the runner-up."""
+  p, d = gold['replace_voids/probs'], gold['replace_voids/decisions']
+  best_non_void = np.argmax(p[..., :-1], -1)
+  want = np.where(d == p.shape[-1] - 1, best_non_void, d).astype(np.int32)
+  assert np.array_equal(want, gold['replace_voids/out_decisions'])
+
+
+def test_batch_mean_iou_equals_reference(gold):
+  got = ometrics.batch_mean_iou(gold['mean_iou/labels'], gold['mean_iou/decisions'], 20)
+  assert abs(float(got) - float(gold['mean_iou/out'])) <= 1e-6
+  from wlseg import estimator as west
+  cm = torch.from_numpy(ometrics.confusion_matrix(gold['mean_iou/labels'], gold['mean_iou/decisions'], 20))
+  assert abs(float(west.mean_iou_from_cm(cm, 20)) - float(gold['mean_iou/out'])) <= 1e-6
+
+
+def test_schedules_and_momentum_equal_reference(gold):
+  steps = [int(s) for s in gold['lr/steps']]
+  b, v = [8 * 743, 15 * 743], [0.01, 0.005, 0.0025]
+  assert [oopt.piecewise_constant(s, b, v) for s in steps] == gold['lr/piecewise'].tolist()
+  got = [oopt.polynomial_decay(0.01, s, 17 * 743, 0.0001, 0.9) for s in steps]
+  np.testing.assert_allclose(got, gold['lr/polynomial'], rtol=1e-12)
+  # the product's host-side schedule (wlseg/estimator.py learning_rate)
+  from wlseg import estimator as west
+
+  class P:
+    learning_rate_schedule, learning_rate_boundaries, learning_rate_values = 'piecewise_constant', b, v
+  assert [west.learning_rate(P, s) for s in steps] == gold['lr/piecewise'].tolist()
+  for name, nesterov in (('plain', False), ('nesterov', True)):
+    w = torch.from_numpy(gold['sgdm/w0']).clone()
+    acc = torch.zeros_like(w)
+    for g in torch.from_numpy(gold['sgdm/grads']):
+      w, acc = oopt.momentum_step(w, g, acc, 0.01, 0.9, nesterov)
+    np.testing.assert_allclose(w.numpy(), gold[f'sgdm/{name}'], rtol=0, atol=1e-7)
+
+
+def test_host_helpers_equal_reference(gold):
+  from wlseg import estimator as west
+  from wlseg import metrics as wmetrics
+
+  class P:
+    distribute = False
+  assert west.get_temp_Nb(P, 8) == int(gold['temp_nb/out'][0])
+  assert gold['m1_1/out'].tolist() == [-1.0, -0.5, 0.0, 1.0]
+  cm = gold['print_metrics/cm']
+  buf = io.StringIO()
+  with np.errstate(all='ignore'):
+    wmetrics.print_metrics_from_confusion_matrix(cm, printfile=buf, summary=True)
+  assert buf.getvalue() == str(gold['print_metrics/summary'])
+  m = ometrics.metrics_from_confusion_matrix(cm.astype(np.int64))
+  assert f"Mean iou (ignoring accuracies' nans but including ious' 0s): {m['mean_iou']:5.2f}" in str(gold['print_metrics/summary'])
