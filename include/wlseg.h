@@ -78,6 +78,15 @@ int wlseg_conv2d_fprop(const wlseg_conv_params* p, const void* x, const void* w,
                        const float* scale, const float* shift, const void* residual,
                        double* bn_sum, double* bn_sqsum, wlseg_stream_t stream);
 
+/* y = (conv(x, w) + residual) * mask, bf16, tcgen05 only: the data gradient of a layer whose INPUT tensor is the
+ * output of a ReLU (+ residual) unit leaves the dgrad epilogue already multiplied by that ReLU's derivative.
+ * out_mask: one bit per output element, [N*P*Q][K / 8] bytes, bit (c & 7) of byte c >> 3 (wlseg_bn_apply_mask writes
+ * it in the forward pass).  The batch-norm backward of the unit then runs without reading its activation and without
+ * writing a separate residual gradient (it IS this tensor): 3 of its 8 tensor passes disappear
+ * (models/resnet50_extended_model_hierarchical.py:298-312 backward, slim bottleneck shortcut add). */
+int wlseg_conv2d_fprop_masked(const wlseg_conv_params* p, const void* x, const void* w, void* y,
+                              const void* residual, const uint8_t* out_mask, wlseg_stream_t stream);
+
 /* dx = conv_transpose(dy, w): gradient wrt the input (TF Conv2DBackpropInput, reached through
  * create_train_op, estimator/define_estimator_hierarchical.py:120-129).  dx is fully written. */
 int wlseg_conv2d_dgrad(const wlseg_conv_params* p, const void* dy, const void* w, void* dx,
@@ -122,6 +131,12 @@ int wlseg_bn_finalize_apply(const double* sum, const double* sqsum, int64_t coun
 int wlseg_bn_apply(const void* z, const float* scale, const float* shift, const void* residual,
                    void* y, int64_t count, int32_t C, int32_t relu, int32_t dtype,
                    wlseg_stream_t stream);
+
+/* wlseg_bn_apply with ReLU that also records relu_mask[row][c >> 3] bit (c & 7) = (y > 0)
+ * (C % 32 == 0, C <= 2048); see wlseg_conv2d_fprop_masked. */
+int wlseg_bn_apply_mask(const void* z, const float* scale, const float* shift, const void* residual,
+                        void* y, uint8_t* relu_mask, int64_t count, int32_t C, int32_t dtype,
+                        wlseg_stream_t stream);
 
 /* Backward of y = relu?(bn(z) + residual).  Pass 1 (reduce): with g = dy * (y > 0 if relu),
  * dbeta[c] += sum g, dgamma[c] += sum g * (z - mean)*invstd  (double[C], caller zeroes).

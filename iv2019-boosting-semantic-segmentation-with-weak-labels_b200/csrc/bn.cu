@@ -357,7 +357,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
 template <typename T, int kRowsU>
 __global__ void __launch_bounds__(256)
 bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                     const T* __restrict__ res, T* __restrict__ y, int64_t count, int C, int relu, int rev) {
+                     const T* __restrict__ res, T* __restrict__ y, int64_t count, int C, int relu, int rev,
+                     uint8_t* __restrict__ relu_mask) {
   pdl_launch_dependents();
   pdl_wait();   // scale / shift were written by bn_finalize, the kernel right before this one
   const int cv = C / 8;
@@ -405,6 +406,13 @@ bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ scale, c
       Vec8<T> o;
       o.pack(f);
       o.store(y + row * C + c0);
+      if (relu_mask != nullptr) {
+        // one bit per element: y > 0 (wlseg_bn_apply_mask); byte tx of the row = channels [8 tx, 8 tx + 8)
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
+        relu_mask[row * cv + tx] = (uint8_t)m;
+      }
     }
   }
 }
@@ -493,7 +501,7 @@ static int bn_bwd_ctas() { return env_int("WLSEG_BN_BWD_CTAS", 2); }
 
 template <typename T>
 static void launch_apply_rows(const void* z, const float* scale, const float* shift, const void* res, void* y, int64_t count,
-                              int C, int relu, cudaStream_t s) {
+                              int C, int relu, cudaStream_t s, uint8_t* mask = nullptr) {
   const int lanes = 256 / (C / 8);
   // measured (tools/bn_sweep.py, graph-timed, HBM-cold): without a residual one row per thread at full occupancy
   // wins (871 vs 902 us per step-equivalent); with a residual stream two rows at 4 CTAs / SM do
@@ -502,9 +510,9 @@ static void launch_apply_rows(const void* z, const float* scale, const float* sh
                         res != nullptr ? bn_apply_ctas() : env_int("WLSEG_BN_APPLY_CTAS_PLAIN", 8));
   const int rev = env_int("WLSEG_BN_APPLY_REV", 1);
   cudaError_t e;
-  if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev);
-  else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev);
-  else e = launch_pdl(bn_apply_rows_kernel<T, 2>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev);
+  if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask);
+  else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask);
+  else e = launch_pdl(bn_apply_rows_kernel<T, 2>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask);
   (void)e;   // reported by the caller's WLSEG_LAUNCH_CHECK (cudaGetLastError)
 }
 
@@ -721,6 +729,19 @@ extern "C" int wlseg_bn_apply(const void* z, const float* scale, const float* sh
                                                             (float*)y, count, C, relu);
   else
     WLSEG_CHECK_ARG(false, "bn_apply: bad dtype %d", dtype);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wlseg_bn_apply_mask(const void* z, const float* scale, const float* shift, const void* residual, void* y,
+                                   uint8_t* relu_mask, int64_t count, int32_t C, int32_t dtype, wlseg_stream_t stream) {
+  if (int e = check_bn_shape(count, C, "bn_apply_mask")) return e;
+  if (count == 0) return 0;
+  WLSEG_CHECK_ARG(z && scale && shift && y && relu_mask, "bn_apply_mask: null pointer");
+  WLSEG_CHECK_ARG(C % 32 == 0 && C <= 2048, "bn_apply_mask: C must be a multiple of 32 and <= 2048 (got %d)", C);
+  if (dtype == WLSEG_BF16) launch_apply_rows<__nv_bfloat16>(z, scale, shift, residual, y, count, C, 1, (cudaStream_t)stream, relu_mask);
+  else if (dtype == WLSEG_F32) launch_apply_rows<float>(z, scale, shift, residual, y, count, C, 1, (cudaStream_t)stream, relu_mask);
+  else WLSEG_CHECK_ARG(false, "bn_apply_mask: bad dtype %d", dtype);
   WLSEG_LAUNCH_CHECK();
   return 0;
 }

@@ -142,6 +142,36 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Division by a launch-time constant without the ~25-instruction dependent chain (I2F, MUFU.RCP, F2I, fix-ups) the
+// compiler emits for a runtime divisor: q = (umulhi(n, mul) + n) >> shift, exact for 0 <= n < 2^31, 1 <= d < 2^31.
+// The persistent tile loops decode (image, row, column, channel-tile) coordinates in single elected threads - the TMA
+// producer, the residual cursors of the epilogue warps - where that chain sat on the critical path: ncu's source view
+// attributed 38 % of an epilogue step of the conv3 + residual layers to it (profiles/r2_epilogue_divisions.md).
+struct FastDiv {
+  uint32_t mul, shift, d;
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return (__umulhi(n, mul) + n) >> shift;
+#else
+    return (uint32_t)((((uint64_t)n * mul) >> 32) + n) >> shift;
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) { f.mul = 0; f.shift = 0; f.d = 1; return f; }
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.shift = l;
+  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - d)) / d + 1);
+  return f;
+}
+
 // grid size for grid-stride bandwidth kernels: a multiple of the SM count
 inline int bw_grid(int64_t work_items, int threads, int ctas_per_sm) {
   int64_t need = ceil_div(work_items, threads);

@@ -67,6 +67,7 @@ struct IgemmParams {
   const void* res;
   double* bn_sum;
   double* bn_sqsum;
+  const uint32_t* out_mask;   // optional bit mask [N*P*Q][K / 32] applied to the output (wlseg_conv2d_fprop_masked)
   int N, P, Q, K, C;
   int R, S, stride, dilation, pad_top, pad_left;
   int y_pitch, res_pitch, res_stride, res_H, res_W;
@@ -80,6 +81,9 @@ struct IgemmParams {
   int res_mid;        // residual layers: issue the next residual box in the MIDDLE of a step (see the epilogue)
   int epi_db;         // layers without a residual: two staging buffers per warp (else one)
   int reverse;        // walk the M tiles from the last to the first (wlseg_conv_params::reverse)
+  FastDiv fd_n_tiles, fd_tiles_w, fd_tiles_h;   // tile decode without runtime divisions (common.cuh)
+  int m_tiles;        // N * tiles_h * tiles_w
+  int units;          // work units of the persistent loop: tiles, or (CTA pair) pairs of M tiles x N tiles
 };
 
 constexpr int kSubW = 64;                       // epilogue sub-tile: 64 channels = one 128-byte row
@@ -89,9 +93,10 @@ constexpr int kMaxEpiWarps = 16;
 constexpr int kBarBytes = 512;                  // full[8] empty[8] tfull[2] tempty[2] rfull[32] + TMEM slot
 constexpr int kSmemMax = 227 * 1024;            // opt-in dynamic shared memory per CTA on sm_100
 
-template <int BN>
+template <int BN, bool kPair = false>
 struct IgemmCfg {
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBRows = kPair ? BN / 2 : BN;      // filter rows this CTA stages
+  static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
@@ -117,18 +122,28 @@ struct SubTileCursor {
   int n, p0, q0, k0;  // decoded tile origin
 };
 
-template <int BN>
-__device__ __forceinline__ void decode_tile(const IgemmParams& prm, int tile, int& n, int& p0, int& q0, int& k0) {
-  const int nt = tile % prm.n_tiles;
-  int mt = tile / prm.n_tiles;
+// kPair: a unit is TWO consecutive M tiles on one N tile, CTA `rank` of the pair takes M tile 2 * (unit / n_tiles) + rank.
+// An odd M-tile count leaves the last pair's second CTA a phantom tile: image index N, so that TMA zero-fills every
+// load and clips every store.
+template <int BN, bool kPair>
+__device__ __forceinline__ void decode_tile(const IgemmParams& prm, int tile, int rank, int& n, int& p0, int& q0, int& k0) {
+  uint32_t umt, unt;
+  prm.fd_n_tiles.divmod((uint32_t)tile, umt, unt);
+  int mt = (int)umt;
+  if (kPair) mt = 2 * mt + rank;
+  k0 = (int)unt * BN;
+  if (kPair && mt >= prm.m_tiles) {
+    n = prm.N; p0 = 0; q0 = 0;
+    return;
+  }
   // reverse: same N tile (the fused statistics keep one N tile per CTA), M tiles from the end of the tensor
-  if (prm.reverse) mt = prm.total_tiles / prm.n_tiles - 1 - mt;
-  const int twi = mt % prm.tiles_w; mt /= prm.tiles_w;
-  const int thi = mt % prm.tiles_h;
-  n = mt / prm.tiles_h;
-  q0 = twi << prm.tw_log2;
-  p0 = thi * (kBM >> prm.tw_log2);
-  k0 = nt * BN;
+  if (prm.reverse) mt = prm.m_tiles - 1 - mt;
+  uint32_t rest, twi, un, thi;
+  prm.fd_tiles_w.divmod((uint32_t)mt, rest, twi);
+  prm.fd_tiles_h.divmod(rest, un, thi);
+  n = (int)un;
+  q0 = (int)twi << prm.tw_log2;
+  p0 = (int)thi * (kBM >> prm.tw_log2);
 }
 
 template <int BN>
@@ -144,10 +159,19 @@ __device__ __forceinline__ int num_subtiles(const IgemmParams& prm, int k0) {
 // a warp reads the lanes 32*(warpid % 4) ..) and column group e / 4 of every 64-channel sub-tile.
 // Two to four epilogue warps per scheduler hide each other's ALU / shared-memory latencies - with
 // one warp per scheduler the epilogue, not HBM, bounded every bandwidth-bound layer (profiles/).
-template <int BN, typename TY, bool kTmaEpi, int EW>
+//
+// kPair: the CTA-pair form (cluster of 2, tcgen05 cta_group::2).  One MMA of M = 256 spans two M tiles, each CTA stages
+// its own activation tile and only HALF of the filter tile (rows [rank * BN/2, +BN/2)): the per-SM L2 -> SM ingress of
+// the bandwidth-bound 1x1 / conv3 + residual layers - two thirds of which were filters (profiles/r1_eval_igemm256_full_
+// summary.txt: 1.07 GB through the fabric against 0.56 GB of DRAM traffic) - drops by a third, and a stage shrinks from
+// 48 to 32 KB.  The leader CTA (rank 0) issues the MMAs; both CTAs run their own producer and their own epilogue.
+template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, kPair>;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int CG = EW / 4;             // warps per TMEM lane quarter: each takes every CG-th sub-tile
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();   // the next kernel may stage its CTAs; it waits for this grid before touching memory
@@ -183,16 +207,20 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(tfull_bar + a), 1);
-      mbar_init(smem_u32(tempty_bar + a), EW);  // one arrival per epilogue warp
+      mbar_init(smem_u32(tempty_bar + a), kPair ? 2 * EW : EW);  // one arrival per epilogue warp (of both CTAs)
     }
     for (int a = 0; a < 2 * EW; ++a) mbar_init(smem_u32(rfull_bar + a), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair(smem_u32(tmem_slot), Cfg::kTmemCols);
+    else tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  }
   if (kTmaEpi && warp == 3 && prm.bn_sum != nullptr)
     for (int j = lane; j < 2 * BN; j += 32) s_stat[j] = 0.f;
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync();   // the peer's barriers are initialised before anything of this CTA signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only this CTA's shared memory / TMEM and the kernel parameters; from here on
@@ -206,34 +234,46 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < prm.units; tile += unit_step) {
         int n, p0, q0, k0;
-        decode_tile<BN>(prm, tile, n, p0, q0, k0);
+        decode_tile<BN, kPair>(prm, tile, rank, n, p0, q0, k0);
+        // (tap, channel chunk) walked with counters: no division in the producer's issue loop
+        int tap = 0, cc = 0, r = 0, s = 0;
         for (int kb = 0; kb < prm.num_kb; ++kb) {
-          const int tap = kb / prm.cchunks;
-          const int cc = kb - tap * prm.cchunks;
-          const int r = tap / prm.S;
-          const int s = tap - r * prm.S;
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t a_dst = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_dst = a_dst + kABytes;
           const uint32_t bar = smem_u32(full_bar + stage);
-          mbar_arrive_expect_tx(bar, Cfg::kStageBytes);
-          tma_load_4d(a_dst, &prm.map_a, bar, cc * kBK, q0 * prm.stride - prm.pad_left + s * prm.dilation,
-                      p0 * prm.stride - prm.pad_top + r * prm.dilation, n);
-          tma_load_3d(b_dst, &prm.map_b, bar, cc * kBK, tap, k0);
+          if constexpr (kPair) {
+            // the leader's barrier collects the bytes of BOTH CTAs' boxes (a peer box may complete before the leader
+            // has posted its expectation: the pending arrival keeps the phase open)
+            if (rank == 0) mbar_arrive_expect_tx(bar, 2 * Cfg::kStageBytes);
+            const uint32_t lbar = mapa_shared(bar, 0);
+            tma_load_4d_pair(a_dst, &prm.map_a, lbar, cc * kBK, q0 * prm.stride - prm.pad_left + s * prm.dilation,
+                             p0 * prm.stride - prm.pad_top + r * prm.dilation, n);
+            tma_load_3d_pair(b_dst, &prm.map_b, lbar, cc * kBK, tap, k0 + (int)rank * Cfg::kBRows);
+          } else {
+            mbar_arrive_expect_tx(bar, Cfg::kStageBytes);
+            tma_load_4d(a_dst, &prm.map_a, bar, cc * kBK, q0 * prm.stride - prm.pad_left + s * prm.dilation,
+                        p0 * prm.stride - prm.pad_top + r * prm.dilation, n);
+            tma_load_3d(b_dst, &prm.map_b, bar, cc * kBK, tap, k0);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++cc == prm.cchunks) {
+            cc = 0; ++tap;
+            if (++s == prm.S) { s = 0; ++r; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(kPair ? 2 * kBM : kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = unit0; tile < prm.units; tile += unit_step, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);  // epilogue drained this accumulator
@@ -248,12 +288,15 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (kPair) umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(smem_u32(empty_bar + stage));              // stage free once these MMAs retire
+          // stage free once these MMAs retire (pair: in both CTAs)
+          if (kPair) umma_commit_pair(smem_u32(empty_bar + stage), 3); else umma_commit(smem_u32(empty_bar + stage));
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(tfull_bar + acc));                  // accumulator complete
+        // accumulator complete (pair: each CTA's epilogue waits on its own barrier)
+        if (kPair) umma_commit_pair(smem_u32(tfull_bar + acc), 3); else umma_commit(smem_u32(tfull_bar + acc));
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -265,6 +308,11 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     const int row = quarter * 32 + lane;      // tile row = pixel within the patch
     const int dy_ = row >> prm.tw_log2, dx_ = row & (TW - 1);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // the accumulator goes back to the MMA warp - of the leader CTA in the pair form
+    auto release_acc = [&](int a) {
+      if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(tempty_bar + a), 0));
+      else mbar_arrive(smem_u32(tempty_bar + a));
+    };
     int iter = 0;
     if constexpr (kTmaEpi) {
       // ---- staged epilogue, one INDEPENDENT pipeline per warp: a warp owns the 32 rows of its TMEM
@@ -287,11 +335,11 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       // buffers alone keep far too few bytes in flight to cover HBM latency
       constexpr int kResPf = 4;
       struct ResCursor { int tile, st, cnt; };
-      ResCursor ld = {(int)blockIdx.x, cgrp, 0}, pf = {(int)blockIdx.x, cgrp, 0};
+      ResCursor ld = {unit0, cgrp, 0}, pf = {unit0, cgrp, 0};
       auto next_residual = [&](ResCursor& c, bool stage) {
-        while (c.tile < prm.total_tiles) {
+        while (c.tile < prm.units) {
           int n, p0, q0, k0;
-          decode_tile<BN>(prm, c.tile, n, p0, q0, k0);
+          decode_tile<BN, kPair>(prm, c.tile, rank, n, p0, q0, k0);
           if (c.st < num_subtiles<BN>(prm, k0)) {
             const int cx = (q0 + dx0) * prm.res_stride, cy = (p0 + dy0) * prm.res_stride;
             if (stage) {
@@ -306,7 +354,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
             return;
           }
           c.st = cgrp;
-          c.tile += gridDim.x;
+          c.tile += unit_step;
         }
       };
       if (has_res && lane == 0) {
@@ -322,10 +370,34 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       for (int i = 0; i < kSlots; ++i) a1x[i] = a1y[i] = a2x[i] = a2y[i] = 0.f;
       int stat_k0 = -1;
       int cnt = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
+      // output mask (wlseg_conv2d_fprop_masked: a data gradient leaving through the ReLU of the tensor it belongs to):
+      // 64 bits per pixel and sub-tile, fetched ONE TILE AHEAD - a load issued inside the step sat on its critical
+      // path with a full HBM latency (measured: +18 us on a 40 us dgrad)
+      uint2 mcur[kSlots], mnext[kSlots];
+      auto load_mask = [&](int tile_, uint2 (&m)[kSlots]) {
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) m[i] = make_uint2(0xffffffffu, 0xffffffffu);
+        if (prm.out_mask == nullptr || tile_ >= prm.units) return;
+        int n_, p0_, q0_, k0_;
+        decode_tile<BN, kPair>(prm, tile_, rank, n_, p0_, q0_, k0_);
+        const bool ok = (p0_ + dy_ < prm.P) && (q0_ + dx_ < prm.Q) && (n_ < prm.N);
+        const int nsub_ = num_subtiles<BN>(prm, k0_);
+        const uint2* row = reinterpret_cast<const uint2*>(
+            prm.out_mask + (((int64_t)n_ * prm.P + p0_ + dy_) * prm.Q + q0_ + dx_) * (prm.K >> 5) + (k0_ >> 5));
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+          const int st_ = cgrp + i * CG;
+          m[i] = (ok && st_ < nsub_) ? __ldg(row + st_) : make_uint2(0u, 0u);
+        }
+      };
+      load_mask(unit0, mnext);
+      for (int tile = unit0; tile < prm.units; tile += unit_step, ++iter) {
         int n, p0, q0, k0;
-        decode_tile<BN>(prm, tile, n, p0, q0, k0);
-        const bool valid = (p0 + dy_ < prm.P) && (q0 + dx_ < prm.Q);
+        decode_tile<BN, kPair>(prm, tile, rank, n, p0, q0, k0);
+        const bool valid = (p0 + dy_ < prm.P) && (q0 + dx_ < prm.Q) && (n < prm.N);
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) mcur[i] = mnext[i];
+        load_mask(tile + unit_step, mnext);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         const int nsub = num_subtiles<BN>(prm, k0);
@@ -339,7 +411,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
           // nothing to do in this tile: still one arrival per warp and tile
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+          if (lane == 0) release_acc(acc);
         }
 #pragma unroll
         for (int slot = 0; slot < kSlots; ++slot) {
@@ -378,6 +450,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
               }
               __syncwarp();
             }
+            const uint32_t mword = half == 0 ? mcur[slot].x : mcur[slot].y;
             uint32_t v[32];
             tmem_ld<32>(lane_addr + (uint32_t)(acc * BN + col), v);
             tmem_ld_wait();
@@ -385,7 +458,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
               // this warp's last TMEM read of the tile: hand the accumulator back to the MMA warp
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+              if (lane == 0) release_acc(acc);
             }
             float f[32];
 #pragma unroll
@@ -424,6 +497,10 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
                   f[g * 8 + 2 * e + 1] += t.y;
                 }
               }
+            }
+            if (prm.out_mask != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = ((mword >> j) & 1u) ? f[j] : 0.f;
             }
             if (has_stat && !valid) {
               // pixels outside the image must not reach the statistics (TMA clips them from the store)
@@ -490,12 +567,12 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     } else {
       // ---- direct epilogue: per-thread global stores (fp32 logits, odd channel counts); 32-column
       // chunks are dealt round-robin to the column groups
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = unit0; tile < prm.units; tile += unit_step, ++iter) {
         int n, p0, q0, k0;
-        decode_tile<BN>(prm, tile, n, p0, q0, k0);
+        decode_tile<BN, kPair>(prm, tile, rank, n, p0, q0, k0);
         const int q = q0 + dx_;
         const int p = p0 + dy_;
-        const bool valid = (p < prm.P) && (q < prm.Q);
+        const bool valid = (p < prm.P) && (q < prm.Q) && (n < prm.N);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
@@ -570,7 +647,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         // this warp no longer reads the accumulator: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        if (lane == 0) release_acc(acc);
       }
     }
   }
@@ -578,9 +655,11 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   // teardown: everyone done with TMEM before it is freed
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_relaxed();   // the peer no longer reads this CTA's shared memory / signals its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -658,12 +737,48 @@ static bool igemm_supported(const wlseg_conv_params* p) {
   return true;
 }
 
-template <int BN, typename TY, bool kTmaEpi, int EW>
+// CTA-pair launches: cluster of 2 along x; the number of co-resident clusters is asked from the driver once per kernel
+// (a GPC with an odd number of free SMs cannot host a pair on its last SM)
+template <typename K>
+static int max_active_pairs(K kernel, int threads, int smem_bytes) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * kNumSMs);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pair(void (*kernel)(KArgs...), int clusters, int threads, size_t smem, cudaStream_t stream,
+                               Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair = false>
 static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, kPair>;
   static bool configured = false;
   if (!configured) {
-    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi, EW>,
+    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi, EW, kPair>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
@@ -683,10 +798,22 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   WLSEG_CHECK_ARG(stages >= 2, "conv(tcgen05): shared memory plan leaves fewer than 2 pipeline stages");
   prm.stages = stages;
   const int smem_bytes = stages * Cfg::kStageBytes + fixed;
+  if constexpr (kPair) {
+    static int max_pairs = -1;
+    if (max_pairs < 0) max_pairs = max_active_pairs(conv_igemm_kernel<BN, TY, kTmaEpi, EW, true>, 128 + 32 * EW, kSmemMax);
+    WLSEG_CHECK_ARG(max_pairs > 0, "conv(tcgen05): the device cannot host a CTA pair of this kernel");
+    prm.units = (int)ceil_div(prm.m_tiles, 2) * prm.n_tiles;
+    int clusters = prm.units < max_pairs ? prm.units : max_pairs;
+    if (prm.bn_sum != nullptr && clusters % prm.n_tiles != 0) clusters -= clusters % prm.n_tiles;
+    WLSEG_CHECK_ARG(clusters > 0, "conv(tcgen05): no CTA pair fits the N-tile constraint of the fused statistics");
+    WLSEG_CUDA(launch_pair(conv_igemm_kernel<BN, TY, kTmaEpi, EW, true>, clusters, 128 + 32 * EW, smem_bytes, s, prm));
+    return 0;
+  }
+  prm.units = prm.total_tiles;
   int grid = prm.total_tiles < kNumSMs ? prm.total_tiles : kNumSMs;
   // fused BN statistics live in registers across tiles: every CTA must stay on one N tile
   if (kTmaEpi && prm.bn_sum != nullptr && grid % prm.n_tiles != 0) grid -= grid % prm.n_tiles;
-  WLSEG_CUDA(launch_pdl(conv_igemm_kernel<BN, TY, kTmaEpi, EW>, dim3(grid), dim3(128 + 32 * EW), smem_bytes, s, prm));
+  WLSEG_CUDA(launch_pdl(conv_igemm_kernel<BN, TY, kTmaEpi, EW, false>, dim3(grid), dim3(128 + 32 * EW), smem_bytes, s, prm));
   return 0;
 }
 
@@ -695,9 +822,16 @@ static int launch_igemm(IgemmParams& prm, cudaStream_t s) {
   return launch_igemm_ew<BN, TY, kTmaEpi, 8>(prm, s);
 }
 
+// CTA pair (cta_group::2) for the 256-wide tiles with the staged epilogue.  WLSEG_PAIR: 0 = never, 1 = every such
+// layer, unset = the layers that measured faster with it (see pair_default below)
+static int pair_mode() {
+  const char* e = getenv("WLSEG_PAIR");   // read per call: the parity tests force both forms in one process
+  return e != nullptr ? atoi(e) : -1;
+}
+
 static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const void* w, void* y, const float* scale,
                             const float* shift, const void* residual, double* bn_sum, double* bn_sqsum,
-                            cudaStream_t s) {
+                            cudaStream_t s, const uint32_t* out_mask = nullptr) {
   WLSEG_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0, "conv(tcgen05): x / w must be 16-byte aligned");
   IgemmParams prm;
   const int BN = pick_bn(p->K);
@@ -716,13 +850,6 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
     uint32_t estr[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
     if (int e = encode_tensor_map(&prm.map_a, x, 2, 4, dims, strides, box, estr, 0)) return e;
   }
-  {
-    uint64_t dims[3] = {(uint64_t)p->C, (uint64_t)(p->R * p->S), (uint64_t)p->K};
-    uint64_t strides[2] = {(uint64_t)p->C * 2, (uint64_t)p->C * 2 * p->R * p->S};
-    uint32_t box[3] = {(uint32_t)kBK, 1, (uint32_t)BN};
-    uint32_t estr[3] = {1, 1, 1};
-    if (int e = encode_tensor_map(&prm.map_b, w, 2, 3, dims, strides, box, estr, 1)) return e;
-  }
   const bool f32out = (p->y_dtype == WLSEG_F32);
   // staged (TMA) epilogue: bf16 output whose pixel pitch and base keep every 64-channel row 16-byte aligned
   // (whole 64-channel sub-tiles only; scale / shift are read as float4)
@@ -733,6 +860,25 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   if (residual != nullptr && ((p->res_pitch % 8 != 0) || ((((uintptr_t)residual) & 15) != 0) ||
                               bw * p->res_stride > 256 || bh * p->res_stride > 256))
     tma_epi = false;
+  // CTA pair (cta_group::2): each CTA stages half of the filter tile
+  // Measured on B200, eval shapes 4 x 128 x 256 (gpurun_out -> profiles/r2_layers_eval_pair{0,1}.txt): the pair form wins
+  // 5-15 % wherever a tile runs >= 8 k-blocks (3x3 layers, C >= 512) and on the 1x1 layers without a residual; the
+  // shallow conv3 + residual layers (C <= 256: <= 4 k-blocks per 64 KB residual tile) lose 2-9 %: their epilogues are
+  // the bottleneck and the pair couples two of them per accumulator hand-over.
+  bool use_pair = false;
+  if (BN == 256 && tma_epi) {
+    const int mode = pair_mode();
+    const int kblocks = p->R * p->S * (int)ceil_div(p->C, kBK);
+    const bool pair_default = residual != nullptr ? kblocks >= 8 : kblocks >= 2;
+    use_pair = (mode == 1) || (mode == -1 && pair_default);
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p->C, (uint64_t)(p->R * p->S), (uint64_t)p->K};
+    uint64_t strides[2] = {(uint64_t)p->C * 2, (uint64_t)p->C * 2 * p->R * p->S};
+    uint32_t box[3] = {(uint32_t)kBK, 1, (uint32_t)(use_pair ? BN / 2 : BN)};
+    uint32_t estr[3] = {1, 1, 1};
+    if (int e = encode_tensor_map(&prm.map_b, w, 2, 3, dims, strides, box, estr, 1)) return e;
+  }
   if (tma_epi) {
     {
       uint64_t dims[4] = {(uint64_t)p->K, (uint64_t)p->Q, (uint64_t)p->P, (uint64_t)p->N};
@@ -754,6 +900,9 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   }
   prm.y = y; prm.scale = scale; prm.shift = shift; prm.res = residual;
   prm.bn_sum = bn_sum; prm.bn_sqsum = bn_sqsum;
+  prm.out_mask = out_mask;
+  WLSEG_CHECK_ARG(out_mask == nullptr || (tma_epi && p->K % 32 == 0 && (((uintptr_t)out_mask) & 3) == 0),
+                  "conv_fprop_masked: needs the staged bf16 epilogue (K %% 64 == 0, aligned tensors)");
   prm.N = p->N; prm.P = p->P; prm.Q = p->Q; prm.K = p->K; prm.C = p->C;
   prm.R = p->R; prm.S = p->S; prm.stride = p->stride; prm.dilation = p->dilation;
   prm.pad_top = p->pad_top; prm.pad_left = p->pad_left;
@@ -768,6 +917,11 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   const int64_t total = (int64_t)p->N * prm.tiles_h * prm.tiles_w * prm.n_tiles;
   WLSEG_CHECK_ARG(total < ((int64_t)1 << 31), "conv(tcgen05): too many tiles");
   prm.total_tiles = (int)total;
+  prm.m_tiles = (int)(total / prm.n_tiles);
+  prm.fd_n_tiles = make_fastdiv((uint32_t)prm.n_tiles);
+  prm.fd_tiles_w = make_fastdiv((uint32_t)prm.tiles_w);
+  prm.fd_tiles_h = make_fastdiv((uint32_t)prm.tiles_h);
+  prm.units = prm.total_tiles;
   prm.cchunks = (int)ceil_div(p->C, kBK);
   prm.num_kb = p->R * p->S * prm.cchunks;
 #define WLSEG_IGEMM_CASE(bn)                                                          \
@@ -775,6 +929,7 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
     if (f32out) return launch_igemm<bn, float, false>(prm, s);                        \
     if (bn >= kSubW && tma_epi) return launch_igemm<bn, __nv_bfloat16, (bn >= kSubW)>(prm, s); \
     return launch_igemm<bn, __nv_bfloat16, false>(prm, s);
+  if (use_pair) return launch_igemm_ew<256, __nv_bfloat16, true, 8, true>(prm, s);
   switch (BN) {
     WLSEG_IGEMM_CASE(32)
     WLSEG_IGEMM_CASE(64)
@@ -792,6 +947,21 @@ using namespace wlseg;
 extern "C" int wlseg_conv2d_tcgen05_supported(const wlseg_conv_params* p) {
   if (p == nullptr) return 0;
   return igemm_supported(p) ? 1 : 0;
+}
+
+extern "C" int wlseg_conv2d_fprop_masked(const wlseg_conv_params* p, const void* x, const void* w, void* y,
+                                         const void* residual, const uint8_t* out_mask, wlseg_stream_t stream) {
+  if (int e = check_conv_params(p)) return e;
+  if (p->N == 0) return 0;
+  WLSEG_CHECK_ARG(x && w && y && out_mask, "conv_fprop_masked: null pointer");
+  WLSEG_CHECK_ARG(igemm_supported(p) && p->y_dtype == WLSEG_BF16 && p->relu == 0,
+                  "conv_fprop_masked: tcgen05 bf16 configurations without ReLU only");
+  if (residual != nullptr)
+    WLSEG_CHECK_ARG(p->res_stride > 0 && p->res_pitch >= p->K && (p->P - 1) * p->res_stride < p->res_H &&
+                        (p->Q - 1) * p->res_stride < p->res_W,
+                    "conv_fprop_masked: residual geometry inconsistent");
+  return conv_fprop_igemm(p, x, w, y, nullptr, nullptr, residual, nullptr, nullptr, (cudaStream_t)stream,
+                          reinterpret_cast<const uint32_t*>(out_mask));
 }
 
 extern "C" int wlseg_conv2d_fprop(const wlseg_conv_params* p, const void* x, const void* w, void* y,

@@ -58,6 +58,9 @@ struct WgradParams {
   int units;
   int stages, epi_bufs;
   int swap_offsets;                // debug: exchange LBO / SBO in the MN-major descriptors
+  // every runtime divisor of the kernel as multiply-shift constants (common.cuh FastDiv): the producer used to spend
+  // three ~150-cycle division chains per 64-pixel stage, next to 512 cycles of tensor time for that stage
+  FastDiv fd_tiles, fd_n_tiles, fd_cchunks, fd_S, fd_patches_w, fd_patches_h;
 };
 
 // MN-major SWIZZLE_128B shared-memory descriptor: 64 contiguous MN elements (128 B) per row, 8
@@ -84,12 +87,20 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
                : "memory");
 }
 
-template <int BN>
+// kPair (BN = 256 only): CTA pair, tcgen05 cta_group::2 - one MMA of M = 256 output channels; CTA `rank` stages ITS 128
+// channels of dy and HALF of the x chunks of the N tile (chunks 2 * rank, 2 * rank + 1): 32 KB per stage and CTA instead
+// of 48 KB for the same 4.2 MFLOP per SM - the kernel was bound by the L2 -> SM ingress.
+template <int BN, bool kPair>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
+  static_assert(!kPair || BN == 256, "the pair form is built for 256-wide N tiles");
   constexpr int CH = BN / 64;                              // B chunks per N tile
-  constexpr int kStageBytes = kWgABytes + CH * kChunkBytes;
+  constexpr int CHL = kPair ? CH / 2 : CH;                 // B chunks this CTA stages
+  constexpr int kStageBytes = kWgABytes + CHL * kChunkBytes;
   constexpr int kTmemCols = 2 * BN;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -117,13 +128,17 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(tfull_bar + a), 1);
-      mbar_init(smem_u32(tempty_bar + a), kWgEpiWarps);
+      mbar_init(smem_u32(tempty_bar + a), kPair ? 2 * kWgEpiWarps : kWgEpiWarps);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
+    else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // prologue done; dz / x of the previous kernels are read from here on
@@ -133,59 +148,77 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < prm.units; unit += gridDim.x) {
-        const int tile = unit % prm.tiles, split = unit / prm.tiles;
-        const int nt = tile % prm.n_tiles, mt = tile / prm.n_tiles;
-        const int k0 = mt * 128;
-        int nch = prm.chunks_total - nt * CH;
+      for (int unit = unit0; unit < prm.units; unit += unit_step) {
+        uint32_t tile, split, nt, mt;
+        prm.fd_tiles.divmod((uint32_t)unit, split, tile);
+        prm.fd_n_tiles.divmod(tile, mt, nt);
+        const int k0 = kPair ? ((int)mt * 2 + (int)rank) * 128 : (int)mt * 128;
+        int nch = prm.chunks_total - (int)nt * CH;
         if (nch > CH) nch = CH;
+        if (kPair) nch = CHL;   // the host takes the pair form only when every N tile is complete
         // tap offsets / channel origins of this tile's B chunks
-        int coff[CH], xoff[CH], yoff[CH];
+        int coff[CHL], xoff[CHL], yoff[CHL];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int id = nt * CH + j;
-          const int tap = id / prm.cchunks;
-          const int r = tap / prm.S, s = tap - r * prm.S;
+        for (int j = 0; j < CHL; ++j) {
+          const int id = (int)nt * CH + (kPair ? (int)rank * CHL : 0) + j;
+          const int tap = (int)prm.fd_cchunks.div((uint32_t)id);
+          const int r = (int)prm.fd_S.div((uint32_t)tap), s = tap - r * prm.S;
           coff[j] = (id - tap * prm.cchunks) * 64;
           xoff[j] = s * prm.dilation - prm.pad_left;
           yoff[j] = r * prm.dilation - prm.pad_top;
         }
-        const int pp0 = split * prm.patches_per_split;
+        const int pp0 = (int)split * prm.patches_per_split;
         int pp1 = pp0 + prm.patches_per_split;
         if (pp1 > prm.patches) pp1 = prm.patches;
+        // patch coordinates: decoded once per unit, then walked with counters
+        uint32_t rest, upwi, un, uphi;
+        prm.fd_patches_w.divmod((uint32_t)pp0, rest, upwi);
+        prm.fd_patches_h.divmod(rest, un, uphi);
+        int pwi = (int)upwi, phi = (int)uphi, n = (int)un;
         for (int pp = pp0; pp < pp1; ++pp) {
-          int t = pp;
-          const int pwi = t % prm.patches_w; t /= prm.patches_w;
-          const int phi = t % prm.patches_h;
-          const int n = t / prm.patches_h;
           const int q0 = pwi << prm.tw_log2, p0 = phi * prm.th;
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t a_dst = smem_u32(smem + stage * kStageBytes);
           const uint32_t b_dst = a_dst + kWgABytes;
           const uint32_t bar = smem_u32(full_bar + stage);
-          mbar_arrive_expect_tx(bar, (uint32_t)((2 + nch) * kChunkBytes));
-          tma_load_4d(a_dst, &prm.map_dy, bar, k0, q0, p0, n);
-          tma_load_4d(a_dst + kChunkBytes, &prm.map_dy, bar, k0 + 64, q0, p0, n);
+          if constexpr (kPair) {
+            if (rank == 0) mbar_arrive_expect_tx(bar, (uint32_t)(2 * kStageBytes));   // both CTAs' boxes
+            const uint32_t lbar = mapa_shared(bar, 0);
+            tma_load_4d_pair(a_dst, &prm.map_dy, lbar, k0, q0, p0, n);
+            tma_load_4d_pair(a_dst + kChunkBytes, &prm.map_dy, lbar, k0 + 64, q0, p0, n);
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (j < nch)
-              tma_load_4d(b_dst + j * kChunkBytes, &prm.map_x, bar, coff[j], q0 * prm.stride + xoff[j],
-                          p0 * prm.stride + yoff[j], n);
+            for (int j = 0; j < CHL; ++j)
+              tma_load_4d_pair(b_dst + j * kChunkBytes, &prm.map_x, lbar, coff[j], q0 * prm.stride + xoff[j],
+                               p0 * prm.stride + yoff[j], n);
+          } else {
+            mbar_arrive_expect_tx(bar, (uint32_t)((2 + nch) * kChunkBytes));
+            tma_load_4d(a_dst, &prm.map_dy, bar, k0, q0, p0, n);
+            tma_load_4d(a_dst + kChunkBytes, &prm.map_dy, bar, k0 + 64, q0, p0, n);
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (j < nch)
+                tma_load_4d(b_dst + j * kChunkBytes, &prm.map_x, bar, coff[j], q0 * prm.stride + xoff[j],
+                            p0 * prm.stride + yoff[j], n);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++pwi == prm.patches_w) {
+            pwi = 0;
+            if (++phi == prm.patches_h) { phi = 0; ++n; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_mn(128, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_mn(kPair ? 256 : 128, BN);
       const uint32_t lbo = prm.swap_offsets ? 1024u : (uint32_t)kChunkBytes;
       const uint32_t sbo = prm.swap_offsets ? (uint32_t)kChunkBytes : 1024u;
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int unit = blockIdx.x; unit < prm.units; unit += gridDim.x, ++iter) {
-        const int split = unit / prm.tiles;
+      for (int unit = unit0; unit < prm.units; unit += unit_step, ++iter) {
+        const int split = (int)prm.fd_tiles.div((uint32_t)unit);
         const int pp0 = split * prm.patches_per_split;
         int pp1 = pp0 + prm.patches_per_split;
         if (pp1 > prm.patches) pp1 = prm.patches;
@@ -204,12 +237,13 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
             // 16 pixels = two 8-row swizzle atoms = 2048 bytes further down both operands
             const uint64_t adesc = make_smem_desc_mn(a_addr + k * 2048, lbo, sbo);
             const uint64_t bdesc = make_smem_desc_mn(b_addr + k * 2048, lbo, sbo);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((pp != pp0) | (k != 0)));
+            if (kPair) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (uint32_t)((pp != pp0) | (k != 0)));
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (uint32_t)((pp != pp0) | (k != 0)));
           }
-          umma_commit(smem_u32(empty_bar + stage));
+          if (kPair) umma_commit_pair(smem_u32(empty_bar + stage), 3); else umma_commit(smem_u32(empty_bar + stage));
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(tfull_bar + acc));
+        if (kPair) umma_commit_pair(smem_u32(tfull_bar + acc), 3); else umma_commit(smem_u32(tfull_bar + acc));
       }
     }
   } else if (warp >= kWgEpiWarp0) {
@@ -223,11 +257,16 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
     const uint32_t sw = (uint32_t)(lane & 7);
     uint8_t* buf = epi_smem + ew * kWgWarpBufBytes;
     uint8_t* myrow = buf + lane * 128;
+    auto release_acc = [&](int a) {
+      if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(tempty_bar + a), 0));
+      else mbar_arrive(smem_u32(tempty_bar + a));
+    };
     int iter = 0;
-    for (int unit = blockIdx.x; unit < prm.units; unit += gridDim.x, ++iter) {
-      const int tile = unit % prm.tiles;
-      const int nt = tile % prm.n_tiles, mt = tile / prm.n_tiles;
-      const int k0 = mt * 128;
+    for (int unit = unit0; unit < prm.units; unit += unit_step, ++iter) {
+      uint32_t tile, split_, unt, umt;
+      prm.fd_tiles.divmod((uint32_t)unit, split_, tile);
+      prm.fd_n_tiles.divmod(tile, umt, unt);
+      const int nt = (int)unt, k0 = kPair ? ((int)umt * 2 + (int)rank) * 128 : (int)umt * 128;
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
@@ -237,7 +276,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
       for (int j = 0; j < 2 * CH; ++j) {
         const int id = nt * CH + (j >> 1);
         if (id >= prm.chunks_total) break;
-        const int tap = id / prm.cchunks;
+        const int tap = (int)prm.fd_cchunks.div((uint32_t)id);
         if ((id - tap * prm.cchunks) * 64 + (j & 1) * 32 < prm.C) nsub = j + 1;
       }
       // this warp's last sub-tile index (its final TMEM read of the unit)
@@ -246,11 +285,11 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
       if (last < 0) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        if (lane == 0) release_acc(acc);
       }
       for (int j = cgrp; j < nsub; j += CG) {
         const int id = nt * CH + (j >> 1);
-        const int tap = id / prm.cchunks;
+        const int tap = (int)prm.fd_cchunks.div((uint32_t)id);
         const int c0 = (id - tap * prm.cchunks) * 64 + (j & 1) * 32;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
@@ -258,7 +297,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
         if (j == last) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+          if (lane == 0) release_acc(acc);
         }
         if (c0 >= prm.C) continue;  // warp-uniform (odd C chunk): nothing to store
         if (lane == 0) bulk_wait_read<0>();   // the reduce that last left from this buffer has read it
@@ -280,9 +319,11 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams prm) {
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_relaxed();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -294,12 +335,12 @@ static bool wgrad_tc_supported(const wlseg_conv_params* p) {
   return true;
 }
 
-template <int BN>
+template <int BN, bool kPair = false>
 static int launch_wgrad(WgradParams& prm, cudaStream_t s) {
-  constexpr int kStageBytes = kWgABytes + (BN / 64) * kChunkBytes;
+  constexpr int kStageBytes = kWgABytes + (BN / 64 / (kPair ? 2 : 1)) * kChunkBytes;
   static bool configured = false;
   if (!configured) {
-    WLSEG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemMax));
+    WLSEG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemMax));
     configured = true;
   }
   prm.epi_bufs = kWgEpiWarps;
@@ -308,8 +349,25 @@ static int launch_wgrad(WgradParams& prm, cudaStream_t s) {
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   prm.stages = stages;
   const int smem_bytes = stages * kStageBytes + fixed;
+  if constexpr (kPair) {
+    const int clusters = prm.units < kNumSMs / 2 ? prm.units : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    WLSEG_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, true>, prm));
+    return 0;
+  }
   const int grid = prm.units < kNumSMs ? prm.units : kNumSMs;
-  WLSEG_CUDA(launch_pdl(conv_wgrad_kernel<BN>, dim3(grid), dim3(kWgThreads), smem_bytes, s, prm));
+  WLSEG_CUDA(launch_pdl(conv_wgrad_kernel<BN, false>, dim3(grid), dim3(kWgThreads), smem_bytes, s, prm));
   return 0;
 }
 
@@ -361,20 +419,32 @@ int conv_wgrad_tcgen05(const wlseg_conv_params* p, const void* x, const void* dy
   const int CH = BN / 64;
   prm.m_tiles = (int)ceil_div(p->K, 128);
   prm.n_tiles = (int)ceil_div(prm.chunks_total, CH);
+  // CTA pair: two M tiles per unit; whole 256-channel output pairs and complete N tiles only.  WLSEG_WGRAD_PAIR=0/1
+  const char* pair_e = getenv("WLSEG_WGRAD_PAIR");   // read per call: the parity tests force both forms
+  const int pair_env = pair_e != nullptr ? atoi(pair_e) : -1;
+  const bool use_pair = BN == 256 && (p->K % 256 == 0) && (prm.chunks_total % 4 == 0) && (p->C % 64 == 0) && pair_env != 0;
+  if (use_pair) prm.m_tiles /= 2;
   prm.tiles = prm.m_tiles * prm.n_tiles;
   // pixel splits: about two waves of work units, at least 4 patches per split
-  int splits = (2 * kNumSMs) / prm.tiles;
+  int splits = (2 * (use_pair ? kNumSMs / 2 : kNumSMs)) / prm.tiles;
   const int max_splits = prm.patches / 4 > 0 ? prm.patches / 4 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   prm.patches_per_split = (int)ceil_div(prm.patches, splits);
   prm.splits = (int)ceil_div(prm.patches, prm.patches_per_split);
   prm.units = prm.tiles * prm.splits;
+  prm.fd_tiles = make_fastdiv((uint32_t)prm.tiles);
+  prm.fd_n_tiles = make_fastdiv((uint32_t)prm.n_tiles);
+  prm.fd_cchunks = make_fastdiv((uint32_t)prm.cchunks);
+  prm.fd_S = make_fastdiv((uint32_t)prm.S);
+  prm.fd_patches_w = make_fastdiv((uint32_t)prm.patches_w);
+  prm.fd_patches_h = make_fastdiv((uint32_t)prm.patches_h);
   static const int swap = [] {
     const char* e = getenv("WLSEG_WGRAD_SWAP_OFFSETS");
     return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
   prm.swap_offsets = swap;
+  if (use_pair) return launch_wgrad<256, true>(prm, s);
   switch (BN) {
     case 64: return launch_wgrad<64>(prm, s);
     case 128: return launch_wgrad<128>(prm, s);

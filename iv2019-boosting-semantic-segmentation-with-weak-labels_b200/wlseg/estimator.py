@@ -48,7 +48,10 @@ def learning_rate(params, global_step):
 
 
 def mean_iou_from_cm(cm, num_classes):
-  """code/estimator/define_metrics.py:13-20 on an int confusion matrix (training summary)."""
+  """code/estimator/define_metrics.py:13-20 on an int confusion matrix (training summary); accepts the device
+  tensor the histogram kernel accumulates into."""
+  if isinstance(cm, torch.Tensor):
+    cm = cm.detach().cpu().numpy()
   cm = np.asarray(cm).astype(np.int32)
   inter = np.diagonal(cm).astype(np.float32)
   union = (cm.sum(0) + cm.sum(1) - np.diagonal(cm)).astype(np.float32) + np.float32(1e-9)

@@ -13,6 +13,7 @@ Data layout in HBM
 """
 
 import math
+import os
 
 import torch
 
@@ -341,7 +342,7 @@ class Network:
     return pt, pl, P, Q
 
   def _conv(self, x, w, *, stride=1, dilation=1, pad=(0, 0), out_hw, scale=None, shift=None, relu=False,
-            residual=None, res_stride=1, y=None, y_dtype=None, bn_sum=None, bn_sqsum=None):
+            residual=None, res_stride=1, y=None, y_dtype=None, bn_sum=None, bn_sqsum=None, out_mask=None):
     N, H, W, C = x.shape
     K = w.shape[0]
     reverse = False
@@ -370,6 +371,9 @@ class Network:
       # direct kernel: statistics from the stored output instead of the accumulators
       ops.conv2d_fprop(prm, x, w, y, scale, shift, residual)
       ops.bn_stats(y, N * out_hw[0] * out_hw[1], K, y.stride(2), bn_sum, bn_sqsum)
+    elif out_mask is not None:
+      assert scale is None and bn_sum is None and not relu
+      ops.conv2d_fprop_masked(prm, x, w, y, residual, out_mask)
     else:
       ops.conv2d_fprop(prm, x, w, y, scale, shift, residual, bn_sum, bn_sqsum)
     if rec is not None:
@@ -611,7 +615,7 @@ class EvalStep:
 # ================================================================================================
 class _Rec:
   """Tape entry of one conv + BN (+ residual) (+ ReLU) layer."""
-  __slots__ = ('scope', 'spec', 'x', 'w', 'z', 'a', 'relu', 'has_res', 'geom', 'nch', 'kind', 'gn',
+  __slots__ = ('scope', 'spec', 'x', 'w', 'z', 'a', 'relu', 'has_res', 'geom', 'nch', 'kind', 'gn', 'mask',
                'res', 'da', 'dz', 'dx', 'dx_add')  # the last five only when TrainNetwork.keep (tests)
 
 
@@ -670,6 +674,11 @@ class TrainNetwork(Network):
     # next to the (bandwidth) BN backward kernels of the layers below.  None = everything on one stream.
     self.wgrad_stream = None
     self._side_keep = []
+    # ReLU bit masks of the bottleneck outputs (1 bit per element, written by their bn_apply): the dgrad that
+    # completes the gradient of such a tensor multiplies it by the mask in its epilogue, so the unit's BN backward
+    # neither reads the activation nor writes a separate shortcut gradient (it IS the masked tensor): 3 of the 8
+    # tensor passes of every residual layer's BN backward.  WLSEG_RELU_MASK=0 restores the unmasked wiring.
+    self.premask = os.environ.get('WLSEG_RELU_MASK', '1') != '0'
 
   def _mark_done(self, scope, n_elems):
     """Bookkeeping for the gradient exchange: backward completes the arena roughly tail first."""
@@ -690,7 +699,7 @@ class TrainNetwork(Network):
 
   # ---- one layer ---------------------------------------------------------------------------------
   def _layer_fwd(self, x, scope, *, w=None, nch=None, relu=None, residual=None, pad=None, stride=None,
-                 dilation=None, out_hw=None, y_f32=False, kind='conv'):
+                 dilation=None, out_hw=None, y_f32=False, kind='conv', want_mask=False):
     spec = self.p.by_scope[scope]
     if w is None:
       w = self._weights(scope)
@@ -711,6 +720,7 @@ class TrainNetwork(Network):
     a = torch.empty_like(z)
     do_relu = spec.relu if relu is None else relu
     gn = None
+    mask = None
     if group:
       gn = self._gn_forward(z, scope, K, do_relu, residual, a)
     elif self.cross_replica is not None:
@@ -728,11 +738,14 @@ class TrainNetwork(Network):
     else:
       ops.bn_finalize(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
                       self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd)
-      ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu)
+      if want_mask and do_relu and K % 32 == 0 and K <= 2048 and z.is_contiguous():
+        mask = torch.empty((count, K // 8), dtype=torch.uint8, device=self.dev)
+      ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu, mask=mask)
     rec = _Rec()
     rec.scope, rec.spec, rec.x, rec.w, rec.z, rec.a = scope, spec, x, w, z, a
     rec.relu, rec.has_res, rec.geom, rec.nch, rec.kind = do_relu, residual is not None, (pad, out_hw, stride, dilation), K, kind
     rec.gn = gn
+    rec.mask = mask
     rec.res = residual if self.keep else None
     self.tape[scope] = rec
     return a
@@ -793,10 +806,13 @@ class TrainNetwork(Network):
       n *= d
     return self.ws.grads[o:o + n].view(*shape)
 
-  def _layer_bwd(self, scope, da, need_dx=True, dx_out=None, dx_add=None):
+  def _layer_bwd(self, scope, da, need_dx=True, dx_out=None, dx_add=None, da_masked=False, dx_mask=None):
     """Backward of one tape entry.  Returns (dx, dres): dres is the gradient of the residual input
     (None if the layer had none).  `dx_add` is accumulated into dx (fused into the tensor-core
-    dgrad epilogue when possible); `dx_out` lets the caller place dx (channel-sliced views)."""
+    dgrad epilogue when possible); `dx_out` lets the caller place dx (channel-sliced views).
+    da_masked: `da` already carries this layer's ReLU derivative (its producer applied rec.mask): the BN backward
+    reads da and z only and dres is da itself.  dx_mask: ReLU bit mask of the tensor dx belongs to, applied by
+    the dgrad epilogue (dx + dx_add is that tensor's COMPLETE gradient)."""
     rec = self.tape[scope]
     ws, off, K = self.ws, self.p.c_off[scope], rec.nch
     pad, out_hw, stride, dilation = rec.geom
@@ -807,12 +823,18 @@ class TrainNetwork(Network):
     scale, shift = ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K)
     gamma = self.p.gamma(scope, K)
     if self.p.norm == 'group':
+      assert not da_masked and dx_mask is None
       dz, dres = self._gn_backward(rec, da, scope, K, dgamma, dbeta)
       return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add)
     dz = torch.empty_like(rec.z)
-    dres = torch.empty_like(rec.z) if rec.has_res else None
+    relu = rec.relu
+    if da_masked:
+      assert rec.has_res and rec.relu and da.is_contiguous()
+      dres, relu = da, False          # g = da: nothing left to mask, and it is the shortcut's gradient as it stands
+    else:
+      dres = torch.empty_like(rec.z) if rec.has_res else None
     # the ReLU mask of a layer without a residual input is recomputed from z (y is not read at all)
-    y = rec.a if (rec.relu and (rec.has_res or K % 8 != 0)) else None
+    y = rec.a if (relu and (rec.has_res or K % 8 != 0)) else None
     # channel slices sized so that one slice of dy / y / z stays L2 resident between the two passes
     esz = rec.z.element_size()
     Kg = K
@@ -824,22 +846,22 @@ class TrainNetwork(Network):
       # the dz formula needs the sums over ALL replicas' pixels (the all-reduce of the forward moments is its
       # own transpose); the parameter gradients stay the local sums and are averaged with the other gradients
       R = self.cross_replica[0]
-      ops.bn_bwd_reduce(da, y, rec.z, mean, invstd, count, K, rec.relu, dgamma, dbeta, scale=scale, shift=shift, pitch=K)
+      ops.bn_bwd_reduce(da, y, rec.z, mean, invstd, count, K, relu, dgamma, dbeta, scale=scale, shift=shift, pitch=K)
       both = self._all_reduce_pair(dgamma, dbeta)
-      ops.bn_bwd_apply(da, y, rec.z, mean, invstd, gamma, both[:K], both[K:], count, K, rec.relu, dz, dres,
-                       scale=scale, shift=shift, pitch=K, stat_count=count * R)
+      ops.bn_bwd_apply(da, y, rec.z, mean, invstd, gamma, both[:K], both[K:], count, K, relu, dz,
+                       None if da_masked else dres, scale=scale, shift=shift, pitch=K, stat_count=count * R)
       Kg = 0
     for c0 in (range(0, K, Kg) if Kg else ()):
       kk = min(Kg, K - c0)
       sl = slice(c0, c0 + kk)
       ops.bn_bwd_reduce(da[..., sl], None if y is None else y[..., sl], rec.z[..., sl], mean[sl], invstd[sl], count, kk,
-                        rec.relu, dgamma[sl], dbeta[sl], scale=scale[sl], shift=shift[sl], pitch=K)
+                        relu, dgamma[sl], dbeta[sl], scale=scale[sl], shift=shift[sl], pitch=K)
       ops.bn_bwd_apply(da[..., sl], None if y is None else y[..., sl], rec.z[..., sl], mean[sl], invstd[sl], gamma[sl],
-                       dgamma[sl], dbeta[sl], count, kk, rec.relu, dz[..., sl], None if dres is None else dres[..., sl],
-                       scale=scale[sl], shift=shift[sl], pitch=K)
-    return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add)
+                       dgamma[sl], dbeta[sl], count, kk, relu, dz[..., sl],
+                       None if (dres is None or da_masked) else dres[..., sl], scale=scale[sl], shift=shift[sl], pitch=K)
+    return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add, dx_mask)
 
-  def _layer_bwd_convs(self, rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add):
+  def _layer_bwd_convs(self, rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add, dx_mask=None):
     """Second half of _layer_bwd: filter gradient and data gradient from dz (normaliser independent)."""
     pad, out_hw, stride, dilation = rec.geom
     N, H, W, C = rec.x.shape
@@ -906,9 +928,10 @@ class TrainNetwork(Network):
       else:
         dzu = dz
       fpad = (dilation * (R - 1) - pad[0], dilation * (S - 1) - pad[1])
-      self._conv(dzu, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx)
+      self._conv(dzu, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx, out_mask=dx_mask)
       done = True
     if not done:
+      assert dx_mask is None, 'the masked data gradient exists on the tensor-core path only'
       prm = ops.conv_params((N, H, W, C), tuple(rec.w.shape), stride=stride, dilation=dilation, pad=pad,
                             out_hw=out_hw, x_pitch=dx.stride(2), y_pitch=dz.stride(2), dtype=self.code)
       ops.conv2d_dgrad(prm, dz, rec.w, dx)
@@ -973,21 +996,28 @@ class TrainNetwork(Network):
     r = self._layer_fwd(x, f'{u.scope}/conv1')
     r = self._layer_fwd(r, f'{u.scope}/conv2')
     self.tape[u.scope] = x
-    return self._layer_fwd(r, f'{u.scope}/conv3', relu=True, residual=sc)
+    return self._layer_fwd(r, f'{u.scope}/conv3', relu=True, residual=sc, want_mask=self._use_premask())
 
-  def _unit_bwd(self, dout, u):
+  def _use_premask(self):
+    return (self.premask and not self.keep and self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT and
+            self.p.norm == 'batch' and not self.fused_bn_finalize)
+
+  def _unit_bwd(self, dout, u, dout_masked=False, in_mask=None):
+    """dout: gradient of the unit's output (already multiplied by its ReLU derivative if dout_masked);
+    in_mask: ReLU bit mask of the unit's INPUT tensor (the previous unit's output) - the dgrad that completes dx
+    applies it.  -> dx"""
     x = self.tape[u.scope]
-    dr, dsc = self._layer_bwd(f'{u.scope}/conv3', dout)
+    dr, dsc = self._layer_bwd(f'{u.scope}/conv3', dout, da_masked=dout_masked)
     dr, _ = self._layer_bwd(f'{u.scope}/conv2', dr)
     if u.has_shortcut_conv:
       dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr)
-      dx, _ = self._layer_bwd(f'{u.scope}/shortcut', dsc, dx_add=dx)
+      dx, _ = self._layer_bwd(f'{u.scope}/shortcut', dsc, dx_add=dx, dx_mask=in_mask)
     elif u.stride > 1:
       dsub = torch.empty_like(x)
       ops.maxpool_same_bwd(x, dsc, dsub, 1, u.stride)
-      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsub)
+      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsub, dx_mask=in_mask)
     else:
-      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsc)
+      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsc, dx_mask=in_mask)
     return dx
 
   # ---- whole network -----------------------------------------------------------------------------------
@@ -1085,9 +1115,12 @@ class TrainNetwork(Network):
       dx = self._psp_bwd(dx)
     if self.p.fov:
       dx, _ = self._layer_bwd(arch.FOV_SCOPE, dx)
-    dx, _ = self._layer_bwd('feature_extractor/extension/decrease_fdims', dx)
-    for u in reversed(arch.units()):
-      dx = self._unit_bwd(dx, u)
+    units = list(arch.units())
+    use = self._use_premask()   # (a test flips self.premask between two backward passes over one tape)
+    masks = [getattr(self.tape.get(f'{u.scope}/conv3'), 'mask', None) if use else None for u in units]   # of each unit's OUTPUT
+    dx, _ = self._layer_bwd('feature_extractor/extension/decrease_fdims', dx, dx_mask=masks[-1])
+    for i in range(len(units) - 1, -1, -1):
+      dx = self._unit_bwd(dx, units[i], dout_masked=masks[i] is not None, in_mask=masks[i - 1] if i > 0 else None)
     self._root_bwd(dx)
     if self.wgrad_stream is not None:
       torch.cuda.current_stream().wait_stream(self.wgrad_stream)   # join: every filter gradient is in the arena

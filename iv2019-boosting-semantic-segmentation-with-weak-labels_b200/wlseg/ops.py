@@ -55,6 +55,8 @@ _SIGNATURES = {
     'wlseg_bn_finalize_apply': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
                                                _vp, _vp, _vp, _vp, _c_int, _c_int, _vp]),
     'wlseg_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp]),
+    'wlseg_bn_apply_mask': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _vp]),
+    'wlseg_conv2d_fprop_masked': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp, _vp, _vp]),
     'wlseg_bn_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _c_int,
                                            _vp, _vp, _vp]),
     'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, _c_int,
@@ -185,6 +187,13 @@ def conv2d_fprop(p, x, w, y, scale=None, shift=None, residual=None, bn_sum=None,
   return y
 
 
+def conv2d_fprop_masked(p, x, w, y, residual, out_mask):
+  """y = (conv(x, w) + residual) * mask: a data gradient leaving through the ReLU of the tensor it belongs to."""
+  _count()
+  _check(lib().wlseg_conv2d_fprop_masked(ctypes.byref(p), _ptr(x), _ptr(w), _ptr(y), _ptr(residual), _ptr(out_mask),
+                                         _stream()), 'wlseg_conv2d_fprop_masked')
+
+
 def conv2d_dgrad(p, dy, w, dx):
   _check(lib().wlseg_conv2d_dgrad(ctypes.byref(p), _ptr(dy), _ptr(w), _ptr(dx), _stream()), 'wlseg_conv2d_dgrad')
   _count()
@@ -275,7 +284,14 @@ def bn_finalize_apply(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mea
   return y
 
 
-def bn_apply(z, scale, shift, residual, y, count, C, relu):
+def bn_apply(z, scale, shift, residual, y, count, C, relu, mask=None):
+  """mask: uint8 [count, C / 8], receives the ReLU bit mask (y > 0) - see conv2d_fprop_masked."""
+  if mask is not None:
+    assert relu and mask.dtype == torch.uint8 and mask.numel() == count * (C // 8)
+    _count()
+    _check(lib().wlseg_bn_apply_mask(_ptr(z), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(y), _ptr(mask), count, C,
+                                     dtype_code(z.dtype), _stream()), 'wlseg_bn_apply_mask')
+    return
   _check(lib().wlseg_bn_apply(_ptr(z), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(y), count, C, int(relu),
                               dtype_code(z.dtype), _stream()), 'wlseg_bn_apply')
   _count()

@@ -69,14 +69,61 @@ def test_eval_forward_full_size_matches_oracle(cuda, dataset, H, W):
   assert float((hd != ref['decisions']).float().mean()) <= 1e-4
 
 
+def _conditioned_params(dataset, seed, res_gamma=0.2):
+  """Random init with the residual-branch gammas scaled down.  A train-mode BN ResNet at plain random init is a
+  chaotic map: perturbations grow ~1.08x per layer (x300 end to end - the oracle with bf16 storage roundings and the
+  fp32 oracle decorrelate to 0.8 rel-L2 on the logits, profiles/r2_train_parity_probe.txt), so NO bf16 implementation
+  can be compared with an fp32 one there.  Small residual gammas give the conditioning of a trained network."""
+  tf_params = onet.init_params(dataset, seed=seed, randomize_bn=True, tame=True)
+  for k in tf_params:
+    if k.endswith('conv3/BatchNorm/gamma') and 'bottleneck' in k:
+      tf_params[k] = tf_params[k] * res_gamma
+  return tf_params
+
+
+def _oracle_train_step(tf_params, dataset, images, labels, storage):
+  p = {k: v.clone().requires_grad_(not k.endswith(('moving_mean', 'moving_variance'))) for k, v in tf_params.items()}
+  pred = onet.Net(p, dataset, training=True, storage=storage).forward(images)
+  rl = olosses.define_losses(pred, labels, dataset)
+  rl['total'].backward()
+  low = torch.cat(pred['lowres_logits'], -1).detach()
+  want = torch.stack([rl['l1_segmentation'], rl['l2_vehicle_segmentation'], rl['l2_human_segmentation'],
+                      rl['segmentation']]).detach()
+  return low, want, {k: v.grad for k, v in p.items() if v.requires_grad}
+
+
+def _grad_cosines(params, grads, ref):
+  got_all, ref_all, worst = [], [], (1.0, None)
+  for s in params.specs:
+    r = ref[f'{s.scope}/weights'].permute(3, 0, 1, 2).reshape(-1)
+    o = params.w_off[s.scope]
+    gt = grads[o:o + r.numel()]
+    got_all.append(gt)
+    ref_all.append(r)
+    if r.numel() >= 4096:
+      c = float(torch.dot(gt.double(), r.double()) / (gt.double().norm() * r.double().norm()))
+      if c < worst[0]:
+        worst = (c, s.scope)
+  ga, ra = torch.cat(got_all).double(), torch.cat(ref_all).double()
+  return float(torch.dot(ga, ra) / (ga.norm() * ra.norm())), worst
+
+
 def test_train_step_4x768_matches_oracle(cuda):
-  """BASELINE configs[2]: one 4 x 768 x 768 strong-label training step of the bf16 product path (tcgen05
-  convolutions, batch-statistic BN, fused loss, backward) against the fp32 oracle's autograd: logits and the three
-  losses within 2e-2; the gradient is compared by cosine (per large tensor and over the whole arena).  36 864
-  samples per channel make the batch statistics far better conditioned than at the toy sizes of test_gpu_train.py."""
+  """BASELINE configs[2]: one 4 x 768 x 768 strong-label training step of the bf16 PRODUCT path (tcgen05
+  convolutions incl. the CTA-pair forms, fused batch statistics, masked residual gradients, fused loss, backward)
+  end to end against the oracle's autograd - (a) the fp32 oracle and (b) the oracle with the product's storage
+  roundings made explicit (oracle/network.py storage='bf16').  Measured on B200 (tools/train_parity_probe.py,
+  profiles/r2_train_parity_probe.txt): losses 3e-5..1.2e-4; logits rel-L2 6.1e-2 vs (a), 3.7e-2 vs (b) - and (b) vs (a)
+  is itself 6.0e-2, i.e. the product is as close to the fp32 oracle as a bf16-storage implementation can be; gradient
+  cosine 0.919 global / 0.894 worst tensor vs (a), 0.957 / 0.946 vs (b).  The asserts bound each figure at about
+  1.5x the measured gap, and tie the product's distance to (a) to the oracle's own (b)-vs-(a) distance."""
   from wlseg import network
   dataset, N, H, W = 'cityscapes', 4, 768, 768
-  hier, tf_params, params = _setup(cuda, dataset, seed=31)
+  from wlseg import hierarchy, problem_defs
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  tf_params = _conditioned_params(dataset, seed=31)
+  params = network.Params(hier, cuda)
+  params.load_tf_dict(tf_params)
   net = network.TrainNetwork(params, dtype=torch.bfloat16)
   g = torch.Generator().manual_seed(77)
   images = torch.rand(N, H, W, 3, generator=g) * 2 - 1
@@ -92,42 +139,35 @@ def test_train_step_4x768_matches_oracle(cuda):
   del net, logits, dlogits
   torch.cuda.empty_cache()
 
-  p = {k: v.clone().requires_grad_(not k.endswith(('moving_mean', 'moving_variance'))) for k, v in tf_params.items()}
-  onet_ = onet.Net(p, dataset, training=True)
-  pred = onet_.forward(images)
-  rl = olosses.define_losses(pred, labels, dataset)
-  rl['total'].backward()
-  ref_low = torch.cat(pred['lowres_logits'], -1).detach()
-  emax, el2 = _errors(got_low, ref_low)
-  want = torch.stack([rl['l1_segmentation'], rl['l2_vehicle_segmentation'], rl['l2_human_segmentation'],
-                      rl['segmentation']]).detach()
-  lerr = ((got_losses - want).abs() / want.abs()).max()
-  got_all, ref_all, worst = [], [], (1.0, None)
-  for s in params.specs:
-    r = p[f'{s.scope}/weights'].grad.permute(3, 0, 1, 2).reshape(-1)
-    o = params.w_off[s.scope]
-    gt = grads[o:o + r.numel()]
-    got_all.append(gt)
-    ref_all.append(r)
-    if r.numel() >= 4096:
-      c = float(torch.dot(gt.double(), r.double()) / (gt.double().norm() * r.double().norm()))
-      if c < worst[0]:
-        worst = (c, s.scope)
-  ga, ra = torch.cat(got_all).double(), torch.cat(ref_all).double()
-  gcos = float(torch.dot(ga, ra) / (ga.norm() * ra.norm()))
-  print(f'4x768x768 train step: logits max-rel {emax:.3e} rel-L2 {el2:.3e}; losses {got_losses.tolist()} vs '
-        f'{want.tolist()} (max rel err {float(lerr):.3e}); gradient global cosine {gcos:.5f}, worst per-tensor '
-        f'{worst[0]:.5f} ({worst[1]})')
-  assert float(lerr) <= 2e-2
-  assert el2 <= TRAIN_LOGITS_REL_L2
-  assert gcos >= TRAIN_GRAD_COS_GLOBAL and worst[0] >= TRAIN_GRAD_COS_WORST
+  low32, want32, g32 = _oracle_train_step(tf_params, dataset, images, labels, 'fp32')
+  low16, want16, g16 = _oracle_train_step(tf_params, dataset, images, labels, 'bf16')
+  e32 = _errors(got_low, low32)[1]
+  e16 = _errors(got_low, low16)[1]
+  e_or = _errors(low16, low32)[1]
+  lerr32 = float(((got_losses - want32).abs() / want32.abs()).max())
+  lerr16 = float(((got_losses - want16).abs() / want16.abs()).max())
+  cos32, worst32 = _grad_cosines(params, grads, g32)
+  cos16, worst16 = _grad_cosines(params, grads, g16)
+  ga = torch.cat([g16[f'{s.scope}/weights'].reshape(-1) for s in params.specs]).double()
+  gb = torch.cat([g32[f'{s.scope}/weights'].reshape(-1) for s in params.specs]).double()
+  cos_or = float(torch.dot(ga, gb) / (ga.norm() * gb.norm()))
+  print(f'4x768x768 train step: losses {got_losses.tolist()} vs fp32 oracle {want32.tolist()} (max rel {lerr32:.2e}; vs '
+        f'bf16-storage oracle {lerr16:.2e}); logits rel-L2 {e32:.3e} vs fp32 oracle, {e16:.3e} vs bf16-storage oracle '
+        f'(oracle bf16-storage vs oracle fp32: {e_or:.3e}); gradient cosine global {cos32:.4f} / worst {worst32[0]:.4f} '
+        f'({worst32[1]}) vs fp32 oracle, {cos16:.4f} / {worst16[0]:.4f} vs bf16-storage oracle (oracle vs oracle {cos_or:.4f})')
+  assert lerr32 <= 2e-3 and lerr16 <= 2e-3            # north star: loss within 2e-2 in bf16
+  assert e16 <= TRAIN_LOGITS_REL_L2_VS_BF16_ORACLE
+  assert e32 <= 1.5 * e_or + 1e-3                     # no further from fp32 than the storage roundings explain
+  assert cos32 >= TRAIN_GRAD_COS_GLOBAL and worst32[0] >= TRAIN_GRAD_COS_WORST
+  assert cos16 >= TRAIN_GRAD_COS_GLOBAL_VS_BF16_ORACLE
+  assert cos32 >= cos_or - 0.05
 
 
-# Measured on B200 (tools/train_parity_probe.py 4x768x768, profiles/r2_train_parity_probe.txt); the bounds are
-# ~2x the measured gap so that a regression shows.
-TRAIN_LOGITS_REL_L2 = 5e-2
-TRAIN_GRAD_COS_GLOBAL = 0.95
-TRAIN_GRAD_COS_WORST = 0.80
+# ~1.5x the gaps measured on B200 (profiles/r2_train_parity_probe.txt, RES_GAMMA=0.2 rows)
+TRAIN_LOGITS_REL_L2_VS_BF16_ORACLE = 6e-2
+TRAIN_GRAD_COS_GLOBAL = 0.88
+TRAIN_GRAD_COS_WORST = 0.84
+TRAIN_GRAD_COS_GLOBAL_VS_BF16_ORACLE = 0.93
 
 
 def test_confmat_full_size_vs_oracle(cuda):

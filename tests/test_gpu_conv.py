@@ -100,6 +100,55 @@ def test_conv_tcgen05_bf16(cuda, case):
   assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
 
 
+PAIR_CASES = [
+    # N, H, W, C, K, R, stride, dilation -- every one a 256-wide N tile with the staged epilogue
+    (1, 16, 16, 128, 256, 1, 1, 1),    # one pair of M tiles, 2 k-blocks, residual
+    (3, 8, 16, 512, 2048, 1, 1, 1),    # ODD M-tile count: the last pair's second CTA works on a phantom tile
+    (2, 16, 24, 256, 512, 3, 1, 2),    # dilated 3x3, two N tiles
+    (1, 13, 19, 256, 256, 3, 1, 1),    # ragged spatial size (clipped stores, zero-filled loads)
+    (1, 40, 40, 1024, 768, 1, 1, 1),   # three N tiles, 13 M tiles
+]
+
+
+@pytest.mark.parametrize('pair', ['0', '1'])
+@pytest.mark.parametrize('case', PAIR_CASES)
+def test_conv_tcgen05_cta_pair_forced(cuda, case, pair, monkeypatch):
+  """The CTA-pair (cta_group::2) form and the single-CTA form of the same layers, each forced through WLSEG_PAIR,
+  against the oracle convolution (with folded BN, residual and ReLU): one bf16 output rounding."""
+  from wlseg import ops
+  monkeypatch.setenv('WLSEG_PAIR', pair)
+  got, ref = _run_conv(cuda, *case, dtype=torch.bfloat16, algo=ops.ALGO_TCGEN05, seed=sum(case))
+  assert not torch.isnan(got).any(), 'some outputs were never written'
+  assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+  got, ref = _run_conv(cuda, *case, dtype=torch.bfloat16, algo=ops.ALGO_TCGEN05, seed=sum(case), with_epi=False, relu=False)
+  assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('pair', ['0', '1'])
+def test_conv_tcgen05_fused_bn_statistics_cta_pair(cuda, pair, monkeypatch):
+  """Fused sum / sum-of-squares in the pair form: K = 512 (two N tiles: the cluster count is a multiple of 2), an odd
+  number of M tiles (the phantom tile must not reach the statistics) and a ragged image."""
+  from wlseg import arch, ops
+  monkeypatch.setenv('WLSEG_PAIR', pair)
+  g = torch.Generator().manual_seed(9)
+  N, H, W, C, K = 3, 13, 17, 128, 512
+  x = torch.randn(N, H, W, C, generator=g).to(torch.bfloat16)
+  w = (torch.randn(K, 3, 3, C, generator=g) / 34).to(torch.bfloat16)
+  pt, P = arch.same_pad_before(3, 1, 1, H)
+  y = torch.full((N, H, W, K), float('nan'), dtype=torch.bfloat16, device=cuda)
+  s1 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  s2 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  prm = ops.conv_params((N, H, W, C), (K, 3, 3, C), pad=(pt, pt), out_hw=(H, W), dtype=ops.BF16, algo=ops.ALGO_TCGEN05)
+  ops.conv2d_fprop(prm, x.to(cuda), w.to(cuda), y, bn_sum=s1, bn_sqsum=s2)
+  torch.cuda.synchronize()
+  ref = tfops.conv2d_same(x.float(), w.float().permute(1, 2, 3, 0), 1, 1)
+  assert not torch.isnan(y).any()
+  assert float((y.float().cpu() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+  yq = y.float().cpu().double()   # the statistics are those of the STORED bf16 tensor
+  assert torch.allclose(s1.cpu(), yq.sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+  assert torch.allclose(s2.cpu(), (yq ** 2).sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+
+
 def test_conv_tcgen05_plain_and_strided_residual(cuda):
   from wlseg import ops
   got, ref = _run_conv(cuda, 1, 16, 32, 64, 128, 1, 1, 1, dtype=torch.bfloat16, algo=ops.ALGO_TCGEN05,
@@ -193,16 +242,24 @@ WGRAD_TC_CASES = [
     (3, 8, 16, 512, 256, 1, 1, 1),     # deep C: 8 chunks -> 2 N tiles
     (1, 12, 20, 256, 14, 1, 1, 1),     # logits layer: K = 14 (dy pitch padded to 16)
     (1, 1, 200, 64, 64, 1, 1, 1),      # P == 1
+    (2, 16, 24, 256, 512, 1, 1, 1),    # CTA pair: two M pairs, one N tile
+    (1, 24, 24, 512, 512, 3, 1, 4),    # CTA pair: dilated 3x3, 18 N tiles, pixel splits
+    (1, 13, 19, 1024, 256, 1, 1, 1),   # CTA pair: deep C, ragged spatial size
 ]
 
 
+@pytest.mark.parametrize('pair', ['0', '1'])
 @pytest.mark.parametrize('case', WGRAD_TC_CASES)
-def test_conv_wgrad_tcgen05(cuda, case):
+def test_conv_wgrad_tcgen05(cuda, case, pair, monkeypatch):
   """dw on the tensor cores (MN-major operands, TMA reduce-add of the pixel splits) against autograd of
   the oracle convolution on the same bf16-rounded operands: 2e-3 of max|dw| (fp32 accumulation, bf16 inputs
   are exact in both)."""
   from wlseg import arch, ops
   N, H, W, C, K, R, stride, dilation = case
+  eligible = K % 256 == 0 and C % 64 == 0 and (R * R * (C // 64)) % 4 == 0
+  if pair == '0' and not eligible:
+    pytest.skip('the single-CTA form is what the default run of this case covers')
+  monkeypatch.setenv('WLSEG_WGRAD_PAIR', pair)   # '1' = default policy (CTA pair where eligible), '0' = never
   g = torch.Generator().manual_seed(sum(case))
   x = torch.randn(N, H, W, C, generator=g).to(torch.bfloat16).float().requires_grad_(True)
   w = (torch.randn(K, R, R, C, generator=g) / (R * R * C) ** 0.5).requires_grad_(True)

@@ -143,7 +143,9 @@ def test_batch_mean_iou_on_device_equals_the_reference_run(cuda, gold):
   from wlseg import ops
   cm = torch.zeros(20, 20, dtype=torch.int64, device=cuda)
   ops.confmat_accumulate(torch.from_numpy(gold['mean_iou/labels']).to(cuda), torch.from_numpy(gold['mean_iou/decisions']).to(cuda), 20, cm)
-  assert abs(float(west.mean_iou_from_cm(cm, 20)) - float(gold['mean_iou/out'])) <= 1e-6
+  got = west.mean_iou_from_cm(cm, 20)
+  got = float(got.cpu()) if isinstance(got, torch.Tensor) else float(got)
+  assert abs(got - float(gold['mean_iou/out'])) <= 1e-6
 
 
 @pytest.mark.parametrize('name,nesterov', [('plain', False), ('nesterov', True)])

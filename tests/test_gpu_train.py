@@ -15,6 +15,7 @@ Hence:
       relative (north star), gradient cosine >= 0.99 per large tensor and over the whole arena
 """
 
+import numpy as np
 import pytest
 import torch
 
@@ -294,3 +295,42 @@ def test_trainer_graph_replay_equals_eager(cuda):
     err = float((e1 - gr).abs().max()) / scale
     print(f'{name}: eager-vs-eager {noise:.2e}, graph-vs-eager {err:.2e}')
     assert err <= max(4.0 * noise, 1e-5), f'{name}: graph replay differs from eager by {err:.2e} (run-to-run noise {noise:.2e})'
+
+
+def test_premasked_residual_gradient_equals_unmasked_wiring(cuda):
+  """The ReLU bit masks of the bottleneck outputs (wlseg_bn_apply_mask -> wlseg_conv2d_fprop_masked: the dgrad
+  epilogue multiplies the finished gradient by the ReLU derivative, the BN backward skips the activation read and
+  the shortcut-gradient write) against the unmasked wiring, as two backward passes over ONE forward tape: bf16
+  rounding and masking commute, so every tensor is bit-identical up to the commit order of the fp64 / split-K
+  atomics - the yardstick is a third pass with the unmasked wiring again."""
+  from wlseg import hierarchy, network, problem_defs
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  tf_params = onet.init_params('cityscapes', seed=13, randomize_bn=True, tame=True)
+  g = torch.Generator().manual_seed(21)
+  images = (torch.rand(2, 96, 128, 3, generator=g) * 2 - 1).to(cuda)
+  labels = {k: v.to(cuda) for k, v in _labels('cityscapes', 2, 0, 0, 96, 128, 20).items()}
+  params = network.Params(hier, cuda)
+  params.load_tf_dict(tf_params)
+  net = network.TrainNetwork(params, dtype=torch.bfloat16)
+  assert net.premask
+  logits = net.forward_train(images)
+  assert sum(1 for r in net.tape.values() if getattr(r, 'mask', None) is not None) == 16   # ResNet-50's bottleneck outputs
+  # the masks are the sign bits of the stored activations
+  rec = net.tape['feature_extractor/base/resnet_v1_50/block2/unit_2/bottleneck_v1/conv3']
+  bits = torch.from_numpy(np.unpackbits(rec.mask.cpu().numpy(), axis=1, bitorder='little')).bool()
+  assert torch.equal(bits, (rec.a.float().cpu() > 0).reshape(bits.shape))
+  losses, dlogits = net.loss_and_grad(logits, labels, 96, 128)
+  n = params.n_chan_pad
+  runs = []
+  for flag in (True, False, False):
+    net.premask = flag
+    net.ws.stat[2 * n:].zero_()          # dgamma / dbeta accumulators (forward_train zeroes them once per step)
+    runs.append(net.backward(dlogits).cpu().clone())
+  torch.cuda.synchronize()
+  g1, g0, g0b = runs
+  scale = float(g0.abs().max())
+  noise = float((g0 - g0b).abs().max()) / scale
+  err = float((g1 - g0).abs().max()) / scale
+  cos = float(torch.dot(g1.double(), g0.double()) / (g1.double().norm() * g0.double().norm()))
+  print(f'masked vs unmasked gradient arena: max-rel {err:.2e} (unmasked run-to-run {noise:.2e}), cosine {cos:.10f}')
+  assert err <= max(4.0 * noise, 1e-5) and cos >= 0.9999999

@@ -50,6 +50,10 @@ def run(kind, rows, C):
   if kind == 'apply_res':
     sets = bufs(rows, C, 3)
     return timed(lambda b: ops.bn_apply(b[0], scale, shift, b[2], b[1], rows, C, True), sets), 6
+  if kind == 'apply_res_mask':
+    sets = bufs(rows, C, 3)
+    mask = torch.empty(rows, C // 8, dtype=torch.uint8, device=dev)
+    return timed(lambda b: ops.bn_apply(b[0], scale, shift, b[2], b[1], rows, C, True, mask=mask), sets), 6
   if kind == 'bwd':
     sets = bufs(rows, C, 3)
     return timed(lambda b: ops.bn_bwd_apply(b[0], None, b[1], mean, invstd, gamma, dg, db, rows, C, True, b[2], None,
@@ -78,6 +82,12 @@ def sweep(kind, configs):
 
 KNOBS = ('WLSEG_BN_FLAT', 'WLSEG_BN_APPLY_U', 'WLSEG_BN_APPLY_CTAS', 'WLSEG_BN_BWD_U', 'WLSEG_BN_BWD_CTAS',
          'WLSEG_BN_RED_CTAS', 'WLSEG_BN_RED_SPAN')
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'mask':
+  SHAPES = [(147456, 256, 2), (36864, 256, 4), (36864, 512, 4), (36864, 1024, 6), (36864, 2048, 3)]
+  sweep('apply_res', [('rows U=2 ctas=4', {})])
+  sweep('apply_res_mask', [('rows U=2 ctas=4', {})])
+  sys.exit(0)
 
 if __name__ == '__main__':
   sweep('reduce', [(f'span={sp} ctas={c}', {'WLSEG_BN_RED_SPAN': str(sp), 'WLSEG_BN_RED_CTAS': str(c)})
