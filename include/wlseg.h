@@ -119,13 +119,14 @@ int wlseg_bn_finalize(const double* sum, const double* sqsum, int64_t count, int
                       float moving_var_factor, float* moving_mean, float* moving_var, float* scale,
                       float* shift, float* saved_mean, float* saved_invstd, wlseg_stream_t stream);
 
-/* wlseg_bn_finalize + wlseg_bn_apply in one launch (C % 8 == 0, C <= 2048): every CTA derives
- * scale / shift from the sums; CTA 0 publishes them (+ saved mean / invstd, moving statistics). */
+/* wlseg_bn_finalize + wlseg_bn_apply in one launch (C % 8 == 0, C <= 2048): every thread derives scale / shift of
+ * its 8 channels from the sums; CTA 0 publishes them (+ saved mean / invstd, moving statistics).  relu_mask (may be
+ * NULL): as wlseg_bn_apply_mask. */
 int wlseg_bn_finalize_apply(const double* sum, const double* sqsum, int64_t count, int32_t C,
                             const float* gamma, const float* beta, float eps, float decay,
                             float* moving_mean, float* moving_var, float* scale, float* shift,
                             float* saved_mean, float* saved_invstd, const void* z, const void* residual,
-                            void* y, int32_t relu, int32_t dtype, wlseg_stream_t stream);
+                            void* y, uint8_t* relu_mask, int32_t relu, int32_t dtype, wlseg_stream_t stream);
 
 /* y = relu?( z*scale[c] + shift[c] + residual ), elementwise over count x C. */
 int wlseg_bn_apply(const void* z, const float* scale, const float* shift, const void* residual,
@@ -279,6 +280,19 @@ int wlseg_replace_voids(const wlseg_hierarchy* hier, const float* l1_probs, cons
                         const float* l2h_probs, int32_t* decisions, int64_t n_pixels, int32_t void_cid,
                         wlseg_stream_t stream);
 
+/* wlseg_loss_fwd_bwd with the weak labels in their COMPACT form: the bbox images carry
+ * (class, box) lists - coords float32 [n_bbox, max_boxes, 4] = (xmin, xmax, ymin, ymax) normalised, cids int32
+ * [n_bbox, max_boxes], anything outside [0, 14] = padding - and the image-level images one 15-way vector each
+ * (float32 [n_image, 15]).  The kernel evaluates `_generate_rla` (input_subset_bboxes_v2.py:74-98) and the
+ * image-level tiling (input_subset_image_labels.py:73-107) per pixel in registers instead of reading 60 B per
+ * pixel of dense labels; results are identical to rasterising first.  14/7/3 hierarchy at >= 2x upsampling
+ * (the column-walking kernel); other configurations return an error: rasterise and call wlseg_loss_fwd_bwd. */
+int wlseg_loss_fwd_bwd_lists(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch,
+                             int32_t n_strong, int32_t n_bbox, int32_t n_image, int32_t h, int32_t w,
+                             int32_t H, int32_t W, const int32_t* strong_labels, const float* box_coords,
+                             const int32_t* box_cids, int32_t max_boxes, const float* image_vectors,
+                             double* sums, double* counts, float* dlogits, wlseg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Hierarchical strong + weak masked cross-entropy, forward and backward fused with the
  * bilinear upsample and its transpose (replaces estimator/define_losses_hierarchical.py:97-203
@@ -361,6 +375,18 @@ int wlseg_zero_insert(const void* src, void* dst, int32_t N, int32_t P, int32_t 
  * (csrc/transform.cu gives the exact index map). */
 int wlseg_conv1_pack(const void* img, int32_t dtype, int32_t N, int32_t H, int32_t W, void* out,
                      wlseg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input-side resize + random crop, input_pipelines/utils.py:181-247 `resize_images_and_labels`
+ * (over utils/utils.py:540-605): x [N,H,W,C] is resized to RH x RW with tf.image.resize_images,
+ * align_corners=False (kind 0: fp32 BILINEAR for images; 1: fp32 NEAREST_NEIGHBOR for dense weak
+ * labels; 2: int32 NEAREST_NEIGHBOR for class-id labels, C = 1) and the window [oy, oy+TH) x
+ * [ox, ox+TW) of the result is written to y [N,TH,TW,C].  Without --preserve_aspect_ratio
+ * RH x RW = TH x TW and the offsets are 0.
+ * ------------------------------------------------------------------------------------------ */
+int wlseg_resize_crop(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t RH,
+                      int32_t RW, int32_t oy, int32_t ox, int32_t TH, int32_t TW, int32_t kind,
+                      wlseg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'wlseg', 'lib')
 LIB = os.path.join(LIBDIR, 'libwlseg.so')
 SOURCES = ['abi.cu', 'confmat.cu', 'head.cu', 'loss.cu', 'pool.cu', 'bn.cu', 'optim.cu', 'conv_direct.cu',
-           'conv_igemm_sm100.cu', 'conv_wgrad_sm100.cu', 'transform.cu', 'weak_labels.cu', 'psp.cu', 'postproc.cu', 'gn.cu']
+           'conv_igemm_sm100.cu', 'conv_wgrad_sm100.cu', 'transform.cu', 'weak_labels.cu', 'psp.cu', 'postproc.cu', 'gn.cu', 'preproc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC',
               '-Xptxas', '-v']

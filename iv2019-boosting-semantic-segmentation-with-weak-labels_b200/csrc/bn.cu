@@ -354,22 +354,71 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const 
 // is a multiply-add instead of the 64-bit divide + modulo per 16-byte vector of the flat-index kernels
 // above; kRowsU independent rows are in flight per thread.  A warp still touches 512 contiguous bytes
 // (C >= 256) or 32 * 16 contiguous bytes spanning consecutive rows (C < 256, dense rows).
+// bn_finalize folded into the row-mapped apply kernel: a thread derives scale / shift of ITS 8 channels from the fp64
+// sums (same arithmetic as bn_finalize_kernel) instead of reading them; the first row lane of CTA 0 publishes scale /
+// shift / saved mean / inverse std for the backward pass and updates the moving statistics.  One launch less per
+// layer (64 per training step at ~3 us each) without the per-CTA shared-memory staging of bn_finalize_apply_kernel.
+struct BnFin {
+  const double* sum;      // NULL: scale / shift are inputs (plain wlseg_bn_apply)
+  const double* sqsum;
+  const float* gamma;
+  const float* beta;
+  float* moving_mean;
+  float* moving_var;
+  float* scale_out;
+  float* shift_out;
+  float* saved_mean;
+  float* saved_invstd;
+  int64_t count;
+  float eps, decay;
+};
+
 template <typename T, int kRowsU>
 __global__ void __launch_bounds__(256)
 bn_apply_rows_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                      const T* __restrict__ res, T* __restrict__ y, int64_t count, int C, int relu, int rev,
-                     uint8_t* __restrict__ relu_mask) {
+                     uint8_t* __restrict__ relu_mask, const BnFin fin) {
   pdl_launch_dependents();
-  pdl_wait();   // scale / shift were written by bn_finalize, the kernel right before this one
+  pdl_wait();   // scale / shift (or the sums) were written by the kernel right before this one
   const int cv = C / 8;
   const int lanes = 256 / cv;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
   if (ty >= lanes) return;
   const int c0 = tx * 8;
-  const float4 sa = *reinterpret_cast<const float4*>(scale + c0), sb = *reinterpret_cast<const float4*>(scale + c0 + 4);
-  const float4 ha = *reinterpret_cast<const float4*>(shift + c0), hb = *reinterpret_cast<const float4*>(shift + c0 + 4);
-  const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-  const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+  float sc[8], sh[8];
+  if (fin.sum != nullptr) {
+    // same fp64 arithmetic as bn_finalize_kernel, bit for bit (multiplying by 1 / n instead was measured too: the 16
+    // divisions cost ~7 us per launch, but the fused launch loses to two launches even without them)
+    const double n = (double)fin.count;
+    const bool publish = blockIdx.x == 0 && ty == 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const double m = fin.sum[c] / n;
+      double var = fin.sqsum[c] / n - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mf = (float)m, vf = (float)var;
+      const float inv = rsqrtf(vf + fin.eps);
+      sc[j] = fin.gamma[c] * inv;
+      sh[j] = fin.beta[c] - mf * sc[j];
+      if (publish) {
+        fin.scale_out[c] = sc[j];
+        fin.shift_out[c] = sh[j];
+        fin.saved_mean[c] = mf;
+        fin.saved_invstd[c] = inv;
+        if (fin.moving_mean != nullptr) {
+          const float unbiased = fin.count > 1 ? (float)(var * (n / (n - 1.0))) : vf;
+          fin.moving_mean[c] -= (1.0f - fin.decay) * (fin.moving_mean[c] - mf);
+          fin.moving_var[c] -= (1.0f - fin.decay) * (fin.moving_var[c] - unbiased);
+        }
+      }
+    }
+  } else {
+    const float4 sa = *reinterpret_cast<const float4*>(scale + c0), sb = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 ha = *reinterpret_cast<const float4*>(shift + c0), hb = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    sc[0] = sa.x; sc[1] = sa.y; sc[2] = sa.z; sc[3] = sa.w; sc[4] = sb.x; sc[5] = sb.y; sc[6] = sb.z; sc[7] = sb.w;
+    sh[0] = ha.x; sh[1] = ha.y; sh[2] = ha.z; sh[3] = ha.w; sh[4] = hb.x; sh[5] = hb.y; sh[6] = hb.z; sh[7] = hb.w;
+  }
   const int64_t step = (int64_t)gridDim.x * lanes;
   for (int64_t row0 = (int64_t)blockIdx.x * lanes + ty; row0 < count; row0 += step * kRowsU) {
     Vec8<T> v[kRowsU], vr[kRowsU];
@@ -501,7 +550,9 @@ static int bn_bwd_ctas() { return env_int("WLSEG_BN_BWD_CTAS", 2); }
 
 template <typename T>
 static void launch_apply_rows(const void* z, const float* scale, const float* shift, const void* res, void* y, int64_t count,
-                              int C, int relu, cudaStream_t s, uint8_t* mask = nullptr) {
+                              int C, int relu, cudaStream_t s, uint8_t* mask = nullptr, const BnFin* finp = nullptr) {
+  BnFin fin = {};
+  if (finp != nullptr) fin = *finp;
   const int lanes = 256 / (C / 8);
   // measured (tools/bn_sweep.py, graph-timed, HBM-cold): without a residual one row per thread at full occupancy
   // wins (871 vs 902 us per step-equivalent); with a residual stream two rows at 4 CTAs / SM do
@@ -510,9 +561,9 @@ static void launch_apply_rows(const void* z, const float* scale, const float* sh
                         res != nullptr ? bn_apply_ctas() : env_int("WLSEG_BN_APPLY_CTAS_PLAIN", 8));
   const int rev = env_int("WLSEG_BN_APPLY_REV", 1);
   cudaError_t e;
-  if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask);
-  else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask);
-  else e = launch_pdl(bn_apply_rows_kernel<T, 2>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask);
+  if (U == 1) e = launch_pdl(bn_apply_rows_kernel<T, 1>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask, fin);
+  else if (U == 4) e = launch_pdl(bn_apply_rows_kernel<T, 4>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask, fin);
+  else e = launch_pdl(bn_apply_rows_kernel<T, 2>, dim3(g), dim3(256), 0, s, (const T*)z, scale, shift, (const T*)res, (T*)y, count, C, relu, rev, mask, fin);
   (void)e;   // reported by the caller's WLSEG_LAUNCH_CHECK (cudaGetLastError)
 }
 
@@ -673,11 +724,20 @@ extern "C" int wlseg_bn_finalize_apply(const double* sum, const double* sqsum, i
                                        const float* gamma, const float* beta, float eps, float decay,
                                        float* moving_mean, float* moving_var, float* scale, float* shift,
                                        float* saved_mean, float* saved_invstd, const void* z, const void* residual,
-                                       void* y, int32_t relu, int32_t dtype, wlseg_stream_t stream) {
+                                       void* y, uint8_t* relu_mask, int32_t relu, int32_t dtype, wlseg_stream_t stream) {
   WLSEG_CHECK_ARG(count > 0 && C > 0 && C % 8 == 0 && C <= 2048, "bn_finalize_apply: C (%d) must be a multiple of 8, <= 2048", C);
   WLSEG_CHECK_ARG(sum && sqsum && gamma && beta && scale && shift && saved_mean && saved_invstd && z && y,
                   "bn_finalize_apply: null pointer");
   WLSEG_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize_apply: moving stats must come in pairs");
+  WLSEG_CHECK_ARG(relu_mask == nullptr || (relu && C % 32 == 0 && bn_rows_enabled()), "bn_finalize_apply: the ReLU mask needs relu, C %% 32 == 0");
+  if (bn_rows_enabled()) {
+    BnFin fin = {sum, sqsum, gamma, beta, moving_mean, moving_var, scale, shift, saved_mean, saved_invstd, count, eps, decay};
+    if (dtype == WLSEG_BF16) launch_apply_rows<__nv_bfloat16>(z, nullptr, nullptr, residual, y, count, C, relu, (cudaStream_t)stream, relu_mask, &fin);
+    else if (dtype == WLSEG_F32) launch_apply_rows<float>(z, nullptr, nullptr, residual, y, count, C, relu, (cudaStream_t)stream, relu_mask, &fin);
+    else WLSEG_CHECK_ARG(false, "bn_finalize_apply: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
   const int grid = bw_grid(count * (C / 8), 256, 8);
   const size_t smem = 2 * (size_t)C * sizeof(float);
   if (dtype == WLSEG_BF16)

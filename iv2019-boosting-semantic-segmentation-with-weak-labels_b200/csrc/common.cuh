@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/wlseg.h"
 
@@ -46,6 +47,18 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+
+// SMs the persistent tensor-core kernels (one 200+ KB CTA per SM, statically strided tiles) spread over.  Data-parallel
+// training sets WLSEG_CONV_SMS=144 (wlseg/trainer.py): an NCCL all-reduce kernel overlapping backward needs SMs of its
+// own - its CTAs cannot co-reside with a convolution CTA (shared memory), and a convolution CTA that has to wait for an
+// SM delays the whole statically scheduled grid by the length of the collective (measured: +4-7 % per step).
+inline int conv_sms() {
+  const char* e = getenv("WLSEG_CONV_SMS");
+  if (e == nullptr) return kNumSMs;
+  int v = atoi(e);
+  v -= v % 2;
+  return v < 2 ? 2 : (v > kNumSMs ? kNumSMs : v);
+}
 
 // ---- storage type helpers (fp32 / bf16), arithmetic always in fp32 ----
 template <typename T> __device__ __forceinline__ float to_f32(T v);

@@ -804,13 +804,14 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
     WLSEG_CHECK_ARG(max_pairs > 0, "conv(tcgen05): the device cannot host a CTA pair of this kernel");
     prm.units = (int)ceil_div(prm.m_tiles, 2) * prm.n_tiles;
     int clusters = prm.units < max_pairs ? prm.units : max_pairs;
+    if (clusters > conv_sms() / 2) clusters = conv_sms() / 2;
     if (prm.bn_sum != nullptr && clusters % prm.n_tiles != 0) clusters -= clusters % prm.n_tiles;
     WLSEG_CHECK_ARG(clusters > 0, "conv(tcgen05): no CTA pair fits the N-tile constraint of the fused statistics");
     WLSEG_CUDA(launch_pair(conv_igemm_kernel<BN, TY, kTmaEpi, EW, true>, clusters, 128 + 32 * EW, smem_bytes, s, prm));
     return 0;
   }
   prm.units = prm.total_tiles;
-  int grid = prm.total_tiles < kNumSMs ? prm.total_tiles : kNumSMs;
+  int grid = prm.total_tiles < conv_sms() ? prm.total_tiles : conv_sms();
   // fused BN statistics live in registers across tiles: every CTA must stay on one N tile
   if (kTmaEpi && prm.bn_sum != nullptr && grid % prm.n_tiles != 0) grid -= grid % prm.n_tiles;
   WLSEG_CUDA(launch_pdl(conv_igemm_kernel<BN, TY, kTmaEpi, EW, false>, dim3(grid), dim3(128 + 32 * EW), smem_bytes, s, prm));

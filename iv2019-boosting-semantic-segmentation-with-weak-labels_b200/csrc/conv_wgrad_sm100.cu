@@ -350,7 +350,7 @@ static int launch_wgrad(WgradParams& prm, cudaStream_t s) {
   prm.stages = stages;
   const int smem_bytes = stages * kStageBytes + fixed;
   if constexpr (kPair) {
-    const int clusters = prm.units < kNumSMs / 2 ? prm.units : kNumSMs / 2;
+    const int clusters = prm.units < conv_sms() / 2 ? prm.units : conv_sms() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(kWgThreads);
@@ -366,7 +366,7 @@ static int launch_wgrad(WgradParams& prm, cudaStream_t s) {
     WLSEG_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, true>, prm));
     return 0;
   }
-  const int grid = prm.units < kNumSMs ? prm.units : kNumSMs;
+  const int grid = prm.units < conv_sms() ? prm.units : conv_sms();
   WLSEG_CUDA(launch_pdl(conv_wgrad_kernel<BN, false>, dim3(grid), dim3(kWgThreads), smem_bytes, s, prm));
   return 0;
 }
@@ -426,7 +426,7 @@ int conv_wgrad_tcgen05(const wlseg_conv_params* p, const void* x, const void* dy
   if (use_pair) prm.m_tiles /= 2;
   prm.tiles = prm.m_tiles * prm.n_tiles;
   // pixel splits: about two waves of work units, at least 4 patches per split
-  int splits = (2 * (use_pair ? kNumSMs / 2 : kNumSMs)) / prm.tiles;
+  int splits = (2 * (use_pair ? conv_sms() / 2 : conv_sms())) / prm.tiles;
   const int max_splits = prm.patches / 4 > 0 ? prm.patches / 4 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

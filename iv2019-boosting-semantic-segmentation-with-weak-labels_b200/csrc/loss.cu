@@ -44,7 +44,17 @@ struct LossArgs {
   double* sums;
   double* counts;
   float* dlogits;
+  // weak labels in their COMPACT form (wlseg_loss_fwd_bwd_lists): the kernel builds each pixel's 15-way multinomial
+  // itself instead of reading 60 B of it - input_subset_bboxes_v2.py:74-98 (`_generate_rla`) and
+  // input_subset_image_labels.py:73-107 evaluated in registers.  Used when bbox / image are NULL.
+  const float* box_coords;    // [n_bbox][max_boxes][4] = xmin, xmax, ymin, ymax, normalised
+  const int32_t* box_cids;    // [n_bbox][max_boxes], outside [0, 14] = padding / unknown label
+  int max_boxes;
+  const float* image_vec;     // [n_image][15]
 };
+
+constexpr int kLossMaxBoxes = 516;   // MAX_N_BBOXES, input_subset_bboxes_v2.py:33
+struct LossBox { int x0, x1, y0, y1, cid; };
 
 __device__ __forceinline__ void softmax_stats(const float* g, int C, float& mx, int& arg, float& lse_minus_max) {
   mx = g[0];
@@ -384,6 +394,9 @@ loss_cols_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a)
   __shared__ float redc[3][kColTX / 32];
   __shared__ float selv[kNumWeak * CV];
   __shared__ float selh[kNumWeak * CH];
+  __shared__ LossBox sbox[kWeak ? kLossMaxBoxes : 1];
+  __shared__ int snbox;
+  __shared__ float simg[kNumWeak];
   if (kWeak) {
     for (int i = threadIdx.x; i < kNumWeak * CV; i += kColTX) selv[i] = (hier.bb_to_veh[i / CV] == i % CV) ? 1.f : 0.f;
     for (int i = threadIdx.x; i < kNumWeak * CH; i += kColTX) selh[i] = (hier.bb_to_hum[i / CH] == i % CH) ? 1.f : 0.f;
@@ -406,6 +419,40 @@ loss_cols_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* wl_s = wstage + warp * (32 * kNumWeak);
   const int kind = (b < a.n_strong) ? 0 : (b < a.n_strong + a.n_bbox ? 1 : 2);
+  // compact weak labels: the boxes of this image that touch this CTA's tile, as integer pixel bounds - the same
+  // arithmetic as wlseg_rasterize_bbox_labels (int(coord * size) in double, python slice [min : max + 1] clipped)
+  const bool from_boxes = kWeak && kind == 1 && a.bbox == nullptr;
+  const bool from_vec = kWeak && kind == 2 && a.image == nullptr;
+  if constexpr (kWeak) {
+    if (threadIdx.x == 0) snbox = 0;
+    __syncthreads();
+    if (from_boxes) {
+      const int bi = b - a.n_strong;
+      for (int k = threadIdx.x; k < a.max_boxes; k += kColTX) {
+        const int cid = a.box_cids[(int64_t)bi * a.max_boxes + k];
+        if (cid < 0 || cid >= kNumWeak) continue;
+        const float* c = a.box_coords + ((int64_t)bi * a.max_boxes + k) * 4;
+        LossBox bx;
+        bx.x0 = (int)((double)c[0] * (double)a.W);
+        bx.x1 = (int)((double)c[1] * (double)a.W);
+        bx.y0 = (int)((double)c[2] * (double)a.H);
+        bx.y1 = (int)((double)c[3] * (double)a.H);
+        bx.cid = cid;
+        if (bx.x0 < 0) bx.x0 = 0;
+        if (bx.y0 < 0) bx.y0 = 0;
+        if (bx.x1 > a.W - 1) bx.x1 = a.W - 1;
+        if (bx.y1 > a.H - 1) bx.y1 = a.H - 1;
+        if (bx.x0 > bx.x1 || bx.y0 > bx.y1) continue;
+        if (bx.x1 < x0 || bx.x0 >= x0 + kColTX || bx.y1 < y0 || bx.y0 >= y0 + kColTY) continue;   // misses this tile
+        const int slot = atomicAdd(&snbox, 1);
+        if (slot < kLossMaxBoxes) sbox[slot] = bx;
+      }
+    }
+    if (from_vec && threadIdx.x < kNumWeak)
+      simg[threadIdx.x] = a.image_vec[(int64_t)(b - a.n_strong - a.n_bbox) * kNumWeak + threadIdx.x];
+    __syncthreads();
+  }
+  const int nbox_tile = kWeak ? min(snbox, kLossMaxBoxes) : 0;
   const int x = x0 + threadIdx.x;
   const bool live = x < a.W;
   const int xc = live ? x : a.W - 1;
@@ -496,19 +543,49 @@ loss_cols_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a)
         acc_loss[2] += lh; acc_cnt[2] += wh;
       }
     } else {
-      // weak image: stage the warp's 32 x 15 label floats with coalesced loads
-      const float* lab = (kind == 1)
-          ? a.bbox + ((int64_t)(b - a.n_strong) * a.H * a.W + (int64_t)y * a.W + warp_x0) * kNumWeak
-          : a.image + ((int64_t)(b - a.n_strong - a.n_bbox) * a.H * a.W + (int64_t)y * a.W + warp_x0) * kNumWeak;
-      __syncwarp();
-      if (n_valid > 0) {
-        const int total = n_valid * kNumWeak;
-        for (int i = lane; i < total; i += 32) wl_s[i] = __ldg(lab + i);
-      }
-      __syncwarp();
       float wl[kNumWeak];
+      if (from_boxes) {
+        // _generate_rla for this pixel: one count per class over the boxes that contain it, normalised to a
+        // multinomial (one IEEE division per channel), void where no box
 #pragma unroll
-      for (int c = 0; c < kNumWeak; ++c) wl[c] = live ? wl_s[lane * kNumWeak + c] : 0.f;
+        for (int c = 0; c < kNumWeak; ++c) wl[c] = 0.f;
+        for (int k = 0; k < nbox_tile; ++k) {
+          const LossBox bx = sbox[k];
+          const bool in = (xc >= bx.x0) & (xc <= bx.x1) & (y >= bx.y0) & (y <= bx.y1);
+#pragma unroll
+          for (int c = 0; c < kNumWeak; ++c) wl[c] += (in && bx.cid == c) ? 1.f : 0.f;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kNumWeak; ++c) s += wl[c];
+        if (s > 0.5f) {
+#pragma unroll
+          for (int c = 0; c < kNumWeak; ++c) wl[c] = __fdiv_rn(wl[c], s);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kNumWeak; ++c) wl[c] = (c == kNumWeak - 1) ? 1.f : 0.f;
+        }
+        if (!live) {
+#pragma unroll
+          for (int c = 0; c < kNumWeak; ++c) wl[c] = 0.f;
+        }
+      } else if (from_vec) {
+#pragma unroll
+        for (int c = 0; c < kNumWeak; ++c) wl[c] = live ? simg[c] : 0.f;
+      } else {
+        // dense weak labels: stage the warp's 32 x 15 label floats with coalesced loads
+        const float* lab = (kind == 1)
+            ? a.bbox + ((int64_t)(b - a.n_strong) * a.H * a.W + (int64_t)y * a.W + warp_x0) * kNumWeak
+            : a.image + ((int64_t)(b - a.n_strong - a.n_bbox) * a.H * a.W + (int64_t)y * a.W + warp_x0) * kNumWeak;
+        __syncwarp();
+        if (n_valid > 0) {
+          const int total = n_valid * kNumWeak;
+          for (int i = lane; i < total; i += 32) wl_s[i] = __ldg(lab + i);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < kNumWeak; ++c) wl[c] = live ? wl_s[lane * kNumWeak + c] : 0.f;
+      }
       // no L1 loss, but the current L1 argmax gates the L2 weights
       float best;
       int d1;
@@ -623,10 +700,12 @@ __global__ void loss_finalize_kernel(int C1, int Cv, int Ch, int cp, const doubl
 
 using namespace wlseg;
 
-extern "C" int wlseg_loss_fwd_bwd(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch,
-                                  int32_t n_strong, int32_t n_bbox, int32_t n_image, int32_t h, int32_t w, int32_t H, int32_t W,
-                                  const int32_t* strong_labels, const float* bbox_labels, const float* image_labels,
-                                  double* sums, double* counts, float* dlogits, wlseg_stream_t stream) {
+static int loss_impl(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch, int32_t n_strong, int32_t n_bbox,
+                     int32_t n_image, int32_t h, int32_t w, int32_t H, int32_t W, const int32_t* strong_labels,
+                     const float* bbox_labels, const float* image_labels, const float* box_coords, const int32_t* box_cids,
+                     int32_t max_boxes, const float* image_vectors, double* sums, double* counts, float* dlogits,
+                     wlseg_stream_t stream) {
+  const bool lists = box_coords != nullptr || image_vectors != nullptr;
   if (int e = check_hierarchy(hier)) return e;
   WLSEG_CHECK_ARG(n_strong >= 0 && n_bbox >= 0 && n_image >= 0, "loss: negative batch part");
   WLSEG_CHECK_ARG(h > 0 && w > 0 && H >= h && W >= w, "loss: expects upsampling (h,w)=(%d,%d) -> (H,W)=(%d,%d)", h, w, H, W);
@@ -635,8 +714,9 @@ extern "C" int wlseg_loss_fwd_bwd(const wlseg_hierarchy* hier, const float* logi
   if (B == 0) return 0;
   WLSEG_CHECK_ARG(logits && sums && counts && dlogits, "loss: null pointer");
   WLSEG_CHECK_ARG(n_strong == 0 || strong_labels, "loss: strong labels missing");
-  WLSEG_CHECK_ARG(n_bbox == 0 || bbox_labels, "loss: bbox labels missing");
-  WLSEG_CHECK_ARG(n_image == 0 || image_labels, "loss: image labels missing");
+  WLSEG_CHECK_ARG(n_bbox == 0 || bbox_labels || (box_coords && box_cids && max_boxes >= 0), "loss: bbox labels missing");
+  WLSEG_CHECK_ARG(n_image == 0 || image_labels || image_vectors, "loss: image labels missing");
+  WLSEG_CHECK_ARG(max_boxes <= kLossMaxBoxes, "loss: more than %d boxes per image", kLossMaxBoxes);
   WLSEG_CHECK_ARG(B <= 65535, "loss: batch too large");
   WLSEG_CHECK_ARG(logits_pitch >= hier->C1 + hier->Cv + hier->Ch, "loss: logits_pitch %d < channels", logits_pitch);
   LossArgs a;
@@ -650,6 +730,7 @@ extern "C" int wlseg_loss_fwd_bwd(const wlseg_hierarchy* hier, const float* logi
   a.gs = Ct | 1;
   a.strong = strong_labels; a.bbox = bbox_labels; a.image = image_labels;
   a.sums = sums; a.counts = counts; a.dlogits = dlogits;
+  a.box_coords = box_coords; a.box_cids = box_cids; a.max_boxes = max_boxes; a.image_vec = image_vectors;
   // Cityscapes hierarchy (14/7/3), upsampling >= 2x: the WEAK images (60 B/pixel of labels, targets by
   // segment sums) take the register-resident column-walking kernel, measured 1.3x faster than the generic
   // tile kernel there; the strong images (4 B/pixel) stay on the generic kernel, which is 1.3x faster for
@@ -670,6 +751,10 @@ extern "C" int wlseg_loss_fwd_bwd(const wlseg_hierarchy* hier, const float* logi
       if (rc == 0) n_generic = all ? 0 : n_strong;
     }
   }
+  // the compact weak labels exist in the column-walking kernel only
+  WLSEG_CHECK_ARG(!lists || n_generic <= n_strong,
+                  "loss(lists): box / class lists need the 14/7/3 hierarchy at >= 2x upsampling; rasterise them "
+                  "(wlseg_rasterize_bbox_labels, wlseg_tile_image_labels) and call wlseg_loss_fwd_bwd");
   if (n_generic == 0) return 0;
   a.ph = (int)fminf((float)h, floorf(kLossTY * a.sy) + 3.f);
   a.pw = (int)fminf((float)w, floorf(kLossTX * a.sx) + 3.f);
@@ -681,6 +766,25 @@ extern "C" int wlseg_loss_fwd_bwd(const wlseg_hierarchy* hier, const float* logi
   loss_fwd_bwd_kernel<<<grid, kLossThreads, smem, (cudaStream_t)stream>>>(*hier, a);
   WLSEG_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int wlseg_loss_fwd_bwd(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch,
+                                  int32_t n_strong, int32_t n_bbox, int32_t n_image, int32_t h, int32_t w, int32_t H, int32_t W,
+                                  const int32_t* strong_labels, const float* bbox_labels, const float* image_labels,
+                                  double* sums, double* counts, float* dlogits, wlseg_stream_t stream) {
+  return loss_impl(hier, logits, logits_pitch, n_strong, n_bbox, n_image, h, w, H, W, strong_labels, bbox_labels, image_labels,
+                   nullptr, nullptr, 0, nullptr, sums, counts, dlogits, stream);
+}
+
+extern "C" int wlseg_loss_fwd_bwd_lists(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch,
+                                        int32_t n_strong, int32_t n_bbox, int32_t n_image, int32_t h, int32_t w, int32_t H,
+                                        int32_t W, const int32_t* strong_labels, const float* box_coords,
+                                        const int32_t* box_cids, int32_t max_boxes, const float* image_vectors,
+                                        double* sums, double* counts, float* dlogits, wlseg_stream_t stream) {
+  WLSEG_CHECK_ARG(n_bbox == 0 || (box_coords && box_cids), "loss(lists): box lists missing");
+  WLSEG_CHECK_ARG(n_image == 0 || image_vectors, "loss(lists): image-level class vectors missing");
+  return loss_impl(hier, logits, logits_pitch, n_strong, n_bbox, n_image, h, w, H, W, strong_labels, nullptr, nullptr,
+                   box_coords, box_cids, max_boxes, image_vectors, sums, counts, dlogits, stream);
 }
 
 extern "C" int wlseg_loss_finalize(const wlseg_hierarchy* hier, const double* sums, const double* counts,

@@ -661,9 +661,12 @@ class TrainNetwork(Network):
     self.grad_ready = None  # callback(lo): every conv-kernel gradient at arena offset >= lo is final
     self.keep = False       # tests: keep per-layer gradient tensors on the tape
     self._flipped = None    # {scope: dgrad filter bank view}, refreshed at the start of backward()
-    # one launch for bn_finalize + bn_apply: measured 0.15 ms/step SLOWER than two launches inside the
-    # step graph (every CTA redoes the fp64 finalisation), so off by default; kept for eager use
-    self.fused_bn_finalize = False
+    # one launch for bn_finalize + bn_apply: OFF.  Round 1's form (every CTA staged all C constants in shared memory)
+    # measured 0.15 ms/step slower than two launches inside the step graph; round 2's form (csrc/bn.cu BnFin: a thread
+    # derives only its own 8 channels, fp64 multiplications instead of divisions) still loses, 352 against 361
+    # images/s in two A/B pairs on one box: the dependent chain fp64 loads -> rsqrt -> constants in front of every
+    # thread's first streaming load costs more than a 3 us launch of the finalisation kernel.  WLSEG_BN_FUSED_FINALIZE=1
+    self.fused_bn_finalize = os.environ.get('WLSEG_BN_FUSED_FINALIZE', '0') == '1'
     # per-slice working set of the two BN backward passes.  Measured on B200 (profiles/): 64 MB slices
     # (second pass from L2) LOSE to whole-tensor passes - 512-byte row segments at a 4 KB pitch halve
     # the HBM efficiency of the first pass - so slicing is off by default.
@@ -731,10 +734,12 @@ class TrainNetwork(Network):
                       self.bn_decay, self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean,
                       invstd, moving_var_factor=(count - 1.0) / count)
       ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu)
-    elif self.fused_bn_finalize and K % 8 == 0 and K <= 2048:
+    elif self.fused_bn_finalize and K % 8 == 0 and K <= 2048 and z.is_contiguous():
+      if want_mask and do_relu and K % 32 == 0:
+        mask = torch.empty((count, K // 8), dtype=torch.uint8, device=self.dev)
       ops.bn_finalize_apply(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
                             self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd,
-                            z, residual, a, do_relu)
+                            z, residual, a, do_relu, mask=mask)
     else:
       ops.bn_finalize(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
                       self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd)
@@ -1000,7 +1005,7 @@ class TrainNetwork(Network):
 
   def _use_premask(self):
     return (self.premask and not self.keep and self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT and
-            self.p.norm == 'batch' and not self.fused_bn_finalize)
+            self.p.norm == 'batch')
 
   def _unit_bwd(self, dout, u, dout_masked=False, in_mask=None):
     """dout: gradient of the unit's output (already multiplied by its ReLU derivative if dout_masked);
@@ -1154,9 +1159,24 @@ class TrainNetwork(Network):
     # algorithmic HBM bytes: the labels once + low-res logits read + low-res gradient written
     nbytes = sum(v.numel() * v.element_size() for v in labels.values() if v is not None)
     nbytes += 2 * logits.shape[0] * logits.shape[1] * logits.shape[2] * sum(self.hier.head_widths) * 4
+    compact = labels.get('bbox_coords') is not None or labels.get('image_vectors') is not None
+    if compact and not (self.hier.head_widths == (14, 7, 3) and H >= 2 * logits.shape[1] and W >= 2 * logits.shape[2]):
+      # compact weak labels outside the column-walking kernel's reach (Vistas heads): rasterise, then the dense path
+      labels = dict(labels)
+      if labels.get('bbox_coords') is not None:
+        labels['prolabels_per_bbox'] = ops.rasterize_bbox_labels(labels.pop('bbox_coords'), labels.pop('bbox_cids'), H, W)
+      if labels.get('image_vectors') is not None:
+        labels['prolabels_per_image'] = ops.tile_image_labels(labels.pop('image_vectors'), H, W)
+      compact = False
     with self._Timed(self, 'loss_fwd_bwd', nbytes):
-      ops.loss_fwd_bwd(self.hstruct, logits, H, W, labels.get('prolabels_per_pixel'),
-                       labels.get('prolabels_per_bbox'), labels.get('prolabels_per_image'), ws.loss_sums,
-                       ws.loss_counts, dlogits)
+      if compact:
+        assert labels.get('prolabels_per_bbox') is None and labels.get('prolabels_per_image') is None, \
+            'weak labels come either dense or compact, not both'
+        ops.loss_fwd_bwd_lists(self.hstruct, logits, H, W, labels.get('prolabels_per_pixel'), labels.get('bbox_coords'),
+                               labels.get('bbox_cids'), labels.get('image_vectors'), ws.loss_sums, ws.loss_counts, dlogits)
+      else:
+        ops.loss_fwd_bwd(self.hstruct, logits, H, W, labels.get('prolabels_per_pixel'),
+                         labels.get('prolabels_per_bbox'), labels.get('prolabels_per_image'), ws.loss_sums,
+                         ws.loss_counts, dlogits)
     ops.loss_finalize(self.hstruct, ws.loss_sums, ws.loss_counts, l2_coef, grad_scale, dlogits, ws.losses)
     return ws.losses, dlogits

@@ -53,7 +53,7 @@ _SIGNATURES = {
     'wlseg_bn_finalize': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _vp]),
     'wlseg_bn_finalize_apply': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _vp, _c_f, _c_f, _vp, _vp, _vp, _vp, _vp,
-                                               _vp, _vp, _vp, _vp, _c_int, _c_int, _vp]),
+                                               _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _vp]),
     'wlseg_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp]),
     'wlseg_bn_apply_mask': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _vp]),
     'wlseg_conv2d_fprop_masked': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -81,6 +81,8 @@ _SIGNATURES = {
     'wlseg_replace_voids': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _vp, _vp, _vp, _c_i64, _c_int, _vp]),
     'wlseg_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                           _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'wlseg_loss_fwd_bwd_lists': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                                _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp]),
     'wlseg_loss_finalize': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _vp, _c_f, _c_f, _vp, _c_int, _c_i64, _vp,
                                            _vp]),
     'wlseg_confmat_accumulate': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _c_int, _vp, _vp, _vp]),
@@ -93,6 +95,7 @@ _SIGNATURES = {
     'wlseg_weights_transpose_flip_batched': (ctypes.c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     'wlseg_zero_insert': (ctypes.c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
     'wlseg_conv1_pack': (ctypes.c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    'wlseg_resize_crop': (ctypes.c_int, [_vp, _vp] + [_c_int] * 11 + [_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -275,10 +278,10 @@ def bn_finalize(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mean, mov
 
 
 def bn_finalize_apply(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, saved_mean,
-                      saved_invstd, z, residual, y, relu):
+                      saved_invstd, z, residual, y, relu, mask=None):
   _check(lib().wlseg_bn_finalize_apply(_ptr(sum_), _ptr(sqsum), count, C, _ptr(gamma), _ptr(beta), eps, decay,
                                        _ptr(moving_mean), _ptr(moving_var), _ptr(scale), _ptr(shift), _ptr(saved_mean),
-                                       _ptr(saved_invstd), _ptr(z), _ptr(residual), _ptr(y), int(relu),
+                                       _ptr(saved_invstd), _ptr(z), _ptr(residual), _ptr(y), _ptr(mask), int(relu),
                                        dtype_code(z.dtype), _stream()), 'wlseg_bn_finalize_apply')
   _count()
   return y
@@ -488,6 +491,28 @@ def loss_fwd_bwd(hier, logits, H, W, strong_labels, bbox_labels, image_labels, s
   _count()
 
 
+def loss_fwd_bwd_lists(hier, logits, H, W, strong_labels, box_coords, box_cids, image_vectors, sums, counts, dlogits):
+  """loss_fwd_bwd with compact weak labels: box_coords fp32 [nb, max_boxes, 4] + box_cids int32 [nb, max_boxes] for
+  the bbox images, image_vectors fp32 [ni, 15] for the image-level ones (batch order: strong, bbox, image)."""
+  B, h, w, pitch = logits.shape
+  ns = 0 if strong_labels is None else strong_labels.shape[0]
+  nb = 0 if box_coords is None else box_coords.shape[0]
+  ni = 0 if image_vectors is None else image_vectors.shape[0]
+  assert ns + nb + ni == B, 'labels do not cover the batch'
+  assert logits.dtype == torch.float32 and logits.is_contiguous() and dlogits.shape == logits.shape
+  mb = 0 if box_coords is None else box_coords.shape[1]
+  if nb:
+    assert box_coords.dtype == torch.float32 and box_cids.dtype == torch.int32 and tuple(box_cids.shape) == (nb, mb)
+    box_coords, box_cids = box_coords.contiguous(), box_cids.contiguous()
+  if ni:
+    assert image_vectors.dtype == torch.float32 and image_vectors.shape[1] == 15
+    image_vectors = image_vectors.contiguous()
+  _check(lib().wlseg_loss_fwd_bwd_lists(ctypes.byref(hier), _ptr(logits), pitch, ns, nb, ni, h, w, H, W,
+                                        _ptr(strong_labels), _ptr(box_coords), _ptr(box_cids), mb, _ptr(image_vectors),
+                                        _ptr(sums), _ptr(counts), _ptr(dlogits), _stream()), 'wlseg_loss_fwd_bwd_lists')
+  _count()
+
+
 def loss_finalize(hier, sums, counts, l2_coef, grad_scale, dlogits, losses):
   pitch = dlogits.shape[-1] if dlogits is not None else hier.C1 + hier.Cv + hier.Ch
   npix = 0 if dlogits is None else dlogits.numel() // pitch
@@ -525,3 +550,23 @@ def add_inplace(dst, src):
          'wlseg_add_inplace')
   _count()
   return dst
+
+
+def resize_crop(x, resized_hw, offset, target_hw, kind):
+  """tf.image.resize_images(align_corners=False) to `resized_hw` + crop of the `target_hw` window at `offset`, one pass
+  (input_pipelines/utils.py:181-247).  kind: 'bilinear' (fp32 images), 'nearest' (fp32 dense labels or int32 ids)."""
+  squeeze = x.dim() == 3
+  xx = x.unsqueeze(-1) if squeeze else x
+  N, H, W, C = xx.shape
+  if kind == 'bilinear':
+    assert xx.dtype == torch.float32
+    k = 0
+  else:
+    assert xx.dtype in (torch.float32, torch.int32)
+    k = 1 if xx.dtype == torch.float32 else 2
+  y = torch.empty((N, target_hw[0], target_hw[1], C), dtype=xx.dtype, device=xx.device)
+  _check(lib().wlseg_resize_crop(_ptr(xx.contiguous()), _ptr(y), N, H, W, C, int(resized_hw[0]), int(resized_hw[1]),
+                                 int(offset[0]), int(offset[1]), int(target_hw[0]), int(target_hw[1]), k, _stream()),
+         'wlseg_resize_crop')
+  _count()
+  return y.squeeze(-1) if squeeze else y

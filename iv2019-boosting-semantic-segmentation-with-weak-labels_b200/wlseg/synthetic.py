@@ -56,23 +56,36 @@ class SyntheticInputs:
     coords, cids = self.bbox_lists(n, max_boxes)
     return ops.rasterize_bbox_labels(coords, cids, h, w)
 
-  def image_labels(self, n, h, w, max_classes=3):
-    """m ~ U{1..max_classes} classes per image, value 1/m, tiled over the image on the device
-    (input_subset_image_labels.py:73-107)."""
-    from wlseg import ops
+  def image_vectors(self, n, max_classes=3):
+    """Compact image-level labels: m ~ U{1..max_classes} classes per image, value 1/m -> fp32 [n, 15]."""
     vec = torch.zeros((n, NUM_WEAK), dtype=torch.float32, device=self.device)
     for i in range(n):
       m = int(torch.randint(1, max_classes + 1, (1,), generator=self.gen, device=self.device))
       cids = torch.randperm(NUM_WEAK - 1, generator=self.gen, device=self.device)[:m]
       vec[i, cids] = 1.0 / m
-    return ops.tile_image_labels(vec, h, w)
+    return vec
+
+  def image_labels(self, n, h, w, max_classes=3):
+    """m ~ U{1..max_classes} classes per image, value 1/m, tiled over the image on the device
+    (input_subset_image_labels.py:73-107)."""
+    from wlseg import ops
+    return ops.tile_image_labels(self.image_vectors(n, max_classes), h, w)
 
   # ---- batches in the reference's (features, labels) form ------------------------------------
-  def train_batch(self, npp, npb, npi, h, w):
+  def train_batch(self, npp, npb, npi, h, w, compact=False):
+    """compact: the weak labels stay in the form the Open Images side stores - (class, box) lists and one 15-way
+    vector per image-level image ('bbox_coords', 'bbox_cids', 'image_vectors') - and the loss kernel expands them
+    per pixel in registers (wlseg_loss_fwd_bwd_lists) instead of reading 60 B/pixel of dense labels."""
     features = {'proimages': self.images(npp + npb + npi, h, w)}
-    labels = {'prolabels_per_pixel': self.strong_labels(npp, h, w),
-              'prolabels_per_bbox': self.bbox_labels(npb, h, w) if npb else None,
-              'prolabels_per_image': self.image_labels(npi, h, w) if npi else None}
+    labels = {'prolabels_per_pixel': self.strong_labels(npp, h, w)}
+    if compact:
+      if npb:
+        labels['bbox_coords'], labels['bbox_cids'] = self.bbox_lists(npb)
+      if npi:
+        labels['image_vectors'] = self.image_vectors(npi)
+    else:
+      labels['prolabels_per_bbox'] = self.bbox_labels(npb, h, w) if npb else None
+      labels['prolabels_per_image'] = self.image_labels(npi, h, w) if npi else None
     return features, labels
 
   def eval_batch(self, n, h, w):

@@ -40,7 +40,7 @@ def run(args, ctx, cpu_train_sample=None):
   st.batch_norm_decay, st.distribute, st.ema_decay = 0.9, world > 1, 0.0
   tr = wtrainer.Trainer(params, st, dtype=torch.bfloat16, rank=rank, world_size=world)
   src = synthetic.SyntheticInputs(hier.num_classes, dev, rank=rank)
-  batches = [src.train_batch(NB, npb, npi, H, W) for _ in range(2)]
+  batches = [src.train_batch(NB, npb, npi, H, W, compact=boxes) for _ in range(2)]
 
   def step(i):
     f, l = batches[i % 2]
@@ -136,8 +136,9 @@ def run(args, ctx, cpu_train_sample=None):
       lab = {'prolabels_per_pixel': torch.randint(0, hier.num_classes, (NB, H, W), generator=g, dtype=torch.int32).pin_memory()}
       if mixed:
         f, l = batches[0]
-        lab['prolabels_per_bbox'] = l['prolabels_per_bbox'].cpu().pin_memory()
-        lab['prolabels_per_image'] = l['prolabels_per_image'].cpu().pin_memory()
+        for k in ('prolabels_per_bbox', 'prolabels_per_image', 'bbox_coords', 'bbox_cids', 'image_vectors'):
+          if l.get(k) is not None:
+            lab[k] = l[k].cpu().pin_memory()
       host.append(({'proimages': img}, lab))
     est = west.Estimator.__new__(west.Estimator)
     st.rank, st.world_size = rank, world

@@ -27,7 +27,7 @@ class GradientBuckets:
   all-reduced asynchronously on `comm_stream` (NCCL) or inline (gloo / CPU tests); `finish()`
   flushes the rest and averages.  Device agnostic so that the logic is testable with gloo."""
 
-  def __init__(self, flat, bucket_elems, world_size, process_group=None, comm_stream=None, extra=()):
+  def __init__(self, flat, bucket_elems, world_size, process_group=None, comm_stream=None, extra=(), tail_elems=0):
     self.flat = flat
     self.extra = list(extra)  # tensors that only become final at the very end (BN gamma / beta gradients)
     self.also_wait = []       # further streams whose work a bucket depends on (the wgrad side stream)
@@ -35,13 +35,18 @@ class GradientBuckets:
     self.world = world_size
     self.group = process_group
     self.stream = comm_stream
-    # bucket boundaries from the tail: [n - k*b, n - (k-1)*b)
+    # bucket boundaries from the tail: [n - k*b, n - (k-1)*b).  The LOWEST addresses (root convolution, block1)
+    # become final last, and whatever bucket holds them is exposed in front of the optimizer: it is cut down to
+    # `tail_elems` (measured at 2 GPUs: a 19 MB last bucket = 75 us exposed, profiles/r2_timeline_train_n2.txt)
     self.bounds = []
     hi = self.n
-    while hi > 0:
-      lo = max(0, hi - bucket_elems)
+    tail = min(tail_elems, self.n) if tail_elems else 0
+    while hi > tail:
+      lo = max(tail, hi - bucket_elems)
       self.bounds.append((lo, hi))
       hi = lo
+    if tail:
+      self.bounds.append((0, tail))
     self.next = 0
     self.handles = []
     self.launched_bytes = 0
@@ -75,9 +80,23 @@ class GradientBuckets:
   def finish(self):
     """All remaining buckets; returns the factor the caller must scale the summed gradient by
     (1/world: mean over replicas) - folded into the optimizer kernel's grad_scale."""
-    self.ready(0)
-    for t in self.extra:
-      self._launch_view(t)
+    if self.world > 1 and self.stream is not None and self.next < len(self.bounds) and self.extra:
+      # the last bucket and the BN parameter gradients leave as ONE grouped collective (one NCCL kernel)
+      import torch.distributed as dist
+      views = [self.flat[lo:hi] for lo, hi in self.bounds[self.next:]] + list(self.extra)
+      self.next = len(self.bounds)
+      self.stream.wait_stream(torch.cuda.current_stream())
+      for st in self.also_wait:
+        self.stream.wait_stream(st)
+      with torch.cuda.stream(self.stream):
+        with dist._coalescing_manager(group=self.group, device=self.flat.device):
+          for v in views:
+            self.launched_bytes += v.numel() * v.element_size()
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+    else:
+      self.ready(0)
+      for t in self.extra:
+        self._launch_view(t)
     for h in self.handles:
       h.wait()
     self.handles = []
@@ -115,8 +134,16 @@ class Trainer:
       # variable's initial value and zero-debiasing is NOT applied (it only applies to plain tensors)
       self.ws.ema_shadow = params.master.clone()
     self.comm_stream = torch.cuda.Stream(device=params.device) if (world_size > 1 and params.device.type == 'cuda') else None
+    # (WLSEG_CONV_SMS=144 + NCCL_MAX_CTAS=4 would give the collectives SMs of their own next to the persistent
+    # convolution kernels - csrc/common.cuh conv_sms; measured at 8 GPUs it does NOT pay: 11.77 ms/step with all 148 SMs
+    # and NCCL's defaults, 11.86 with 144 + 4, 12.54 with 140 + 8, profiles/r2_n8_sm_partition.txt)
+    # last (exposed) bucket: everything below block2 - conv1 + block1, ~0.9 MB - so that the tail of the exchange is
+    # one small collective; it travels with the BN gamma / beta gradients, which also become final at the very end
+    spec_off = [params.w_off[s.scope] for s in params.specs if '/block2/' in s.scope]
+    tail = min(spec_off) if spec_off else 0
     self.buckets = GradientBuckets(self.ws.grads[:params.n_conv_pad], bucket_mb * (1 << 20) // 4, world_size,
-                                   comm_stream=self.comm_stream, extra=[self.ws.grads[params.n_conv_pad:]])
+                                   comm_stream=self.comm_stream, extra=[self.ws.grads[params.n_conv_pad:]],
+                                   tail_elems=tail)
     self.net.grad_ready = self.buckets.ready if world_size > 1 else None
     if os.environ.get('WLSEG_WGRAD_STREAM', '0') == '1' and params.device.type == 'cuda':
       self.net.wgrad_stream = torch.cuda.Stream(device=params.device)

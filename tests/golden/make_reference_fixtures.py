@@ -14,6 +14,7 @@ below are the reference's own objects, called unmodified:
   estimator.define_optimizer.define_optimizer                            (define_optimizer.py:3-26)
   input_pipelines.open_images.input_subset_bboxes_v2._generate_rla       (input_subset_bboxes_v2.py:74-98)
   input_pipelines.utils.get_temp_Nb, from_0_1_to_m1_1                    (input_pipelines/utils.py:93-124)
+  input_pipelines.utils.resize_images_and_labels                         (input_pipelines/utils.py:181-247)
   utils.utils._replacevoids, print_metrics_from_confusion_matrix         (utils/utils.py:286-289,385-446)
 
 Inputs are seeded and stored next to the outputs; gradients of the reference's `total` loss with respect to the
@@ -249,6 +250,28 @@ def main():
     uu.print_metrics_from_confusion_matrix(cm, printfile=buf, summary=True)
   out['print_metrics/cm'] = cm
   out['print_metrics/summary'] = np.asarray(buf.getvalue())
+
+  # ---- resize_images_and_labels (input_pipelines/utils.py:181-247): aspect-preserving resize + random crop
+  for tag, shape, lab_kind, target, preserve, seed in (
+      ('crop_ids', (2, 20, 31, 3), 'ids', (16, 16), True, 5),
+      ('crop_dense', (1, 24, 18, 3), 'dense', (20, 20), True, 9),
+      ('crop_ids_tall', (1, 37, 16, 3), 'ids', (12, 12), True, 2),
+      ('resize_plain', (2, 20, 31, 3), 'ids', (13, 40), False, 1)):
+    gg = torch.Generator().manual_seed(seed)
+    img = torch.rand(*shape, generator=gg)
+    if lab_kind == 'ids':
+      lab = torch.randint(0, 20, shape[:3], generator=gg, dtype=torch.int32)
+    else:
+      lab = torch.softmax(3 * torch.randn(*shape[:3], 15, generator=gg), -1)
+    tf.set_random_seed(seed)
+    pi, pl = iu.resize_images_and_labels(tf.as_tf(img), tf.as_tf(lab), target, preserve_aspect_ratio=preserve)
+    out[f'{tag}/images'] = img.numpy()
+    out[f'{tag}/labels'] = lab.numpy()
+    out[f'{tag}/target'] = np.asarray(target, dtype=np.int32)
+    out[f'{tag}/preserve'] = np.asarray(preserve)
+    out[f'{tag}/offset'] = np.asarray(list(tf.RANDOM_LOG) if preserve else [0, 0], dtype=np.int32)
+    out[f'{tag}/out_images'] = torch.Tensor(pi).numpy() if False else pi.as_subclass(torch.Tensor).numpy()
+    out[f'{tag}/out_labels'] = pl.as_subclass(torch.Tensor).numpy()
 
   np.savez_compressed(args.out, **out)
   print(f'wrote {args.out}: {len(out)} arrays, {os.path.getsize(args.out) / 1024:.0f} KB')

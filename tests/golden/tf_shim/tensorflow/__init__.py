@@ -88,6 +88,74 @@ def _register(name, **attrs):
   return m
 
 
+# ------------------------------------------------------------------------------------------------ tensors with a TF shape
+class _Dim(int):
+  """tf.Dimension: an int with `.value`."""
+
+  @property
+  def value(self):
+    return int(self)
+
+
+class _Shape(tuple):
+  """tf.TensorShape of an eager tensor: always fully defined."""
+
+  def __new__(cls, dims):
+    return super().__new__(cls, (_Dim(d) for d in dims))
+
+  def __getitem__(self, i):
+    r = tuple.__getitem__(self, i)
+    return _Shape(r) if isinstance(i, slice) else r
+
+  @property
+  def ndims(self):
+    return len(self)
+
+  def as_list(self):
+    return [int(d) for d in self]
+
+  def is_fully_defined(self):
+    return True
+
+  def assert_is_fully_defined(self):
+    return None
+
+  def with_rank(self, rank):
+    assert len(self) == rank
+    return self
+
+  def with_rank_at_least(self, rank):
+    assert len(self) >= rank
+    return self
+
+  def assert_has_rank(self, rank):
+    assert len(self) == rank
+
+  def is_compatible_with(self, other):
+    return tuple(self) == tuple(other)
+
+
+class TFTensor(torch.Tensor):
+  """torch.Tensor whose `.shape` behaves like a tf.TensorShape (`.ndims`, `.as_list()`, `shape[-1].value`, ...) and
+  that accepts `set_shape` / `get_shape`.  Results of torch operations on it are TFTensors again."""
+
+  @property
+  def shape(self):
+    return _Shape(torch.Tensor.size(self))
+
+  def get_shape(self):
+    return self.shape
+
+  def set_shape(self, shape_):
+    for have, want in zip(torch.Tensor.size(self), shape_):
+      assert want is None or int(want) == have, f'set_shape({tuple(shape_)}) contradicts {tuple(torch.Tensor.size(self))}'
+
+
+def as_tf(x):
+  """(shim helper) wrap a torch tensor for reference code that inspects TensorShape attributes."""
+  return x.as_subclass(TFTensor)
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def _t(x, dtype=None):
   if isinstance(x, torch.Tensor):
@@ -202,6 +270,57 @@ def add_n(xs):
 
 def div(a, b):
   return a / b
+
+
+def unstack(x, num=None, axis=0):
+  return [int(v) for v in x] if isinstance(x, (tuple, list)) else list(torch.unbind(x, dim=axis))
+
+
+def stack(values, axis=0):
+  return torch.stack([_t(v) for v in values], dim=axis)
+
+
+def subtract(a, b):
+  return _t(a) - _t(b)
+
+
+def add(a, b):
+  return _t(a) + _t(b)
+
+
+def maximum(a, b):
+  return torch.maximum(_t(a, torch.float64) if not isinstance(a, torch.Tensor) else a, _t(b, torch.float64) if not isinstance(b, torch.Tensor) else b)
+
+
+def minimum(a, b):
+  return torch.minimum(_t(a, torch.float64) if not isinstance(a, torch.Tensor) else a, _t(b, torch.float64) if not isinstance(b, torch.Tensor) else b)
+
+
+def ceil(x):
+  return torch.ceil(x)
+
+
+def assert_equal(a, b, message=None):
+  ok = tuple(int(v) for v in a) == tuple(int(v) for v in b)
+  assert ok, message or f'tf.assert_equal: {a} != {b}'
+  return torch.tensor(True)
+
+
+RANDOM_LOG = []                      # (shim helper) every value tf.random_uniform returned, in call order
+_rng = torch.Generator().manual_seed(0)
+
+
+def set_random_seed(seed):
+  _rng.manual_seed(int(seed))
+  del RANDOM_LOG[:]
+
+
+def random_uniform(shape_, minval=0, maxval=None, dtype=torch.float32, seed=None, name=None):
+  """integer dtype: uniform over [minval, maxval)."""
+  assert dtype in (torch.int32, torch.int64) and tuple(shape_) == ()
+  v = torch.randint(_int(minval), _int(maxval), (), generator=_rng, dtype=dtype)
+  RANDOM_LOG.append(int(v))
+  return v
 
 
 def argmax(x, axis):

@@ -37,12 +37,13 @@ def _packed_logits(gold, tag, hier):
 
 
 @pytest.mark.parametrize('tag', LOSS_CASES)
-@pytest.mark.parametrize('from_boxes', [False, True])
+@pytest.mark.parametrize('from_boxes', [False, True, 'lists'])
 def test_loss_kernel_equals_the_reference_run(cuda, gold, tag, from_boxes):
   """`define_losses` (define_losses_hierarchical.py:14-224) run by the reference: the three losses and d total /
   d low-res logits, against wlseg_loss_fwd_bwd + wlseg_loss_finalize on the same logits and labels.  from_boxes: the
   bbox labels are rasterised on the device from the (class, box) lists (wlseg_rasterize_bbox_labels) instead of
-  being uploaded dense, the image-level ones tiled on the device."""
+  being uploaded dense, the image-level ones tiled on the device; 'lists': the lists go straight into the loss kernel
+  (wlseg_loss_fwd_bwd_lists), which expands them per pixel in registers - no dense weak label exists at all."""
   from wlseg import ops
   n_pp, n_pb, n_pi, h, w = (int(x) for x in gold[f'{tag}/counts'])
   if from_boxes and n_pb + n_pi == 0:
@@ -53,6 +54,7 @@ def test_loss_kernel_equals_the_reference_run(cuda, gold, tag, from_boxes):
   logits = _packed_logits(gold, tag, hier).to(cuda)
   strong = torch.from_numpy(gold[f'{tag}/prolabels_per_pixel']).to(cuda)
   bbox = image = None
+  coords = cids = None
   if n_pb:
     if from_boxes:
       mb = max(len(gold[f'{tag}/bbox{i}_cids']) for i in range(n_pb))
@@ -62,7 +64,8 @@ def test_loss_kernel_equals_the_reference_run(cuda, gold, tag, from_boxes):
         k = len(gold[f'{tag}/bbox{i}_cids'])
         coords[i, :k] = torch.from_numpy(gold[f'{tag}/bbox{i}_coords'])
         cids[i, :k] = torch.from_numpy(gold[f'{tag}/bbox{i}_cids'])
-      bbox = ops.rasterize_bbox_labels(coords.to(cuda), cids.to(cuda), H, W)
+      coords, cids = coords.to(cuda), cids.to(cuda)
+      bbox = ops.rasterize_bbox_labels(coords, cids, H, W)
       assert torch.equal(bbox.cpu(), torch.from_numpy(gold[f'{tag}/prolabels_per_bbox']))   # vs _generate_rla, bit-exact
     else:
       bbox = torch.from_numpy(gold[f'{tag}/prolabels_per_bbox']).to(cuda)
@@ -73,7 +76,15 @@ def test_loss_kernel_equals_the_reference_run(cuda, gold, tag, from_boxes):
   sums = torch.zeros(3, dtype=torch.float64, device=cuda)
   counts = torch.zeros(3, dtype=torch.float64, device=cuda)
   out = torch.zeros(4, device=cuda)
-  ops.loss_fwd_bwd(hs, logits, H, W, strong, bbox, image, sums, counts, dl)
+  if from_boxes == 'lists':
+    vecd = torch.from_numpy(gold[f'{tag}/prolabels_per_image_vectors']).to(cuda) if n_pi else None
+    if hier.head_widths != (14, 7, 3):
+      with pytest.raises(ops.WlsegError):      # Vistas heads: the caller rasterises (network.loss_and_grad does)
+        ops.loss_fwd_bwd_lists(hs, logits, H, W, strong, coords, cids, vecd, sums, counts, dl)
+      return
+    ops.loss_fwd_bwd_lists(hs, logits, H, W, strong, coords, cids, vecd, sums, counts, dl)
+  else:
+    ops.loss_fwd_bwd(hs, logits, H, W, strong, bbox, image, sums, counts, dl)
   ops.loss_finalize(hs, sums, counts, 0.1, 1.0, dl, out)
   torch.cuda.synchronize()
   got = out.cpu().tolist()
@@ -160,3 +171,23 @@ def test_sgdm_kernel_equals_the_reference_optimizer(cuda, gold, name, nesterov):
   for g in torch.from_numpy(gold['sgdm/grads']):
     ops.sgdm_step(w, g.clone().to(cuda), acc, wb, 0, lr, 0.9, nesterov, 0.0)
   np.testing.assert_allclose(w.cpu().numpy(), gold[f'sgdm/{name}'], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['crop_ids', 'crop_dense', 'crop_ids_tall', 'resize_plain'])
+def test_resize_crop_kernel_equals_the_reference_run(cuda, gold, tag):
+  """input_pipelines/utils.py:181-247 `resize_images_and_labels` run by the reference (crop offsets recorded) vs
+  wlseg_resize_crop: labels (nearest) bit-exact, images (bilinear) 1e-6."""
+  from wlseg import preprocess as wpre
+  img, lab = torch.from_numpy(gold[f'{tag}/images']).to(cuda), torch.from_numpy(gold[f'{tag}/labels']).to(cuda)
+  target = tuple(int(x) for x in gold[f'{tag}/target'])
+  preserve = bool(gold[f'{tag}/preserve'])
+  off = tuple(int(x) for x in gold[f'{tag}/offset'])
+  pi, pl = wpre.resize_images_and_labels(img, lab, target, preserve, offset=off)
+  np.testing.assert_allclose(pi.cpu().numpy(), gold[f'{tag}/out_images'], rtol=0, atol=1e-6)
+  assert np.array_equal(pl.cpu().numpy(), gold[f'{tag}/out_labels'])
+  if preserve:   # drawn offsets stay inside the slack and the call is deterministic under a seeded generator
+    g = torch.Generator().manual_seed(1)
+    a = wpre.resize_images_and_labels(img, lab, target, True, generator=g)
+    g = torch.Generator().manual_seed(1)
+    b = wpre.resize_images_and_labels(img, lab, target, True, generator=g)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and tuple(a[0].shape[1:3]) == target

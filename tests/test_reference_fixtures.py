@@ -162,3 +162,25 @@ def test_host_helpers_equal_reference(gold):
   assert buf.getvalue() == str(gold['print_metrics/summary'])
   m = ometrics.metrics_from_confusion_matrix(cm.astype(np.int64))
   assert f"Mean iou (ignoring accuracies' nans but including ious' 0s): {m['mean_iou']:5.2f}" in str(gold['print_metrics/summary'])
+
+
+CROP_CASES = ['crop_ids', 'crop_dense', 'crop_ids_tall', 'resize_plain']
+
+
+@pytest.mark.parametrize('tag', CROP_CASES)
+def test_resize_and_crop_equals_reference(gold, tag):
+  """input_pipelines/utils.py:181-247 run by the reference (random crop offsets recorded) vs oracle/preprocess.py and
+  the product's size arithmetic (wlseg/preprocess.py resized_size)."""
+  from oracle import preprocess as opre
+  from wlseg import preprocess as wpre
+  img, lab = torch.from_numpy(gold[f'{tag}/images']), torch.from_numpy(gold[f'{tag}/labels'])
+  target = tuple(int(x) for x in gold[f'{tag}/target'])
+  preserve = bool(gold[f'{tag}/preserve'])
+  off = tuple(int(x) for x in gold[f'{tag}/offset'])
+  pi, pl = opre.resize_images_and_labels(img, lab, target, preserve, off)
+  np.testing.assert_allclose(pi.numpy(), gold[f'{tag}/out_images'], rtol=0, atol=1e-6)
+  assert np.array_equal(pl.numpy(), gold[f'{tag}/out_labels'])
+  RH, RW = wpre.resized_size(img.shape[1], img.shape[2], target, preserve)
+  assert 0 <= off[0] <= RH - target[0] and 0 <= off[1] <= RW - target[1]
+  if preserve:   # tight fit: one of the two axes has no slack
+    assert RH == target[0] or RW == target[1]
