@@ -1,6 +1,7 @@
 """Oracle for the hierarchical strong + weak masked cross-entropy losses.
 
-TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Pinned against the reference-run vectors
+(define_losses / _segment_sum executed over tests/golden/tf_shim; tests/test_reference_fixtures.py).
 
 Follows code/estimator/define_losses_hierarchical.py:14-224 step by step;
 gradients come from torch autograd on the same expression, which restates the

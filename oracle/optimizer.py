@@ -1,6 +1,7 @@
 """Oracle for LR schedules, momentum SGD, EMA and the derived step settings.
 
-TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Pinned against the reference-run vectors
+(define_optimizer executed over tests/golden/tf_shim; tests/test_reference_fixtures.py).
 """
 
 import torch
