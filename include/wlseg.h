@@ -87,6 +87,45 @@ int wlseg_conv2d_fprop(const wlseg_conv_params* p, const void* x, const void* w,
 int wlseg_conv2d_fprop_masked(const wlseg_conv_params* p, const void* x, const void* w, void* y,
                               const void* residual, const uint8_t* out_mask, wlseg_stream_t stream);
 
+/* Training-mode batch-norm finalisation carried by the convolution that produces the statistics
+ * (wlseg_conv2d_fprop_bn): what wlseg_bn_finalize computes, run by the last CTA of the convolution grid to commit
+ * its partial sums.  `counter`: one zero-initialised device word, left at zero (shared by all layers of a stream). */
+typedef struct wlseg_bn_finalize_args {
+  int64_t count;             /* pixels the statistics are taken over: N * P * Q */
+  float eps, decay;
+  float moving_var_factor;   /* < 0: Bessel-corrected moving variance (slim.batch_norm); >= 0: var * factor */
+  int32_t reserved;
+  const float* gamma;
+  const float* beta;
+  float* moving_mean;        /* may both be NULL */
+  float* moving_var;
+  float* scale;              /* out: gamma * invstd */
+  float* shift;              /* out: beta - mean * scale */
+  float* saved_mean;         /* out */
+  float* saved_invstd;       /* out */
+  uint32_t* counter;
+} wlseg_bn_finalize_args;
+
+/* y = conv(x, w) (raw, bf16), bn_sum / bn_sqsum += per-channel sums of the stored y, and - by the last CTA - the
+ * layer's scale / shift / saved mean / inverse std and moving statistics: wlseg_conv2d_fprop(..., bn_sum, bn_sqsum)
+ * followed by wlseg_bn_finalize in ONE launch (slim.conv2d + training-mode FusedBatchNorm statistics,
+ * models/resnet50_extended_model_hierarchical.py:298-312).  tcgen05 only, K % 64 == 0. */
+int wlseg_conv2d_fprop_bn(const wlseg_conv_params* p, const void* x, const void* w, void* y, double* bn_sum,
+                          double* bn_sqsum, const wlseg_bn_finalize_args* fin, wlseg_stream_t stream);
+
+/* y = conv(x, w) * relu'(bn(z)), bf16, tcgen05 only, fused with the batch-norm backward REDUCTION of the layer that
+ * produced z: the data gradient of a tensor a = relu(z * scale + shift) leaves the dgrad epilogue already multiplied
+ * by the ReLU derivative (sign of the exact fp32 value the forward pass rounded), and the epilogue accumulates
+ *   dgamma[c] += sum y * (z - mean[c]) * invstd[c],   dbeta[c] += sum y     (over the STORED bf16 y, fp64 atomics,
+ * one per channel and CTA) - what wlseg_bn_bwd_reduce would compute in a separate pass over y and z
+ * (FusedBatchNormGrad behind models/resnet50_extended_model_hierarchical.py:298-312; the ReLU is slim.conv2d's
+ * activation_fn).  z has y's shape; the res_* fields of the parameters describe it (res_stride 1, res_H = P,
+ * res_W = Q, res_pitch).  K % 64 == 0; y, z, scale, shift 16-byte aligned.  wlseg_bn_bwd_apply then runs with
+ * relu = 0 on (y, z). */
+int wlseg_conv2d_fprop_bnbwd(const wlseg_conv_params* p, const void* x, const void* w, void* y, const void* z,
+                             const float* scale, const float* shift, const float* mean, const float* invstd,
+                             double* dgamma, double* dbeta, wlseg_stream_t stream);
+
 /* dx = conv_transpose(dy, w): gradient wrt the input (TF Conv2DBackpropInput, reached through
  * create_train_op, estimator/define_estimator_hierarchical.py:120-129).  dx is fully written. */
 int wlseg_conv2d_dgrad(const wlseg_conv_params* p, const void* dy, const void* w, void* dx,

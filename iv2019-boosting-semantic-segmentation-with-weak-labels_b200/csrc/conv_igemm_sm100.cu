@@ -68,6 +68,15 @@ struct IgemmParams {
   double* bn_sum;
   double* bn_sqsum;
   const uint32_t* out_mask;   // optional bit mask [N*P*Q][K / 32] applied to the output (wlseg_conv2d_fprop_masked)
+  // kBnb (wlseg_conv2d_fprop_bnbwd): the output is the gradient of a tensor a = relu(bn(z)); `res` / map_r describe z,
+  // the epilogue multiplies by the ReLU derivative (z * bnb_scale + bnb_shift > 0) and accumulates the BN backward sums
+  // sum g * (z - mean) * invstd -> bn_sum (dgamma), sum g -> bn_sqsum (dbeta)
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
+  // wlseg_conv2d_fprop_bn: the LAST CTA to commit its statistics finalises the layer's batch norm (fin.counter != NULL)
+  wlseg_bn_finalize_args fin;
   int N, P, Q, K, C;
   int R, S, stride, dilation, pad_top, pad_left;
   int y_pitch, res_pitch, res_stride, res_H, res_W;
@@ -165,7 +174,11 @@ __device__ __forceinline__ int num_subtiles(const IgemmParams& prm, int k0) {
 // the bandwidth-bound 1x1 / conv3 + residual layers - two thirds of which were filters (profiles/r1_eval_igemm256_full_
 // summary.txt: 1.07 GB through the fabric against 0.56 GB of DRAM traffic) - drops by a third, and a stage shrinks from
 // 48 to 32 KB.  The leader CTA (rank 0) issues the MMAs; both CTAs run their own producer and their own epilogue.
-template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair>
+//
+// kBnb (staged epilogue only): the BN-backward form of a data gradient, see IgemmParams::bnb_* - three staging buffers
+// per warp: the z tile of the NEXT step arrives by TMA in one of two while this step reads the other, the masked
+// gradient leaves from the third; the sums are read back column-wise from the staged z and g tiles.
+template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair, bool kBnb = false>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   using Cfg = IgemmCfg<BN, kPair>;
@@ -325,7 +338,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       const float lo = prm.relu ? 0.f : -INFINITY;
       const uint32_t sw = (uint32_t)(lane & 7);           // row & 7 of this thread's staging row
       const bool dbuf = has_res || prm.epi_db;            // two staging buffers per warp
-      uint8_t* wbuf = epi_smem + ew * (dbuf ? 2 : 1) * kWarpBufBytes;
+      uint8_t* wbuf = epi_smem + ew * (kBnb ? 3 : (dbuf ? 2 : 1)) * kWarpBufBytes;
       uint64_t* my_rfull = rfull_bar + 2 * ew;
       const int r0 = quarter * 32;                        // first tile row of this warp
       const int dy0 = r0 >> prm.tw_log2, dx0 = r0 & (TW - 1);
@@ -370,6 +383,10 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       for (int i = 0; i < kSlots; ++i) a1x[i] = a1y[i] = a2x[i] = a2y[i] = 0.f;
       int stat_k0 = -1;
       int cnt = 0;
+      // kBnb: saved mean / inverse std of this lane's channel pair, per slot (the CTA never changes its N tile)
+      float bmx[kSlots], bmy[kSlots], bix[kSlots], biy[kSlots];
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) bmx[i] = bmy[i] = bix[i] = biy[i] = 0.f;
       // output mask (wlseg_conv2d_fprop_masked: a data gradient leaving through the ReLU of the tensor it belongs to):
       // 64 bits per pixel and sub-tile, fetched ONE TILE AHEAD - a load issued inside the step sat on its critical
       // path with a full HBM latency (measured: +18 us on a 40 us dgrad)
@@ -403,6 +420,18 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         const int nsub = num_subtiles<BN>(prm, k0);
         if (has_stat) {
           if (stat_k0 >= 0 && k0 != stat_k0) __trap();  // grid not a multiple of the N-tile count
+          if constexpr (kBnb) {
+            if (stat_k0 < 0) {
+#pragma unroll
+              for (int i = 0; i < kSlots; ++i) {
+                const int c = k0 + (cgrp + i * CG) * kSubW + 2 * lane;
+                if (c + 1 < prm.K) {
+                  bmx[i] = __ldg(prm.bnb_mean + c); bmy[i] = __ldg(prm.bnb_mean + c + 1);
+                  bix[i] = __ldg(prm.bnb_invstd + c); biy[i] = __ldg(prm.bnb_invstd + c + 1);
+                }
+              }
+            }
+          }
           stat_k0 = k0;
         }
         mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
@@ -417,6 +446,83 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         for (int slot = 0; slot < kSlots; ++slot) {
           const int st = cgrp + slot * CG;
           if (st >= nsub) break;
+          if constexpr (kBnb) {
+            uint8_t* zb = wbuf + (cnt & 1) * kWarpBufBytes;   // z tile of this step (TMA)
+            uint8_t* ob = wbuf + 2 * kWarpBufBytes;           // masked gradient, leaves by TMA store
+            if (lane == 0) {
+              bulk_wait_read<0>();        // the previous step's store has read `ob`
+              next_residual(ld, true);    // z of step cnt + 1 -> the other z buffer (its readers finished in step cnt - 1)
+              next_residual(pf, false);
+            }
+            __syncwarp();
+            mbar_wait(smem_u32(my_rfull + (cnt & 1)), (uint32_t)((cnt >> 1) & 1));
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int col = st * kSubW + half * 32;
+              uint32_t v[32];
+              tmem_ld<32>(lane_addr + (uint32_t)(acc * BN + col), v);
+              tmem_ld_wait();
+              if (half == 1 && st + CG >= nsub) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) release_acc(acc);
+              }
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.f;
+              uint4 raw[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                raw[g] = *reinterpret_cast<const uint4*>(zb + lane * 128 + ((((uint32_t)(half * 4 + g)) ^ sw) << 4));
+              const float4* sc4 = reinterpret_cast<const float4*>(prm.bnb_scale + k0 + col);
+              const float4* sh4 = reinterpret_cast<const float4*>(prm.bnb_shift + k0 + col);
+              uint4 outv[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&raw[g]);
+                __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv[g]);
+                const float4 sca = __ldg(sc4 + 2 * g), scb = __ldg(sc4 + 2 * g + 1);
+                const float4 sha = __ldg(sh4 + 2 * g), shb = __ldg(sh4 + 2 * g + 1);
+                const float scs[8] = {sca.x, sca.y, sca.z, sca.w, scb.x, scb.y, scb.z, scb.w};
+                const float shs[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 zz = __bfloat1622float2(hz[e]);
+                  // the ReLU derivative from the sign of the exact fp32 value the forward pass rounded (bn_reduce_kernel)
+                  const float gx = fmaf(zz.x, scs[2 * e], shs[2 * e]) > 0.f ? f[g * 8 + 2 * e] : 0.f;
+                  const float gy = fmaf(zz.y, scs[2 * e + 1], shs[2 * e + 1]) > 0.f ? f[g * 8 + 2 * e + 1] : 0.f;
+                  ho[e] = __floats2bfloat162_rn(gx, gy);
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(ob + lane * 128 + ((((uint32_t)(half * 4 + g)) ^ sw) << 4)) = outv[g];
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&prm.map_y, smem_u32(ob), k0 + st * kSubW, q0 + dx0, p0 + dy0, n);
+              bulk_commit();
+            }
+            {
+              // dgamma / dbeta partials of the STORED (bf16) gradient: lane = channel pair, column-wise over the 32 rows
+              const uint32_t coff = (uint32_t)((lane & 3) << 2);
+              float s0x = 0.f, s0y = 0.f, s1x = 0.f, s1y = 0.f;
+              const float mx = bmx[slot], my = bmy[slot], ix = bix[slot], iy = biy[slot];
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t o = (uint32_t)(r * 128) + ((((uint32_t)(lane >> 2)) ^ (uint32_t)(r & 7)) << 4) + coff;
+                const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + o));
+                const float2 z2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zb + o));
+                s0x += g2.x * (z2.x - mx) * ix; s0y += g2.y * (z2.y - my) * iy;
+                s1x += g2.x; s1y += g2.y;
+              }
+              a1x[slot] += s0x; a1y[slot] += s0y; a2x[slot] += s1x; a2y[slot] += s1y;
+            }
+            __syncwarp();   // every lane is done with `zb` before lane 0 lets the next z box land there (next step)
+            ++cnt;
+            continue;
+          }
           uint8_t* buf = wbuf + (dbuf ? (cnt & 1) * kWarpBufBytes : 0);
           // the store that last left from the buffer about to be (re)written must have read it:
           // without a residual that is this step's buffer, with one it is the NEXT step's
@@ -560,6 +666,42 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
               atomicAdd(prm.bn_sum + stat_k0 + j, (double)s_stat[j]);
               atomicAdd(prm.bn_sqsum + stat_k0 + j, (double)s_stat[BN + j]);
             }
+          }
+        }
+      }
+      if constexpr (!kBnb) {
+        if (has_stat && prm.fin.counter != nullptr) {
+          // bn_finalize_kernel's arithmetic, run by the last CTA to arrive: a ~3 us launch per layer less.  Every CTA
+          // of the grid (also one without tiles) passes here exactly once; the counter is left at zero for the next
+          // layer (kernels of one stream do not overlap: the fused form is not combined with programmatic launches).
+          uint32_t* s_last = tmem_slot + 1;
+          __threadfence();                      // this CTA's fp64 atomics before its ticket
+          epi_barrier<32 * EW>();
+          if (et == 0) *s_last = (atomicAdd(prm.fin.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+          epi_barrier<32 * EW>();
+          if (*s_last != 0u) {
+            __threadfence();
+            const double nn = (double)prm.fin.count;
+            for (int c = et; c < prm.K; c += 32 * EW) {
+              const double m = __ldcg(prm.bn_sum + c) / nn;
+              double var = __ldcg(prm.bn_sqsum + c) / nn - m * m;
+              if (var < 0.0) var = 0.0;
+              const float mf = (float)m, vf = (float)var;
+              const float inv = rsqrtf(vf + prm.fin.eps);
+              const float sc = prm.fin.gamma[c] * inv;
+              prm.fin.scale[c] = sc;
+              prm.fin.shift[c] = prm.fin.beta[c] - mf * sc;
+              prm.fin.saved_mean[c] = mf;
+              prm.fin.saved_invstd[c] = inv;
+              if (prm.fin.moving_mean != nullptr) {
+                const float unbiased = prm.fin.moving_var_factor >= 0.f
+                                           ? vf * prm.fin.moving_var_factor
+                                           : (prm.fin.count > 1 ? (float)(var * (nn / (nn - 1.0))) : vf);
+                prm.fin.moving_mean[c] -= (1.0f - prm.fin.decay) * (prm.fin.moving_mean[c] - mf);
+                prm.fin.moving_var[c] -= (1.0f - prm.fin.decay) * (prm.fin.moving_var[c] - unbiased);
+              }
+            }
+            if (et == 0) *prm.fin.counter = 0u;
           }
         }
       }
@@ -773,12 +915,13 @@ static cudaError_t launch_pair(void (*kernel)(KArgs...), int clusters, int threa
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair = false>
+template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair = false, bool kBnb = false>
 static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   using Cfg = IgemmCfg<BN, kPair>;
+  static_assert(!kBnb || kTmaEpi, "the BN-backward form lives in the staged epilogue");
   static bool configured = false;
   if (!configured) {
-    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi, EW, kPair>,
+    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi, EW, kPair, kBnb>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
@@ -790,7 +933,7 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   // store-read wait is therefore NOT what holds the bandwidth-bound layers at 0.5-0.8 of their byte bound.
   prm.epi_db = (kTmaEpi && prm.res == nullptr && prm.R * prm.S == 1 &&
                 (getenv("WLSEG_EPI_DB") != nullptr ? atoi(getenv("WLSEG_EPI_DB")) : 0)) ? 1 : 0;
-  prm.epi_bufs = kTmaEpi ? ((prm.res != nullptr || prm.epi_db) ? 2 * EW : EW) : 0;
+  prm.epi_bufs = kTmaEpi ? (kBnb ? 3 * EW : ((prm.res != nullptr || prm.epi_db) ? 2 * EW : EW)) : 0;
   prm.res_mid = getenv("WLSEG_RES_MID") != nullptr ? atoi(getenv("WLSEG_RES_MID")) : 1;
   const int fixed = prm.epi_bufs * kWarpBufBytes + kBarBytes + (kTmaEpi ? 2 * BN * 4 : 0);
   int stages = (kSmemMax - fixed) / Cfg::kStageBytes;
@@ -800,21 +943,22 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   const int smem_bytes = stages * Cfg::kStageBytes + fixed;
   if constexpr (kPair) {
     static int max_pairs = -1;
-    if (max_pairs < 0) max_pairs = max_active_pairs(conv_igemm_kernel<BN, TY, kTmaEpi, EW, true>, 128 + 32 * EW, kSmemMax);
+    if (max_pairs < 0) max_pairs = max_active_pairs(conv_igemm_kernel<BN, TY, kTmaEpi, EW, true, kBnb>, 128 + 32 * EW, kSmemMax);
     WLSEG_CHECK_ARG(max_pairs > 0, "conv(tcgen05): the device cannot host a CTA pair of this kernel");
     prm.units = (int)ceil_div(prm.m_tiles, 2) * prm.n_tiles;
     int clusters = prm.units < max_pairs ? prm.units : max_pairs;
     if (clusters > conv_sms() / 2) clusters = conv_sms() / 2;
     if (prm.bn_sum != nullptr && clusters % prm.n_tiles != 0) clusters -= clusters % prm.n_tiles;
     WLSEG_CHECK_ARG(clusters > 0, "conv(tcgen05): no CTA pair fits the N-tile constraint of the fused statistics");
-    WLSEG_CUDA(launch_pair(conv_igemm_kernel<BN, TY, kTmaEpi, EW, true>, clusters, 128 + 32 * EW, smem_bytes, s, prm));
+    WLSEG_CUDA(launch_pair(conv_igemm_kernel<BN, TY, kTmaEpi, EW, true, kBnb>, clusters, 128 + 32 * EW, smem_bytes, s, prm));
     return 0;
   }
   prm.units = prm.total_tiles;
   int grid = prm.total_tiles < conv_sms() ? prm.total_tiles : conv_sms();
   // fused BN statistics live in registers across tiles: every CTA must stay on one N tile
   if (kTmaEpi && prm.bn_sum != nullptr && grid % prm.n_tiles != 0) grid -= grid % prm.n_tiles;
-  WLSEG_CUDA(launch_pdl(conv_igemm_kernel<BN, TY, kTmaEpi, EW, false>, dim3(grid), dim3(128 + 32 * EW), smem_bytes, s, prm));
+  WLSEG_CHECK_ARG(grid > 0, "conv(tcgen05): no CTA fits the N-tile constraint of the fused statistics");
+  WLSEG_CUDA(launch_pdl(conv_igemm_kernel<BN, TY, kTmaEpi, EW, false, kBnb>, dim3(grid), dim3(128 + 32 * EW), smem_bytes, s, prm));
   return 0;
 }
 
@@ -830,9 +974,13 @@ static int pair_mode() {
   return e != nullptr ? atoi(e) : -1;
 }
 
+// BN-backward form of a data gradient (wlseg_conv2d_fprop_bnbwd): z travels in the residual slot
+struct BnbArgs { const float* scale; const float* shift; const float* mean; const float* invstd; };
+
 static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const void* w, void* y, const float* scale,
                             const float* shift, const void* residual, double* bn_sum, double* bn_sqsum,
-                            cudaStream_t s, const uint32_t* out_mask = nullptr) {
+                            cudaStream_t s, const uint32_t* out_mask = nullptr, const BnbArgs* bnb = nullptr,
+                            const wlseg_bn_finalize_args* fin = nullptr) {
   WLSEG_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0, "conv(tcgen05): x / w must be 16-byte aligned");
   IgemmParams prm;
   const int BN = pick_bn(p->K);
@@ -872,7 +1020,12 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
     const int kblocks = p->R * p->S * (int)ceil_div(p->C, kBK);
     const bool pair_default = residual != nullptr ? kblocks >= 8 : kblocks >= 2;
     use_pair = (mode == 1) || (mode == -1 && pair_default);
+    // the BN-backward form keeps three staging buffers per warp: only the pair's 32 KB stages leave a deep enough ring
+    if (bnb != nullptr) use_pair = true;
   }
+  WLSEG_CHECK_ARG(bnb == nullptr || (tma_epi && residual != nullptr && BN >= kSubW && p->res_stride == 1 &&
+                                     bn_sum != nullptr && bn_sqsum != nullptr && scale == nullptr && p->relu == 0),
+                  "conv_fprop_bnbwd: needs the staged bf16 epilogue (K %% 64 == 0, 16-byte aligned y / z, pitches %% 8 == 0)");
   {
     uint64_t dims[3] = {(uint64_t)p->C, (uint64_t)(p->R * p->S), (uint64_t)p->K};
     uint64_t strides[2] = {(uint64_t)p->C * 2, (uint64_t)p->C * 2 * p->R * p->S};
@@ -902,6 +1055,16 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   prm.y = y; prm.scale = scale; prm.shift = shift; prm.res = residual;
   prm.bn_sum = bn_sum; prm.bn_sqsum = bn_sqsum;
   prm.out_mask = out_mask;
+  prm.bnb_scale = prm.bnb_shift = prm.bnb_mean = prm.bnb_invstd = nullptr;
+  prm.fin = wlseg_bn_finalize_args{};
+  if (fin != nullptr) {
+    WLSEG_CHECK_ARG(tma_epi && bn_sum != nullptr && bnb == nullptr && !pdl_enabled(),
+                    "conv_fprop_bn: needs the staged bf16 epilogue (K %% 64 == 0, aligned y) and no programmatic launches");
+    prm.fin = *fin;
+  }
+  if (bnb != nullptr) {
+    prm.bnb_scale = bnb->scale; prm.bnb_shift = bnb->shift; prm.bnb_mean = bnb->mean; prm.bnb_invstd = bnb->invstd;
+  }
   WLSEG_CHECK_ARG(out_mask == nullptr || (tma_epi && p->K % 32 == 0 && (((uintptr_t)out_mask) & 3) == 0),
                   "conv_fprop_masked: needs the staged bf16 epilogue (K %% 64 == 0, aligned tensors)");
   prm.N = p->N; prm.P = p->P; prm.Q = p->Q; prm.K = p->K; prm.C = p->C;
@@ -930,6 +1093,11 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
     if (f32out) return launch_igemm<bn, float, false>(prm, s);                        \
     if (bn >= kSubW && tma_epi) return launch_igemm<bn, __nv_bfloat16, (bn >= kSubW)>(prm, s); \
     return launch_igemm<bn, __nv_bfloat16, false>(prm, s);
+  if (bnb != nullptr) {
+    if (BN == 256) return launch_igemm_ew<256, __nv_bfloat16, true, 8, true, true>(prm, s);
+    if (BN == 128) return launch_igemm_ew<128, __nv_bfloat16, true, 8, false, true>(prm, s);
+    return launch_igemm_ew<64, __nv_bfloat16, true, 8, false, true>(prm, s);
+  }
   if (use_pair) return launch_igemm_ew<256, __nv_bfloat16, true, 8, true>(prm, s);
   switch (BN) {
     WLSEG_IGEMM_CASE(32)
@@ -963,6 +1131,34 @@ extern "C" int wlseg_conv2d_fprop_masked(const wlseg_conv_params* p, const void*
                     "conv_fprop_masked: residual geometry inconsistent");
   return conv_fprop_igemm(p, x, w, y, nullptr, nullptr, residual, nullptr, nullptr, (cudaStream_t)stream,
                           reinterpret_cast<const uint32_t*>(out_mask));
+}
+
+extern "C" int wlseg_conv2d_fprop_bnbwd(const wlseg_conv_params* p, const void* x, const void* w, void* y, const void* z,
+                                        const float* scale, const float* shift, const float* mean, const float* invstd,
+                                        double* dgamma, double* dbeta, wlseg_stream_t stream) {
+  if (int e = check_conv_params(p)) return e;
+  if (p->N == 0) return 0;
+  WLSEG_CHECK_ARG(x && w && y && z && scale && shift && mean && invstd && dgamma && dbeta, "conv_fprop_bnbwd: null pointer");
+  WLSEG_CHECK_ARG(igemm_supported(p) && p->y_dtype == WLSEG_BF16 && p->relu == 0 && p->K % 64 == 0,
+                  "conv_fprop_bnbwd: tcgen05 bf16 configurations with K %% 64 == 0 and without ReLU only");
+  WLSEG_CHECK_ARG(p->res_stride == 1 && p->res_pitch >= p->K && p->res_H == p->P && p->res_W == p->Q,
+                  "conv_fprop_bnbwd: z must have the output's shape (res_* fields of the parameters describe it)");
+  WLSEG_CHECK_ARG(((((uintptr_t)scale) | ((uintptr_t)shift)) & 15) == 0, "conv_fprop_bnbwd: scale / shift must be 16-byte aligned");
+  const BnbArgs bnb = {scale, shift, mean, invstd};
+  return conv_fprop_igemm(p, x, w, y, nullptr, nullptr, z, dgamma, dbeta, (cudaStream_t)stream, nullptr, &bnb);
+}
+
+extern "C" int wlseg_conv2d_fprop_bn(const wlseg_conv_params* p, const void* x, const void* w, void* y, double* bn_sum,
+                                     double* bn_sqsum, const wlseg_bn_finalize_args* fin, wlseg_stream_t stream) {
+  if (int e = check_conv_params(p)) return e;
+  if (p->N == 0) return 0;
+  WLSEG_CHECK_ARG(x && w && y && bn_sum && bn_sqsum && fin, "conv_fprop_bn: null pointer");
+  WLSEG_CHECK_ARG(fin->count > 0 && fin->gamma && fin->beta && fin->scale && fin->shift && fin->saved_mean &&
+                      fin->saved_invstd && fin->counter && ((fin->moving_mean == nullptr) == (fin->moving_var == nullptr)),
+                  "conv_fprop_bn: incomplete wlseg_bn_finalize_args");
+  WLSEG_CHECK_ARG(igemm_supported(p) && p->y_dtype == WLSEG_BF16 && p->relu == 0 && p->K % 64 == 0,
+                  "conv_fprop_bn: tcgen05 bf16 configurations with K %% 64 == 0 and without ReLU only");
+  return conv_fprop_igemm(p, x, w, y, nullptr, nullptr, nullptr, bn_sum, bn_sqsum, (cudaStream_t)stream, nullptr, nullptr, fin);
 }
 
 extern "C" int wlseg_conv2d_fprop(const wlseg_conv_params* p, const void* x, const void* w, void* y,

@@ -342,9 +342,15 @@ class Network:
     return pt, pl, P, Q
 
   def _conv(self, x, w, *, stride=1, dilation=1, pad=(0, 0), out_hw, scale=None, shift=None, relu=False,
-            residual=None, res_stride=1, y=None, y_dtype=None, bn_sum=None, bn_sqsum=None, out_mask=None):
+            residual=None, res_stride=1, y=None, y_dtype=None, bn_sum=None, bn_sqsum=None, out_mask=None, bnb=None,
+            fin=None):
+    """bnb = (z, scale, shift, mean, invstd, dgamma, dbeta): the BN-backward form of a data gradient
+    (ops.conv2d_fprop_bnbwd); z takes the residual slot of the parameters."""
     N, H, W, C = x.shape
     K = w.shape[0]
+    if bnb is not None:
+      assert residual is None and out_mask is None and scale is None and bn_sum is None and not relu
+      residual = bnb[0]
     reverse = False
     if self.snake and self.tape is None and scale is not None and bn_sum is None:
       self._snake_flip = not self._snake_flip   # inference layers only (folded BN): alternate
@@ -364,13 +370,22 @@ class Network:
              'flops': 2.0 * N * out_hw[0] * out_hw[1] * w.shape[1] * w.shape[2] * C * K,
              'bytes': float(esz * (N * H * W * C + w.numel()) + y.element_size() * N * out_hw[0] * out_hw[1] * K +
                             (esz * N * out_hw[0] * out_hw[1] * K if residual is not None else 0)),
-             'sig': (N, H, W, C, K, w.shape[1], stride, dilation, residual is not None, bn_sum is not None, 'fprop'),
+             'sig': (N, H, W, C, K, w.shape[1], stride, dilation, residual is not None, bn_sum is not None or bnb is not None,
+                     'fprop'),
              'e0': torch.cuda.Event(enable_timing=True), 'e1': torch.cuda.Event(enable_timing=True)}
       rec['e0'].record()
     if bn_sum is not None and not tc:
       # direct kernel: statistics from the stored output instead of the accumulators
       ops.conv2d_fprop(prm, x, w, y, scale, shift, residual)
       ops.bn_stats(y, N * out_hw[0] * out_hw[1], K, y.stride(2), bn_sum, bn_sqsum)
+      if fin is not None:
+        ops.bn_finalize(bn_sum, bn_sqsum, fin[0], K, *fin[1:-1])
+    elif fin is not None:
+      # statistics + finalisation in the convolution launch (fin = the arguments of ops.bn_finalize after the sums)
+      assert scale is None and residual is None and not relu
+      ops.conv2d_fprop_bn(prm, x, w, y, bn_sum, bn_sqsum, *fin)
+    elif bnb is not None:
+      ops.conv2d_fprop_bnbwd(prm, x, w, y, *bnb)
     elif out_mask is not None:
       assert scale is None and bn_sum is None and not relu
       ops.conv2d_fprop_masked(prm, x, w, y, residual, out_mask)
@@ -639,6 +654,7 @@ class TrainWorkspace:
     self.losses = torch.zeros(4, dtype=torch.float32, device=dev)
     self.reg_loss = torch.zeros(1, dtype=torch.float64, device=dev)
     self.lr = torch.zeros(1, dtype=torch.float32, device=dev)
+    self.fin_counter = torch.zeros(1, dtype=torch.int32, device=dev)   # ops.conv2d_fprop_bn's ticket word (left at zero)
     self.n = n
 
   def view(self, arena, slot, off, k):
@@ -682,6 +698,18 @@ class TrainNetwork(Network):
     # neither reads the activation nor writes a separate shortcut gradient (it IS the masked tensor): 3 of the 8
     # tensor passes of every residual layer's BN backward.  WLSEG_RELU_MASK=0 restores the unmasked wiring.
     self.premask = os.environ.get('WLSEG_RELU_MASK', '1') != '0'
+    # BN backward reduction fused into the dgrad that produces the gradient it reduces (ops.conv2d_fprop_bnbwd): inside a
+    # bottleneck unit the dgrad of conv3 / conv2 multiplies its output by the ReLU derivative of conv2 / conv1's BN and
+    # accumulates that layer's dgamma / dbeta, so 32 of the 61 bn_bwd_reduce passes of a step are never launched.
+    # WLSEG_BNB_FUSE=0 restores the separate passes.
+    self.bnb_fuse = os.environ.get('WLSEG_BNB_FUSE', '1') != '0'
+    # bn_finalize inside the convolution launch that produces the statistics (ops.conv2d_fprop_bn: the last CTA to
+    # commit its sums finalises): 61 launches of ~3 us less per step - and a measured NEGATIVE, 11.00 -> 11.18 ms/step
+    # (357.7 against 363.6 images/s, A/B on one box): every CTA pays a __threadfence behind its fp64 atomics plus two
+    # barriers, and the finalisation's dependent fp64 chain (L2 loads -> divisions -> rsqrt) runs on ONE SM behind
+    # the grid's tail instead of next to it; the convolution launches grew by more (+0.33 ms) than the 0.21 ms the
+    # bn_finalize launches cost.  Kept as an opt-in: WLSEG_BN_FIN_IN_CONV=1.
+    self.fin_in_conv = os.environ.get('WLSEG_BN_FIN_IN_CONV', '0') == '1'
 
   def _mark_done(self, scope, n_elems):
     """Bookkeeping for the gradient exchange: backward completes the arena roughly tail first."""
@@ -716,10 +744,16 @@ class TrainNetwork(Network):
     s1, s2 = ws.view(ws.stat, 0, off, K), ws.view(ws.stat, 1, off, K)
     zdt = torch.float32 if y_f32 else self.dtype
     group = self.p.norm == 'group'
-    z = self._conv(x, w, stride=stride, dilation=dilation, pad=pad, out_hw=out_hw, y_dtype=zdt,
-                   bn_sum=None if group else s1, bn_sqsum=None if group else s2)
     scale, shift = ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K)
     mean, invstd = ws.view(ws.bn, 2, off, K), ws.view(ws.bn, 3, off, K)
+    fin = None
+    if (self.fin_in_conv and not group and self.cross_replica is None and not self.fused_bn_finalize and not y_f32 and
+        self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT and K % 64 == 0 and x.shape[3] % 8 == 0 and
+        x.stride(2) % 8 == 0 and not ops.pdl_enabled()):
+      fin = (count, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay, self.p.moving_mean(scope, K),
+             self.p.moving_var(scope, K), scale, shift, mean, invstd, ws.fin_counter)
+    z = self._conv(x, w, stride=stride, dilation=dilation, pad=pad, out_hw=out_hw, y_dtype=zdt,
+                   bn_sum=None if group else s1, bn_sqsum=None if group else s2, fin=fin)
     a = torch.empty_like(z)
     do_relu = spec.relu if relu is None else relu
     gn = None
@@ -741,8 +775,9 @@ class TrainNetwork(Network):
                             self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd,
                             z, residual, a, do_relu, mask=mask)
     else:
-      ops.bn_finalize(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
-                      self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd)
+      if fin is None:
+        ops.bn_finalize(s1, s2, count, K, self.p.gamma(scope, K), self.p.beta(scope, K), self.eps, self.bn_decay,
+                        self.p.moving_mean(scope, K), self.p.moving_var(scope, K), scale, shift, mean, invstd)
       if want_mask and do_relu and K % 32 == 0 and K <= 2048 and z.is_contiguous():
         mask = torch.empty((count, K // 8), dtype=torch.uint8, device=self.dev)
       ops.bn_apply(z, scale, shift, residual, a, count, K, do_relu, mask=mask)
@@ -811,13 +846,33 @@ class TrainNetwork(Network):
       n *= d
     return self.ws.grads[o:o + n].view(*shape)
 
-  def _layer_bwd(self, scope, da, need_dx=True, dx_out=None, dx_add=None, da_masked=False, dx_mask=None):
+  def _bnb_args(self, scope):
+    """-> the bnb tuple of `scope` (the layer whose OUTPUT activation a dgrad differentiates), or None when the fused
+    form does not cover it."""
+    if not (self.bnb_fuse and not self.keep and self.dtype == torch.bfloat16 and self.conv_algo != ops.ALGO_DIRECT and
+            self.p.norm == 'batch' and self.cross_replica is None):
+      return None
+    rec = self.tape[scope]
+    K = rec.nch
+    if not (rec.relu and not rec.has_res and K % 64 == 0 and rec.z.is_contiguous() and rec.z.dtype == torch.bfloat16):
+      return None
+    ws, off = self.ws, self.p.c_off[scope]
+    if off % 4 != 0:
+      return None   # scale / shift are read as float4
+    return (rec.z, ws.view(ws.bn, 0, off, K), ws.view(ws.bn, 1, off, K), ws.view(ws.bn, 2, off, K),
+            ws.view(ws.bn, 3, off, K), ws.view(ws.stat, 2, off, K), ws.view(ws.stat, 3, off, K))
+
+  def _layer_bwd(self, scope, da, need_dx=True, dx_out=None, dx_add=None, da_masked=False, dx_mask=None,
+                 da_reduced=False, bnb_below=None):
     """Backward of one tape entry.  Returns (dx, dres): dres is the gradient of the residual input
     (None if the layer had none).  `dx_add` is accumulated into dx (fused into the tensor-core
     dgrad epilogue when possible); `dx_out` lets the caller place dx (channel-sliced views).
     da_masked: `da` already carries this layer's ReLU derivative (its producer applied rec.mask): the BN backward
     reads da and z only and dres is da itself.  dx_mask: ReLU bit mask of the tensor dx belongs to, applied by
-    the dgrad epilogue (dx + dx_add is that tensor's COMPLETE gradient)."""
+    the dgrad epilogue (dx + dx_add is that tensor's COMPLETE gradient).
+    da_reduced: the dgrad that produced `da` ran in the BN-backward form - da carries this layer's ReLU derivative and
+    dgamma / dbeta are already accumulated: only bn_bwd_apply runs.  bnb_below: scope of the layer that produced this
+    layer's INPUT; this layer's dgrad then runs in that form for it (the caller passes da_reduced to it)."""
     rec = self.tape[scope]
     ws, off, K = self.ws, self.p.c_off[scope], rec.nch
     pad, out_hw, stride, dilation = rec.geom
@@ -833,6 +888,12 @@ class TrainNetwork(Network):
       return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add)
     dz = torch.empty_like(rec.z)
     relu = rec.relu
+    if da_reduced:
+      assert not rec.has_res and rec.relu and da.is_contiguous() and not da_masked
+      dres, relu = None, False
+      ops.bn_bwd_apply(da, None, rec.z, mean, invstd, gamma, dgamma, dbeta, count, K, False, dz, None, scale=scale,
+                       shift=shift, pitch=K)
+      return self._layer_bwd_convs(rec, scope, da, dz, None, K, need_dx, dx_out, dx_add, dx_mask, bnb_below)
     if da_masked:
       assert rec.has_res and rec.relu and da.is_contiguous()
       dres, relu = da, False          # g = da: nothing left to mask, and it is the shortcut's gradient as it stands
@@ -864,9 +925,9 @@ class TrainNetwork(Network):
       ops.bn_bwd_apply(da[..., sl], None if y is None else y[..., sl], rec.z[..., sl], mean[sl], invstd[sl], gamma[sl],
                        dgamma[sl], dbeta[sl], count, kk, relu, dz[..., sl],
                        None if (dres is None or da_masked) else dres[..., sl], scale=scale[sl], shift=shift[sl], pitch=K)
-    return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add, dx_mask)
+    return self._layer_bwd_convs(rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add, dx_mask, bnb_below)
 
-  def _layer_bwd_convs(self, rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add, dx_mask=None):
+  def _layer_bwd_convs(self, rec, scope, da, dz, dres, K, need_dx, dx_out, dx_add, dx_mask=None, bnb_below=None):
     """Second half of _layer_bwd: filter gradient and data gradient from dz (normaliser independent)."""
     pad, out_hw, stride, dilation = rec.geom
     N, H, W, C = rec.x.shape
@@ -933,7 +994,12 @@ class TrainNetwork(Network):
       else:
         dzu = dz
       fpad = (dilation * (R - 1) - pad[0], dilation * (S - 1) - pad[1])
-      self._conv(dzu, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx, out_mask=dx_mask)
+      bnb = None
+      if bnb_below is not None:
+        assert dx_add is None and dx_mask is None and dx_out is None
+        bnb = self._bnb_args(bnb_below)
+        assert bnb is not None, 'the caller checks _bnb_args first'
+      self._conv(dzu, wf, dilation=dilation, pad=fpad, out_hw=(H, W), residual=dx_add, y=dx, out_mask=dx_mask, bnb=bnb)
       done = True
     if not done:
       assert dx_mask is None, 'the masked data gradient exists on the tensor-core path only'
@@ -1012,17 +1078,20 @@ class TrainNetwork(Network):
     in_mask: ReLU bit mask of the unit's INPUT tensor (the previous unit's output) - the dgrad that completes dx
     applies it.  -> dx"""
     x = self.tape[u.scope]
-    dr, dsc = self._layer_bwd(f'{u.scope}/conv3', dout, da_masked=dout_masked)
-    dr, _ = self._layer_bwd(f'{u.scope}/conv2', dr)
+    c1, c2 = f'{u.scope}/conv1', f'{u.scope}/conv2'
+    f2 = self._bnb_args(c2) is not None   # conv3's dgrad reduces conv2's BN backward, conv2's dgrad conv1's
+    f1 = self._bnb_args(c1) is not None
+    dr, dsc = self._layer_bwd(f'{u.scope}/conv3', dout, da_masked=dout_masked, bnb_below=c2 if f2 else None)
+    dr, _ = self._layer_bwd(c2, dr, da_reduced=f2, bnb_below=c1 if f1 else None)
     if u.has_shortcut_conv:
-      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr)
+      dx, _ = self._layer_bwd(c1, dr, da_reduced=f1)
       dx, _ = self._layer_bwd(f'{u.scope}/shortcut', dsc, dx_add=dx, dx_mask=in_mask)
     elif u.stride > 1:
       dsub = torch.empty_like(x)
       ops.maxpool_same_bwd(x, dsc, dsub, 1, u.stride)
-      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsub, dx_mask=in_mask)
+      dx, _ = self._layer_bwd(c1, dr, dx_add=dsub, dx_mask=in_mask, da_reduced=f1)
     else:
-      dx, _ = self._layer_bwd(f'{u.scope}/conv1', dr, dx_add=dsc, dx_mask=in_mask)
+      dx, _ = self._layer_bwd(c1, dr, dx_add=dsc, dx_mask=in_mask, da_reduced=f1)
     return dx
 
   # ---- whole network -----------------------------------------------------------------------------------

@@ -33,6 +33,14 @@ class ConvParams(ctypes.Structure):
       'accumulate', 'reverse')]
 
 
+class BnFinalizeArgs(ctypes.Structure):
+  _fields_ = [('count', ctypes.c_int64), ('eps', ctypes.c_float), ('decay', ctypes.c_float),
+              ('moving_var_factor', ctypes.c_float), ('reserved', ctypes.c_int32),
+              ('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p), ('moving_mean', ctypes.c_void_p),
+              ('moving_var', ctypes.c_void_p), ('scale', ctypes.c_void_p), ('shift', ctypes.c_void_p),
+              ('saved_mean', ctypes.c_void_p), ('saved_invstd', ctypes.c_void_p), ('counter', ctypes.c_void_p)]
+
+
 class Hierarchy(ctypes.Structure):
   _fields_ = [('C1', _c_int), ('Cv', _c_int), ('Ch', _c_int),
               ('cid_l1_vehicle', _c_int), ('cid_l1_human', _c_int),
@@ -57,6 +65,9 @@ _SIGNATURES = {
     'wlseg_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _vp]),
     'wlseg_bn_apply_mask': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _vp]),
     'wlseg_conv2d_fprop_masked': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp, _vp, _vp]),
+    'wlseg_conv2d_fprop_bnbwd': (ctypes.c_int, [ctypes.POINTER(ConvParams)] + [_vp] * 11),
+    'wlseg_conv2d_fprop_bn': (ctypes.c_int, [ctypes.POINTER(ConvParams), _vp, _vp, _vp, _vp, _vp,
+                                             ctypes.POINTER(BnFinalizeArgs), _vp]),
     'wlseg_bn_bwd_reduce': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, _c_int,
                                            _vp, _vp, _vp]),
     'wlseg_bn_bwd_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, _c_int,
@@ -195,6 +206,32 @@ def conv2d_fprop_masked(p, x, w, y, residual, out_mask):
   _count()
   _check(lib().wlseg_conv2d_fprop_masked(ctypes.byref(p), _ptr(x), _ptr(w), _ptr(y), _ptr(residual), _ptr(out_mask),
                                          _stream()), 'wlseg_conv2d_fprop_masked')
+
+
+def pdl_enabled():
+  """Mirror of pdl_enabled() in csrc/abi.cu (programmatic dependent launches, opt-in)."""
+  return os.environ.get('WLSEG_PDL') is not None
+
+
+def conv2d_fprop_bn(p, x, w, y, bn_sum, bn_sqsum, count, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift,
+                    saved_mean, saved_invstd, counter, moving_var_factor=-1.0):
+  """conv2d_fprop with fused statistics + bn_finalize in one launch (the last CTA finalises); counter: one zeroed
+  int32 device word shared by the layers of a stream."""
+  fin = BnFinalizeArgs(count, eps, decay, moving_var_factor, 0, _ptr(gamma), _ptr(beta), _ptr(moving_mean),
+                       _ptr(moving_var), _ptr(scale), _ptr(shift), _ptr(saved_mean), _ptr(saved_invstd), _ptr(counter))
+  _count()
+  _check(lib().wlseg_conv2d_fprop_bn(ctypes.byref(p), _ptr(x), _ptr(w), _ptr(y), _ptr(bn_sum), _ptr(bn_sqsum),
+                                     ctypes.byref(fin), _stream()), 'wlseg_conv2d_fprop_bn')
+  return y
+
+
+def conv2d_fprop_bnbwd(p, x, w, y, z, scale, shift, mean, invstd, dgamma, dbeta):
+  """y = conv(x, w) * relu'(z * scale + shift), with the BN backward sums of (y, z) accumulated into dgamma / dbeta
+  by the epilogue (the res_* fields of p describe z)."""
+  _count()
+  _check(lib().wlseg_conv2d_fprop_bnbwd(ctypes.byref(p), _ptr(x), _ptr(w), _ptr(y), _ptr(z), _ptr(scale), _ptr(shift),
+                                        _ptr(mean), _ptr(invstd), _ptr(dgamma), _ptr(dbeta), _stream()),
+         'wlseg_conv2d_fprop_bnbwd')
 
 
 def conv2d_dgrad(p, dy, w, dx):

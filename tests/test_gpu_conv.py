@@ -280,3 +280,108 @@ def test_conv_wgrad_tcgen05(cuda, case, pair, monkeypatch):
   err = float((dw.cpu() - w.grad).abs().max()) / float(w.grad.abs().max())
   print(f'wgrad {case}: max-rel {err:.3e}')
   assert err <= 2e-3
+
+
+BNB_CASES = [
+    # N, H, W, C, K, R, dilation       (K = channels of the tensor whose gradient leaves: BN tile 64 / 128 / 256 / pair)
+    (2, 24, 40, 64, 64, 3, 1),         # block1 conv2 dgrad, BN = 64
+    (2, 20, 24, 512, 128, 1, 1),       # block2 conv3 dgrad, BN = 128
+    (1, 19, 27, 128, 128, 3, 1),       # ragged spatial size: partial tiles must not reach the sums
+    (2, 24, 24, 1024, 256, 1, 1),      # block3 conv3 dgrad, BN = 256 (CTA pair), 16 k-blocks
+    (1, 16, 24, 256, 256, 3, 2),       # block3 conv2 dgrad, dilated
+    (1, 17, 24, 512, 512, 3, 4),       # block4 conv2 dgrad, two N tiles
+    (1, 24, 40, 256, 256, 1, 1),       # 15 M tiles: the last pair's second CTA runs a phantom tile
+    (4, 96, 96, 256, 256, 3, 2),       # BASELINE size: 288 M tiles, 2 units per CTA pair (z ring + staging reuse across tiles)
+    (2, 128, 136, 64, 64, 3, 1),       # 306 tiles on 148 single CTAs, ragged width
+]
+
+
+@pytest.mark.parametrize('case', BNB_CASES)
+def test_fprop_bnbwd_equals_conv_then_bn_bwd_reduce(cuda, case):
+  """wlseg_conv2d_fprop_bnbwd (the dgrad epilogue applies the ReLU derivative of the BN layer below and accumulates
+  its dgamma / dbeta) against the two launches it replaces: wlseg_conv2d_fprop, then wlseg_bn_bwd_reduce with the
+  mask recomputed from z.  The masked gradient must be BIT-IDENTICAL to mask(bf16(conv)) - rounding and masking
+  commute - and the sums agree to fp32 summation-order noise (1e-5 of the sum of magnitudes)."""
+  from wlseg import ops
+  N, H, W, C, K, R, dil = case
+  g = torch.Generator().manual_seed(sum(case))
+  dt = torch.bfloat16
+  x = torch.randn(N, H, W, C, generator=g).to(dt).to(cuda)
+  w = (torch.randn(K, R, R, C, generator=g) / (R * R * C) ** 0.5).to(dt).to(cuda)
+  z = torch.randn(N, H, W, K, generator=g).to(dt).to(cuda)
+  scale = (0.5 + torch.rand(K, generator=g)).to(cuda)
+  shift = (torch.randn(K, generator=g) * 0.3).to(cuda)
+  mean = (torch.randn(K, generator=g) * 0.2).to(cuda)
+  invstd = (0.5 + torch.rand(K, generator=g)).to(cuda)
+  pad = dil * (R - 1) // 2
+  count = N * H * W
+  code = ops.dtype_code(dt)
+  # unfused: convolution, then the reduction pass (mask from the sign of z * scale + shift)
+  y0 = torch.empty((N, H, W, K), dtype=dt, device=cuda)
+  prm0 = ops.conv_params((N, H, W, C), (K, R, R, C), dilation=dil, pad=(pad, pad), out_hw=(H, W), dtype=code)
+  ops.conv2d_fprop(prm0, x, w, y0)
+  dg0 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  db0 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  ops.bn_bwd_reduce(y0, None, z, mean, invstd, count, K, True, dg0, db0, scale=scale, shift=shift, pitch=K)
+  # fmaf(z, scale, shift) is the correctly rounded value of the exact real number z * scale + shift, so its sign is the
+  # sign of that number: evaluated here in fp64, where product and sum of these operands are exact
+  on = (z.double() * scale.double() + shift.double()) > 0
+  # fused
+  y1 = torch.full((N, H, W, K), float('nan'), dtype=dt, device=cuda)
+  dg1 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  db1 = torch.zeros(K, dtype=torch.float64, device=cuda)
+  prm1 = ops.conv_params((N, H, W, C), (K, R, R, C), dilation=dil, pad=(pad, pad), out_hw=(H, W), dtype=code, res=z,
+                         res_stride=1)
+  ops.conv2d_fprop_bnbwd(prm1, x, w, y1, z, scale, shift, mean, invstd, dg1, db1)
+  torch.cuda.synchronize()
+  want = torch.where(on, y0, torch.zeros_like(y0))
+  diff = (y1.float() - want.float()).abs()
+  assert int((diff > 0).sum()) == 0, f'masked gradient differs at {int((diff > 0).sum())} elements (max {float(diff.max()):.3e})'
+  mag_b = (want.float().abs().double()).sum((0, 1, 2))
+  mag_g = (want.float().abs().double() * ((z.float() - mean).abs() * invstd).double()).sum((0, 1, 2))
+  eb = float(((db1 - db0).abs() / (mag_b + 1e-12)).max())
+  eg = float(((dg1 - dg0).abs() / (mag_g + 1e-12)).max())
+  print(f'bnbwd {case}: dbeta err {eb:.2e}, dgamma err {eg:.2e} (relative to the sum of magnitudes)')
+  assert eb <= 1e-5 and eg <= 1e-5
+
+
+@pytest.mark.parametrize('case', [(2, 24, 40, 64, 64, 3, 1), (2, 20, 24, 128, 512, 1, 1), (4, 96, 96, 256, 256, 3, 2),
+                                  (1, 17, 24, 512, 2048, 1, 1)])
+def test_fprop_bn_equals_conv_then_bn_finalize(cuda, case):
+  """wlseg_conv2d_fprop_bn (the last CTA of the convolution grid finalises the batch norm) against the two launches
+  it replaces, wlseg_conv2d_fprop with fused statistics + wlseg_bn_finalize: same raw output bit for bit, scale / shift
+  / saved mean / inverse std / moving statistics to 1e-6 (the fp64 atomics commit in another order); the ticket word
+  is left at zero, so that consecutive layers share it."""
+  from wlseg import ops
+  N, H, W, C, K, R, dil = case
+  g = torch.Generator().manual_seed(sum(case) + 1)
+  dt = torch.bfloat16
+  x = torch.randn(N, H, W, C, generator=g).to(dt).to(cuda)
+  w = (torch.randn(K, R, R, C, generator=g) / (R * R * C) ** 0.5).to(dt).to(cuda)
+  gamma = (0.5 + torch.rand(K, generator=g)).to(cuda)
+  beta = (torch.randn(K, generator=g) * 0.3).to(cuda)
+  pad = dil * (R - 1) // 2
+  count = N * H * W
+  prm = ops.conv_params((N, H, W, C), (K, R, R, C), dilation=dil, pad=(pad, pad), out_hw=(H, W), dtype=ops.dtype_code(dt))
+  counter = torch.zeros(1, dtype=torch.int32, device=cuda)
+  outs = []
+  for fused in (False, True, True):     # the second fused call reuses the counter
+    y = torch.full((N, H, W, K), float('nan'), dtype=dt, device=cuda)
+    s1 = torch.zeros(K, dtype=torch.float64, device=cuda)
+    s2 = torch.zeros(K, dtype=torch.float64, device=cuda)
+    mm = torch.full((K,), 0.25, device=cuda)
+    mv = torch.full((K,), 1.5, device=cuda)
+    o = [torch.full((K,), float('nan'), device=cuda) for _ in range(4)]
+    if fused:
+      ops.conv2d_fprop_bn(prm, x, w, y, s1, s2, count, gamma, beta, 1e-5, 0.9, mm, mv, o[0], o[1], o[2], o[3], counter)
+    else:
+      ops.conv2d_fprop(prm, x, w, y, bn_sum=s1, bn_sqsum=s2)
+      ops.bn_finalize(s1, s2, count, K, gamma, beta, 1e-5, 0.9, mm, mv, o[0], o[1], o[2], o[3])
+    torch.cuda.synchronize()
+    assert int(counter.item()) == 0
+    outs.append((y.cpu(), [t.cpu() for t in o + [mm, mv]]))
+  for y, vec in outs[1:]:
+    assert torch.equal(y, outs[0][0])
+    for name, a, b in zip(('scale', 'shift', 'mean', 'invstd', 'moving_mean', 'moving_var'), vec, outs[0][1]):
+      err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+      assert err <= 1e-6, f'{name}: {err:.2e}'

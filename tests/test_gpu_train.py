@@ -334,3 +334,64 @@ def test_premasked_residual_gradient_equals_unmasked_wiring(cuda):
   cos = float(torch.dot(g1.double(), g0.double()) / (g1.double().norm() * g0.double().norm()))
   print(f'masked vs unmasked gradient arena: max-rel {err:.2e} (unmasked run-to-run {noise:.2e}), cosine {cos:.10f}')
   assert err <= max(4.0 * noise, 1e-5) and cos >= 0.9999999
+
+
+def test_fused_bn_backward_reduction_equals_separate_passes(cuda):
+  """WLSEG_BNB_FUSE wiring (TrainNetwork.bnb_fuse: inside a bottleneck unit the dgrad of conv3 / conv2 runs as
+  wlseg_conv2d_fprop_bnbwd for the BN of conv2 / conv1, whose bn_bwd_reduce pass is never launched) against the
+  separate passes, as backward passes over ONE forward tape.
+  The masked gradients are bit-identical (tests/test_gpu_conv.py::test_fprop_bnbwd_...), but the fused sums are fp32
+  partials in another order than bn_reduce_kernel's: dgamma / dbeta differ by ~1e-7, which flips a few bf16 roundings
+  of dz, and a train-mode BN ResNet amplifies any perturbation on its way down (~x300 end to end at plain random init,
+  tests/test_gpu_baseline_shapes.py::_conditioned_params).  Hence: (a) 32 launches fewer; (b) the FIRST fused unit
+  of the backward pass (block4/unit_3, nothing amplified yet) is tight - conv2's dgamma / dbeta 1e-5 of their
+  maximum, its filter gradient 1e-3; (c) on the conditioned network the whole arena agrees to cosine >= 0.9999."""
+  from wlseg import hierarchy, network, ops, problem_defs
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  # the conditioning of tests/test_gpu_baseline_shapes.py::_conditioned_params: residual-branch gammas x 0.2
+  tf_params = onet.init_params('cityscapes', seed=17, randomize_bn=True, tame=True)
+  for k in tf_params:
+    if k.endswith('conv3/BatchNorm/gamma') and 'bottleneck' in k:
+      tf_params[k] = tf_params[k] * 0.2
+  g = torch.Generator().manual_seed(23)
+  H, W = 192, 264
+  images = (torch.rand(2, H, W, 3, generator=g) * 2 - 1).to(cuda)
+  labels = {k: v.to(cuda) for k, v in _labels('cityscapes', 2, 0, 0, H, W, 20).items()}
+  params = network.Params(hier, cuda)
+  params.load_tf_dict(tf_params)
+  net = network.TrainNetwork(params, dtype=torch.bfloat16)
+  assert net.bnb_fuse
+  logits = net.forward_train(images)
+  losses, dlogits = net.loss_and_grad(logits, labels, H, W)
+  n = params.n_chan_pad
+  runs, launches = [], []
+  for flag in (True, False, False):
+    net.bnb_fuse = flag
+    net.ws.stat[2 * n:].zero_()          # dgamma / dbeta accumulators (forward_train zeroes them once per step)
+    l0 = ops.launches
+    runs.append(net.backward(dlogits).cpu().clone())
+    launches.append(ops.launches - l0)
+  torch.cuda.synchronize()
+  assert launches[1] - launches[0] == 32, f'expected 32 fewer launches in the fused form, got {launches}'
+  g1, g0, g0b = runs
+
+  def rel(scope, what):
+    sp = params.by_scope[scope]
+    if what == 'dw':
+      o, k = params.w_off[scope], sp.K * sp.R * sp.S * sp.C
+    else:
+      o, k = params.n_conv_pad + (n if what == 'dbeta' else 0) + params.c_off[scope], sp.K
+    a, b = g1[o:o + k], g0[o:o + k]
+    return float((a - b).abs().max() / b.abs().max())
+
+  u = 'feature_extractor/base/resnet_v1_50/block4/unit_3/bottleneck_v1'
+  first = {w: rel(f'{u}/conv2', w) for w in ('dgamma', 'dbeta', 'dw')}
+  second = {w: rel(f'{u}/conv1', w) for w in ('dgamma', 'dbeta', 'dw')}
+  scale = float(g0.abs().max())
+  noise = float((g0 - g0b).abs().max()) / scale
+  err = float((g1 - g0).abs().max()) / scale
+  cos = float(torch.dot(g1.double(), g0.double()) / (g1.double().norm() * g0.double().norm()))
+  print(f'fused vs separate BN backward reduction: first fused layer {first}, next {second}; gradient arena max-rel {err:.2e} '
+        f'(separate run-to-run {noise:.2e}), cosine {cos:.8f}')
+  assert first['dgamma'] <= 1e-5 and first['dbeta'] <= 1e-5 and first['dw'] <= 1e-3
+  assert cos >= 0.9999

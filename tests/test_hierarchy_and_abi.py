@@ -60,6 +60,7 @@ def test_library_loads_and_exports_every_declared_symbol():
   assert lib.wlseg_version() == 100
   assert ctypes.sizeof(ops.Hierarchy) == 4 * (5 + 64 + 16 + 8 + 1 + 240 + 30)
   assert ctypes.sizeof(ops.ConvParams) == 4 * 25   # 24 fields of round-1 start + `reverse`
+  assert ctypes.sizeof(ops.BnFinalizeArgs) == 8 + 4 * 4 + 9 * 8   # wlseg_bn_finalize_args: count, 3 floats + pad, 9 pointers
 
 
 def test_invalid_arguments_are_reported_not_crashed():
