@@ -300,6 +300,18 @@ int wlseg_head_fwd(const wlseg_hierarchy* hier, const float* logits, int32_t log
                    float* l2v_probs, float* l2h_probs, float* fullres_logits,
                    wlseg_stream_t stream);
 
+/* Evaluation step tail in ONE launch: x8 bilinear upsample + three arg-maxima + hierarchical composition
+ * (models/resnet50_extended_model_hierarchical.py:84-117) fused with the streaming confusion matrix
+ * (estimator/define_estimator_hierarchical.py:185-194) and the decisions part of _map_predictions_to_new_cids (:511-514,
+ * `lut`).  cm[label, lut[decision]] += 1 for every pixel, bit-exact (integer); out-of-range pairs are skipped and counted
+ * in *invalid (may be NULL).  decisions (int32 [N,H,W]) is optional: NULL = the decisions never touch HBM.
+ * labels NULL = decisions only.  Decisions are bit-identical to wlseg_head_fwd's.  Hierarchies other than 14/7/3 and
+ * 53/12/5, or an upsampling factor below 2, fall back to wlseg_head_fwd + wlseg_confmat_accumulate and need the
+ * decisions buffer. */
+int wlseg_head_confmat(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch, int32_t N, int32_t h,
+                       int32_t w, int32_t H, int32_t W, const int32_t* labels, int32_t num_classes, const int32_t* lut,
+                       int32_t lut_size, int64_t* cm, int64_t* invalid, int32_t* decisions, wlseg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Prediction post-processing (estimator/define_estimator_hierarchical.py:530-571 `_resize_predictions`,
  * :573-630 `_replace_voids`), used by the EVAL branch when labels and network differ in size and by the

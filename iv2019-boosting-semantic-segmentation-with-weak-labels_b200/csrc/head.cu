@@ -321,6 +321,210 @@ static int launch_head_cols(const wlseg_hierarchy* hier, HeadArgs& a, cudaStream
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Evaluation head: decisions and / or the confusion matrix, nothing else (define_estimator EVAL,
+// code/estimator/define_estimator_hierarchical.py:161-202: argmax composition -> _streaming_confusion_matrix).
+// Same column walk and the same arithmetic as head_fwd_cols_kernel (bit-identical decisions), trimmed for the
+// evaluation step - ncu on the general kernel (profiles/r2_head_loss_ncu.md): 247 instructions per pixel, only
+// ~110 of them the interpolation and the three arg-maxima:
+//   * the y-interpolation keeps `bot - top` in registers (one FFMA per channel and pixel instead of FADD + FFMA);
+//   * the L2 heads are interpolated and arg-maxed only in rows where some lane of the warp decided the L1 vehicle /
+//     human super-class (the composition reads them nowhere else);
+//   * one output pointer advanced per row, no per-map branches;
+//   * the confusion matrix is fused: label and decision meet in registers, a thread merges its vertical run of equal
+//     (label, decision) pairs and commits it to the CTA's shared int32 histogram once per run; the histogram is
+//     flushed with 64-bit global atomics (integer, order independent: bit-exact).  The 8 B/pixel round trip of the
+//     decisions through HBM (4 written here + 4 read by confmat_kernel) disappears when the caller asks for the
+//     matrix only.
+constexpr int kEvalTX = 128;
+constexpr int kEvalTY = 32;
+
+struct HeadEvalArgs {
+  const float* logits;
+  int N, h, w, H, W, cp;
+  float sy, sx;
+  int ph, pw;
+  int32_t* decisions;          // may be NULL
+  const int32_t* labels;       // may be NULL (no confusion matrix)
+  int num_classes;
+  const int32_t* lut;          // decisions -> evaluation class ids, may be NULL
+  int lut_size;
+  unsigned long long* cm;
+  unsigned long long* invalid;
+};
+
+template <int LO, int C, int CT>
+__device__ __forceinline__ void eval_load_rows(const float* __restrict__ rt, const float* __restrict__ rb, int o0, int o1,
+                                               float lx, float (&top)[CT], float (&dlt)[CT]) {
+#pragma unroll
+  for (int c = LO; c < LO + C; ++c) {
+    const float tl = rt[o0 + c], tr = rt[o1 + c];
+    const float bl = rb[o0 + c], br = rb[o1 + c];
+    const float t = tl + (tr - tl) * lx;   // TF ResizeBilinear: top = tl + (tr - tl) * x_lerp
+    const float b = bl + (br - bl) * lx;
+    top[c] = t;
+    dlt[c] = b - t;
+  }
+}
+
+// kCm: accumulate the confusion matrix; kLut: decisions pass through a.lut first; kDec: store the decisions
+template <int C1, int CV, int CH, bool kCm, bool kLut, bool kDec>
+__global__ void __launch_bounds__(kEvalTX, (C1 + CV + CH <= 32) ? 4 : 1)
+head_eval_kernel(const __grid_constant__ wlseg_hierarchy hier, const HeadEvalArgs a) {
+  constexpr int CT = C1 + CV + CH;
+  extern __shared__ float patch[];   // [ph][pw][CT], then the int32 histogram [num_classes^2] and the label tile [TY][TX]
+  const int cells = a.ph * a.pw;
+  int32_t* hist = reinterpret_cast<int32_t*>(patch + cells * CT);
+  int32_t* slab = hist + a.num_classes * a.num_classes;
+  __shared__ unsigned s_bad;
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * kEvalTY, x0 = blockIdx.x * kEvalTX;
+  const int yl0 = (int)floorf(y0 * a.sy), xl0 = (int)floorf(x0 * a.sx);
+  const float* src = a.logits + (int64_t)n * a.h * a.w * a.cp;
+  for (int i = threadIdx.x; i < cells * CT; i += kEvalTX) {
+    const int c = i % CT;
+    const int cell = i / CT;
+    const int px = cell % a.pw, py = cell / a.pw;
+    const int yy = min(yl0 + py, a.h - 1), xx = min(xl0 + px, a.w - 1);
+    patch[i] = __ldg(src + ((int64_t)yy * a.w + xx) * a.cp + c);
+  }
+  constexpr bool want_cm = kCm;
+  const int bins = a.num_classes * a.num_classes;
+  if (want_cm) {
+    for (int i = threadIdx.x; i < bins; i += kEvalTX) hist[i] = 0;
+    if (threadIdx.x == 0) s_bad = 0u;
+    // the CTA's label tile, all rows in flight at once (a thread walking its column would otherwise wait one HBM
+    // latency per row: measured +32 us on a 67 us launch)
+    const int32_t* lsrc = a.labels + ((int64_t)n * a.H + y0) * a.W + x0;
+    const bool in_x = x0 + (int)threadIdx.x < a.W;
+#pragma unroll 8
+    for (int r = 0; r < kEvalTY; ++r)
+      slab[r * kEvalTX + threadIdx.x] = (in_x && y0 + r < a.H) ? __ldg(lsrc + (int64_t)r * a.W + threadIdx.x) : 0;
+  }
+  __syncthreads();
+
+  const int x = x0 + threadIdx.x;
+  const bool live = x < a.W;
+  const int xc = live ? x : a.W - 1;
+  const float fx = xc * a.sx;
+  const int xl = (int)floorf(fx);
+  const int xh = min(xl + 1, a.w - 1);
+  const float lx = fx - (float)xl;
+  const int o0 = (xl - xl0) * CT, o1 = (xh - xl0) * CT;
+
+  float top[CT], dlt[CT];
+  int row = -1;               // source row pair (row, min(row + 1, h - 1)) held in top / dlt
+  bool l2_loaded = false;     // ... including the L2 channels
+  int run_bin = -2, run_len = 0;
+  unsigned bad = 0;
+  const int y_end = min(y0 + kEvalTY, a.H);
+  int32_t* dptr = kDec ? a.decisions + ((int64_t)n * a.H + y0) * a.W + x : nullptr;
+  const int32_t* lptr = slab + threadIdx.x;
+  const float* rt = patch;
+  const float* rb = patch;
+  const int C = a.num_classes;
+  for (int y = y0; y < y_end; ++y) {
+    const float fy = y * a.sy;
+    const int yl = (int)floorf(fy);
+    const float ly = fy - (float)yl;
+    if (yl != row) {          // uniform over the CTA
+      rt = patch + (yl - yl0) * a.pw * CT;
+      rb = patch + (min(yl + 1, a.h - 1) - yl0) * a.pw * CT;
+      eval_load_rows<0, C1, CT>(rt, rb, o0, o1, lx, top, dlt);
+      row = yl;
+      l2_loaded = false;
+    }
+    float v[C1];
+#pragma unroll
+    for (int c = 0; c < C1; ++c) v[c] = top[c] + dlt[c] * ly;   // = top + (bot - top) * y_lerp
+    int d1;
+    float m1;
+    tree_argmax<0, C1, C1>(v, m1, d1);
+    const bool is_v = d1 == hier.cid_l1_vehicle, is_h = d1 == hier.cid_l1_human;
+    int dec = hier.l1_to_common[d1];
+    if (__any_sync(0xffffffffu, is_v || is_h)) {    // warp-uniform
+      if (!l2_loaded) {
+        eval_load_rows<C1, CV + CH, CT>(rt, rb, o0, o1, lx, top, dlt);
+        l2_loaded = true;
+      }
+      float u[CV + CH];
+#pragma unroll
+      for (int c = 0; c < CV + CH; ++c) u[c] = top[C1 + c] + dlt[C1 + c] * ly;
+      int dv, dh;
+      float mv, mh;
+      tree_argmax<0, CV, CV + CH>(u, mv, dv);
+      tree_argmax<CV, CV + CH, CV + CH>(u, mh, dh);
+      dh -= CV;
+      if (is_v) dec = hier.veh_to_common[dv];
+      else if (is_h) dec = hier.hum_to_common[dh];
+    }
+    if (kDec) {
+      if (live) *dptr = dec;
+      dptr += a.W;
+    }
+    if (want_cm) {
+      const int32_t l = *lptr;
+      lptr += kEvalTX;
+      int d = dec;
+      bool ok = true;
+      if (kLut) {
+        ok = (unsigned)d < (unsigned)a.lut_size;
+        d = ok ? __ldg(a.lut + d) : 0;
+      }
+      ok = ok && (unsigned)l < (unsigned)C && (unsigned)d < (unsigned)C;
+      const int bin = !live ? -2 : (ok ? l * C + d : -1);   // -2: idle lane; -1: out-of-range pair, skipped and counted
+      if (bin != run_bin) {
+        if (run_bin >= 0) atomicAdd(&hist[run_bin], run_len);
+        else if (run_bin == -1) bad += (unsigned)run_len;
+        run_bin = bin;
+        run_len = 0;
+      }
+      ++run_len;
+    }
+  }
+  if (want_cm) {
+    if (run_bin >= 0) atomicAdd(&hist[run_bin], run_len);
+    else if (run_bin == -1) bad += (unsigned)run_len;
+    if (bad) atomicAdd(&s_bad, bad);
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += kEvalTX) {
+      const int32_t c = hist[i];
+      if (c) atomicAdd(a.cm + i, (unsigned long long)c);
+    }
+    if (threadIdx.x == 0 && a.invalid != nullptr && s_bad) atomicAdd(a.invalid, (unsigned long long)s_bad);
+  }
+}
+
+template <int C1, int CV, int CH, bool kCm, bool kLut, bool kDec>
+static int launch_head_eval_v(const wlseg_hierarchy* hier, HeadEvalArgs& a, size_t smem, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    WLSEG_CUDA(cudaFuncSetAttribute(head_eval_kernel<C1, CV, CH, kCm, kLut, kDec>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    200 * 1024));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(a.W, kEvalTX), (unsigned)ceil_div(a.H, kEvalTY), (unsigned)a.N);
+  head_eval_kernel<C1, CV, CH, kCm, kLut, kDec><<<grid, kEvalTX, smem, stream>>>(*hier, a);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int C1, int CV, int CH>
+static int launch_head_eval(const wlseg_hierarchy* hier, HeadEvalArgs& a, cudaStream_t stream) {
+  constexpr int CT = C1 + CV + CH;
+  a.ph = (int)fminf((float)a.h, floorf(kEvalTY * a.sy) + 3.f);
+  a.pw = (int)fminf((float)a.w, floorf(kEvalTX * a.sx) + 3.f);
+  const bool cm = a.labels != nullptr, lut = a.lut != nullptr, dec = a.decisions != nullptr;
+  const size_t smem = (size_t)a.ph * a.pw * CT * sizeof(float) +
+                      (cm ? ((size_t)a.num_classes * a.num_classes + kEvalTX * kEvalTY) * sizeof(int32_t) : 0);
+  if (smem > 200 * 1024) return 1;
+  if (!cm) return launch_head_eval_v<C1, CV, CH, false, false, true>(hier, a, smem, stream);
+  if (lut) return dec ? launch_head_eval_v<C1, CV, CH, true, true, true>(hier, a, smem, stream)
+                      : launch_head_eval_v<C1, CV, CH, true, true, false>(hier, a, smem, stream);
+  return dec ? launch_head_eval_v<C1, CV, CH, true, false, true>(hier, a, smem, stream)
+             : launch_head_eval_v<C1, CV, CH, true, false, false>(hier, a, smem, stream);
+}
+
 int check_hierarchy(const wlseg_hierarchy* hier) {
   WLSEG_CHECK_ARG(hier != nullptr, "hierarchy is NULL");
   WLSEG_CHECK_ARG(hier->C1 > 0 && hier->C1 <= 64 && hier->Cv > 0 && hier->Cv <= 16 && hier->Ch > 0 && hier->Ch <= 8,
@@ -379,4 +583,48 @@ extern "C" int wlseg_head_fwd(const wlseg_hierarchy* hier, const float* logits, 
   head_fwd_kernel<<<grid, kHeadThreads, smem, (cudaStream_t)stream>>>(*hier, a);
   WLSEG_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int wlseg_confmat_accumulate(const int32_t* labels, const int32_t* decisions, int64_t n, int32_t num_classes,
+                                        const int32_t* lut, int32_t lut_size, int64_t* cm, int64_t* invalid,
+                                        wlseg_stream_t stream);
+
+extern "C" int wlseg_head_confmat(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch, int32_t N,
+                                  int32_t h, int32_t w, int32_t H, int32_t W, const int32_t* labels, int32_t num_classes,
+                                  const int32_t* lut, int32_t lut_size, int64_t* cm, int64_t* invalid, int32_t* decisions,
+                                  wlseg_stream_t stream) {
+  if (int e = check_hierarchy(hier)) return e;
+  WLSEG_CHECK_ARG(N >= 0 && h > 0 && w > 0 && H > 0 && W > 0, "head_confmat: bad shape");
+  if (N == 0) return 0;
+  WLSEG_CHECK_ARG(logits != nullptr, "head_confmat: logits is NULL");
+  WLSEG_CHECK_ARG(N <= 65535, "head_confmat: N too large");
+  WLSEG_CHECK_ARG(logits_pitch >= hier->C1 + hier->Cv + hier->Ch, "head_confmat: logits_pitch %d < channels", logits_pitch);
+  WLSEG_CHECK_ARG(labels != nullptr || decisions != nullptr, "head_confmat: neither labels nor a decisions buffer given");
+  if (labels != nullptr) {
+    WLSEG_CHECK_ARG(cm != nullptr, "head_confmat: cm is NULL");
+    WLSEG_CHECK_ARG(num_classes > 0 && num_classes <= 104, "head_confmat: num_classes %d out of (0, 104]", num_classes);
+    WLSEG_CHECK_ARG(lut == nullptr || lut_size > 0, "head_confmat: lut given with lut_size %d", lut_size);
+  }
+  HeadEvalArgs a;
+  a.logits = logits;
+  a.N = N; a.h = h; a.w = w; a.H = H; a.W = W; a.cp = logits_pitch;
+  a.sy = resize_scale(h, H);
+  a.sx = resize_scale(w, W);
+  a.decisions = decisions; a.labels = labels; a.num_classes = num_classes; a.lut = lut; a.lut_size = lut_size;
+  a.cm = reinterpret_cast<unsigned long long*>(cm);
+  a.invalid = reinterpret_cast<unsigned long long*>(invalid);
+  int rc = 1;
+  if (a.sy <= 0.5f && a.sx <= 0.5f && getenv("WLSEG_HEAD_GENERIC") == nullptr) {
+    if (hier->C1 == 14 && hier->Cv == 7 && hier->Ch == 3) rc = launch_head_eval<14, 7, 3>(hier, a, (cudaStream_t)stream);
+    else if (hier->C1 == 53 && hier->Cv == 12 && hier->Ch == 5) rc = launch_head_eval<53, 12, 5>(hier, a, (cudaStream_t)stream);
+  }
+  if (rc != 1) return rc;
+  // other hierarchies / upsampling factors below 2: the general head kernel into a decisions buffer, then the
+  // histogram kernel (the caller must provide the buffer in that case)
+  WLSEG_CHECK_ARG(decisions != nullptr, "head_confmat: this configuration needs a decisions buffer (general kernels)");
+  if (int e = wlseg_head_fwd(hier, logits, logits_pitch, N, h, w, H, W, decisions, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, stream))
+    return e;
+  if (labels == nullptr) return 0;
+  return wlseg_confmat_accumulate(labels, decisions, (int64_t)N * H * W, num_classes, lut, lut_size, cm, invalid, stream);
 }

@@ -51,6 +51,7 @@ struct LossArgs {
   const int32_t* box_cids;    // [n_bbox][max_boxes], outside [0, 14] = padding / unknown label
   int max_boxes;
   const float* image_vec;     // [n_image][15]
+  int first;                  // generic tile kernel: first image of its range (blockIdx.z + first)
 };
 
 constexpr int kLossMaxBoxes = 516;   // MAX_N_BBOXES, input_subset_bboxes_v2.py:33
@@ -124,7 +125,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs
   __shared__ double red[3][kLossThreads / 32];
   __shared__ double redc[3][kLossThreads / 32];
 
-  const int b = blockIdx.z;
+  const int b = blockIdx.z + a.first;
   const int y0 = blockIdx.y * kLossTY, x0 = blockIdx.x * kLossTX;
   const int yl0 = (int)floorf(y0 * a.sy), xl0 = (int)floorf(x0 * a.sx);
   const int tile_w = min(kLossTX, a.W - x0);
@@ -645,6 +646,376 @@ loss_cols_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strong-label images, round 2 (the product path for the 14/7/3 hierarchy): the column walk of loss_cols_kernel with
+// the instruction count cut to what the arithmetic needs.  ncu on the kernels above (profiles/r2_head_loss_ncu.md):
+// the tile kernel retires 2370 instructions per pixel, the column kernel 845 at 25 % issue utilisation (12 warps per
+// SM, 166 registers) - against ~170 for the arithmetic itself.  Here:
+//   * a CTA is 128 columns x kLsTY rows and TWO warp groups: warps 0-3 walk the L1 head (14 channels), warps 4-7 the two
+//     L2 heads (7 + 3) of the same columns - half the registers per thread, twice the warps, and the L2 group skips
+//     every row in which no lane of its warp has a vehicle / human label (the weights are zero there: 70-90 % of a
+//     street scene), which the reference computes and multiplies by zero;
+//   * no arg-max (the loss needs the maximum only: FMNMX tree), exp2 with the max folded into one FFMA per class,
+//     one reciprocal per head, the softmax scale folded into the two gradient accumulator weights;
+//   * the one-hot part of the gradient never becomes a per-class select chain: a thread merges its vertical run of
+//     equal target classes into two scalars and subtracts them from the CTA's gradient patch with four shared atomics
+//     per run; the target logit is re-interpolated from the shared patch (10 instructions, bit-identical);
+//   * the label tile is staged once per CTA (all rows in flight), the label -> class tables sit in shared memory.
+constexpr int kLsTX = 128;
+constexpr int kLsTY = 16;
+constexpr int kLsThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int LO, int HI, int CT>
+__device__ __forceinline__ float tree_max(const float (&v)[CT]) {
+  if constexpr (HI - LO == 1) {
+    return v[LO];
+  } else {
+    constexpr int MID = LO + (HI - LO + 1) / 2;
+    return fmaxf(tree_max<LO, MID, CT>(v), tree_max<MID, HI, CT>(v));
+  }
+}
+
+// State of one head (channels [LO, LO + C) of the logits) along one output column.  The gradient of the source-row
+// pair (row, row + 1) accumulates in accT / accB; when the walk moves to the pair (row + 1, row + 2), accT is complete:
+// it leaves through the warp's shared staging area G (transpose of the x-interpolation, see flush_top), accB carries
+// over as the new accT.
+template <int LO, int C, int CT>
+struct StrongHead {
+  static constexpr int kPitch = 2 * C + 1;   // floats per lane in G (odd: conflict-free row writes)
+  float top[C], dlt[C], accT[C], accB[C];
+  float runT, runB;   // one-hot part of the current run of equal targets: sums of (1 - ly) * w and ly * w
+  int run_idx;
+  float loss, cnt;
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int c = 0; c < C; ++c) accT[c] = accB[c] = 0.f;
+    runT = runB = 0.f;
+    run_idx = -1;
+    loss = cnt = 0.f;
+  }
+  __device__ __forceinline__ void load(const float* __restrict__ rt, const float* __restrict__ rb, int o0, int o1, float lx) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float tl = rt[o0 + LO + c], tr = rt[o1 + LO + c];
+      const float bl = rb[o0 + LO + c], br = rb[o1 + LO + c];
+      const float t = tl + (tr - tl) * lx;   // TF ResizeBilinear: top = tl + (tr - tl) * x_lerp
+      const float b = bl + (br - bl) * lx;
+      top[c] = t;
+      dlt[c] = b - t;
+    }
+  }
+  // the finished run's one-hot gradient (-w on class run_idx) joins the accumulators: one select chain per RUN
+  __device__ __forceinline__ void fold_run() {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const bool hit = c == run_idx;
+      accT[c] -= hit ? runT : 0.f;
+      accB[c] -= hit ? runB : 0.f;
+    }
+    runT = runB = 0.f;
+  }
+  // accT (gradient of source row `grow`, complete) -> global dlogits through the transpose of the x-interpolation:
+  // every lane stages (1 - lx) * accT and lx * accT in G, then lane = (source column j, class c) sums the lanes of
+  // run j (their left neighbour is j) and of run j - 1 (their right neighbour is j) and issues ONE global reduction.
+  // xs[j] = first lane whose left neighbour is column j of the warp's span (xs[jw] = 32).  No shared atomics: a
+  // float atomicAdd on shared memory is a compare-and-swap loop, and eight lanes share every source column.
+  __device__ __forceinline__ void flush_top(float* __restrict__ G, const int* __restrict__ xs, int jw, int lane, float w0,
+                                            float w1, float* __restrict__ gdst /* dlogits of (grow, first column), or NULL */,
+                                            int cp, int cols_left) {
+    fold_run_top();
+    float* mine = G + lane * kPitch;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      mine[c] = w0 * accT[c];
+      mine[C + c] = w1 * accT[c];
+    }
+    __syncwarp();
+    if (gdst != nullptr) {
+      for (int it = lane; it < jw * C; it += 32) {
+        const int j = it / C, c = it - j * C;
+        float sum = 0.f;
+        for (int l = xs[j]; l < xs[j + 1]; ++l) sum += G[l * kPitch + c];
+        if (j > 0)
+          for (int l = xs[j - 1]; l < xs[j]; ++l) sum += G[l * kPitch + C + c];
+        if (sum != 0.f && j < cols_left) atomicAdd(gdst + j * cp + LO + c, sum);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < C; ++c) { accT[c] = accB[c]; accB[c] = 0.f; }
+    runT = runB;
+    runB = 0.f;
+  }
+  __device__ __forceinline__ void fold_run_top() {
+    // only the top half of the run leaves with accT; the bottom half stays with the carried accumulator
+#pragma unroll
+    for (int c = 0; c < C; ++c) accT[c] -= (c == run_idx) ? runT : 0.f;
+    runT = 0.f;
+  }
+  // one pixel: idx = target class (relative to LO), w = 0 / 1
+  __device__ __forceinline__ void pixel(int idx, float w, float ly, const float* __restrict__ rt, const float* __restrict__ rb,
+                                        int o0, int o1, float lx) {
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = top[c] + dlt[c] * ly;
+    const float m = tree_max<0, C, C>(v);
+    const float mb = -m * kLog2e;
+    float e[C];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { e[c] = ex2_approx(fmaf(v[c], kLog2e, mb)); s += e[c]; }
+    // target logit, re-interpolated (the same operations as v[idx])
+    const float tl = rt[o0 + LO + idx], tr = rt[o1 + LO + idx];
+    const float bl = rb[o0 + LO + idx], br = rb[o1 + LO + idx];
+    const float t = tl + (tr - tl) * lx;
+    const float b = bl + (br - bl) * lx;
+    const float vy = t + (b - t) * ly;
+    const float lse = fmaf(lg2_approx(s), kLn2, m);
+    loss += w * (lse - vy);
+    cnt += w;
+    const float inv = __fdividef(w, s);
+    const float wt = 1.0f - ly;
+    const float ga = wt * inv, gb = ly * inv;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      accT[c] = fmaf(ga, e[c], accT[c]);
+      accB[c] = fmaf(gb, e[c], accB[c]);
+    }
+    if (idx != run_idx) {
+      fold_run();
+      run_idx = idx;
+    }
+    runT = fmaf(wt, w, runT);
+    runB = fmaf(ly, w, runB);
+  }
+};
+
+constexpr int kLsMaxJw = 8;   // source columns under one warp's 32 output columns (+ the right neighbour)
+
+template <int C1, int CV, int CH>
+__global__ void __launch_bounds__(kLsThreads, 2)
+loss_strong_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a) {
+  constexpr int CT = C1 + CV + CH;
+  constexpr int CL2 = CV > CH ? CV : CH;
+  constexpr int CG = C1 > CL2 ? C1 : CL2;
+  constexpr int kGFloats = 32 * (2 * CG + 1);
+  extern __shared__ float smem[];
+  const int cells = a.ph * a.pw;
+  float* patch = smem;                                          // [ph][pw][CT] logits
+  float* Gall = patch + cells * CT;                             // [8 warps][32][2 * CG + 1] staging
+  int32_t* slab = reinterpret_cast<int32_t*>(Gall + (kLsThreads / 32) * kGFloats);   // [kLsTY][kLsTX] labels
+  int32_t* map1 = slab + kLsTY * kLsTX;                         // [80] x 3: label -> target class per head
+  int32_t* mapv = map1 + 80;
+  int32_t* maph = mapv + 80;
+  int32_t* xsall = maph + 80;                                   // [8 warps][kLsMaxJw + 2] run starts
+  __shared__ float red[3][kLsThreads / 32];
+  __shared__ float redc[3][kLsThreads / 32];
+  __shared__ int s_done;
+
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * kLsTY, x0 = blockIdx.x * kLsTX;
+  const int yl0 = (int)floorf(y0 * a.sy), xl0 = (int)floorf(x0 * a.sx);
+  const float* src = a.logits + (int64_t)b * a.h * a.w * a.cp;
+  for (int i = threadIdx.x; i < cells * CT; i += kLsThreads) {
+    const int c = i % CT;
+    const int cell = i / CT;
+    const int px = cell % a.pw, py = cell / a.pw;
+    const int yy = min(yl0 + py, a.h - 1), xx = min(xl0 + px, a.w - 1);
+    patch[i] = __ldg(src + ((int64_t)yy * a.w + xx) * a.cp + c);
+  }
+  for (int i = threadIdx.x; i < 80; i += kLsThreads) {
+    map1[i] = hier.pp_to_l1[i];
+    mapv[i] = hier.pp_to_veh[i];
+    maph[i] = hier.pp_to_hum[i];
+  }
+  if (threadIdx.x == 0) s_done = 0;
+  {
+    // label tile: every row in flight at once; -1 (malformed: contributes nothing) outside the image
+    const int32_t* lsrc = a.strong + ((int64_t)b * a.H + y0) * a.W + x0;
+    for (int i = threadIdx.x; i < kLsTY * kLsTX; i += kLsThreads) {
+      const int r = i / kLsTX, cx = i % kLsTX;
+      slab[i] = (x0 + cx < a.W && y0 + r < a.H) ? __ldg(lsrc + (int64_t)r * a.W + cx) : -1;
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = threadIdx.x & (kLsTX - 1);
+  const int role = threadIdx.x / kLsTX;          // 0: L1 head, 1: the two L2 heads (warp-uniform)
+  const int x = min(x0 + col, a.W - 1);
+  const float fx = x * a.sx;
+  const int xl = (int)floorf(fx);
+  const int xh = min(xl + 1, a.w - 1);
+  const float lx = fx - (float)xl;
+  const int o0 = (xl - xl0) * CT, o1 = (xh - xl0) * CT;
+  // x weights of the transpose; at the right border both neighbours are the last column
+  const float w0 = xh == xl ? 1.0f : 1.0f - lx, w1 = xh == xl ? 0.0f : lx;
+  // the warp's span of source columns and the first lane of every run of equal left neighbours
+  const int xlw = __shfl_sync(0xffffffffu, xl, 0);
+  const int jw = __shfl_sync(0xffffffffu, xl, 31) - xlw + 2;   // + the right neighbour of the last run
+  int* xs = xsall + warp * (kLsMaxJw + 2);
+  for (int j = 0; j <= jw; ++j) {
+    const int first = __popc(__ballot_sync(0xffffffffu, xl - xlw < j));
+    if (lane == 0) xs[j] = first;
+  }
+  __syncwarp();
+  float* G = Gall + warp * kGFloats;
+  const int y_end = min(y0 + kLsTY, a.H);
+  const int32_t* lptr = slab + col;
+  const int nc = hier.num_classes;
+  float* dimg = a.dlogits + (int64_t)b * a.h * a.w * a.cp;
+  const int cols_left = a.w - xlw;
+  float out_loss[3] = {0.f, 0.f, 0.f}, out_cnt[3] = {0.f, 0.f, 0.f};
+  if (jw > kLsMaxJw) __trap();   // the host checks the upsampling factor
+
+  auto grad_row = [&](int r) -> float* { return dimg + ((int64_t)r * a.w + xlw) * a.cp; };
+
+  if (role == 0) {
+    StrongHead<0, C1, CT> hd;
+    hd.init();
+    int row = -1;
+    const float* rt = patch; const float* rb = patch;
+    for (int y = y0; y < y_end; ++y, lptr += kLsTX) {
+      const float fy = y * a.sy;
+      const int yl = (int)floorf(fy);
+      const float ly = fy - (float)yl;
+      if (yl != row) {
+        if (row >= 0) hd.flush_top(G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left);
+        rt = patch + (yl - yl0) * a.pw * CT;
+        rb = patch + (min(yl + 1, a.h - 1) - yl0) * a.pw * CT;
+        hd.load(rt, rb, o0, o1, lx);
+        row = yl;
+      }
+      const int32_t label = *lptr;
+      const bool valid = (unsigned)label < (unsigned)nc;
+      const int idx = valid ? map1[label] : 0;
+      const float w = (valid && idx <= C1 - 2) ? 1.f : 0.f;     // the L1 void class carries no weight
+      if (!__any_sync(0xffffffffu, w != 0.f)) continue;
+      hd.pixel(idx, w, ly, rt, rb, o0, o1, lx);
+    }
+    if (row >= 0) {
+      const int rowh = min(row + 1, a.h - 1);
+      hd.flush_top(G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left);
+      hd.flush_top(G, xs, jw, lane, w0, w1, grad_row(rowh), a.cp, cols_left);   // the carried bottom half
+    }
+    out_loss[0] = hd.loss; out_cnt[0] = hd.cnt;
+  } else {
+    StrongHead<C1, CV, CT> hv;
+    StrongHead<C1 + CV, CH, CT> hh;
+    hv.init(); hh.init();
+    int row = -1;
+    bool loaded_v = false, loaded_h = false;   // this source-row pair's logits are in registers
+    bool dirty_v = false, dirty_h = false;     // the accumulators hold something (also carried bottoms)
+    const float* rt = patch; const float* rb = patch;
+    for (int y = y0; y < y_end; ++y, lptr += kLsTX) {
+      const float fy = y * a.sy;
+      const int yl = (int)floorf(fy);
+      const float ly = fy - (float)yl;
+      if (yl != row) {
+        if (row >= 0) {
+          // warp-uniform flags: a head that saw no weighted pixel in the last TWO source-row pairs has nothing to flush
+          if (dirty_v) hv.flush_top(G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left);
+          if (dirty_h) hh.flush_top(G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left);
+          dirty_v = loaded_v;   // what was accumulated in this pair's bottom half is carried
+          dirty_h = loaded_h;
+        }
+        rt = patch + (yl - yl0) * a.pw * CT;
+        rb = patch + (min(yl + 1, a.h - 1) - yl0) * a.pw * CT;
+        row = yl;
+        loaded_v = loaded_h = false;
+      }
+      const int32_t label = *lptr;
+      const bool valid = (unsigned)label < (unsigned)nc;
+      const int iv = valid ? mapv[label] : CV - 1;
+      const int ih = valid ? maph[label] : CH - 1;
+      const float wv = iv != CV - 1 ? 1.f : 0.f;
+      const float wh = ih != CH - 1 ? 1.f : 0.f;
+      if (__any_sync(0xffffffffu, wv != 0.f)) {       // warp-uniform: rows without a vehicle pixel cost nothing
+        if (!loaded_v) { hv.load(rt, rb, o0, o1, lx); loaded_v = true; dirty_v = true; }
+        hv.pixel(iv, wv, ly, rt, rb, o0, o1, lx);
+      }
+      if (__any_sync(0xffffffffu, wh != 0.f)) {
+        if (!loaded_h) { hh.load(rt, rb, o0, o1, lx); loaded_h = true; dirty_h = true; }
+        hh.pixel(ih, wh, ly, rt, rb, o0, o1, lx);
+      }
+    }
+    if (row >= 0) {
+      const int rowh = min(row + 1, a.h - 1);
+      if (dirty_v) {
+        hv.flush_top(G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left);
+        if (loaded_v) hv.flush_top(G, xs, jw, lane, w0, w1, grad_row(rowh), a.cp, cols_left);
+      }
+      if (dirty_h) {
+        hh.flush_top(G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left);
+        if (loaded_h) hh.flush_top(G, xs, jw, lane, w0, w1, grad_row(rowh), a.cp, cols_left);
+      }
+    }
+    out_loss[1] = hv.loss; out_cnt[1] = hv.cnt;
+    out_loss[2] = hh.loss; out_cnt[2] = hh.cnt;
+  }
+
+  // loss / count partials: warp shuffle -> shared; the LAST warp of the CTA to arrive adds the CTA's sums to the global
+  // fp64 accumulators (no CTA-wide barrier: the two warp groups finish at different times)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float l = warp_sum(out_loss[k]);
+    const float n = warp_sum(out_cnt[k]);
+    if (lane == 0) { red[k][warp] = l; redc[k][warp] = n; }
+  }
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = atomicAdd(&s_done, 1) == kLsThreads / 32 - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last && lane < 3) {
+    __threadfence_block();
+    double l = 0.0, n = 0.0;
+    for (int i = 0; i < kLsThreads / 32; ++i) { l += (double)red[lane][i]; n += (double)redc[lane][i]; }
+    if (n != 0.0 || l != 0.0) {
+      atomicAdd(a.sums + lane, l);
+      atomicAdd(a.counts + lane, n);
+    }
+  }
+}
+
+template <int C1, int CV, int CH>
+static int launch_loss_strong(const wlseg_hierarchy* hier, LossArgs& a, cudaStream_t stream) {
+  constexpr int CT = C1 + CV + CH;
+  constexpr int CL2 = CV > CH ? CV : CH;
+  constexpr int CG = C1 > CL2 ? C1 : CL2;
+  a.ph = (int)fminf((float)a.h, floorf(kLsTY * a.sy) + 3.f);
+  a.pw = (int)fminf((float)a.w, floorf(kLsTX * a.sx) + 3.f);
+  if ((int)floorf(32 * a.sx) + 3 > kLsMaxJw) return 1;
+  const size_t smem = ((size_t)a.ph * a.pw * CT + (size_t)(kLsThreads / 32) * 32 * (2 * CG + 1)) * sizeof(float) +
+                      (size_t)(kLsTY * kLsTX + 3 * 80 + (kLsThreads / 32) * (kLsMaxJw + 2)) * sizeof(int32_t);
+  if (smem > 200 * 1024) return 1;
+  static bool configured = false;
+  if (!configured) {
+    WLSEG_CUDA(cudaFuncSetAttribute(loss_strong_kernel<C1, CV, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(a.W, kLsTX), (unsigned)ceil_div(a.H, kLsTY), (unsigned)a.n_strong);
+  loss_strong_kernel<C1, CV, CH><<<grid, kLsThreads, smem, stream>>>(*hier, a);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int C1, int CV, int CH, int kColTY>
 static int launch_loss_cols(const wlseg_hierarchy* hier, LossArgs& a, int first, int count, cudaStream_t stream) {
   // images [first, first + count) of the batch; first < n_strong selects the strong-label instantiation
@@ -731,31 +1102,41 @@ static int loss_impl(const wlseg_hierarchy* hier, const float* logits, int32_t l
   a.strong = strong_labels; a.bbox = bbox_labels; a.image = image_labels;
   a.sums = sums; a.counts = counts; a.dlogits = dlogits;
   a.box_coords = box_coords; a.box_cids = box_cids; a.max_boxes = max_boxes; a.image_vec = image_vectors;
-  // Cityscapes hierarchy (14/7/3), upsampling >= 2x: the WEAK images (60 B/pixel of labels, targets by
-  // segment sums) take the register-resident column-walking kernel, measured 1.3x faster than the generic
-  // tile kernel there; the strong images (4 B/pixel) stay on the generic kernel, which is 1.3x faster for
-  // them (profiles/).  The 70-channel Vistas hierarchy always takes the generic kernel.
-  int n_generic = B;  // images [0, n_generic) are processed by the generic kernel
+  // Cityscapes hierarchy (14/7/3), upsampling >= 2x: the strong images take loss_strong_kernel, the WEAK images
+  // (60 B/pixel of labels, targets by segment sums) the register-resident column-walking loss_cols_kernel (measured
+  // 1.3x faster than the generic tile kernel there).  The 70-channel Vistas hierarchy takes the generic kernel.
+  int g0 = 0, g1 = B;   // images [g0, g1) are left to the generic tile kernel
+  a.first = 0;
   if (a.sy <= 0.5f && a.sx <= 0.5f && hier->C1 == 14 && hier->Cv == 7 && hier->Ch == 3) {
-    const char* mode = getenv("WLSEG_LOSS_COLS");  // experiments: "all" | "none" | "ty16"
+    // WLSEG_LOSS_COLS (experiments): "all" = strong images on loss_cols_kernel too, "none" = everything on the tile
+    // kernel, "old" = round-1 split (strong on the tile kernel, weak on loss_cols_kernel), "ty16" = 16-row weak strips
+    const char* mode = getenv("WLSEG_LOSS_COLS");
     const bool all = mode != nullptr && mode[0] == 'a';
     const bool none = mode != nullptr && mode[0] == 'n';
+    const bool old = mode != nullptr && mode[0] == 'o';
     const bool ty16 = mode != nullptr && mode[0] == 't';
     if (!none) {
-      int rc = 0;
-      if (all && n_strong > 0) rc = launch_loss_cols<14, 7, 3, 32>(hier, a, 0, n_strong, (cudaStream_t)stream);
-      if (rc == 0 && B - n_strong > 0)
-        rc = ty16 ? launch_loss_cols<14, 7, 3, 16>(hier, a, n_strong, B - n_strong, (cudaStream_t)stream)
-                  : launch_loss_cols<14, 7, 3, 32>(hier, a, n_strong, B - n_strong, (cudaStream_t)stream);
-      if (rc > 1 || rc < 0) return rc;
-      if (rc == 0) n_generic = all ? 0 : n_strong;
+      if (n_strong > 0 && !old) {
+        const int rc = all ? launch_loss_cols<14, 7, 3, 32>(hier, a, 0, n_strong, (cudaStream_t)stream)
+                           : launch_loss_strong<14, 7, 3>(hier, a, (cudaStream_t)stream);
+        if (rc > 1 || rc < 0) return rc;
+        if (rc == 0) g0 = n_strong;
+      }
+      if (B - n_strong > 0) {
+        const int rc = ty16 ? launch_loss_cols<14, 7, 3, 16>(hier, a, n_strong, B - n_strong, (cudaStream_t)stream)
+                            : launch_loss_cols<14, 7, 3, 32>(hier, a, n_strong, B - n_strong, (cudaStream_t)stream);
+        if (rc > 1 || rc < 0) return rc;
+        if (rc == 0) g1 = n_strong;
+      }
     }
   }
   // the compact weak labels exist in the column-walking kernel only
-  WLSEG_CHECK_ARG(!lists || n_generic <= n_strong,
+  WLSEG_CHECK_ARG(!lists || g1 <= n_strong,
                   "loss(lists): box / class lists need the 14/7/3 hierarchy at >= 2x upsampling; rasterise them "
                   "(wlseg_rasterize_bbox_labels, wlseg_tile_image_labels) and call wlseg_loss_fwd_bwd");
-  if (n_generic == 0) return 0;
+  if (g0 >= g1) return 0;
+  a.first = g0;
+  const int n_generic = g1 - g0;
   a.ph = (int)fminf((float)h, floorf(kLossTY * a.sy) + 3.f);
   a.pw = (int)fminf((float)w, floorf(kLossTX * a.sx) + 3.f);
   size_t smem = (size_t)(2 * a.ph * a.pw * Ct + 2 * kLossTX * a.gs + 2 * kLossTX + a.pw + 1) * sizeof(float);

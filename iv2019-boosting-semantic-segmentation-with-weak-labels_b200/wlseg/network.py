@@ -579,6 +579,15 @@ class EvalStep:
   def _body(self, images, labels):
     want = ('decisions',) + (('l1_probabilities', 'l2_vehicle_probabilities', 'l2_human_probabilities')
                              if self.replace_voids else ())
+    if not self.replace_voids and os.environ.get('WLSEG_HEAD_CONFMAT', '1') != '0':
+      # the step's tail in one launch: decisions and labels meet in registers (ops.head_confmat)
+      low = self.net.lowres_logits_infer(images)
+      H, W = labels.shape[1], labels.shape[2]
+      N = low.shape[0]
+      nbytes = N * H * W * 4 + N * low.shape[1] * low.shape[2] * sum(self.net.hier.head_widths) * 4
+      with self.net._Timed(self.net, 'head_confmat', nbytes):
+        ops.head_confmat(self.net.hstruct, low, H, W, labels, self.num_classes, self.cm, self.lut, self.invalid)
+      return
     out = self.net.predict(images, want=want)
     if self.replace_voids:
       ops.replace_voids(self.net.hstruct, out['l1_probabilities'], out['l2_vehicle_probabilities'],

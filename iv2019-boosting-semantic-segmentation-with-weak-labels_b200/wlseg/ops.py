@@ -97,6 +97,8 @@ _SIGNATURES = {
     'wlseg_loss_finalize': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _vp, _c_f, _c_f, _vp, _c_int, _c_i64, _vp,
                                            _vp]),
     'wlseg_confmat_accumulate': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp, _c_int, _vp, _vp, _vp]),
+    'wlseg_head_confmat': (ctypes.c_int, [ctypes.POINTER(Hierarchy), _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                          _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp]),
     'wlseg_sgdm_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _c_f, _c_int, _c_f, _c_f, _vp, _vp]),
     'wlseg_ema_update': (ctypes.c_int, [_vp, _vp, _vp, _c_i64, _c_f, _c_f, _vp]),
     'wlseg_add_inplace': (ctypes.c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
@@ -556,6 +558,21 @@ def loss_finalize(hier, sums, counts, l2_coef, grad_scale, dlogits, losses):
   _check(lib().wlseg_loss_finalize(ctypes.byref(hier), _ptr(sums), _ptr(counts), l2_coef, grad_scale, _ptr(dlogits),
                                    pitch, npix, _ptr(losses), _stream()), 'wlseg_loss_finalize')
   _count()
+
+
+def head_confmat(hier, logits, H, W, labels, num_classes, cm, lut=None, invalid=None, decisions=None):
+  """Low-res logits -> hierarchical decisions -> cm[label, lut[decision]] += 1 in one launch (wlseg_head_confmat);
+  decisions: optional int32 [N, H, W] output; labels None = decisions only."""
+  N, h, w, pitch = logits.shape
+  assert logits.dtype == torch.float32 and logits.is_contiguous()
+  if labels is not None:
+    assert labels.dtype == torch.int32 and labels.is_contiguous() and tuple(labels.shape) == (N, H, W)
+    assert cm.dtype == torch.int64 and cm.is_contiguous()
+  _check(lib().wlseg_head_confmat(ctypes.byref(hier), _ptr(logits), pitch, N, h, w, H, W, _ptr(labels), num_classes,
+                                  _ptr(lut), 0 if lut is None else lut.numel(), _ptr(cm), _ptr(invalid), _ptr(decisions),
+                                  _stream()), 'wlseg_head_confmat')
+  _count()
+  return cm
 
 
 def confmat_accumulate(labels, decisions, num_classes, cm, lut=None, invalid=None):

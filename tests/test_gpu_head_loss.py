@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from oracle import losses as olosses
+from oracle import metrics as ometrics
 from oracle import network as onet
 from oracle import tfops
 from oracle import weak_labels as oweak
@@ -200,3 +201,66 @@ def test_loss_from_compact_weak_labels_equals_dense_at_training_size(cuda):
   assert torch.equal(c0, c1) and float(c0[1]) > 0 and float(c0[2]) > 0
   assert torch.allclose(o0, o1, rtol=1e-6, atol=1e-7)
   assert float((d0 - d1).abs().max()) <= 1e-6 * float(d0.abs().max())
+
+
+@pytest.mark.parametrize('dataset,N,h,w,H,W,with_lut', [
+    ('cityscapes', 2, 8, 16, 64, 128, False),
+    ('cityscapes', 1, 7, 9, 50, 70, True),        # ragged tile, odd scale, decisions remapped through a LUT
+    ('cityscapes', 3, 33, 41, 264, 328, False),   # several CTAs per image, runs crossing strip boundaries
+    ('vistas', 1, 9, 12, 68, 95, False),
+    ('cityscapes', 4, 128, 256, 1024, 2048, True),   # BASELINE configs[1] step
+])
+def test_head_confmat_equals_oracle_composition_and_histogram(cuda, dataset, N, h, w, H, W, with_lut):
+  """wlseg_head_confmat (evaluation tail in one launch) against the ORACLE: decisions from the oracle's
+  resize_bilinear + compose_predictions, confusion matrix from the oracle histogram of (labels, lut[decisions]) -
+  both bit-exact - and against the two-launch product path (wlseg_head_fwd + wlseg_confmat_accumulate).  Labels carry
+  out-of-range ids (counted in `invalid`, skipped) and blocky runs as a segmentation map has them."""
+  from wlseg import network, ops
+  hier = _hier(dataset)
+  C = hier.num_classes
+  logits = _lowres(hier, N, h, w, seed=h * 100 + W + 1)
+  # make the L2 heads matter: push the vehicle / human super-classes up in a third of the cells
+  g = torch.Generator().manual_seed(5)
+  cells = torch.rand(N, h, w, generator=g)
+  logits[..., hier.as_struct().cid_l1_vehicle] += torch.where(cells < 0.2, 6.0, 0.0)
+  logits[..., hier.as_struct().cid_l1_human] += torch.where((cells >= 0.2) & (cells < 0.33), 6.0, 0.0)
+  rng = np.random.default_rng(H + W)
+  blocks = rng.integers(-1, C + 1, size=(N, -(-H // 16), -(-W // 24)), dtype=np.int32)   # -1 and C are out of range
+  labels = torch.from_numpy(np.repeat(np.repeat(blocks, 16, axis=1), 24, axis=2)[:, :H, :W].copy())
+  lut = None
+  if with_lut:
+    lut = torch.from_numpy(rng.integers(0, C, size=C, dtype=np.int32))
+    lut[3] = C + 7          # a decision that maps outside the matrix: counted as invalid
+  l1, l2v, l2h = [tfops.resize_bilinear(z.contiguous(), H, W) for z in _split(hier, logits)]
+  ref_dec = onet.compose_predictions(l1, l2v, l2h, dataset)['decisions']
+  mapped = ref_dec if lut is None else lut[ref_dec.long()]
+  ok = (labels >= 0) & (labels < C) & (mapped >= 0) & (mapped < C)
+  want_cm = ometrics.confusion_matrix(labels[ok].numpy(), mapped[ok].numpy(), C)
+  want_bad = int((~ok).sum())
+
+  low = logits.to(cuda)
+  lab = labels.to(cuda)
+  lut_d = None if lut is None else lut.to(cuda)
+  hs = hier.as_struct()
+  for keep_decisions in (True, False):
+    cm = torch.zeros(C, C, dtype=torch.int64, device=cuda)
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda)
+    dec = torch.full((N, H, W), -7, dtype=torch.int32, device=cuda) if keep_decisions else None
+    ops.head_confmat(hs, low, H, W, lab, C, cm, lut_d, bad, dec)
+    ops.head_confmat(hs, low, H, W, lab, C, cm, lut_d, bad, dec)       # accumulates
+    torch.cuda.synchronize()
+    assert np.array_equal(cm.cpu().numpy(), 2 * want_cm)
+    assert int(bad.item()) == 2 * want_bad
+    if keep_decisions:
+      assert torch.equal(dec.cpu(), ref_dec)
+  # decisions only (labels None), and the two-launch path on the same inputs
+  dec2 = torch.empty((N, H, W), dtype=torch.int32, device=cuda)
+  ops.head_confmat(hs, low, H, W, None, C, None, None, None, dec2)
+  net = network.Network.__new__(network.Network)
+  net.hier, net.hstruct, net.dev = hier, hs, cuda
+  dec3 = net.head(low, H, W, ('decisions',))['decisions']
+  cm3 = torch.zeros(C, C, dtype=torch.int64, device=cuda)
+  ops.confmat_accumulate(lab, dec3, C, cm3, lut_d)
+  torch.cuda.synchronize()
+  assert torch.equal(dec2.cpu(), ref_dec) and torch.equal(dec3.cpu(), ref_dec)
+  assert np.array_equal(cm3.cpu().numpy(), want_cm)

@@ -44,8 +44,9 @@ def head_cm():
 
 
 timed(head_cm, 'head + confmat 4x1024x2048', N * H * W * 8 + low.numel() * 4)
-if hasattr(network.Network, 'head_confmat'):
-  timed(lambda: net.head_confmat(low, H, W, labels, 20, cm), 'fused head_confmat 4x1024x2048', N * H * W * 4 + low.numel() * 4)
+timed(lambda: ops.head_confmat(hs, low, H, W, labels, 20, cm), 'fused head_confmat 4x1024x2048', N * H * W * 4 + low.numel() * 4)
+dbuf = torch.empty((N, H, W), dtype=torch.int32, device=dev)
+timed(lambda: ops.head_confmat(hs, low, H, W, None, 20, None, None, None, dbuf), 'head_confmat, decisions only', N * H * W * 4 + low.numel() * 4)
 
 # ---- training losses at 768 x 768
 H, W = 768, 768
