@@ -662,7 +662,6 @@ loss_cols_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a)
 //     per run; the target logit is re-interpolated from the shared patch (10 instructions, bit-identical);
 //   * the label tile is staged once per CTA (all rows in flight), the label -> class tables sit in shared memory.
 constexpr int kLsTX = 128;
-constexpr int kLsTY = 16;
 constexpr int kLsThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -806,7 +805,7 @@ struct StrongHead {
 
 constexpr int kLsMaxJw = 8;   // source columns under one warp's 32 output columns (+ the right neighbour)
 
-template <int C1, int CV, int CH>
+template <int C1, int CV, int CH, int kLsTY>
 __global__ void __launch_bounds__(kLsThreads, 2)
 loss_strong_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a) {
   constexpr int CT = C1 + CV + CH;
@@ -994,7 +993,7 @@ loss_strong_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs 
   }
 }
 
-template <int C1, int CV, int CH>
+template <int C1, int CV, int CH, int kLsTY>
 static int launch_loss_strong(const wlseg_hierarchy* hier, LossArgs& a, cudaStream_t stream) {
   constexpr int CT = C1 + CV + CH;
   constexpr int CL2 = CV > CH ? CV : CH;
@@ -1007,11 +1006,11 @@ static int launch_loss_strong(const wlseg_hierarchy* hier, LossArgs& a, cudaStre
   if (smem > 200 * 1024) return 1;
   static bool configured = false;
   if (!configured) {
-    WLSEG_CUDA(cudaFuncSetAttribute(loss_strong_kernel<C1, CV, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    WLSEG_CUDA(cudaFuncSetAttribute(loss_strong_kernel<C1, CV, CH, kLsTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(a.W, kLsTX), (unsigned)ceil_div(a.H, kLsTY), (unsigned)a.n_strong);
-  loss_strong_kernel<C1, CV, CH><<<grid, kLsThreads, smem, stream>>>(*hier, a);
+  loss_strong_kernel<C1, CV, CH, kLsTY><<<grid, kLsThreads, smem, stream>>>(*hier, a);
   WLSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -1071,6 +1070,11 @@ __global__ void loss_finalize_kernel(int C1, int Cv, int Ch, int cp, const doubl
 
 using namespace wlseg;
 
+static int env_ty() {
+  const char* e = getenv("WLSEG_LOSS_TY");   // rows per CTA strip of loss_strong_kernel: 16 | 32
+  return e != nullptr ? atoi(e) : 32;
+}
+
 static int loss_impl(const wlseg_hierarchy* hier, const float* logits, int32_t logits_pitch, int32_t n_strong, int32_t n_bbox,
                      int32_t n_image, int32_t h, int32_t w, int32_t H, int32_t W, const int32_t* strong_labels,
                      const float* bbox_labels, const float* image_labels, const float* box_coords, const int32_t* box_cids,
@@ -1118,7 +1122,8 @@ static int loss_impl(const wlseg_hierarchy* hier, const float* logits, int32_t l
     if (!none) {
       if (n_strong > 0 && !old) {
         const int rc = all ? launch_loss_cols<14, 7, 3, 32>(hier, a, 0, n_strong, (cudaStream_t)stream)
-                           : launch_loss_strong<14, 7, 3>(hier, a, (cudaStream_t)stream);
+                           : (env_ty() == 16 ? launch_loss_strong<14, 7, 3, 16>(hier, a, (cudaStream_t)stream)
+                                             : launch_loss_strong<14, 7, 3, 32>(hier, a, (cudaStream_t)stream));
         if (rc > 1 || rc < 0) return rc;
         if (rc == 0) g0 = n_strong;
       }
