@@ -649,22 +649,35 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         }
       }
       if (has_stat) {
-        // combine the 8 warps' partials in shared memory, then ONE fp64 atomic per channel and CTA
-        // (same-address L2 atomics serialise: per-warp flushes cost more than the layer's math)
+        // combine the warps' partials in a FIXED order, then ONE fp64 atomic per channel and CTA (same-address L2
+        // atomics serialise: per-warp flushes cost more than the layer's math).  Every warp parks its partial sums in
+        // its own staging buffer - float atomics on shared memory commit in a varying order, and a 1e-7 wobble of a
+        // batch-norm sum is amplified ~1e5 by a train-mode ResNet at random init (run-to-run 1.8e-2 on the gradients)
+        constexpr int kBufsPerWarp = kBnb ? 3 : 0;   // 0: (dbuf ? 2 : 1), resolved below
+        const int nbuf = kBufsPerWarp ? kBufsPerWarp : (dbuf ? 2 : 1);
+        if (lane == 0) bulk_wait_read<0>();          // the last stores have read the staging buffers
+        __syncwarp();
+        float* park = reinterpret_cast<float*>(wbuf);
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-          const int c = (cgrp + i * CG) * kSubW + 2 * lane;
-          if (c < BN) {
-            atomicAdd(s_stat + c, a1x[i]); atomicAdd(s_stat + c + 1, a1y[i]);
-            atomicAdd(s_stat + BN + c, a2x[i]); atomicAdd(s_stat + BN + c + 1, a2y[i]);
-          }
+          park[(i * 2 + 0) * kSubW + 2 * lane] = a1x[i]; park[(i * 2 + 0) * kSubW + 2 * lane + 1] = a1y[i];
+          park[(i * 2 + 1) * kSubW + 2 * lane] = a2x[i]; park[(i * 2 + 1) * kSubW + 2 * lane + 1] = a2y[i];
         }
         epi_barrier<32 * EW>();
         if (stat_k0 >= 0) {
           for (int j = et; j < BN; j += 32 * EW) {
             if (stat_k0 + j < prm.K) {
-              atomicAdd(prm.bn_sum + stat_k0 + j, (double)s_stat[j]);
-              atomicAdd(prm.bn_sqsum + stat_k0 + j, (double)s_stat[BN + j]);
+              const int st = j / kSubW, ch = j % kSubW;
+              const int cg = st % CG, i = st / CG;
+              float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float* src = reinterpret_cast<const float*>(epi_smem + (q4 + 4 * cg) * nbuf * kWarpBufBytes);
+                t1 += src[(i * 2 + 0) * kSubW + ch];
+                t2 += src[(i * 2 + 1) * kSubW + ch];
+              }
+              atomicAdd(prm.bn_sum + stat_k0 + j, (double)t1);
+              atomicAdd(prm.bn_sqsum + stat_k0 + j, (double)t2);
             }
           }
         }

@@ -475,6 +475,9 @@ loss_cols_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a)
       dst[c] = tl + (tr - tl) * lx;
     }
   };
+  // (Round 2 tried the staged warp transpose of loss_strong_kernel here instead of shared atomics: SLOWER for the weak
+  // images, 567 -> 735 us per 4 + 8 + 4 batch - their gradients are sparse (an L2 weight needs the L1 decision AND a
+  // box), so the `g != 0` guards below skip most of the atomics, while the staged form always pays in full.)
   auto flush_row = [&](int r, const float (&acc)[CT]) {
     float* base = D + (r - yl0) * a.pw * CT;
     const float w0 = 1.0f - lx;
