@@ -806,7 +806,8 @@ struct StrongHead {
   }
 };
 
-constexpr int kLsMaxJw = 8;   // source columns under one warp's 32 output columns (+ the right neighbour)
+constexpr int kLsMaxJw = 8;
+constexpr int kColMaxJwWide = 8;   // source columns under one warp's 32 output columns (+ the right neighbour)
 
 template <int C1, int CV, int CH, int kLsTY>
 __global__ void __launch_bounds__(kLsThreads, 2)
@@ -1018,6 +1019,317 @@ static int launch_loss_strong(const wlseg_hierarchy* hier, LossArgs& a, cudaStre
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide hierarchies (Vistas 53 / 12 / 5): the same column walk with a head SPLIT INTO CHUNKS of <= kChunk classes, one
+// warp per chunk over the same 32 output columns, so that no thread holds more than 5 x kChunk gradient / logit
+// registers.  The softmax of a split head needs the maximum and the sum over all of its chunks: every chunk warp
+// publishes its local (max, sum of exp) per pixel in shared memory, one named barrier per row joins the warps of the
+// head, and each rescales its own exponentials - exp(m_own - M) / S.  Only the chunk that holds the target class adds
+// the pixel's loss and the one-hot gradient.  A CTA is 32 columns x kLwTY rows x (number of chunks) warps.
+constexpr int kChunk = 11;
+constexpr int kLwTY = 32;
+constexpr int kLwMaxWarps = 8;
+
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+struct ChunkRole { int head_lo, head_c, lo, c, head_id, peers, peer0; };   // peer0: first warp of the head
+
+// one chunk [LO, LO + C) of a head along one output column; see StrongHead for the accumulator protocol
+template <int C>
+struct ChunkWalk {
+  float top[C], dlt[C], accT[C], accB[C];
+  float runT, runB;
+  int run_idx;     // target class relative to the chunk, -1 = not in this chunk
+  float loss, cnt;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int c = 0; c < C; ++c) top[c] = dlt[c] = accT[c] = accB[c] = 0.f;
+    runT = runB = loss = cnt = 0.f;
+    run_idx = -1;
+  }
+};
+
+template <int C>
+__device__ __forceinline__ void chunk_load(ChunkWalk<C>& k, int nc, const float* __restrict__ rt, const float* __restrict__ rb,
+                                           int o0, int o1, int lo, float lx) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    if (c < nc) {
+      const float tl = rt[o0 + lo + c], tr = rt[o1 + lo + c];
+      const float bl = rb[o0 + lo + c], br = rb[o1 + lo + c];
+      const float t = tl + (tr - tl) * lx;
+      const float b = bl + (br - bl) * lx;
+      k.top[c] = t;
+      k.dlt[c] = b - t;
+    }
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void chunk_flush_top(ChunkWalk<C>& k, int nc, float* __restrict__ G, const int* __restrict__ xs, int jw,
+                                                int lane, float w0, float w1, float* __restrict__ gdst, int cp, int cols_left,
+                                                int lo) {
+  constexpr int kPitch = 2 * C + 1;
+#pragma unroll
+  for (int c = 0; c < C; ++c) k.accT[c] -= (c == k.run_idx) ? k.runT : 0.f;
+  k.runT = 0.f;
+  float* mine = G + lane * kPitch;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    mine[c] = w0 * k.accT[c];
+    mine[C + c] = w1 * k.accT[c];
+  }
+  __syncwarp();
+  for (int it = lane; it < jw * nc; it += 32) {
+    const int j = it / nc, c = it - j * nc;
+    float sum = 0.f;
+    for (int l = xs[j]; l < xs[j + 1]; ++l) sum += G[l * kPitch + c];
+    if (j > 0)
+      for (int l = xs[j - 1]; l < xs[j]; ++l) sum += G[l * kPitch + C + c];
+    if (sum != 0.f && j < cols_left) atomicAdd(gdst + j * cp + lo + c, sum);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < C; ++c) { k.accT[c] = k.accB[c]; k.accB[c] = 0.f; }
+  k.runT = k.runB;
+  k.runB = 0.f;
+}
+
+__global__ void __launch_bounds__(32 * kLwMaxWarps, 2)
+loss_strong_wide_kernel(const __grid_constant__ wlseg_hierarchy hier, const LossArgs a, int n_warps) {
+  extern __shared__ float smem[];
+  const int CT = hier.C1 + hier.Cv + hier.Ch;
+  const int cells = a.ph * a.pw;
+  constexpr int kGFloats = 32 * (2 * kChunk + 1);
+  float* patch = smem;                                          // [ph][pw][CT] logits
+  float* Gall = patch + cells * CT;                             // [n_warps][32][2 * kChunk + 1] staging
+  float* exch = Gall + n_warps * kGFloats;                      // [2 row parities][n_warps][32][2]: local max, sum of exp
+  int32_t* slab = reinterpret_cast<int32_t*>(exch + 2 * n_warps * 64);   // [kLwTY][32] labels
+  int32_t* map1 = slab + kLwTY * 32;
+  int32_t* mapv = map1 + 80;
+  int32_t* maph = mapv + 80;
+  __shared__ int xs[kColMaxJwWide + 2];
+  __shared__ float red[3][kLwMaxWarps];
+  __shared__ float redc[3][kLwMaxWarps];
+  __shared__ int s_done;
+  __shared__ ChunkRole roles[kLwMaxWarps];
+
+  const int nthreads = 32 * n_warps;
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * kLwTY, x0 = blockIdx.x * 32;
+  const int yl0 = (int)floorf(y0 * a.sy), xl0 = (int)floorf(x0 * a.sx);
+  const float* src = a.logits + (int64_t)b * a.h * a.w * a.cp;
+  for (int i = threadIdx.x; i < cells * CT; i += nthreads) {
+    const int c = i % CT;
+    const int cell = i / CT;
+    const int px = cell % a.pw, py = cell / a.pw;
+    const int yy = min(yl0 + py, a.h - 1), xx = min(xl0 + px, a.w - 1);
+    patch[i] = __ldg(src + ((int64_t)yy * a.w + xx) * a.cp + c);
+  }
+  for (int i = threadIdx.x; i < 80; i += nthreads) {
+    map1[i] = hier.pp_to_l1[i];
+    mapv[i] = hier.pp_to_veh[i];
+    maph[i] = hier.pp_to_hum[i];
+  }
+  if (threadIdx.x == 0) {
+    s_done = 0;
+    // warp -> chunk of a head, in head order
+    int wi = 0;
+    const int hlo[3] = {0, hier.C1, hier.C1 + hier.Cv}, hc[3] = {hier.C1, hier.Cv, hier.Ch};
+    for (int hd = 0; hd < 3; ++hd) {
+      const int nch = (hc[hd] + kChunk - 1) / kChunk;
+      const int per = (hc[hd] + nch - 1) / nch;   // balanced chunks
+      for (int q = 0; q < nch; ++q, ++wi) {
+        roles[wi].head_lo = hlo[hd]; roles[wi].head_c = hc[hd]; roles[wi].head_id = hd;
+        roles[wi].lo = q * per; roles[wi].c = min(per, hc[hd] - q * per);
+        roles[wi].peers = nch; roles[wi].peer0 = wi - q;
+      }
+    }
+  }
+  {
+    const int32_t* lsrc = a.strong + ((int64_t)b * a.H + y0) * a.W + x0;
+    for (int i = threadIdx.x; i < kLwTY * 32; i += nthreads) {
+      const int r = i >> 5, cx = i & 31;
+      slab[i] = (x0 + cx < a.W && y0 + r < a.H) ? __ldg(lsrc + (int64_t)r * a.W + cx) : -1;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = min(x0 + lane, a.W - 1);
+  const float fx = x * a.sx;
+  const int xl = (int)floorf(fx);
+  const int xh = min(xl + 1, a.w - 1);
+  const float lx = fx - (float)xl;
+  const float w0 = xh == xl ? 1.0f : 1.0f - lx, w1 = xh == xl ? 0.0f : lx;
+  const int xlw = __shfl_sync(0xffffffffu, xl, 0);
+  const int jw = __shfl_sync(0xffffffffu, xl, 31) - xlw + 2;
+  if (warp == 0) {
+    for (int j = 0; j <= jw && j <= kColMaxJwWide + 1; ++j) {
+      const int first = __popc(__ballot_sync(0xffffffffu, xl - xlw < j));
+      if (lane == 0) xs[j] = first;
+    }
+  }
+  __syncthreads();
+  if (jw > kColMaxJwWide) __trap();
+
+  const ChunkRole role = roles[warp];
+  const int lo = role.head_lo + role.lo;     // first channel of this chunk in the logits
+  const int nc = role.c;
+  const int o0 = (xl - xl0) * CT, o1 = (xh - xl0) * CT;
+  const int32_t* mp = role.head_id == 0 ? map1 : (role.head_id == 1 ? mapv : maph);
+  const int void_idx = role.head_c - 1;      // every head's last class is its void / "other" class: no weight
+  float* G = Gall + warp * kGFloats;
+  float* dimg = a.dlogits + (int64_t)b * a.h * a.w * a.cp;
+  const int cols_left = a.w - xlw;
+  const int ncls = hier.num_classes;
+  const int y_end = min(y0 + kLwTY, a.H);
+  const int32_t* lptr = slab + lane;
+  auto grad_row = [&](int r) -> float* { return dimg + ((int64_t)r * a.w + xlw) * a.cp; };
+
+  ChunkWalk<kChunk> k;
+  k.init();
+  int row = -1;
+  bool loaded = false, dirty = false;
+  int parity = 0;
+  const float* rt = patch; const float* rb = patch;
+  for (int y = y0; y < y_end; ++y, lptr += 32) {
+    const float fy = y * a.sy;
+    const int yl = (int)floorf(fy);
+    const float ly = fy - (float)yl;
+    if (yl != row) {
+      if (row >= 0) {
+        if (dirty) chunk_flush_top(k, nc, G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left, lo);
+        dirty = loaded;
+      }
+      rt = patch + (yl - yl0) * a.pw * CT;
+      rb = patch + (min(yl + 1, a.h - 1) - yl0) * a.pw * CT;
+      row = yl;
+      loaded = false;
+    }
+    const int32_t label = *lptr;
+    const bool valid = (unsigned)label < (unsigned)ncls;
+    const int idx = valid ? mp[label] : void_idx;          // target class of this head
+    const float w = idx != void_idx ? 1.f : 0.f;
+    if (!__any_sync(0xffffffffu, w != 0.f)) continue;     // identical in every chunk warp of the head: same labels
+    if (!loaded) { chunk_load(k, nc, rt, rb, o0, o1, lo, lx); loaded = true; dirty = true; }
+    float v[kChunk];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c) {
+      v[c] = k.top[c] + k.dlt[c] * ly;
+      if (c < nc) m = fmaxf(m, v[c]);
+    }
+    const float mb = -m * kLog2e;
+    float e[kChunk];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c) {
+      e[c] = c < nc ? ex2_approx(fmaf(v[c], kLog2e, mb)) : 0.f;
+      s += e[c];
+    }
+    float M = m, S = s, f = 1.0f;
+    if (role.peers > 1) {
+      float* ex = exch + ((parity * n_warps + warp) * 32 + lane) * 2;
+      ex[0] = m; ex[1] = s;
+      named_barrier(1 + role.head_id, 32 * role.peers);
+      S = 0.f;
+      for (int q = 0; q < role.peers; ++q) M = fmaxf(M, exch[((parity * n_warps + role.peer0 + q) * 32 + lane) * 2]);
+      for (int q = 0; q < role.peers; ++q) {
+        const float* o = exch + ((parity * n_warps + role.peer0 + q) * 32 + lane) * 2;
+        S = fmaf(o[1], ex2_approx((o[0] - M) * kLog2e), S);
+      }
+      f = ex2_approx((m - M) * kLog2e);
+      parity ^= 1;
+    }
+    const int rel = idx - role.lo;                         // target class relative to this chunk
+    const bool mine = rel >= 0 && rel < nc;
+    const float wm = mine ? w : 0.f;
+    {
+      // target logit, re-interpolated from the shared patch (any chunk could; the owner does)
+      const int ch = role.head_lo + idx;
+      const float tl = rt[o0 + ch], tr = rt[o1 + ch];
+      const float bl = rb[o0 + ch], br = rb[o1 + ch];
+      const float t = tl + (tr - tl) * lx;
+      const float bb = bl + (br - bl) * lx;
+      const float vy = t + (bb - t) * ly;
+      const float lse = fmaf(lg2_approx(S), kLn2, M);
+      k.loss += wm * (lse - vy);
+      k.cnt += wm;
+    }
+    const float inv = __fdividef(w * f, S);
+    const float wt = 1.0f - ly;
+    const float ga = wt * inv, gb = ly * inv;
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c) {
+      k.accT[c] = fmaf(ga, e[c], k.accT[c]);
+      k.accB[c] = fmaf(gb, e[c], k.accB[c]);
+    }
+    const int ridx = mine ? rel : -1;
+    if (ridx != k.run_idx) {
+#pragma unroll
+      for (int c = 0; c < kChunk; ++c) {
+        const bool hit = c == k.run_idx;
+        k.accT[c] -= hit ? k.runT : 0.f;
+        k.accB[c] -= hit ? k.runB : 0.f;
+      }
+      k.runT = k.runB = 0.f;
+      k.run_idx = ridx;
+    }
+    k.runT = fmaf(wt, wm, k.runT);
+    k.runB = fmaf(ly, wm, k.runB);
+  }
+  if (row >= 0 && dirty) {
+    const int rowh = min(row + 1, a.h - 1);
+    chunk_flush_top(k, nc, G, xs, jw, lane, w0, w1, grad_row(row), a.cp, cols_left, lo);
+    if (loaded) chunk_flush_top(k, nc, G, xs, jw, lane, w0, w1, grad_row(rowh), a.cp, cols_left, lo);
+  }
+  {
+    const float l = warp_sum(k.loss);
+    const float n = warp_sum(k.cnt);
+    if (lane == 0) { red[role.head_id][warp] = l; redc[role.head_id][warp] = n; }
+  }
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = atomicAdd(&s_done, 1) == n_warps - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last && lane < 3) {
+    __threadfence_block();
+    double l = 0.0, n = 0.0;
+    for (int i = 0; i < n_warps; ++i)
+      if (roles[i].head_id == lane) { l += (double)red[lane][i]; n += (double)redc[lane][i]; }
+    if (n != 0.0 || l != 0.0) {
+      atomicAdd(a.sums + lane, l);
+      atomicAdd(a.counts + lane, n);
+    }
+  }
+}
+
+static int launch_loss_strong_wide(const wlseg_hierarchy* hier, LossArgs& a, cudaStream_t stream) {
+  const int CT = hier->C1 + hier->Cv + hier->Ch;
+  int n_warps = 0;
+  for (int c : {hier->C1, hier->Cv, hier->Ch}) n_warps += (c + kChunk - 1) / kChunk;
+  if (n_warps > kLwMaxWarps) return 1;
+  a.ph = (int)fminf((float)a.h, floorf(kLwTY * a.sy) + 3.f);
+  a.pw = (int)fminf((float)a.w, floorf(32 * a.sx) + 3.f);
+  if ((int)floorf(32 * a.sx) + 3 > kColMaxJwWide) return 1;
+  const size_t smem = ((size_t)a.ph * a.pw * CT + (size_t)n_warps * 32 * (2 * kChunk + 1) + (size_t)2 * n_warps * 64) * sizeof(float) +
+                      (size_t)(kLwTY * 32 + 3 * 80) * sizeof(int32_t);
+  if (smem > 200 * 1024) return 1;
+  static bool configured = false;
+  if (!configured) {
+    WLSEG_CUDA(cudaFuncSetAttribute(loss_strong_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(a.W, 32), (unsigned)ceil_div(a.H, kLwTY), (unsigned)a.n_strong);
+  loss_strong_wide_kernel<<<grid, 32 * n_warps, smem, stream>>>(*hier, a, n_warps);
+  WLSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int C1, int CV, int CH, int kColTY>
 static int launch_loss_cols(const wlseg_hierarchy* hier, LossArgs& a, int first, int count, cudaStream_t stream) {
   // images [first, first + count) of the batch; first < n_strong selects the strong-label instantiation
@@ -1137,6 +1449,12 @@ static int loss_impl(const wlseg_hierarchy* hier, const float* logits, int32_t l
         if (rc == 0) g1 = n_strong;
       }
     }
+  }
+  else if (a.sy <= 0.5f && a.sx <= 0.5f && n_strong > 0 && getenv("WLSEG_LOSS_WIDE_OFF") == nullptr) {
+    // wider hierarchies (Vistas 53 / 12 / 5): the strong images take the chunked column walk, weak images the tile kernel
+    const int rc = launch_loss_strong_wide(hier, a, (cudaStream_t)stream);
+    if (rc > 1 || rc < 0) return rc;
+    if (rc == 0) g0 = n_strong;
   }
   // the compact weak labels exist in the column-walking kernel only
   WLSEG_CHECK_ARG(!lists || g1 <= n_strong,

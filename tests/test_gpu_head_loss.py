@@ -95,6 +95,8 @@ def _weak_labels(rng, n, H, W, kind):
     ('cityscapes', 2, 0, 0, 8, 12, 64, 96),
     ('cityscapes', 1, 2, 1, 6, 20, 45, 150),     # mixed strong + bbox + image, ragged tile edges
     ('vistas', 1, 1, 1, 5, 7, 40, 56),
+    ('vistas', 2, 0, 0, 17, 30, 136, 239),       # chunked wide-hierarchy kernel: several CTAs, ragged width, 3 strips
+    ('cityscapes', 3, 0, 0, 25, 40, 200, 317),   # loss_strong_kernel: several strips per image, ragged tile edges
     ('cityscapes', 0, 1, 1, 4, 6, 32, 48),       # weak only: L1 loss must be exactly 0
 ])
 def test_loss_fwd_bwd_matches_oracle(cuda, dataset, ns, nb, ni, h, w, H, W):
