@@ -80,10 +80,13 @@ def load_traffic(workload, kernel_prefix):
     return None, None
   with open(os.path.join(pdir, files[-1])) as fp:
     t = json.load(fp).get(workload, {})
-  for k, v in t.items():
-    if k.startswith(kernel_prefix):
-      return v['dram_bytes_per_launch'], files[-1]
-  return None, None
+  # the kernel class spans several template instantiations (single CTA / CTA pair / BN-backward epilogue):
+  # launch-weighted mean over all of them
+  hits = [v for k, v in t.items() if k.startswith(kernel_prefix)]
+  n = sum(v['launches'] for v in hits)
+  if not n:
+    return None, None
+  return sum(v['dram_bytes_per_launch'] * v['launches'] for v in hits) / n, files[-1]
 
 
 class ClockSampler:

@@ -77,6 +77,9 @@ struct IgemmParams {
   const float* bnb_invstd;
   // wlseg_conv2d_fprop_bn: the LAST CTA to commit its statistics finalises the layer's batch norm (fin.counter != NULL)
   wlseg_bn_finalize_args fin;
+  // kHalo: ONE activation box per tile {64 ch, 16 px, TH + R - 1 rows} (map_ah) and the whole filter bank resident
+  CUtensorMap map_ah;
+  int halo_rows, halo_bytes, halo_sbo;
   int N, P, Q, K, C;
   int R, S, stride, dilation, pad_top, pad_left;
   int y_pitch, res_pitch, res_stride, res_H, res_W;
@@ -178,7 +181,16 @@ __device__ __forceinline__ int num_subtiles(const IgemmParams& prm, int k0) {
 // kBnb (staged epilogue only): the BN-backward form of a data gradient, see IgemmParams::bnb_* - three staging buffers
 // per warp: the z tile of the NEXT step arrives by TMA in one of two while this step reads the other, the masked
 // gradient leaves from the third; the sums are read back column-wise from the staged z and g tiles.
-template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair, bool kBnb = false>
+//
+// kHalo (C = 64, K <= 64, stride 1, dilation 1, S in {1, 3}; single CTA): the narrow 3x3 layers of block1 and the packed
+// root convolution were bound by the L2 -> SM fabric, not by HBM or the tensor pipe - every tap re-fetched the same
+// activations (9 x 16 KB per 128-pixel tile) and the 8 KB filter slice of the tap (profiles/r1_layers_eval.txt: 0.27-0.49
+// of their byte bound).  Here the activation patch arrives ONCE per tile with its halo - a 4-D box {64 ch, 16 px, TH + R - 1
+// rows} whose pixel rows are 2048 bytes apart in shared memory - and a tap is a shared-memory DESCRIPTOR shifted by
+// r * 2048 + s * 128 bytes (8-row groups `halo_sbo` apart, base_offset = the row phase inside the swizzle period);
+// the R * S filter slices (8 KB each) are loaded once per CTA and stay.  Two patch buffers: the TMA of tile i + 1 runs
+// under the MMAs of tile i.
+template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair, bool kBnb = false, bool kHalo = false>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   using Cfg = IgemmCfg<BN, kPair>;
@@ -192,7 +204,9 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   // so the dynamic window starts at offset 0 of the CTA's shared space)
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int stages = prm.stages;
-  uint8_t* epi_smem = smem + stages * Cfg::kStageBytes;            // [buf0 .. buf(epi_bufs-1)]
+  // kHalo: [2 patch buffers][num_kb filter slices][epilogue buffers]
+  uint8_t* halo_b = smem + 2 * prm.halo_bytes;
+  uint8_t* epi_smem = kHalo ? halo_b + prm.num_kb * Cfg::kBBytes : smem + stages * Cfg::kStageBytes;   // [buf0 .. buf(epi_bufs-1)]
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + prm.epi_bufs * kWarpBufBytes);
   uint64_t* full_bar = bars;                             // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;               // [kMaxStages]
@@ -200,13 +214,16 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;      // [2]
   uint64_t* rfull_bar = bars + 2 * kMaxStages + 4;       // [2 * EW] residual box landed (per warp, per buffer)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + 2 * kMaxEpiWarps);
+  uint64_t* afull_bar = bars + 2 * kMaxStages + 4 + 2 * kMaxEpiWarps + 1;   // [2] kHalo: patch landed
+  uint64_t* aempty_bar = afull_bar + 2;                                     // [2] kHalo: patch consumed
+  uint64_t* bfull_bar = afull_bar + 4;                                      // kHalo: filter bank landed
   float* s_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][BN] (kTmaEpi)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&prm.map_a);
+    tma_prefetch_desc(kHalo ? &prm.map_ah : &prm.map_a);
     tma_prefetch_desc(&prm.map_b);
     if (kTmaEpi) {
       tma_prefetch_desc(&prm.map_y);
@@ -223,6 +240,10 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       mbar_init(smem_u32(tempty_bar + a), kPair ? 2 * EW : EW);  // one arrival per epilogue warp (of both CTAs)
     }
     for (int a = 0; a < 2 * EW; ++a) mbar_init(smem_u32(rfull_bar + a), 1);
+    if (kHalo) {
+      for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(afull_bar + a), 1); mbar_init(smem_u32(aempty_bar + a), 1); }
+      mbar_init(smem_u32(bfull_bar), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -244,7 +265,22 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (kHalo && lane == 0) {
+      // the filter bank once (one N tile: k0 = 0), then one patch per tile
+      mbar_arrive_expect_tx(smem_u32(bfull_bar), prm.num_kb * Cfg::kBBytes);
+      for (int kb = 0; kb < prm.num_kb; ++kb)
+        tma_load_3d(smem_u32(halo_b + kb * Cfg::kBBytes), &prm.map_b, smem_u32(bfull_bar), 0, kb, 0);
+      int it = 0;
+      for (int tile = unit0; tile < prm.units; tile += unit_step, ++it) {
+        int n, p0, q0, k0;
+        decode_tile<BN, kPair>(prm, tile, rank, n, p0, q0, k0);
+        const int ab = it & 1;
+        mbar_wait(smem_u32(aempty_bar + ab), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(smem_u32(afull_bar + ab), prm.halo_bytes);
+        tma_load_4d(smem_u32(smem + ab * prm.halo_bytes), &prm.map_ah, smem_u32(afull_bar + ab), 0, q0 - prm.pad_left,
+                    p0 - prm.pad_top, n);
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < prm.units; tile += unit_step) {
@@ -281,7 +317,31 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    if (kHalo && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      mbar_wait(smem_u32(bfull_bar), 0);
+      int iter = 0;
+      for (int tile = unit0; tile < prm.units; tile += unit_step, ++iter) {
+        const int acc = iter & 1, ab = iter & 1;
+        const uint32_t ph = (iter >> 1) & 1;
+        mbar_wait(smem_u32(tempty_bar + acc), ph ^ 1);   // epilogue drained this accumulator
+        mbar_wait(smem_u32(afull_bar + ab), ph);          // this tile's patch has landed
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t a_base = smem_u32(smem + ab * prm.halo_bytes);
+        int r = 0, sx = 0;
+        for (int kb = 0; kb < prm.num_kb; ++kb) {
+          const uint64_t adesc = make_smem_desc_shifted(a_base + (uint32_t)(r * 2048 + sx * 128), (uint32_t)prm.halo_sbo);
+          const uint64_t bdesc = make_smem_desc(smem_u32(halo_b + kb * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          if (++sx == prm.S) { sx = 0; ++r; }
+        }
+        umma_commit(smem_u32(aempty_bar + ab));   // the patch buffer is free once these MMAs retire
+        umma_commit(smem_u32(tfull_bar + acc));
+      }
+    } else if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(kPair ? 2 * kBM : kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -338,7 +398,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       const float lo = prm.relu ? 0.f : -INFINITY;
       const uint32_t sw = (uint32_t)(lane & 7);           // row & 7 of this thread's staging row
       const bool dbuf = has_res || prm.epi_db;            // two staging buffers per warp
-      uint8_t* wbuf = epi_smem + ew * (kBnb ? 3 : (dbuf ? 2 : 1)) * kWarpBufBytes;
+      // kHalo (BN = 64: only the warps of column group 0 ever stage anything) keeps buffers for those four warps only
+      uint8_t* wbuf = epi_smem + (kHalo ? quarter : ew) * (kBnb ? 3 : (dbuf ? 2 : 1)) * kWarpBufBytes;
       uint64_t* my_rfull = rfull_bar + 2 * ew;
       const int r0 = quarter * 32;                        // first tile row of this warp
       const int dy0 = r0 >> prm.tw_log2, dx0 = r0 & (TW - 1);
@@ -660,6 +721,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         float* park = reinterpret_cast<float*>(wbuf);
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
+          if (kHalo && cgrp != 0) break;   // no buffer of its own, and nothing to add
           park[(i * 2 + 0) * kSubW + 2 * lane] = a1x[i]; park[(i * 2 + 0) * kSubW + 2 * lane + 1] = a1y[i];
           park[(i * 2 + 1) * kSubW + 2 * lane] = a2x[i]; park[(i * 2 + 1) * kSubW + 2 * lane + 1] = a2y[i];
         }
@@ -928,15 +990,36 @@ static cudaError_t launch_pair(void (*kernel)(KArgs...), int clusters, int threa
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair = false, bool kBnb = false>
+// shared memory of the halo form: two patch buffers, the resident filter bank, staging buffers of the four working
+// epilogue warps (BN = 64), barriers + statistics
+static int halo_smem_bytes(const IgemmParams& prm, int bn, int bufs_per_warp) {
+  return 2 * prm.halo_bytes + prm.num_kb * bn * kBK * 2 + 4 * bufs_per_warp * kWarpBufBytes + kBarBytes + 2 * bn * 4;
+}
+
+template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair = false, bool kBnb = false, bool kHalo = false>
 static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   using Cfg = IgemmCfg<BN, kPair>;
   static_assert(!kBnb || kTmaEpi, "the BN-backward form lives in the staged epilogue");
+  static_assert(!kHalo || (kTmaEpi && !kPair && BN == 64), "the halo form: staged epilogue, single CTA, BN = 64");
   static bool configured = false;
   if (!configured) {
-    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi, EW, kPair, kBnb>,
+    WLSEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TY, kTmaEpi, EW, kPair, kBnb, kHalo>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
+  }
+  if constexpr (kHalo) {
+    prm.epi_db = 0;
+    prm.res_mid = getenv("WLSEG_RES_MID") != nullptr ? atoi(getenv("WLSEG_RES_MID")) : 1;
+    const int bufs = kBnb ? 3 : (prm.res != nullptr ? 2 : 1);
+    prm.epi_bufs = 4 * bufs;
+    prm.stages = 0;
+    const int smem_bytes = halo_smem_bytes(prm, BN, bufs);
+    WLSEG_CHECK_ARG(smem_bytes <= kSmemMax, "conv(tcgen05, halo): shared memory plan does not fit");
+    prm.units = prm.total_tiles;
+    int grid = prm.total_tiles < conv_sms() ? prm.total_tiles : conv_sms();
+    WLSEG_CUDA(launch_pdl(conv_igemm_kernel<BN, TY, kTmaEpi, EW, false, kBnb, true>, dim3(grid), dim3(128 + 32 * EW), smem_bytes,
+                          s, prm));
+    return 0;
   }
   // shared memory plan: [stages x {A,B}] [epi_bufs x 4 KB] [barriers]
   // layers without a residual: a second staging buffer per warp for the 1x1 layers, so that the previous step's
@@ -1002,6 +1085,12 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   if (p->Q <= 8) tw_log2 = 3;
   if (p->Q <= 4) tw_log2 = 2;
   if (p->P == 1) tw_log2 = 7;
+  // halo form (see conv_igemm_kernel): C = 64, K = 64 (one N tile), stride 1, dilation 1, S in {1, 3}, 1 < R * S <= 9;
+  // its tile is 8 x 16 pixels (S = 1) or 16 x 8 (S = 3)
+  const bool halo_shape = BN == 64 && p->C == 64 && p->K == 64 && p->stride == 1 && p->dilation == 1 &&
+                          (p->S == 1 || p->S == 3) && p->R * p->S <= 9 && p->R * p->S > 1 && p->W >= 16 && p->Q >= 16 &&
+                          p->P > 1 && p->y_dtype != WLSEG_F32 && env_int("WLSEG_HALO", 1) != 0;
+  if (halo_shape) tw_log2 = p->S == 1 ? 4 : 3;
   const int TW = 1 << tw_log2, TH = kBM / TW;
   WLSEG_CHECK_ARG(TW * p->stride <= 256 && TH * p->stride <= 256, "conv(tcgen05): TMA box too large");
   {
@@ -1039,6 +1128,23 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
   WLSEG_CHECK_ARG(bnb == nullptr || (tma_epi && residual != nullptr && BN >= kSubW && p->res_stride == 1 &&
                                      bn_sum != nullptr && bn_sqsum != nullptr && scale == nullptr && p->relu == 0),
                   "conv_fprop_bnbwd: needs the staged bf16 epilogue (K %% 64 == 0, 16-byte aligned y / z, pitches %% 8 == 0)");
+  bool use_halo = false;
+  if (halo_shape && tma_epi) {
+    prm.halo_rows = TH + p->R - 1;
+    prm.halo_bytes = prm.halo_rows * 2048;
+    prm.halo_sbo = p->S == 1 ? 1024 : 2048;
+    prm.num_kb = p->R * p->S;
+    const int bufs = bnb != nullptr ? 3 : (residual != nullptr ? 2 : 1);
+    if (halo_smem_bytes(prm, BN, bufs) <= kSmemMax) {
+      use_halo = true;
+      use_pair = false;
+      uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+      uint64_t strides[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->x_pitch * 2 * p->W, (uint64_t)p->x_pitch * 2 * p->W * p->H};
+      uint32_t box[4] = {(uint32_t)kBK, 16, (uint32_t)prm.halo_rows, 1};
+      uint32_t estr[4] = {1, 1, 1, 1};
+      if (int e = encode_tensor_map(&prm.map_ah, x, 2, 4, dims, strides, box, estr, 4)) return e;
+    }
+  }
   {
     uint64_t dims[3] = {(uint64_t)p->C, (uint64_t)(p->R * p->S), (uint64_t)p->K};
     uint64_t strides[2] = {(uint64_t)p->C * 2, (uint64_t)p->C * 2 * p->R * p->S};
@@ -1106,6 +1212,10 @@ static int conv_fprop_igemm(const wlseg_conv_params* p, const void* x, const voi
     if (f32out) return launch_igemm<bn, float, false>(prm, s);                        \
     if (bn >= kSubW && tma_epi) return launch_igemm<bn, __nv_bfloat16, (bn >= kSubW)>(prm, s); \
     return launch_igemm<bn, __nv_bfloat16, false>(prm, s);
+  if (use_halo) {
+    if (bnb != nullptr) return launch_igemm_ew<64, __nv_bfloat16, true, 8, false, true, true>(prm, s);
+    return launch_igemm_ew<64, __nv_bfloat16, true, 8, false, false, true>(prm, s);
+  }
   if (bnb != nullptr) {
     if (BN == 256) return launch_igemm_ew<256, __nv_bfloat16, true, 8, true, true>(prm, s);
     if (BN == 128) return launch_igemm_ew<128, __nv_bfloat16, true, 8, false, true>(prm, s);

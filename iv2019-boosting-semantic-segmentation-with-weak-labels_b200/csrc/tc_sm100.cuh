@@ -206,6 +206,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major SWIZZLE_128B descriptor of an operand that starts INSIDE a swizzle period and whose 8-row groups are `sbo`
+// bytes apart (the halo tile of conv_igemm_kernel<..., kHalo>: a tap shifts the start by whole 128-byte pixel rows).
+// base_offset [49,52) = (start address >> 7) & 7, the row phase of the first row inside the 1024-byte swizzle period.
+__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A bf16 [7,10)=1,
 // B bf16 [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {

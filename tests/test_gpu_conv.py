@@ -385,3 +385,65 @@ def test_fprop_bn_equals_conv_then_bn_finalize(cuda, case):
     for name, a, b in zip(('scale', 'shift', 'mean', 'invstd', 'moving_mean', 'moving_var'), vec, outs[0][1]):
       err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
       assert err <= 1e-6, f'{name}: {err:.2e}'
+
+
+HALO_CASES = [
+    # N, H, W, R, S, pad_top, pad_left, epilogue      (C = K = 64, stride 1: the halo form of conv_igemm_kernel)
+    (2, 40, 56, 3, 3, 1, 1, 'plain'),
+    (1, 37, 45, 3, 3, 1, 1, 'bn_relu_res'),     # ragged tiles on both axes, folded BN + residual + ReLU
+    (2, 64, 96, 3, 3, 1, 1, 'stats'),           # training forward: raw output + fused statistics
+    (1, 50, 64, 4, 1, 2, 0, 'bn_relu'),         # the packed root convolution: R = 4, S = 1, pad (2, 0)
+    (4, 192, 192, 3, 3, 1, 1, 'plain'),         # BASELINE block1 size: 1152 tiles, 8 per CTA (patch double buffering)
+    (2, 128, 256, 4, 1, 2, 0, 'stats'),
+]
+
+
+@pytest.mark.parametrize('case', HALO_CASES)
+def test_halo_form_equals_per_tap_form_and_oracle(cuda, case, monkeypatch):
+  """The halo form (one activation patch per tile, taps as shifted shared-memory descriptors, resident filters) against
+  the per-tap form of the same kernel (WLSEG_HALO=0) - same MMAs in the same order: BIT-IDENTICAL outputs - and against
+  the oracle's convolution (1e-2 of max|ref|: one bf16 output rounding)."""
+  from wlseg import ops
+  N, H, W, R, S, pt, pl, epi = case
+  C = K = 64
+  g = torch.Generator().manual_seed(N * 1000 + H + W + R)
+  dt = torch.bfloat16
+  x = torch.randn(N, H, W, C, generator=g).to(dt)
+  w = (torch.randn(K, R, S, C, generator=g) / (R * S * C) ** 0.5).to(dt)
+  scale = shift = res = None
+  relu = False
+  if epi.startswith('bn_relu'):
+    scale = 0.5 + torch.rand(K, generator=g)
+    shift = torch.randn(K, generator=g) * 0.2
+    relu = True
+  if epi == 'bn_relu_res':
+    res = torch.randn(N, H, W, K, generator=g).to(dt)
+  P, Q = H, W     # SAME geometry: R = 3 pads (1, 1); the packed root R = 4 pads 2 above and 1 below
+  prm = ops.conv_params((N, H, W, C), (K, R, S, C), pad=(pt, pl), out_hw=(P, Q), relu=relu, dtype=ops.dtype_code(dt),
+                        res=None if res is None else res.to(cuda), res_stride=1)
+  outs = []
+  for halo in ('1', '0'):
+    monkeypatch.setenv('WLSEG_HALO', halo)
+    y = torch.full((N, P, Q, K), float('nan'), dtype=dt, device=cuda)
+    s1 = torch.zeros(K, dtype=torch.float64, device=cuda) if epi == 'stats' else None
+    s2 = torch.zeros(K, dtype=torch.float64, device=cuda) if epi == 'stats' else None
+    ops.conv2d_fprop(prm, x.to(cuda), w.to(cuda), y, None if scale is None else scale.to(cuda),
+                     None if shift is None else shift.to(cuda), None if res is None else res.to(cuda), s1, s2)
+    torch.cuda.synchronize()
+    outs.append((y.cpu(), None if s1 is None else (s1.cpu(), s2.cpu())))
+  (y1, st1), (y0, st0) = outs
+  assert torch.equal(y1, y0), f'halo vs per-tap: {int((y1 != y0).sum())} elements differ, max {float((y1.float() - y0.float()).abs().max()):.3e}'
+  if st1 is not None:
+    for a, b in zip(st1, st0):
+      assert float((a - b).abs().max() / b.abs().max()) <= 1e-6
+  # oracle: zero-pad explicitly, VALID correlation
+  xp = torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (pl, Q + S - 1 - W - pl, pt, P + R - 1 - H - pt))
+  ref = torch.nn.functional.conv2d(xp, w.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+  if scale is not None:
+    ref = ref * scale + shift
+  if res is not None:
+    ref = ref + res.float()
+  if relu:
+    ref = torch.relu(ref)
+  err = float((y1.float() - ref).abs().max() / ref.abs().max())
+  assert err <= 1e-2, err

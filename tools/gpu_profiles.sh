@@ -14,10 +14,10 @@ python tools/step_timeline.py train > gpurun_out/${R}_timeline_train.txt 2>&1; h
 python tools/step_timeline.py eval > gpurun_out/${R}_timeline_eval.txt 2>&1
 python tools/layer_table.py eval > gpurun_out/${R}_layers_eval.txt 2>&1
 python tools/layer_table.py train > gpurun_out/${R}_layers_train.txt 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${R}_eval_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_eval.log 2>&1; echo "ncu eval launches rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 5000 --csv --log-file gpurun_out/${R}_train_launches.csv python bench.py --workload train --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_train.log 2>&1; echo "ncu train launches rc=$?"
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_igemm|conv_wgrad" -c 400 --csv --log-file gpurun_out/${R}_eval_conv_dram.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_eval_dram.log 2>&1; echo "ncu eval dram rc=$?"
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_igemm|conv_wgrad|bn_|loss_|head_|confmat|sgdm" -c 3000 --csv --log-file gpurun_out/${R}_train_dram.csv python bench.py --workload train --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_train_dram.log 2>&1; echo "ncu train dram rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"conv_igemm_kernel" --launch-skip 95 --launch-count 8 -o gpurun_out/${R}_eval_igemm256_full -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_eval_full.log 2>&1; echo "ncu eval full rc=$?"
-ncu --set full --clock-control none -k regex:"head_eval|loss_strong|bn_bwd_apply|bn_reduce|bn_apply_rows|conv_wgrad_kernel<256|conv_igemm_kernel<256, __nv_bfloat16, true, 8, true, true" --launch-skip 40 --launch-count 12 -o gpurun_out/${R}_train_bw_full -f python bench.py --workload train --steps 1 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_train_full.log 2>&1; echo "ncu train full rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${R}_eval_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --sustained-seconds 0 > gpurun_out/ncu_eval.log 2>&1; echo "ncu eval launches rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 5000 --csv --log-file gpurun_out/${R}_train_launches.csv python bench.py --workload train --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --sustained-seconds 0 > gpurun_out/ncu_train.log 2>&1; echo "ncu train launches rc=$?"
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_igemm|conv_wgrad" -c 400 --csv --log-file gpurun_out/${R}_eval_conv_dram.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --sustained-seconds 0 > gpurun_out/ncu_eval_dram.log 2>&1; echo "ncu eval dram rc=$?"
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_igemm|conv_wgrad|bn_|loss_|head_|confmat|sgdm" -c 3000 --csv --log-file gpurun_out/${R}_train_dram.csv python bench.py --workload train --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --sustained-seconds 0 > gpurun_out/ncu_train_dram.log 2>&1; echo "ncu train dram rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"conv_igemm_kernel" --launch-skip 95 --launch-count 8 -o gpurun_out/${R}_eval_igemm256_full -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --sustained-seconds 0 > gpurun_out/ncu_eval_full.log 2>&1; echo "ncu eval full rc=$?"
+ncu --set full --clock-control none -k regex:"head_eval|loss_strong|bn_bwd_apply|bn_reduce|bn_apply_rows|conv_wgrad_kernel<256|conv_igemm_kernel<256, __nv_bfloat16, true, 8, true, true" --launch-skip 40 --launch-count 12 -o gpurun_out/${R}_train_bw_full -f python bench.py --workload train --steps 1 --warmup 2 --no-cpu-baseline --no-e2e --sustained-seconds 0 > gpurun_out/ncu_train_full.log 2>&1; echo "ncu train full rc=$?"
 ls -la gpurun_out/*.ncu-rep
