@@ -80,6 +80,7 @@ struct IgemmParams {
   // kHalo: ONE activation box per tile {64 ch, 16 px, TH + R - 1 rows} (map_ah) and the whole filter bank resident
   CUtensorMap map_ah;
   int halo_rows, halo_bytes, halo_sbo;
+  int epi_split;      // BN = 64 (one sub-tile per tile): the two epilogue column groups take alternate TILES
   int N, P, Q, K, C;
   int R, S, stride, dilation, pad_top, pad_left;
   int y_pitch, res_pitch, res_stride, res_H, res_W;
@@ -187,7 +188,7 @@ __device__ __forceinline__ int num_subtiles(const IgemmParams& prm, int k0) {
 // activations (9 x 16 KB per 128-pixel tile) and the 8 KB filter slice of the tap (profiles/r1_layers_eval.txt: 0.27-0.49
 // of their byte bound).  Here the activation patch arrives ONCE per tile with its halo - a 4-D box {64 ch, 16 px, TH + R - 1
 // rows} whose pixel rows are 2048 bytes apart in shared memory - and a tap is a shared-memory DESCRIPTOR shifted by
-// r * 2048 + s * 128 bytes (8-row groups `halo_sbo` apart, base_offset = the row phase inside the swizzle period);
+// r * 2048 + s * 128 bytes (8-row groups `halo_sbo` apart; the swizzle follows the absolute address bits);
 // the R * S filter slices (8 KB each) are loaded once per CTA and stay.  Two patch buffers: the TMA of tile i + 1 runs
 // under the MMAs of tile i.
 template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair, bool kBnb = false, bool kHalo = false>
@@ -399,7 +400,16 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       const uint32_t sw = (uint32_t)(lane & 7);           // row & 7 of this thread's staging row
       const bool dbuf = has_res || prm.epi_db;            // two staging buffers per warp
       // kHalo (BN = 64: only the warps of column group 0 ever stage anything) keeps buffers for those four warps only
-      uint8_t* wbuf = epi_smem + (kHalo ? quarter : ew) * (kBnb ? 3 : (dbuf ? 2 : 1)) * kWarpBufBytes;
+      // split (BN = 64): a tile is ONE 64-channel sub-tile, so the second column group would idle - and one warp per
+      // TMEM lane quarter walking the tiles serially bounded the narrow layers (root convolution: 110 tiles per CTA x
+      // ~1.3 us of epilogue step latency = the whole 154 us launch).  The groups take alternate tiles instead:
+      // group g drains accumulator buffer g, two tiles' epilogues are in flight per quarter.
+      const bool split = BN == kSubW && prm.epi_split != 0;
+      uint8_t* wbuf = epi_smem + ((kHalo && !split) ? quarter : ew) * (kBnb ? 3 : (dbuf ? 2 : 1)) * kWarpBufBytes;
+      const int st0 = split ? 0 : cgrp;            // this warp's first sub-tile of a tile, its sub-tile stride,
+      const int st_step = split ? BN / kSubW : CG;
+      const int tile0 = unit0 + (split ? cgrp * unit_step : 0);   // its first tile and its tile stride
+      const int tile_step = split ? 2 * unit_step : unit_step;
       uint64_t* my_rfull = rfull_bar + 2 * ew;
       const int r0 = quarter * 32;                        // first tile row of this warp
       const int dy0 = r0 >> prm.tw_log2, dx0 = r0 & (TW - 1);
@@ -409,7 +419,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       // buffers alone keep far too few bytes in flight to cover HBM latency
       constexpr int kResPf = 4;
       struct ResCursor { int tile, st, cnt; };
-      ResCursor ld = {unit0, cgrp, 0}, pf = {unit0, cgrp, 0};
+      ResCursor ld = {tile0, st0, 0}, pf = {tile0, st0, 0};
       auto next_residual = [&](ResCursor& c, bool stage) {
         while (c.tile < prm.units) {
           int n, p0, q0, k0;
@@ -424,11 +434,11 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
               tma_prefetch_4d(&prm.map_r, k0 + c.st * kSubW, cx, cy, n);
             }
             ++c.cnt;
-            c.st += CG;
+            c.st += st_step;
             return;
           }
-          c.st = cgrp;
-          c.tile += unit_step;
+          c.st = st0;
+          c.tile += tile_step;
         }
       };
       if (has_res && lane == 0) {
@@ -464,7 +474,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
             prm.out_mask + (((int64_t)n_ * prm.P + p0_ + dy_) * prm.Q + q0_ + dx_) * (prm.K >> 5) + (k0_ >> 5));
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-          const int st_ = cgrp + i * CG;
+          const int st_ = st0 + i * st_step;
           m[i] = (ok && st_ < nsub_) ? __ldg(row + st_) : make_uint2(0u, 0u);
         }
       };
@@ -485,7 +495,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
             if (stat_k0 < 0) {
 #pragma unroll
               for (int i = 0; i < kSlots; ++i) {
-                const int c = k0 + (cgrp + i * CG) * kSubW + 2 * lane;
+                const int c = k0 + (st0 + i * st_step) * kSubW + 2 * lane;
                 if (c + 1 < prm.K) {
                   bmx[i] = __ldg(prm.bnb_mean + c); bmy[i] = __ldg(prm.bnb_mean + c + 1);
                   bix[i] = __ldg(prm.bnb_invstd + c); biy[i] = __ldg(prm.bnb_invstd + c + 1);
@@ -497,7 +507,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         }
         mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
         tc_fence_after();
-        if (cgrp >= nsub) {
+        const bool idle = split ? ((iter & 1) != cgrp) : (cgrp >= nsub);
+        if (idle) {
           // nothing to do in this tile: still one arrival per warp and tile
           tc_fence_before();
           __syncwarp();
@@ -505,8 +516,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         }
 #pragma unroll
         for (int slot = 0; slot < kSlots; ++slot) {
-          const int st = cgrp + slot * CG;
-          if (st >= nsub) break;
+          const int st = st0 + slot * st_step;
+          if (st >= nsub || idle) break;
           if constexpr (kBnb) {
             uint8_t* zb = wbuf + (cnt & 1) * kWarpBufBytes;   // z tile of this step (TMA)
             uint8_t* ob = wbuf + 2 * kWarpBufBytes;           // masked gradient, leaves by TMA store
@@ -721,7 +732,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
         float* park = reinterpret_cast<float*>(wbuf);
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-          if (kHalo && cgrp != 0) break;   // no buffer of its own, and nothing to add
+          if (kHalo && !split && cgrp != 0) break;   // no buffer of its own, and nothing to add
           park[(i * 2 + 0) * kSubW + 2 * lane] = a1x[i]; park[(i * 2 + 0) * kSubW + 2 * lane + 1] = a1y[i];
           park[(i * 2 + 1) * kSubW + 2 * lane] = a2x[i]; park[(i * 2 + 1) * kSubW + 2 * lane + 1] = a2y[i];
         }
@@ -730,13 +741,15 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
           for (int j = et; j < BN; j += 32 * EW) {
             if (stat_k0 + j < prm.K) {
               const int st = j / kSubW, ch = j % kSubW;
-              const int cg = st % CG, i = st / CG;
+              const int cg = split ? 0 : st % CG, i = split ? 0 : st / CG;
               float t1 = 0.f, t2 = 0.f;
+              for (int g2 = 0; g2 < (split ? CG : 1); ++g2) {     // split: both column groups hold partials of sub-tile 0
 #pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const float* src = reinterpret_cast<const float*>(epi_smem + (q4 + 4 * cg) * nbuf * kWarpBufBytes);
-                t1 += src[(i * 2 + 0) * kSubW + ch];
-                t2 += src[(i * 2 + 1) * kSubW + ch];
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const float* src = reinterpret_cast<const float*>(epi_smem + (q4 + 4 * (cg + g2)) * nbuf * kWarpBufBytes);
+                  t1 += src[(i * 2 + 0) * kSubW + ch];
+                  t2 += src[(i * 2 + 1) * kSubW + ch];
+                }
               }
               atomicAdd(prm.bn_sum + stat_k0 + j, (double)t1);
               atomicAdd(prm.bn_sqsum + stat_k0 + j, (double)t2);
@@ -992,9 +1005,11 @@ static cudaError_t launch_pair(void (*kernel)(KArgs...), int clusters, int threa
 
 // shared memory of the halo form: two patch buffers, the resident filter bank, staging buffers of the four working
 // epilogue warps (BN = 64), barriers + statistics
-static int halo_smem_bytes(const IgemmParams& prm, int bn, int bufs_per_warp) {
-  return 2 * prm.halo_bytes + prm.num_kb * bn * kBK * 2 + 4 * bufs_per_warp * kWarpBufBytes + kBarBytes + 2 * bn * 4;
+static int halo_smem_bytes(const IgemmParams& prm, int bn, int bufs_per_warp, int warps = 4) {
+  return 2 * prm.halo_bytes + prm.num_kb * bn * kBK * 2 + warps * bufs_per_warp * kWarpBufBytes + kBarBytes + 2 * bn * 4;
 }
+// BN = 64: the two epilogue column groups take alternate tiles (conv_igemm_kernel, `split`); WLSEG_EPI_SPLIT=0 disables
+static bool epi_split_enabled() { return env_int("WLSEG_EPI_SPLIT", 1) != 0; }
 
 template <int BN, typename TY, bool kTmaEpi, int EW, bool kPair = false, bool kBnb = false, bool kHalo = false>
 static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
@@ -1011,9 +1026,13 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
     prm.epi_db = 0;
     prm.res_mid = getenv("WLSEG_RES_MID") != nullptr ? atoi(getenv("WLSEG_RES_MID")) : 1;
     const int bufs = kBnb ? 3 : (prm.res != nullptr ? 2 : 1);
-    prm.epi_bufs = 4 * bufs;
+    // staging buffers for all eight epilogue warps when they fit (then the column groups alternate tiles), else for
+    // the four warps of group 0
+    prm.epi_split = (epi_split_enabled() && halo_smem_bytes(prm, BN, bufs, 8) <= kSmemMax) ? 1 : 0;
+    const int ewarps = prm.epi_split ? 8 : 4;
+    prm.epi_bufs = ewarps * bufs;
     prm.stages = 0;
-    const int smem_bytes = halo_smem_bytes(prm, BN, bufs);
+    const int smem_bytes = halo_smem_bytes(prm, BN, bufs, ewarps);
     WLSEG_CHECK_ARG(smem_bytes <= kSmemMax, "conv(tcgen05, halo): shared memory plan does not fit");
     prm.units = prm.total_tiles;
     int grid = prm.total_tiles < conv_sms() ? prm.total_tiles : conv_sms();
@@ -1030,6 +1049,7 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   prm.epi_db = (kTmaEpi && prm.res == nullptr && prm.R * prm.S == 1 &&
                 (getenv("WLSEG_EPI_DB") != nullptr ? atoi(getenv("WLSEG_EPI_DB")) : 0)) ? 1 : 0;
   prm.epi_bufs = kTmaEpi ? (kBnb ? 3 * EW : ((prm.res != nullptr || prm.epi_db) ? 2 * EW : EW)) : 0;
+  prm.epi_split = (kTmaEpi && BN == kSubW && epi_split_enabled()) ? 1 : 0;
   prm.res_mid = getenv("WLSEG_RES_MID") != nullptr ? atoi(getenv("WLSEG_RES_MID")) : 1;
   const int fixed = prm.epi_bufs * kWarpBufBytes + kBarBytes + (kTmaEpi ? 2 * BN * 4 : 0);
   int stages = (kSmemMax - fixed) / Cfg::kStageBytes;

@@ -208,14 +208,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // K-major SWIZZLE_128B descriptor of an operand that starts INSIDE a swizzle period and whose 8-row groups are `sbo`
 // bytes apart (the halo tile of conv_igemm_kernel<..., kHalo>: a tap shifts the start by whole 128-byte pixel rows).
-// base_offset [49,52) = (start address >> 7) & 7, the row phase of the first row inside the 1024-byte swizzle period.
+// The swizzle is a function of the absolute shared-memory address bits, and the PATTERN (the TMA-written patch) starts
+// 1024-byte aligned: base_offset [49,52) stays 0 - it describes a misaligned pattern, not a start inside an aligned
+// one (setting it to the row phase of the start address shifted every row twice: measured, all outputs wrong).
 __device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(sbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)((saddr >> 7) & 7u) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }

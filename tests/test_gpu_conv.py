@@ -422,8 +422,9 @@ def test_halo_form_equals_per_tap_form_and_oracle(cuda, case, monkeypatch):
   prm = ops.conv_params((N, H, W, C), (K, R, S, C), pad=(pt, pl), out_hw=(P, Q), relu=relu, dtype=ops.dtype_code(dt),
                         res=None if res is None else res.to(cuda), res_stride=1)
   outs = []
-  for halo in ('1', '0'):
+  for halo, split in (('1', '1'), ('0', '0'), ('0', '1'), ('1', '0')):
     monkeypatch.setenv('WLSEG_HALO', halo)
+    monkeypatch.setenv('WLSEG_EPI_SPLIT', split)    # BN = 64: the epilogue column groups alternate tiles
     y = torch.full((N, P, Q, K), float('nan'), dtype=dt, device=cuda)
     s1 = torch.zeros(K, dtype=torch.float64, device=cuda) if epi == 'stats' else None
     s2 = torch.zeros(K, dtype=torch.float64, device=cuda) if epi == 'stats' else None
@@ -431,11 +432,13 @@ def test_halo_form_equals_per_tap_form_and_oracle(cuda, case, monkeypatch):
                      None if shift is None else shift.to(cuda), None if res is None else res.to(cuda), s1, s2)
     torch.cuda.synchronize()
     outs.append((y.cpu(), None if s1 is None else (s1.cpu(), s2.cpu())))
-  (y1, st1), (y0, st0) = outs
-  assert torch.equal(y1, y0), f'halo vs per-tap: {int((y1 != y0).sum())} elements differ, max {float((y1.float() - y0.float()).abs().max()):.3e}'
-  if st1 is not None:
-    for a, b in zip(st1, st0):
-      assert float((a - b).abs().max() / b.abs().max()) <= 1e-6
+  (y1, st1), (y0, st0) = outs[0], outs[1]
+  for tag, (yv, stv) in zip(('halo + split', 'per-tap + split', 'halo'), (outs[0], outs[2], outs[3])):
+    assert torch.equal(yv, y0), (f'{tag} vs per-tap: {int((yv != y0).sum())} elements differ, max '
+                                 f'{float((yv.float() - y0.float()).abs().max()):.3e}')
+    if stv is not None:
+      for a, b in zip(stv, st0):
+        assert float((a - b).abs().max() / b.abs().max()) <= 1e-6
   # oracle: zero-pad explicitly, VALID correlation
   xp = torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (pl, Q + S - 1 - W - pl, pt, P + R - 1 - H - pt))
   ref = torch.nn.functional.conv2d(xp, w.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
