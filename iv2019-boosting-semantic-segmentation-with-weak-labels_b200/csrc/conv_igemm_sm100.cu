@@ -396,7 +396,6 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
       // warp).  No CTA-wide barrier: the warps drift apart and hide each other's latencies.
       const bool has_res = prm.res != nullptr;
       const bool has_stat = prm.bn_sum != nullptr;
-      const float lo = prm.relu ? 0.f : -INFINITY;
       const uint32_t sw = (uint32_t)(lane & 7);           // row & 7 of this thread's staging row
       const bool dbuf = has_res || prm.epi_db;            // two staging buffers per warp
       // kHalo (BN = 64: only the warps of column group 0 ever stage anything) keeps buffers for those four warps only
@@ -686,12 +685,23 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
               for (int j = 0; j < 32; ++j) f[j] = 0.f;
             }
             uint4 outv[4];
+            if (prm.relu) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv[g]);
+              for (int g = 0; g < 4; ++g) {
+                __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv[g]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                ho[e] = __floats2bfloat162_rn(fmaxf(f[g * 8 + 2 * e], lo), fmaxf(f[g * 8 + 2 * e + 1], lo));
+                for (int e = 0; e < 4; ++e)
+                  ho[e] = __floats2bfloat162_rn(fmaxf(f[g * 8 + 2 * e], 0.f), fmaxf(f[g * 8 + 2 * e + 1], 0.f));
+              }
+            } else {
+              // training forward (raw z) and every data gradient: no clamp - 64 FMNMX of a ~650-instruction step that
+              // ncu shows issue-bound on the shallow layers (profiles/r2_epilogue_issue_bound.md)
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv[g]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+              }
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) *slot4[g] = outv[g];
@@ -1046,8 +1056,13 @@ static int launch_igemm_ew(IgemmParams& prm, cudaStream_t s) {
   // costs the fourth operand stage, which the wide-C layers need more (1024 -> 2048: 439 -> 469 us, 2048 -> 512:
   // 216 -> 250 us) than the narrow ones gain (256 -> 768: 83 -> 78 us); eval step 8.75 -> 8.95 ms.  The exposed
   // store-read wait is therefore NOT what holds the bandwidth-bound layers at 0.5-0.8 of their byte bound.
-  prm.epi_db = (kTmaEpi && prm.res == nullptr && prm.R * prm.S == 1 &&
-                (getenv("WLSEG_EPI_DB") != nullptr ? atoi(getenv("WLSEG_EPI_DB")) : 0)) ? 1 : 0;
+  // Round 2: ON for the SHALLOW 1x1 layers (<= 8 k-blocks per tile: the expansions 64 -> 256, 128 -> 512, 256 -> 1024, 256 -> 768):
+  // their tiles finish their MMAs long before the epilogue has drained the previous one, the operand ring is never
+  // deeper than a tile, and with one buffer every step waits for the previous store to have READ it.
+  // WLSEG_EPI_DB = 0 / 1 forces it off / on for every 1x1 layer without a residual.
+  const int db_env = getenv("WLSEG_EPI_DB") != nullptr ? atoi(getenv("WLSEG_EPI_DB")) : -1;
+  prm.epi_db = (kTmaEpi && !kBnb && prm.res == nullptr && prm.R * prm.S == 1 &&
+                (db_env >= 0 ? db_env != 0 : prm.num_kb <= 8)) ? 1 : 0;
   prm.epi_bufs = kTmaEpi ? (kBnb ? 3 * EW : ((prm.res != nullptr || prm.epi_db) ? 2 * EW : EW)) : 0;
   prm.epi_split = (kTmaEpi && BN == kSubW && epi_split_enabled()) ? 1 : 0;
   prm.res_mid = getenv("WLSEG_RES_MID") != nullptr ? atoi(getenv("WLSEG_RES_MID")) : 1;

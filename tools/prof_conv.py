@@ -96,6 +96,11 @@ if len(sys.argv) > 2 and sys.argv[2] == 'stats':
       fprop(4, 192, 192, 64, 256, 1, 1, stats=st, relu=False)
   sys.exit(0)
 
+if len(sys.argv) > 2 and sys.argv[2] == 'statone':
+  fprop(4, 96, 96, 256, 1024, 1, 1, stats=True, relu=False)
+  fprop(4, 96, 96, 256, 1024, 1, 1, stats=False, relu=False)
+  sys.exit(0)
+
 if len(sys.argv) > 2 and sys.argv[2] == 'pairprobe':
   fprop(4, 128, 256, 256, 1024, 1, 1, res=True)
   fprop(4, 128, 256, 512, 2048, 1, 1, res=True)
