@@ -110,3 +110,19 @@ if nccl:
     tr._graphs.clear()
     torch.cuda.synchronize()
     dist.destroy_process_group()
+
+# WLSEG_TIMELINE_LIST=<regex>: per-launch durations (mean over the profiled steps) of the matching kernels in step order,
+# with the kernel that ran before each one - to match bandwidth passes to layers
+pat = os.environ.get('WLSEG_TIMELINE_LIST')
+if pat:
+  per = len(ev) // STEPS
+  rows = collections.OrderedDict()
+  for i, e in enumerate(ev):
+    if re.search(pat, e.name):
+      k = i % per
+      r = rows.setdefault(k, [re.sub(r'\(.*', '', e.name)[:44], re.sub(r'\(.*', '', ev[i - 1].name)[:60], 0.0, 0])
+      r[2] += e.time_range.end - e.time_range.start
+      r[3] += 1
+  print(f'---- per-launch list of /{pat}/ ({len(rows)} per step)')
+  for k, (n, prev, t, c) in rows.items():
+    print(f'{k:5d} {t / c:8.1f} us  {n:44s} after {prev}')
