@@ -425,8 +425,15 @@ int conv_wgrad_tcgen05(const wlseg_conv_params* p, const void* x, const void* dy
   const bool use_pair = BN == 256 && (p->K % 256 == 0) && (prm.chunks_total % 4 == 0) && (p->C % 64 == 0) && pair_env != 0;
   if (use_pair) prm.m_tiles /= 2;
   prm.tiles = prm.m_tiles * prm.n_tiles;
-  // pixel splits: about two waves of work units, at least 4 patches per split
-  int splits = (2 * (use_pair ? conv_sms() / 2 : conv_sms())) / prm.tiles;
+  // pixel splits: about one wave of work units, at least 4 patches per split
+  // work units per SM (pair) the pixel splits aim at.  Round 1 took two waves; every split adds one fp32 reduce-add
+  // pass over dw through L2 (a 1 MB 256 <-> 1024 gradient was summed 37 times: those launches sat at 0.46 of their byte
+  // bound), and one wave measured faster on the whole step: 10.84 -> 10.68 / 10.75 ms (three waves: 10.88 / 10.97).
+  static const int waves = [] {
+    const char* e = getenv("WLSEG_WGRAD_WAVES");
+    return e != nullptr && atoi(e) > 0 ? atoi(e) : 1;
+  }();
+  int splits = (waves * (use_pair ? conv_sms() / 2 : conv_sms())) / prm.tiles;
   const int max_splits = prm.patches / 4 > 0 ? prm.patches / 4 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
