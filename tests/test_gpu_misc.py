@@ -12,7 +12,7 @@ from oracle import tfops
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('shape,k,s', [((2, 12, 16, 64), 3, 2), ((1, 9, 7, 8), 3, 2), ((1, 8, 8, 16), 1, 2)])
+@pytest.mark.parametrize('shape,k,s', [((2, 12, 16, 64), 3, 2), ((1, 9, 7, 8), 3, 2), ((1, 8, 8, 16), 1, 2), ((2, 37, 45, 64), 3, 2)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_maxpool_same_fwd_bwd(cuda, shape, k, s, dtype):
   from wlseg import ops
