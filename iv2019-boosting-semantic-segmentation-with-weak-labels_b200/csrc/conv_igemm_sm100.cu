@@ -690,8 +690,13 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams prm) {
               for (int g = 0; g < 4; ++g) {
                 __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&outv[g]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  ho[e] = __floats2bfloat162_rn(fmaxf(f[g * 8 + 2 * e], 0.f), fmaxf(f[g * 8 + 2 * e + 1], 0.f));
+                for (int e = 0; e < 4; ++e) {
+                  // cvt.rn.relu: clamp and round in ONE instruction (rounding is monotone and keeps zero: the same bits
+                  // as fmaxf followed by the conversion, 64 FMNMX per step less)
+                  uint32_t packed;
+                  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(f[g * 8 + 2 * e + 1]), "f"(f[g * 8 + 2 * e]));
+                  reinterpret_cast<uint32_t*>(ho)[e] = packed;
+                }
               }
             } else {
               // training forward (raw z) and every data gradient: no clamp - 64 FMNMX of a ~650-instruction step that
