@@ -97,36 +97,79 @@ zero_insert_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int P,
   }
 }
 
-// All dgrad filter banks of the network in ONE launch: blockIdx.y = layer (table row
-// {src_off, dst_off, K, R, S, C}), dst[c][R-1-r][S-1-s][k] = src[k][r][s][c]: per tap a K x C -> C x K
-// transpose, done in 64 x 64 tiles through shared memory (reads coalesced along c, writes along k).
+// All dgrad filter banks of the network in ONE launch (table row per layer: {src_off, dst_off, K, R, S, C}),
+// dst[c][R-1-r][S-1-s][k] = src[k][r][s][c]: per tap a K x C -> C x K transpose, done in 64 x 64 tiles through shared
+// memory (reads coalesced along c, writes along k).  Round 2: ONE flat list of tiles over all layers, walked by a
+// persistent 1-D grid (the first version gave every layer 48 CTAs: the three 512 x 3 x 3 x 512 banks were the long pole
+// while the CTAs of the small layers had nothing to do), and 4-byte accesses for 2-byte elements: 124 us -> see
+// profiles/r2_timeline_train.txt.
+constexpr int kFlipMaxLayers = 512;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-transpose_flip_batched_kernel(const T* __restrict__ src, T* __restrict__ dst, const int32_t* __restrict__ table) {
+transpose_flip_batched_kernel(const T* __restrict__ src, T* __restrict__ dst, const int32_t* __restrict__ table,
+                              int n_layers) {
   __shared__ T tile[64][66];
-  const int32_t* e = table + 6 * blockIdx.y;
-  const int64_t so = e[0], dofs = e[1];
-  const int K = e[2], R = e[3], S = e[4], C = e[5];
-  const int RS = R * S;
-  const int kt = (K + 63) / 64, ct = (C + 63) / 64;
-  const int units = RS * kt * ct;
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int tap = u / (kt * ct);
-    const int rem = u - tap * (kt * ct);
+  __shared__ int pref[kFlipMaxLayers + 1];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < n_layers; ++l) {
+      const int32_t* e = table + 6 * l;
+      pref[l] = acc;
+      acc += e[3] * e[4] * ((e[2] + 63) / 64) * ((e[5] + 63) / 64);
+    }
+    pref[n_layers] = acc;
+  }
+  __syncthreads();
+  const int total = pref[n_layers];
+  int layer = 0;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    while (u >= pref[layer + 1]) ++layer;   // u only grows
+    const int32_t* e = table + 6 * layer;
+    const int64_t so = e[0], dofs = e[1];
+    const int K = e[2], R = e[3], S = e[4], C = e[5];
+    const int RS = R * S;
+    const int kt = (K + 63) / 64, ct = (C + 63) / 64;
+    const int lu = u - pref[layer];
+    const int tap = lu / (kt * ct);
+    const int rem = lu - tap * (kt * ct);
     const int k0 = (rem / ct) * 64, c0 = (rem % ct) * 64;
     const int tap2 = RS - 1 - tap;  // (R-1-r)*S + (S-1-s)
+    const bool vec2 = sizeof(T) == 2 && ((K | C) & 1) == 0 && ((so | dofs) & 1) == 0;
+    if (vec2) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int idx = threadIdx.x + i * 256;
-      const int kk = idx >> 6, cc = idx & 63;
-      if (k0 + kk < K && c0 + cc < C) tile[kk][cc] = src[so + ((int64_t)(k0 + kk) * RS + tap) * C + c0 + cc];
-    }
-    __syncthreads();
+      for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        const int kk = idx >> 5, cc = (idx & 31) * 2;
+        if (k0 + kk < K && c0 + cc < C)
+          *reinterpret_cast<uint32_t*>(&tile[kk][cc]) =
+              *reinterpret_cast<const uint32_t*>(src + so + ((int64_t)(k0 + kk) * RS + tap) * C + c0 + cc);
+      }
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int idx = threadIdx.x + i * 256;
-      const int cc = idx >> 6, kk = idx & 63;
-      if (k0 + kk < K && c0 + cc < C) dst[dofs + ((int64_t)(c0 + cc) * RS + tap2) * K + k0 + kk] = tile[kk][cc];
+      for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        const int cc = idx >> 5, kk = (idx & 31) * 2;
+        if (k0 + kk < K && c0 + cc < C) {
+          const uint32_t lo = *reinterpret_cast<const uint16_t*>(&tile[kk][cc]);
+          const uint32_t hi = *reinterpret_cast<const uint16_t*>(&tile[kk + 1][cc]);
+          *reinterpret_cast<uint32_t*>(dst + dofs + ((int64_t)(c0 + cc) * RS + tap2) * K + k0 + kk) = lo | (hi << 16);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        const int kk = idx >> 6, cc = idx & 63;
+        if (k0 + kk < K && c0 + cc < C) tile[kk][cc] = src[so + ((int64_t)(k0 + kk) * RS + tap) * C + c0 + cc];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        const int cc = idx >> 6, kk = idx & 63;
+        if (k0 + kk < K && c0 + cc < C) dst[dofs + ((int64_t)(c0 + cc) * RS + tap2) * K + k0 + kk] = tile[kk][cc];
+      }
     }
     __syncthreads();
   }
@@ -160,13 +203,13 @@ extern "C" int wlseg_weights_transpose_flip_batched(const void* src_arena, void*
   WLSEG_CHECK_ARG(n_layers >= 0, "transpose_flip_batched: bad layer count");
   if (n_layers == 0) return 0;
   WLSEG_CHECK_ARG(src_arena && dst_arena && table, "transpose_flip_batched: null pointer");
-  WLSEG_CHECK_ARG(n_layers <= 65535, "transpose_flip_batched: too many layers");
-  dim3 grid(48, n_layers);
+  WLSEG_CHECK_ARG(n_layers <= kFlipMaxLayers, "transpose_flip_batched: too many layers");
+  dim3 grid(8 * kNumSMs);
   if (dtype == WLSEG_BF16)
     transpose_flip_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_arena,
-                                                                          (__nv_bfloat16*)dst_arena, table);
+                                                                          (__nv_bfloat16*)dst_arena, table, n_layers);
   else if (dtype == WLSEG_F32)
-    transpose_flip_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src_arena, (float*)dst_arena, table);
+    transpose_flip_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src_arena, (float*)dst_arena, table, n_layers);
   else
     WLSEG_CHECK_ARG(false, "transpose_flip_batched: bad dtype %d", dtype);
   WLSEG_LAUNCH_CHECK();
