@@ -254,6 +254,71 @@ maxpool_bwd_argmax_kernel(const uint8_t* __restrict__ argmax, const T* __restric
   }
 }
 
+// Round 2: row-mapped forms of the two backward kernels the training step launches.  The flat-index kernels above
+// decode (n, h, w, c8) with three 64-bit divisions per 16-byte vector and loop over runtime window bounds: 105 us
+// (3x3 / 2 arg-max backward, 4 x 384 x 384 x 64) and 68 us (the two stride-2 identity shortcuts) against ~16 / ~22 us
+// of bytes.  Here blockIdx.z = image, blockIdx.y = input row, x = (column, channel vector): 32-bit arithmetic only.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_argmax_rows_kernel(const uint8_t* __restrict__ argmax, const T* __restrict__ dy, T* __restrict__ dx,
+                               PoolGeom g) {
+  const int cv = g.C / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.W * cv) return;
+  const int w = idx / cv, c8 = idx - w * cv;
+  const int h = blockIdx.y, n = blockIdx.z;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  int p_lo = h + g.pad_t - g.k + g.stride;
+  p_lo = p_lo <= 0 ? 0 : p_lo / g.stride;
+  const int p_hi = min((h + g.pad_t) / g.stride, g.P - 1);
+  int q_lo = w + g.pad_l - g.k + g.stride;
+  q_lo = q_lo <= 0 ? 0 : q_lo / g.stride;
+  const int q_hi = min((w + g.pad_l) / g.stride, g.Q - 1);
+  for (int p = p_lo; p <= p_hi; ++p) {
+    const int r = h - (p * g.stride - g.pad_t);
+    const int64_t row = ((int64_t)n * g.P + p) * g.Q;
+    for (int q = q_lo; q <= q_hi; ++q) {
+      const int s = w - (q * g.stride - g.pad_l);
+      const uint32_t pos = (uint32_t)(r * g.k + s);
+      const int64_t oi = (row + q) * g.C + c8 * 8;
+      const uint2 am = *reinterpret_cast<const uint2*>(argmax + oi);
+      Vec8<T> gv;
+      gv.load(dy + oi);
+      float gf[8];
+      gv.unpack(gf);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j] += (((am.x >> (8 * j)) & 255u) == pos) ? gf[j] : 0.f;
+        acc[4 + j] += (((am.y >> (8 * j)) & 255u) == pos) ? gf[4 + j] : 0.f;
+      }
+    }
+  }
+  Vec8<T> o;
+  o.pack(acc);
+  o.store(dx + (((int64_t)n * g.H + h) * g.W + w) * g.C + c8 * 8);
+}
+
+// k = 1 (the stride-s subsampling of an identity shortcut): dx is dy scattered onto the sampled cells, zero elsewhere
+template <typename T>
+__global__ void __launch_bounds__(256)
+subsample_bwd_rows_kernel(const T* __restrict__ dy, T* __restrict__ dx, PoolGeom g) {
+  const int cv = g.C / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.W * cv) return;
+  const int w = idx / cv, c8 = idx - w * cv;
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int hh = h + g.pad_t, ww = w + g.pad_l;
+  const int p = hh / g.stride, q = ww / g.stride;
+  Vec8<T> v;
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  v.pack(z);
+  if (p * g.stride == hh && q * g.stride == ww && p < g.P && q < g.Q)
+    v.load(dy + (((int64_t)n * g.P + p) * g.Q + q) * g.C + c8 * 8);
+  v.store(dx + (((int64_t)n * g.H + h) * g.W + w) * g.C + c8 * 8);
+}
+
 static int make_geom(PoolGeom& g, int N, int H, int W, int C, int k, int stride) {
   WLSEG_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0, "maxpool: bad shape");
   WLSEG_CHECK_ARG(C % 8 == 0, "maxpool: C (%d) must be a multiple of 8", C);
@@ -312,6 +377,30 @@ extern "C" int wlseg_maxpool_same_bwd(const void* x, const uint8_t* argmax, cons
   WLSEG_CHECK_ARG((x || argmax) && dy && dx, "maxpool_bwd: null pointer");
   int64_t items = (int64_t)N * H * W * (C / 8);
   int grid = bw_grid(items, 256, 8);
+  const bool rows_ok = H <= 65535 && N <= 65535 && getenv("WLSEG_POOL_FLAT") == nullptr;
+  const dim3 rgrid((unsigned)ceil_div((int64_t)W * (C / 8), 256), (unsigned)H, (unsigned)N);
+  if (rows_ok && ksize == 1) {
+    // dx depends on dy alone (every window is one cell)
+    if (dtype == WLSEG_BF16)
+      subsample_bwd_rows_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, g);
+    else if (dtype == WLSEG_F32)
+      subsample_bwd_rows_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (float*)dx, g);
+    else
+      WLSEG_CHECK_ARG(false, "maxpool_bwd: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
+  if (rows_ok && argmax != nullptr) {
+    if (dtype == WLSEG_BF16)
+      maxpool_bwd_argmax_rows_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(argmax, (const __nv_bfloat16*)dy,
+                                                                              (__nv_bfloat16*)dx, g);
+    else if (dtype == WLSEG_F32)
+      maxpool_bwd_argmax_rows_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(argmax, (const float*)dy, (float*)dx, g);
+    else
+      WLSEG_CHECK_ARG(false, "maxpool_bwd: bad dtype %d", dtype);
+    WLSEG_LAUNCH_CHECK();
+    return 0;
+  }
   if (argmax != nullptr) {
     if (dtype == WLSEG_BF16)
       maxpool_bwd_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(argmax, (const __nv_bfloat16*)dy,
