@@ -41,7 +41,10 @@ def units(output_stride=8):
 
 
 def adaptation_units(d=256):
-  return [UnitSpec(f'adaptation_module/{br}/bottleneck_v1', d, d, d, 1, 1, False) for br, _ in BRANCHES]
+  # resnet_v1.bottleneck(..., scope='l1_features') (resnet50_extended_model_hierarchical.py:59-72): an explicit scope REPLACES
+  # the default 'bottleneck_v1' of tf.variable_scope(scope, 'bottleneck_v1') - the variables are adaptation_module/<branch>/convK/...
+  # (confirmed by running the reference's model() over tests/golden/tf_shim, which records the names it asks for)
+  return [UnitSpec(f'adaptation_module/{br}', d, d, d, 1, 1, False) for br, _ in BRANCHES]
 
 
 PSP_SCOPES = tuple('feature_extractor/pyramid_module/Conv' + ('' if i == 0 else f'_{i}') for i in range(5))

@@ -11,17 +11,21 @@ uninstallable third-party dependency `tensorflow==1.12.0`
 (`code/requirements.txt:9`), and none of the reference's own tests exercises the
 model, the loss, the estimator or the metrics.
 PINNED (round 2) by golden vectors produced by RUNNING THE REFERENCE'S OWN PYTHON
-over an emulation of the TF-1.12 calls it makes (tests/golden/tf_shim,
-tests/golden/make_reference_fixtures.py -> tests/golden/reference_run.npz,
-checked in tests/test_reference_fixtures.py): losses.py, weak_labels.py,
-metrics.py, optimizer.py, preprocess.py and the remap / resize / void helpers.
-PARITY UNPINNED for network.py / tfops.py (the ResNet-50 body is
-`tf.contrib.slim`'s `resnet_v1_50`, un-vendored: restated from the published
-behaviour of TF 1.12, pinned only by the worked examples the reference carries
-in its comments, SURVEY.md section 8c, `tests/test_oracle_known_answers.py`).
-The shim is itself our reading of TF's op semantics, so "pinned" means: the
-reference's own call graph, constants, masks, tables and reductions are the ones
-that ran - not that TensorFlow's kernels did.
+over an emulation of the TF-1.12 / tf.contrib.slim calls it makes
+(tests/golden/tf_shim): tests/golden/reference_run.npz (losses.py,
+weak_labels.py, metrics.py, optimizer.py, preprocess.py, the remap / resize /
+void helpers) and tests/golden/reference_model_run.npz (network.py: the
+reference's `model()` + `feature_extractor()` + `module_arg_scope()` executed
+on 330-variable parameter dictionaries, five configurations incl. training-mode
+batch norm, pyramid / field-of-view / hybrid upsampling and group norm) -
+checked in tests/test_reference_fixtures.py (oracle) and
+tests/test_gpu_reference_fixtures.py (CUDA path, no oracle in between).
+What stays RESTATED: TensorFlow's and slim's own internals (un-vendored): the
+shim is our reading of the op semantics (SAME padding split, fused batch norm,
+resize_bilinear align_corners, resnet_v1's output-stride bookkeeping, variable
+scoping rules ...), so "pinned" means: the reference's own call graph, wiring,
+constants, masks, tables and reductions are the ones that ran - not that
+TensorFlow's kernels did.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import this package, and only as the checker.  The

@@ -1,7 +1,8 @@
 """Oracle forward pass: ResNet-50 (OS8) + extension + adaptation + hierarchical heads.
 
-TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED (the
-ResNet-50 graph itself is tf.contrib.slim's `resnet_v1_50`, un-vendored).
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Pinned against the reference's own
+`model()` run over tests/golden/tf_shim (tests/golden/reference_model_run.npz: identical
+decisions, logits to 0 .. 1e-4); slim's `resnet_v1_50` internals themselves are restated.
 
 Follows, in order:
   code/models/resnet50_extended_feature_extractor.py:8-51   (base + decrease_fdims)
@@ -61,7 +62,7 @@ def conv_specs(dataset='cityscapes', feature_dims_decreased=256, psp=False, fov=
       specs[sc] = (1, 1, d, d)
     specs[PSP_SCOPES[4]] = (1, 1, 5 * d, d)
   for br in ('l1_features', 'l2_vehicle_features', 'l2_human_features'):
-    sc = f'adaptation_module/{br}/bottleneck_v1'
+    sc = f'adaptation_module/{br}'
     specs[f'{sc}/conv1'] = (1, 1, d, d)
     specs[f'{sc}/conv2'] = (3, 3, d, d)
     specs[f'{sc}/conv3'] = (1, 1, d, d)
@@ -284,7 +285,7 @@ class Net:
     out = []
     for br, lg in (('l1_features', 'l1_logits'), ('l2_vehicle_features', 'l2_vehicle_logits'),
                    ('l2_human_features', 'l2_human_logits')):
-      a = self._bottleneck(f, f'adaptation_module/{br}/bottleneck_v1', d, d, 1, 1)
+      a = self._bottleneck(f, f'adaptation_module/{br}', d, d, 1, 1)
       # slim.conv2d(activation_fn=None) inside the arg scope: BN still applied
       out.append(self._conv_bn(a, f'softmax_classifier/{lg}', relu=False, fp32_out=True))
     if self.upsampling == 'hybrid':

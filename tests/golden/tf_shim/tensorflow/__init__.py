@@ -547,6 +547,35 @@ def _deprecated(date, instructions):
 
 _register('tensorflow.python.util.deprecation', deprecated=_deprecated)
 
+# ------------------------------------------------------------------------------------------------ tf.contrib.slim & co
+# (tensorflow/_slim.py: what the reference's model code calls of slim, tf.contrib.layers and slim.nets.resnet_v1)
+from tensorflow import _slim  # noqa: E402
+
+variable_scope = _slim.variable_scope   # the stack-keeping version: slim variables are looked up by scope path
+nn.relu = _slim.relu
+_layers_ns = types.SimpleNamespace(avg_pool2d=_slim.avg_pool2d, batch_norm=_slim.batch_norm, group_norm=_slim.group_norm)
+_resnet_v1 = _register('tensorflow.contrib.slim.nets.resnet_v1', resnet_v1_50=_slim.resnet_v1_50, bottleneck=_slim.bottleneck)
+_resnet_utils = _register('tensorflow.contrib.slim.nets.resnet_utils', conv2d_same=_slim.conv2d_same, subsample=_slim.subsample)
+_nets = _register('tensorflow.contrib.slim.nets', resnet_v1=_resnet_v1, resnet_utils=_resnet_utils)
+_slim_mod = _register('tensorflow.contrib.slim', arg_scope=_slim.arg_scope, add_arg_scope=_slim.add_arg_scope, conv2d=_slim.conv2d,
+                      conv2d_transpose=_slim.conv2d_transpose, batch_norm=_slim.batch_norm, max_pool2d=_slim.max_pool2d,
+                      avg_pool2d=_slim.avg_pool2d, layers=_layers_ns, l2_regularizer=_slim.l2_regularizer,
+                      variance_scaling_initializer=_slim.variance_scaling_initializer, nets=_nets)
+_framework = _register('tensorflow.contrib.framework', arg_scope=_slim.arg_scope, add_arg_scope=_slim.add_arg_scope)
+_layers = _register('tensorflow.contrib.layers', batch_norm=_slim.batch_norm, group_norm=_slim.group_norm,
+                    l2_regularizer=_slim.l2_regularizer, variance_scaling_initializer=_slim.variance_scaling_initializer)
+_register('tensorflow.contrib', slim=_slim_mod, framework=_framework, layers=_layers)
+
+
+class _BaseLayer:
+  """base class only: utils/cross_replica_batch_normalization.py derives from tf.layers.BatchNormalization at import time"""
+
+  def __init__(self, *a, **k):
+    raise NotImplementedError('tf shim: tf.layers.BatchNormalization is not emulated')
+
+
+_register('tensorflow.layers', BatchNormalization=_BaseLayer, Layer=_BaseLayer)
+
 sys.meta_path.insert(0, _Finder())
 for _name, _m in list(_SUBMODULES.items()):
   sys.modules[_name] = _m

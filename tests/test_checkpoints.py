@@ -52,7 +52,7 @@ def test_predict_saver_keys():
   plain = ck.predict_var_dict(p, restore_emas=False)
   assert all(k == v for k, v in plain.items()) and len(plain) == 330
   emas = ck.predict_var_dict(p, restore_emas=True)
-  sc = 'adaptation_module/l1_features/bottleneck_v1/conv2'
+  sc = 'adaptation_module/l1_features/conv2'
   assert emas[f'exponential_moving_averages/{sc}/weights/ExponentialMovingAverage'] == f'{sc}/weights'
   assert emas[f'exponential_moving_averages/{sc}/BatchNorm/gamma/ExponentialMovingAverage'] == f'{sc}/BatchNorm/gamma'
   assert emas[f'{sc}/BatchNorm/moving_mean'] == f'{sc}/BatchNorm/moving_mean'

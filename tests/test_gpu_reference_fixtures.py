@@ -191,3 +191,98 @@ def test_resize_crop_kernel_equals_the_reference_run(cuda, gold, tag):
     g = torch.Generator().manual_seed(1)
     b = wpre.resize_images_and_labels(img, lab, target, True, generator=g)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and tuple(a[0].shape[1:3]) == target
+
+
+# ------------------------------------------------------------------------------------------------ the network
+# tests/golden/reference_model_run.npz: the reference's own model() executed over tests/golden/tf_shim (+ _slim.py)
+MODEL_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_model_run.npz')
+
+
+@pytest.fixture(scope='module')
+def model_gold():
+  return np.load(MODEL_GOLD)
+
+
+def _model_case(tag):
+  import importlib.util
+  spec = importlib.util.spec_from_file_location('make_reference_model_fixtures', os.path.join(
+      os.path.dirname(os.path.abspath(__file__)), 'golden', 'make_reference_model_fixtures.py'))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)          # only main() touches /root/reference
+  return gen, gen.CASES[tag], gen.case_params(tag)
+
+
+def _build(cuda, tag, dtype, train=False):
+  from wlseg import network
+  gen, (dataset, N, H, W, _, accumulate, init_kw, flags), tfp = _model_case(tag)
+  hier = _hier(dataset)
+  params = network.Params(hier, cuda, psp=init_kw.get('psp', False), fov=init_kw.get('fov'),
+                          upsampling=init_kw.get('upsampling', 'bilinear'), norm=init_kw.get('norm', 'batch'))
+  params.load_tf_dict(tfp)
+  cls = network.TrainNetwork if (train or init_kw.get('norm') == 'group') else network.Network
+  return gen, hier, tfp, params, cls(params, dtype=dtype)
+
+
+@pytest.mark.parametrize('tag', ['cs_eval', 'vistas_eval', 'cs_psp_fov_hybrid', 'cs_group'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_network_equals_the_reference_model_run(cuda, model_gold, tag, dtype):
+  """The CUDA forward pass (wlseg.network: convolutions, folded batch norm / group norm, pooling, pyramid module,
+  transposed-convolution upsampler, head) against the predictions the REFERENCE's model() produced for the same
+  variables and images.  fp32 check mode: full-resolution logits 1e-4 of their maximum (north star), decisions equal
+  except where two logits tie to that level (<= 0.2 % of the pixels); bf16 product path: logits rel-L2 <= 2e-2
+  (5e-2 for group norm, which normalises by the statistics of the rounded tensor itself)."""
+  gen, hier, tfp, params, net = _build(cuda, tag, dtype)
+  images = torch.from_numpy(model_gold[f'{tag}/images'])
+  out = net.predict(images.to(cuda), want=('logits', 'decisions', 'l1_decisions', 'l2_vehicle_decisions', 'l2_human_decisions'))
+  torch.cuda.synchronize()
+  s = gen.LOGIT_STRIDE
+  worst_max, num, den = 0.0, 0.0, 0.0
+  for k in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits'):
+    want = torch.from_numpy(model_gold[f'{tag}/{k}'])
+    got = out[k].cpu()[:, ::s, ::s]
+    assert got.shape == want.shape
+    worst_max = max(worst_max, float((got - want).abs().max()) / float(want.abs().max()))
+    num += float((got - want).double().pow(2).sum())
+    den += float(want.double().pow(2).sum())
+  rel_l2 = (num / den) ** 0.5
+  mism = max(float((out[k].cpu() != torch.from_numpy(model_gold[f'{tag}/{k}'].astype(np.int32))).float().mean())
+             for k in ('decisions', 'l1_decisions', 'l2_vehicle_decisions', 'l2_human_decisions'))
+  print(f'{tag} {dtype}: logits max-rel {worst_max:.2e}, rel-L2 {rel_l2:.2e}, decision mismatch {100 * mism:.3f} %')
+  if dtype == torch.float32:
+    assert worst_max <= 1e-4 and mism <= 2e-3
+  else:
+    assert rel_l2 <= (5e-2 if tag == 'cs_group' else 2e-2) and mism <= 0.08
+
+
+def test_training_mode_network_equals_the_reference_model_run(cuda, model_gold):
+  """Training-mode batch norm (batch statistics in every layer, `batch_norm_accumulate_statistics`): the fp32 check mode's
+  forward_train against the reference run - logits 1e-3 of their maximum (70 positions per channel in the deepest
+  layers: last-bit differences are amplified layer after layer, the oracle itself is at 1e-4 here), and the moving
+  statistics it leaves behind against moving - (1 - decay) * (moving - statistic) with the reference run's batch mean
+  and Bessel-corrected variance."""
+  tag = 'cs_train_bn'
+  gen, hier, tfp, params, net = _build(cuda, tag, torch.float32, train=True)
+  images = torch.from_numpy(model_gold[f'{tag}/images'])
+  N, H, W, _ = images.shape
+  low = net.forward_train(images.to(cuda))
+  out = net.head(low, H, W, ('logits', 'decisions'))
+  torch.cuda.synchronize()
+  s = gen.LOGIT_STRIDE
+  for k in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits'):
+    want = torch.from_numpy(model_gold[f'{tag}/{k}'])
+    got = out[k].cpu()[:, ::s, ::s]
+    err = float((got - want).abs().max()) / float(want.abs().max())
+    print(f'{k}: {err:.2e}')
+    assert err <= 1e-3, k
+  assert float((out['decisions'].cpu() != torch.from_numpy(model_gold[f'{tag}/decisions'].astype(np.int32))).float().mean()) <= 5e-3
+  back = params.to_tf_dict()
+  scopes = sorted({k.split('/update/')[1].rsplit('/', 1)[0] for k in model_gold.files if k.startswith(f'{tag}/update/')})
+  assert len(scopes) >= 3
+  for sc in scopes:
+    mean = torch.from_numpy(model_gold[f'{tag}/update/{sc}/mean'])
+    var = torch.from_numpy(model_gold[f'{tag}/update/{sc}/unbiased_variance'])
+    want_mean = tfp[f'{sc}/moving_mean'] - 0.1 * (tfp[f'{sc}/moving_mean'] - mean)
+    want_var = tfp[f'{sc}/moving_variance'] - 0.1 * (tfp[f'{sc}/moving_variance'] - var)
+    em = float((back[f'{sc}/moving_mean'].cpu() - want_mean).abs().max()) / (float(want_mean.abs().max()) + 1e-6)
+    ev = float((back[f'{sc}/moving_variance'].cpu() - want_var).abs().max()) / float(want_var.abs().max())
+    assert em <= 1e-3 and ev <= 1e-3, (sc, em, ev)

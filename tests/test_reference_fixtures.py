@@ -184,3 +184,131 @@ def test_resize_and_crop_equals_reference(gold, tag):
   assert 0 <= off[0] <= RH - target[0] and 0 <= off[1] <= RW - target[1]
   if preserve:   # tight fit: one of the two axes has no slack
     assert RH == target[0] or RW == target[1]
+
+
+# ------------------------------------------------------------------------------------------------ the network
+# tests/golden/reference_model_run.npz: the reference's own model() executed over tests/golden/tf_shim (+ _slim.py)
+MODEL_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_model_run.npz')
+MODEL_CASES = ['cs_eval', 'cs_train_bn', 'vistas_eval', 'cs_psp_fov_hybrid', 'cs_group']
+
+
+@pytest.fixture(scope='module')
+def model_gold():
+  return np.load(MODEL_GOLD)
+
+
+def _model_case(tag):
+  import importlib.util
+  spec = importlib.util.spec_from_file_location('make_reference_model_fixtures', os.path.join(
+      os.path.dirname(os.path.abspath(__file__)), 'golden', 'make_reference_model_fixtures.py'))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)          # only main() touches /root/reference
+  return gen, gen.CASES[tag], gen.case_params(tag)
+
+
+@pytest.mark.parametrize('tag', MODEL_CASES)
+def test_oracle_network_equals_the_reference_model_run(model_gold, tag):
+  """oracle/network.py::Net against the predictions the REFERENCE's model() returned (feature_extractor, arg scope,
+  adaptation bottlenecks, logits + normaliser, upsampler, pyramid / field-of-view / hybrid-upsampling / group-norm
+  variants, softmax / argmax / decision composition): logits 1e-5 of their maximum on the stored grid, every
+  decision map equal."""
+  from oracle import network as onet
+  gen, (dataset, N, H, W, train, accumulate, init_kw, flags), tfp = _model_case(tag)
+  assert abs(gen.checksum(tfp) - float(model_gold[f'{tag}/params_checksum'])) <= 1e-6 * float(model_gold[f'{tag}/params_checksum'])
+  images = torch.from_numpy(model_gold[f'{tag}/images'])
+  assert torch.equal(images, gen.case_images(tag))
+  net = onet.Net(tfp, dataset, training=accumulate, psp=init_kw.get('psp', False), fov=init_kw.get('fov'),
+                 upsampling=init_kw.get('upsampling', 'bilinear'), norm=init_kw.get('norm', 'batch'))
+  with torch.no_grad():
+    pred = net.forward(images)
+  s = gen.LOGIT_STRIDE
+  # inference-mode normalisation: 1e-5 and identical decisions.  Normalising by the statistics of the tensor itself
+  # (training-mode batch norm over 2 x 5 x 7 positions, group norm per sample) amplifies the last-bit differences of
+  # two fp32 evaluation orders layer after layer: 1e-3, and decisions may differ where two logits tie to that level
+  exact = tag not in ('cs_train_bn', 'cs_group')
+  tol = 1e-5 if exact else 1e-3
+  worst = 0.0
+  for k in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits'):
+    want = torch.from_numpy(model_gold[f'{tag}/{k}'])
+    got = pred[k][:, ::s, ::s]
+    assert got.shape == want.shape
+    err = float((got - want).abs().max()) / float(want.abs().max())
+    worst = max(worst, err)
+    assert err <= tol, (k, err)
+  for k in ('decisions', 'l1_decisions', 'l2_vehicle_decisions', 'l2_human_decisions'):
+    want = torch.from_numpy(model_gold[f'{tag}/{k}'].astype(np.int32))
+    got = pred[k].to(torch.int32)
+    if exact:
+      assert torch.equal(got, want), k
+    else:
+      assert float((got != want).float().mean()) <= 5e-3, k
+  print(f'{tag}: worst logits error {worst:.2e} of the maximum')
+
+
+@pytest.mark.parametrize('tag', ['cs_eval', 'cs_psp_fov_hybrid', 'cs_group'])
+def test_product_variable_names_equal_what_the_reference_model_asks_for(model_gold, tag):
+  """The checkpoint variable names and shapes of the product (wlseg/arch.py, wlseg/checkpoints.py) are EXACTLY the
+  variables the reference's model() requested from the variable store while it ran (slim's scoping rules restated in
+  tests/golden/tf_shim/tensorflow/_slim.py): e.g. adaptation_module/l1_features/conv1/weights - an explicit `scope`
+  replaces resnet_v1.bottleneck's default 'bottleneck_v1' - and the default scopes Conv .. Conv_4 / Conv2d_transpose .. _2."""
+  import types
+  from wlseg import arch, checkpoints as ck
+  gen, (dataset, N, H, W, train, accumulate, init_kw, flags), tfp = _model_case(tag)
+  up = init_kw.get('upsampling', 'bilinear')
+  specs = arch.conv_specs((14, 7, 3), psp=init_kw.get('psp', False), fov=init_kw.get('fov'), upsampling=up)
+  p = types.SimpleNamespace(specs=specs, norm=init_kw.get('norm', 'batch'),
+                            plain=tuple(arch.UPSAMPLING_SCOPES) if up == 'hybrid' else ())
+  mine = dict(ck.model_variables(p))
+  asked = str(model_gold[f'{tag}/variables']).split('\n')
+  assert len(set(asked)) == len(asked)
+  assert set(mine) == set(asked), sorted(set(mine) ^ set(asked))[:6]
+  for name, shape in mine.items():
+    assert tuple(tfp[name].shape) == tuple(shape), name
+  # every convolution kernel carries an L2 regulariser (module_arg_scope, _create_upsampler); its weight is
+  # --regularization_weight in TRAIN mode (the evaluation graph keeps module_arg_scope's default, where it is unused)
+  reg = [l.split() for l in str(model_gold[f'{tag}/regularized']).split('\n')]
+  assert {n for n, _ in reg} == {n for n in mine if n.endswith('/weights')}
+  reg = [l.split() for l in str(model_gold['cs_train_bn/regularized']).split('\n')]
+  assert len(reg) == 66 and {float(v) for _, v in reg} == {0.00017}
+
+
+def test_arg_scope_constants_of_the_reference_run(model_gold):
+  """module_arg_scope as it actually reached the normaliser calls (resnet50_extended_model_hierarchical.py:278-354):
+  epsilon 1e-5, scale (gamma) on, decay = --batch_norm_decay in TRAIN, is_training = batch_norm_accumulate_statistics;
+  group norm: 32 groups, 1 for the logits layers (`args_context(groups=1)`, :75-77)."""
+  from wlseg import network
+  import inspect
+  calls = [l.split() for l in str(model_gold['cs_train_bn/norm_calls']).split('\n')]
+  assert len(calls) == 66 and {c[1] for c in calls} == {'batch'}
+  assert {(float(c[2]), float(c[3]), c[4], c[5]) for c in calls} == {(0.9, 1e-5, 'True', 'True')}
+  calls = [l.split() for l in str(model_gold['cs_eval/norm_calls']).split('\n')]
+  assert {(float(c[3]), c[4], c[5]) for c in calls} == {(1e-5, 'True', 'False')}
+  sig = inspect.signature(network.TrainNetwork.__init__).parameters
+  assert sig['bn_decay'].default == 0.9 and sig['eps'].default == 1e-5
+  calls = [l.split() for l in str(model_gold['cs_group/norm_calls']).split('\n')]
+  groups = {c[0].rsplit('/', 1)[0]: int(c[5]) for c in calls}
+  assert {g for s, g in groups.items() if s.startswith('softmax_classifier/')} == {1}
+  assert {g for s, g in groups.items() if not s.startswith('softmax_classifier/')} == {32}
+  assert {float(c[3]) for c in calls} == {1e-5}
+
+
+def test_moving_statistics_of_the_reference_run(model_gold):
+  """Training-mode batch norm of the reference run: the statistics a layer would push into its moving averages (batch
+  mean, Bessel-corrected batch variance - [TF-1.12] fused batch norm) against the oracle's `new_moving`."""
+  from oracle import network as onet
+  gen, (dataset, N, H, W, train, accumulate, init_kw, flags), tfp = _model_case('cs_train_bn')
+  net = onet.Net(tfp, dataset, training=True, bn_decay=0.9)
+  with torch.no_grad():
+    net.forward(torch.from_numpy(model_gold['cs_train_bn/images']))
+  scopes = sorted({k.split('/update/')[1].rsplit('/', 1)[0] for k in model_gold.files if k.startswith('cs_train_bn/update/')})
+  assert len(scopes) >= 3
+  for sc in scopes:
+    mean = torch.from_numpy(model_gold[f'cs_train_bn/update/{sc}/mean'])
+    var = torch.from_numpy(model_gold[f'cs_train_bn/update/{sc}/unbiased_variance'])
+    decay = float(model_gold[f'cs_train_bn/update/{sc}/decay'])
+    assert decay == 0.9
+    want_mean = tfp[f'{sc}/moving_mean'] - (1 - decay) * (tfp[f'{sc}/moving_mean'] - mean)
+    want_var = tfp[f'{sc}/moving_variance'] - (1 - decay) * (tfp[f'{sc}/moving_variance'] - var)
+    got_mean, got_var = net.new_moving[f'{sc}/moving_mean'], net.new_moving[f'{sc}/moving_variance']
+    assert float((got_mean - want_mean).abs().max()) <= 1e-5 * float(want_mean.abs().max()) + 1e-6, sc
+    assert float((got_var - want_var).abs().max()) <= 1e-5 * float(want_var.abs().max()) + 1e-6, sc

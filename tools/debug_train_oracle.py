@@ -27,7 +27,7 @@ o.record_layers = True
 with torch.no_grad():
   low = o.lowres_logits(images)
 d = 256
-s0 = 'adaptation_module/l1_features/bottleneck_v1/conv1'
+s0 = 'adaptation_module/l1_features/conv1'
 for s in params.specs:
   if s.scope not in net.tape:
     continue
