@@ -17,8 +17,9 @@ weak_labels.py, metrics.py, optimizer.py, preprocess.py, the remap / resize /
 void helpers) and tests/golden/reference_model_run.npz (network.py: the
 reference's `model()` + `feature_extractor()` + `module_arg_scope()` executed
 on 330-variable parameter dictionaries, five configurations incl. training-mode
-batch norm, pyramid / field-of-view / hybrid upsampling and group norm) -
-checked in tests/test_reference_fixtures.py (oracle) and
+batch norm, pyramid / field-of-view / hybrid upsampling and group norm) and
+tests/golden/reference_driver_run.json (argument parsers, train.py / evaluate.py
+overrides, SemanticSegmentation's derived settings) - checked in tests/test_reference_fixtures.py (oracle) and
 tests/test_gpu_reference_fixtures.py (CUDA path, no oracle in between).
 What stays RESTATED: TensorFlow's and slim's own internals (un-vendored): the
 shim is our reading of the op semantics (SAME padding split, fused batch norm,

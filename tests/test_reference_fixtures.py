@@ -312,3 +312,104 @@ def test_moving_statistics_of_the_reference_run(model_gold):
     got_mean, got_var = net.new_moving[f'{sc}/moving_mean'], net.new_moving[f'{sc}/moving_variance']
     assert float((got_mean - want_mean).abs().max()) <= 1e-5 * float(want_mean.abs().max()) + 1e-6, sc
     assert float((got_var - want_var).abs().max()) <= 1e-5 * float(want_var.abs().max()) + 1e-6, sc
+
+
+# ------------------------------------------------------------------------------------------------ the driver layer
+# tests/golden/reference_driver_run.json: the reference's own argument parsers, train.py::_add_extra_args,
+# evaluate.py::_add_extra_args and SemanticSegmentation.__init__ / .train() / .evaluate() executed over tests/golden/tf_shim
+DRIVER_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_driver_run.json')
+# values that name files of the reference's author's machine / checkout, not behaviour
+_PATH_KEYS = {'init_ckpt_path', 'training_problem_def_path', 'tfrecords_path', 'tfrecords_path_per_pixel', 'tfrecords_path_per_bbox',
+              'tfrecords_path_per_image', 'evaluation_problem_def_path', 'inference_problem_def_path', 'ckpt_path'}
+
+
+class _FakeEstimator:
+  def __init__(self, system, calls):
+    self.system, self.calls = system, calls
+
+  def train(self, batches, max_steps):
+    self.calls.append(('train', max_steps))
+
+  def evaluate(self, batches, num_classes, lut=None):
+    # (the product's estimator consumes the batches the input function yields - settings.num_eval_steps of them)
+    self.calls.append(('evaluate', num_classes))
+    C = self.system.settings.output_Nclasses
+    cm = ((np.arange(C * C, dtype=np.int64).reshape(C, C) % 7) + np.eye(C, dtype=np.int64) * 50).astype(np.int32)
+    return {'global_step': 1234, 'loss': 0.5, 'confusion_matrix': cm}
+
+
+def _load_driver_gold():
+  import json
+  with open(DRIVER_GOLD) as fp:
+    return json.load(fp)
+
+
+@pytest.mark.parametrize('tag', ['train_cityscapes_defaults', 'train_vistas_defaults', 'train_cityscapes_flags'])
+def test_train_driver_settings_equal_the_reference_run(tag, tmp_path, monkeypatch):
+  """wlseg.settings (CLI) + train_extra_args + wlseg.system_factory.SemanticSegmentation.__init__ / .train() on the argv
+  the reference run was given: every attribute the REFERENCE left on `system.settings` (parsed flags with their defaults,
+  train.py's hard overrides, derived class count, steps per epoch, total steps, learning-rate boundaries in steps and the
+  values, checkpoint cadence, the EMA switch under --distribute) has the same value here, and the estimator is asked
+  for the same number of steps."""
+  from wlseg import settings as wsettings
+  from wlseg import system_factory as sf
+  gold = _load_driver_gold()[tag]
+  st = wsettings.build_parser(wsettings.TRAIN).parse_args([str(tmp_path / 'log')] + gold['argv'])
+  for k, v in gold['parsed'].items():
+    if k not in _PATH_KEYS:
+      assert getattr(st, k) == v, f'parsed flag {k}: {getattr(st, k)!r} != {v!r}'
+  wsettings.train_extra_args(st)
+  st.rank, st.world_size = 0, 1
+  calls = []
+  system = sf.SemanticSegmentation({'train': lambda config, params: iter(())}, None, st)
+  monkeypatch.setattr(system, '_create_estimator',
+                      lambda *a, **k: setattr(system, '_estimator', _FakeEstimator(system, calls)))
+  system.train()
+  mine = vars(system.settings)
+  for k, v in gold['settings'].items():
+    if k in _PATH_KEYS:
+      continue
+    assert k in mine, f'the reference sets settings.{k}, the product does not'
+    assert mine[k] == v, f'settings.{k}: {mine[k]!r} != {v!r} (reference)'
+  want_steps = [kw['max_steps'] for n, kw in gold['calls'] if n == 'train']
+  assert calls == [('train', want_steps[0])]
+
+
+@pytest.mark.parametrize('tag', ['eval_cityscapes', 'eval_vistas'])
+def test_evaluate_driver_settings_equal_the_reference_run(tag, tmp_path, monkeypatch):
+  """The evaluation side of the same: evaluate.py's flags + overrides, derived step counts, the id map to evaluation
+  classes, `eval_NN` directory naming, and the confusion matrix handed back for a given raw one (void row / column
+  trimmed, system_factory.py:400-405)."""
+  from wlseg import settings as wsettings
+  from wlseg import system_factory as sf
+  from wlseg import problem_defs
+  gold = _load_driver_gold()[tag]
+  argv = list(gold['argv'])
+  problem_defs.write_all()
+  argv[1] = problem_defs.default_path(argv[3])    # the same problem definition, at the product's location
+  st = wsettings.build_parser(wsettings.EVAL).parse_args([str(tmp_path / 'log')] + argv)
+  for k, v in gold['parsed'].items():
+    if k not in _PATH_KEYS:
+      assert getattr(st, k) == v, f'parsed flag {k}: {getattr(st, k)!r} != {v!r}'
+  st = wsettings.eval_extra_args(st)
+  st.rank, st.world_size = 0, 1
+  st.synthetic = True
+  os.makedirs(st.log_dir, exist_ok=True)
+  calls = []
+  system = sf.SemanticSegmentation({'eval': lambda config, params: iter(())}, None, st)
+  monkeypatch.setattr(system, '_create_estimator',
+                      lambda *a, **k: setattr(system, '_estimator', _FakeEstimator(system, calls)))
+  import contextlib
+  with contextlib.redirect_stdout(io.StringIO()):
+    metrics = system.evaluate()
+  mine = vars(system.settings)
+  for k, v in gold['settings'].items():
+    if k in _PATH_KEYS:
+      continue
+    assert k in mine, f'the reference sets settings.{k}, the product does not'
+    assert mine[k] == v, f'settings.{k}: {mine[k]!r} != {v!r} (reference)'
+  assert os.path.basename(system.settings.eval_res_dir) == gold['eval_res_dir_name']
+  assert system.settings.num_eval_steps == [kw['steps'] for n, kw in gold['calls'] if n == 'evaluate'][0]
+  assert calls == [('evaluate', gold['settings']['output_Nclasses'])]
+  cm = np.asarray(metrics[0]['confusion_matrix'])
+  assert list(cm.shape) == gold['returned_cm_shape'] and int(cm.sum()) == gold['returned_cm_sum']
