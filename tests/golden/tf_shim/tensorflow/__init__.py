@@ -497,6 +497,7 @@ class _MomentumOptimizer:
 
   def __init__(self, learning_rate, momentum, use_locking=False, name='Momentum', use_nesterov=False):
     self.learning_rate, self.momentum, self.use_nesterov = learning_rate, momentum, use_nesterov
+    self._learning_rate = learning_rate     # the attribute define_estimator reads for its summaries
     self.slots = {}
 
   def apply_dense(self, key, var, grad):
@@ -512,7 +513,7 @@ class _MomentumOptimizer:
 
 class _GradientDescentOptimizer:
   def __init__(self, learning_rate, use_locking=False, name='GradientDescent'):
-    self.learning_rate = learning_rate
+    self.learning_rate = self._learning_rate = learning_rate
 
   def apply_dense(self, key, var, grad):
     return var - self.learning_rate * grad
@@ -565,6 +566,24 @@ _framework = _register('tensorflow.contrib.framework', arg_scope=_slim.arg_scope
 _layers = _register('tensorflow.contrib.layers', batch_norm=_slim.batch_norm, group_norm=_slim.group_norm,
                     l2_regularizer=_slim.l2_regularizer, variance_scaling_initializer=_slim.variance_scaling_initializer)
 _register('tensorflow.contrib', slim=_slim_mod, framework=_framework, layers=_layers)
+
+
+# ------------------------------------------------------------------------------------------------ training machinery
+# (tensorflow/_train.py: global step, UPDATE_OPS, ExponentialMovingAverage, create_train_op, EstimatorSpec)
+from tensorflow import _train  # noqa: E402
+
+GraphKeys = _train.GraphKeys
+model_variables = _train.model_variables
+trainable_variables = _train.trainable_variables
+add_to_collection = _train.add_to_collection
+get_collection = _train.get_collection
+train.get_or_create_global_step = _train.get_or_create_global_step
+train.ExponentialMovingAverage = _train.ExponentialMovingAverage
+train.Scaffold = _train.Scaffold
+train.SecondOrStepTimer = _train.SecondOrStepTimer
+estimator.EstimatorSpec = _train.EstimatorSpec
+_register('tensorflow.contrib.training', create_train_op=_train.create_train_op)
+_SUBMODULES['tensorflow.contrib'].training = _SUBMODULES['tensorflow.contrib.training']
 
 
 class _BaseLayer:

@@ -252,8 +252,12 @@ REGULARIZED = []     # (shim helper) names of the kernels an l2_regularizer was 
 
 
 def l2_regularizer(scale, scope=None):
+  """[TF-1.12] slim.l2_regularizer: scale * tf.nn.l2_loss(w) = scale * sum(w^2) / 2, added to REGULARIZATION_LOSSES."""
   def reg(w, name):
+    import tensorflow as tf
     REGULARIZED.append((name, float(scale)))
+    if w.requires_grad:      # training runs only (the fixture script marks the variables it trains)
+      tf.add_regularization_loss(float(scale) * 0.5 * (w * w).sum())
   return reg
 
 

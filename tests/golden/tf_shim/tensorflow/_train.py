@@ -1,0 +1,156 @@
+"""Eager emulation of the graph-mode TRAINING machinery the reference's `define_estimator` (TRAIN branch,
+code/estimator/define_estimator_hierarchical.py:77-159) assembles: global step, the UPDATE_OPS collection,
+tf.train.ExponentialMovingAverage, tf.contrib.training.create_train_op, EstimatorSpec / Scaffold containers.
+
+Test infrastructure (tests/golden/make_reference_train_fixtures.py only).  TensorFlow is un-vendored: what follows restates
+its published behaviour -
+  * create_train_op(total_loss, optimizer, global_step): every op of GraphKeys.UPDATE_OPS runs BEFORE the gradients are
+    applied (with_dependencies on total_loss), gradients are taken w.r.t. tf.trainable_variables(), apply_gradients
+    increments the global step last;
+  * ExponentialMovingAverage(decay, num_updates, zero_debias).apply(var_list): decay' = min(decay, (1 + n) / (10 + n)),
+    shadow <- shadow - (1 - decay') (shadow - var); the shadow of a tf.Variable starts at the variable's initial value and is
+    NOT zero-debiased (zero_debias only applies to plain tensors); shadow names <scope>/<var>/ExponentialMovingAverage;
+  * fused batch norm's moving-statistic updates (queued by tensorflow/_slim.py::batch_norm) are UPDATE_OPS too.
+The reference's own choices - which variables get an EMA, decay and num_updates, the variable scopes, which loss is
+differentiated, the optimizer and its schedule - are executed, not restated.
+"""
+
+import types
+
+import torch
+
+from tensorflow import _slim
+
+GLOBAL_STEP = [None]
+EMA_SHADOWS = {}     # {shadow variable name: tensor}
+COLLECTIONS = {}     # user collections (tf.add_to_collection)
+OPT_SLOTS = {}       # {variable name: Momentum accumulator} - slot variables outlive the optimizer OBJECT, which the eager
+                     # run re-creates on every step (in TF they are graph variables `train_ops/<var>/Momentum`)
+
+
+class GraphKeys:
+  UPDATE_OPS = 'update_ops'
+  REGULARIZATION_LOSSES = 'regularization_losses'
+  GLOBAL_VARIABLES = 'variables'
+  TRAINABLE_VARIABLES = 'trainable_variables'
+  MODEL_VARIABLES = 'model_variables'
+
+
+def reset():
+  GLOBAL_STEP[0] = None
+  EMA_SHADOWS.clear()
+  COLLECTIONS.clear()
+  OPT_SLOTS.clear()
+
+
+class _Var:
+  """What tf.model_variables() hands out: `.name` ('<scope>:0'), `.op.name`, and the live tensor."""
+
+  def __init__(self, name):
+    self.name = name + ':0'
+    self.op = types.SimpleNamespace(name=name)
+    self.key = name
+
+  @property
+  def value(self):
+    return _slim.VARS[self.key]
+
+
+def model_variables():
+  seen, out = set(), []
+  for n in _slim.REQUESTED:      # slim registers every variable it creates as a model variable, in creation order
+    if n not in seen:
+      seen.add(n)
+      out.append(_Var(n))
+  return out
+
+
+def trainable_variables():
+  return [v for v in model_variables() if '/moving_' not in v.key]
+
+
+def get_or_create_global_step():
+  if GLOBAL_STEP[0] is None:
+    GLOBAL_STEP[0] = torch.zeros((), dtype=torch.int64)
+  return GLOBAL_STEP[0]
+
+
+def add_to_collection(name, value):
+  COLLECTIONS.setdefault(name, []).append(value)
+
+
+def get_collection(name, scope=None):
+  return list(COLLECTIONS.get(name, []))
+
+
+class ExponentialMovingAverage:
+  def __init__(self, decay, num_updates=None, zero_debias=False, name='ExponentialMovingAverage'):
+    self.decay, self.num_updates, self.name = float(decay), num_updates, name
+    self.scope = _slim._prefix()
+
+  def apply(self, var_list=None):
+    scope = _slim._prefix()
+    names = []
+    for v in var_list:
+      shadow = f'{scope}/{v.key}/{self.name}'
+      # a Variable's shadow starts at its initial value; no zero-debias for Variables
+      EMA_SHADOWS.setdefault(shadow, v.value.detach().clone())
+      names.append((shadow, v.key))
+
+    def op():
+      d = self.decay
+      if self.num_updates is not None:
+        n = float(int(self.num_updates))
+        d = min(d, (1.0 + n) / (10.0 + n))
+      for shadow, key in names:
+        s = EMA_SHADOWS[shadow]
+        s -= (1.0 - d) * (s - _slim.VARS[key].detach())
+    return op
+
+
+def create_train_op(total_loss, optimizer, global_step=None, update_ops=None, variables_to_train=None, summarize_gradients=False,
+                    check_numerics=True, **unused):
+  assert update_ops is None and variables_to_train is None
+  if hasattr(optimizer, 'slots'):
+    optimizer.slots = OPT_SLOTS
+  variables = trainable_variables()
+  queued = list(get_collection(GraphKeys.UPDATE_OPS))
+  moving = list(_slim.UPDATE_OPS)
+
+  def train_op():
+    grads = torch.autograd.grad(total_loss, [v.value for v in variables], allow_unused=True)
+    # 1. UPDATE_OPS (moving statistics of this forward pass, then whatever the model function queued: the EMA)
+    for scope, mean, var, decay in moving:
+      mm, mv = _slim.VARS[f'{scope}/moving_mean'], _slim.VARS[f'{scope}/moving_variance']
+      with torch.no_grad():
+        mm -= (1.0 - decay) * (mm - mean.detach())
+        mv -= (1.0 - decay) * (mv - var.detach())
+    with torch.no_grad():
+      for op in queued:
+        op()
+      # 2. apply_gradients, 3. global step
+      for v, g in zip(variables, grads):
+        if g is None:
+          continue
+        new = optimizer.apply_dense(v.key, v.value.detach(), g)
+        v.value.copy_(new)
+      if global_step is not None:
+        global_step.add_(1)
+    return total_loss.detach()
+  train_op.optimizer = optimizer
+  return train_op
+
+
+def EstimatorSpec(mode, predictions=None, loss=None, train_op=None, eval_metric_ops=None, training_hooks=None, scaffold=None,
+                  **kw):
+  return types.SimpleNamespace(mode=mode, predictions=predictions, loss=loss, train_op=train_op,
+                               eval_metric_ops=eval_metric_ops, training_hooks=training_hooks, scaffold=scaffold)
+
+
+def Scaffold(saver=None, **kw):
+  return types.SimpleNamespace(saver=saver)
+
+
+class SecondOrStepTimer:
+  def __init__(self, every_secs=None, every_steps=None):
+    self.every_secs, self.every_steps = every_secs, every_steps

@@ -413,3 +413,148 @@ def test_evaluate_driver_settings_equal_the_reference_run(tag, tmp_path, monkeyp
   assert calls == [('evaluate', gold['settings']['output_Nclasses'])]
   cm = np.asarray(metrics[0]['confusion_matrix'])
   assert list(cm.shape) == gold['returned_cm_shape'] and int(cm.sum()) == gold['returned_cm_sum']
+
+
+# ------------------------------------------------------------------------------------------------ the TRAIN branch
+TRAIN_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_train_run.npz')
+TRAIN_CASES = ['cs_mixed_sgdm_ema', 'cs_strong_nesterov_poly']
+
+
+@pytest.fixture(scope='module')
+def train_gold():
+  return np.load(TRAIN_GOLD)
+
+
+def train_case_batches(train_gold, tag):
+  """-> (generator module, case tuple, [(images, labels dict with DENSE weak labels)] per step)."""
+  import importlib
+  gen = importlib.import_module('tests.golden.make_reference_train_fixtures')
+  dataset, n_pp, n_pb, n_pi, H, W, steps, opt = gen.CASES[tag]
+  batches = []
+  for i in range(steps):
+    images = torch.from_numpy(train_gold[f'{tag}/step{i}/images'])
+    labels = {'prolabels_per_pixel': torch.from_numpy(train_gold[f'{tag}/step{i}/prolabels_per_pixel'].astype(np.int32))}
+    if n_pb:
+      dense = []
+      for j in range(n_pb):
+        coords, cids = train_gold[f'{tag}/step{i}/bbox{j}_coords'], train_gold[f'{tag}/step{i}/bbox{j}_cids']
+        dense.append(torch.from_numpy(oweak.bbox_labels([(int(c),) + tuple(float(v) for v in xy) for c, xy in zip(cids, coords)], H, W)))
+      labels['prolabels_per_bbox'] = torch.stack(dense)
+    if n_pi:
+      vec = torch.from_numpy(train_gold[f'{tag}/step{i}/image_vectors'])
+      labels['prolabels_per_image'] = vec[:, None, None, :].expand(n_pi, H, W, 15).contiguous()
+    batches.append((images, labels))
+  return gen, gen.CASES[tag], batches
+
+
+def test_generator_inputs_are_reproducible(train_gold):
+  """The stored images / labels are what the committed generator's seeded `case_batches` produces."""
+  import importlib
+  gen = importlib.import_module('tests.golden.make_reference_train_fixtures')
+  for tag in TRAIN_CASES:
+    for i, (images, per_pixel, boxes, vectors) in enumerate(gen.case_batches(tag)):
+      assert np.array_equal(images.numpy(), train_gold[f'{tag}/step{i}/images'])
+      assert np.array_equal(per_pixel.numpy(), train_gold[f'{tag}/step{i}/prolabels_per_pixel'])
+      for j, (coords, cids) in enumerate(boxes):
+        assert np.array_equal(coords, train_gold[f'{tag}/step{i}/bbox{j}_coords'])
+        assert np.array_equal(cids, train_gold[f'{tag}/step{i}/bbox{j}_cids'])
+
+
+def compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum, ema, loss_rows, first_tol, later_tol,
+                        cos_min, norm_tol, moving_tol=2e-3):
+  """Shared by the CPU (oracle) and GPU (product) replays of a reference training run.
+  loss_rows: per step [total, l1, l2_vehicle, l2_human, regularization]; variables / momentum / ema: {TF name: tensor}.
+  The UPDATES (final - initial variables, Momentum slots, shadow - initial) are compared by cosine and norm ratio."""
+  for i, mine in enumerate(loss_rows):
+    ref = train_gold[f'{tag}/step{i}/losses']
+    # later steps: the two l2 losses are averaged over pixels selected by the l1 DECISIONS of the weak images
+    # (define_losses_hierarchical.py:154-185) - a handful of flipped arg-maxes moves them discontinuously: 10x the bound
+    tols = [first_tol] * 5 if i == 0 else [later_tol, later_tol, 10 * later_tol, 10 * later_tol, later_tol]
+    print(tag, 'step', i, 'losses', [round(float(m), 6) for m in mine], 'reference', ref.tolist())
+    for m, r, tol in zip(mine, ref, tols):
+      assert abs(float(m) - r) <= tol * max(1.0, abs(r)), (tag, i, list(mine), ref.tolist())
+  names = str(train_gold[f'{tag}/names']).split('\n')
+  ema_names = [n for n in str(train_gold[f'{tag}/ema_names']).split('\n') if n]
+  # which variables carry an EMA: the model variables without 'BatchNorm/moving' (:103-106), under the scope of :97
+  assert sorted(f'exponential_moving_averages/{k}/ExponentialMovingAverage' for k in ema) == ema_names
+  assert sorted(variables) == names
+  for n, r in zip(names, train_gold[f'{tag}/final/momentum_checksums']):
+    assert (n in momentum) == (r >= 0), ('momentum slot', n)      # one slot per TRAINABLE variable
+  # every variable moved by about what the reference moved it (sum |final - initial|)
+  for n, r in zip(names, train_gold[f'{tag}/final/update_checksums']):
+    m = float((variables[n].double() - initial[n].double()).abs().sum())
+    assert abs(m - r) <= max(5.0 * norm_tol * r, 1e-9), ('update size', n, m, r)
+  worst_cos, worst_norm, bad = 1.0, 0.0, []
+  for store, key, base in ((variables, 'final', initial), (momentum, 'final_momentum', None), (ema, 'final_ema', initial)):
+    for n in gen.KEEP:
+      k = f'{tag}/{key}/{n}'
+      if k not in train_gold.files:
+        assert n not in store or key == 'final', (key, n)
+        continue
+      r = torch.from_numpy(train_gold[k]).double()
+      m = store[n].double().cpu()
+      if '/moving_' in n:
+        err = float((m - r).abs().max()) / float(r.abs().max())
+        if err > moving_tol:
+          bad.append((key, n, 'moving statistic', err))
+        continue
+      if base is not None:
+        r, m = r - base[n].double(), m - base[n].double()
+      cos = float((r * m).sum() / (r.norm() * m.norm()))
+      ratio = float(m.norm() / r.norm())
+      worst_cos, worst_norm = min(worst_cos, cos), max(worst_norm, abs(ratio - 1.0))
+      if not (cos >= cos_min and abs(ratio - 1.0) <= norm_tol):
+        bad.append((key, n, cos, ratio))
+  print(tag, f'worst update cosine {worst_cos:.6f}, worst norm deviation {worst_norm:.2e}')
+  assert not bad, bad
+
+
+def test_product_state_names_equal_the_reference_training_run(train_gold):
+  """The names under which the product exports its training state (wlseg/checkpoints.py) against what the reference's
+  TRAIN graph created: the model variables, and an ExponentialMovingAverage shadow for exactly the variables
+  define_estimator_hierarchical.py:103-106 selects, under the scope of :97."""
+  import types
+  from wlseg import arch, checkpoints as ck
+  p = types.SimpleNamespace(specs=arch.conv_specs((14, 7, 3)), norm='batch', plain=())
+  names = [n for n, _ in ck.model_variables(p)]
+  assert sorted(names) == str(train_gold['cs_mixed_sgdm_ema/names']).split('\n')
+  assert sorted(ck.ema_name(n) for n in names if ck.has_ema(n)) == str(train_gold['cs_mixed_sgdm_ema/ema_names']).split('\n')
+  slots = train_gold['cs_mixed_sgdm_ema/final/momentum_checksums']
+  assert [ck.trainable(n) for n in sorted(names)] == [bool(c >= 0) for c in slots]
+
+
+def reference_lr(train_gold, tag, opt, step):
+  if opt['learning_rate_schedule'] == 'piecewise_constant':
+    lr = oopt.piecewise_constant(step, opt['learning_rate_boundaries'], opt['learning_rate_values'])
+  else:
+    lr = oopt.polynomial_decay(opt['learning_rate_initial'], step, opt['num_training_steps'],
+                               opt['learning_rate_final'], opt['learning_rate_power'])
+  assert abs(lr - float(train_gold[f'{tag}/step{step}/learning_rate'])) <= 1e-12
+  return lr
+
+
+@pytest.mark.parametrize('tag', TRAIN_CASES)
+def test_oracle_training_steps_equal_the_reference_run(train_gold, tag):
+  """define_estimator_hierarchical.py:77-159 executed by the reference itself (model() in training mode -> define_losses
+  -> EMA in UPDATE_OPS -> define_optimizer -> create_train_op) for 3 / 2 optimizer steps vs oracle/train.py on the same
+  seeded batches: every step's five losses and learning rate, then the variables, Momentum slots, EMA shadows and moving
+  statistics the session is left with.  fp32 on both sides over independent formulations of a train-mode BN ResNet
+  (NHWC tf-shim vs the oracle's own ops; the generator's header explains the conditioning): first-step losses 1e-5
+  relative, later steps 1e-4 (l2 heads 1e-3); updates: cosine >= 0.999, norms within 1 %; moving statistics 2e-3 of their maximum."""
+  from oracle import train as otrain
+  gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), batches = train_case_batches(train_gold, tag)
+  initial = gen.case_params(tag)
+  state = otrain.TrainState(initial, ema_decay=opt['ema_decay'])
+  rows = []
+  for i, (images, labels) in enumerate(batches):
+    assert int(train_gold[f'{tag}/step{i}/global_step_before']) == state.global_step == i
+    lr = reference_lr(train_gold, tag, opt, state.global_step)
+    got = otrain.train_step(state, images, labels, dataset, lr, momentum=opt['momentum'], nesterov=opt['use_nesterov'],
+                            regularization_weight=opt['regularization_weight'], bn_decay=opt['batch_norm_decay'])
+    rows.append([got[k] for k in ('total', 'l1_segmentation', 'l2_vehicle_segmentation', 'l2_human_segmentation', 'regularization')])
+  assert state.global_step == int(train_gold[f'{tag}/global_step'])
+  if opt['ema_decay'] > 0:
+    assert str(train_gold[f'{tag}/ema_notice']) == (f'Found {len(initial)} variables, saving exponential moving averages '
+                                                    f'for {len(state.ema)} of them.')
+  compare_train_state(train_gold, tag, gen, opt, initial, state.vars, state.momentum, state.ema, rows,
+                      first_tol=1e-5, later_tol=1e-4, cos_min=0.999, norm_tol=1e-2)
