@@ -580,8 +580,12 @@ get_collection = _train.get_collection
 train.get_or_create_global_step = _train.get_or_create_global_step
 train.ExponentialMovingAverage = _train.ExponentialMovingAverage
 train.Scaffold = _train.Scaffold
+train.Saver = _train.Saver
+global_variables = _train.global_variables
 train.SecondOrStepTimer = _train.SecondOrStepTimer
 estimator.EstimatorSpec = _train.EstimatorSpec
+_register('tensorflow.python.ops', metrics_impl=_register('tensorflow.python.ops.metrics_impl',
+                                                         _streaming_confusion_matrix=_train._streaming_confusion_matrix))
 _register('tensorflow.contrib.training', create_train_op=_train.create_train_op)
 _SUBMODULES['tensorflow.contrib'].training = _SUBMODULES['tensorflow.contrib.training']
 

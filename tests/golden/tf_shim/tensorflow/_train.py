@@ -24,6 +24,7 @@ from tensorflow import _slim
 GLOBAL_STEP = [None]
 EMA_SHADOWS = {}     # {shadow variable name: tensor}
 COLLECTIONS = {}     # user collections (tf.add_to_collection)
+METRIC_VARS = {}     # {name: float64 tensor} - local "metric variables" of the evaluation graph (total_confusion_matrix)
 OPT_SLOTS = {}       # {variable name: Momentum accumulator} - slot variables outlive the optimizer OBJECT, which the eager
                      # run re-creates on every step (in TF they are graph variables `train_ops/<var>/Momentum`)
 
@@ -41,6 +42,7 @@ def reset():
   EMA_SHADOWS.clear()
   COLLECTIONS.clear()
   OPT_SLOTS.clear()
+  METRIC_VARS.clear()
 
 
 class _Var:
@@ -56,13 +58,34 @@ class _Var:
     return _slim.VARS[self.key]
 
 
+_VAR_OBJECTS = {}    # one object per variable name (the savers compare variables by identity)
+
+
+def _var(name):
+  if name not in _VAR_OBJECTS:
+    _VAR_OBJECTS[name] = _Var(name)
+  return _VAR_OBJECTS[name]
+
+
 def model_variables():
   seen, out = set(), []
   for n in _slim.REQUESTED:      # slim registers every variable it creates as a model variable, in creation order
     if n not in seen:
       seen.add(n)
-      out.append(_Var(n))
+      out.append(_var(n))
   return out
+
+
+def global_variables():
+  """Model variables + the global step (what the EVAL / PREDICT graphs hold; the TRAIN graph adds slots and shadows)."""
+  return model_variables() + [_var('global_step')]
+
+
+class Saver:
+  """Container: the reference's savers only choose WHICH variables are saved / restored under WHICH checkpoint names."""
+
+  def __init__(self, var_list=None, sharded=False, max_to_keep=5, save_relative_paths=False, **kw):
+    self.var_list = var_list
 
 
 def trainable_variables():
@@ -154,3 +177,21 @@ def Scaffold(saver=None, **kw):
 class SecondOrStepTimer:
   def __init__(self, every_secs=None, every_steps=None):
     self.every_secs, self.every_steps = every_secs, every_steps
+
+
+def _streaming_confusion_matrix(labels, predictions, num_classes, weights=None):
+  """[TF-1.12] tensorflow/python/ops/metrics_impl.py::_streaming_confusion_matrix: a float64 [num_classes, num_classes]
+  metric variable `total_confusion_matrix`; labels and predictions are cast to int64 and flattened; update_op =
+  assign_add(total_cm, confusion_matrix(labels, predictions, num_classes, dtype=float64)); returns (total_cm, update_op).
+  Eager emulation: one define_estimator call stands for one session.run of the evaluation loop, which runs update_op -
+  the update is applied here and the returned tensor is the variable AFTER it (what Estimator.evaluate reads at the end)."""
+  import tensorflow as tf
+  assert weights is None
+  num_classes = int(num_classes)
+  total = METRIC_VARS.setdefault('total_confusion_matrix', torch.zeros(num_classes, num_classes, dtype=torch.float64))
+  lab = torch.as_tensor(labels).to(torch.int64).reshape(-1)
+  pred = torch.as_tensor(predictions).to(torch.int64).reshape(-1)
+  if int(lab.min()) < 0 or int(lab.max()) >= num_classes or int(pred.min()) < 0 or int(pred.max()) >= num_classes:
+    raise ValueError('InvalidArgumentError: confusion_matrix index out of bounds')   # TF fails the run
+  total += torch.as_tensor(tf.confusion_matrix(lab, pred, num_classes)).to(torch.float64)
+  return total, (lambda: total)

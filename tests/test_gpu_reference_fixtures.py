@@ -336,3 +336,87 @@ def test_trainer_equals_the_reference_training_run(cuda, train_gold, tag, dtype)
   tol = dict(first_tol=1e-4, later_tol=5e-4, cos_min=0.999, norm_tol=1e-2, moving_tol=2e-3) if dtype == 'fp32' else \
       dict(first_tol=2e-2, later_tol=2e-2, cos_min=0.90, norm_tol=1.5e-1, moving_tol=2e-2)
   cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum, ema, rows, **tol)
+
+
+# ------------------------------------------------------------------------------------------------ EVAL / PREDICT branches
+@pytest.fixture(scope='module')
+def eval_gold():
+  from tests import test_reference_fixtures as cpu_side
+  return np.load(cpu_side.EVAL_GOLD)
+
+
+@pytest.mark.parametrize('tag', ['eval_cs_same_size', 'eval_cs_labels_2x', 'eval_vistas_labels_odd'])
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_system_evaluate_equals_the_reference_eval_run(cuda, eval_gold, tmp_path, tag, dtype):
+  """The reference's EVAL branch (define_estimator_hierarchical.py:160-201) run by the reference itself over two
+  batches, against the product's WHOLE evaluation stack on the same batches: evaluate.py's settings ->
+  SemanticSegmentation.evaluate() (cid map from the problem definition, `_replacevoids`, void row / column trimmed,
+  system_factory.py:400-405) -> Estimator.evaluate -> wlseg_head_confmat / resize + wlseg_confmat_accumulate, with the
+  weights restored from a checkpoint file under their TF names (predict_saver).
+  fp32 check mode: the streaming confusion matrix is the reference's, entry by entry.  bf16 product path: the matrices
+  may differ where an arg-max is a near-tie - at most 2 % of the pixels moved (north star: decisions >= 98 %)."""
+  from tests import test_reference_fixtures as cpu_side
+  from wlseg import checkpoints, problem_defs, settings as wsettings
+  from wlseg.system_factory import SemanticSegmentation
+  gen = cpu_side._eval_gen()
+  dataset, nbatches, N, H, W, LH, LW = gen.EVAL_CASES[tag]
+  ckpt = checkpoints.save_file(os.path.join(str(tmp_path), 'model.ckpt-7.pt'), gen.case_params(dataset), 7)
+  argv = [str(tmp_path), str(N * nbatches), problem_defs.default_path(dataset), 'unused', dataset, '--Nb', str(N),
+          '--height_feature_extractor', str(H), '--width_feature_extractor', str(W), '--dtype', dtype, '--ckpt_path', ckpt]
+  st = wsettings.eval_extra_args(wsettings.build_parser(wsettings.EVAL).parse_args(argv))
+  st.device, st.rank, st.world_size = 'cuda:0', 0, 1
+
+  def input_fn(config, params):
+    for b in range(nbatches):
+      yield ({'proimages': torch.from_numpy(eval_gold[f'{tag}/batch{b}/images'])},
+             {'prolabels': torch.from_numpy(eval_gold[f'{tag}/batch{b}/prolabels'].astype(np.int32))})
+
+  system = SemanticSegmentation({'eval': input_fn}, None, st)
+  assert system.settings.training_cids2evaluation_cids == eval_gold[f'{tag}/training_cids2evaluation_cids'].tolist()
+  metrics = system.evaluate()
+  assert len(metrics) == 1 and metrics[0]['global_step'] == 7 and metrics[0]['steps'] == nbatches and metrics[0]['loss'] == 0.0
+  ref = eval_gold[f'{tag}/confusion_matrix'].astype(np.int64)
+  got = metrics[0]['confusion_matrix']
+  assert got.dtype == np.int32 and got.shape == (ref.shape[0] - 1, ref.shape[1] - 1)      # void trimmed
+  full = metrics[0]['confusion_matrix_int64']
+  assert int(full.sum()) == int(ref.sum()) == N * nbatches * LH * LW
+  assert np.array_equal(full.sum(1), ref.sum(1))                                          # label histogram: exact always
+  moved = int(np.abs(full - ref).sum()) // 2
+  print(f'{tag} {dtype}: {moved} of {int(ref.sum())} pixels in another cell')
+  if dtype == 'fp32':
+    assert np.array_equal(full, ref) and np.array_equal(got, ref[:-1, :-1])
+  else:
+    assert moved <= 0.02 * ref.sum(), moved
+
+
+@pytest.mark.parametrize('tag', ['predict_cs_system_size', 'predict_cs_raw_size'])
+def test_estimator_predict_equals_the_reference_predict_run(cuda, eval_gold, tag):
+  """The reference's PREDICT branch (:204-237) run by the reference itself, against Estimator.predict (fp32 check mode):
+  output size (height_system x width_system, or the raw image's), decisions (nearest), probabilities (bilinear) 1e-4,
+  raw images / paths passed through."""
+  import argparse
+  from tests import test_reference_fixtures as cpu_side
+  from wlseg import estimator as est, network
+  gen = cpu_side._eval_gen()
+  dataset, N, H, W, system, raw = gen.PREDICT_CASES[tag]
+  s = argparse.Namespace(dtype='fp32', stride_feature_extractor=8, psp_module=False, height_system=system[0],
+                         width_system=system[1], replace_voids=False, batch_norm_decay=1.0)
+  e = est.Estimator(s, _hier(dataset), device=cuda)
+  e.params.load_tf_dict(gen.case_params(dataset))
+  e.net = network.Network(e.params, dtype=torch.float32)
+  features = {'proimages': torch.from_numpy(eval_gold[f'{tag}/images'])}
+  keys = ['decisions', *gen.PROB_KEYS]
+  if raw is not None:
+    features['rawimages'] = torch.zeros(N, raw[0], raw[1], 3, dtype=torch.uint8)
+    features['rawimagespaths'] = ['a.png'] * N
+    keys += ['rawimages', 'rawimagespaths']
+  outs = list(e.predict([(features, None)], keys))
+  assert len(outs) == N and sorted(outs[0].keys()) == str(eval_gold[f'{tag}/prediction_keys']).split('\n')
+  oh, ow = (int(v) for v in eval_gold[f'{tag}/size'])
+  for i, ex in enumerate(outs):
+    assert ex['decisions'].shape == (oh, ow)
+    dis = float((ex['decisions'] != eval_gold[f'{tag}/decisions'][i]).mean())
+    assert dis <= 1e-3, dis       # fp32 on both sides: near-ties only (measured 0)
+    for k in gen.PROB_KEYS:
+      ref = eval_gold[f'{tag}/{k}'][i]
+      assert np.abs(ex[k][::gen.PROB_STRIDE, ::gen.PROB_STRIDE] - ref).max() <= 1e-4, k

@@ -558,3 +558,77 @@ def test_oracle_training_steps_equal_the_reference_run(train_gold, tag):
                                                     f'for {len(state.ema)} of them.')
   compare_train_state(train_gold, tag, gen, opt, initial, state.vars, state.momentum, state.ema, rows,
                       first_tol=1e-5, later_tol=1e-4, cos_min=0.999, norm_tol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ EVAL / PREDICT branches
+EVAL_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_eval_run.npz')
+
+
+@pytest.fixture(scope='module')
+def eval_gold():
+  return np.load(EVAL_GOLD)
+
+
+def _eval_gen():
+  import importlib
+  return importlib.import_module('tests.golden.make_reference_eval_fixtures')
+
+
+@pytest.mark.parametrize('tag', ['eval_cs_same_size', 'eval_cs_labels_2x', 'eval_vistas_labels_odd'])
+def test_oracle_eval_branch_equals_the_reference_run(eval_gold, tag):
+  """define_estimator_hierarchical.py:160-201 run by the reference (inference-mode model(), cid map, nearest resize to
+  the label size, streaming confusion matrix over the batches) vs the oracle's pieces composed in the same order:
+  decisions of every batch and the accumulated confusion matrix, bit-exact (fp32 logits on both sides; an arg-max flip
+  between the two formulations would show up here - there is none on these inputs)."""
+  from oracle import network as onet
+  gen = _eval_gen()
+  dataset, nbatches, N, H, W, LH, LW = gen.EVAL_CASES[tag]
+  t2e = eval_gold[f'{tag}/training_cids2evaluation_cids'].tolist()
+  lut = ometrics.replacevoids(t2e)
+  num_classes = max(lut) + 1
+  assert num_classes == int(eval_gold[f'{tag}/num_classes'])
+  net = onet.Net(gen.case_params(dataset), dataset, training=False)
+  cm = np.zeros((num_classes, num_classes), dtype=np.int64)
+  for b in range(nbatches):
+    with torch.no_grad():
+      pred = net.forward(torch.from_numpy(eval_gold[f'{tag}/batch{b}/images']))
+    decs = ometrics.map_decisions_to_new_cids(pred['decisions'].numpy(), t2e)
+    decs = tfops.resize_nearest(torch.from_numpy(decs)[..., None], LH, LW, align_corners=True)[..., 0].numpy()
+    assert np.array_equal(decs, eval_gold[f'{tag}/batch{b}/decisions']), tag
+    cm += ometrics.confusion_matrix(eval_gold[f'{tag}/batch{b}/prolabels'], decs, num_classes)
+  assert np.array_equal(cm, eval_gold[f'{tag}/confusion_matrix'])
+  assert np.array_equal(ometrics.confusion_matrix_c(eval_gold[f'{tag}/batch0/prolabels'], eval_gold[f'{tag}/batch0/decisions'], num_classes),
+                        ometrics.confusion_matrix(eval_gold[f'{tag}/batch0/prolabels'], eval_gold[f'{tag}/batch0/decisions'], num_classes))
+
+
+@pytest.mark.parametrize('tag', ['predict_cs_system_size', 'predict_cs_raw_size'])
+def test_oracle_predict_branch_equals_the_reference_run(eval_gold, tag):
+  """define_estimator_hierarchical.py:204-237: the four supported keys resized to (height_system, width_system), or to
+  the raw image's size when either is unset (raw images and paths are then passed through)."""
+  from oracle import network as onet
+  gen = _eval_gen()
+  dataset, N, H, W, system, raw = gen.PREDICT_CASES[tag]
+  oh, ow = (int(v) for v in eval_gold[f'{tag}/size'])
+  assert (oh, ow) == (tuple(system) if raw is None else tuple(raw))
+  keys = str(eval_gold[f'{tag}/prediction_keys']).split('\n')
+  assert keys == sorted(['decisions', *gen.PROB_KEYS] + (['rawimages', 'rawimagespaths'] if raw is not None else []))
+  net = onet.Net(gen.case_params(dataset), dataset, training=False)
+  with torch.no_grad():
+    pred = net.forward(torch.from_numpy(eval_gold[f'{tag}/images']))
+  decs = tfops.resize_nearest(pred['decisions'][..., None], oh, ow, align_corners=True)[..., 0].numpy()
+  assert np.array_equal(decs, eval_gold[f'{tag}/decisions'])
+  for k in gen.PROB_KEYS:
+    got = tfops.resize_bilinear(pred[k], oh, ow, align_corners=True).numpy()[:, ::gen.PROB_STRIDE, ::gen.PROB_STRIDE]
+    assert np.abs(got - eval_gold[f'{tag}/{k}']).max() <= 1e-5, k
+
+
+def test_product_restore_names_equal_the_reference_savers(eval_gold):
+  """evaluate_saver / predict_saver (define_savers.py:38-69) as the reference built them in the EVAL and PREDICT runs:
+  checkpoint key -> graph variable, with and without --restore_emas, against wlseg.checkpoints.predict_var_dict."""
+  import types
+  from wlseg import arch, checkpoints as ck
+  p = types.SimpleNamespace(specs=arch.conv_specs((14, 7, 3)), norm='batch', plain=())
+  for tag, emas in (('eval_cs_same_size', False), ('predict_cs_system_size', False), ('predict_cs_raw_size', True)):
+    ref = dict(l.split() for l in str(eval_gold[f'{tag}/saver']).split('\n'))
+    assert ref.pop('global_step') == 'global_step'
+    assert ref == dict(ck.predict_var_dict(p, restore_emas=emas)), tag
