@@ -632,3 +632,38 @@ def test_product_restore_names_equal_the_reference_savers(eval_gold):
     ref = dict(l.split() for l in str(eval_gold[f'{tag}/saver']).split('\n'))
     assert ref.pop('global_step') == 'global_step'
     assert ref == dict(ck.predict_var_dict(p, restore_emas=emas)), tag
+
+
+# ------------------------------------------------------------------------------------------------ --cross_replica_norm
+def test_oracle_cross_replica_batch_norm_equals_the_reference_layer_run():
+  """CrossReplicaBatchNormalization._fused_batch_norm + _assign_moving_average (code/utils/
+  cross_replica_batch_normalization.py:381-476) executed by the reference over a 2-tower emulation
+  (tests/golden/make_reference_xreplica_fixtures.py) vs oracle/tfops.py::cross_replica_batch_norm: per-tower outputs,
+  moving statistics after the update - including the reference's (n - 1) / n factor with the PER-TOWER n on a variance
+  without Bessel's correction - and the gradients through the cross-tower moments (1e-5 of each tensor's maximum)."""
+  gold = np.load(os.path.join(os.path.dirname(TRAIN_GOLD), 'reference_xreplica_run.npz'))
+  xs = [torch.from_numpy(gold[f'tower{r}/x']).clone().requires_grad_(True) for r in range(2)]
+  gamma = torch.from_numpy(gold['gamma']).clone().requires_grad_(True)
+  beta = torch.from_numpy(gold['beta']).clone().requires_grad_(True)
+  ys, mm, mv, mean, var = tfops.cross_replica_batch_norm(
+      xs, gamma, beta, torch.from_numpy(gold['moving_mean_before']), torch.from_numpy(gold['moving_variance_before']),
+      decay=float(gold['momentum']), eps=float(gold['epsilon']))
+  loss = sum((y * torch.from_numpy(gold[f'tower{r}/w'])).sum() for r, y in enumerate(ys))
+  grads = torch.autograd.grad(loss, xs + [gamma, beta])
+
+  def close(a, b, what):
+    b = torch.from_numpy(b)
+    err = float((a.detach() - b).abs().max()) / float(b.abs().max())
+    assert err <= 1e-5, (what, err)
+
+  for r in range(2):
+    close(ys[r], gold[f'tower{r}/y'], f'y{r}')
+    close(grads[r], gold[f'tower{r}/dx'], f'dx{r}')
+  close(grads[2], gold['dgamma'], 'dgamma')
+  close(grads[3], gold['dbeta'], 'dbeta')
+  close(mm, gold['tower0/moving_mean_after'], 'moving mean')
+  close(mv, gold['tower0/moving_variance_after'], 'moving variance')
+  # the quirk is visible at this sample size: Bessel's correction instead would differ by ~2/n = 2.9e-2 of the update
+  n = xs[0].shape[0] * xs[0].shape[1] * xs[0].shape[2]
+  bessel = torch.from_numpy(gold['moving_variance_before']) * 0.9 + 0.1 * var.detach() * n / (n - 1)
+  assert float((bessel - torch.from_numpy(gold['tower0/moving_variance_after'])).abs().max()) > 1e-3
