@@ -110,6 +110,66 @@ def case_batches(tag, ib=None):
   return batches
 
 
+def imagenet_checkpoint_variables(model_names, shapes):
+  """What tf.train.list_variables reports for the slim ImageNet resnet_v1_50 checkpoint --init_ckpt_path points at: the
+  base network's variables without the reference's `feature_extractor/base/` prefix, plus the checkpoint's own
+  global_step, mean_rgb and 1000-way logits."""
+  out = [('global_step', ()), ('resnet_v1_50/mean_rgb', (3,)), ('resnet_v1_50/logits/weights', (1, 1, 2048, 1000)),
+         ('resnet_v1_50/logits/biases', (1000,))]
+  prefix = 'feature_extractor/base/'
+  for n in model_names:
+    if n.startswith(prefix + 'resnet_v1_50/'):
+      out.append((n[len(prefix):], tuple(shapes[n])))
+  return sorted(out)
+
+
+def warm_start_cases(tf, _slim, _train, de, rm, out):
+  """The TRAIN graph built with --init_ckpt_path set (nothing is run): `replace_initializers`
+  (define_initializers.py:72-131) chooses which graph variables the ImageNet checkpoint initialises, `train_saver`
+  (define_savers.py:3-36) which variables are saved; stored next to tf.global_variables() of that graph."""
+  if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+  from oracle import network as onet
+  ckpt = '/imagenet/resnet_v1_50.ckpt'
+  for tag, psp in (('warm_start', False), ('warm_start_psp', True)):
+    tfp = onet.init_params('cityscapes', seed=SEED, randomize_bn=True, tame=True, psp=psp)
+    for n in tfp:
+      if '/moving_' not in n:
+        tfp[n].requires_grad_(True)
+    _slim.reset(tfp)
+    _train.reset()
+    tf.reset_collections()
+    _train.CHECKPOINT_VARIABLES[ckpt] = imagenet_checkpoint_variables(sorted(tfp), {k: v.shape for k, v in tfp.items()})
+    H, W = 48, 64
+    params = types.SimpleNamespace(
+        name_feature_extractor='resnet_v1_50', norm_layer='batch', norm_train_variables=True,
+        batch_norm_accumulate_statistics=True, cross_replica_norm=False, psp_module=psp, per_pixel_dataset_name='cityscapes',
+        height_feature_extractor=H, width_feature_extractor=W, upsampling_method='bilinear', stride_feature_extractor=8,
+        feature_dims_decreased=256, fov_expansion_kernel_rate=0, fov_expansion_kernel_size=0, Nb=1, Nb_per_pixel=1,
+        Nb_per_bbox=0, Nb_per_image=0, distribute=False, init_ckpt_path=ckpt, log_dir='/tmp/unused', num_training_steps=100,
+        save_checkpoints_steps=50, learning_rate_schedule='piecewise_constant', learning_rate_boundaries=[50],
+        learning_rate_values=[0.01, 0.005], optimizer='SGDM', momentum=0.9, use_nesterov=False, ema_decay=0.9,
+        regularization_weight=0.00017, batch_norm_decay=0.9)
+    config = types.SimpleNamespace(train_distribute=None, keep_checkpoint_max=2)
+    g = torch.Generator().manual_seed(SEED)
+    features = {'proimages': tf.as_tf(torch.rand(1, H, W, 3, generator=g) * 2 - 1)}
+    labels = {'prolabels_per_pixel': torch.randint(0, 20, (1, H, W), generator=g, dtype=torch.int32),
+              'prolabels_per_bbox': torch.zeros(0, H, W, 15), 'prolabels_per_image': torch.zeros(0, H, W, 15)}
+    stdout, sys.stdout = sys.stdout, io.StringIO()
+    try:
+      spec = de.define_estimator(tf.estimator.ModeKeys.TRAIN, features, labels, rm.model, config, params)
+    finally:
+      sys.stdout = stdout
+    (path, var_dict), = _train.INIT_FROM_CHECKPOINT
+    assert path == ckpt
+    out[f'{tag}/checkpoint_variables'] = np.asarray('\n'.join(f'{n} {" ".join(str(d) for d in s)}' for n, s in _train.CHECKPOINT_VARIABLES[ckpt]))
+    out[f'{tag}/global_variables'] = np.asarray('\n'.join(v.op.name for v in tf.global_variables()))
+    out[f'{tag}/init_from_checkpoint'] = np.asarray('\n'.join(f'{k} {v.op.name}' for k, v in sorted(var_dict.items())))
+    out[f'{tag}/train_saver'] = np.asarray('\n'.join(v.op.name for v in spec.scaffold.saver.var_list))
+    print(f'{tag}: {len(tf.global_variables())} global variables, {len(var_dict)} initialised from the checkpoint, '
+          f'{len(spec.scaffold.saver.var_list)} saved')
+
+
 def main():
   sys.path.insert(0, os.path.join(HERE, 'tf_shim'))
   sys.path.insert(0, REF)
@@ -210,6 +270,7 @@ def main():
       if sh in _train.EMA_SHADOWS:
         out[f'{tag}/final_ema/{n}'] = _train.EMA_SHADOWS[sh].numpy().copy()
     print(f'{tag}: {len(names)} variables, {len(_train.OPT_SLOTS)} Momentum slots, {len(_train.EMA_SHADOWS)} EMA shadows')
+  warm_start_cases(tf, _slim, _train, de, rm, out)
   np.savez_compressed(OUT, **out)
   print('wrote', OUT, os.path.getsize(OUT), 'bytes')
 

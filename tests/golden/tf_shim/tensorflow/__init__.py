@@ -535,7 +535,7 @@ class _ModeKeys:
 estimator = _register('tensorflow.estimator', ModeKeys=_ModeKeys)
 logging = _register('tensorflow.logging', info=lambda *a, **k: None, warn=lambda *a, **k: None,
                     warning=lambda *a, **k: None, debug=lambda *a, **k: None, INFO=20, DEBUG=10,
-                    set_verbosity=lambda *a, **k: None)
+                    set_verbosity=lambda *a, **k: None, get_verbosity=lambda: 20, WARN=30)
 summary = _register('tensorflow.summary', image=lambda *a, **k: None, scalar=lambda *a, **k: None,
                     histogram=lambda *a, **k: None)
 
@@ -581,6 +581,11 @@ train.get_or_create_global_step = _train.get_or_create_global_step
 train.ExponentialMovingAverage = _train.ExponentialMovingAverage
 train.Scaffold = _train.Scaffold
 train.Saver = _train.Saver
+train.list_variables = _train.list_variables
+train.init_from_checkpoint = _train.init_from_checkpoint
+TensorShape = _train.TensorShape
+_register('tensorflow.contrib.distribute.python.values', DistributedValues=_train.DistributedValues,
+          TowerLocalVariable=_train.DistributedValues, MirroredVariable=_train.DistributedValues)
 global_variables = _train.global_variables
 train.SecondOrStepTimer = _train.SecondOrStepTimer
 estimator.EstimatorSpec = _train.EstimatorSpec

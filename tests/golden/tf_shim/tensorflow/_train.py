@@ -25,6 +25,9 @@ GLOBAL_STEP = [None]
 EMA_SHADOWS = {}     # {shadow variable name: tensor}
 COLLECTIONS = {}     # user collections (tf.add_to_collection)
 METRIC_VARS = {}     # {name: float64 tensor} - local "metric variables" of the evaluation graph (total_confusion_matrix)
+SLOT_NAMES = []      # names of the Momentum slot variables create_train_op made: <variable scope>/<variable>/Momentum
+INIT_FROM_CHECKPOINT = []   # (checkpoint path, {checkpoint name: graph variable}) of every tf.train.init_from_checkpoint call
+CHECKPOINT_VARIABLES = {}   # {checkpoint path: [(name, shape)]} - what tf.train.list_variables reports (set by the script)
 OPT_SLOTS = {}       # {variable name: Momentum accumulator} - slot variables outlive the optimizer OBJECT, which the eager
                      # run re-creates on every step (in TF they are graph variables `train_ops/<var>/Momentum`)
 
@@ -43,6 +46,7 @@ def reset():
   COLLECTIONS.clear()
   OPT_SLOTS.clear()
   METRIC_VARS.clear()
+  del SLOT_NAMES[:], INIT_FROM_CHECKPOINT[:]
 
 
 class _Var:
@@ -56,6 +60,14 @@ class _Var:
   @property
   def value(self):
     return _slim.VARS[self.key]
+
+  @property
+  def shape(self):
+    base = self.key
+    for suffix in ('/Momentum', '/ExponentialMovingAverage'):      # a slot / shadow has its variable's shape
+      if base.endswith(suffix):
+        base = base[:-len(suffix)].split('/', 1)[1]
+    return tuple(_slim.VARS[base].shape) if base in _slim.VARS else ()
 
 
 _VAR_OBJECTS = {}    # one object per variable name (the savers compare variables by identity)
@@ -77,8 +89,30 @@ def model_variables():
 
 
 def global_variables():
-  """Model variables + the global step (what the EVAL / PREDICT graphs hold; the TRAIN graph adds slots and shadows)."""
-  return model_variables() + [_var('global_step')]
+  """Creation order: model variables, the global step and - in the TRAIN graph - the EMA shadows and Momentum slots."""
+  return model_variables() + [_var('global_step')] + [_var(n) for n in EMA_SHADOWS] + [_var(n) for n in SLOT_NAMES]
+
+
+class TensorShape:
+  """[TF-1.12] fully defined shapes: compatible = same rank and equal dimensions."""
+
+  def __init__(self, dims):
+    self.dims = tuple(int(d) for d in dims)
+
+  def is_compatible_with(self, other):
+    return self.dims == tuple(int(d) for d in getattr(other, 'dims', other))
+
+
+def list_variables(path):
+  return list(CHECKPOINT_VARIABLES[path])
+
+
+def init_from_checkpoint(path, assignment_map):
+  INIT_FROM_CHECKPOINT.append((path, dict(assignment_map)))
+
+
+class DistributedValues:
+  """tf.contrib.distribute values container: nothing here is one (single tower)."""
 
 
 class Saver:
@@ -137,6 +171,10 @@ def create_train_op(total_loss, optimizer, global_step=None, update_ops=None, va
   if hasattr(optimizer, 'slots'):
     optimizer.slots = OPT_SLOTS
   variables = trainable_variables()
+  # [TF-1.12] slot_creator: apply_gradients creates one slot per trainable variable, named <current variable scope>/
+  # <variable op name>/<optimizer name> - the scope is whatever `with tf.variable_scope(...)` the reference wrapped around
+  if hasattr(optimizer, 'slots'):
+    SLOT_NAMES.extend(f'{_slim._prefix()}/{v.key}/Momentum' for v in variables)
   queued = list(get_collection(GraphKeys.UPDATE_OPS))
   moving = list(_slim.UPDATE_OPS)
 

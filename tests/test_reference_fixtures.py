@@ -667,3 +667,28 @@ def test_oracle_cross_replica_batch_norm_equals_the_reference_layer_run():
   n = xs[0].shape[0] * xs[0].shape[1] * xs[0].shape[2]
   bessel = torch.from_numpy(gold['moving_variance_before']) * 0.9 + 0.1 * var.detach() * n / (n - 1)
   assert float((bessel - torch.from_numpy(gold['tower0/moving_variance_after'])).abs().max()) > 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ warm start / train_saver
+@pytest.mark.parametrize('tag,psp', [('warm_start', False), ('warm_start_psp', True)])
+def test_product_warm_start_equals_the_reference_graph(train_gold, tag, psp):
+  """The TRAIN graph built by the reference with --init_ckpt_path (define_estimator -> replace_initializers,
+  define_initializers.py:72-131; train_saver, define_savers.py:3-36): tf.global_variables() of that graph - model
+  variables, global_step, `exponential_moving_averages/.../ExponentialMovingAverage` shadows, `train_ops/.../Momentum`
+  slots -, the checkpoint-name -> graph-variable map handed to tf.train.init_from_checkpoint, and the saved set,
+  against wlseg.checkpoints.global_variables / match_init_checkpoint / export names."""
+  import types
+  from wlseg import arch, checkpoints as ck
+  p = types.SimpleNamespace(specs=arch.conv_specs((14, 7, 3), psp=psp), norm='batch', plain=())
+  ref_globals = str(train_gold[f'{tag}/global_variables']).split('\n')
+  mine = ck.global_variables(p)
+  assert sorted(n for n, _ in mine) == sorted(ref_globals) and len(set(ref_globals)) == len(ref_globals)
+  ckpt_vars = []
+  for line in str(train_gold[f'{tag}/checkpoint_variables']).split('\n'):
+    name, *dims = line.split()
+    ckpt_vars.append((name, tuple(int(d) for d in dims)))
+  ref_map = dict(l.split() for l in str(train_gold[f'{tag}/init_from_checkpoint']).split('\n'))
+  assert dict(ck.match_init_checkpoint(ckpt_vars, mine, psp_module=psp)) == ref_map
+  assert len(ref_map) == 53 * 5
+  # with an init checkpoint the train saver keeps every global variable (exclude = [])
+  assert sorted(str(train_gold[f'{tag}/train_saver']).split('\n')) == sorted(ref_globals)
