@@ -19,8 +19,16 @@ reference's `model()` + `feature_extractor()` + `module_arg_scope()` executed
 on 330-variable parameter dictionaries, five configurations incl. training-mode
 batch norm, pyramid / field-of-view / hybrid upsampling and group norm) and
 tests/golden/reference_driver_run.json (argument parsers, train.py / evaluate.py
-overrides, SemanticSegmentation's derived settings) - checked in tests/test_reference_fixtures.py (oracle) and
-tests/test_gpu_reference_fixtures.py (CUDA path, no oracle in between).
+overrides, SemanticSegmentation's derived settings), tests/golden/reference_train_run.npz
+(train.py: `define_estimator` in TRAIN mode with the reference's model() for 3 / 2 optimizer
+steps - losses, Momentum, EMA in UPDATE_OPS, moving statistics; plus the TRAIN graph's
+global variables, warm-start map and saver with --init_ckpt_path),
+tests/golden/reference_eval_run.npz (`define_estimator` in EVAL / PREDICT mode: cid map,
+nearest resize to the label size, streaming confusion matrix over batches, restore names)
+and tests/golden/reference_xreplica_run.npz (tfops.cross_replica_batch_norm: the reference's
+CrossReplicaBatchNormalization._fused_batch_norm over two emulated towers) - checked in
+tests/test_reference_fixtures.py (oracle) and tests/test_gpu_reference_fixtures.py (CUDA path,
+no oracle in between).
 What stays RESTATED: TensorFlow's and slim's own internals (un-vendored): the
 shim is our reading of the op semantics (SAME padding split, fused batch norm,
 resize_bilinear align_corners, resnet_v1's output-stride bookkeeping, variable
