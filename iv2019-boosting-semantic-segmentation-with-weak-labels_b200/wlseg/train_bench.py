@@ -181,7 +181,8 @@ def run(args, ctx, cpu_train_sample=None):
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline and cpu_train_sample is not None:
-    cpu = cpu_train_sample(args.dataset, H, W)
+    # one step over the arm's own batch (about 10 s of host work at 4 x 768 x 768)
+    cpu = cpu_train_sample(args.dataset, H, W, images_per_step=NB if not mixed else 1, mixed=mixed)
 
   fwd = arch.conv_flops(params.specs, H, W) / 1e9
   line = {'metric': 'train_images_per_s', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
