@@ -1,90 +1,157 @@
 """`SemanticSegmentation`: the reference's system facade on the B200 kernels.
 
-Mirrors code/system_factory.py:27-461: same constructor signature
-`SemanticSegmentation(input_fns, model_fn, settings)`, same derived settings
-(`output_Nclasses` :124-130, cid maps :138-157, steps and LR schedule :197-233, checkpoint cadence
-:246-248, eval directory naming :159-172), same `.train()`, `.evaluate() -> list of metrics dicts`
-(void row / column trimmed, :400-405), `.predict() -> iterator of per-image dicts`, `.settings`.
-`tf.estimator.Estimator` is replaced by wlseg.estimator.Estimator.
+Drop-in for code/system_factory.py:27-461: the constructor `SemanticSegmentation(input_fns, model_fn, settings)`,
+`.train()`, `.evaluate() -> [metrics dict per checkpoint]`, `.predict() -> iterator of per-image dicts`, `.settings`.
+Every attribute the reference leaves on `settings` is derived here as well (tests/golden/reference_driver_run.json holds
+the reference's own values for 56 training and 37 evaluation attributes; tests/test_reference_fixtures.py compares):
+
+  derivation (pure functions below)                 reference
+  ------------------------------------------------  ----------------------------
+  problem definitions, fall-backs                   system_factory.py:95-117
+  class count, training -> inference / eval maps    :124-157
+  eval_NN result directory                          :159-172
+  steps per epoch / total steps                     :197-201, :355-361
+  piecewise schedule: epochs -> steps, plateau lrs  :207-233
+  checkpoint cadence, EMA switch under --distribute :238-248
+  void row / column of the confusion matrix         :400-405
+
+`tf.estimator.Estimator` is replaced by wlseg.estimator.Estimator; one process per GPU replaces MirroredStrategy, so the
+log-directory preconditions are decided on rank 0 and agreed on collectively.
 """
 
-import collections
 import copy
 import glob
 import json
 import os
-from os.path import exists, isdir, join, split
 
 from wlseg import estimator as est
 from wlseg import hierarchy, metrics
 
+_VOID = -1
 
+
+# ---------------------------------------------------------------------------------------------- pure derivations
+def _read_json(path):
+  with open(path, 'r') as fp:
+    return json.load(fp)
+
+
+def attach_problem_definitions(s):
+  """training_problem_def always; inference / evaluation ones when the mode has the flag, falling back to the training
+  definition when the flag is empty."""
+  s.training_problem_def = _read_json(s.training_problem_def_path)
+  for kind in ('inference', 'evaluation'):
+    flag = f'{kind}_problem_def_path'
+    if hasattr(s, flag):
+      path = getattr(s, flag)
+      setattr(s, f'{kind}_problem_def', _read_json(path) if path else s.training_problem_def)
+
+
+def check_settings(s):
+  """The reference's `_validate_settings` (:431-461): network size == feature-extractor size, exactly one of
+  decay / values for the piecewise schedule, contiguous training class ids."""
+  if (s.height_network, s.width_network) != (s.height_feature_extractor, s.width_feature_extractor):
+    raise AssertionError(f'network size {s.height_network}x{s.width_network} must equal the feature extractor size '
+                         f'{s.height_feature_extractor}x{s.width_feature_extractor} for now.')
+  if getattr(s, 'learning_rate_schedule', None) == 'piecewise_constant':
+    if bool(s.learning_rate_decay) == bool(s.learning_rate_values):
+      raise AttributeError('piecewise_constant needs exactly one of learning_rate_decay / learning_rate_values.')
+  cids = set(s.training_problem_def['lids2cids']) - {_VOID}
+  if cids != set(range(max(cids) + 1)):
+    raise ValueError('lids2cids of the training problem definition must cover 0..max without gaps.')
+
+
+def class_id_space(s):
+  """-> (has unlabeled ids, number of output classes): one extra class when label ids map to void or a void class is
+  trained explicitly."""
+  lids2cids = s.training_problem_def['lids2cids']
+  unlabeled = _VOID in lids2cids
+  return unlabeled, max(lids2cids) + 1 + (unlabeled or s.train_void_class)
+
+
+def training_cids_to(problem_def, key, n_classes, last_is_void):
+  """Map from training class ids to the ids of another problem definition: the definition's own table when it has one,
+  else the identity with the trailing void class sent to -1."""
+  if key in problem_def:
+    return problem_def[key]
+  ids = list(range(n_classes))
+  if last_is_void:
+    ids[-1] = _VOID
+  return ids
+
+
+def next_eval_dir(log_dir):
+  """log_dir/eval_NN with NN one above the highest existing."""
+  taken = [int(os.path.basename(d)[-2:]) for d in glob.glob(os.path.join(log_dir, 'eval_*')) if os.path.isdir(d)]
+  return os.path.join(log_dir, f'eval_{max(taken, default=-1) + 1:02}')
+
+
+def steps_per_epoch(n_examples, s):
+  """(examples per epoch, batches per epoch); the size ratio is 1 while network == feature-extractor size."""
+  examples = int(n_examples * s.height_network // s.height_feature_extractor * s.width_network // s.width_feature_extractor)
+  return examples, int(examples / s.Nb)
+
+
+def piecewise_schedule_in_steps(s):
+  """Boundaries given in epochs become steps; a boundary at the last epoch is dropped; with a decay factor the plateau
+  values are lr0 * decay^i."""
+  if not (s.learning_rate_decay or s.learning_rate_values):
+    s.learning_rate_decay = 0.5
+  epochs = s.learning_rate_boundaries
+  if epochs[-1] > s.Ne:
+    raise ValueError('Ne is less than learning rate boundaries.')
+  if epochs[-1] == s.Ne:
+    epochs.pop()
+  s.learning_rate_boundaries_epochs = epochs
+  s.learning_rate_boundaries = [e * s.num_batches_per_epoch for e in epochs]
+  if s.learning_rate_decay:
+    s.learning_rate_values = [s.learning_rate_initial * s.learning_rate_decay ** i for i in range(len(epochs) + 1)]
+
+
+def _rank(s):
+  return getattr(s, 'rank', 0)
+
+
+def _any_rank(flag, settings):
+  """Logical OR of `flag` over the ranks (identity in a single process)."""
+  import torch
+  import torch.distributed as dist
+  if getattr(settings, 'world_size', 1) > 1 and dist.is_available() and dist.is_initialized():
+    dev = getattr(settings, 'device', 'cuda') if dist.get_backend() == 'nccl' else 'cpu'
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(int(t.item()))
+  return bool(flag)
+
+
+# ---------------------------------------------------------------------------------------------- the facade
 class SemanticSegmentation(object):
 
   def __init__(self, input_fns, model_fn, settings):
-    assert settings is not None, ('settings must be provided for now.')
-    self._settings = copy.deepcopy(settings)
-    s = self._settings
-    s.height_network = s.height_feature_extractor
-    s.width_network = s.width_feature_extractor
+    if settings is None:
+      raise AssertionError('settings must be provided for now.')
+    s = self._settings = copy.deepcopy(settings)
+    self._input_fns, self._model_fn, self._estimator = input_fns, model_fn, None
 
-    with open(s.training_problem_def_path, 'r') as fp:
-      s.training_problem_def = json.load(fp)
-    if hasattr(s, 'inference_problem_def_path'):
-      if s.inference_problem_def_path:
-        with open(s.inference_problem_def_path, 'r') as fp:
-          s.inference_problem_def = json.load(fp)
-      else:
-        s.inference_problem_def = s.training_problem_def
-    if hasattr(s, 'evaluation_problem_def_path'):
-      if s.evaluation_problem_def_path:
-        with open(s.evaluation_problem_def_path, 'r') as fp:
-          s.evaluation_problem_def = json.load(fp)
-      else:
-        s.evaluation_problem_def = s.training_problem_def
+    s.height_network, s.width_network = s.height_feature_extractor, s.width_feature_extractor
+    attach_problem_definitions(s)
+    if getattr(s, 'learning_rate_schedule', None) == 'piecewise_constant' and not (s.learning_rate_decay or s.learning_rate_values):
+      s.learning_rate_decay = 0.5
+    check_settings(s)
 
-    _set_defaults(s)
-    _validate_settings(s)
+    s.lids_training_contain_unlabeled, s.output_Nclasses = class_id_space(s)
+    last_is_void = s.lids_training_contain_unlabeled and not s.train_void_class
+    for kind in ('inference', 'evaluation'):
+      if hasattr(s, f'{kind}_problem_def'):
+        key = f'training_cids2{kind}_cids'
+        setattr(s, key, training_cids_to(getattr(s, f'{kind}_problem_def'), key, s.output_Nclasses, last_is_void))
+    s.eval_res_dir = next_eval_dir(s.log_dir)
 
-    self._input_fns = input_fns
-    self._model_fn = model_fn
-    self._estimator = None
-
-    lids2cids_training = s.training_problem_def['lids2cids']
-    s.lids_training_contain_unlabeled = -1 in lids2cids_training
-    s.output_Nclasses = (max(lids2cids_training) + 1 +
-                         (s.lids_training_contain_unlabeled or s.train_void_class))
-
-    if hasattr(s, 'inference_problem_def'):
-      if 'training_cids2inference_cids' in s.inference_problem_def.keys():
-        s.training_cids2inference_cids = s.inference_problem_def['training_cids2inference_cids']
-      else:
-        tcids2pcids = list(range(s.output_Nclasses))
-        if s.lids_training_contain_unlabeled and not s.train_void_class:
-          tcids2pcids[-1] = -1
-        s.training_cids2inference_cids = tcids2pcids
-    if hasattr(s, 'evaluation_problem_def'):
-      if 'training_cids2evaluation_cids' in s.evaluation_problem_def.keys():
-        s.training_cids2evaluation_cids = s.evaluation_problem_def['training_cids2evaluation_cids']
-      else:
-        tcids2ecids = list(range(s.output_Nclasses))
-        if s.lids_training_contain_unlabeled and not s.train_void_class:
-          tcids2ecids[-1] = -1
-        s.training_cids2evaluation_cids = tcids2ecids
-
-    existing_eval_dirs = list(filter(isdir, glob.glob(join(s.log_dir, 'eval_*'))))
-    if existing_eval_dirs:
-      max_cnt = max([int(split(ed)[1][-2:]) for ed in existing_eval_dirs])
-    else:
-      max_cnt = -1
-    s.eval_res_dir = join(s.log_dir, 'eval_' + f"{max_cnt + 1:02}")
-
-    # the hierarchy tables are not part of the problem definition upstream (hard-coded per dataset);
-    # here they are derived from its class names
+    # upstream hard-codes the hierarchy tables per dataset; here they come from the class names of the definition
     self._hier = hierarchy.Hierarchy(s.per_pixel_dataset_name, s.training_problem_def['cids2labels'])
-    assert self._hier.num_classes == s.output_Nclasses, (
-        f"problem definition has {s.output_Nclasses} classes but the {s.per_pixel_dataset_name} "
-        f"hierarchy expects {self._hier.num_classes}")
+    if self._hier.num_classes != s.output_Nclasses:
+      raise AssertionError(f'problem definition has {s.output_Nclasses} classes but the {s.per_pixel_dataset_name} '
+                           f'hierarchy expects {self._hier.num_classes}')
 
   @property
   def settings(self):
@@ -117,110 +184,83 @@ class SemanticSegmentation(object):
   # ------------------------------------------------------------------------------------------ train
   def train(self):
     s = self._settings
-    s.num_examples_per_epoch = int(s.Ntrain * s.height_network // s.height_feature_extractor *
-                                   s.width_network // s.width_feature_extractor)
-    s.num_batches_per_epoch = int(s.num_examples_per_epoch / s.Nb)
+    s.num_examples_per_epoch, s.num_batches_per_epoch = steps_per_epoch(s.Ntrain, s)
     s.num_training_steps = int(s.Ne * s.num_batches_per_epoch)
-
     if s.learning_rate_schedule == 'piecewise_constant':
-      if not (s.learning_rate_decay or s.learning_rate_values):
-        s.learning_rate_decay = 0.5
-      last_boundary = s.Ne - s.learning_rate_boundaries[-1]
-      if last_boundary == 0:
-        s.learning_rate_boundaries.pop()
-      elif last_boundary < 0:
-        raise ValueError('Ne is less than learning rate boundaries.')
-      s.learning_rate_boundaries_epochs = s.learning_rate_boundaries
-      s.learning_rate_boundaries = [lrb * s.num_batches_per_epoch for lrb in s.learning_rate_boundaries]
-      if s.learning_rate_decay:
-        decay_steps = len(s.learning_rate_boundaries) + 1
-        s.learning_rate_values = [s.learning_rate_initial * s.learning_rate_decay ** i for i in range(decay_steps)]
-
+      piecewise_schedule_in_steps(s)
     if s.distribute:
-      print('\n\nDisabling moving running averages for distributed training.\n\n')
+      print('\n--distribute: exponential moving averages are switched off.\n')
       s.ema_decay = 0
-
     os.makedirs(s.log_dir, exist_ok=True)
-    if not s.save_checkpoints_steps:
-      s.save_checkpoints_steps = s.num_batches_per_epoch
+    s.save_checkpoints_steps = s.save_checkpoints_steps or s.num_batches_per_epoch
 
-    settings_dict = collections.OrderedDict(sorted(vars(s).items()))
-    settings_filename = join(s.log_dir, 'settings.txt')
-    # one process per GPU: rank 0 owns the log directory (the reference is a single process); its verdict is made
-    # collective so that a failed precondition stops EVERY rank instead of leaving the others in their first collective
-    stale = bool(getattr(s, 'rank', 0) == 0 and exists(settings_filename))
-    stale = _any_rank(stale, s)
-    assert not stale, (
-        f"Previous settings.txt found in {s.log_dir}. Rename or delete it manually and restart training.")
-    if getattr(s, 'rank', 0) == 0:
-      with open(settings_filename, 'w') as f:
-        for k, v in enumerate(settings_dict):
-          print(f"{k:2} : {v} : {settings_dict[v]}", file=f)
+    # settings.txt: one "index : name : value" line per attribute, sorted by name; a previous file stops the run.
+    # Rank 0 owns the log directory (the reference is a single process) and every rank learns its verdict, so that a
+    # failed precondition stops the whole job instead of leaving the other ranks in their first collective.
+    record = os.path.join(s.log_dir, 'settings.txt')
+    if _any_rank(_rank(s) == 0 and os.path.exists(record), s):
+      raise AssertionError(f'Previous settings.txt found in {s.log_dir}. Rename or delete it manually and restart training.')
+    if _rank(s) == 0:
+      with open(record, 'w') as fp:
+        for i, (name, value) in enumerate(sorted(vars(s).items())):
+          print(f'{i:2} : {name} : {value}', file=fp)
 
     self._create_estimator(for_training=True)
-    max_steps = s.num_training_steps if not getattr(s, 'steps', None) else min(s.steps, s.num_training_steps)
+    budget = getattr(s, 'steps', None)
+    max_steps = min(budget, s.num_training_steps) if budget else s.num_training_steps
     return self._estimator.train(self._input_fns['train'](None, s), max_steps)
 
   # ------------------------------------------------------------------------------------------ predict
   def predict(self):
     s = self._settings
     if s.Nb > 1:
-      print('\nWARNING: during prediction only images with same shape (size and channels) '
-            'are supported for batch size greater than one. In case of runtime error '
-            'change batch size to 1.\n')
+      print('\nWARNING: a prediction batch of more than one image needs images of one shape; use --Nb 1 otherwise.\n')
     self._create_estimator(ckpt_path=s.ckpt_path)
-    predict_keys = copy.deepcopy(s.predict_keys)
-    return self._estimator.predict(self._input_fns['predict'](None, s), predict_keys)
+    return self._estimator.predict(self._input_fns['predict'](None, s), list(s.predict_keys))
 
   # ------------------------------------------------------------------------------------------ evaluate
   def evaluate(self):
     s = self._settings
-    s.num_examples = int(s.Neval * s.height_network // s.height_feature_extractor *
-                         s.width_network // s.width_feature_extractor)
-    s.num_batches_per_epoch = int(s.num_examples / s.Nb)
+    s.num_examples, s.num_batches_per_epoch = steps_per_epoch(s.Neval, s)
     s.num_eval_steps = int(s.num_batches_per_epoch * 1)
-
-    eval_res_dir = s.eval_res_dir
-    print(f"\nWriting results in {eval_res_dir}.\n")
-    if getattr(s, 'rank', 0) == 0:
-      os.makedirs(eval_res_dir)
-      if exists(join(eval_res_dir, 'settings.txt')):
-        print(f"WARNING: previous settings.txt in {eval_res_dir} is ovewritten.")
-      with open(join(eval_res_dir, 'settings.txt'), 'w') as f:
-        for k, v in vars(s).items():
-          print(f"{k} : {v}", file=f)
-
-    labels = s.evaluation_problem_def['cids2labels']
-    void_exists = -1 in s.evaluation_problem_def['lids2cids']
-    if void_exists and not s.train_void_class:
-      labels = labels[:-1]
-
     if getattr(s, 'preserve_aspect_ratio', False):
       raise NotImplementedError('evaluation with preserving aspect ratio is not implemented.')
 
-    all_model_checkpoint_paths = [s.ckpt_path]
+    print(f'\nWriting results in {s.eval_res_dir}.\n')
+    if _rank(s) == 0:
+      os.makedirs(s.eval_res_dir)
+      with open(os.path.join(s.eval_res_dir, 'settings.txt'), 'w') as fp:
+        for name, value in vars(s).items():
+          print(f'{name} : {value}', file=fp)
+
+    # the void class (last id) is evaluated only when it was trained explicitly
+    drop_void = _VOID in s.evaluation_problem_def['lids2cids'] and not s.train_void_class
+    class_names = s.evaluation_problem_def['cids2labels']
+    if drop_void:
+      class_names = class_names[:-1]
+
+    checkpoints = [s.ckpt_path]
     if s.eval_all_ckpts:
       s.ckpt_path = None
-      all_model_checkpoint_paths = sorted(glob.glob(join(s.log_dir, 'model.ckpt-*.pt')),
-                                          key=lambda p: int(p.rsplit('-', 1)[1].split('.')[0]))
-      print(f"\n{len(all_model_checkpoint_paths)} checkpoint(s) will be evaluated.\n")
+      checkpoints = sorted(glob.glob(os.path.join(s.log_dir, 'model.ckpt-*.pt')),
+                           key=lambda p: int(p.rsplit('-', 1)[1].split('.')[0]))
+      print(f'\n{len(checkpoints)} checkpoint(s) will be evaluated.\n')
 
-    tcids2ecids = est._replacevoids(s.training_cids2evaluation_cids)
-    num_classes = max(tcids2ecids) + 1
-    identity = tcids2ecids == list(range(len(tcids2ecids)))
+    lut = est._replacevoids(s.training_cids2evaluation_cids)
+    num_classes = max(lut) + 1
+    if lut == list(range(len(lut))):
+      lut = None                      # identity map: the kernel skips the lookup
 
-    all_metrics = []
-    for cp in all_model_checkpoint_paths:
-      self._create_estimator(ckpt_path=cp)
-      metrics_ = self._estimator.evaluate(self._input_fns['eval'](None, s), num_classes,
-                                          lut=None if identity else tcids2ecids)
-      metrics_ = self._reduce_across_ranks(metrics_)
-      if (-1 in s.evaluation_problem_def['lids2cids'] and not s.train_void_class):
-        metrics_['confusion_matrix'] = metrics_['confusion_matrix'][:-1, :-1]
-      if getattr(s, 'rank', 0) == 0:
-        metrics.print_metrics_from_confusion_matrix(metrics_['confusion_matrix'], labels, printcmd=True)
-      all_metrics.append(metrics_)
-    return all_metrics
+    results = []
+    for path in checkpoints:
+      self._create_estimator(ckpt_path=path)
+      m = self._reduce_across_ranks(self._estimator.evaluate(self._input_fns['eval'](None, s), num_classes, lut=lut))
+      if drop_void:
+        m['confusion_matrix'] = m['confusion_matrix'][:-1, :-1]
+      if _rank(s) == 0:
+        metrics.print_metrics_from_confusion_matrix(m['confusion_matrix'], class_names, printcmd=True)
+      results.append(m)
+    return results
 
   def _reduce_across_ranks(self, m):
     """Evaluation sharded by image: integer confusion matrices are summed across ranks (exact)."""
@@ -234,42 +274,3 @@ class SemanticSegmentation(object):
       m['confusion_matrix_int64'] = t.cpu().numpy()
       m['confusion_matrix'] = m['confusion_matrix_int64'].astype(np.int32)
     return m
-
-
-def _any_rank(flag, settings):
-  """Logical OR of `flag` over the ranks (identity in a single process)."""
-  import torch
-  import torch.distributed as dist
-  if getattr(settings, 'world_size', 1) > 1 and dist.is_available() and dist.is_initialized():
-    dev = getattr(settings, 'device', 'cuda') if dist.get_backend() == 'nccl' else 'cpu'
-    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return bool(int(t.item()))
-  return bool(flag)
-
-
-def _set_defaults(settings):
-  if hasattr(settings, 'learning_rate_schedule'):
-    if settings.learning_rate_schedule == 'piecewise_constant':
-      if not (settings.learning_rate_decay or settings.learning_rate_values):
-        settings.learning_rate_decay = 0.5
-
-
-def _validate_settings(settings):
-  assert all([settings.height_network == settings.height_feature_extractor,
-              settings.width_network == settings.width_feature_extractor]), (
-                  f"For now height_network ({settings.height_network}), "
-                  f"height feature_extractor ({settings.height_feature_extractor}), "
-                  f"and width_network ({settings.width_network}), "
-                  f"width_feature_extractor ({settings.width_feature_extractor}) "
-                  "should be equal.")
-  if hasattr(settings, 'learning_rate_schedule'):
-    if settings.learning_rate_schedule == 'piecewise_constant':
-      if not (bool(settings.learning_rate_decay) != bool(settings.learning_rate_values)):
-        raise AttributeError('If `learning_rate_schedule` is `piecewise_constant` exactly one of '
-                             '`learning_rate_decay` or `learning_rate_values` must be given.')
-  lids2cids_unique = set(settings.training_problem_def['lids2cids'])
-  cid_max = max(lids2cids_unique)
-  lids2cids_unique.discard(-1)
-  if not (lids2cids_unique == set(range(cid_max + 1))):
-    raise ValueError('lids2cids field in training problem definition contains not continuous class ids.')
