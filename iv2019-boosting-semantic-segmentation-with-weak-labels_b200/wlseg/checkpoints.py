@@ -108,7 +108,8 @@ def export_train_state(params, trainer=None):
   out = collections.OrderedDict(params.to_tf_dict())
   if trainer is None:
     return out
-  arenas = [(momentum_name, trainer.ws.momentum)]
+  # --optimizer SGD: tf.train.GradientDescentOptimizer has no slot variables (define_optimizer.py:21-22)
+  arenas = [(momentum_name, trainer.ws.momentum)] if getattr(trainer, 'optimizer', 'SGDM') == 'SGDM' else []
   if getattr(trainer.ws, 'ema_shadow', None) is not None:
     arenas.append((ema_name, trainer.ws.ema_shadow))
   for namer, arena in arenas:

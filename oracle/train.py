@@ -24,10 +24,11 @@ from oracle import optimizer as oopt
 class TrainState:
   """What the TF session holds between steps: variables, Momentum slots, EMA shadows, the global step."""
 
-  def __init__(self, tf_params, ema_decay=0.0):
+  def __init__(self, tf_params, ema_decay=0.0, optimizer='SGDM'):
     self.vars = {k: v.detach().clone() for k, v in tf_params.items()}
     self.trainable = [k for k in self.vars if '/moving_' not in k]
-    self.momentum = {k: torch.zeros_like(self.vars[k]) for k in self.trainable}
+    # tf.train.GradientDescentOptimizer ('SGD', define_optimizer.py:21-22) creates no slot variables
+    self.momentum = {k: torch.zeros_like(self.vars[k]) for k in self.trainable} if optimizer == 'SGDM' else {}
     self.ema_decay = float(ema_decay)
     # [TF-1.12] the shadow of a tf.Variable starts at the variable's initial value (no zero-debias for Variables)
     self.ema = {k: self.vars[k].clone() for k in self.trainable} if self.ema_decay > 0 else {}
@@ -35,10 +36,12 @@ class TrainState:
 
 
 def train_step(state, images, labels, dataset, lr, momentum=0.9, nesterov=False, regularization_weight=0.00017,
-               bn_decay=0.9, storage='fp32'):
-  """One `session.run(train_op)`; -> dict of the step's losses (python floats) and the gradients."""
-  params = {k: v.clone().requires_grad_(k in state.momentum) for k, v in state.vars.items()}
-  net = onet.Net(params, dataset, training=True, bn_decay=bn_decay, storage=storage)
+               bn_decay=0.9, storage='fp32', **model_flags):
+  """One `session.run(train_op)`; -> dict of the step's losses (python floats) and the gradients.
+  model_flags: psp / fov / upsampling / norm of oracle.network.Net."""
+  trainable = set(state.trainable)
+  params = {k: v.clone().requires_grad_(k in trainable) for k, v in state.vars.items()}
+  net = onet.Net(params, dataset, training=True, bn_decay=bn_decay, storage=storage, **model_flags)
   pred = net.forward(images)
   kernels = [params[k] for k in state.trainable if k.endswith('/weights')]
   losses = olosses.define_losses(pred, labels, dataset, conv_weights=kernels, regularization_weight=regularization_weight)
@@ -55,7 +58,10 @@ def train_step(state, images, labels, dataset, lr, momentum=0.9, nesterov=False,
     for k in state.trainable:
       g = params[k].grad
       grads[k] = g
-      state.vars[k], state.momentum[k] = oopt.momentum_step(state.vars[k], g, state.momentum[k], lr, momentum, nesterov)
+      if state.momentum:
+        state.vars[k], state.momentum[k] = oopt.momentum_step(state.vars[k], g, state.momentum[k], lr, momentum, nesterov)
+      else:
+        state.vars[k] = state.vars[k] - lr * g
     state.global_step += 1
   out = {k: float(v.detach()) for k, v in losses.items() if k != 'counts'}
   out['grads'] = grads

@@ -58,6 +58,22 @@ CASES = {
                                      learning_rate_final=0.0001, learning_rate_power=0.9, num_training_steps=5,
                                      optimizer='SGDM', momentum=0.8, use_nesterov=True, ema_decay=0.0,
                                      regularization_weight=0.02, batch_norm_decay=0.95)),
+    'vistas_mixed_sgdm': ('vistas', 1, 1, 1, 40, 56, 2,
+                          dict(learning_rate_schedule='piecewise_constant', learning_rate_boundaries=[50],
+                               learning_rate_values=[0.01, 0.005], optimizer='SGDM', momentum=0.9, use_nesterov=False,
+                               ema_decay=0.0, regularization_weight=0.00017, batch_norm_decay=0.9)),
+    'cs_psp_fov_hybrid': ('cityscapes', 2, 0, 0, 48, 64, 2,
+                          dict(learning_rate_schedule='piecewise_constant', learning_rate_boundaries=[50],
+                               learning_rate_values=[0.01, 0.005], optimizer='SGDM', momentum=0.9, use_nesterov=False,
+                               ema_decay=0.9, regularization_weight=0.00017, batch_norm_decay=0.9,
+                               model=({'psp': True, 'fov': (3, 2), 'upsampling': 'hybrid'},
+                                      {'psp_module': True, 'fov_expansion_kernel_size': 3, 'fov_expansion_kernel_rate': 2,
+                                       'upsampling_method': 'hybrid'}))),
+    'cs_group_norm': ('cityscapes', 1, 1, 0, 40, 56, 2,
+                      dict(learning_rate_schedule='piecewise_constant', learning_rate_boundaries=[50],
+                           learning_rate_values=[0.01, 0.005], optimizer='SGD', momentum=0.9, use_nesterov=False,
+                           ema_decay=0.0, regularization_weight=0.00017, batch_norm_decay=0.9,
+                           model=({'norm': 'group'}, {'norm_layer': 'group'}))),
 }
 # variables stored whole (everything else: checksums)
 KEEP = ('feature_extractor/base/resnet_v1_50/conv1/weights',
@@ -77,9 +93,10 @@ def case_params(tag):
   if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
   from oracle import network as onet
-  params = onet.init_params(CASES[tag][0], seed=SEED, randomize_bn=True, tame=True)
+  init_kw = CASES[tag][7].get('model', ({}, {}))[0]
+  params = onet.init_params(CASES[tag][0], seed=SEED, randomize_bn=True, tame=True, **init_kw)
   for k in params:
-    if k.endswith('/conv3/BatchNorm/gamma'):
+    if k.endswith(('/conv3/BatchNorm/gamma', '/conv3/GroupNorm/gamma')):
       params[k] = params[k] * RESIDUAL_GAMMA_SCALE
   return params
 
@@ -206,8 +223,10 @@ def main():
         height_feature_extractor=H, width_feature_extractor=W, upsampling_method='bilinear', stride_feature_extractor=8,
         feature_dims_decreased=256, fov_expansion_kernel_rate=0, fov_expansion_kernel_size=0, Nb=n_pp + n_pb + n_pi,
         Nb_per_pixel=n_pp, Nb_per_bbox=n_pb, Nb_per_image=n_pi, distribute=False, init_ckpt_path='', log_dir='/tmp/unused',
-        num_training_steps=opt.get('num_training_steps', 100), save_checkpoints_steps=50, **{k: v for k, v in opt.items()
-                                                                                            if k != 'num_training_steps'})
+        num_training_steps=opt.get('num_training_steps', 100), save_checkpoints_steps=50,
+        **{k: v for k, v in opt.items() if k not in ('num_training_steps', 'model')})
+    for k, v in opt.get('model', ({}, {}))[1].items():
+      setattr(params, k, v)
     config = types.SimpleNamespace(train_distribute=None, keep_checkpoint_max=2)
     batches = case_batches(tag)
     out[f'{tag}/names'] = np.asarray('\n'.join(names))
@@ -263,6 +282,10 @@ def main():
     out[f'{tag}/final/ema_checksums'] = sums(_train.EMA_SHADOWS, lambda n: f'exponential_moving_averages/{n}/ExponentialMovingAverage')
     out[f'{tag}/ema_names'] = np.asarray('\n'.join(sorted(_train.EMA_SHADOWS.keys())))
     for n in KEEP:
+      if n not in _slim.VARS:        # group norm: no moving statistics, <scope>/GroupNorm/{beta,gamma}
+        n = n.replace('/BatchNorm/', '/GroupNorm/')
+        if n not in _slim.VARS:
+          continue
       out[f'{tag}/final/{n}'] = _slim.VARS[n].detach().numpy().copy()
       if n in _train.OPT_SLOTS:
         out[f'{tag}/final_momentum/{n}'] = _train.OPT_SLOTS[n].numpy().copy()

@@ -295,8 +295,10 @@ def train_gold():
   return np.load(cpu_side.TRAIN_GOLD)
 
 
-@pytest.mark.parametrize('tag', ['cs_mixed_sgdm_ema', 'cs_strong_nesterov_poly'])
-@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+@pytest.mark.parametrize('tag,dtype', [('cs_mixed_sgdm_ema', 'fp32'), ('cs_mixed_sgdm_ema', 'bf16'),
+                                       ('cs_strong_nesterov_poly', 'fp32'), ('cs_strong_nesterov_poly', 'bf16'),
+                                       ('vistas_mixed_sgdm', 'fp32'), ('vistas_mixed_sgdm', 'bf16'),
+                                       ('cs_psp_fov_hybrid', 'fp32'), ('cs_group_norm', 'fp32')])
 def test_trainer_equals_the_reference_training_run(cuda, train_gold, tag, dtype):
   """The reference's `define_estimator` TRAIN branch (define_estimator_hierarchical.py:77-159: model() in training mode,
   define_losses, EMA in UPDATE_OPS, define_optimizer, create_train_op), executed by the reference itself for 3 / 2
@@ -314,7 +316,7 @@ def test_trainer_equals_the_reference_training_run(cuda, train_gold, tag, dtype)
   gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), batches = cpu_side.train_case_batches(train_gold, tag)
   initial = gen.case_params(tag)
   hier = _hier(dataset)
-  params = network.Params(hier, cuda)
+  params = network.Params(hier, cuda, **opt.get('model', ({}, {}))[0])     # psp / fov / upsampling / norm
   params.load_tf_dict(initial)
   settings = type('S', (), dict(momentum=opt['momentum'], use_nesterov=opt['use_nesterov'], optimizer=opt['optimizer'],
                                 regularization_weight=opt['regularization_weight'], batch_norm_decay=opt['batch_norm_decay'],

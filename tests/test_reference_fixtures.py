@@ -8,6 +8,7 @@ tests/golden/reference_run.npz is written by tests/golden/make_reference_fixture
 gathers, masks, weights, normalisation, remaps, resize calls); TensorFlow's own kernels stay restated.
 """
 
+import importlib
 import io
 import os
 
@@ -417,7 +418,7 @@ def test_evaluate_driver_settings_equal_the_reference_run(tag, tmp_path, monkeyp
 
 # ------------------------------------------------------------------------------------------------ the TRAIN branch
 TRAIN_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_train_run.npz')
-TRAIN_CASES = ['cs_mixed_sgdm_ema', 'cs_strong_nesterov_poly']
+TRAIN_CASES = ['cs_mixed_sgdm_ema', 'cs_strong_nesterov_poly', 'vistas_mixed_sgdm', 'cs_psp_fov_hybrid', 'cs_group_norm']
 
 
 @pytest.fixture(scope='module')
@@ -487,6 +488,8 @@ def compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum,
   worst_cos, worst_norm, bad = 1.0, 0.0, []
   for store, key, base in ((variables, 'final', initial), (momentum, 'final_momentum', None), (ema, 'final_ema', initial)):
     for n in gen.KEEP:
+      if n not in initial:      # group norm: <scope>/GroupNorm/{beta,gamma}, no moving statistics
+        n = n.replace('/BatchNorm/', '/GroupNorm/')
       k = f'{tag}/{key}/{n}'
       if k not in train_gold.files:
         assert n not in store or key == 'final', (key, n)
@@ -512,15 +515,28 @@ def compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum,
 def test_product_state_names_equal_the_reference_training_run(train_gold):
   """The names under which the product exports its training state (wlseg/checkpoints.py) against what the reference's
   TRAIN graph created: the model variables, and an ExponentialMovingAverage shadow for exactly the variables
-  define_estimator_hierarchical.py:103-106 selects, under the scope of :97."""
+  define_estimator_hierarchical.py:103-106 selects, under the scope of :97; one Momentum slot per trainable variable
+  (none with --optimizer SGD).  Plain, Vistas, pyramid + field-of-view + hybrid upsampling, group norm."""
   import types
   from wlseg import arch, checkpoints as ck
-  p = types.SimpleNamespace(specs=arch.conv_specs((14, 7, 3)), norm='batch', plain=())
-  names = [n for n, _ in ck.model_variables(p)]
-  assert sorted(names) == str(train_gold['cs_mixed_sgdm_ema/names']).split('\n')
-  assert sorted(ck.ema_name(n) for n in names if ck.has_ema(n)) == str(train_gold['cs_mixed_sgdm_ema/ema_names']).split('\n')
-  slots = train_gold['cs_mixed_sgdm_ema/final/momentum_checksums']
-  assert [ck.trainable(n) for n in sorted(names)] == [bool(c >= 0) for c in slots]
+  gen = importlib.import_module('tests.golden.make_reference_train_fixtures')
+  for tag in TRAIN_CASES:
+    dataset, opt = gen.CASES[tag][0], gen.CASES[tag][7]
+    kw = opt.get('model', ({}, {}))[0]
+    up = kw.get('upsampling', 'bilinear')
+    heads = (14, 7, 3) if dataset == 'cityscapes' else (53, 12, 5)
+    p = types.SimpleNamespace(specs=arch.conv_specs(heads, psp=kw.get('psp', False), fov=kw.get('fov'), upsampling=up),
+                              norm=kw.get('norm', 'batch'), plain=tuple(arch.UPSAMPLING_SCOPES) if up == 'hybrid' else ())
+    names = [n for n, _ in ck.model_variables(p)]
+    assert sorted(names) == str(train_gold[f'{tag}/names']).split('\n'), tag
+    ema_names = [n for n in str(train_gold[f'{tag}/ema_names']).split('\n') if n]
+    if opt['ema_decay'] > 0:
+      assert sorted(ck.ema_name(n) for n in names if ck.has_ema(n)) == ema_names, tag
+    else:
+      assert ema_names == []
+    slots = train_gold[f'{tag}/final/momentum_checksums']
+    want = [ck.trainable(n) and opt['optimizer'] == 'SGDM' for n in sorted(names)]
+    assert want == [bool(c >= 0) for c in slots], tag
 
 
 def reference_lr(train_gold, tag, opt, step):
@@ -544,13 +560,14 @@ def test_oracle_training_steps_equal_the_reference_run(train_gold, tag):
   from oracle import train as otrain
   gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), batches = train_case_batches(train_gold, tag)
   initial = gen.case_params(tag)
-  state = otrain.TrainState(initial, ema_decay=opt['ema_decay'])
+  state = otrain.TrainState(initial, ema_decay=opt['ema_decay'], optimizer=opt['optimizer'])
+  model_flags = opt.get('model', ({}, {}))[0]
   rows = []
   for i, (images, labels) in enumerate(batches):
     assert int(train_gold[f'{tag}/step{i}/global_step_before']) == state.global_step == i
     lr = reference_lr(train_gold, tag, opt, state.global_step)
     got = otrain.train_step(state, images, labels, dataset, lr, momentum=opt['momentum'], nesterov=opt['use_nesterov'],
-                            regularization_weight=opt['regularization_weight'], bn_decay=opt['batch_norm_decay'])
+                            regularization_weight=opt['regularization_weight'], bn_decay=opt['batch_norm_decay'], **model_flags)
     rows.append([got[k] for k in ('total', 'l1_segmentation', 'l2_vehicle_segmentation', 'l2_human_segmentation', 'regularization')])
   assert state.global_step == int(train_gold[f'{tag}/global_step'])
   if opt['ema_decay'] > 0:
