@@ -13,6 +13,7 @@ below are the reference's own objects, called unmodified:
   estimator.define_metrics.mean_iou                                      (define_metrics.py:5-20)
   estimator.define_optimizer.define_optimizer                            (define_optimizer.py:3-26)
   input_pipelines.open_images.input_subset_bboxes_v2._generate_rla       (input_subset_bboxes_v2.py:74-98)
+  input_pipelines.open_images.input_subset_image_labels._generate_rla    (input_subset_image_labels.py:73-94)
   input_pipelines.utils.get_temp_Nb, from_0_1_to_m1_1                    (input_pipelines/utils.py:93-124)
   input_pipelines.utils.resize_images_and_labels                         (input_pipelines/utils.py:181-247)
   utils.utils._replacevoids, print_metrics_from_confusion_matrix         (utils/utils.py:286-289,385-446)
@@ -166,6 +167,19 @@ def main():
   out['rla/cids'] = np.asarray([ib.mid2cid.get(m.decode(), -1) for m in mids], dtype=np.int32)
   out['rla/size'] = np.asarray([20, 28], dtype=np.int32)
   out['rla/out'] = ib._generate_rla(b'x', mids, coords, np.asarray([20, 28], dtype=np.int32))
+
+  # ---- image-level labels: input_subset_image_labels._generate_rla (:73-94) - one, several, duplicated, unknown, no mids
+  from input_pipelines.open_images import input_subset_image_labels as il
+  cid2mid = {}
+  for mid, cid in il.mid2cid.items():
+    cid2mid.setdefault(cid, mid)
+  cases = [[3], [0, 5, 9], [2, 2, 11], [], [13, 0]]
+  vectors = []
+  for k, cids in enumerate(cases):
+    mids = [cid2mid[c].encode('utf-8') for c in cids] + ([b'/m/unknown'] if k == 2 else [])
+    vectors.append(il._generate_rla(b'img', np.asarray(mids, dtype=object), np.asarray([4, 6], dtype=np.int32)))
+  out['rla_image/cids'] = np.asarray([c + [-1] * (3 - len(c)) for c in cases], dtype=np.int32)
+  out['rla_image/out'] = np.stack(vectors).astype(np.float32)
 
   # ---- _map_predictions_to_new_cids: the worked example (:494-496) and the Cityscapes evaluation map
   g = torch.Generator().manual_seed(7)

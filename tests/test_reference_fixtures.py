@@ -82,6 +82,15 @@ def test_rasteriser_equals_generate_rla(gold):
       assert np.array_equal(oweak.bbox_labels(boxes, 8 * hh, 8 * ww), gold[f'{tag}/prolabels_per_bbox'][i]), (tag, i)
 
 
+def test_image_level_vectors_equal_generate_rla(gold):
+  """input_subset_image_labels.py:73-94 `_generate_rla` run by the reference (one class, several, a duplicate + an
+  unknown mid, none -> void) vs oracle/weak_labels.py::image_labels, bit-exact; the tiling is :102."""
+  for cids, want in zip(gold['rla_image/cids'], gold['rla_image/out']):
+    present = sorted({int(c) for c in cids if c >= 0})
+    got = oweak.image_labels(present, 4, 6)
+    assert got.shape == (4, 6, 15) and np.array_equal(got[0, 0], want) and np.array_equal(got, np.broadcast_to(want, got.shape))
+
+
 def test_segment_sum_worked_example(gold):
   """:112-113, 219-224: half a vehicle + half a human on one pixel -> 1/2 car + 1/2 void for the vehicle head."""
   lab = torch.from_numpy(gold['segment_sum/labels'])
