@@ -718,3 +718,47 @@ def test_product_warm_start_equals_the_reference_graph(train_gold, tag, psp):
   assert len(ref_map) == 53 * 5
   # with an init checkpoint the train saver keeps every global variable (exclude = [])
   assert sorted(str(train_gold[f'{tag}/train_saver']).split('\n')) == sorted(ref_globals)
+
+
+# ------------------------------------------------------------------------------------------------ predict.py
+def test_predict_driver_and_exports_equal_the_reference_run(tmp_path):
+  """code/predict.py::main executed by the reference (tests/golden/make_reference_predict_fixtures.py): parsed flags,
+  `_add_extra_args`, SemanticSegmentation's derived settings, what the estimator is asked for, and the export loop
+  (:137-164) on two fixed examples - against wlseg.settings + wlseg.system_factory + wlseg.cli.export_outputs: the same
+  settings, the same file names, the same PNG pixels (label ids through cids2lids, colours through cids2colors, the
+  50:50 overlay truncated to uint8)."""
+  import json
+  from PIL import Image
+  from wlseg import cli, problem_defs, settings as wsettings
+  from wlseg import system_factory as sf
+  gold = np.load(os.path.join(os.path.dirname(TRAIN_GOLD), 'reference_predict_run.npz'))
+  argv = json.loads(str(gold['argv']))
+  problem_defs.write_all()
+  argv[0] = problem_defs.default_path('cityscapes')       # the same problem definition, at the product's location
+  results = tmp_path / 'results'
+  results.mkdir()
+  st = wsettings.build_parser(wsettings.PREDICT).parse_args([str(tmp_path / 'log')] + argv + ['--results_dir', str(results)])
+  st = wsettings.predict_extra_args(st)
+  st.rank, st.world_size = 0, 1
+  system = sf.SemanticSegmentation({'predict': lambda config, params: iter(())}, None, st)
+  mine = vars(system.settings)
+  ref = json.loads(str(gold['settings']))
+  for k, v in ref.items():
+    if k in _PATH_KEYS:
+      continue
+    assert k in mine, f'the reference sets settings.{k}, the product does not'
+    assert mine[k] == v, f'settings.{k}: {mine[k]!r} != {v!r} (reference)'
+  (_, asked), = json.loads(str(gold['calls']))
+  assert asked['predict_keys'] == system.settings.predict_keys and asked['checkpoint_path'] == system.settings.ckpt_path
+  s = system.settings
+  idspalette = np.array(s.inference_problem_def['cids2lids'], dtype=np.uint8)
+  colorpalette = np.array(s.inference_problem_def['cids2colors'], dtype=np.uint8)
+  for i in range(2):
+    cli.export_outputs({'decisions': gold[f'example{i}/decisions'], 'rawimages': gold[f'example{i}/rawimages'],
+                        'rawimagespaths': str(gold[f'example{i}/rawimagespaths']).encode()}, s, idspalette, colorpalette)
+  names = sorted(os.listdir(str(results)))
+  assert names == str(gold['files']).split('\n')
+  for n in names:
+    got = np.asarray(Image.open(str(results / n)))
+    want = gold[f'png/{n}']
+    assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), n
