@@ -7,7 +7,6 @@ images per GPU, the reference's 4:8:4 ratio, train.py:52-55).
 """
 
 import json
-import os
 import time
 
 import torch

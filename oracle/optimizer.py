@@ -4,8 +4,6 @@ TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Pinned against the referenc
 (define_optimizer executed over tests/golden/tf_shim; tests/test_reference_fixtures.py).
 """
 
-import torch
-
 
 def piecewise_constant(step, boundaries, values):
   """[TF-1.12] tf.train.piecewise_constant via code/estimator/define_optimizer.py:5-7:
