@@ -1,4 +1,5 @@
-"""Golden vectors of predict.py produced by running the reference's own script:  tests/golden/reference_predict_run.npz.
+"""Golden vectors of predict.py and evaluate.py produced by running the reference's own scripts:
+tests/golden/reference_predict_run.npz.
 
     python tests/golden/make_reference_predict_fixtures.py       # needs /root/reference; run in the build container
 
@@ -12,6 +13,11 @@ what it was asked for; matplotlib (absent here, imported at the top of predict.p
 is an empty module.  Stored: the parsed settings, predict_keys, checkpoint path handed to the estimator, the file names
 written and the decoded PNGs.  tests/test_reference_fixtures.py runs wlseg.settings + wlseg.cli.export_outputs on the
 same examples and compares names and pixels.
+
+`code/evaluate.py::main(argv)` (the `__main__` guard raises upstream, main() itself is intact) runs the same way over the
+stub estimator of make_reference_driver_fixtures.py (a fixed 20 x 20 confusion matrix, global_step 1234): stored are the
+text of `eval_00/all_metrics.txt` (print_metrics_from_confusion_matrix through `printfile`) and the unpickled
+`all_metrics.p`.  The test runs wlseg.cli.evaluate_main on the same argv with the same fake estimator.
 """
 
 import contextlib
@@ -30,6 +36,9 @@ OUT = os.path.join(HERE, 'reference_predict_run.npz')
 SEED = 53
 ARGV_TAIL = ['problem_definitions/cityscapes/problem01.json', 'some/predict/dir', 'cityscapes', '--export_lids_images',
              '--export_color_decisions', '--export_overlapped_color_decisions', '--ckpt_path', 'model.ckpt-12631']
+
+
+EVAL_ARGV_TAIL = ['500', 'problem_definitions/cityscapes/problem01.json', 'tfrecords/x.tfrecords', 'cityscapes']
 
 
 def examples():
@@ -94,6 +103,26 @@ def main():
         'log_dir', 'results_dir', 'eval_res_dir', 'training_problem_def', 'inference_problem_def', 'evaluation_problem_def')}, sort_keys=True))
     out['calls'] = np.asarray(json.dumps([c for c in calls if c[0] == 'predict']))
     out['argv'] = np.asarray(json.dumps(ARGV_TAIL))
+    # ---- evaluate.py::main
+    import pickle
+    import evaluate as revaluate
+    del calls[:]
+    with tempfile.TemporaryDirectory() as tmp:
+      log_dir = os.path.join(tmp, 'log')
+      os.makedirs(log_dir)
+      with contextlib.redirect_stdout(io.StringIO()):
+        revaluate.main([log_dir] + EVAL_ARGV_TAIL)
+      res = os.path.join(log_dir, 'eval_00')
+      out['evaluate/files'] = np.asarray('\n'.join(sorted(os.listdir(res))))
+      with open(os.path.join(res, 'all_metrics.txt')) as fp:
+        out['evaluate/all_metrics_txt'] = np.asarray(fp.read())
+      with open(os.path.join(res, 'all_metrics.p'), 'rb') as fp:
+        pickled = pickle.load(fp)
+      out['evaluate/pickle_keys'] = np.asarray('\n'.join(sorted(pickled[0].keys())))
+      out['evaluate/pickle_len'] = np.asarray(len(pickled))
+      out['evaluate/pickle_cm'] = np.asarray(pickled[0]['confusion_matrix'])
+      out['evaluate/pickle_global_step'] = np.asarray(pickled[0]['global_step'])
+    out['evaluate/argv'] = np.asarray(json.dumps(EVAL_ARGV_TAIL))
     for i, ex in enumerate(examples()):
       out[f'example{i}/decisions'] = ex['decisions']
       out[f'example{i}/rawimages'] = ex['rawimages']

@@ -762,3 +762,37 @@ def test_predict_driver_and_exports_equal_the_reference_run(tmp_path):
     got = np.asarray(Image.open(str(results / n)))
     want = gold[f'png/{n}']
     assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), n
+
+
+def test_evaluate_script_outputs_equal_the_reference_run(tmp_path, monkeypatch):
+  """code/evaluate.py::main executed by the reference over a stub estimator (fixed 20 x 20 confusion matrix, step 1234):
+  the files it leaves in eval_00/ - `all_metrics.txt` (step + print_metrics_from_confusion_matrix through `printfile`,
+  utils/utils.py:385-446) character by character, and the pickled metrics list - against wlseg.cli.evaluate_main on the
+  same argv with the same fake estimator."""
+  import json
+  import pickle
+  from wlseg import cli, problem_defs
+  from wlseg import system_factory as sf
+  gold = np.load(os.path.join(os.path.dirname(TRAIN_GOLD), 'reference_predict_run.npz'))
+  argv = json.loads(str(gold['evaluate/argv']))
+  problem_defs.write_all()
+  argv[1] = problem_defs.default_path('cityscapes')
+  log_dir = tmp_path / 'log'
+  log_dir.mkdir()
+  calls = []
+
+  def fake_create(self, *a, **k):
+    self._estimator = _FakeEstimator(self, calls)
+  monkeypatch.setattr(sf.SemanticSegmentation, '_create_estimator', fake_create)
+  import contextlib
+  with contextlib.redirect_stdout(io.StringIO()):
+    cli.evaluate_main([str(log_dir)] + argv + ['--synthetic'])
+  res = log_dir / 'eval_00'
+  assert sorted(os.listdir(str(res))) == str(gold['evaluate/files']).split('\n')
+  assert (res / 'all_metrics.txt').read_text() == str(gold['evaluate/all_metrics_txt'])
+  with open(str(res / 'all_metrics.p'), 'rb') as fp:
+    pickled = pickle.load(fp)
+  assert len(pickled) == int(gold['evaluate/pickle_len'])
+  assert sorted(pickled[0].keys()) == str(gold['evaluate/pickle_keys']).split('\n')
+  assert pickled[0]['global_step'] == int(gold['evaluate/pickle_global_step'])
+  assert pickled[0]['confusion_matrix'].dtype == np.int32 and np.array_equal(pickled[0]['confusion_matrix'], gold['evaluate/pickle_cm'])
