@@ -66,7 +66,8 @@ def predict_input_fn(config, params):
         continue
       im = im.convert(mode='RGB')
     raw = torch.from_numpy(np.asarray(im, dtype=np.uint8).copy())                 # [H, W, 3]
-    img = raw.to(torch.float32) / 255.0                                           # tf.image.convert_image_dtype
+    # tf.image.convert_image_dtype [TF-1.12]: cast, then MULTIPLY by the float32 constant 1 / 255 (not a division)
+    img = raw.to(torch.float32) * torch.tensor(1.0 / 255.0, dtype=torch.float32)
     pro = (resize_bilinear_legacy(img, hf, wf) - 0.5) / 0.5                       # from_0_1_to_m1_1
     yield {'proimages': pro.unsqueeze(0).contiguous(), 'rawimages': raw.unsqueeze(0),
            'rawimagespaths': [fname.encode('utf-8')]}, None

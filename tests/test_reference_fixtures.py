@@ -796,3 +796,36 @@ def test_evaluate_script_outputs_equal_the_reference_run(tmp_path, monkeypatch):
   assert sorted(pickled[0].keys()) == str(gold['evaluate/pickle_keys']).split('\n')
   assert pickled[0]['global_step'] == int(gold['evaluate/pickle_global_step'])
   assert pickled[0]['confusion_matrix'].dtype == np.int32 and np.array_equal(pickled[0]['confusion_matrix'], gold['evaluate/pickle_cm'])
+
+
+def test_predict_input_equals_the_reference_pipeline_run(tmp_path):
+  """dataset_agnostic_predict_input.py: `_predict_image_generator` (:88-107) + `_predict_preprocess` (:109-119) run by the
+  reference on a small directory tree (RGB / grey / palette / RGBA, nested folders, upper-case extension, PPM, a
+  non-image file) vs wlseg.image_input.predict_input_fn on the same tree: the same set of files, raw RGB arrays bit-exact,
+  processed images (uint8 -> [0, 1] by the float32 constant 1 / 255 -> legacy bilinear resize -> [-1, 1)) bit-exact."""
+  import argparse
+  import contextlib
+  from wlseg import image_input
+  gen = importlib.import_module('tests.golden.make_reference_predict_input_fixtures')
+  gold = np.load(gen.OUT)
+  root = str(tmp_path / 'images')
+  os.makedirs(root)
+  gen.write_images(root)
+  hf, wf = (int(v) for v in gold['size'])
+  params = argparse.Namespace(predict_dir=root, height_feature_extractor=hf, width_feature_extractor=wf, Nb=1,
+                              preserve_aspect_ratio=False)
+  with contextlib.redirect_stdout(io.StringIO()):
+    batches = list(image_input.predict_input_fn(None, params))
+  seen = []
+  worst = 0.0
+  for features, labels in batches:
+    assert labels is None and sorted(features) == ['proimages', 'rawimages', 'rawimagespaths']
+    (path,) = features['rawimagespaths']
+    key = os.path.relpath(path.decode('utf-8'), root)
+    seen.append(key)
+    raw, pro = features['rawimages'], features['proimages']
+    assert raw.dtype == torch.uint8 and tuple(raw.shape[:1]) == (1,) and np.array_equal(raw[0].numpy(), gold[f'raw/{key}'])
+    assert pro.dtype == torch.float32 and tuple(pro.shape) == (1, hf, wf, 3)
+    worst = max(worst, float(np.abs(pro[0].numpy() - gold[f'pro/{key}']).max()))
+  assert sorted(seen) == str(gold['paths']).split('\n')
+  assert worst == 0.0, worst
