@@ -149,6 +149,11 @@ def test_schedules_and_momentum_equal_reference(gold):
   class P:
     learning_rate_schedule, learning_rate_boundaries, learning_rate_values = 'piecewise_constant', b, v
   assert [west.learning_rate(P, s) for s in steps] == gold['lr/piecewise'].tolist()
+
+  class Q:
+    learning_rate_schedule, learning_rate_initial, learning_rate_final = 'polynomial_decay', 0.01, 0.0001
+    learning_rate_power, num_training_steps = 0.9, 17 * 743
+  np.testing.assert_allclose([west.learning_rate(Q, s) for s in steps], gold['lr/polynomial'], rtol=1e-12)
   for name, nesterov in (('plain', False), ('nesterov', True)):
     w = torch.from_numpy(gold['sgdm/w0']).clone()
     acc = torch.zeros_like(w)
