@@ -47,7 +47,7 @@ def test_forward_bf16_matches_oracle(cuda, dataset, shape):
   assert emax <= 2e-2 and el2 <= 2e-2
   dis = float((out['decisions'].cpu() != ref['decisions']).float().mean())
   print(f'decision disagreement rate {dis:.4f}')
-  assert dis <= 0.05
+  assert dis <= 0.005   # measured 0.0000 / 0.0001 / 0.0014 on the three cases (near-ties of the random-init network)
   assert float((out['l1_probabilities'].cpu() - ref['l1_probabilities']).abs().max()) <= 5e-2
 
 
