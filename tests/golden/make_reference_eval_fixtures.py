@@ -42,6 +42,8 @@ EVAL_CASES = {
     'eval_cs_same_size': ('cityscapes', 2, 2, 40, 56, 40, 56),
     'eval_cs_labels_2x': ('cityscapes', 2, 1, 40, 56, 80, 112),
     'eval_vistas_labels_odd': ('vistas', 1, 1, 40, 56, 53, 75),
+    # --upsampling_method no: predictions stay at H/8 x W/8 and `_resize_predictions` carries them to the label size
+    'eval_cs_no_upsampling': ('cityscapes', 1, 2, 40, 56, 40, 56),
 }
 # tag -> (dataset, N, network H, W, (height_system, width_system), raw image size or None)
 PREDICT_CASES = {
@@ -96,6 +98,8 @@ def main():
     _train.reset()
     t2e = CITYSCAPES_TRAINING_CIDS2EVALUATION_CIDS if dataset == 'cityscapes' else VISTAS_TRAINING_CIDS2EVALUATION_CIDS
     params = _model_params(dataset, H, W, N)
+    if tag.endswith('no_upsampling'):
+      params.upsampling_method = 'no'
     params.training_cids2evaluation_cids = list(t2e)
     g = torch.Generator().manual_seed(SEED + len(tag))
     for b in range(nbatches):

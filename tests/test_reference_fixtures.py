@@ -605,7 +605,7 @@ def _eval_gen():
   return importlib.import_module('tests.golden.make_reference_eval_fixtures')
 
 
-@pytest.mark.parametrize('tag', ['eval_cs_same_size', 'eval_cs_labels_2x', 'eval_vistas_labels_odd'])
+@pytest.mark.parametrize('tag', ['eval_cs_same_size', 'eval_cs_labels_2x', 'eval_vistas_labels_odd', 'eval_cs_no_upsampling'])
 def test_oracle_eval_branch_equals_the_reference_run(eval_gold, tag):
   """define_estimator_hierarchical.py:160-201 run by the reference (inference-mode model(), cid map, nearest resize to
   the label size, streaming confusion matrix over the batches) vs the oracle's pieces composed in the same order:
@@ -618,7 +618,8 @@ def test_oracle_eval_branch_equals_the_reference_run(eval_gold, tag):
   lut = ometrics.replacevoids(t2e)
   num_classes = max(lut) + 1
   assert num_classes == int(eval_gold[f'{tag}/num_classes'])
-  net = onet.Net(gen.case_params(dataset), dataset, training=False)
+  # --upsampling_method no: the network's predictions stay at H/8 x W/8, the nearest resize carries them to the labels
+  net = onet.Net(gen.case_params(dataset), dataset, training=False, upsampling='no' if tag.endswith('no_upsampling') else 'bilinear')
   cm = np.zeros((num_classes, num_classes), dtype=np.int64)
   for b in range(nbatches):
     with torch.no_grad():
