@@ -31,12 +31,17 @@ OUT = os.path.join(HERE, 'reference_driver_run.json')
 TRAIN_CASES = {
     'train_cityscapes_defaults': ['cityscapes'],
     'train_vistas_defaults': ['vistas'],
+    'train_cityscapes_void_poly': ['cityscapes', '--train_void_class', '--learning_rate_schedule', 'polynomial_decay', '--Ne', '5',
+                                   '--Nb', '2', '--optimizer', 'SGD', '--use_nesterov', '--ema_decay', '0.99'],
     'train_cityscapes_flags': ['cityscapes', '--Ne', '30', '--learning_rate_initial', '0.02', '--learning_rate_boundaries', '10', '20', '30',
                                '--distribute', '--psp_module', '--save_checkpoints_steps', '500'],
 }
 EVAL_CASES = {
     'eval_cityscapes': (['500', 'problem_definitions/cityscapes/problem01.json', 'tfrecords/x.tfrecords', 'cityscapes'], 20),
     'eval_vistas': (['2000', 'problem_definitions/vistas/problem01.json', 'tfrecords/x.tfrecords', 'vistas', '--Nb', '2'], 66),
+    # --train_void_class: the void class is a trained class - the id map keeps it and the matrix is handed back untrimmed
+    'eval_cityscapes_train_void': (['500', 'problem_definitions/cityscapes/problem01.json', 'tfrecords/x.tfrecords', 'cityscapes',
+                                    '--train_void_class', '--restore_emas', '--Nb', '4'], 20),
 }
 
 

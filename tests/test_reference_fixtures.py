@@ -359,7 +359,8 @@ def _load_driver_gold():
     return json.load(fp)
 
 
-@pytest.mark.parametrize('tag', ['train_cityscapes_defaults', 'train_vistas_defaults', 'train_cityscapes_flags'])
+@pytest.mark.parametrize('tag', ['train_cityscapes_defaults', 'train_vistas_defaults', 'train_cityscapes_flags',
+                                 'train_cityscapes_void_poly'])
 def test_train_driver_settings_equal_the_reference_run(tag, tmp_path, monkeypatch):
   """wlseg.settings (CLI) + train_extra_args + wlseg.system_factory.SemanticSegmentation.__init__ / .train() on the argv
   the reference run was given: every attribute the REFERENCE left on `system.settings` (parsed flags with their defaults,
@@ -390,7 +391,7 @@ def test_train_driver_settings_equal_the_reference_run(tag, tmp_path, monkeypatc
   assert calls == [('train', want_steps[0])]
 
 
-@pytest.mark.parametrize('tag', ['eval_cityscapes', 'eval_vistas'])
+@pytest.mark.parametrize('tag', ['eval_cityscapes', 'eval_vistas', 'eval_cityscapes_train_void'])
 def test_evaluate_driver_settings_equal_the_reference_run(tag, tmp_path, monkeypatch):
   """The evaluation side of the same: evaluate.py's flags + overrides, derived step counts, the id map to evaluation
   classes, `eval_NN` directory naming, and the confusion matrix handed back for a given raw one (void row / column
