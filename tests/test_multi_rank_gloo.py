@@ -4,7 +4,9 @@
     the per-rank gradients (the MirroredStrategy semantics the reference trains with,
     code/system_factory.py:279-283), for ready-notifications in any order
   * evaluation sharded by image: per-rank integer confusion matrices summed == the single-rank
-    confusion matrix of all images, bit-exact (code/estimator/define_estimator_hierarchical.py:185-194)
+    confusion matrix of all images, bit-exact (code/estimator/define_estimator_hierarchical.py:185-194), through the
+    oracle's histogram and through the product's `SemanticSegmentation._reduce_across_ranks`; rank 0's precondition
+    verdict reaches every rank (`_any_rank`)
 """
 
 import os
@@ -56,6 +58,17 @@ def _worker(rank, world, port, q):
     t = torch.from_numpy(part.astype(np.int64))
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     ok_cm = bool(np.array_equal(t.numpy(), full))
+    # ---- the product's own N > 1 host logic: SemanticSegmentation._reduce_across_ranks and the collective verdict on
+    # rank 0's log-directory precondition (wlseg/system_factory.py)
+    import types
+    from wlseg import system_factory as sf
+    st = types.SimpleNamespace(world_size=world, device='cpu', rank=rank)
+    holder = types.SimpleNamespace(_settings=st, _estimator=types.SimpleNamespace(device='cpu'))
+    m = sf.SemanticSegmentation._reduce_across_ranks(
+        holder, {'confusion_matrix_int64': part.astype(np.int64).copy(), 'confusion_matrix': part.astype(np.int32), 'steps': 4})
+    ok_cm = ok_cm and bool(np.array_equal(m['confusion_matrix_int64'], full)) and m['confusion_matrix'].dtype == np.int32 \
+        and bool(np.array_equal(m['confusion_matrix'], full))
+    ok_cm = ok_cm and sf._any_rank(rank == 0, st) is True and sf._any_rank(False, st) is False
     q.put((rank, ok_grad, ok_cm))
   finally:
     dist.destroy_process_group()
