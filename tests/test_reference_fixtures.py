@@ -836,3 +836,19 @@ def test_predict_input_equals_the_reference_pipeline_run(tmp_path):
     worst = max(worst, float(np.abs(pro[0].numpy() - gold[f'pro/{key}']).max()))
   assert sorted(seen) == str(gold['paths']).split('\n')
   assert worst == 0.0, worst
+
+
+@pytest.mark.parametrize('dataset', ['cityscapes', 'vistas'])
+def test_regenerated_problem_definitions_equal_the_reference_files(dataset):
+  """wlseg/problem_defs.py regenerates code/problem_definitions/<dataset>/problem01.json from the public label tables;
+  every field except the free-text `comments` has the SHA-256 of the reference's value
+  (tests/golden/make_problem_def_digests.py)."""
+  import json
+  from wlseg import problem_defs
+  gen = importlib.import_module('tests.golden.make_problem_def_digests')
+  with open(gen.OUT) as fp:
+    want = json.load(fp)[dataset]
+  mine = problem_defs.GENERATORS[dataset]()
+  assert sorted(k for k in mine if k != 'comments') == sorted(want)
+  for k, d in want.items():
+    assert gen.digest(mine[k]) == d, f'{dataset}: field {k} differs from the reference file'
