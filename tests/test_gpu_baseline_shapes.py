@@ -207,3 +207,33 @@ def test_batch_mean_iou_product_function_on_device_path(cuda):
   # known answer on a hand-made matrix: IoUs 1/2, 1/3, 0 (union 1), 0 (union 0 -> 0 / 1e-9) -> mean over ALL 4 classes
   cm4 = np.array([[1, 1, 0, 0], [0, 1, 0, 0], [0, 1, 0, 0], [0, 0, 0, 0]])
   assert abs(estimator.mean_iou_from_cm(cm4, 4) - (0.5 + 1 / 3) / 4) < 1e-6
+
+
+def test_predict_config0_512x1024_matches_oracle(cuda):
+  """BASELINE configs[0] - the reference's own CPU-runnable case: predict.py's forward, batch 1, one 512 x 1024
+  Cityscapes-shaped image, random init - on the bf16 product path against the fp32 CPU oracle on the same input and
+  weights: the keys predict.py requests (decisions, l1 and l2_vehicle probability maps at full resolution).
+  Low-res logits rel-L2 <= 2e-2 (measured 7-9e-3 at every other shape); decisions: disagreement <= 2 % (Cityscapes heads
+  measure <= 0.15 %); probability maps: mean absolute difference <= 1e-2."""
+  from wlseg import network
+  H, W = 512, 1024
+  hier, tf_params, params = _setup(cuda, 'cityscapes', seed=22)
+  net = network.Network(params, dtype=torch.bfloat16)
+  g = torch.Generator().manual_seed(H + W)
+  images = torch.rand(1, H, W, 3, generator=g) * 2 - 1
+  out = net.predict(images.to(cuda), want=('decisions', 'l1_probabilities', 'l2_vehicle_probabilities'))
+  torch.cuda.synchronize()
+  with torch.no_grad():
+    ref = onet.Net(tf_params, 'cityscapes').forward(images)
+  ref_low = torch.cat(ref['lowres_logits'], -1)
+  got_low = out['lowres_logits'][..., :hier.total_channels].cpu()
+  emax, el2 = _errors(got_low, ref_low)
+  decs = out['decisions'].cpu()
+  assert tuple(decs.shape) == (1, H, W) and decs.dtype == torch.int32
+  dis = float((decs != ref['decisions']).float().mean())
+  dp1 = float((out['l1_probabilities'].cpu() - ref['l1_probabilities']).abs().mean())
+  dpv = float((out['l2_vehicle_probabilities'].cpu() - ref['l2_vehicle_probabilities']).abs().mean())
+  print(f'configs[0] 1x{H}x{W}: low-res logits max-rel {emax:.3e} rel-L2 {el2:.3e}; decision disagreement {dis:.4f}; '
+        f'mean |dp| l1 {dp1:.2e} l2_vehicle {dpv:.2e}')
+  assert tuple(out['l1_probabilities'].shape) == (1, H, W, 14) and tuple(out['l2_vehicle_probabilities'].shape) == (1, H, W, 7)
+  assert el2 <= 2e-2 and dis <= 2e-2 and dp1 <= 1e-2 and dpv <= 1e-2
