@@ -39,6 +39,10 @@ CASES = {
                           {'psp_module': True, 'fov_expansion_kernel_size': 3, 'fov_expansion_kernel_rate': 2,
                            'upsampling_method': 'hybrid'}),
     'cs_group': ('cityscapes', 2, 40, 56, False, False, {'norm': 'group'}, {'norm_layer': 'group'}),
+    # sizes that are no multiple of 8 - the shape class of train.py's Vistas default 621 x 855 (621 = 5, 855 = 7 mod 8):
+    # asymmetric SAME padding, pooling on odd maps, ceil-divided feature maps, x8 upsampling to an odd size
+    'vistas_odd_size': ('vistas', 1, 45, 63, False, False, {}, {}),
+    'cs_odd_size_train_bn': ('cityscapes', 2, 37, 51, True, True, {}, {}),
 }
 SEED = 11
 LOGIT_STRIDE = 3

@@ -204,7 +204,7 @@ def test_resize_and_crop_equals_reference(gold, tag):
 # ------------------------------------------------------------------------------------------------ the network
 # tests/golden/reference_model_run.npz: the reference's own model() executed over tests/golden/tf_shim (+ _slim.py)
 MODEL_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_model_run.npz')
-MODEL_CASES = ['cs_eval', 'cs_train_bn', 'vistas_eval', 'cs_psp_fov_hybrid', 'cs_group']
+MODEL_CASES = ['cs_eval', 'cs_train_bn', 'vistas_eval', 'cs_psp_fov_hybrid', 'cs_group', 'vistas_odd_size', 'cs_odd_size_train_bn']
 
 
 @pytest.fixture(scope='module')
@@ -240,7 +240,7 @@ def test_oracle_network_equals_the_reference_model_run(model_gold, tag):
   # inference-mode normalisation: 1e-5 and identical decisions.  Normalising by the statistics of the tensor itself
   # (training-mode batch norm over 2 x 5 x 7 positions, group norm per sample) amplifies the last-bit differences of
   # two fp32 evaluation orders layer after layer: 1e-3, and decisions may differ where two logits tie to that level
-  exact = tag not in ('cs_train_bn', 'cs_group')
+  exact = tag not in ('cs_train_bn', 'cs_group', 'cs_odd_size_train_bn')
   tol = 1e-5 if exact else 1e-3
   worst = 0.0
   for k in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits'):
