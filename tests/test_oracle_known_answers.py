@@ -291,3 +291,28 @@ def test_new_oracle_ops_against_independent_formulations():
   xr = torch.tensor([[[[0.0], [4.0]], [[8.0], [12.0]]]])
   got = tfops.resize_bilinear(xr, 3, 3, align_corners=True)[0, :, :, 0]
   assert got.tolist() == [[0.0, 2.0, 4.0], [4.0, 6.0, 8.0], [8.0, 10.0, 12.0]]
+
+
+def test_product_convolution_geometry_equals_the_oracle_padding_rules():
+  """wlseg/arch.py::same_pad_before (leading zero padding + output size of every slim convolution: TF 'SAME' for
+  stride 1 and for 1x1 kernels, resnet_utils.conv2d_same's explicit padding for strided k > 1) against the oracle's
+  tfops.same_pad / conv2d_same arithmetic - which the reference's model() run pins at sizes that are no multiple of 8
+  (tests/golden/reference_model_run.npz: vistas_odd_size, cs_odd_size_train_bn) - for every size 1..80."""
+  import torch
+  from oracle import tfops
+  from wlseg import arch
+  for size in range(1, 81):
+    for k in (1, 3, 7):
+      for stride in (1, 2):
+        for rate in (1, 2, 4):
+          if stride > 1 and rate > 1:
+            continue          # never combined: a strided unit past the target stride runs at stride 1 with a rate
+          before, out = arch.same_pad_before(k, stride, rate, size)
+          if stride == 1 or k == 1:
+            want_before, _, want_out = tfops.same_pad(size, k, stride, rate)
+          else:
+            k_eff = k + (k - 1) * (rate - 1)
+            want_before = (k_eff - 1) // 2
+            x = torch.zeros(1, size, size, 1)
+            want_out = tfops.conv2d_same(x, torch.zeros(k, k, 1, 1), stride, rate).shape[1]
+          assert (before, out) == (want_before, want_out), (size, k, stride, rate)
