@@ -1,0 +1,143 @@
+"""The product's HOST orchestration of the inference path (wlseg/network.py: which layer runs with which geometry, pad,
+stride, dilation, residual and residual stride, folded batch-norm constants, the adaptation-unit GEMM merge, the packed
+root convolution of the bf16 path, the logits buffer layout, the head call) executed on CPU, with the handful of C-ABI
+entry points it launches replaced by torch restatements of their contracts in include/wlseg.h:
+
+  wlseg_conv2d_fprop    y = [relu]( conv(x, w; stride, dilation, pad_top / pad_left, P x Q outputs) * scale + shift
+                            + residual[::res_stride] )
+  wlseg_maxpool_same_*  TF 'SAME' max pooling
+  wlseg_conv1_pack      space-to-depth(2) of the image with the 4 horizontal taps unrolled -> 64 channels
+  wlseg_head_fwd        align-corners bilinear x8 + softmax / arg-max x3 + decision composition
+  wlseg_cast_f32_to_bf16
+
+Compared with the predictions the REFERENCE's model() returned (tests/golden/reference_model_run.npz), in particular at
+sizes that are no multiple of 8 (the shape class of train.py's Vistas default 621 x 855), which no GPU test covers end to
+end.  This checks Python, not kernels: the kernels' own parity is the business of the `-m gpu` tests.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import network as onet
+from oracle import tfops
+
+
+def _emulated_ops(monkeypatch):
+  from wlseg import ops
+
+  def cast_f32_to_bf16(src, dst):
+    dst.copy_(src.to(torch.bfloat16))
+    return dst
+
+  def conv2d_fprop(p, x, w, y, scale=None, shift=None, residual=None, bn_sum=None, bn_sqsum=None):
+    assert bn_sum is None and bn_sqsum is None
+    assert tuple(x.shape) == (p.N, p.H, p.W, p.C) and tuple(w.shape) == (p.K, p.R, p.S, p.C) and tuple(y.shape) == (p.N, p.P, p.Q, p.K)
+    xn = x.float().permute(0, 3, 1, 2)
+    need_h = (p.P - 1) * p.stride + (p.R - 1) * p.dilation + 1
+    need_w = (p.Q - 1) * p.stride + (p.S - 1) * p.dilation + 1
+    xn = F.pad(xn, (p.pad_left, max(need_w - p.W - p.pad_left, 0), p.pad_top, max(need_h - p.H - p.pad_top, 0)))
+    out = F.conv2d(xn[:, :, :need_h, :need_w], w.float().permute(0, 3, 1, 2), stride=p.stride, dilation=p.dilation)
+    out = out.permute(0, 2, 3, 1)
+    assert tuple(out.shape) == tuple(y.shape), (tuple(out.shape), tuple(y.shape))
+    if scale is not None:
+      out = out * scale[:p.K].float() + shift[:p.K].float()
+    if residual is not None:
+      rs = p.res_stride
+      assert tuple(residual.shape[1:3]) == (p.res_H, p.res_W)
+      out = out + residual.float()[:, ::rs, ::rs, :][:, :p.P, :p.Q, :]
+    if p.relu:
+      out = torch.relu(out)
+    y.copy_(out.to(y.dtype))
+    return y
+
+  def maxpool_same_fwd(x, y, ksize, stride, argmax=None):
+    assert argmax is None
+    y.copy_(tfops.max_pool_same(x.float(), ksize, stride).to(y.dtype))
+    return y
+
+  def conv1_pack(img, out):
+    # channel = b * 16 + slot; slot = (ii * 2 + jj) * 3 + c for slot < 12, zero above; b = horizontal tap;
+    # source pixel (2 y + ii, 2 (x - 2 + b) + jj), zero outside the image (csrc/transform.cu)
+    N, H, W, _ = img.shape
+    Hs, Ws = out.shape[1], out.shape[2]
+    assert (Hs, Ws) == ((H + 1) // 2, (W + 1) // 2)
+    pad = torch.zeros(N, 2 * Hs + 2, 2 * (Ws + 4), 3)
+    pad[:, :H, 4:4 + W] = img.float()                     # column offset 4 = two packed pixels to the left
+    res = torch.zeros(N, Hs, Ws, 64)
+    for b in range(4):
+      for ii in range(2):
+        for jj in range(2):
+          for c in range(3):
+            col0 = 4 + 2 * (b - 2) + jj
+            res[..., b * 16 + (ii * 2 + jj) * 3 + c] = pad[:, ii:ii + 2 * Hs:2, col0:col0 + 2 * Ws:2, c]
+    out.copy_(res.to(out.dtype))
+    return out
+
+  def head_fwd(hier, logits, H, W, decisions=None, l1_decisions=None, l2v_decisions=None, l2h_decisions=None,
+               l1_probs=None, l2v_probs=None, l2h_probs=None, fullres_logits=None):
+    c1, cv, ch = head_fwd.widths
+    low = [logits[..., :c1], logits[..., c1:c1 + cv], logits[..., c1 + cv:c1 + cv + ch]]
+    if (H, W) != tuple(logits.shape[1:3]):
+      low = [tfops.resize_bilinear(z, H, W, align_corners=True) for z in low]
+    pred = onet.compose_predictions(*low, head_fwd.dataset)
+    for buf, key in ((decisions, 'decisions'), (l1_decisions, 'l1_decisions'), (l2v_decisions, 'l2_vehicle_decisions'),
+                     (l2h_decisions, 'l2_human_decisions'), (l1_probs, 'l1_probabilities'),
+                     (l2v_probs, 'l2_vehicle_probabilities'), (l2h_probs, 'l2_human_probabilities')):
+      if buf is not None:
+        buf.copy_(pred[key].to(buf.dtype))
+    if fullres_logits is not None:
+      fullres_logits.copy_(torch.cat(low, -1))
+
+  for name, fn in (('cast_f32_to_bf16', cast_f32_to_bf16), ('conv2d_fprop', conv2d_fprop), ('maxpool_same_fwd', maxpool_same_fwd),
+                   ('conv1_pack', conv1_pack), ('head_fwd', head_fwd)):
+    monkeypatch.setattr(ops, name, fn)
+  return head_fwd
+
+
+def _reference_case(tag):
+  import importlib.util
+  here = os.path.dirname(os.path.abspath(__file__))
+  spec = importlib.util.spec_from_file_location('make_reference_model_fixtures', os.path.join(here, 'golden', 'make_reference_model_fixtures.py'))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)
+  gold = np.load(os.path.join(here, 'golden', 'reference_model_run.npz'))
+  return gen, gold
+
+
+@pytest.mark.parametrize('tag', ['cs_eval', 'vistas_eval', 'vistas_odd_size'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_inference_orchestration_reproduces_the_reference_model_run(monkeypatch, tag, dtype):
+  """fp32: the direct-convolution wiring, logits 1e-5 of their maximum and every decision map equal to the reference's.
+  bf16: the product path's wiring (packed root convolution, bf16 operand arena and activations, every layer's output
+  rounded to bf16 by the emulation) - logits within 4e-2 of their maximum (measured 0.9-1.9e-2), decisions 3 %."""
+  from wlseg import hierarchy, network, problem_defs
+  head = _emulated_ops(monkeypatch)
+  gen, gold = _reference_case(tag)
+  dataset, N, H, W, train, accumulate, init_kw, flags = gen.CASES[tag]
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  head.widths, head.dataset = hier.head_widths, dataset
+  params = network.Params(hier, 'cpu')
+  params.load_tf_dict(gen.case_params(tag))
+  net = network.Network(params, dtype=dtype)
+  images = torch.from_numpy(gold[f'{tag}/images'])
+  keys = ('decisions', 'l1_decisions', 'l2_vehicle_decisions', 'l2_human_decisions', 'l1_logits')
+  out = net.predict(images, want=keys)
+  h, w = (H + 7) // 8, (W + 7) // 8
+  assert tuple(out['lowres_logits'].shape[:3]) == (N, h, w)
+  s = gen.LOGIT_STRIDE
+  worst = 0.0
+  for k in ('l1_logits', 'l2_vehicle_logits', 'l2_human_logits'):
+    want = torch.from_numpy(gold[f'{tag}/{k}'])
+    got = out[k][:, ::s, ::s]
+    assert got.shape == want.shape
+    worst = max(worst, float((got - want).abs().max()) / float(want.abs().max()))
+  mism = max(float((out[k] != torch.from_numpy(gold[f'{tag}/{k}'].astype(np.int32))).float().mean()) for k in keys[:4])
+  print(f'{tag} {dtype}: worst logits error {worst:.2e} of the maximum, decisions differing {mism:.4f}')
+  if dtype == torch.float32:
+    assert worst <= 1e-5 and mism == 0.0
+  else:
+    assert worst <= 4e-2 and mism <= 3e-2
