@@ -141,3 +141,45 @@ def test_inference_orchestration_reproduces_the_reference_model_run(monkeypatch,
     assert worst <= 1e-5 and mism == 0.0
   else:
     assert worst <= 4e-2 and mism <= 3e-2
+
+
+@pytest.mark.parametrize('tag', ['predict_cs_system_size', 'predict_cs_raw_size'])
+def test_estimator_predict_orchestration_reproduces_the_reference_predict_run(monkeypatch, tag):
+  """Estimator.predict's host logic (requested keys, output size from --height_system / --width_system or from the raw
+  image, per-example splitting, raw images / paths passed through) on CPU over the emulated calls (+ the two resize
+  entry points) against the reference's own PREDICT run (tests/golden/reference_eval_run.npz), fp32 wiring."""
+  import argparse
+  import importlib
+  from wlseg import estimator as est, hierarchy, network, ops, problem_defs
+  head = _emulated_ops(monkeypatch)
+
+  def resize_probabilities(probs, H, W):
+    return probs if tuple(probs.shape[1:3]) == (H, W) else tfops.resize_bilinear(probs, H, W, align_corners=True)
+
+  def resize_decisions(decs, H, W):
+    return decs if tuple(decs.shape[1:3]) == (H, W) else tfops.resize_nearest(decs[..., None], H, W, align_corners=True)[..., 0]
+  monkeypatch.setattr(ops, 'resize_probabilities', resize_probabilities)
+  monkeypatch.setattr(ops, 'resize_decisions', resize_decisions)
+  gen = importlib.import_module('tests.golden.make_reference_eval_fixtures')
+  gold = np.load(gen.OUT)
+  dataset, N, H, W, system, raw = gen.PREDICT_CASES[tag]
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  head.widths, head.dataset = hier.head_widths, dataset
+  s = argparse.Namespace(dtype='fp32', stride_feature_extractor=8, psp_module=False, height_system=system[0],
+                         width_system=system[1], replace_voids=False, batch_norm_decay=1.0)
+  e = est.Estimator(s, hier, device='cpu')
+  e.params.load_tf_dict(gen.case_params(dataset))
+  e.net = network.Network(e.params, dtype=torch.float32)
+  features = {'proimages': torch.from_numpy(gold[f'{tag}/images'])}
+  keys = ['decisions', *gen.PROB_KEYS]
+  if raw is not None:
+    features['rawimages'] = torch.zeros(N, raw[0], raw[1], 3, dtype=torch.uint8)
+    features['rawimagespaths'] = ['a.png'] * N
+    keys += ['rawimages', 'rawimagespaths']
+  outs = list(e.predict([(features, None)], keys))
+  assert len(outs) == N and sorted(outs[0].keys()) == str(gold[f'{tag}/prediction_keys']).split('\n')
+  oh, ow = (int(v) for v in gold[f'{tag}/size'])
+  for i, ex in enumerate(outs):
+    assert ex['decisions'].shape == (oh, ow) and np.array_equal(ex['decisions'], gold[f'{tag}/decisions'][i])
+    for k in gen.PROB_KEYS:
+      assert np.abs(ex[k][::gen.PROB_STRIDE, ::gen.PROB_STRIDE] - gold[f'{tag}/{k}'][i]).max() <= 1e-5, k
