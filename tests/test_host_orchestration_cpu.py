@@ -8,7 +8,7 @@ entry points it launches replaced by torch restatements of their contracts in in
   wlseg_maxpool_same_*  TF 'SAME' max pooling
   wlseg_conv1_pack      space-to-depth(2) of the image with the 4 horizontal taps unrolled -> 64 channels
   wlseg_head_fwd        align-corners bilinear x8 + softmax / arg-max x3 + decision composition
-  wlseg_cast_f32_to_bf16
+  wlseg_cast_f32_to_bf16, and for --psp_module wlseg_avgpool_valid_fwd / wlseg_resize_bilinear_fwd
 
 Compared with the predictions the REFERENCE's model() returned (tests/golden/reference_model_run.npz), in particular at
 sizes that are no multiple of 8 (the shape class of train.py's Vistas default 621 x 855), which no GPU test covers end to
@@ -92,8 +92,17 @@ def _emulated_ops(monkeypatch):
     if fullres_logits is not None:
       fullres_logits.copy_(torch.cat(low, -1))
 
+  def avgpool_valid_fwd(x, y, kh, kw):           # --psp_module: VALID average pooling, stride == kernel
+    y.copy_(tfops.avg_pool_valid(x.float(), (kh, kw), (kh, kw)).to(y.dtype))
+    return y
+
+  def resize_bilinear_fwd(x, y):                 # --psp_module: align-corners resize into a channel slice
+    y.copy_(tfops.resize_bilinear(x.float(), y.shape[1], y.shape[2], align_corners=True).to(y.dtype))
+    return y
+
   for name, fn in (('cast_f32_to_bf16', cast_f32_to_bf16), ('conv2d_fprop', conv2d_fprop), ('maxpool_same_fwd', maxpool_same_fwd),
-                   ('conv1_pack', conv1_pack), ('head_fwd', head_fwd)):
+                   ('conv1_pack', conv1_pack), ('head_fwd', head_fwd), ('avgpool_valid_fwd', avgpool_valid_fwd),
+                   ('resize_bilinear_fwd', resize_bilinear_fwd)):
     monkeypatch.setattr(ops, name, fn)
   return head_fwd
 
@@ -108,7 +117,7 @@ def _reference_case(tag):
   return gen, gold
 
 
-@pytest.mark.parametrize('tag', ['cs_eval', 'vistas_eval', 'vistas_odd_size'])
+@pytest.mark.parametrize('tag', ['cs_eval', 'vistas_eval', 'vistas_odd_size', 'cs_psp_fov_hybrid'])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_inference_orchestration_reproduces_the_reference_model_run(monkeypatch, tag, dtype):
   """fp32: the direct-convolution wiring, logits 1e-5 of their maximum and every decision map equal to the reference's.
@@ -120,7 +129,7 @@ def test_inference_orchestration_reproduces_the_reference_model_run(monkeypatch,
   dataset, N, H, W, train, accumulate, init_kw, flags = gen.CASES[tag]
   hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
   head.widths, head.dataset = hier.head_widths, dataset
-  params = network.Params(hier, 'cpu')
+  params = network.Params(hier, 'cpu', **init_kw)       # psp / fov / upsampling of the case
   params.load_tf_dict(gen.case_params(tag))
   net = network.Network(params, dtype=dtype)
   images = torch.from_numpy(gold[f'{tag}/images'])
