@@ -69,6 +69,12 @@ CASES = {
                                model=({'psp': True, 'fov': (3, 2), 'upsampling': 'hybrid'},
                                       {'psp_module': True, 'fov_expansion_kernel_size': 3, 'fov_expansion_kernel_rate': 2,
                                        'upsampling_method': 'hybrid'}))),
+    # sizes that are no multiple of 8 (the shape class of train.py's Vistas default 621 x 855): asymmetric SAME padding,
+    # the strided unit and both pooling layers on odd maps, and their gradients
+    'cs_odd_size_momentum': ('cityscapes', 1, 1, 0, 37, 51, 2,
+                             dict(learning_rate_schedule='piecewise_constant', learning_rate_boundaries=[50],
+                                  learning_rate_values=[0.01, 0.005], optimizer='SGDM', momentum=0.9, use_nesterov=False,
+                                  ema_decay=0.0, regularization_weight=0.00017, batch_norm_decay=0.9)),
     'cs_group_norm': ('cityscapes', 1, 1, 0, 40, 56, 2,
                       dict(learning_rate_schedule='piecewise_constant', learning_rate_boundaries=[50],
                            learning_rate_values=[0.01, 0.005], optimizer='SGD', momentum=0.9, use_nesterov=False,
@@ -110,8 +116,8 @@ def case_batches(tag, ib=None):
   batches = []
   for _ in range(steps):
     images = torch.rand(n_pp + n_pb + n_pi, H, W, 3, generator=g) * 2 - 1
-    blocks = torch.randint(0, ncls, (n_pp, H // 8, W // 8), generator=g, dtype=torch.int32)
-    per_pixel = blocks.repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
+    blocks = torch.randint(0, ncls, (n_pp, -(-H // 8), -(-W // 8)), generator=g, dtype=torch.int32)
+    per_pixel = blocks.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :H, :W].contiguous()
     boxes = []
     for _ in range(n_pb):
       n = int(rng.integers(2, 6))

@@ -192,3 +192,212 @@ def test_estimator_predict_orchestration_reproduces_the_reference_predict_run(mo
     assert ex['decisions'].shape == (oh, ow) and np.array_equal(ex['decisions'], gold[f'{tag}/decisions'][i])
     for k in gen.PROB_KEYS:
       assert np.abs(ex[k][::gen.PROB_STRIDE, ::gen.PROB_STRIDE] - gold[f'{tag}/{k}'][i]).max() <= 1e-5, k
+
+
+# ================================================================================================ training
+def _emulated_training_ops(monkeypatch, hier, dataset):
+  """The calls of the fp32 (check-mode) TRAINING wiring, each restated from its contract in include/wlseg.h."""
+  from oracle import losses as olosses
+  from wlseg import ops
+  _emulated_ops(monkeypatch)
+
+  def rows(t, C):
+    return t.reshape(-1, t.shape[-1])[:, :C]
+
+  def conv_geometry(p):
+    need_h = (p.P - 1) * p.stride + (p.R - 1) * p.dilation + 1
+    need_w = (p.Q - 1) * p.stride + (p.S - 1) * p.dilation + 1
+    return need_h, need_w, max(need_h - p.H - p.pad_top, 0), max(need_w - p.W - p.pad_left, 0)
+
+  def bn_stats(z, count, C, pitch, sum_, sqsum):
+    r = rows(z, C).double()
+    assert r.shape[0] == count
+    sum_ += r.sum(0)
+    sqsum += (r * r).sum(0)
+
+  def bn_finalize(sum_, sqsum, count, C, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, saved_mean,
+                  saved_invstd, moving_var_factor=-1.0):
+    mean = sum_[:C] / count
+    var = sqsum[:C] / count - mean * mean
+    invstd = torch.rsqrt(var + eps)
+    scale.copy_((gamma.double() * invstd).float())
+    shift.copy_((beta.double() - mean * gamma.double() * invstd).float())
+    saved_mean.copy_(mean.float())
+    saved_invstd.copy_(invstd.float())
+    if moving_mean is not None:
+      factor = count / (count - 1.0) if moving_var_factor < 0 else moving_var_factor
+      moving_mean.sub_((1.0 - decay) * (moving_mean - mean.float()))
+      moving_var.sub_((1.0 - decay) * (moving_var - (var * factor).float()))
+
+  def bn_apply(z, scale, shift, residual, y, count, C, relu, mask=None):
+    assert mask is None
+    out = z.float() * scale[:C] + shift[:C]
+    if residual is not None:
+      out = out + residual.float()
+    y.copy_((torch.relu(out) if relu else out).to(y.dtype))
+    return y
+
+  def masked_gradient(dy, y, z, scale, shift, relu, C):
+    g = dy.float()
+    if relu:
+      live = (y.float() > 0) if y is not None else (torch.addcmul(shift[:C], z.float(), scale[:C]) > 0)
+      g = g * live
+    return g
+
+  def bn_bwd_reduce(dy, y, z, mean, invstd, count, C, relu, dgamma, dbeta, scale=None, shift=None, pitch=None):
+    g = masked_gradient(dy, y, z, scale, shift, relu, C)
+    zhat = (z.float() - mean[:C]) * invstd[:C]
+    dbeta += rows(g, C).double().sum(0)
+    dgamma += rows(g * zhat, C).double().sum(0)
+
+  def bn_bwd_apply(dy, y, z, mean, invstd, gamma, dgamma, dbeta, count, C, relu, dz, dres=None, scale=None, shift=None,
+                   pitch=None, stat_count=None):
+    n = count if stat_count is None else stat_count
+    g = masked_gradient(dy, y, z, scale, shift, relu, C)
+    zhat = (z.float() - mean[:C]) * invstd[:C]
+    dz.copy_((gamma[:C] * invstd[:C] * (g - (dbeta[:C] / n).float() - zhat * (dgamma[:C] / n).float())).to(dz.dtype))
+    if dres is not None:
+      dres.copy_(g.to(dres.dtype))
+    return dz
+
+  def conv2d_wgrad(p, x, dy, dw):
+    need_h, need_w, pb, pr = conv_geometry(p)
+    xn = F.pad(x.float().permute(0, 3, 1, 2), (p.pad_left, pr, p.pad_top, pb))[:, :, :need_h, :need_w]
+    g = torch.nn.grad.conv2d_weight(xn, (p.K, p.C, p.R, p.S), dy.float().permute(0, 3, 1, 2)[:, :p.K], stride=p.stride,
+                                    padding=0, dilation=p.dilation).permute(0, 2, 3, 1)
+    if p.accumulate:
+      dw += g
+    else:
+      dw.copy_(g)
+
+  def conv2d_dgrad(p, dy, w, dx):
+    need_h, need_w, pb, pr = conv_geometry(p)
+    full = torch.nn.grad.conv2d_input((p.N, p.C, need_h, need_w), w.float().permute(0, 3, 1, 2),
+                                      dy.float().permute(0, 3, 1, 2)[:, :p.K], stride=p.stride, padding=0, dilation=p.dilation)
+    full = F.pad(full, (0, max(p.pad_left + p.W - need_w, 0), 0, max(p.pad_top + p.H - need_h, 0)))
+    dx.copy_(full[:, :, p.pad_top:p.pad_top + p.H, p.pad_left:p.pad_left + p.W].permute(0, 2, 3, 1).to(dx.dtype))
+    return dx
+
+  def add_inplace(dst, src):
+    dst += src
+    return dst
+
+  def pool_windows(x, k, stride):
+    N, H, W, C = x.shape
+    pt, pb, P = tfops.same_pad(H, k, stride)
+    pl, pr, Q = tfops.same_pad(W, k, stride)
+    xn = F.pad(x.float().permute(0, 3, 1, 2), (pl, pr, pt, pb), value=float('-inf'))
+    win = xn.unfold(2, k, stride).unfold(3, k, stride)            # [N, C, P, Q, k, k]
+    return win.reshape(N, C, P, Q, k * k), (pt, pl, P, Q)
+
+  def maxpool_same_fwd(x, y, ksize, stride, argmax=None):
+    win, _ = pool_windows(x, ksize, stride)
+    best = win.max(-1).values
+    y.copy_(best.permute(0, 2, 3, 1).to(y.dtype))
+    if argmax is not None:      # first maximum in row-major scan order
+      argmax.copy_((win == best[..., None]).float().argmax(-1).permute(0, 2, 3, 1).to(torch.uint8))
+    return y
+
+  def maxpool_same_bwd(x, dy, dx, ksize, stride, argmax=None):
+    N, H, W, C = dx.shape
+    pt, _, P = tfops.same_pad(H, ksize, stride)
+    pl, _, Q = tfops.same_pad(W, ksize, stride)
+    if argmax is None:
+      win, _ = pool_windows(x, ksize, stride)
+      argmax = (win == win.max(-1).values[..., None]).float().argmax(-1).permute(0, 2, 3, 1)
+    am = argmax.long()
+    out = torch.zeros(N, H + 2 * ksize, W + 2 * ksize, C)
+    pp = torch.arange(P).view(1, P, 1, 1) * stride - pt + am // ksize + ksize
+    qq = torch.arange(Q).view(1, 1, Q, 1) * stride - pl + am % ksize + ksize
+    nn_ = torch.arange(N).view(N, 1, 1, 1).expand_as(am)
+    cc = torch.arange(C).view(1, 1, 1, C).expand_as(am)
+    out.index_put_((nn_, pp.expand_as(am), qq.expand_as(am), cc), dy.float(), accumulate=True)
+    dx.copy_(out[:, ksize:ksize + H, ksize:ksize + W].to(dx.dtype))
+    return dx
+
+  c1, cv, ch = hier.head_widths
+  state = {}
+
+  def loss_fwd_bwd(hstruct, logits, H, W, strong_labels, bbox_labels, image_labels, sums, counts, dlogits):
+    low = [logits[..., :c1].clone().requires_grad_(True), logits[..., c1:c1 + cv].clone().requires_grad_(True),
+           logits[..., c1 + cv:c1 + cv + ch].clone().requires_grad_(True)]
+    full = [tfops.resize_bilinear(z, H, W, align_corners=True) for z in low]
+    pred = onet.compose_predictions(*full, dataset)
+    labels = {'prolabels_per_pixel': strong_labels}
+    if bbox_labels is not None:
+      labels['prolabels_per_bbox'] = bbox_labels
+    if image_labels is not None:
+      labels['prolabels_per_image'] = image_labels
+    got = olosses.define_losses(pred, labels, dataset)
+    n = [float(got['counts'][k]) for k in ('l1', 'l2_vehicle', 'l2_human')]
+    heads = [got['l1_segmentation'], got['l2_vehicle_segmentation'], got['l2_human_segmentation']]
+    off = 0
+    for i, (z, c) in enumerate(zip(low, (c1, cv, ch))):
+      total = heads[i] * n[i]                     # sum(ce * w): the UNNORMALISED sum the kernel accumulates
+      sums[i] += float(total.detach())
+      counts[i] += n[i]
+      if n[i] > 0:
+        dlogits[..., off:off + c] += torch.autograd.grad(total, z, retain_graph=True)[0]
+      off += c
+
+  def loss_finalize(hstruct, sums, counts, l2_coef, grad_scale, dlogits, losses):
+    per = [float(sums[i] / counts[i]) if float(counts[i]) > 0 else 0.0 for i in range(3)]
+    losses.copy_(torch.tensor(per + [per[0] + l2_coef * (per[1] + per[2])]))
+    off = 0
+    for i, (c, coef) in enumerate(zip((c1, cv, ch), (1.0, l2_coef, l2_coef))):
+      dlogits[..., off:off + c] *= (grad_scale * coef / float(counts[i])) if float(counts[i]) > 0 else 0.0
+      off += c
+
+  def sgdm_step(w, g, acc, w_bf16, n_decay, lr_dev, momentum, nesterov, wd, grad_scale=1.0, reg_loss=None):
+    lr = float(lr_dev)
+    if reg_loss is not None:
+      reg_loss += 0.5 * wd * float((w[:n_decay].double() ** 2).sum())
+    gp = g * grad_scale
+    gp[:n_decay] += wd * w[:n_decay]
+    acc.mul_(momentum).add_(gp)
+    w.sub_(lr * (gp + momentum * acc) if nesterov else lr * acc)
+    if w_bf16 is not None:
+      w_bf16.copy_(w.to(torch.bfloat16))
+
+  def ema_update(biased, shadow, w, decay, inv_correction):
+    biased.sub_((1.0 - decay) * (biased - w))
+    if shadow is not biased:
+      shadow.copy_(biased * inv_correction)
+
+  for name, fn in list(locals().items()):
+    if callable(fn) and hasattr(ops, name) and name not in ('rows',):
+      monkeypatch.setattr(ops, name, fn)
+  return state
+
+
+@pytest.mark.parametrize('tag', ['cs_strong_nesterov_poly', 'cs_mixed_sgdm_ema', 'cs_odd_size_momentum', 'vistas_mixed_sgdm'])
+def test_training_orchestration_reproduces_the_reference_training_run(monkeypatch, tag):
+  """wlseg/trainer.py + the training half of wlseg/network.py (fp32 check-mode wiring: forward with batch statistics and
+  the tape, loss call, backward through heads, adaptation units, bottleneck units with their shortcut / subsample
+  gradients, pooling, root; BN parameter gradients, optimizer and EMA arenas) on CPU over the emulated calls, against
+  the training runs the reference's own define_estimator executed: every step's losses, then variables, Momentum slots,
+  EMA shadows and moving statistics (tests/test_reference_fixtures.py::compare_train_state, fp32 tolerances)."""
+  from tests import test_reference_fixtures as cpu_side
+  from wlseg import checkpoints, hierarchy, network, problem_defs, trainer as wtrainer
+  train_gold = np.load(cpu_side.TRAIN_GOLD)
+  gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), batches = cpu_side.train_case_batches(train_gold, tag)
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  _emulated_training_ops(monkeypatch, hier, dataset)
+  initial = gen.case_params(tag)
+  params = network.Params(hier, 'cpu')
+  params.load_tf_dict(initial)
+  settings = type('S', (), dict(momentum=opt['momentum'], use_nesterov=opt['use_nesterov'], optimizer=opt['optimizer'],
+                                regularization_weight=opt['regularization_weight'], batch_norm_decay=opt['batch_norm_decay'],
+                                distribute=False, ema_decay=opt['ema_decay']))
+  tr = wtrainer.Trainer(params, settings, dtype=torch.float32, use_graph=False)
+  rows_ = []
+  for i, (images, labels) in enumerate(batches):
+    lr = cpu_side.reference_lr(train_gold, tag, opt, tr.global_step)
+    out = tr.step({'proimages': images}, dict(labels), lr)
+    rows_.append([float(out[0]), float(out[2]), float(out[3]), float(out[4]), float(out[5])])
+  state = checkpoints.export_train_state(params, tr)
+  variables = {k: v for k, v in state.items() if k in initial}
+  momentum = {k: state[checkpoints.momentum_name(k)] for k in initial if checkpoints.momentum_name(k) in state}
+  ema = {k: state[checkpoints.ema_name(k)] for k in initial if checkpoints.ema_name(k) in state}
+  cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum, ema, rows_, first_tol=1e-4,
+                               later_tol=5e-4, cos_min=0.999, norm_tol=1e-2, moving_tol=2e-3)

@@ -433,7 +433,8 @@ def test_evaluate_driver_settings_equal_the_reference_run(tag, tmp_path, monkeyp
 
 # ------------------------------------------------------------------------------------------------ the TRAIN branch
 TRAIN_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_train_run.npz')
-TRAIN_CASES = ['cs_mixed_sgdm_ema', 'cs_strong_nesterov_poly', 'vistas_mixed_sgdm', 'cs_psp_fov_hybrid', 'cs_group_norm']
+TRAIN_CASES = ['cs_mixed_sgdm_ema', 'cs_strong_nesterov_poly', 'vistas_mixed_sgdm', 'cs_psp_fov_hybrid', 'cs_group_norm',
+               'cs_odd_size_momentum']
 
 
 @pytest.fixture(scope='module')
