@@ -34,7 +34,6 @@ def _emulated_ops(monkeypatch):
     return dst
 
   def conv2d_fprop(p, x, w, y, scale=None, shift=None, residual=None, bn_sum=None, bn_sqsum=None):
-    assert bn_sum is None and bn_sqsum is None
     assert tuple(x.shape) == (p.N, p.H, p.W, p.C) and tuple(w.shape) == (p.K, p.R, p.S, p.C) and tuple(y.shape) == (p.N, p.P, p.Q, p.K)
     xn = x.float().permute(0, 3, 1, 2)
     need_h = (p.P - 1) * p.stride + (p.R - 1) * p.dilation + 1
@@ -52,6 +51,10 @@ def _emulated_ops(monkeypatch):
     if p.relu:
       out = torch.relu(out)
     y.copy_(out.to(y.dtype))
+    if bn_sum is not None:        # training mode: per-channel sums of the STORED output (fp64 accumulators)
+      stored = y.reshape(-1, p.K).double()
+      bn_sum[:p.K] += stored.sum(0)
+      bn_sqsum[:p.K] += (stored * stored).sum(0)
     return y
 
   def maxpool_same_fwd(x, y, ksize, stride, argmax=None):
@@ -230,12 +233,53 @@ def _emulated_training_ops(monkeypatch, hier, dataset):
       moving_var.sub_((1.0 - decay) * (moving_var - (var * factor).float()))
 
   def bn_apply(z, scale, shift, residual, y, count, C, relu, mask=None):
-    assert mask is None
     out = z.float() * scale[:C] + shift[:C]
     if residual is not None:
       out = out + residual.float()
     y.copy_((torch.relu(out) if relu else out).to(y.dtype))
+    if mask is not None:          # wlseg_bn_apply_mask: bit (c & 7) of byte [row][c >> 3] = (y > 0)
+      bits = (y.reshape(-1, C) > 0).to(torch.uint8).reshape(-1, C // 8, 8)
+      mask.copy_((bits << torch.arange(8, dtype=torch.uint8)).sum(-1).to(torch.uint8))
     return y
+
+  def unpack_mask(mask, K):
+    return ((mask[..., None] >> torch.arange(8, dtype=torch.uint8)) & 1).reshape(mask.shape[0], K).float()
+
+  plain_fprop = ops.conv2d_fprop       # the inference emulation installed above
+
+  def conv2d_fprop_masked(p, x, w, y, residual, out_mask):
+    tmp = torch.empty(tuple(y.shape), dtype=torch.float32)
+    q = ops.conv_params((p.N, p.H, p.W, p.C), (p.K, p.R, p.S, p.C), stride=p.stride, dilation=p.dilation,
+                        pad=(p.pad_top, p.pad_left), out_hw=(p.P, p.Q), dtype=ops.F32, res=residual, res_stride=p.res_stride)
+    plain_fprop(q, x, w, tmp, None, None, residual)
+    y.copy_((tmp * unpack_mask(out_mask, p.K).reshape(tmp.shape)).to(y.dtype))
+
+  def conv2d_fprop_bnbwd(p, x, w, y, z, scale, shift, mean, invstd, dgamma, dbeta):
+    tmp = torch.empty(tuple(y.shape), dtype=torch.float32)
+    q = ops.conv_params((p.N, p.H, p.W, p.C), (p.K, p.R, p.S, p.C), stride=p.stride, dilation=p.dilation,
+                        pad=(p.pad_top, p.pad_left), out_hw=(p.P, p.Q), dtype=ops.F32)
+    plain_fprop(q, x, w, tmp, None, None, None)
+    live = torch.addcmul(shift[:p.K], z.float(), scale[:p.K]) > 0
+    y.copy_((tmp * live).to(y.dtype))
+    stored = y.float()
+    dbeta += stored.reshape(-1, p.K).double().sum(0)
+    dgamma += (stored * (z.float() - mean[:p.K]) * invstd[:p.K]).reshape(-1, p.K).double().sum(0)
+
+  def weights_transpose_flip(src, dst):
+    # dst[c, r, s, k] = src[k, R-1-r, S-1-s, c]: the bank a stride-1 dgrad runs as an fprop
+    dst.copy_(src.flip(1, 2).permute(3, 1, 2, 0))
+    return dst
+
+  def weights_transpose_flip_batched(src_arena, dst_arena, table):
+    for so, do, K, R, S, C in table.tolist():
+      n = K * R * S * C
+      weights_transpose_flip(src_arena[so:so + n].view(K, R, S, C), dst_arena[do:do + n].view(C, R, S, K))
+    return dst_arena
+
+  def zero_insert(src, dst, stride):
+    dst.zero_()
+    dst[:, ::stride, ::stride, :] = src
+    return dst
 
   def masked_gradient(dy, y, z, scale, shift, relu, C):
     g = dy.float()
@@ -365,7 +409,7 @@ def _emulated_training_ops(monkeypatch, hier, dataset):
       shadow.copy_(biased * inv_correction)
 
   for name, fn in list(locals().items()):
-    if callable(fn) and hasattr(ops, name) and name not in ('rows',):
+    if callable(fn) and hasattr(ops, name) and name not in ('rows', 'plain_fprop'):
       monkeypatch.setattr(ops, name, fn)
   return state
 
@@ -401,3 +445,37 @@ def test_training_orchestration_reproduces_the_reference_training_run(monkeypatc
   ema = {k: state[checkpoints.ema_name(k)] for k in initial if checkpoints.ema_name(k) in state}
   cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum, ema, rows_, first_tol=1e-4,
                                later_tol=5e-4, cos_min=0.999, norm_tol=1e-2, moving_tol=2e-3)
+
+
+@pytest.mark.parametrize('tag', ['cs_strong_nesterov_poly', 'cs_odd_size_momentum'])
+def test_bf16_training_orchestration_reproduces_the_reference_training_run(monkeypatch, tag):
+  """The PRODUCT wiring of the training step (bf16: packed root convolution and its filter gradient in the packed domain,
+  statistics fused into the convolutions, data gradients as convolutions over zero-inserted gradients with the rotated
+  filter banks of the one-launch refresh, ReLU bit masks, BN-backward sums inside the dgrad of the layer above) on CPU
+  over the emulated calls - every tensor rounded to bf16 where the kernels store bf16 - against the fp32 training runs
+  the reference executed, with the bounds of the GPU test (losses 2e-2, update cosine >= 0.90)."""
+  from tests import test_reference_fixtures as cpu_side
+  from wlseg import checkpoints, hierarchy, network, problem_defs, trainer as wtrainer
+  train_gold = np.load(cpu_side.TRAIN_GOLD)
+  gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), batches = cpu_side.train_case_batches(train_gold, tag)
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  _emulated_training_ops(monkeypatch, hier, dataset)
+  initial = gen.case_params(tag)
+  params = network.Params(hier, 'cpu')
+  params.load_tf_dict(initial)
+  settings = type('S', (), dict(momentum=opt['momentum'], use_nesterov=opt['use_nesterov'], optimizer=opt['optimizer'],
+                                regularization_weight=opt['regularization_weight'], batch_norm_decay=opt['batch_norm_decay'],
+                                distribute=False, ema_decay=opt['ema_decay']))
+  tr = wtrainer.Trainer(params, settings, dtype=torch.bfloat16, use_graph=False)
+  assert tr.net._use_premask() and tr.net.bnb_fuse
+  rows_ = []
+  for i, (images, labels) in enumerate(batches):
+    lr = cpu_side.reference_lr(train_gold, tag, opt, tr.global_step)
+    out = tr.step({'proimages': images}, dict(labels), lr)
+    rows_.append([float(out[0]), float(out[2]), float(out[3]), float(out[4]), float(out[5])])
+  assert sum(1 for r in tr.net.tape.values() if getattr(r, 'mask', None) is not None) == 16
+  state = checkpoints.export_train_state(params, tr)
+  variables = {k: v for k, v in state.items() if k in initial}
+  momentum = {k: state[checkpoints.momentum_name(k)] for k in initial if checkpoints.momentum_name(k) in state}
+  cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum, {}, rows_, first_tol=2e-2,
+                               later_tol=2e-2, cos_min=0.90, norm_tol=1.5e-1, moving_tol=2e-2)
