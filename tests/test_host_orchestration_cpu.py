@@ -537,3 +537,92 @@ def test_bf16_training_orchestration_reproduces_the_reference_training_run(monke
   ema = {k: state[checkpoints.ema_name(k)] for k in initial if checkpoints.ema_name(k) in state}
   cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, variables, momentum, ema, rows_, first_tol=2e-2,
                                later_tol=2e-2, cos_min=0.90, norm_tol=1.5e-1, moving_tol=2e-2)
+
+
+# ================================================================================================ evaluation stack
+def _host_only_runtime(monkeypatch):
+  """The CUDA runtime pieces of the estimator loops (copy stream + events of the prefetcher, pinned buffers, device
+  synchronisation) replaced by their host no-ops: batches pass through untouched."""
+  from wlseg import estimator as est
+
+  class PassThrough:
+    def __init__(self, it, device, depth=3, rings=None):
+      self.it, self.h2d_bytes = iter(it), 0
+
+    def __iter__(self):
+      return self
+
+    def __next__(self):
+      return next(self.it)
+  monkeypatch.setattr(est, '_Prefetcher', PassThrough)
+  monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self, *a, **k: self)
+  monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+
+
+def _emulated_eval_tail(monkeypatch, dataset, widths):
+  from oracle import metrics as ometrics
+  from wlseg import ops
+  c1, cv, ch = widths
+
+  def confmat_accumulate(labels, decisions, num_classes, cm, lut=None, invalid=None):
+    decs = decisions if lut is None else lut[decisions.long()]
+    ok = (labels >= 0) & (labels < num_classes) & (decs >= 0) & (decs < num_classes)
+    if invalid is not None:
+      invalid += int((~ok).sum())
+    cm += torch.from_numpy(ometrics.confusion_matrix(labels[ok].numpy(), decs[ok].numpy(), num_classes))
+    return cm
+
+  def head_confmat(hier, logits, H, W, labels, num_classes, cm, lut=None, invalid=None, decisions=None):
+    low = [logits[..., :c1], logits[..., c1:c1 + cv], logits[..., c1 + cv:c1 + cv + ch]]
+    if (H, W) != tuple(logits.shape[1:3]):
+      low = [tfops.resize_bilinear(z, H, W, align_corners=True) for z in low]
+    decs = onet.compose_predictions(*low, dataset)['decisions'].to(torch.int32)
+    if decisions is not None:
+      decisions.copy_(decs)
+    if labels is not None:
+      confmat_accumulate(labels, decs, num_classes, cm, lut, invalid)
+    return cm
+
+  def resize_decisions(decs, H, W):
+    return decs if tuple(decs.shape[1:3]) == (H, W) else tfops.resize_nearest(decs[..., None], H, W, align_corners=True)[..., 0].to(torch.int32)
+  for name, fn in (('confmat_accumulate', confmat_accumulate), ('head_confmat', head_confmat), ('resize_decisions', resize_decisions)):
+    monkeypatch.setattr(ops, name, fn)
+
+
+@pytest.mark.parametrize('tag', ['eval_cs_same_size', 'eval_cs_labels_2x', 'eval_vistas_labels_odd'])
+def test_evaluation_stack_reproduces_the_reference_eval_run(monkeypatch, tmp_path, tag):
+  """evaluate.py's settings -> SemanticSegmentation.evaluate() -> Estimator.evaluate (checkpoint restored under its TF
+  names, cid map, EvalStep / the resize path, streaming confusion matrix, void row and column trimmed) on CPU over the
+  emulated calls, fp32 wiring, against the reference's own EVAL run: the matrix equal entry by entry (the same
+  comparison `test_system_evaluate_equals_the_reference_eval_run` makes on the GPU with the real kernels)."""
+  import importlib
+  from wlseg import checkpoints, hierarchy, problem_defs, settings as wsettings
+  from wlseg.system_factory import SemanticSegmentation
+  gen = importlib.import_module('tests.golden.make_reference_eval_fixtures')
+  gold = np.load(gen.OUT)
+  dataset, nbatches, N, H, W, LH, LW = gen.EVAL_CASES[tag]
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  head = _emulated_ops(monkeypatch)
+  head.widths, head.dataset = hier.head_widths, dataset
+  _emulated_eval_tail(monkeypatch, dataset, hier.head_widths)
+  _host_only_runtime(monkeypatch)
+  ckpt = checkpoints.save_file(os.path.join(str(tmp_path), 'model.ckpt-7.pt'), gen.case_params(dataset), 7)
+  problem_defs.write_all()
+  argv = [str(tmp_path), str(N * nbatches), problem_defs.default_path(dataset), 'unused', dataset, '--Nb', str(N),
+          '--height_feature_extractor', str(H), '--width_feature_extractor', str(W), '--dtype', 'fp32', '--ckpt_path', ckpt]
+  st = wsettings.eval_extra_args(wsettings.build_parser(wsettings.EVAL).parse_args(argv))
+  st.device, st.rank, st.world_size = 'cpu', 0, 1
+
+  def input_fn(config, params):
+    for b in range(nbatches):
+      yield ({'proimages': torch.from_numpy(gold[f'{tag}/batch{b}/images'])},
+             {'prolabels': torch.from_numpy(gold[f'{tag}/batch{b}/prolabels'].astype(np.int32))})
+  import contextlib
+  import io
+  system = SemanticSegmentation({'eval': input_fn}, None, st)
+  with contextlib.redirect_stdout(io.StringIO()):
+    metrics = system.evaluate()
+  ref = gold[f'{tag}/confusion_matrix'].astype(np.int64)
+  assert metrics[0]['global_step'] == 7 and metrics[0]['steps'] == nbatches
+  assert np.array_equal(metrics[0]['confusion_matrix_int64'], ref)
+  assert metrics[0]['confusion_matrix'].dtype == np.int32 and np.array_equal(metrics[0]['confusion_matrix'], ref[:-1, :-1])
