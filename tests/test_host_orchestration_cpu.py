@@ -626,3 +626,49 @@ def test_evaluation_stack_reproduces_the_reference_eval_run(monkeypatch, tmp_pat
   assert metrics[0]['global_step'] == 7 and metrics[0]['steps'] == nbatches
   assert np.array_equal(metrics[0]['confusion_matrix_int64'], ref)
   assert metrics[0]['confusion_matrix'].dtype == np.int32 and np.array_equal(metrics[0]['confusion_matrix'], ref[:-1, :-1])
+
+
+def test_estimator_train_loop_checkpoints_and_resume_on_cpu(monkeypatch, tmp_path):
+  """Estimator.train (the MonitoredTrainingSession loop: learning rate of the pre-increment step from the schedule,
+  periodic + final checkpoints under TF variable names) on the reference's mixed-batch training run, then a second
+  Estimator that continues from log_dir: the state after the run equals the reference's, the checkpoint file holds
+  exactly the exported state, and the resumed trainer starts from the same weights, Momentum slots, EMA shadows and step."""
+  import argparse
+  from tests import test_reference_fixtures as cpu_side
+  from wlseg import checkpoints, estimator as est, hierarchy, problem_defs
+  tag = 'cs_mixed_sgdm_ema'
+  train_gold = np.load(cpu_side.TRAIN_GOLD)
+  gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), batches = cpu_side.train_case_batches(train_gold, tag)
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  _emulated_training_ops(monkeypatch, hier, dataset)
+  _host_only_runtime(monkeypatch)
+  initial = gen.case_params(tag)
+  log_dir = str(tmp_path / 'log')
+  os.makedirs(log_dir)
+
+  def settings():
+    return argparse.Namespace(dtype='fp32', stride_feature_extractor=8, psp_module=False, log_dir=log_dir, rank=0, world_size=1,
+                              distribute=False, save_checkpoints_steps=2, num_training_steps=100, synthetic=True,
+                              **{k: v for k, v in opt.items() if k != 'model'})
+  e = est.Estimator(settings(), hier, device='cpu')
+  e.initialize(log_dir=log_dir, for_training=True)
+  e.params.load_tf_dict(initial)
+  losses = e.train([({'proimages': im}, dict(lab)) for im, lab in batches], max_steps=steps)
+  assert losses.shape == (steps, 6) and e.global_step == steps
+  rows_ = [[r[0], r[2], r[3], r[4], r[5]] for r in losses.tolist()]
+  state = checkpoints.export_train_state(e.params, e.trainer)
+  pick = lambda namer: {k: state[namer(k)] for k in initial if namer(k) in state}      # noqa: E731
+  cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, {k: state[k] for k in initial}, pick(checkpoints.momentum_name),
+                               pick(checkpoints.ema_name), rows_, first_tol=1e-4, later_tol=5e-4, cos_min=0.999, norm_tol=1e-2)
+  # periodic (step 2) and final (step 3) checkpoints; the last one holds exactly the exported state
+  assert sorted(f for f in os.listdir(log_dir) if f.startswith('model.ckpt-')) == ['model.ckpt-2.pt', 'model.ckpt-3.pt']
+  saved, step = checkpoints.load_file(os.path.join(log_dir, 'model.ckpt-3.pt'))
+  assert step == steps and set(saved) == set(state) and all(torch.equal(saved[k], state[k]) for k in state)
+  # continue from log_dir
+  e2 = est.Estimator(settings(), hier, device='cpu')
+  assert e2.initialize(log_dir=log_dir, for_training=True).endswith('model.ckpt-3.pt') and e2.global_step == steps
+  e2.train([], max_steps=0)          # builds the trainer and imports the slots; no step runs
+  again = checkpoints.export_train_state(e2.params, e2.trainer)
+  assert e2.trainer.global_step == steps and set(again) == set(state)
+  for k in state:
+    assert torch.equal(again[k], state[k]), k
