@@ -672,3 +672,65 @@ def test_estimator_train_loop_checkpoints_and_resume_on_cpu(monkeypatch, tmp_pat
   assert e2.trainer.global_step == steps and set(again) == set(state)
   for k in state:
     assert torch.equal(again[k], state[k]), k
+
+
+@pytest.mark.parametrize('tag', ['cs_mixed_sgdm_ema', 'vistas_mixed_sgdm'])
+def test_compact_weak_labels_take_the_same_training_trajectory(monkeypatch, tag):
+  """Weak labels handed over in their COMPACT form - (class, box) lists and 15-way image-level vectors, SURVEY 8f-2 -
+  instead of dense 60 B/pixel tensors: the host logic of network.loss_and_grad (lists straight into the loss call for
+  the 14/7/3 heads; rasterise / tile first for the Vistas heads) on CPU over the emulated calls, against the SAME
+  reference training runs as the dense form."""
+  from oracle import weak_labels as oweak
+  from tests import test_reference_fixtures as cpu_side
+  from wlseg import checkpoints, hierarchy, network, ops, problem_defs, trainer as wtrainer
+  train_gold = np.load(cpu_side.TRAIN_GOLD)
+  gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), _ = cpu_side.train_case_batches(train_gold, tag)
+  hier = hierarchy.Hierarchy(dataset, problem_defs.GENERATORS[dataset]()['cids2labels'])
+  _emulated_training_ops(monkeypatch, hier, dataset)
+  dense_loss = ops.loss_fwd_bwd
+  used = []
+
+  def rasterize_bbox_labels(coords, cids, Hh, Ww, out=None):
+    used.append('rasterize')
+    return torch.stack([torch.from_numpy(oweak.bbox_labels(
+        [(int(c),) + tuple(float(v) for v in xy) for c, xy in zip(ci.tolist(), co.tolist()) if 0 <= c <= 14], Hh, Ww))
+        for co, ci in zip(coords, cids)])
+
+  def tile_image_labels(vec, Hh, Ww, out=None):
+    used.append('tile')
+    return vec[:, None, None, :].expand(vec.shape[0], Hh, Ww, 15).contiguous()
+
+  def loss_fwd_bwd_lists(hstruct, logits, Hh, Ww, strong, box_coords, box_cids, image_vectors, sums, counts, dlogits):
+    used.append('lists')
+    bbox = None if box_coords is None else rasterize_bbox_labels(box_coords, box_cids, Hh, Ww)
+    image = None if image_vectors is None else tile_image_labels(image_vectors, Hh, Ww)
+    dense_loss(hstruct, logits, Hh, Ww, strong, bbox, image, sums, counts, dlogits)
+  for name, fn in (('rasterize_bbox_labels', rasterize_bbox_labels), ('tile_image_labels', tile_image_labels),
+                   ('loss_fwd_bwd_lists', loss_fwd_bwd_lists)):
+    monkeypatch.setattr(ops, name, fn)
+  initial = gen.case_params(tag)
+  params = network.Params(hier, 'cpu')
+  params.load_tf_dict(initial)
+  settings = type('S', (), dict(momentum=opt['momentum'], use_nesterov=opt['use_nesterov'], optimizer=opt['optimizer'],
+                                regularization_weight=opt['regularization_weight'], batch_norm_decay=opt['batch_norm_decay'],
+                                distribute=False, ema_decay=opt['ema_decay']))
+  tr = wtrainer.Trainer(params, settings, dtype=torch.float32, use_graph=False)
+  rows_ = []
+  for i in range(steps):
+    boxes = [(train_gold[f'{tag}/step{i}/bbox{j}_coords'], train_gold[f'{tag}/step{i}/bbox{j}_cids']) for j in range(n_pb)]
+    mb = max(len(c) for _, c in boxes) + 1          # one padding entry per image: cid -1
+    coords = torch.zeros(n_pb, mb, 4)
+    cids = torch.full((n_pb, mb), -1, dtype=torch.int32)
+    for j, (co, ci) in enumerate(boxes):
+      coords[j, :len(ci)] = torch.from_numpy(co)
+      cids[j, :len(ci)] = torch.from_numpy(ci)
+    labels = {'prolabels_per_pixel': torch.from_numpy(train_gold[f'{tag}/step{i}/prolabels_per_pixel'].astype(np.int32)),
+              'bbox_coords': coords, 'bbox_cids': cids, 'image_vectors': torch.from_numpy(train_gold[f'{tag}/step{i}/image_vectors'])}
+    lr = cpu_side.reference_lr(train_gold, tag, opt, tr.global_step)
+    out = tr.step({'proimages': torch.from_numpy(train_gold[f'{tag}/step{i}/images'])}, labels, lr)
+    rows_.append([float(out[0]), float(out[2]), float(out[3]), float(out[4]), float(out[5])])
+  assert set(used) == ({'lists', 'rasterize', 'tile'} if dataset == 'cityscapes' else {'rasterize', 'tile'}), set(used)
+  state = checkpoints.export_train_state(params, tr)
+  pick = lambda namer: {k: state[namer(k)] for k in initial if namer(k) in state}      # noqa: E731
+  cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, {k: state[k] for k in initial}, pick(checkpoints.momentum_name),
+                               pick(checkpoints.ema_name), rows_, first_tol=1e-4, later_tol=5e-4, cos_min=0.999, norm_tol=1e-2)
