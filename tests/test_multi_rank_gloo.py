@@ -104,3 +104,142 @@ def test_get_temp_Nb_splits_the_global_batch():
   with pytest.raises(AssertionError):
     get_temp_Nb(s, 6)
   assert get_temp_Nb(types.SimpleNamespace(distribute=False), 6) == 6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The REAL multi-rank training orchestration (wlseg/trainer.py, wlseg/network.py) on two gloo ranks: the C-ABI calls
+# are the torch restatements of tests/test_host_orchestration_cpu.py, the collectives are torch.distributed's.
+class _Setter:
+  @staticmethod
+  def setattr(obj, name, value):
+    setattr(obj, name, value)
+
+
+def _training_worker(rank, world, port, q):
+  for p in (ROOT, PKG):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  torch.set_num_threads(2)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    from oracle import network as onet
+    from tests import test_host_orchestration_cpu as emu
+    from tests import test_reference_fixtures as cpu_side
+    from wlseg import hierarchy, network, problem_defs, trainer as wtrainer
+    hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+    emu._emulated_training_ops(_Setter, hier, 'cityscapes')
+    out = {}
+
+    # ---- (A) --cross_replica_norm: two ranks with half a batch each == one process with the whole batch
+    g = torch.Generator().manual_seed(11)
+    images = torch.rand(2, 32, 64, 3, generator=g) * 2 - 1
+    dlogits = torch.randn(2, 4, 8, 24, generator=g) * 1e-2
+    tfp = onet.init_params('cityscapes', seed=4, randomize_bn=True, tame=True)
+    for k in tfp:      # a well-conditioned start (tests/golden/make_reference_train_fixtures.py explains): the two summation
+      if k.endswith('/conv3/BatchNorm/gamma'):   # orders of the moments then agree far below the tolerances
+        tfp[k] = tfp[k] * 0.1
+
+    def run(cross_replica, sl):
+      params = network.Params(hier, 'cpu')
+      params.load_tf_dict(tfp)
+      net = network.TrainNetwork(params, dtype=torch.float32, cross_replica=cross_replica)
+      logits = net.forward_train(images[sl])
+      dl = torch.zeros_like(logits)
+      dl[..., :24] = dlogits[sl]
+      net.backward(dl)
+      return params, net, logits
+    params, net, logits = run((world, None), slice(rank, rank + 1))
+    grads = net.ws.grads.clone()
+    dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+    both = [torch.zeros_like(logits) for _ in range(world)]
+    dist.all_gather(both, logits)
+    if rank == 0:
+      n = params.n_chan_pad
+      mov0 = network.Params(hier, 'cpu')
+      mov0.load_tf_dict(tfp)
+      mov0 = mov0.moving.clone()
+      p1, n1, l1 = run(None, slice(0, 2))
+      out['xr_logits'] = max(float((both[r][0, ..., :24] - l1[r, ..., :24]).abs().max()) / float(l1[r, ..., :24].abs().max()) for r in range(2))
+      out['xr_grads'] = float((grads - n1.ws.grads).norm() / n1.ws.grads.norm())
+      out['xr_moving_mean'] = bool(torch.allclose(params.moving[:n], p1.moving[:n], rtol=1e-3, atol=1e-5))
+      # the reference's quirk: GLOBAL biased variance times (n_local - 1) / n_local (cross_replica_batch_normalization.py:452-459)
+      invstd = n1.ws.bn[3 * n:4 * n]
+      var = 1.0 / (invstd * invstd) - 1e-5
+      counts = torch.zeros(n)
+      for s in p1.specs:
+        rec = n1.tape.get(s.scope)
+        if rec is not None:
+          counts[p1.c_off[s.scope]:p1.c_off[s.scope] + rec.nch] = rec.geom[1][0] * rec.geom[1][1]     # per-replica pixels
+      used = counts > 0
+      want = mov0[n:] - 0.1 * (mov0[n:] - var * ((counts - 1.0) / counts.clamp(min=1)))
+      out['xr_moving_var'] = bool(torch.allclose(params.moving[n:][used], want[used], rtol=2e-3, atol=1e-5))
+
+    # ---- (B) data-parallel Trainer.step: MirroredStrategy semantics - the update uses the MEAN of the replicas' gradients
+    tag = 'cs_strong_nesterov_poly'
+    gold = __import__('numpy').load(cpu_side.TRAIN_GOLD)
+    gen, (dataset, n_pp, n_pb, n_pi, H, W, steps, opt), batches = cpu_side.train_case_batches(gold, tag)
+    images, labels = batches[0]
+    mine = ({'proimages': images[rank:rank + 1]}, {'prolabels_per_pixel': labels['prolabels_per_pixel'][rank:rank + 1]})
+    initial = gen.case_params(tag)
+
+    def fresh():
+      p = network.Params(hier, 'cpu')
+      p.load_tf_dict(initial)
+      return p
+    solo = network.TrainNetwork(fresh(), dtype=torch.float32)
+    lg = solo.forward_train(mine[0]['proimages'])
+    _, dlg = solo.loss_and_grad(lg, mine[1], H, W)
+    local = solo.backward(dlg).clone()                   # this replica's own gradient of its own normalised loss
+    every = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(every, local)
+    mean = torch.stack(every).mean(0)
+    settings = type('S', (), dict(momentum=opt['momentum'], use_nesterov=opt['use_nesterov'], optimizer=opt['optimizer'],
+                                  regularization_weight=opt['regularization_weight'], batch_norm_decay=opt['batch_norm_decay'],
+                                  distribute=True, ema_decay=0.0))
+    p = fresh()
+    w0 = p.master.clone()
+    tr = wtrainer.Trainer(p, settings, dtype=torch.float32, rank=rank, world_size=world, use_graph=False, bucket_mb=1)
+    lr = 0.02
+    tr.step(*mine, lr)
+    assert tr.buckets.next == len(tr.buckets.bounds) and len(tr.buckets.bounds) > 20      # many buckets, all launched
+    summed = tr.ws.grads
+    gp = mean.clone()
+    gp[:p.n_conv_pad] += opt['regularization_weight'] * w0[:p.n_conv_pad]
+    want_w = w0 - lr * (gp + opt['momentum'] * gp)       # Nesterov, first step: acc = g'
+    masters = [torch.zeros_like(p.master) for _ in range(world)]
+    dist.all_gather(masters, p.master)
+    if rank == 0:
+      out['dp_grads'] = float((summed / world - mean).norm() / mean.norm())
+      out['dp_weights'] = float((p.master - want_w).norm() / (want_w - w0).norm())
+      out['dp_replicas_equal'] = bool(torch.equal(masters[0], masters[1]))
+    q.put((rank, out))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_training_orchestration_cross_replica_norm_and_data_parallel_step():
+  """Two gloo ranks run the product's own training orchestration over the emulated calls:
+  (A) --cross_replica_norm (utils/cross_replica_batch_normalization.py:398-459): logits of rank r == rows r of ONE
+      process on the concatenated batch, summed gradients == its gradients, moving mean equal, moving variance = global
+      biased variance x (n_local - 1) / n_local - the assertions of tests/test_gpu_cross_replica.py (which needs two
+      GPUs and is skipped on a one-GPU box);
+  (B) the data-parallel step (MirroredStrategy, code/system_factory.py:279-283): the bucketed all-reduce leaves the SUM of
+      the replicas' gradients, the update uses their MEAN (1 / world folded into the optimizer call), replicas stay
+      bit-identical."""
+  world = 2
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = 29500 + ((os.getpid() + 977) % 2000)
+  procs = [ctx.Process(target=_training_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  res = dict(q.get(timeout=600) for _ in range(world))
+  for p in procs:
+    p.join(timeout=120)
+    assert p.exitcode == 0
+  out = res[0]
+  print(out)
+  assert out['xr_logits'] <= 1e-4 and out['xr_grads'] <= 1e-3 and out['xr_moving_mean'] and out['xr_moving_var']
+  assert out['dp_grads'] <= 1e-5 and out['dp_weights'] <= 1e-4 and out['dp_replicas_equal']
