@@ -734,3 +734,65 @@ def test_compact_weak_labels_take_the_same_training_trajectory(monkeypatch, tag)
   pick = lambda namer: {k: state[namer(k)] for k in initial if namer(k) in state}      # noqa: E731
   cpu_side.compare_train_state(train_gold, tag, gen, opt, initial, {k: state[k] for k in initial}, pick(checkpoints.momentum_name),
                                pick(checkpoints.ema_name), rows_, first_tol=1e-4, later_tol=5e-4, cos_min=0.999, norm_tol=1e-2)
+
+
+# ================================================================================================ the facade, end to end
+def _facade_emulation(monkeypatch):
+  """Everything `SemanticSegmentation.train()` / `.evaluate()` launch on the synthetic input side, emulated."""
+  from oracle import weak_labels as oweak
+  from wlseg import hierarchy, ops, problem_defs
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  _emulated_training_ops(monkeypatch, hier, 'cityscapes')
+  _emulated_eval_tail(monkeypatch, 'cityscapes', hier.head_widths)
+  ops.head_fwd.widths, ops.head_fwd.dataset = hier.head_widths, 'cityscapes'
+  _host_only_runtime(monkeypatch)
+
+  def rasterize_bbox_labels(coords, cids, H, W, out=None):
+    return torch.stack([torch.from_numpy(oweak.bbox_labels(
+        [(int(c),) + tuple(float(v) for v in xy) for c, xy in zip(ci.tolist(), co.tolist()) if 0 <= c <= 14], H, W))
+        for co, ci in zip(coords, cids)])
+  monkeypatch.setattr(ops, 'rasterize_bbox_labels', rasterize_bbox_labels)
+  monkeypatch.setattr(ops, 'tile_image_labels', lambda vec, H, W, out=None: vec[:, None, None, :].expand(vec.shape[0], H, W, 15).contiguous())
+
+
+def test_facade_train_then_evaluate_from_its_checkpoint_on_cpu(monkeypatch, tmp_path):
+  """train.py's settings -> SemanticSegmentation.train() on the synthetic generator (strong + bbox + image-level batch)
+  -> the final checkpoint (tf.estimator always writes one when train() ends) -> evaluate.py's settings WITHOUT
+  --synthetic -> SemanticSegmentation.evaluate() must find and restore it; without a checkpoint EVAL raises as
+  tf.estimator does, and --synthetic opts into random weights.  The CPU twin of tests/test_gpu_estimator.py."""
+  import contextlib
+  import io
+  from tests import test_gpu_estimator as twin
+  from wlseg import synthetic
+  from wlseg.system_factory import SemanticSegmentation
+  _facade_emulation(monkeypatch)
+  monkeypatch.setattr(twin, 'H', 32)
+  monkeypatch.setattr(twin, 'W', 48)
+
+  def on_cpu(st):
+    st.device, st.dtype = 'cpu', 'fp32'
+    return st
+  empty = tmp_path / 'empty'
+  empty.mkdir()
+  with contextlib.redirect_stdout(io.StringIO()):
+    ev = SemanticSegmentation({'eval': synthetic.eval_input_fn}, None, on_cpu(twin._eval_settings(empty, synthetic=False)))
+    with pytest.raises(ValueError, match='Could not find trained model'):
+      ev.evaluate()
+    ev = SemanticSegmentation({'eval': synthetic.eval_input_fn}, None, on_cpu(twin._eval_settings(empty, synthetic=True)))
+    assert int(ev.evaluate()[0]['confusion_matrix_int64'].sum()) == 4 * 32 * 48
+    system = SemanticSegmentation({'train': synthetic.train_input_fn}, None, on_cpu(twin._train_settings(tmp_path / 'run')))
+    losses = system.train()
+  assert losses.shape == (3, 6) and np.isfinite(losses).all()
+  run = str(tmp_path / 'run')
+  assert sorted(f for f in os.listdir(run) if f.startswith('model.ckpt')) == ['model.ckpt-3.pt']
+  assert os.path.isfile(os.path.join(run, 'settings.txt'))
+  trained, moving = system.estimator.params.master.clone(), system.estimator.params.moving.clone()
+  with contextlib.redirect_stdout(io.StringIO()):
+    ev = SemanticSegmentation({'eval': synthetic.eval_input_fn}, None, on_cpu(twin._eval_settings(tmp_path / 'run', synthetic=False)))
+    metrics = ev.evaluate()
+  assert metrics[0]['global_step'] == 3
+  assert torch.equal(ev.estimator.params.master, trained) and torch.equal(ev.estimator.params.moving, moving)
+  assert metrics[0]['confusion_matrix'].shape == (19, 19) and int(metrics[0]['confusion_matrix_int64'].sum()) == 4 * 32 * 48
+  # a second training run into the same log directory is refused (settings.txt exists), as upstream
+  with pytest.raises(AssertionError, match='Previous settings.txt'):
+    SemanticSegmentation({'train': synthetic.train_input_fn}, None, on_cpu(twin._train_settings(tmp_path / 'run'))).train()
