@@ -796,3 +796,55 @@ def test_facade_train_then_evaluate_from_its_checkpoint_on_cpu(monkeypatch, tmp_
   # a second training run into the same log directory is refused (settings.txt exists), as upstream
   with pytest.raises(AssertionError, match='Previous settings.txt'):
     SemanticSegmentation({'train': synthetic.train_input_fn}, None, on_cpu(twin._train_settings(tmp_path / 'run'))).train()
+
+
+def test_predict_script_on_real_image_files_on_cpu(monkeypatch, tmp_path):
+  """predict.py end to end on a directory of image files: wlseg.cli.predict_main -> settings -> SemanticSegmentation
+  .predict() -> wlseg.image_input (file discovery, RGB conversion, legacy resize, [-1, 1)) -> Estimator.predict
+  (network at the feature-extractor size, predictions carried back to each RAW image's size) -> the PNG exports.
+  Every exported label-id / colour image equals what the oracle predicts for that file, pixel for pixel."""
+  import contextlib
+  import importlib
+  import io
+  from PIL import Image
+  from wlseg import checkpoints, cli, hierarchy, image_input, ops, problem_defs
+  gen = importlib.import_module('tests.golden.make_reference_predict_input_fixtures')
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  head = _emulated_ops(monkeypatch)
+  head.widths, head.dataset = hier.head_widths, 'cityscapes'
+  _host_only_runtime(monkeypatch)
+  monkeypatch.setattr(ops, 'resize_probabilities',
+                      lambda probs, H, W: probs if tuple(probs.shape[1:3]) == (H, W) else tfops.resize_bilinear(probs, H, W, align_corners=True))
+  monkeypatch.setattr(ops, 'resize_decisions',
+                      lambda d, H, W: d if tuple(d.shape[1:3]) == (H, W) else tfops.resize_nearest(d[..., None], H, W, align_corners=True)[..., 0].to(torch.int32))
+
+  def on_cpu(st):
+    st.rank, st.world_size, st.device = 0, 1, 'cpu'
+    return st
+  monkeypatch.setattr(cli, '_dist_env', on_cpu)
+  images, results, log_dir = str(tmp_path / 'images'), str(tmp_path / 'results'), str(tmp_path / 'log')
+  for d in (images, results, log_dir):
+    os.makedirs(d)
+  gen.write_images(images)
+  tfp = onet.init_params('cityscapes', seed=5, randomize_bn=True, tame=True)
+  ckpt = checkpoints.save_file(os.path.join(log_dir, 'model.ckpt-9.pt'), tfp, 9)
+  problem_defs.write_all()
+  hf, wf = 24, 40
+  with contextlib.redirect_stdout(io.StringIO()):
+    cli.predict_main([log_dir, problem_defs.default_path('cityscapes'), images, 'cityscapes', '--ckpt_path', ckpt, '--dtype', 'fp32',
+                      '--height_feature_extractor', str(hf), '--width_feature_extractor', str(wf), '--results_dir', results,
+                      '--export_lids_images', '--export_color_decisions'])
+  pd = problem_defs.cityscapes()
+  lids, colors = np.array(pd['cids2lids'], dtype=np.uint8), np.array(pd['cids2colors'], dtype=np.uint8)
+  files = image_input.list_images(images)
+  assert len(files) == 6 and len(os.listdir(results)) == 12
+  net = onet.Net(tfp, 'cityscapes')
+  for f in files:
+    raw = np.asarray(Image.open(f).convert('RGB'), dtype=np.uint8)
+    pro = (image_input.resize_bilinear_legacy(torch.from_numpy(raw.copy()).float() * torch.tensor(1.0 / 255.0), hf, wf) - 0.5) / 0.5
+    with torch.no_grad():
+      decs = net.forward(pro[None])['decisions']
+    decs = tfops.resize_nearest(decs[..., None], raw.shape[0], raw.shape[1], align_corners=True)[0, ..., 0].numpy()
+    stem = os.path.splitext(os.path.basename(f))[0]
+    assert np.array_equal(np.asarray(Image.open(os.path.join(results, stem + '_result_lids.png'))), lids[decs]), f
+    assert np.array_equal(np.asarray(Image.open(os.path.join(results, stem + '_result_color.png'))), colors[decs]), f
