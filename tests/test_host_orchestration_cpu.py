@@ -848,3 +848,14 @@ def test_predict_script_on_real_image_files_on_cpu(monkeypatch, tmp_path):
     stem = os.path.splitext(os.path.basename(f))[0]
     assert np.array_equal(np.asarray(Image.open(os.path.join(results, stem + '_result_lids.png'))), lids[decs]), f
     assert np.array_equal(np.asarray(Image.open(os.path.join(results, stem + '_result_color.png'))), colors[decs]), f
+
+
+def test_smoke_training_step_runs_over_the_emulation(monkeypatch):
+  """__graft_entry__.smoke()'s training half (one bf16 optimizer step on the first batch of the reference's training run,
+  losses checked against the reference's) executed on CPU over the emulated calls: the entry point's own code path."""
+  import __graft_entry__ as entry
+  from wlseg import hierarchy, problem_defs
+  hier = hierarchy.Hierarchy('cityscapes', problem_defs.cityscapes()['cids2labels'])
+  _emulated_training_ops(monkeypatch, hier, 'cityscapes')
+  monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+  assert entry._smoke_train_step(torch.device('cpu')) <= 2e-2
